@@ -1,0 +1,64 @@
+"""Stub-loader for the reference's numba kernels (TEST INFRASTRUCTURE ONLY).
+
+Loads ``wflow/wflow_funcs.py`` and ``wflow/wflow_sbm.py`` from the read-only
+reference checkout *by file path*, with empty stand-ins for the modules the
+reference imports but this container does not have (pcraster, osgeo, pyproj …;
+SURVEY.md §8c / Appendix D).  Nothing is copied; the reference files are executed
+where they lie.  Only usable where ``/root/reference`` exists (this container) —
+never on the GPU box, and never from the product path.
+
+Used by ``oracle/gen_golden.py`` (to write tests/golden/*.npz) and by
+``tests/test_oracle_vs_reference.py`` (skipped when the reference is absent).
+"""
+import importlib.util
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("WFLOW_REFERENCE_ROOT", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "wflow", "wflow_sbm.py"))
+
+
+_cache = {}
+
+
+def load():
+    """Return (wflow_funcs, wflow_sbm) reference modules."""
+    if "mods" in _cache:
+        return _cache["mods"]
+    if not available():
+        raise RuntimeError("reference checkout not present at %s" % REFERENCE_ROOT)
+    sys.dont_write_bytecode = True  # reference mount is read-only
+
+    def _stub(name, **kw):
+        m = types.ModuleType(name)
+        m.__dict__.update(kw)
+        sys.modules[name] = m
+        return m
+
+    if "pcraster" not in sys.modules:
+        pcr = _stub("pcraster")
+        fw = _stub(
+            "pcraster.framework",
+            DynamicModel=type("DynamicModel", (), {"__init__": lambda s: None}),
+        )
+        pcr.framework = fw
+    if "wflow" not in sys.modules:
+        _stub("wflow").__path__ = []
+        _stub("wflow.wf_DynamicFramework")
+        _stub("wflow.wflow_adapt")
+
+    def _load(name, path):
+        spec = importlib.util.spec_from_file_location(name, path)
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[name] = m
+        spec.loader.exec_module(m)
+        return m
+
+    funcs = _load("wflow.wflow_funcs", os.path.join(REFERENCE_ROOT, "wflow", "wflow_funcs.py"))
+    sbm = _load("wflow.wflow_sbm", os.path.join(REFERENCE_ROOT, "wflow", "wflow_sbm.py"))
+    _cache["mods"] = (funcs, sbm)
+    return funcs, sbm

@@ -1,0 +1,239 @@
+"""Synthetic wflow_sbm cases: drainage networks,
+parameter maps in the value ranges of ``examples/wflow_rhine_sbm/intbl``, forcing.
+
+Host-side, numpy.  Deterministic for a given seed.
+"""
+import numpy as np
+
+from . import params
+
+F32 = np.float32
+
+# PCRaster LDD codes: 7 8 9 / 4 5 6 / 1 2 3, pit = 5  (wflow/wflow_funcs.py:43)
+LDD_DR = {7: -1, 8: -1, 9: -1, 4: 0, 5: 0, 6: 0, 1: 1, 2: 1, 3: 1}
+LDD_DC = {7: -1, 8: 0, 9: 1, 4: -1, 5: 0, 6: 1, 1: -1, 2: 0, 3: 1}
+_CODE = np.array([[7, 8, 9], [4, 5, 6], [1, 2, 3]], dtype=np.uint8)
+
+
+def _hash32(seed, r, c):
+    """Cheap integer hash (uint32) of (seed, row, col), vectorised."""
+    h = (r.astype(np.uint64) * np.uint64(0x9E3779B1) + c.astype(np.uint64) * np.uint64(0x85EBCA77)
+         + np.uint64(seed) * np.uint64(0xC2B2AE3D)) & np.uint64(0xFFFFFFFF)
+    h ^= h >> np.uint64(15)
+    h = (h * np.uint64(0x2C1B3C6D)) & np.uint64(0xFFFFFFFF)
+    h ^= h >> np.uint64(12)
+    h = (h * np.uint64(0x297A2D39)) & np.uint64(0xFFFFFFFF)
+    h ^= h >> np.uint64(15)
+    return h
+
+
+def ldd_all_pits(nrow, ncol):
+    """Config 2: every cell is a pit (one level, no lateral connection)."""
+    return np.full((nrow, ncol), 5, np.uint8)
+
+
+def ldd_basin_tiles(nrow, ncol, tile=1024, seed=7, mask_frac=0.0):
+    """Config 3/5: independent tile-sized basins, each a random D8 tree.
+
+    Outlet (pit) at the bottom-centre of each tile; every other cell drains to one of
+    its in-tile neighbours that is strictly closer (Chebyshev) to the outlet, chosen by
+    hash(seed,row,col).  Acyclic, <= tile-1 levels, hop distance = Chebyshev distance.
+    ``mask_frac`` > 0 removes (sets to 0 = missing) a hashed fraction of *leaf-side*
+    cells: a masked cell takes its whole upstream subtree with it is avoided by only
+    masking cells on the tile's outer ring.
+    """
+    rr, cc = np.meshgrid(np.arange(nrow, dtype=np.int64), np.arange(ncol, dtype=np.int64), indexing="ij")
+    tr, tc = rr % tile, cc % tile
+    th = np.minimum(tile, nrow - (rr - tr))  # actual tile height/width at grid edges
+    tw = np.minimum(tile, ncol - (cc - tc))
+    ro, co = th - 1, tw // 2
+    d = np.maximum(np.abs(tr - ro), np.abs(tc - co))
+    h = _hash32(seed, rr, cc)
+    ncand = np.zeros((nrow, ncol), np.int64)
+    cand_ok = []
+    for dr in (-1, 0, 1):
+        for dc in (-1, 0, 1):
+            if dr == 0 and dc == 0:
+                continue
+            r2, c2 = tr + dr, tc + dc
+            ok = (r2 >= 0) & (r2 < th) & (c2 >= 0) & (c2 < tw)
+            d2 = np.maximum(np.abs(r2 - ro), np.abs(c2 - co))
+            ok &= d2 == d - 1
+            cand_ok.append((dr, dc, ok))
+            ncand += ok
+    pick = (h % np.maximum(ncand, 1).astype(np.uint64)).astype(np.int64)
+    ldd = np.full((nrow, ncol), 5, np.uint8)
+    seen = np.zeros((nrow, ncol), np.int64)
+    for dr, dc, ok in cand_ok:
+        sel = ok & (seen == pick) & (d > 0)
+        ldd[sel] = _CODE[dr + 1, dc + 1]
+        seen += ok
+    if mask_frac > 0:
+        ring = (tr == 0) | (tc == 0) | (tc == tw - 1)
+        ring &= d > 0
+        hm = _hash32(seed + 101, rr, cc)
+        ldd[ring & ((hm % np.uint64(10000)) < np.uint64(int(mask_frac * 10000)))] = 0
+    return ldd
+
+
+def ldd_random_forest(nrow, ncol, seed=0, pit_frac=0.02, missing_frac=0.05):
+    """Small irregular test networks: cells drain to a random neighbour with a lower
+    random 'elevation' (pit if none); some cells missing."""
+    rng = np.random.default_rng(seed)
+    z = rng.random((nrow, ncol))
+    ldd = np.zeros((nrow, ncol), np.uint8)
+    for r in range(nrow):
+        for c in range(ncol):
+            best, code = z[r, c], 5
+            order = [(dr, dc) for dr in (-1, 0, 1) for dc in (-1, 0, 1) if (dr, dc) != (0, 0)]
+            rng.shuffle(order)
+            for dr, dc in order:
+                r2, c2 = r + dr, c + dc
+                if 0 <= r2 < nrow and 0 <= c2 < ncol and z[r2, c2] < best:
+                    best, code = z[r2, c2], _CODE[dr + 1, dc + 1]
+                    if rng.random() < 0.5:
+                        break
+            if rng.random() < pit_frac:
+                code = 5
+            ldd[r, c] = code
+    miss = rng.random((nrow, ncol)) < missing_frac
+    ldd[miss] = 0
+    # cells pointing at a missing cell or out of the map become pits (lddrepair)
+    for r in range(nrow):
+        for c in range(ncol):
+            k = ldd[r, c]
+            if k in (0, 5):
+                continue
+            r2, c2 = r + LDD_DR[int(k)], c + LDD_DC[int(k)]
+            if not (0 <= r2 < nrow and 0 <= c2 < ncol) or ldd[r2, c2] == 0:
+                ldd[r, c] = 5
+    return ldd
+
+
+def upstream_count(ldd):
+    """Number of cells draining through each cell (incl. itself) = catchmenttotal(1, ldd).
+    Vectorised Kahn sweep; only for moderate grids (tests, synthetic river definition)."""
+    nrow, ncol = ldd.shape
+    n = nrow * ncol
+    flat = ldd.ravel()
+    valid = (flat >= 1) & (flat <= 9)
+    dr = np.zeros(10, np.int64)
+    dc = np.zeros(10, np.int64)
+    for k in range(1, 10):
+        dr[k], dc[k] = LDD_DR[k], LDD_DC[k]
+    idx = np.arange(n, dtype=np.int64)
+    down = idx + dr[flat * valid] * ncol + dc[flat * valid]
+    down[~valid | (flat == 5)] = -1
+    indeg = np.zeros(n, np.int64)
+    np.add.at(indeg, down[down >= 0], 1)
+    acc = valid.astype(np.int64)
+    frontier = idx[valid & (indeg == 0)]
+    while frontier.size:
+        d = down[frontier]
+        ok = d >= 0
+        np.add.at(acc, d[ok], acc[frontier[ok]])
+        np.subtract.at(indeg, d[ok], 1)
+        cand = np.unique(d[ok])
+        frontier = cand[indeg[cand] == 0]
+    return acc.reshape(nrow, ncol)
+
+
+def _smooth_noise(rng, nrow, ncol, coarse=64):
+    """Bilinear interpolation of coarse white noise (spatially smooth field in [0,1))."""
+    gr, gc = max(2, nrow // coarse + 2), max(2, ncol // coarse + 2)
+    g = rng.random((gr, gc)).astype(F32)
+    y = np.linspace(0, gr - 1.001, nrow, dtype=F32)
+    x = np.linspace(0, gc - 1.001, ncol, dtype=F32)
+    y0, x0 = y.astype(np.int64), x.astype(np.int64)
+    fy, fx = (y - y0)[:, None], (x - x0)[None, :]
+    a = g[y0][:, x0]
+    b = g[y0][:, x0 + 1]
+    c = g[y0 + 1][:, x0]
+    d = g[y0 + 1][:, x0 + 1]
+    return ((a * (1 - fx) + b * fx) * (1 - fy) + (c * (1 - fx) + d * fx) * fy).astype(F32)
+
+
+def base_parameters(nrow, ncol, seed=42, block=64, n_layers=4):
+    """Per-class parameter values (land use 1..6, soil 1..14 per ``block``² cells) drawn
+    from the ranges of examples/wflow_rhine_sbm/intbl/*.tbl."""
+    rng = np.random.default_rng(seed)
+    br, bc = (nrow + block - 1) // block, (ncol + block - 1) // block
+    lu = np.kron(rng.integers(0, 6, (br, bc)), np.ones((block, block), np.int64))[:nrow, :ncol]
+    so = np.kron(rng.integers(0, 14, (br, bc)), np.ones((block, block), np.int64))[:nrow, :ncol]
+
+    def by_lu(lo, hi, log=False):
+        v = np.exp(rng.uniform(np.log(lo), np.log(hi), 6)) if log else rng.uniform(lo, hi, 6)
+        return v.astype(F32)[lu]
+
+    def by_soil(lo, hi, log=False):
+        v = np.exp(rng.uniform(np.log(lo), np.log(hi), 14)) if log else rng.uniform(lo, hi, 14)
+        return v.astype(F32)[so]
+
+    base = {
+        "KsatVer": by_soil(100, 8000, True), "M": by_soil(17, 12880, True), "thetaS": by_soil(0.4, 0.6),
+        "thetaR": by_soil(0.01, 0.1), "SoilThickness": by_soil(400, 7100), "RootingDepth": by_lu(2, 750),
+        "CanopyGapFraction": by_lu(0.1, 0.8), "Cmax": by_lu(0.0, 1.0), "EoverR": by_lu(0.0, 0.25),
+        "PathFrac": by_lu(0.01, 0.9), "InfiltCapSoil": by_soil(100, 600), "InfiltCapPath": by_soil(5, 10),
+        "TT": by_lu(-1.42, 0.0), "TTM": by_lu(-1.42, 0.0), "TTI": F32(1.0), "Cfmax": F32(3.76), "WHC": F32(0.1),
+        "CapScale": F32(100.0), "rootdistpar": F32(-8000.0), "MaxLeakage": by_soil(0.0, 0.5),
+        "KsatHorFrac": by_soil(1.0, 100.0, True), "N": by_lu(0.03, 0.6, True), "N_River": F32(0.036),
+        "WaterFrac": (by_lu(0.0, 0.05) * (rng.random(6) < 0.5).astype(F32)[lu]).astype(F32),
+    }
+    Cm = base["Cmax"]
+    Cm[lu == 0] = 0.0  # one open class without canopy (Cmax <= 0 branch of Gash)
+    for k in range(n_layers):
+        base["c_%d" % k] = by_soil(8.0, 12.0)
+        base["KsatVerFrac_%d" % k] = by_soil(0.5, 1.5)
+    slope = np.exp(np.log(1e-3) + _smooth_noise(rng, nrow, ncol) * (np.log(0.3) - np.log(1e-3))).astype(F32)
+    base["landSlope"] = slope
+    base["riverSlope"] = np.maximum(slope * F32(0.3), F32(1e-4)).astype(F32)
+    base["elev"] = (_smooth_noise(rng, nrow, ncol, 128) * F32(2000.0)).astype(F32)
+    base["TempCor"] = (F32(-0.0065) * base["elev"]).astype(F32)
+    return base
+
+
+class Forcing:
+    """Per-step P / PET / TEMP rasters (SURVEY.md §8d config 2 definition)."""
+
+    def __init__(self, nrow, ncol, seed=42, timestepsecs=86400):
+        self.rng = np.random.default_rng(seed + 1)
+        self.shape = (nrow, ncol)
+        self.scale = F32(timestepsecs / 86400.0)
+        self.pattern = _smooth_noise(self.rng, nrow, ncol, 96)
+
+    def step(self, t):
+        rng = np.random.default_rng(1000003 * (t + 1) + 17)
+        wet = rng.random() > 0.6 or True
+        field = _smooth_noise(rng, *self.shape, coarse=128)
+        dry = field < F32(0.6)  # 60 % dry
+        p = (-np.log1p(-np.minimum(field, F32(0.999))) * F32(6.0)).astype(F32)
+        p[dry] = 0.0
+        p = (p * self.scale).astype(F32)
+        pet = np.full(self.shape, (2.0 + 1.5 * np.sin(2 * np.pi * t / 365.0)), F32) * self.scale
+        temp = np.full(self.shape, 8.0 + 12.0 * np.sin(2 * np.pi * (t - 100) / 365.0), F32) + (self.pattern - F32(0.5)) * F32(4.0)
+        del wet
+        return p.astype(F32), pet.astype(F32), temp.astype(F32)
+
+
+def make_case(nrow, ncol, *, kind="pits", tile=1024, seed=42, timestepsecs=86400, layer_thickness=(100, 300, 800),
+              river_area=500, mask_frac=0.0):
+    """Assemble (ldd, river, static, state) for a synthetic case."""
+    if kind == "pits":
+        ldd = ldd_all_pits(nrow, ncol)
+        river = np.zeros((nrow, ncol), np.uint8)
+    elif kind == "tiles":
+        ldd = ldd_basin_tiles(nrow, ncol, tile=tile, seed=7, mask_frac=mask_frac)
+        river = (upstream_count(ldd) >= river_area).astype(np.uint8)
+    elif kind == "forest":
+        ldd = ldd_random_forest(nrow, ncol, seed=seed)
+        river = (upstream_count(ldd) >= river_area).astype(np.uint8)
+    else:
+        raise ValueError(kind)
+    n_layers = len(layer_thickness) + 1 if len(layer_thickness) else 1
+    base = base_parameters(nrow, ncol, seed=seed, n_layers=n_layers)
+    up = upstream_count(ldd).astype(F32)
+    base["RiverWidth"] = np.where(river != 0, F32(2.0) * np.power(np.maximum(up, 1), F32(0.35)), F32(0.0)).astype(F32)
+    base["BankfullDepth"] = np.where(river != 0, F32(1.0), F32(0.0)).astype(F32)
+    static = params.derive_static(base, ldd, river, timestepsecs, cellsize=1000.0, n_layers=n_layers)
+    state = params.cold_state(static, n_layers)
+    return ldd, river, static, state
