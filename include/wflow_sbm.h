@@ -1,0 +1,153 @@
+/*
+ * wflow_sbm.h -- C-ABI of libwflowsbm.so: the B200-native per-timestep hot path of
+ * wflow_sbm (SBM vertical column + LDD-ordered kinematic wave for subsurface, overland
+ * and river flow + gauge/area accumulation).
+ *
+ * Plain C: opaque handle, raw pointers and sizes, int status codes.  No torch types.
+ * Every entry point cites the reference interface it replaces (paths relative to the
+ * openstreams/wflow checkout).  INTEGRATION.md shows the ctypes stub a maintainer of the
+ * reference would add to WflowModel to call these instead of sbm_cell()/kin_wave().
+ *
+ * Conventions
+ *   * Rasters are float32, row-major, north-up, nrow*ncol, exactly what
+ *     pcr.pcr2numpy(map, mv) hands to the reference's numba kernels
+ *     (wflow/wflow_sbm.py:2885-2909).  Cells outside the drainage network are ignored
+ *     on input and receive `mv` on output.
+ *   * Field names are the reference's attribute names, list-valued
+ *     ones as Name_<k> like the reference's state files (wf_DynamicFramework.py:1780-1827).
+ *   * All functions return 0 on success, a negative WF_E* code otherwise;
+ *     wf_last_error() returns a message for the calling thread's last failure.
+ *   * A handle is bound to one CUDA device and is not thread-safe.  There is no CPU
+ *     fallback: wf_create fails with WF_ENODEVICE when no sm_100 GPU is usable.
+ */
+#ifndef WFLOW_SBM_H
+#define WFLOW_SBM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WF_MAX_LAYERS 8
+
+enum {
+  WF_OK = 0,
+  WF_EINVAL = -1,    /* bad argument / unknown field name */
+  WF_ENODEVICE = -2, /* no usable CUDA device, or a CUDA call failed */
+  WF_ENOMEM = -3,
+  WF_ECYCLE = -4,    /* the LDD contains a cycle */
+  WF_EUNSUPPORTED = -5
+};
+
+/* Model options: the [model]/[run] ini settings that reach the hot path
+ * (wflow/wflow_sbm.py:1233-1339, 1757-1766). */
+typedef struct wf_config {
+  int32_t nrow, ncol;
+  int32_t n_layer_thickness;                 /* entries of [model] UStoreLayerThickness (0 = unset -> one layer) */
+  double layer_thickness[WF_MAX_LAYERS];     /* mm */
+  int32_t model_snow;                        /* [model] ModelSnow */
+  int32_t soil_inf_redu;                     /* [model] soilInfRedu */
+  int32_t transfer_method;                   /* [model] transfermethod */
+  int32_t ust;                               /* [model] Whole_UST_Avail */
+  int32_t glacier;                           /* GlacierFrac parameter configured */
+  int32_t it_kin_l;                          /* overland sub-steps  (wflow_sbm.py:2911-2923) */
+  int32_t it_kin_r;                          /* river sub-steps     (wflow_sbm.py:3159-3171) */
+  int32_t device;                            /* CUDA device ordinal */
+  double timestepsecs;                       /* [run] timestepsecs */
+  double beta;                               /* kinematic-wave exponent; the reference fixes 0.6 as REAL4 (wflow_sbm.py:1643); 0 = that default */
+} wf_config;
+
+typedef struct wf_model wf_model;
+
+const char *wf_last_error(void);
+const char *wf_version(void);
+
+/* --- network ------------------------------------------------------------------------
+ * Replaces set_dd(ldd) (wflow/wflow_funcs.py:70-95), called for the full LDD and for the
+ * river-only LDD (wflow/wflow_sbm.py:2385-2389), and owns the level schedule.
+ * ldd: PCRaster codes 1..9 (5 = pit), anything else = missing.  river: non-zero = river. */
+int wf_create(const wf_config *cfg, const uint8_t *ldd, const uint8_t *river, wf_model **out);
+void wf_destroy(wf_model *m);
+
+/* Host-only schedule construction (no GPU needed): the same builder wf_create uses. */
+typedef struct wf_schedule wf_schedule;
+int wf_schedule_create(const uint8_t *ldd, int nrow, int ncol, wf_schedule **out);
+void wf_schedule_destroy(wf_schedule *s);
+int64_t wf_schedule_num_cells(const wf_schedule *s);
+int64_t wf_schedule_num_levels(const wf_schedule *s);
+/* nodes / nodes_up / lev_off as in wf_get_network. */
+int wf_schedule_get(const wf_schedule *s, int64_t *nodes, int64_t *nodes_up, int64_t *lev_off);
+
+int64_t wf_num_cells(const wf_model *m);        /* cells in the drainage network */
+int64_t wf_num_levels(const wf_model *m);
+int64_t wf_num_river_cells(const wf_model *m);  /* cells of the river network (rnodes) */
+int64_t wf_num_river_levels(const wf_model *m);
+/* The schedule in the reference's own form, for bit-exact comparison with set_dd:
+ * nodes[ncells] (flat grid indices, level-major, level 0 = farthest from its pit),
+ * nodes_up[ncells*8] (-1 padded, neighbour order NW,N,NE,W,E,SW,S,SE), lev_off[nlevels+1].
+ * which = 0: full network, 1: river network.  Any output pointer may be NULL. */
+int wf_get_network(const wf_model *m, int which, int64_t *nodes, int64_t *nodes_up, int64_t *lev_off);
+/* catchmenttotal(values, ldd) on the model's network (PCRaster op used by initial(),
+ * wflow/wflow_sbm.py:2070-2073, 3468): out = values accumulated over the upstream area.
+ * values == NULL accumulates 1 per cell. */
+int wf_catchment_total(const wf_model *m, const float *values, double *out_grid);
+
+/* --- fields -------------------------------------------------------------------------
+ * Replace the pcr2numpy / numpy2pcr copies around the kernels (wflow/wflow_sbm.py:2885-2909,
+ * 2944-3129, 3190-3201) and wf_supplyMapAsNumpy / wf_setValuesAsNumpy
+ * (wflow/wf_DynamicFramework.py:2582, 2203) at the raster level. */
+int wf_set_field(wf_model *m, const char *name, const float *grid);        /* host raster -> device */
+int wf_set_field_uniform(wf_model *m, const char *name, float value);
+int wf_get_field(wf_model *m, const char *name, float *grid, float mv);    /* device -> host raster */
+/* Enable (1) / disable (0) a diagnostic output so that the kernels materialise it. */
+int wf_request_output(wf_model *m, const char *name, int enable);
+/* Number of known field names and the i-th name / kind (0 forcing, 1 static, 2 state, 3 diagnostic). */
+int wf_num_fields(void);
+const char *wf_field_name(int i);
+int wf_field_kind(int i);
+/* Device-resident access (for callers that already hold data on the GPU): pointer to the
+ * field's device array in network order (see wf_cell_order) and its length.
+ * River-only fields (kind has bit 8 set) are in river-network order. */
+int wf_field_device_ptr(wf_model *m, const char *name, void **dptr, int64_t *n);
+int wf_cell_order(const wf_model *m, int64_t *flat_index /* [wf_num_cells] */);
+/* Same as wf_set_field, but `grid` is a DEVICE pointer to an nrow*ncol raster. */
+int wf_set_field_from_device(wf_model *m, const char *name, const float *dgrid);
+
+/* --- stepping -----------------------------------------------------------------------
+ * Replaces one pass of WflowModel.dynamic() (wflow/wflow_sbm.py:2518-3528): the PCRaster
+ * phases (interception, snow, evaporation split), sbm_cell() (:332-900) and kin_wave()
+ * (wflow/wflow_funcs.py:155-207), with states re-quantised to float32 at the step boundary
+ * like the reference's numpy2pcr copies.  nsteps > 1 repeats with the same forcing. */
+int wf_step(wf_model *m, int nsteps);
+int wf_synchronize(wf_model *m);
+/* Device time of the kernels of the last wf_step call, milliseconds (CUDA events on the
+ * model's stream): [0] vertical column, [1] lateral sweep, [2] whole step. */
+int wf_last_step_ms(wf_model *m, float ms[3]);
+/* Number of kernel launches issued by the model since creation. */
+int64_t wf_launch_count(const wf_model *m);
+/* The CUDA stream (cudaStream_t) the model launches on. */
+void *wf_stream(wf_model *m);
+
+/* --- gauge / area accumulation --------------------------------------------------------
+ * Replaces wf_OutputTimeSeriesArea.writestep (wflow/wf_DynamicFramework.py:404-499):
+ * areaaverage / areatotal / areamaximum / areaminimum of a field over an id map, one
+ * value per unique id > 0 (ascending).  Returns an area-set handle >= 0. */
+enum { WF_AREA_AVERAGE = 0, WF_AREA_TOTAL = 1, WF_AREA_MAXIMUM = 2, WF_AREA_MINIMUM = 3 };
+int wf_area_create(wf_model *m, const int32_t *idmap /* nrow*ncol, <=0 = none */);
+int wf_area_num_ids(wf_model *m, int area);
+int wf_area_ids(wf_model *m, int area, int32_t *ids);
+int wf_area_reduce(wf_model *m, int area, const char *field, int op, float *out /* [num_ids] */);
+/* Sample a field at cells (gauges): out[i] = field[flat_index[i]] (mv outside the network). */
+int wf_sample(wf_model *m, const char *field, const int64_t *flat_index, int64_t n, float *out, float mv);
+
+/* --- one-step rollback ------------------------------------------------------------------
+ * Replaces wf_QuickSuspend / wf_QuickResume (wflow/wf_DynamicFramework.py:2131-2175), used by
+ * BMI update_until() to step back once: a device-side snapshot of all states. */
+int wf_quick_suspend(wf_model *m);
+int wf_quick_resume(wf_model *m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WFLOW_SBM_H */

@@ -1,0 +1,66 @@
+"""Shared helpers of the parity tests: build the same synthetic case for the CPU oracle and
+for the CUDA model, step both, compare."""
+import numpy as np
+
+from wflow_b200 import synth
+
+DIAGS = ["SatWaterDepth", "UStoreDepth", "CapFlux", "Transfer", "ActEvapUStore", "ActEvapSat", "soilevap",
+         "soilevapsat", "ActEvap", "Recharge", "InwaterMM", "qo_toriver", "ssf_toriver", "ExfiltWater",
+         "InfiltExcess", "ExcessWater", "ActInfilt", "ActLeakage", "SoilInf", "PathInf", "InfiltExcessSoil",
+         "InfiltExcessPath", "ActInfiltSoil", "ActInfiltPath", "ExfiltFromUstore", "ExfiltFromSat", "InwaterL",
+         "InflowKinWaveCellLand", "CellInFlow", "RootStore_unsat", "Precipitation", "PotenEvap", "ThroughFall",
+         "StemFlow", "Interception", "PotTransSoil", "RainFallPlusMelt", "AvailableForInfiltration",
+         "RunoffRiverCells", "RunoffLandCells", "ActEvapOpenWaterRiver", "ActEvapOpenWaterLand", "RestEvap",
+         "PotSoilEvap", "PotTrans", "Transpiration", "InterceptionWatBal", "SurfaceWatbal"]
+RIVER_STATES = ["RiverRunoff", "RiverRunoffsub", "WaterLevelR", "WaterLevelRsub"]
+
+
+def state_names(max_layers, snow=True):
+    s = ["zi", "SubsurfaceFlow", "LandRunoff", "LandRunoffsub", "WaterLevelL", "WaterLevelLsub", "CanopyStorage"]
+    s += ["UStoreLayerDepth_%d" % k for k in range(max_layers)]
+    if snow:
+        s += ["Snow", "SnowWater", "TSoil"]
+    return s + RIVER_STATES
+
+
+def make_pair(nrow, ncol, *, kind="forest", tile=16, layer_thickness=(100, 300, 800), dt=86400, snow=1, itL=1, itR=1,
+              seed=3, river_area=8, tm=0, ust=0, sir=0, oracle=True, gpu=True):
+    """Returns (oracle_model or None, cuda_model or None, ldd, river)."""
+    ldd, river, static, state = synth.make_case(nrow, ncol, kind=kind, tile=tile, seed=seed, timestepsecs=dt,
+                                                layer_thickness=layer_thickness, river_area=river_area)
+    orc = mod = None
+    if oracle:
+        from oracle import oracle as O
+        orc = O.Oracle(ldd, river, timestepsecs=dt, layer_thickness=layer_thickness, modelSnow=snow, it_kinL=itL,
+                       it_kinR=itR, transferMethod=tm, ust=ust, soilInfRedu=sir)
+        for k, v in static.items():
+            orc.set(k, v)
+        for k, v in state.items():
+            orc.set(k, v)
+    if gpu:
+        from wflow_b200.core import SbmModel
+        mod = SbmModel(ldd, river, timestepsecs=dt, layer_thickness=layer_thickness, model_snow=snow, it_kin_l=itL,
+                       it_kin_r=itR, transfer_method=tm, ust=ust, soil_inf_redu=sir)
+        skip = {"River", "Beta", "SatWaterDepth"}
+        for k, v in static.items():
+            if k not in skip:
+                mod.set(k, v)
+        for k, v in state.items():
+            if k not in skip:
+                mod.set(k, v)
+    return orc, mod, ldd, river
+
+
+def network_mask(orc):
+    m = np.zeros(orc.shape, bool)
+    m.flat[orc.net.flat_nodes] = True
+    return m
+
+
+def compare(a, b, mask, rtol, atol):
+    """max over masked cells of |a-b| / (atol + rtol*|b|); <= 1 passes."""
+    a = a[mask].astype(np.float64)
+    b = b[mask].astype(np.float64)
+    if a.size == 0:
+        return 0.0
+    return float(np.max(np.abs(a - b) / (atol + rtol * np.abs(b))))

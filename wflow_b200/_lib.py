@@ -1,0 +1,109 @@
+"""ctypes binding of libwflowsbm.so (C-ABI: include/wflow_sbm.h).
+
+There is deliberately no fallback: if the CUDA library has not been built, or no B200 is
+visible, the error surfaces here.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwflowsbm.so")
+
+WF_MAX_LAYERS = 8
+
+
+class WfConfig(C.Structure):
+    _fields_ = [
+        ("nrow", C.c_int32), ("ncol", C.c_int32),
+        ("n_layer_thickness", C.c_int32),
+        ("layer_thickness", C.c_double * WF_MAX_LAYERS),
+        ("model_snow", C.c_int32), ("soil_inf_redu", C.c_int32), ("transfer_method", C.c_int32),
+        ("ust", C.c_int32), ("glacier", C.c_int32), ("it_kin_l", C.c_int32), ("it_kin_r", C.c_int32),
+        ("device", C.c_int32),
+        ("timestepsecs", C.c_double), ("beta", C.c_double),
+    ]
+
+
+class WflowLibError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# every symbol include/wflow_sbm.h declares (checked by tests/test_cabi.py)
+SYMBOLS = [
+    "wf_last_error", "wf_version", "wf_create", "wf_destroy", "wf_num_cells", "wf_num_levels",
+    "wf_num_river_cells", "wf_num_river_levels", "wf_get_network", "wf_catchment_total", "wf_set_field",
+    "wf_set_field_uniform", "wf_get_field", "wf_request_output", "wf_num_fields", "wf_field_name",
+    "wf_field_kind", "wf_field_device_ptr", "wf_cell_order", "wf_set_field_from_device", "wf_step",
+    "wf_synchronize", "wf_last_step_ms", "wf_launch_count", "wf_stream", "wf_area_create", "wf_area_num_ids",
+    "wf_area_ids", "wf_area_reduce", "wf_sample", "wf_quick_suspend", "wf_quick_resume",
+    "wf_schedule_create", "wf_schedule_destroy", "wf_schedule_num_cells", "wf_schedule_num_levels",
+    "wf_schedule_get",
+]
+
+
+def build():
+    """Compile libwflowsbm.so in-tree (nvcc, sm_100a)."""
+    import subprocess
+    subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc"), "-s"])
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise WflowLibError(
+            "libwflowsbm.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C wflow_b200/csrc`. There is no CPU fallback." % LIB_PATH)
+    l = C.CDLL(LIB_PATH)
+    l.wf_last_error.restype = C.c_char_p
+    l.wf_version.restype = C.c_char_p
+    l.wf_field_name.restype = C.c_char_p
+    l.wf_field_name.argtypes = [C.c_int]
+    l.wf_field_kind.argtypes = [C.c_int]
+    l.wf_create.argtypes = [C.POINTER(WfConfig), C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    l.wf_destroy.argtypes = [C.c_void_p]
+    l.wf_destroy.restype = None
+    for name in ("wf_num_cells", "wf_num_levels", "wf_num_river_cells", "wf_num_river_levels", "wf_launch_count"):
+        getattr(l, name).restype = C.c_int64
+        getattr(l, name).argtypes = [C.c_void_p]
+    l.wf_get_network.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    l.wf_catchment_total.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    l.wf_set_field.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+    l.wf_set_field_from_device.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+    l.wf_set_field_uniform.argtypes = [C.c_void_p, C.c_char_p, C.c_float]
+    l.wf_get_field.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_float]
+    l.wf_request_output.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    l.wf_field_device_ptr.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    l.wf_cell_order.argtypes = [C.c_void_p, C.c_void_p]
+    l.wf_step.argtypes = [C.c_void_p, C.c_int]
+    l.wf_synchronize.argtypes = [C.c_void_p]
+    l.wf_last_step_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    l.wf_stream.argtypes = [C.c_void_p]
+    l.wf_stream.restype = C.c_void_p
+    l.wf_area_create.argtypes = [C.c_void_p, C.c_void_p]
+    l.wf_area_num_ids.argtypes = [C.c_void_p, C.c_int]
+    l.wf_area_ids.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    l.wf_area_reduce.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_void_p]
+    l.wf_sample.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float]
+    l.wf_schedule_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    l.wf_schedule_destroy.argtypes = [C.c_void_p]
+    l.wf_schedule_destroy.restype = None
+    l.wf_schedule_num_cells.argtypes = [C.c_void_p]
+    l.wf_schedule_num_cells.restype = C.c_int64
+    l.wf_schedule_num_levels.argtypes = [C.c_void_p]
+    l.wf_schedule_num_levels.restype = C.c_int64
+    l.wf_schedule_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    l.wf_quick_suspend.argtypes = [C.c_void_p]
+    l.wf_quick_resume.argtypes = [C.c_void_p]
+    _lib = l
+    return l
+
+
+def check(rc):
+    if rc < 0:
+        raise WflowLibError("libwflowsbm: %s (code %d)" % (lib().wf_last_error().decode(), rc))
+    return rc

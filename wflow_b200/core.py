@@ -1,0 +1,187 @@
+"""`SbmModel`: thin Python owner of a libwflowsbm handle (one model grid on one B200).
+
+This is the raster-level layer the framework mirror (wflow_b200.framework) and the BMI
+(wflow_b200.bmi) sit on.  It exposes exactly what the reference's WflowModel does around
+its numba kernels: set rasters, step, read rasters -- with the arithmetic on the GPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+AREA_OPS = {"average": 0, "total": 1, "maximum": 2, "minimum": 3}
+
+
+def build_schedule(ldd):
+    """Host-only level schedule of an LDD raster (no GPU needed): (nodes, nodes_up, lev_off)
+    in the reference's set_dd form (wflow/wflow_funcs.py:70-95), flattened."""
+    l = _lib.lib()
+    ldd = np.ascontiguousarray(ldd, dtype=np.uint8)
+    h = C.c_void_p()
+    _lib.check(l.wf_schedule_create(ldd.ctypes.data, ldd.shape[0], ldd.shape[1], C.byref(h)))
+    try:
+        n, nl = int(l.wf_schedule_num_cells(h)), int(l.wf_schedule_num_levels(h))
+        nodes = np.zeros(max(n, 1), np.int64)
+        up = np.zeros(max(n, 1) * 8, np.int64)
+        off = np.zeros(nl + 1, np.int64)
+        _lib.check(l.wf_schedule_get(h, nodes.ctypes.data, up.ctypes.data, off.ctypes.data))
+    finally:
+        l.wf_schedule_destroy(h)
+    return nodes[:n], up[: n * 8].reshape(n, 8), off
+
+
+class SbmModel:
+    def __init__(self, ldd, river=None, *, timestepsecs=86400, layer_thickness=(), model_snow=1, soil_inf_redu=0,
+                 transfer_method=0, ust=0, glacier=0, it_kin_l=1, it_kin_r=1, device=0, beta=0.0):
+        self._l = _lib.lib()
+        ldd = np.ascontiguousarray(ldd, dtype=np.uint8)
+        if ldd.ndim != 2:
+            raise ValueError("ldd must be a 2-D raster")
+        self.shape = ldd.shape
+        self._ldd = ldd
+        riv = None if river is None else np.ascontiguousarray(np.asarray(river) != 0, dtype=np.uint8)
+        cfg = _lib.WfConfig()
+        cfg.nrow, cfg.ncol = self.shape
+        cfg.n_layer_thickness = len(layer_thickness)
+        for i, t in enumerate(layer_thickness):
+            cfg.layer_thickness[i] = float(t)
+        cfg.model_snow, cfg.soil_inf_redu, cfg.transfer_method = int(model_snow), int(soil_inf_redu), int(transfer_method)
+        cfg.ust, cfg.glacier, cfg.it_kin_l, cfg.it_kin_r = int(ust), int(glacier), int(it_kin_l), int(it_kin_r)
+        cfg.device, cfg.timestepsecs, cfg.beta = int(device), float(timestepsecs), float(beta)
+        self.cfg = cfg
+        self.max_layers = len(layer_thickness) + 1 if len(layer_thickness) else 1
+        h = C.c_void_p()
+        _lib.check(self._l.wf_create(C.byref(cfg), ldd.ctypes.data_as(C.c_void_p),
+                                     None if riv is None else riv.ctypes.data_as(C.c_void_p), C.byref(h)))
+        self._h = h
+
+    # -- lifetime ------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._l.wf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- network ---------------------------------------------------------------------------
+    @property
+    def num_cells(self):
+        return int(self._l.wf_num_cells(self._h))
+
+    @property
+    def num_levels(self):
+        return int(self._l.wf_num_levels(self._h))
+
+    @property
+    def num_river_cells(self):
+        return int(self._l.wf_num_river_cells(self._h))
+
+    def network(self, river=False):
+        """(nodes, nodes_up, lev_off) in the reference's set_dd form, flattened."""
+        n = int(self._l.wf_num_river_cells(self._h) if river else self._l.wf_num_cells(self._h))
+        nl = int(self._l.wf_num_river_levels(self._h) if river else self._l.wf_num_levels(self._h))
+        nodes = np.zeros(max(n, 1), np.int64)
+        up = np.zeros(max(n, 1) * 8, np.int64)
+        off = np.zeros(nl + 1, np.int64)
+        _lib.check(self._l.wf_get_network(self._h, int(river), nodes.ctypes.data, up.ctypes.data, off.ctypes.data))
+        return nodes[:n], up[: n * 8].reshape(n, 8), off
+
+    def cell_order(self):
+        o = np.zeros(max(self.num_cells, 1), np.int64)
+        _lib.check(self._l.wf_cell_order(self._h, o.ctypes.data))
+        return o[: self.num_cells]
+
+    def catchment_total(self, values=None):
+        out = np.zeros(self.shape, np.float64)
+        v = None if values is None else np.ascontiguousarray(values, np.float32)
+        _lib.check(self._l.wf_catchment_total(self._h, None if v is None else v.ctypes.data, out.ctypes.data))
+        return out
+
+    # -- fields ----------------------------------------------------------------------------
+    def set(self, name, value):
+        a = np.asarray(value, dtype=np.float32)
+        if a.ndim == 0 or a.size == 1:
+            _lib.check(self._l.wf_set_field_uniform(self._h, name.encode(), float(a.reshape(-1)[0])))
+            return
+        if a.shape != self.shape:
+            raise ValueError("raster %s has shape %s, model grid is %s" % (name, a.shape, self.shape))
+        a = np.ascontiguousarray(a)
+        _lib.check(self._l.wf_set_field(self._h, name.encode(), a.ctypes.data))
+        # the copy is asynchronous on the model's stream: keep the host buffer alive until it is consumed
+        _lib.check(self._l.wf_synchronize(self._h))
+
+    def set_many(self, fields):
+        for k, v in fields.items():
+            self.set(k, v)
+
+    def set_pinned(self, name, host_ptr):
+        """Asynchronous upload from a caller-owned (ideally pinned) nrow*ncol float32 buffer."""
+        _lib.check(self._l.wf_set_field(self._h, name.encode(), host_ptr))
+
+    def get(self, name, mv=-999.0):
+        out = np.empty(self.shape, np.float32)
+        _lib.check(self._l.wf_get_field(self._h, name.encode(), out.ctypes.data, float(mv)))
+        return out
+
+    def request(self, *names, enable=True):
+        for n in names:
+            _lib.check(self._l.wf_request_output(self._h, n.encode(), int(enable)))
+
+    def device_ptr(self, name):
+        p, n = C.c_void_p(), C.c_int64()
+        _lib.check(self._l.wf_field_device_ptr(self._h, name.encode(), C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    # -- stepping --------------------------------------------------------------------------
+    def step(self, nsteps=1):
+        _lib.check(self._l.wf_step(self._h, int(nsteps)))
+
+    def synchronize(self):
+        _lib.check(self._l.wf_synchronize(self._h))
+
+    def last_step_ms(self):
+        ms = (C.c_float * 3)()
+        _lib.check(self._l.wf_last_step_ms(self._h, ms))
+        return tuple(ms)
+
+    @property
+    def launch_count(self):
+        return int(self._l.wf_launch_count(self._h))
+
+    @property
+    def stream(self):
+        return self._l.wf_stream(self._h)
+
+    def quick_suspend(self):
+        _lib.check(self._l.wf_quick_suspend(self._h))
+
+    def quick_resume(self):
+        _lib.check(self._l.wf_quick_resume(self._h))
+
+    # -- gauges / areas -------------------------------------------------------------------
+    def area_create(self, idmap):
+        a = np.ascontiguousarray(idmap, dtype=np.int32)
+        if a.shape != self.shape:
+            raise ValueError("id map shape mismatch")
+        h = _lib.check(self._l.wf_area_create(self._h, a.ctypes.data))
+        n = _lib.check(self._l.wf_area_num_ids(self._h, h))
+        ids = np.zeros(max(n, 1), np.int32)
+        _lib.check(self._l.wf_area_ids(self._h, h, ids.ctypes.data))
+        return h, ids[:n]
+
+    def area_reduce(self, area, field, op="average"):
+        n = _lib.check(self._l.wf_area_num_ids(self._h, area))
+        out = np.zeros(max(n, 1), np.float32)
+        _lib.check(self._l.wf_area_reduce(self._h, area, field.encode(), AREA_OPS[op], out.ctypes.data))
+        return out[:n]
+
+    def sample(self, field, flat_index, mv=-999.0):
+        idx = np.ascontiguousarray(flat_index, dtype=np.int64)
+        out = np.zeros(max(idx.size, 1), np.float32)
+        _lib.check(self._l.wf_sample(self._h, field.encode(), idx.ctypes.data, idx.size, out.ctypes.data, float(mv)))
+        return out[: idx.size]

@@ -1,0 +1,663 @@
+// C-ABI of libwflowsbm.so (include/wflow_sbm.h): model handle, field staging, stepping.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/wflow_sbm.h"
+#include "fields.h"
+#include "kernels.cuh"
+#include "network.h"
+#include "reduce.cuh"
+
+namespace wf {
+
+const FieldInfo g_fields[F_COUNT] = {
+#define X(n, k) {#n, (int)(k)},
+    WF_FIELDS(X)
+#undef X
+};
+
+int field_index(const char *name) {
+  static std::map<std::string, int> idx;
+  if (idx.empty())
+    for (int i = 0; i < F_COUNT; i++) idx[g_fields[i].name] = i;
+  auto it = idx.find(name ? name : "");
+  return it == idx.end() ? -1 : it->second;
+}
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_OK(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(WF_ENODEVICE, std::string(#call) + ": " + cudaGetErrorString(e_));               \
+  } while (0)
+
+struct AreaSet {
+  std::vector<int32_t> ids;   // ascending unique ids > 0
+  int32_t *d_perm = nullptr;  // cells (network order index) sorted by id
+  int32_t *d_seg = nullptr;   // ids.size()+1 offsets into perm
+  int64_t ncell = 0;
+};
+
+}  // namespace wf
+
+using namespace wf;
+
+struct wf_schedule {
+  Network net;
+};
+
+struct wf_model {
+  wf_config cfg;
+  Network net, rnet;                 // full and river-only schedules (reference form recoverable)
+  std::vector<int32_t> river_slot;   // network order -> river order (or -1)
+  std::vector<int64_t> river_flat;   // river order -> flat grid index (first nrnet: rnet.order)
+  int64_t n = 0;
+  int32_t nr = 0, nrnet = 0;
+  DevModel dm;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  int64_t *d_order = nullptr, *d_rorder = nullptr, *d_lev_off = nullptr;
+  float *d_stage = nullptr;          // nrow*ncol staging raster
+  std::vector<float *> snapshot;     // quick-suspend copies of the state arrays
+  std::vector<AreaSet> areas;
+  int64_t launches = 0;
+  int coop_blocks = 0;
+  bool timed = false;
+  int ML = 1;
+};
+
+namespace {
+
+int64_t field_len(const wf_model *m, int id) { return (g_fields[id].kind & K_RIVER) ? m->nr : m->n; }
+
+int ensure_field(wf_model *m, int id) {
+  if (m->dm.f[id]) return WF_OK;
+  const int64_t len = std::max<int64_t>(field_len(m, id), 1);
+  float *p = nullptr;
+  CUDA_OK(cudaMalloc(&p, sizeof(float) * len));
+  CUDA_OK(cudaMemsetAsync(p, 0, sizeof(float) * len, m->stream));
+  m->dm.f[id] = p;
+  return WF_OK;
+}
+
+template <int ML>
+int launch_step(wf_model *m) {
+  const int64_t n = m->n;
+  if (n == 0) return WF_OK;
+  if (m->timed) cudaEventRecord(m->ev[0], m->stream);
+  const int tb = 128;
+  k_vertical<ML><<<(unsigned)((n + tb - 1) / tb), tb, 0, m->stream>>>(m->dm);
+  m->launches++;
+  if (m->timed) cudaEventRecord(m->ev[1], m->stream);
+  if (m->dm.nlev == 1) {
+    const int lb = 256;
+    k_lateral_one_level<ML><<<(unsigned)((n + lb - 1) / lb), lb, 0, m->stream>>>(m->dm, 0, n);
+  } else {
+    if (m->coop_blocks == 0) {
+      int dev = 0, sms = 0, per_sm = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lateral<ML>, 256, 0);
+      if (per_sm < 1) return fail(WF_ENODEVICE, "k_lateral does not fit on an SM");
+      m->coop_blocks = sms * per_sm;
+    }
+    // no more blocks than the widest level can use
+    int64_t widest = 1;
+    for (size_t l = 0; l + 1 < m->net.lev_off.size(); l++)
+      widest = std::max(widest, m->net.lev_off[l + 1] - m->net.lev_off[l]);
+    int blocks = (int)std::min<int64_t>(m->coop_blocks, (widest + 255) / 256);
+    void *args[] = {(void *)&m->dm};
+    CUDA_OK(cudaLaunchCooperativeKernel((void *)k_lateral<ML>, dim3(blocks), dim3(256), args, 0, m->stream));
+  }
+  m->launches++;
+  if (m->timed) cudaEventRecord(m->ev[2], m->stream);
+  CUDA_OK(cudaGetLastError());
+  return WF_OK;
+}
+
+int dispatch_step(wf_model *m) {
+  switch (m->ML) {
+    case 1: return launch_step<1>(m);
+    case 2: return launch_step<2>(m);
+    case 3: return launch_step<3>(m);
+    case 4: return launch_step<4>(m);
+    case 5: return launch_step<5>(m);
+    case 6: return launch_step<6>(m);
+    case 7: return launch_step<7>(m);
+    case 8: return launch_step<8>(m);
+  }
+  return fail(WF_EINVAL, "unsupported number of soil layers");
+}
+
+const int kRequired[] = {F_P, F_PET, F_Cmax, F_EoverR, F_CanopyGapFraction, F_et_RefToPot, F_WaterFrac,
+                         F_SoilThickness, F_thetaS, F_thetaR, F_KsatVer, F_f, F_InfiltCapSoil, F_InfiltCapPath,
+                         F_PathFrac, F_CapScale, F_rootdistpar, F_RootingDepth, F_AirEntryPressure, F_MaxLeakage,
+                         F_xl, F_yl, F_KsatHorFrac, F_landSlope, F_DL, F_DW, F_SW, F_AlphaL};
+const int kRequiredSnow[] = {F_TEMP, F_TempCor, F_TTI, F_TT, F_TTM, F_Cfmax, F_WHC, F_w_soil};
+const int kRequiredRiver[] = {F_RiverFrac, F_AlphaR, F_DCL, F_Bw};
+const int kRequiredGlacier[] = {F_GlacierFrac, F_G_TT, F_G_Cfmax, F_G_SIfrac};
+
+int check_ready(wf_model *m) {
+  auto need = [&](int id) -> int {
+    if (!m->dm.f[id]) return fail(WF_EINVAL, std::string("field not set: ") + g_fields[id].name);
+    return WF_OK;
+  };
+  for (int id : kRequired)
+    if (int rc = need(id)) return rc;
+  for (int k = 0; k < m->ML; k++) {
+    if (int rc = need(F_c_0 + k)) return rc;
+    if (int rc = need(F_KsatVerFrac_0 + k)) return rc;
+  }
+  if (m->cfg.model_snow)
+    for (int id : kRequiredSnow)
+      if (int rc = need(id)) return rc;
+  if (m->cfg.model_snow && m->cfg.soil_inf_redu)
+    if (int rc = need(F_cf_soil)) return rc;
+  if (m->nr > 0)
+    for (int id : kRequiredRiver)
+      if (int rc = need(id)) return rc;
+  if (m->cfg.glacier)
+    for (int id : kRequiredGlacier)
+      if (int rc = need(id)) return rc;
+  return WF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *wf_last_error(void) { return g_err.c_str(); }
+const char *wf_version(void) { return "wflow_b200 0.1 (sm_100a)"; }
+
+int wf_num_fields(void) { return F_COUNT; }
+const char *wf_field_name(int i) { return (i >= 0 && i < F_COUNT) ? g_fields[i].name : nullptr; }
+int wf_field_kind(int i) { return (i >= 0 && i < F_COUNT) ? g_fields[i].kind : -1; }
+
+int wf_create(const wf_config *cfg, const uint8_t *ldd, const uint8_t *river, wf_model **out) {
+  if (!cfg || !ldd || !out) return fail(WF_EINVAL, "null argument");
+  if (cfg->nrow <= 0 || cfg->ncol <= 0) return fail(WF_EINVAL, "bad grid size");
+  if (cfg->n_layer_thickness < 0 || cfg->n_layer_thickness + 1 > WF_MAX_LAYERS)
+    return fail(WF_EINVAL, "too many soil layers");
+  if (cfg->it_kin_l < 1 || cfg->it_kin_r < 1) return fail(WF_EINVAL, "it_kin_l / it_kin_r must be >= 1");
+  if (!(cfg->timestepsecs > 0)) return fail(WF_EINVAL, "timestepsecs must be > 0");
+  const int64_t N = (int64_t)cfg->nrow * cfg->ncol;
+  if (N >= (int64_t)1 << 31) return fail(WF_EUNSUPPORTED, "grids of 2^31 cells or more are not supported");
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail(WF_ENODEVICE, "no CUDA device available (this library has no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(WF_ENODEVICE, "bad device ordinal");
+  CUDA_OK(cudaSetDevice(cfg->device));
+
+  wf_model *m = new wf_model();
+  m->cfg = *cfg;
+  if (m->cfg.beta == 0.0) m->cfg.beta = (double)0.6f;  // REAL4 0.6, wflow_sbm.py:1643
+  // wflow_sbm.py:1757-1766
+  m->ML = (cfg->n_layer_thickness > 0) ? cfg->n_layer_thickness + 1 : 1;
+
+  if (build_network(ldd, cfg->nrow, cfg->ncol, m->net) != 0) {
+    delete m;
+    return fail(WF_ECYCLE, "could not build the drainage network");
+  }
+  // river-only ldd: non-river cells -> missing (wflow_sbm.py:2387-2389)
+  {
+    std::vector<uint8_t> lr((size_t)N, 0);
+    if (river)
+      for (int64_t i = 0; i < N; i++) lr[(size_t)i] = river[i] ? ldd[i] : 0;
+    if (build_network(lr.data(), cfg->nrow, cfg->ncol, m->rnet) != 0) {
+      delete m;
+      return fail(WF_ECYCLE, "could not build the river network");
+    }
+  }
+  m->n = m->net.ncells;
+  const int64_t n = m->n;
+  // river order: river-network cells in rnodes order, then river-map cells kin_wave never visits
+  m->river_slot.assign((size_t)std::max<int64_t>(n, 1), -1);
+  {
+    std::vector<int32_t> slot_of_flat((size_t)N, -1);
+    std::vector<int32_t> pos_of_flat((size_t)N, -1);
+    for (int64_t k = 0; k < n; k++) pos_of_flat[(size_t)m->net.order[(size_t)k]] = (int32_t)k;
+    int32_t s = 0;
+    for (int64_t k = 0; k < m->rnet.ncells; k++) {
+      const int64_t fl = m->rnet.order[(size_t)k];
+      if (pos_of_flat[(size_t)fl] < 0) continue;  // cannot happen: river network is a sub-forest
+      slot_of_flat[(size_t)fl] = s++;
+      m->river_flat.push_back(fl);
+    }
+    m->nrnet = s;
+    if (river)
+      for (int64_t k = 0; k < n; k++) {
+        const int64_t fl = m->net.order[(size_t)k];
+        if (river[fl] && slot_of_flat[(size_t)fl] < 0) {
+          slot_of_flat[(size_t)fl] = s++;
+          m->river_flat.push_back(fl);
+        }
+      }
+    m->nr = s;
+    for (int64_t k = 0; k < n; k++) m->river_slot[(size_t)k] = slot_of_flat[(size_t)m->net.order[(size_t)k]];
+  }
+
+  CUDA_OK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  for (auto &e : m->ev) CUDA_OK(cudaEventCreate(&e));
+
+  DevModel &dm = m->dm;
+  std::memset(&dm, 0, sizeof(dm));
+  dm.n = n;
+  dm.nr = m->nr;
+  dm.nrnet = m->nrnet;
+  dm.nlev = (int32_t)m->net.nlevels();
+  dm.ML = m->ML;
+  dm.nrLayers = (cfg->n_layer_thickness > 0) ? cfg->n_layer_thickness : 1;
+  for (int k = 0; k < WF_MAXL; k++) dm.layerThickness[k] = (k < cfg->n_layer_thickness) ? cfg->layer_thickness[k] : 0.0;
+  dm.modelSnow = cfg->model_snow;
+  dm.soilInfRedu = cfg->soil_inf_redu;
+  dm.transferMethod = cfg->transfer_method;
+  dm.ust = cfg->ust;
+  dm.glacier = cfg->glacier;
+  dm.gash = cfg->timestepsecs >= (23 * 3600);  // wflow_sbm.py:2639
+  dm.itL = cfg->it_kin_l;
+  dm.itR = cfg->it_kin_r;
+  dm.dt = cfg->timestepsecs;
+  dm.basetimestep = 86400.0;  // wflow_sbm.py:1222
+  dm.beta = m->cfg.beta;
+
+  auto upload = [&](const void *src, size_t bytes, void **dst) -> int {
+    CUDA_OK(cudaMalloc(dst, std::max<size_t>(bytes, 16)));
+    if (bytes) CUDA_OK(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    return WF_OK;
+  };
+  int rc;
+  std::vector<uint8_t> topo((size_t)std::max<int64_t>(n, 1));
+  for (int64_t k = 0; k < n; k++)
+    topo[(size_t)k] = (uint8_t)((m->net.nup[(size_t)k] << 4) | (ldd[m->net.order[(size_t)k]] & 15));
+  if ((rc = upload(m->net.order.data(), sizeof(int64_t) * n, (void **)&m->d_order))) return rc;
+  if ((rc = upload(m->river_flat.data(), sizeof(int64_t) * m->nr, (void **)&m->d_rorder))) return rc;
+  if ((rc = upload(m->net.lev_off.data(), sizeof(int64_t) * m->net.lev_off.size(), (void **)&m->d_lev_off))) return rc;
+  if ((rc = upload(m->net.up_start.data(), sizeof(uint32_t) * n, (void **)&dm.up_start))) return rc;
+  if ((rc = upload(topo.data(), n, (void **)&dm.topo))) return rc;
+  if ((rc = upload(m->river_slot.data(), sizeof(int32_t) * n, (void **)&dm.river_slot))) return rc;
+  dm.lev_off = m->d_lev_off;
+  CUDA_OK(cudaMalloc(&dm.h_r, sizeof(float) * std::max<int64_t>(n, 1)));
+  CUDA_OK(cudaMalloc(&dm.h_surplus, sizeof(float) * std::max<int64_t>(n, 1)));
+  CUDA_OK(cudaMalloc(&dm.h_inwaterMM, sizeof(float) * std::max<int32_t>(m->nr, 1)));
+  if (dm.itL > 1) CUDA_OK(cudaMalloc(&dm.qo_sub, sizeof(float) * (size_t)(dm.itL - 1) * std::max<int64_t>(n, 1)));
+  if (dm.itR > 1) CUDA_OK(cudaMalloc(&dm.qr_sub, sizeof(float) * (size_t)(dm.itR - 1) * std::max<int32_t>(m->nr, 1)));
+  // states exist from the start (zero = the reference's cold ZeroMap)
+  for (int id = 0; id < F_COUNT; id++) {
+    if ((g_fields[id].kind & 0xff) != K_STATE) continue;
+    if (id >= F_UStoreLayerDepth_0 && id <= F_UStoreLayerDepth_7 && id - F_UStoreLayerDepth_0 >= m->ML) continue;
+    if (id == F_GlacierStore && !cfg->glacier) continue;
+    if ((rc = ensure_field(m, id))) return rc;
+  }
+  CUDA_OK(cudaStreamSynchronize(m->stream));
+  *out = m;
+  return WF_OK;
+}
+
+void wf_destroy(wf_model *m) {
+  if (!m) return;
+  cudaSetDevice(m->cfg.device);
+  cudaStreamSynchronize(m->stream);
+  for (int id = 0; id < F_COUNT; id++) cudaFree(m->dm.f[id]);
+  for (float *p : m->snapshot) cudaFree(p);
+  for (auto &a : m->areas) { cudaFree(a.d_perm); cudaFree(a.d_seg); }
+  cudaFree(m->dm.h_r); cudaFree(m->dm.h_surplus); cudaFree(m->dm.h_inwaterMM); cudaFree(m->dm.h_wb);
+  cudaFree(m->dm.qo_sub); cudaFree(m->dm.qr_sub);
+  cudaFree((void *)m->dm.up_start); cudaFree((void *)m->dm.topo); cudaFree((void *)m->dm.river_slot);
+  cudaFree(m->d_order); cudaFree(m->d_rorder); cudaFree(m->d_lev_off); cudaFree(m->d_stage);
+  for (auto &e : m->ev) cudaEventDestroy(e);
+  cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+static void network_to_reference_form(const Network &net, int64_t *nodes, int64_t *nodes_up, int64_t *lev_off) {
+  if (nodes) std::copy(net.order.begin(), net.order.end(), nodes);
+  if (lev_off) std::copy(net.lev_off.begin(), net.lev_off.end(), lev_off);
+  if (nodes_up)
+    for (int64_t k = 0; k < net.ncells; k++)
+      for (int j = 0; j < 8; j++)
+        nodes_up[k * 8 + j] = (j < net.nup[(size_t)k]) ? net.order[(size_t)net.up_start[(size_t)k] + j] : -1;
+}
+
+int wf_schedule_create(const uint8_t *ldd, int nrow, int ncol, wf_schedule **out) {
+  if (!ldd || !out || nrow <= 0 || ncol <= 0) return fail(WF_EINVAL, "bad argument");
+  wf_schedule *s = new wf_schedule();
+  if (build_network(ldd, nrow, ncol, s->net) != 0) {
+    delete s;
+    return fail(WF_ECYCLE, "could not build the drainage network");
+  }
+  *out = s;
+  return WF_OK;
+}
+void wf_schedule_destroy(wf_schedule *s) { delete s; }
+int64_t wf_schedule_num_cells(const wf_schedule *s) { return s ? s->net.ncells : 0; }
+int64_t wf_schedule_num_levels(const wf_schedule *s) { return s ? s->net.nlevels() : 0; }
+int wf_schedule_get(const wf_schedule *s, int64_t *nodes, int64_t *nodes_up, int64_t *lev_off) {
+  if (!s) return fail(WF_EINVAL, "null schedule");
+  network_to_reference_form(s->net, nodes, nodes_up, lev_off);
+  return WF_OK;
+}
+
+int64_t wf_num_cells(const wf_model *m) { return m ? m->n : 0; }
+int64_t wf_num_levels(const wf_model *m) { return m ? m->net.nlevels() : 0; }
+int64_t wf_num_river_cells(const wf_model *m) { return m ? m->rnet.ncells : 0; }
+int64_t wf_num_river_levels(const wf_model *m) { return m ? m->rnet.nlevels() : 0; }
+
+int wf_get_network(const wf_model *m, int which, int64_t *nodes, int64_t *nodes_up, int64_t *lev_off) {
+  if (!m) return fail(WF_EINVAL, "null model");
+  network_to_reference_form(which ? m->rnet : m->net, nodes, nodes_up, lev_off);
+  return WF_OK;
+}
+
+int wf_catchment_total(const wf_model *m, const float *values, double *out_grid) {
+  if (!m || !out_grid) return fail(WF_EINVAL, "null argument");
+  const Network &net = m->net;
+  const int64_t N = (int64_t)net.nrow * net.ncol;
+  for (int64_t i = 0; i < N; i++) out_grid[i] = 0.0;
+  std::vector<double> acc((size_t)std::max<int64_t>(net.ncells, 1));
+  for (int64_t k = 0; k < net.ncells; k++) {  // level order: upstream cells are complete before k
+    double v = values ? (double)values[net.order[(size_t)k]] : 1.0;
+    for (int j = 0; j < net.nup[(size_t)k]; j++) v += acc[(size_t)net.up_start[(size_t)k] + j];
+    acc[(size_t)k] = v;
+    out_grid[net.order[(size_t)k]] = v;
+  }
+  return WF_OK;
+}
+
+static int stage(wf_model *m) {
+  if (!m->d_stage) CUDA_OK(cudaMalloc(&m->d_stage, sizeof(float) * (size_t)m->cfg.nrow * m->cfg.ncol));
+  return WF_OK;
+}
+
+static int gather_into(wf_model *m, int id, const float *dgrid) {
+  if (int rc = ensure_field(m, id)) return rc;
+  const bool riv = g_fields[id].kind & K_RIVER;
+  const int64_t len = riv ? m->nr : m->n;
+  if (len > 0) {
+    k_gather<<<(unsigned)((len + 255) / 256), 256, 0, m->stream>>>(dgrid, riv ? m->d_rorder : m->d_order, m->dm.f[id], len);
+    m->launches++;
+  }
+  CUDA_OK(cudaGetLastError());
+  return WF_OK;
+}
+
+int wf_set_field(wf_model *m, const char *name, const float *grid) {
+  if (!m || !grid) return fail(WF_EINVAL, "null argument");
+  const int id = field_index(name);
+  if (id < 0) return fail(WF_EINVAL, std::string("unknown field: ") + (name ? name : "(null)"));
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  if (int rc = stage(m)) return rc;
+  const size_t bytes = sizeof(float) * (size_t)m->cfg.nrow * m->cfg.ncol;
+  CUDA_OK(cudaMemcpyAsync(m->d_stage, grid, bytes, cudaMemcpyHostToDevice, m->stream));
+  return gather_into(m, id, m->d_stage);
+}
+
+int wf_set_field_from_device(wf_model *m, const char *name, const float *dgrid) {
+  if (!m || !dgrid) return fail(WF_EINVAL, "null argument");
+  const int id = field_index(name);
+  if (id < 0) return fail(WF_EINVAL, std::string("unknown field: ") + (name ? name : "(null)"));
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  return gather_into(m, id, dgrid);
+}
+
+int wf_set_field_uniform(wf_model *m, const char *name, float value) {
+  if (!m) return fail(WF_EINVAL, "null model");
+  const int id = field_index(name);
+  if (id < 0) return fail(WF_EINVAL, std::string("unknown field: ") + (name ? name : "(null)"));
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  if (int rc = ensure_field(m, id)) return rc;
+  const int64_t len = field_len(m, id);
+  if (len > 0) {
+    k_fill<<<(unsigned)((len + 255) / 256), 256, 0, m->stream>>>(m->dm.f[id], value, len);
+    m->launches++;
+  }
+  CUDA_OK(cudaGetLastError());
+  return WF_OK;
+}
+
+int wf_get_field(wf_model *m, const char *name, float *grid, float mv) {
+  if (!m || !grid) return fail(WF_EINVAL, "null argument");
+  const int id = field_index(name);
+  if (id < 0) return fail(WF_EINVAL, std::string("unknown field: ") + (name ? name : "(null)"));
+  if (!m->dm.f[id]) return fail(WF_EINVAL, std::string("field has no data (not set / not requested): ") + name);
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  if (int rc = stage(m)) return rc;
+  const int64_t N = (int64_t)m->cfg.nrow * m->cfg.ncol;
+  const bool riv = g_fields[id].kind & K_RIVER;
+  k_fill<<<(unsigned)((N + 255) / 256), 256, 0, m->stream>>>(m->d_stage, mv, N);
+  m->launches++;
+  if (riv && m->n > 0) {
+    // river-only arrays: the reference holds 0 at the other cells of the network (np.zeros outputs,
+    // wflow_funcs.py:172-182), missing value outside it
+    float *tmp = nullptr;
+    CUDA_OK(cudaMalloc(&tmp, sizeof(float) * m->n));
+    CUDA_OK(cudaMemsetAsync(tmp, 0, sizeof(float) * m->n, m->stream));
+    k_scatter<<<(unsigned)((m->n + 255) / 256), 256, 0, m->stream>>>(tmp, m->d_order, m->d_stage, m->n);
+    m->launches++;
+    CUDA_OK(cudaStreamSynchronize(m->stream));
+    cudaFree(tmp);
+  }
+  const int64_t len = riv ? m->nr : m->n;
+  if (len > 0) {
+    k_scatter<<<(unsigned)((len + 255) / 256), 256, 0, m->stream>>>(m->dm.f[id], riv ? m->d_rorder : m->d_order, m->d_stage, len);
+    m->launches++;
+  }
+  CUDA_OK(cudaMemcpyAsync(grid, m->d_stage, sizeof(float) * N, cudaMemcpyDeviceToHost, m->stream));
+  CUDA_OK(cudaStreamSynchronize(m->stream));
+  return WF_OK;
+}
+
+int wf_request_output(wf_model *m, const char *name, int enable) {
+  if (!m) return fail(WF_EINVAL, "null model");
+  const int id = field_index(name);
+  if (id < 0) return fail(WF_EINVAL, std::string("unknown field: ") + (name ? name : "(null)"));
+  if ((g_fields[id].kind & 0xff) != K_DIAG) return WF_OK;  // forcing/static/state always exist once set
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  if (enable) {
+    if (int rc = ensure_field(m, id)) return rc;
+    if (id == F_SoilWatbal || id == F_watbal) {
+      if (!m->dm.h_wb) CUDA_OK(cudaMalloc(&m->dm.h_wb, sizeof(double) * std::max<int64_t>(m->n, 1)));
+      if (int rc = ensure_field(m, F_SoilWatbal)) return rc;
+      if (id == F_watbal)
+        if (int rc = ensure_field(m, F_SurfaceWatbal)) return rc;
+    }
+  } else if (m->dm.f[id]) {
+    CUDA_OK(cudaStreamSynchronize(m->stream));
+    cudaFree(m->dm.f[id]);
+    m->dm.f[id] = nullptr;
+  }
+  return WF_OK;
+}
+
+int wf_field_device_ptr(wf_model *m, const char *name, void **dptr, int64_t *n) {
+  if (!m || !dptr) return fail(WF_EINVAL, "null argument");
+  const int id = field_index(name);
+  if (id < 0) return fail(WF_EINVAL, std::string("unknown field: ") + (name ? name : "(null)"));
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  if (int rc = ensure_field(m, id)) return rc;
+  *dptr = m->dm.f[id];
+  if (n) *n = field_len(m, id);
+  return WF_OK;
+}
+
+int wf_cell_order(const wf_model *m, int64_t *flat_index) {
+  if (!m || !flat_index) return fail(WF_EINVAL, "null argument");
+  std::copy(m->net.order.begin(), m->net.order.end(), flat_index);
+  return WF_OK;
+}
+
+int wf_step(wf_model *m, int nsteps) {
+  if (!m) return fail(WF_EINVAL, "null model");
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  if (int rc = check_ready(m)) return rc;
+  m->timed = true;
+  for (int s = 0; s < nsteps; s++)
+    if (int rc = dispatch_step(m)) return rc;
+  return WF_OK;
+}
+
+int wf_synchronize(wf_model *m) {
+  if (!m) return fail(WF_EINVAL, "null model");
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  CUDA_OK(cudaStreamSynchronize(m->stream));
+  return WF_OK;
+}
+
+int wf_last_step_ms(wf_model *m, float ms[3]) {
+  if (!m || !ms) return fail(WF_EINVAL, "null argument");
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  CUDA_OK(cudaEventSynchronize(m->ev[2]));
+  CUDA_OK(cudaEventElapsedTime(&ms[0], m->ev[0], m->ev[1]));
+  CUDA_OK(cudaEventElapsedTime(&ms[1], m->ev[1], m->ev[2]));
+  CUDA_OK(cudaEventElapsedTime(&ms[2], m->ev[0], m->ev[2]));
+  return WF_OK;
+}
+
+int64_t wf_launch_count(const wf_model *m) { return m ? m->launches : 0; }
+void *wf_stream(wf_model *m) { return m ? (void *)m->stream : nullptr; }
+
+// ---- gauge / area accumulation ----------------------------------------------------------
+int wf_area_create(wf_model *m, const int32_t *idmap) {
+  if (!m || !idmap) return fail(WF_EINVAL, "null argument");
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  AreaSet a;
+  std::vector<std::pair<int32_t, int32_t>> pairs;  // (id, network index)
+  pairs.reserve((size_t)m->n);
+  for (int64_t k = 0; k < m->n; k++) {
+    const int32_t id = idmap[m->net.order[(size_t)k]];
+    if (id > 0) pairs.emplace_back(id, (int32_t)k);
+  }
+  std::stable_sort(pairs.begin(), pairs.end(),
+                   [](const std::pair<int32_t, int32_t> &x, const std::pair<int32_t, int32_t> &y) { return x.first < y.first; });
+  std::vector<int32_t> perm(pairs.size()), seg;
+  for (size_t i = 0; i < pairs.size(); i++) {
+    if (i == 0 || pairs[i].first != pairs[i - 1].first) {
+      a.ids.push_back(pairs[i].first);
+      seg.push_back((int32_t)i);
+    }
+    perm[i] = pairs[i].second;
+  }
+  seg.push_back((int32_t)pairs.size());
+  a.ncell = (int64_t)pairs.size();
+  CUDA_OK(cudaMalloc(&a.d_perm, sizeof(int32_t) * std::max<size_t>(perm.size(), 1)));
+  CUDA_OK(cudaMalloc(&a.d_seg, sizeof(int32_t) * seg.size()));
+  if (!perm.empty()) CUDA_OK(cudaMemcpy(a.d_perm, perm.data(), sizeof(int32_t) * perm.size(), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(a.d_seg, seg.data(), sizeof(int32_t) * seg.size(), cudaMemcpyHostToDevice));
+  m->areas.push_back(a);
+  return (int)m->areas.size() - 1;
+}
+
+int wf_area_num_ids(wf_model *m, int area) {
+  if (!m || area < 0 || area >= (int)m->areas.size()) return fail(WF_EINVAL, "bad area handle");
+  return (int)m->areas[(size_t)area].ids.size();
+}
+
+int wf_area_ids(wf_model *m, int area, int32_t *ids) {
+  if (!m || !ids || area < 0 || area >= (int)m->areas.size()) return fail(WF_EINVAL, "bad area handle");
+  const auto &v = m->areas[(size_t)area].ids;
+  std::copy(v.begin(), v.end(), ids);
+  return WF_OK;
+}
+
+int wf_area_reduce(wf_model *m, int area, const char *field, int op, float *out) {
+  if (!m || !out || area < 0 || area >= (int)m->areas.size()) return fail(WF_EINVAL, "bad area handle");
+  const int id = field_index(field);
+  if (id < 0 || !m->dm.f[id]) return fail(WF_EINVAL, std::string("field has no data: ") + (field ? field : "(null)"));
+  if (op < 0 || op > 3) return fail(WF_EINVAL, "bad reduction op");
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  AreaSet &a = m->areas[(size_t)area];
+  const int nids = (int)a.ids.size();
+  if (nids == 0) return WF_OK;
+  float *d_out = nullptr;
+  CUDA_OK(cudaMalloc(&d_out, sizeof(float) * nids));
+  const bool riv = g_fields[id].kind & K_RIVER;
+  k_area_reduce<<<nids, 256, 0, m->stream>>>(m->dm.f[id], riv ? m->dm.river_slot : nullptr, a.d_perm, a.d_seg, op, d_out);
+  m->launches++;
+  CUDA_OK(cudaMemcpyAsync(out, d_out, sizeof(float) * nids, cudaMemcpyDeviceToHost, m->stream));
+  CUDA_OK(cudaStreamSynchronize(m->stream));
+  cudaFree(d_out);
+  return WF_OK;
+}
+
+int wf_sample(wf_model *m, const char *field, const int64_t *flat_index, int64_t n, float *out, float mv) {
+  if (!m || !flat_index || !out) return fail(WF_EINVAL, "null argument");
+  const int id = field_index(field);
+  if (id < 0 || !m->dm.f[id]) return fail(WF_EINVAL, std::string("field has no data: ") + (field ? field : "(null)"));
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  // translate flat grid indices to array positions on the host (gauge lists are short)
+  static thread_local std::vector<int32_t> pos;
+  std::map<int64_t, int32_t> want;
+  for (int64_t i = 0; i < n; i++) want[flat_index[i]] = -1;
+  for (int64_t k = 0; k < m->n; k++) {
+    auto it = want.find(m->net.order[(size_t)k]);
+    if (it != want.end()) it->second = (int32_t)k;
+  }
+  const bool riv = g_fields[id].kind & K_RIVER;
+  pos.assign((size_t)n, -1);
+  std::vector<int> zero((size_t)n, 0);
+  for (int64_t i = 0; i < n; i++) {
+    int32_t k = want[flat_index[i]];
+    if (k >= 0 && riv) {
+      const int32_t s = m->river_slot[(size_t)k];
+      if (s < 0) zero[(size_t)i] = 1;
+      k = s;
+    }
+    pos[(size_t)i] = k;
+  }
+  int32_t *d_pos = nullptr;
+  float *d_out = nullptr;
+  CUDA_OK(cudaMalloc(&d_pos, sizeof(int32_t) * std::max<int64_t>(n, 1)));
+  CUDA_OK(cudaMalloc(&d_out, sizeof(float) * std::max<int64_t>(n, 1)));
+  CUDA_OK(cudaMemcpyAsync(d_pos, pos.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, m->stream));
+  if (n > 0) {
+    k_sample<<<(unsigned)((n + 127) / 128), 128, 0, m->stream>>>(m->dm.f[id], d_pos, d_out, n, mv);
+    m->launches++;
+  }
+  CUDA_OK(cudaMemcpyAsync(out, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost, m->stream));
+  CUDA_OK(cudaStreamSynchronize(m->stream));
+  for (int64_t i = 0; i < n; i++)
+    if (zero[(size_t)i]) out[i] = 0.0f;
+  cudaFree(d_pos);
+  cudaFree(d_out);
+  return WF_OK;
+}
+
+// ---- one-step rollback -------------------------------------------------------------------
+int wf_quick_suspend(wf_model *m) {
+  if (!m) return fail(WF_EINVAL, "null model");
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  if (m->snapshot.empty()) m->snapshot.assign(F_COUNT, nullptr);
+  for (int id = 0; id < F_COUNT; id++) {
+    if ((g_fields[id].kind & 0xff) != K_STATE || !m->dm.f[id]) continue;
+    const size_t bytes = sizeof(float) * (size_t)std::max<int64_t>(field_len(m, id), 1);
+    if (!m->snapshot[(size_t)id]) CUDA_OK(cudaMalloc(&m->snapshot[(size_t)id], bytes));
+    CUDA_OK(cudaMemcpyAsync(m->snapshot[(size_t)id], m->dm.f[id], bytes, cudaMemcpyDeviceToDevice, m->stream));
+  }
+  return WF_OK;
+}
+
+int wf_quick_resume(wf_model *m) {
+  if (!m) return fail(WF_EINVAL, "null model");
+  if (m->snapshot.empty()) return fail(WF_EINVAL, "no snapshot: call wf_quick_suspend first");
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  for (int id = 0; id < F_COUNT; id++) {
+    if (!m->snapshot[(size_t)id] || !m->dm.f[id]) continue;
+    const size_t bytes = sizeof(float) * (size_t)std::max<int64_t>(field_len(m, id), 1);
+    CUDA_OK(cudaMemcpyAsync(m->dm.f[id], m->snapshot[(size_t)id], bytes, cudaMemcpyDeviceToDevice, m->stream));
+  }
+  return WF_OK;
+}
+
+}  // extern "C"

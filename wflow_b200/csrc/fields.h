@@ -1,0 +1,82 @@
+// Field table of libwflowsbm: one row per raster the hot path reads or writes.
+// Names are the reference's attribute names (wflow/wflow_sbm.py).
+#pragma once
+#include <cstdint>
+
+namespace wf {
+
+enum FieldKind : int { K_FORCING = 0, K_STATIC = 1, K_STATE = 2, K_DIAG = 3, K_RIVER = 0x100 };
+
+// X(name, kind)   -- K_RIVER marks arrays that exist only for river cells (river order)
+#define WF_FIELDS(X)                                                                               \
+  /* forcing (wf_updateparameters, wflow_sbm.py:2583) */                                           \
+  X(P, K_FORCING) X(PET, K_FORCING) X(TEMP, K_FORCING) X(Inflow, K_FORCING | K_RIVER)              \
+  /* statics of the PCRaster phases (wflow_sbm.py:2636-2819) */                                    \
+  X(Cmax, K_STATIC) X(EoverR, K_STATIC) X(CanopyGapFraction, K_STATIC) X(et_RefToPot, K_STATIC)    \
+  X(TempCor, K_STATIC) X(TTI, K_STATIC) X(TT, K_STATIC) X(TTM, K_STATIC) X(Cfmax, K_STATIC)        \
+  X(WHC, K_STATIC) X(w_soil, K_STATIC) X(cf_soil, K_STATIC) X(WaterFrac, K_STATIC)                 \
+  X(RiverFrac, K_STATIC | K_RIVER)                                                                 \
+  /* statics of the soil column (static/layer dtypes, wflow_sbm.py:2176-2299) */                   \
+  X(SoilThickness, K_STATIC) X(thetaS, K_STATIC) X(thetaR, K_STATIC) X(KsatVer, K_STATIC)          \
+  X(f, K_STATIC) X(InfiltCapSoil, K_STATIC) X(InfiltCapPath, K_STATIC) X(PathFrac, K_STATIC)       \
+  X(CapScale, K_STATIC) X(rootdistpar, K_STATIC) X(RootingDepth, K_STATIC)                         \
+  X(AirEntryPressure, K_STATIC) X(MaxLeakage, K_STATIC) X(xl, K_STATIC) X(yl, K_STATIC)            \
+  X(c_0, K_STATIC) X(c_1, K_STATIC) X(c_2, K_STATIC) X(c_3, K_STATIC)                              \
+  X(c_4, K_STATIC) X(c_5, K_STATIC) X(c_6, K_STATIC) X(c_7, K_STATIC)                              \
+  X(KsatVerFrac_0, K_STATIC) X(KsatVerFrac_1, K_STATIC) X(KsatVerFrac_2, K_STATIC)                 \
+  X(KsatVerFrac_3, K_STATIC) X(KsatVerFrac_4, K_STATIC) X(KsatVerFrac_5, K_STATIC)                 \
+  X(KsatVerFrac_6, K_STATIC) X(KsatVerFrac_7, K_STATIC)                                            \
+  /* lateral statics */                                                                            \
+  X(KsatHorFrac, K_STATIC) X(landSlope, K_STATIC) X(DL, K_STATIC) X(DW, K_STATIC)                  \
+  X(SW, K_STATIC) X(AlphaL, K_STATIC)                                                              \
+  X(AlphaR, K_STATIC | K_RIVER) X(DCL, K_STATIC | K_RIVER) X(Bw, K_STATIC | K_RIVER)               \
+  /* glacier */                                                                                    \
+  X(GlacierFrac, K_STATIC) X(G_TT, K_STATIC) X(G_Cfmax, K_STATIC) X(G_SIfrac, K_STATIC)            \
+  /* states (stateVariables(), wflow_sbm.py:955-1010; zi is the live saturated-zone state) */      \
+  X(CanopyStorage, K_STATE) X(Snow, K_STATE) X(SnowWater, K_STATE) X(TSoil, K_STATE)               \
+  X(zi, K_STATE)                                                                                   \
+  X(UStoreLayerDepth_0, K_STATE) X(UStoreLayerDepth_1, K_STATE) X(UStoreLayerDepth_2, K_STATE)     \
+  X(UStoreLayerDepth_3, K_STATE) X(UStoreLayerDepth_4, K_STATE) X(UStoreLayerDepth_5, K_STATE)     \
+  X(UStoreLayerDepth_6, K_STATE) X(UStoreLayerDepth_7, K_STATE)                                    \
+  X(SubsurfaceFlow, K_STATE) X(LandRunoff, K_STATE) X(LandRunoffsub, K_STATE)                      \
+  X(WaterLevelL, K_STATE) X(WaterLevelLsub, K_STATE)                                               \
+  X(RiverRunoff, K_STATE | K_RIVER) X(RiverRunoffsub, K_STATE | K_RIVER)                           \
+  X(WaterLevelR, K_STATE | K_RIVER) X(WaterLevelRsub, K_STATE | K_RIVER)                           \
+  X(GlacierStore, K_STATE)                                                                         \
+  /* diagnostics, materialised only on request */                                                  \
+  X(SatWaterDepth, K_DIAG) X(Precipitation, K_DIAG) X(PotenEvap, K_DIAG) X(Temperature, K_DIAG)    \
+  X(ThroughFall, K_DIAG) X(StemFlow, K_DIAG) X(Interception, K_DIAG) X(PotTransSoil, K_DIAG)       \
+  X(SnowMelt, K_DIAG) X(SnowFall, K_DIAG) X(RainFallPlusMelt, K_DIAG)                              \
+  X(AvailableForInfiltration, K_DIAG) X(RunoffRiverCells, K_DIAG) X(RunoffLandCells, K_DIAG)       \
+  X(ActEvapOpenWaterRiver, K_DIAG) X(ActEvapOpenWaterLand, K_DIAG) X(RestEvap, K_DIAG)             \
+  X(PotSoilEvap, K_DIAG) X(PotTrans, K_DIAG) X(UStoreDepth, K_DIAG) X(CapFlux, K_DIAG)             \
+  X(Transfer, K_DIAG) X(ActEvapUStore, K_DIAG) X(ActEvapSat, K_DIAG) X(Transpiration, K_DIAG)      \
+  X(soilevap, K_DIAG) X(soilevapsat, K_DIAG) X(ActEvap, K_DIAG) X(Recharge, K_DIAG)                \
+  X(InwaterMM, K_DIAG) X(qo_toriver, K_DIAG) X(ssf_toriver, K_DIAG) X(Inwater, K_DIAG | K_RIVER)   \
+  X(ExfiltWater, K_DIAG) X(InfiltExcess, K_DIAG) X(ExcessWater, K_DIAG) X(ActInfilt, K_DIAG)       \
+  X(ActLeakage, K_DIAG) X(SoilInf, K_DIAG) X(PathInf, K_DIAG) X(InfiltExcessSoil, K_DIAG)          \
+  X(InfiltExcessPath, K_DIAG) X(ActInfiltSoil, K_DIAG) X(ActInfiltPath, K_DIAG)                    \
+  X(ExfiltFromUstore, K_DIAG) X(ExfiltFromSat, K_DIAG) X(InwaterL, K_DIAG)                         \
+  X(InflowKinWaveCellLand, K_DIAG) X(CellInFlow, K_DIAG) X(SoilWatbal, K_DIAG)                     \
+  X(InterceptionWatBal, K_DIAG) X(SurfaceWatbal, K_DIAG) X(watbal, K_DIAG)                         \
+  X(RootStore_unsat, K_DIAG)                                                                       \
+  X(vwc_0, K_DIAG) X(vwc_1, K_DIAG) X(vwc_2, K_DIAG) X(vwc_3, K_DIAG)                              \
+  X(vwc_4, K_DIAG) X(vwc_5, K_DIAG) X(vwc_6, K_DIAG) X(vwc_7, K_DIAG)                              \
+  X(Snow2Glacier, K_DIAG) X(GlacierMelt, K_DIAG)
+
+enum FieldId : int {
+#define X(n, k) F_##n,
+  WF_FIELDS(X)
+#undef X
+      F_COUNT
+};
+
+struct FieldInfo {
+  const char *name;
+  int kind;
+};
+
+extern const FieldInfo g_fields[F_COUNT];
+int field_index(const char *name);
+
+}  // namespace wf
