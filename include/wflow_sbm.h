@@ -78,6 +78,12 @@ int64_t wf_schedule_num_cells(const wf_schedule *s);
 int64_t wf_schedule_num_levels(const wf_schedule *s);
 /* nodes / nodes_up / lev_off as in wf_get_network. */
 int wf_schedule_get(const wf_schedule *s, int64_t *nodes, int64_t *nodes_up, int64_t *lev_off);
+/* catchmenttotal over a host-only schedule (see wf_catchment_total). */
+int wf_schedule_catchment_total(const wf_schedule *s, const float *values, double *out_grid);
+/* wf_create reusing an already built full-network schedule (ownership passes to the model; the
+ * schedule handle must not be used or destroyed afterwards). */
+int wf_create_from_schedule(const wf_config *cfg, wf_schedule *s, const uint8_t *ldd, const uint8_t *river,
+                            wf_model **out);
 
 int64_t wf_num_cells(const wf_model *m);        /* cells in the drainage network */
 int64_t wf_num_levels(const wf_model *m);
@@ -113,6 +119,9 @@ int wf_field_device_ptr(wf_model *m, const char *name, void **dptr, int64_t *n);
 int wf_cell_order(const wf_model *m, int64_t *flat_index /* [wf_num_cells] */);
 /* Same as wf_set_field, but `grid` is a DEVICE pointer to an nrow*ncol raster. */
 int wf_set_field_from_device(wf_model *m, const char *name, const float *dgrid);
+/* Zero-copy forcing: make the model read field `name` from a caller-owned DEVICE array that is
+ * already in network order (river order for river-only fields).  dptr == NULL unbinds. */
+int wf_bind_field(wf_model *m, const char *name, float *dptr);
 
 /* --- stepping -----------------------------------------------------------------------
  * Replaces one pass of WflowModel.dynamic() (wflow/wflow_sbm.py:2518-3528): the PCRaster
@@ -124,6 +133,11 @@ int wf_synchronize(wf_model *m);
 /* Device time of the kernels of the last wf_step call, milliseconds (CUDA events on the
  * model's stream): [0] vertical column, [1] lateral sweep, [2] whole step. */
 int wf_last_step_ms(wf_model *m, float ms[3]);
+/* Accumulated device time since wf_timing_reset over all steps (CUDA events on the model's
+ * stream around each kernel): ms[0] vertical column, ms[1] lateral sweep, ms[2] whole steps;
+ * *nsteps = steps covered.  wf_timing_get synchronises the stream. */
+int wf_timing_reset(wf_model *m);
+int wf_timing_get(wf_model *m, double ms[3], int64_t *nsteps);
 /* Number of kernel launches issued by the model since creation. */
 int64_t wf_launch_count(const wf_model *m);
 /* The CUDA stream (cudaStream_t) the model launches on. */

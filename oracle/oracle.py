@@ -50,7 +50,15 @@ def lib():
         _lib.wfo_kinematic_wave.argtypes = [C.c_double] * 7
         _lib.wfo_kinematic_wave_ssf.argtypes = [C.c_double] * 14 + [C.POINTER(C.c_double)] * 3
         _lib.wfo_kinematic_wave_ssf.restype = None
+        _lib.wfo_set_threads.argtypes = [C.c_int]
     return _lib
+
+
+def set_threads(n):
+    """Threads used by Oracle.step (OpenMP over the cells of a level); returns the count in use."""
+    n = max(1, min(int(n), lib().wfo_max_threads()))
+    lib().wfo_set_threads(n)
+    return n
 
 
 def field_names():

@@ -29,6 +29,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define WFO_MAXL 8
 
@@ -84,6 +87,18 @@ static const char *wfo_names[] = {
     WFO_FIELDS(X)
 #undef X
 };
+
+/* Threads for wfo_step (cells of one level are independent, so the level loops are
+ * parallelised with OpenMP for the CPU-baseline timing; results do not depend on it). */
+static int g_threads = 1;
+void wfo_set_threads(int n) { g_threads = n > 0 ? n : 1; }
+int wfo_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
 
 int wfo_nfields(void) { return WFO_NFIELDS; }
 const char *wfo_field_name(int i) { return (i >= 0 && i < WFO_NFIELDS) ? wfo_names[i] : 0; }
@@ -394,6 +409,7 @@ int wfo_step(const wfo_params *p, const wfo_network *net, const wfo_network *rne
          *OldCanopy = RainPlusMeltD + N, *RunoffRiverD = OldCanopy + N;
 
   /* ---------------- P0-P3: PCRaster REAL4 phases (wflow_sbm.py:2583-2819) ---------------- */
+#pragma omp parallel for schedule(static) num_threads(g_threads)
   for (int64_t i = 0; i < N; i++) {
     if (!active[i]) continue;
     float Precipitation = fmaxf(0.0f, F(P)[i]);                       /* :2584 */
@@ -545,6 +561,7 @@ int wfo_step(const wfo_params *p, const wfo_network *net, const wfo_network *rne
   /* ---------------- P5: sbm_cell (wflow_sbm.py:332-900), float64 ---------------- */
   const double dt = p->timestepsecs;
   for (int64_t lev = 0; lev < net->nlev; lev++) {
+#pragma omp parallel for schedule(dynamic, 64) num_threads(g_threads)
     for (int64_t kk = net->lev_off[lev]; kk < net->lev_off[lev + 1]; kk++) {
       const int64_t idx = net->nodes[kk];
       const int64_t *nbs = net->nodes_up + 8 * kk;
@@ -830,6 +847,7 @@ int wfo_step(const wfo_params *p, const wfo_network *net, const wfo_network *rne
   for (int v = 0; v < itL; v++) {
     memset(qo_new, 0, sizeof(double) * (N + 1));
     for (int64_t lev = 0; lev < net->nlev; lev++) {
+#pragma omp parallel for schedule(dynamic, 64) num_threads(g_threads)
       for (int64_t kk = net->lev_off[lev]; kk < net->lev_off[lev + 1]; kk++) {
         const int64_t idx = net->nodes[kk];
         const int64_t *nbs = net->nodes_up + 8 * kk;
@@ -900,6 +918,7 @@ int wfo_step(const wfo_params *p, const wfo_network *net, const wfo_network *rne
     for (int v = 0; v < itR; v++) { /* kin_wave, wflow_funcs.py:155-207 */
       memset(Qnew, 0, sizeof(double) * (N + 1));
       for (int64_t lev = 0; lev < rnet->nlev; lev++) {
+#pragma omp parallel for schedule(dynamic, 16) num_threads(g_threads)
         for (int64_t kk = rnet->lev_off[lev]; kk < rnet->lev_off[lev + 1]; kk++) {
           const int64_t idx = rnet->nodes[kk];
           const int64_t *nbs = rnet->nodes_up + 8 * kk;

@@ -24,10 +24,11 @@ def state_names(max_layers, snow=True):
 
 
 def make_pair(nrow, ncol, *, kind="forest", tile=16, layer_thickness=(100, 300, 800), dt=86400, snow=1, itL=1, itR=1,
-              seed=3, river_area=8, tm=0, ust=0, sir=0, oracle=True, gpu=True):
+              seed=3, river_area=8, tm=0, ust=0, sir=0, oracle=True, gpu=True, init="random", block=4):
     """Returns (oracle_model or None, cuda_model or None, ldd, river)."""
     ldd, river, static, state = synth.make_case(nrow, ncol, kind=kind, tile=tile, seed=seed, timestepsecs=dt,
-                                                layer_thickness=layer_thickness, river_area=river_area)
+                                                layer_thickness=layer_thickness, river_area=river_area, init=init,
+                                                block=block)
     orc = mod = None
     if oracle:
         from oracle import oracle as O
@@ -64,3 +65,43 @@ def compare(a, b, mask, rtol, atol):
     if a.size == 0:
         return 0.0
     return float(np.max(np.abs(a - b) / (atol + rtol * np.abs(b))))
+
+
+# ---- golden fixtures (tests/golden, written by oracle/gen_golden.py from the reference) ----
+import ast
+import glob
+import os
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_step_cases():
+    return sorted(os.path.basename(p)[5:-4] for p in glob.glob(os.path.join(GOLD, "step_*.npz")))
+
+
+def load_golden_case(name, oracle=True, gpu=False):
+    """Rebuild the oracle / CUDA model of a golden trajectory from its stored inputs."""
+    g = np.load(os.path.join(GOLD, "step_%s.npz" % name))
+    kw = ast.literal_eval(str(g["meta"]))
+    lt = kw["layer_thickness"]
+    opt = dict(dt=kw.get("dt", 86400), snow=kw.get("snow", 1), itL=kw.get("itL", 1), itR=kw.get("itR", 1),
+               tm=kw.get("tm", 0), ust=kw.get("ust", 0), sir=kw.get("sir", 0))
+    static = {k[7:]: g[k] for k in g.files if k.startswith("static/")}
+    state = {k[7:]: g[k] for k in g.files if k.startswith("state0/")}
+    orc = mod = None
+    if oracle:
+        from oracle import oracle as O
+        orc = O.Oracle(g["ldd"], g["river"], timestepsecs=opt["dt"], layer_thickness=lt, modelSnow=opt["snow"],
+                       it_kinL=opt["itL"], it_kinR=opt["itR"], transferMethod=opt["tm"], ust=opt["ust"],
+                       soilInfRedu=opt["sir"])
+        for k, v in {**static, **state}.items():
+            orc.set(k, v)
+    if gpu:
+        from wflow_b200.core import SbmModel
+        mod = SbmModel(g["ldd"], g["river"], timestepsecs=opt["dt"], layer_thickness=lt, model_snow=opt["snow"],
+                       it_kin_l=opt["itL"], it_kin_r=opt["itR"], transfer_method=opt["tm"], ust=opt["ust"],
+                       soil_inf_redu=opt["sir"])
+        for k, v in {**static, **state}.items():
+            if k not in ("River", "Beta", "SatWaterDepth"):
+                mod.set(k, v)
+    return g, kw, orc, mod

@@ -39,7 +39,8 @@ SYMBOLS = [
     "wf_synchronize", "wf_last_step_ms", "wf_launch_count", "wf_stream", "wf_area_create", "wf_area_num_ids",
     "wf_area_ids", "wf_area_reduce", "wf_sample", "wf_quick_suspend", "wf_quick_resume",
     "wf_schedule_create", "wf_schedule_destroy", "wf_schedule_num_cells", "wf_schedule_num_levels",
-    "wf_schedule_get",
+    "wf_schedule_get", "wf_schedule_catchment_total", "wf_create_from_schedule", "wf_bind_field",
+    "wf_timing_reset", "wf_timing_get",
 ]
 
 
@@ -97,6 +98,11 @@ def lib():
     l.wf_schedule_num_levels.argtypes = [C.c_void_p]
     l.wf_schedule_num_levels.restype = C.c_int64
     l.wf_schedule_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    l.wf_schedule_catchment_total.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    l.wf_create_from_schedule.argtypes = [C.POINTER(WfConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    l.wf_bind_field.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+    l.wf_timing_reset.argtypes = [C.c_void_p]
+    l.wf_timing_get.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     l.wf_quick_suspend.argtypes = [C.c_void_p]
     l.wf_quick_resume.argtypes = [C.c_void_p]
     _lib = l

@@ -31,8 +31,45 @@ def build_schedule(ldd):
     return nodes[:n], up[: n * 8].reshape(n, 8), off
 
 
+class Schedule:
+    """Host-only level schedule (no GPU needed).  Can be handed to SbmModel(schedule=...) so the
+    network is built once when a quantity derived from it (e.g. the river mask from the upstream
+    area) is needed before the model exists."""
+
+    def __init__(self, ldd):
+        self._l = _lib.lib()
+        self.ldd = np.ascontiguousarray(ldd, dtype=np.uint8)
+        self.shape = self.ldd.shape
+        h = C.c_void_p()
+        _lib.check(self._l.wf_schedule_create(self.ldd.ctypes.data, self.shape[0], self.shape[1], C.byref(h)))
+        self._h = h
+
+    @property
+    def num_cells(self):
+        return int(self._l.wf_schedule_num_cells(self._h))
+
+    @property
+    def num_levels(self):
+        return int(self._l.wf_schedule_num_levels(self._h))
+
+    def catchment_total(self, values=None):
+        out = np.zeros(self.shape, np.float64)
+        v = None if values is None else np.ascontiguousarray(values, np.float32)
+        _lib.check(self._l.wf_schedule_catchment_total(self._h, None if v is None else v.ctypes.data, out.ctypes.data))
+        return out
+
+    def _release(self):
+        h, self._h = self._h, None
+        return h
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._l.wf_schedule_destroy(self._h)
+            self._h = None
+
+
 class SbmModel:
-    def __init__(self, ldd, river=None, *, timestepsecs=86400, layer_thickness=(), model_snow=1, soil_inf_redu=0,
+    def __init__(self, ldd, river=None, *, schedule=None, timestepsecs=86400, layer_thickness=(), model_snow=1, soil_inf_redu=0,
                  transfer_method=0, ust=0, glacier=0, it_kin_l=1, it_kin_r=1, device=0, beta=0.0):
         self._l = _lib.lib()
         ldd = np.ascontiguousarray(ldd, dtype=np.uint8)
@@ -52,8 +89,9 @@ class SbmModel:
         self.cfg = cfg
         self.max_layers = len(layer_thickness) + 1 if len(layer_thickness) else 1
         h = C.c_void_p()
-        _lib.check(self._l.wf_create(C.byref(cfg), ldd.ctypes.data_as(C.c_void_p),
-                                     None if riv is None else riv.ctypes.data_as(C.c_void_p), C.byref(h)))
+        _lib.check(self._l.wf_create_from_schedule(
+            C.byref(cfg), None if schedule is None else schedule._release(), ldd.ctypes.data_as(C.c_void_p),
+            None if riv is None else riv.ctypes.data_as(C.c_void_p), C.byref(h)))
         self._h = h
 
     # -- lifetime ------------------------------------------------------------------------
@@ -131,6 +169,19 @@ class SbmModel:
     def request(self, *names, enable=True):
         for n in names:
             _lib.check(self._l.wf_request_output(self._h, n.encode(), int(enable)))
+
+    def bind(self, name, dptr):
+        """Zero-copy: read field `name` from a caller-owned device array in network order."""
+        _lib.check(self._l.wf_bind_field(self._h, name.encode(), dptr))
+
+    def timing_reset(self):
+        _lib.check(self._l.wf_timing_reset(self._h))
+
+    def timing_get(self):
+        ms = (C.c_double * 3)()
+        n = C.c_int64()
+        _lib.check(self._l.wf_timing_get(self._h, ms, C.byref(n)))
+        return tuple(ms), int(n.value)
 
     def device_ptr(self, name):
         p, n = C.c_void_p(), C.c_int64()

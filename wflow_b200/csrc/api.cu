@@ -68,6 +68,7 @@ struct wf_model {
   DevModel dm;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_last[3] = {nullptr, nullptr, nullptr};
   int64_t *d_order = nullptr, *d_rorder = nullptr, *d_lev_off = nullptr;
   float *d_stage = nullptr;          // nrow*ncol staging raster
   std::vector<float *> snapshot;     // quick-suspend copies of the state arrays
@@ -76,6 +77,10 @@ struct wf_model {
   int coop_blocks = 0;
   bool timed = false;
   int ML = 1;
+  bool external[F_COUNT] = {};        // field bound to a caller-owned device array
+  float *owned[F_COUNT] = {};         // our own allocation while an external one is bound
+  std::vector<cudaEvent_t> tev;       // timing window: 3 events per step
+  size_t tev_used = 0;
 };
 
 namespace {
@@ -96,11 +101,16 @@ template <int ML>
 int launch_step(wf_model *m) {
   const int64_t n = m->n;
   if (n == 0) return WF_OK;
-  if (m->timed) cudaEventRecord(m->ev[0], m->stream);
+  cudaEvent_t e0 = m->ev[0], e1 = m->ev[1], e2 = m->ev[2];
+  if (m->tev_used + 3 <= m->tev.size()) {
+    e0 = m->tev[m->tev_used]; e1 = m->tev[m->tev_used + 1]; e2 = m->tev[m->tev_used + 2];
+    m->tev_used += 3;
+  }
+  if (m->timed) cudaEventRecord(e0, m->stream);
   const int tb = 128;
   k_vertical<ML><<<(unsigned)((n + tb - 1) / tb), tb, 0, m->stream>>>(m->dm);
   m->launches++;
-  if (m->timed) cudaEventRecord(m->ev[1], m->stream);
+  if (m->timed) cudaEventRecord(e1, m->stream);
   if (m->dm.nlev == 1) {
     const int lb = 256;
     k_lateral_one_level<ML><<<(unsigned)((n + lb - 1) / lb), lb, 0, m->stream>>>(m->dm, 0, n);
@@ -122,7 +132,8 @@ int launch_step(wf_model *m) {
     CUDA_OK(cudaLaunchCooperativeKernel((void *)k_lateral<ML>, dim3(blocks), dim3(256), args, 0, m->stream));
   }
   m->launches++;
-  if (m->timed) cudaEventRecord(m->ev[2], m->stream);
+  if (m->timed) cudaEventRecord(e2, m->stream);
+  m->ev_last[0] = e0; m->ev_last[1] = e1; m->ev_last[2] = e2;
   CUDA_OK(cudaGetLastError());
   return WF_OK;
 }
@@ -176,6 +187,18 @@ int check_ready(wf_model *m) {
 
 }  // namespace
 
+static void catchment_total(const Network &net, const float *values, double *out_grid) {
+  const int64_t N = (int64_t)net.nrow * net.ncol;
+  for (int64_t i = 0; i < N; i++) out_grid[i] = 0.0;
+  std::vector<double> acc((size_t)std::max<int64_t>(net.ncells, 1));
+  for (int64_t k = 0; k < net.ncells; k++) {  // level order: upstream cells are complete before k
+    double v = values ? (double)values[net.order[(size_t)k]] : 1.0;
+    for (int j = 0; j < net.nup[(size_t)k]; j++) v += acc[(size_t)net.up_start[(size_t)k] + j];
+    acc[(size_t)k] = v;
+    out_grid[net.order[(size_t)k]] = v;
+  }
+}
+
 extern "C" {
 
 const char *wf_last_error(void) { return g_err.c_str(); }
@@ -186,6 +209,17 @@ const char *wf_field_name(int i) { return (i >= 0 && i < F_COUNT) ? g_fields[i].
 int wf_field_kind(int i) { return (i >= 0 && i < F_COUNT) ? g_fields[i].kind : -1; }
 
 int wf_create(const wf_config *cfg, const uint8_t *ldd, const uint8_t *river, wf_model **out) {
+  return wf_create_from_schedule(cfg, nullptr, ldd, river, out);
+}
+
+int wf_schedule_catchment_total(const wf_schedule *s, const float *values, double *out_grid) {
+  if (!s || !out_grid) return fail(WF_EINVAL, "null argument");
+  catchment_total(s->net, values, out_grid);
+  return WF_OK;
+}
+
+int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint8_t *ldd, const uint8_t *river,
+                            wf_model **out) {
   if (!cfg || !ldd || !out) return fail(WF_EINVAL, "null argument");
   if (cfg->nrow <= 0 || cfg->ncol <= 0) return fail(WF_EINVAL, "bad grid size");
   if (cfg->n_layer_thickness < 0 || cfg->n_layer_thickness + 1 > WF_MAX_LAYERS)
@@ -207,7 +241,14 @@ int wf_create(const wf_config *cfg, const uint8_t *ldd, const uint8_t *river, wf
   // wflow_sbm.py:1757-1766
   m->ML = (cfg->n_layer_thickness > 0) ? cfg->n_layer_thickness + 1 : 1;
 
-  if (build_network(ldd, cfg->nrow, cfg->ncol, m->net) != 0) {
+  if (sched) {
+    if (sched->net.nrow != cfg->nrow || sched->net.ncol != cfg->ncol) {
+      delete m;
+      return fail(WF_EINVAL, "schedule and config disagree on the grid size");
+    }
+    m->net = std::move(sched->net);
+    delete sched;
+  } else if (build_network(ldd, cfg->nrow, cfg->ncol, m->net) != 0) {
     delete m;
     return fail(WF_ECYCLE, "could not build the drainage network");
   }
@@ -289,8 +330,10 @@ int wf_create(const wf_config *cfg, const uint8_t *ldd, const uint8_t *river, wf
   if ((rc = upload(topo.data(), n, (void **)&dm.topo))) return rc;
   if ((rc = upload(m->river_slot.data(), sizeof(int32_t) * n, (void **)&dm.river_slot))) return rc;
   dm.lev_off = m->d_lev_off;
-  CUDA_OK(cudaMalloc(&dm.h_r, sizeof(float) * std::max<int64_t>(n, 1)));
+  CUDA_OK(cudaMalloc(&dm.h_r, sizeof(double) * std::max<int64_t>(n, 1)));
   CUDA_OK(cudaMalloc(&dm.h_surplus, sizeof(float) * std::max<int64_t>(n, 1)));
+  CUDA_OK(cudaMalloc(&dm.h_ssf, sizeof(double) * std::max<int64_t>(n, 1)));
+  CUDA_OK(cudaMalloc(&dm.h_ulo, sizeof(float) * (size_t)m->ML * std::max<int64_t>(n, 1)));
   CUDA_OK(cudaMalloc(&dm.h_inwaterMM, sizeof(float) * std::max<int32_t>(m->nr, 1)));
   if (dm.itL > 1) CUDA_OK(cudaMalloc(&dm.qo_sub, sizeof(float) * (size_t)(dm.itL - 1) * std::max<int64_t>(n, 1)));
   if (dm.itR > 1) CUDA_OK(cudaMalloc(&dm.qr_sub, sizeof(float) * (size_t)(dm.itR - 1) * std::max<int32_t>(m->nr, 1)));
@@ -310,10 +353,14 @@ void wf_destroy(wf_model *m) {
   if (!m) return;
   cudaSetDevice(m->cfg.device);
   cudaStreamSynchronize(m->stream);
-  for (int id = 0; id < F_COUNT; id++) cudaFree(m->dm.f[id]);
+  for (int id = 0; id < F_COUNT; id++) {
+    if (m->external[id]) cudaFree(m->owned[id]);
+    else cudaFree(m->dm.f[id]);
+  }
+  for (cudaEvent_t e : m->tev) cudaEventDestroy(e);
   for (float *p : m->snapshot) cudaFree(p);
   for (auto &a : m->areas) { cudaFree(a.d_perm); cudaFree(a.d_seg); }
-  cudaFree(m->dm.h_r); cudaFree(m->dm.h_surplus); cudaFree(m->dm.h_inwaterMM); cudaFree(m->dm.h_wb);
+  cudaFree(m->dm.h_r); cudaFree(m->dm.h_surplus); cudaFree(m->dm.h_ulo); cudaFree(m->dm.h_ssf); cudaFree(m->dm.h_inwaterMM); cudaFree(m->dm.h_wb);
   cudaFree(m->dm.qo_sub); cudaFree(m->dm.qr_sub);
   cudaFree((void *)m->dm.up_start); cudaFree((void *)m->dm.topo); cudaFree((void *)m->dm.river_slot);
   cudaFree(m->d_order); cudaFree(m->d_rorder); cudaFree(m->d_lev_off); cudaFree(m->d_stage);
@@ -363,16 +410,7 @@ int wf_get_network(const wf_model *m, int which, int64_t *nodes, int64_t *nodes_
 
 int wf_catchment_total(const wf_model *m, const float *values, double *out_grid) {
   if (!m || !out_grid) return fail(WF_EINVAL, "null argument");
-  const Network &net = m->net;
-  const int64_t N = (int64_t)net.nrow * net.ncol;
-  for (int64_t i = 0; i < N; i++) out_grid[i] = 0.0;
-  std::vector<double> acc((size_t)std::max<int64_t>(net.ncells, 1));
-  for (int64_t k = 0; k < net.ncells; k++) {  // level order: upstream cells are complete before k
-    double v = values ? (double)values[net.order[(size_t)k]] : 1.0;
-    for (int j = 0; j < net.nup[(size_t)k]; j++) v += acc[(size_t)net.up_start[(size_t)k] + j];
-    acc[(size_t)k] = v;
-    out_grid[net.order[(size_t)k]] = v;
-  }
+  catchment_total(m->net, values, out_grid);
   return WF_OK;
 }
 
@@ -518,10 +556,56 @@ int wf_synchronize(wf_model *m) {
 int wf_last_step_ms(wf_model *m, float ms[3]) {
   if (!m || !ms) return fail(WF_EINVAL, "null argument");
   CUDA_OK(cudaSetDevice(m->cfg.device));
-  CUDA_OK(cudaEventSynchronize(m->ev[2]));
-  CUDA_OK(cudaEventElapsedTime(&ms[0], m->ev[0], m->ev[1]));
-  CUDA_OK(cudaEventElapsedTime(&ms[1], m->ev[1], m->ev[2]));
-  CUDA_OK(cudaEventElapsedTime(&ms[2], m->ev[0], m->ev[2]));
+  if (!m->ev_last[2]) return fail(WF_EINVAL, "no step has run yet");
+  CUDA_OK(cudaEventSynchronize(m->ev_last[2]));
+  CUDA_OK(cudaEventElapsedTime(&ms[0], m->ev_last[0], m->ev_last[1]));
+  CUDA_OK(cudaEventElapsedTime(&ms[1], m->ev_last[1], m->ev_last[2]));
+  CUDA_OK(cudaEventElapsedTime(&ms[2], m->ev_last[0], m->ev_last[2]));
+  return WF_OK;
+}
+
+int wf_timing_reset(wf_model *m) {
+  if (!m) return fail(WF_EINVAL, "null model");
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  CUDA_OK(cudaStreamSynchronize(m->stream));
+  const size_t want = 3 * 4096;
+  while (m->tev.size() < want) {
+    cudaEvent_t e;
+    CUDA_OK(cudaEventCreate(&e));
+    m->tev.push_back(e);
+  }
+  m->tev_used = 0;
+  return WF_OK;
+}
+
+int wf_timing_get(wf_model *m, double ms[3], int64_t *nsteps) {
+  if (!m || !ms) return fail(WF_EINVAL, "null argument");
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  CUDA_OK(cudaStreamSynchronize(m->stream));
+  ms[0] = ms[1] = ms[2] = 0.0;
+  for (size_t i = 0; i + 3 <= m->tev_used; i += 3) {
+    float a = 0, b = 0;
+    CUDA_OK(cudaEventElapsedTime(&a, m->tev[i], m->tev[i + 1]));
+    CUDA_OK(cudaEventElapsedTime(&b, m->tev[i + 1], m->tev[i + 2]));
+    ms[0] += a; ms[1] += b; ms[2] += a + b;
+  }
+  if (nsteps) *nsteps = (int64_t)(m->tev_used / 3);
+  return WF_OK;
+}
+
+int wf_bind_field(wf_model *m, const char *name, float *dptr) {
+  if (!m) return fail(WF_EINVAL, "null model");
+  const int id = field_index(name);
+  if (id < 0) return fail(WF_EINVAL, std::string("unknown field: ") + (name ? name : "(null)"));
+  if (dptr) {
+    if (!m->external[id]) m->owned[id] = m->dm.f[id];
+    m->dm.f[id] = dptr;
+    m->external[id] = true;
+  } else if (m->external[id]) {
+    m->dm.f[id] = m->owned[id];
+    m->owned[id] = nullptr;
+    m->external[id] = false;
+  }
   return WF_OK;
 }
 

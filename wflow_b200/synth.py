@@ -193,30 +193,80 @@ def base_parameters(nrow, ncol, seed=42, block=64, n_layers=4):
 
 
 class Forcing:
-    """Per-step P / PET / TEMP rasters (SURVEY.md §8d config 2 definition)."""
+    """Per-step P / PET / TEMP rasters: spatially smooth rain cells over ~40 % of the grid with an
+    exponential-like intensity distribution (mean of wet cells ~`rain_mean` mm/day, tail to
+    ~10x that), sinusoidal PET and a temperature wave that crosses the snow thresholds."""
 
-    def __init__(self, nrow, ncol, seed=42, timestepsecs=86400):
+    def __init__(self, nrow, ncol, seed=42, timestepsecs=86400, rain_mean=8.0, t_mean=6.0, t_amp=12.0, day0=120.0):
         self.rng = np.random.default_rng(seed + 1)
         self.shape = (nrow, ncol)
         self.scale = F32(timestepsecs / 86400.0)
+        self.steps_per_day = 86400.0 / timestepsecs
         self.pattern = _smooth_noise(self.rng, nrow, ncol, 96)
+        self.rain_mean, self.t_mean, self.t_amp = rain_mean, t_mean, t_amp
+        self.seed = seed
+        self.day0 = day0
 
     def step(self, t):
-        rng = np.random.default_rng(1000003 * (t + 1) + 17)
-        wet = rng.random() > 0.6 or True
-        field = _smooth_noise(rng, *self.shape, coarse=128)
-        dry = field < F32(0.6)  # 60 % dry
-        p = (-np.log1p(-np.minimum(field, F32(0.999))) * F32(6.0)).astype(F32)
-        p[dry] = 0.0
+        rng = np.random.default_rng(1000003 * (t + 1) + 17 + self.seed)
+        field = _smooth_noise(rng, *self.shape, coarse=32)
+        u = np.clip((field - F32(0.5)) * F32(4.0), F32(0.0), F32(0.999))  # 0 on the dry part
+        p = (-np.log1p(-u) * F32(self.rain_mean * 1.5) * F32(rng.uniform(0.2, 2.0))).astype(F32)
         p = (p * self.scale).astype(F32)
-        pet = np.full(self.shape, (2.0 + 1.5 * np.sin(2 * np.pi * t / 365.0)), F32) * self.scale
-        temp = np.full(self.shape, 8.0 + 12.0 * np.sin(2 * np.pi * (t - 100) / 365.0), F32) + (self.pattern - F32(0.5)) * F32(4.0)
-        del wet
+        day = self.day0 + t / self.steps_per_day
+        pet = np.full(self.shape, (2.0 + 1.5 * np.sin(2 * np.pi * day / 365.0)), F32) * self.scale
+        temp = (np.full(self.shape, self.t_mean + self.t_amp * np.sin(2 * np.pi * (day - 100) / 365.0), F32)
+                + (self.pattern - F32(0.5)) * F32(8.0) + F32(rng.normal(0, 3)))
         return p.astype(F32), pet.astype(F32), temp.astype(F32)
 
 
+def random_state(static, n_layers, layer_thickness, seed=0):
+    """A physically consistent but well-mixed initial state (instead of the cold start): water
+    tables from the surface to the bottom, partly filled unsaturated layers, snow packs, wet
+    canopies, flowing rivers and land.  Exercises the branches a cold start never reaches."""
+    rng = np.random.default_rng(seed)
+    st = static["SoilThickness"]
+    shape = st.shape
+    neff = (static["thetaS"] - static["thetaR"]).astype(F32)
+    u = rng.random(shape).astype(F32)
+    zi = (st * np.where(u < 0.15, F32(0.0) + u * F32(0.2), u)).astype(F32)   # 15 % (nearly) saturated
+    zi[rng.random(shape) < 0.03] = 0.0
+    state = params.cold_state(static, n_layers)
+    state["zi"] = zi
+    state["SatWaterDepth"] = (neff * (st - zi)).astype(F32)
+    fabs = np.abs(static["f"])
+    state["SubsurfaceFlow"] = (((static["KsatHorFrac"] * static["KsatVer"] * static["landSlope"]) / fabs)
+                               * (np.exp(-fabs * zi) - np.exp(-fabs * st)) * static["DW"] * F32(1000.0)).astype(F32)
+    # unsaturated storage: fill each layer above the water table to a random fraction of capacity
+    tops = np.zeros(shape, F32)
+    thick_list = list(layer_thickness)
+    for k in range(n_layers):
+        if k < len(thick_list):
+            th = np.minimum(F32(thick_list[k]), np.maximum(st - tops, 0)).astype(F32)
+        else:
+            th = np.maximum(st - tops, 0).astype(F32)
+        unsat = np.clip(zi - tops, 0, th).astype(F32)
+        state["UStoreLayerDepth_%d" % k] = (unsat * neff * rng.random(shape).astype(F32) * F32(0.95)).astype(F32)
+        tops = (tops + th).astype(F32)
+    wet = rng.random(shape) < 0.3
+    state["LandRunoffsub"] = np.where(wet, np.exp(rng.uniform(np.log(1e-5), np.log(0.5), shape)), 0).astype(F32)
+    state["LandRunoff"] = state["LandRunoffsub"].copy()
+    state["WaterLevelL"] = np.where(wet, rng.uniform(0, 0.01, shape), 0).astype(F32)
+    river = static["River"] != 0
+    state["RiverRunoffsub"] = np.where(river, np.exp(rng.uniform(np.log(1e-3), np.log(300.0), shape)), 0).astype(F32)
+    state["RiverRunoff"] = state["RiverRunoffsub"].copy()
+    state["WaterLevelR"] = np.where(river, rng.uniform(0.01, 2.0, shape), 0).astype(F32)
+    state["WaterLevelRsub"] = state["WaterLevelR"].copy()
+    snowy = rng.random(shape) < 0.35
+    state["Snow"] = np.where(snowy, rng.uniform(0, 80, shape), 0).astype(F32)
+    state["SnowWater"] = (state["Snow"] * rng.uniform(0, 0.1, shape)).astype(F32)
+    state["TSoil"] = rng.uniform(-6, 12, shape).astype(F32)
+    state["CanopyStorage"] = (static["Cmax"] * rng.uniform(0, 1.3, shape)).astype(F32)
+    return state
+
+
 def make_case(nrow, ncol, *, kind="pits", tile=1024, seed=42, timestepsecs=86400, layer_thickness=(100, 300, 800),
-              river_area=500, mask_frac=0.0):
+              river_area=500, mask_frac=0.0, init="cold", block=64):
     """Assemble (ldd, river, static, state) for a synthetic case."""
     if kind == "pits":
         ldd = ldd_all_pits(nrow, ncol)
@@ -230,10 +280,13 @@ def make_case(nrow, ncol, *, kind="pits", tile=1024, seed=42, timestepsecs=86400
     else:
         raise ValueError(kind)
     n_layers = len(layer_thickness) + 1 if len(layer_thickness) else 1
-    base = base_parameters(nrow, ncol, seed=seed, n_layers=n_layers)
+    base = base_parameters(nrow, ncol, seed=seed, n_layers=n_layers, block=block)
     up = upstream_count(ldd).astype(F32)
     base["RiverWidth"] = np.where(river != 0, F32(2.0) * np.power(np.maximum(up, 1), F32(0.35)), F32(0.0)).astype(F32)
     base["BankfullDepth"] = np.where(river != 0, F32(1.0), F32(0.0)).astype(F32)
     static = params.derive_static(base, ldd, river, timestepsecs, cellsize=1000.0, n_layers=n_layers)
-    state = params.cold_state(static, n_layers)
+    if init == "cold":
+        state = params.cold_state(static, n_layers)
+    else:
+        state = random_state(static, n_layers, layer_thickness, seed=seed + 7)
     return ldd, river, static, state
