@@ -155,6 +155,15 @@ int wf_area_reduce(wf_model *m, int area, const char *field, int op, float *out 
 /* Sample a field at cells (gauges): out[i] = field[flat_index[i]] (mv outside the network). */
 int wf_sample(wf_model *m, const char *field, const int64_t *flat_index, int64_t n, float *out, float mv);
 
+/* --- batched solvers ----------------------------------------------------------------------
+ * The two Newton solvers of the path, exposed on their own so that they can be checked against
+ * the reference's scalar functions: kinematic_wave(Qin, Qold, q, alpha, beta, deltaT, deltaX)
+ * (wflow/wflow_funcs.py:119-152) and kinematic_wave_ssf(ssf_in, ssf_old, zi_old, r, Ks_hor, Ks,
+ * slope, neff, f, D, dt, dx, w, ssf_max) -> (ssf, zi, exfilt) (wflow/wflow_funcs.py:210-292).
+ * args: HOST arrays of n float64 each (7 resp. 14 of them); out: HOST array n resp. 3*n. */
+int wf_kinematic_wave_batch(int device, int64_t n, const double *const *args, double *out);
+int wf_kinematic_wave_ssf_batch(int device, int64_t n, const double *const *args, double *out);
+
 /* --- one-step rollback ------------------------------------------------------------------
  * Replaces wf_QuickSuspend / wf_QuickResume (wflow/wf_DynamicFramework.py:2131-2175), used by
  * BMI update_until() to step back once: a device-side snapshot of all states. */

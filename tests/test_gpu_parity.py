@@ -206,3 +206,22 @@ def test_missing_field_is_an_error():
         mod.step()
     with pytest.raises(_lib.WflowLibError):
         mod.set("NoSuchField", np.zeros((4, 4), np.float32))
+
+
+def test_newton_solvers_match_reference_golden():
+    """The two float64 solvers against the reference's scalar functions (rel 1e-9 where float64 is
+    kept; they agree to ~1e-12)."""
+    from wflow_b200 import core
+    g = np.load(common.GOLD + "/kinwave.npz")
+    out = core.kinematic_wave(g["Qin"], g["Qold"], g["q"], g["alpha"], g["beta"], g["dT"], g["dX"])
+    ref = g["out"]
+    assert np.array_equal(out == 0, ref == 0)  # the zero early-out
+    rel = np.abs(out - ref) / np.maximum(np.abs(ref), 1e-300)
+    assert rel.max() < 1e-9, float(rel.max())
+    g = np.load(common.GOLD + "/kinwave_ssf.npz")
+    out = core.kinematic_wave_ssf(*g["args"])
+    ref = g["out"]
+    ok = np.isfinite(ref).all(axis=1)
+    scale = np.maximum(np.abs(ref[ok]), [1.0, 1e-3, 1e-6])
+    rel = np.abs(out[ok] - ref[ok]) / scale
+    assert rel.max() < 1e-9, rel.max(axis=0)

@@ -40,7 +40,7 @@ SYMBOLS = [
     "wf_area_ids", "wf_area_reduce", "wf_sample", "wf_quick_suspend", "wf_quick_resume",
     "wf_schedule_create", "wf_schedule_destroy", "wf_schedule_num_cells", "wf_schedule_num_levels",
     "wf_schedule_get", "wf_schedule_catchment_total", "wf_create_from_schedule", "wf_bind_field",
-    "wf_timing_reset", "wf_timing_get",
+    "wf_timing_reset", "wf_timing_get", "wf_kinematic_wave_batch", "wf_kinematic_wave_ssf_batch",
 ]
 
 
@@ -103,6 +103,8 @@ def lib():
     l.wf_bind_field.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
     l.wf_timing_reset.argtypes = [C.c_void_p]
     l.wf_timing_get.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    l.wf_kinematic_wave_batch.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
+    l.wf_kinematic_wave_ssf_batch.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
     l.wf_quick_suspend.argtypes = [C.c_void_p]
     l.wf_quick_resume.argtypes = [C.c_void_p]
     _lib = l

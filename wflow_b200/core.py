@@ -31,6 +31,28 @@ def build_schedule(ldd):
     return nodes[:n], up[: n * 8].reshape(n, 8), off
 
 
+def _solver_batch(fn, args, nout, device):
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in args]
+    n = arrs[0].size
+    ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    out = np.zeros(n * nout, np.float64)
+    _lib.check(fn(int(device), n, ptrs, out.ctypes.data))
+    return out if nout == 1 else out.reshape(n, nout)
+
+
+def kinematic_wave(Qin, Qold, q, alpha, beta, deltaT, deltaX, device=0):
+    """Batched kinematic_wave on the GPU (reference: wflow/wflow_funcs.py:119-152)."""
+    return _solver_batch(_lib.lib().wf_kinematic_wave_batch, [Qin, Qold, q, alpha, beta, deltaT, deltaX], 1, device)
+
+
+def kinematic_wave_ssf(*args, device=0):
+    """Batched kinematic_wave_ssf on the GPU (reference: wflow/wflow_funcs.py:210-292);
+    returns an (n, 3) array of (ssf, zi, exfilt)."""
+    if len(args) != 14:
+        raise ValueError("kinematic_wave_ssf takes 14 arrays")
+    return _solver_batch(_lib.lib().wf_kinematic_wave_ssf_batch, list(args), 3, device)
+
+
 class Schedule:
     """Host-only level schedule (no GPU needed).  Can be handed to SbmModel(schedule=...) so the
     network is built once when a quantity derived from it (e.g. the river mask from the upstream

@@ -12,6 +12,7 @@
 #include "../../include/wflow_sbm.h"
 #include "fields.h"
 #include "kernels.cuh"
+#include "lateral.cuh"
 #include "network.h"
 #include "reduce.cuh"
 
@@ -75,6 +76,7 @@ struct wf_model {
   std::vector<AreaSet> areas;
   int64_t launches = 0;
   int coop_blocks = 0;
+  int64_t max_tick_items = 1;
   bool timed = false;
   int ML = 1;
   bool external[F_COUNT] = {};        // field bound to a caller-owned device array
@@ -111,25 +113,19 @@ int launch_step(wf_model *m) {
   k_vertical<ML><<<(unsigned)((n + tb - 1) / tb), tb, 0, m->stream>>>(m->dm);
   m->launches++;
   if (m->timed) cudaEventRecord(e1, m->stream);
-  if (m->dm.nlev == 1) {
-    const int lb = 256;
-    k_lateral_one_level<ML><<<(unsigned)((n + lb - 1) / lb), lb, 0, m->stream>>>(m->dm, 0, n);
-  } else {
+  {
     if (m->coop_blocks == 0) {
       int dev = 0, sms = 0, per_sm = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lateral<ML>, 256, 0);
-      if (per_sm < 1) return fail(WF_ENODEVICE, "k_lateral does not fit on an SM");
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lateral_wave<ML>, 256, 0);
+      if (per_sm < 1) return fail(WF_ENODEVICE, "k_lateral_wave does not fit on an SM");
       m->coop_blocks = sms * per_sm;
     }
-    // no more blocks than the widest level can use
-    int64_t widest = 1;
-    for (size_t l = 0; l + 1 < m->net.lev_off.size(); l++)
-      widest = std::max(widest, m->net.lev_off[l + 1] - m->net.lev_off[l]);
-    int blocks = (int)std::min<int64_t>(m->coop_blocks, (widest + 255) / 256);
+    // no more blocks than the busiest tick can use (subsurface + overland + river items)
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(m->coop_blocks, (m->max_tick_items + 255) / 256));
     void *args[] = {(void *)&m->dm};
-    CUDA_OK(cudaLaunchCooperativeKernel((void *)k_lateral<ML>, dim3(blocks), dim3(256), args, 0, m->stream));
+    CUDA_OK(cudaLaunchCooperativeKernel((void *)k_lateral_wave<ML>, dim3(blocks), dim3(256), args, 0, m->stream));
   }
   m->launches++;
   if (m->timed) cudaEventRecord(e2, m->stream);
@@ -335,6 +331,35 @@ int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint
   CUDA_OK(cudaMalloc(&dm.h_ssf, sizeof(double) * std::max<int64_t>(n, 1)));
   CUDA_OK(cudaMalloc(&dm.h_ulo, sizeof(float) * (size_t)m->ML * std::max<int64_t>(n, 1)));
   CUDA_OK(cudaMalloc(&dm.h_inwaterMM, sizeof(float) * std::max<int32_t>(m->nr, 1)));
+  CUDA_OK(cudaMalloc(&dm.h_inwO, sizeof(double) * std::max<int64_t>(n, 1)));
+  CUDA_OK(cudaMalloc(&dm.h_ssf_tr, sizeof(float) * std::max<int32_t>(m->nr, 1)));
+  CUDA_OK(cudaMalloc(&dm.h_inwater, sizeof(float) * std::max<int32_t>(m->nr, 1)));
+  CUDA_OK(cudaMalloc(&dm.h_racc, sizeof(double) * std::max<int32_t>(m->nr, 1)));
+  CUDA_OK(cudaMalloc(&dm.h_rh, sizeof(double) * std::max<int32_t>(m->nr, 1)));
+  {
+    // river schedule in river order (= rnet order for the first nrnet cells)
+    int64_t *d_rlev = nullptr;
+    if ((rc = upload(m->rnet.lev_off.data(), sizeof(int64_t) * m->rnet.lev_off.size(), (void **)&d_rlev))) return rc;
+    dm.rlev_off = d_rlev;
+    if ((rc = upload(m->rnet.up_start.data(), sizeof(uint32_t) * m->rnet.ncells, (void **)&dm.r_up_start))) return rc;
+    if ((rc = upload(m->rnet.nup.data(), m->rnet.ncells, (void **)&dm.r_nup))) return rc;
+    dm.nrlev = (int32_t)m->rnet.nlevels();
+    dm.rlev_shift = dm.nlev - dm.nrlev;
+    // busiest tick of the wavefront
+    const int D = dm.nlev;
+    int64_t best = 1;
+    for (int t = 0; t < D + 1 + dm.itR; t++) {
+      int64_t items = 0;
+      if (t < D) items += m->net.lev_off[(size_t)t + 1] - m->net.lev_off[(size_t)t];
+      if (t >= 1 && t - 1 < D) items += m->net.lev_off[(size_t)t] - m->net.lev_off[(size_t)t - 1];
+      for (int v = 0; v < dm.itR; v++) {
+        const int lr = (t - 2 - v) - dm.rlev_shift;
+        if (lr >= 0 && lr < dm.nrlev) items += m->rnet.lev_off[(size_t)lr + 1] - m->rnet.lev_off[(size_t)lr];
+      }
+      best = std::max(best, items);
+    }
+    m->max_tick_items = best;
+  }
   if (dm.itL > 1) CUDA_OK(cudaMalloc(&dm.qo_sub, sizeof(float) * (size_t)(dm.itL - 1) * std::max<int64_t>(n, 1)));
   if (dm.itR > 1) CUDA_OK(cudaMalloc(&dm.qr_sub, sizeof(float) * (size_t)(dm.itR - 1) * std::max<int32_t>(m->nr, 1)));
   // states exist from the start (zero = the reference's cold ZeroMap)
@@ -360,7 +385,9 @@ void wf_destroy(wf_model *m) {
   for (cudaEvent_t e : m->tev) cudaEventDestroy(e);
   for (float *p : m->snapshot) cudaFree(p);
   for (auto &a : m->areas) { cudaFree(a.d_perm); cudaFree(a.d_seg); }
-  cudaFree(m->dm.h_r); cudaFree(m->dm.h_surplus); cudaFree(m->dm.h_ulo); cudaFree(m->dm.h_ssf); cudaFree(m->dm.h_inwaterMM); cudaFree(m->dm.h_wb);
+  cudaFree(m->dm.h_r); cudaFree(m->dm.h_surplus); cudaFree(m->dm.h_ulo); cudaFree(m->dm.h_ssf);
+  cudaFree(m->dm.h_inwO); cudaFree(m->dm.h_ssf_tr); cudaFree(m->dm.h_inwater); cudaFree(m->dm.h_racc); cudaFree(m->dm.h_rh);
+  cudaFree((void *)m->dm.rlev_off); cudaFree((void *)m->dm.r_up_start); cudaFree((void *)m->dm.r_nup); cudaFree(m->dm.h_inwaterMM); cudaFree(m->dm.h_wb);
   cudaFree(m->dm.qo_sub); cudaFree(m->dm.qr_sub);
   cudaFree((void *)m->dm.up_start); cudaFree((void *)m->dm.topo); cudaFree((void *)m->dm.river_slot);
   cudaFree(m->d_order); cudaFree(m->d_rorder); cudaFree(m->d_lev_off); cudaFree(m->d_stage);
@@ -716,6 +743,33 @@ int wf_sample(wf_model *m, const char *field, const int64_t *flat_index, int64_t
   cudaFree(d_pos);
   cudaFree(d_out);
   return WF_OK;
+}
+
+// ---- batched solvers -----------------------------------------------------------------------
+static int solver_batch(int device, int64_t n, const double *const *args, int nargs, int nout, double *out, bool ssf) {
+  if (!args || !out || n < 0) return fail(WF_EINVAL, "bad argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail(WF_ENODEVICE, "no CUDA device available (this library has no CPU fallback)");
+  if (n == 0) return WF_OK;
+  CUDA_OK(cudaSetDevice(device));
+  double *d_a = nullptr, *d_o = nullptr;
+  CUDA_OK(cudaMalloc(&d_a, sizeof(double) * n * nargs));
+  CUDA_OK(cudaMalloc(&d_o, sizeof(double) * n * nout));
+  for (int k = 0; k < nargs; k++) CUDA_OK(cudaMemcpy(d_a + (size_t)k * n, args[k], sizeof(double) * n, cudaMemcpyHostToDevice));
+  if (ssf) k_kinwave_ssf_batch<<<(unsigned)((n + 127) / 128), 128>>>(n, d_a, d_o);
+  else k_kinwave_batch<<<(unsigned)((n + 127) / 128), 128>>>(n, d_a, d_o);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpy(out, d_o, sizeof(double) * n * nout, cudaMemcpyDeviceToHost));
+  cudaFree(d_a);
+  cudaFree(d_o);
+  return WF_OK;
+}
+int wf_kinematic_wave_batch(int device, int64_t n, const double *const *args, double *out) {
+  return solver_batch(device, n, args, 7, 1, out, false);
+}
+int wf_kinematic_wave_ssf_batch(int device, int64_t n, const double *const *args, double *out) {
+  return solver_batch(device, n, args, 14, 3, out, true);
 }
 
 // ---- one-step rollback -------------------------------------------------------------------

@@ -1,0 +1,419 @@
+// Lateral flow: the level-ordered kinematic waves as a skewed wavefront.
+//
+// The reference walks the network three times per timestep, serially, upstream to downstream:
+// subsurface flow inside sbm_cell (wflow/wflow_sbm.py:370-821), overland flow (:823-883) and the
+// river (kin_wave, wflow/wflow_funcs.py:155-207, once per sub-step).  The dependencies are
+//     subsurface(level l)      <- subsurface(l-1)
+//     overland(l)              <- overland(l-1), subsurface(l)            (InwaterO of the cell)
+//     river(l, sub-step v)     <- river(l-1, v), river(l, v-1), overland(l-1), subsurface(l-1)
+// so one persistent cooperative kernel advances a wavefront: at tick t it solves
+//     subsurface for level t, overland for level t-1, river sub-step v for level t-2-v,
+// all concurrently in different warps, one grid barrier per tick: D + 1 + it_kinR ticks whose
+// critical path is ONE Newton solve instead of the reference's (2 + it_kinR) * D serial solves.
+//
+// Inside a level the cells are contiguous in network order and so are each cell's upstream
+// neighbours (network.h): every load of a level is coalesced, the inflow gather is a short
+// contiguous run read with ld.global.cg (written by other SMs one tick earlier).
+#pragma once
+#include "kernels.cuh"
+
+namespace wf {
+
+// x^b for x >= 0 as exp(b*log(x)): the two CUDA double routines are each accurate to ~1 ulp, the
+// result to ~1e-15 relative -- three times cheaper than pow()'s correctly rounded path, far inside
+// the 1e-9 the float64 quantities are held to.  x = 0 gives 0 (b > 0) or inf (b < 0) like pow.
+__device__ __forceinline__ double pow_el(double x, double b) { return exp(b * log(x)); }
+
+// kinematic_wave, wflow/wflow_funcs.py:119-152.
+// The reference's Newton iteration converges to the root of  dT/dX*Q + alpha*Q^beta = C  to
+// rounding (it only stops on |f| <= 1e-12 or its 3000-iteration cap), so the result is a property
+// of the equation, not of the path.  Here: float64 constant term C, a float32 Newton run from the
+// reference's own first guess to get within ~1e-6, then float64 Newton steps until |f| <= 1e-12
+// or the step falls below 2 ulp (the reference's iterates only wander in rounding noise from
+// there).  Agreement with the reference: a few ulp (tests: 1e-12 relative).
+// Also returns Q^beta at the solution (for the water level), by first-order correction.
+__device__ __noinline__ double kinematic_wave(double Qin, double Qold, double q, double alpha, double beta,
+                                              double deltaT, double deltaX, double &Qbeta) {
+  Qbeta = 0.0;
+  if ((Qin + Qold + q) == 0.0) return 0.0;
+  const double deltaTX = deltaT / deltaX;
+  const double C = deltaTX * Qin + alpha * pow_el(Qold, beta) + deltaT * q;
+  // first guess and float32 iterations
+  const float a32 = (float)alpha, b32 = (float)beta, dtx32 = (float)deltaTX, C32 = (float)C;
+  const float ab_pQ = a32 * b32 * powf((float)((Qold + Qin) / 2.0), b32 - 1.0f);
+  float Qf = ((float)(deltaTX * Qin) + (float)Qold * ab_pQ + (float)(deltaT * q)) / (dtx32 + ab_pQ);
+  if (isnan(Qf)) Qf = 0.0f;
+  Qf = fmaxf(Qf, 1e-30f);
+#pragma unroll 1
+  for (int it = 0; it < 12; it++) {
+    const float qb = powf(Qf, b32);
+    const float f = dtx32 * Qf + a32 * qb - C32;
+    const float df = dtx32 + a32 * b32 * (qb / Qf);
+    const float Qn = fmaxf(Qf - f / df, 1e-30f);
+    const bool done = fabsf(Qn - Qf) <= 2e-6f * Qn;
+    Qf = Qn;
+    if (done) break;
+  }
+  double Qkx = (double)Qf;
+  double qb = 0.0, Qprev = Qkx;
+#pragma unroll 1
+  for (int it = 0; it < 60; it++) {
+    qb = pow_el(Qkx, beta);
+    const double f = deltaTX * Qkx + alpha * qb - C;
+    const double df = deltaTX + alpha * beta * (qb / Qkx);
+    const double Qn = fmax(Qkx - f / df, 1e-30);
+    const bool stalled = fabs(Qn - Qkx) <= 4.440892098500626e-16 * Qn;
+    Qprev = Qkx;
+    Qkx = Qn;
+    if (fabs(f) <= 1e-12 || stalled) break;
+  }
+  Qbeta = qb + beta * (qb / Qprev) * (Qkx - Qprev);  // Q^beta at Qkx, O((dQ/Q)^2) accurate
+  return Qkx;
+}
+
+// kinematic_wave_ssf, wflow/wflow_funcs.py:210-292.  Literal iteration (the returned zi is the one
+// computed from the LAST-BUT-ONE iterate, so the path matters); only loop-invariant quotients are
+// hoisted and the loop also stops when the Newton step falls below 2 ulp.
+__device__ __noinline__ void kinematic_wave_ssf(double ssf_in, double ssf_old, double zi_old, double r,
+                                                double Ks_hor, double Ks, double slope, double neff, double f,
+                                                double D, double efD, double dt, double dx, double w, double ssf_max,
+                                                double &ssf_out, double &zi_out, double &exfilt_out) {
+  const double epsilon = 1e-3;
+  const int MAX_ITERS = 3000;
+  if ((ssf_in + ssf_old) == 0.0 && (r <= 0)) {
+    ssf_out = 0.0; zi_out = D; exfilt_out = 0.0;
+    return;
+  }
+  double ssf_n = (ssf_old + ssf_in) / 2.0;
+  int count = 0;
+  const double den = w * Ks_hor * Ks * slope;
+  const double dtdx = dt / dx;
+  const double khs = Ks_hor * Ks;
+  double zi = log((f * ssf_n) / den + efD) / -f;
+  double Cn = (khs * exp(-f * zi) * slope) / neff;
+  double invCn = 1.0 / Cn;
+  double c = dtdx * ssf_in + invCn * ssf_n + dt * (r - (zi_old - zi) * neff * w);
+  double fQ = dtdx * ssf_n + invCn * ssf_n - c;
+  double dfQ = dtdx + 1 / Cn;
+  ssf_n = ssf_n - (fQ / dfQ);
+  if (isnan(ssf_n)) ssf_n = 0.0;
+  ssf_n = pymax(ssf_n, 1e-30);
+  while (fabs(fQ) > epsilon && count < MAX_ITERS) {
+    zi = log((f * ssf_n) / den + efD) / -f;
+    Cn = (khs * exp(-f * zi) * slope) / neff;
+    invCn = 1.0 / Cn;
+    c = dtdx * ssf_in + invCn * ssf_n + dt * (r - (zi_old - zi) * neff * w);
+    fQ = dtdx * ssf_n + invCn * ssf_n - c;
+    dfQ = dtdx + invCn;
+    double sn = ssf_n - (fQ / dfQ);
+    if (isnan(sn)) sn = 0.0;
+    sn = pymax(sn, 1e-30);
+    const bool stalled = fabs(sn - ssf_n) <= 4.440892098500626e-16 * sn;
+    ssf_n = sn;
+    count++;
+    if (stalled) break;
+  }
+  ssf_n = pymin(ssf_n, (ssf_max * w));
+  const double rest = zi_old - (ssf_in + r * dx - ssf_n) / (w * dx) / neff;
+  exfilt_out = pymin(rest, 0.0) * -neff;
+  zi_out = pymax(0.0, zi);
+  ssf_out = ssf_n;
+}
+
+// Fraction of an upstream neighbour's outflow that a river cell takes straight into the channel
+// (wflow_sbm.py:395-398, 843-846): slope-weighted for neighbours that drain in another direction.
+__device__ __forceinline__ double chan_perc(const DevModel &m, int64_t nb, int myldd, double slope_i) {
+  const int lnb = __ldg(m.topo + nb) & 15;
+  if (lnb == myldd) return 0.0;
+  const double slnb = (double)__ldg(m.f[F_landSlope] + nb);
+  return slnb / (slope_i + slnb);
+}
+
+// ---- task 1: subsurface flow + post-ssf column tail of one cell ------------------------------
+template <int ML>
+__device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t i) {
+  const uint8_t tp = __ldg(m.topo + i);
+  const int nup = tp >> 4;
+  const int myldd = tp & 15;
+  const uint32_t us = __ldg(m.up_start + i);
+  const int32_t rs = __ldg(m.river_slot + i);
+  const bool riverMap = rs >= 0;
+  const double slope_i = LD(landSlope);
+  // own-cell operands first (independent of the gather): the loads overlap the inflow latency
+  const double ST = LD(SoilThickness), thetaS = LD(thetaS), thetaR = LD(thetaR);
+  const float neff_f = LD(thetaS) - LD(thetaR);
+  const double KsatVer = LD(KsatVer), fpar = LD(f), Kh = LD(KsatHorFrac);
+  const double DW = LD(DW), DLd = LD(DL);
+  const double zi_old = m.f[F_zi][i];
+  const double rsum = m.h_r[i];
+  float *const ssfp = m.f[F_SubsurfaceFlow];
+  const double ssf_old = ssfp[i];
+  const double surplus = m.h_surplus[i];
+  const double xlyl = (double)LD(xl) * (double)LD(yl);
+  double U[ML];
+#pragma unroll
+  for (int k = 0; k < ML; k++)
+    U[k] = (double)m.f[F_UStoreLayerDepth_0 + k][i] + (double)m.h_ulo[(int64_t)k * m.n + i];
+
+  // inflow gather, reference summation order (wflow_sbm.py:395-410)
+  double ssf_in = 0.0, ssf_tr = 0.0;
+  if (riverMap) {
+#pragma unroll 1
+    for (int j = 0; j < nup; j++) {
+      const int64_t nb = (int64_t)us + j;
+      const double sv = __ldcg(m.h_ssf + nb);
+      const double cp = chan_perc(m, nb, myldd, slope_i);
+      ssf_in = ssf_in + (1 - cp) * sv;
+      ssf_tr = ssf_tr + cp * sv;
+    }
+    m.h_ssf_tr[rs] = (float)(ssf_tr / (1000 * 1000 * 1000) / m.dt);
+  } else {
+#pragma unroll 1
+    for (int j = 0; j < nup; j++) ssf_in = ssf_in + __ldcg(m.h_ssf + (int64_t)us + j);
+  }
+
+  const double neff = (double)neff_f;
+  const double dneff = thetaS - thetaR;
+  const double r = rsum * DW * 1000;                                   // :674
+  const double efD = exp(-fpar * ST);
+  const double ssfmax = ((Kh * KsatVer * slope_i) / fpar) * (1.0 - efD);  // :2291-2299
+  double ssf_n, zi_n, ExfiltSatWater;
+  kinematic_wave_ssf(ssf_in, ssf_old, zi_old, r, Kh, KsatVer, slope_i, neff, fpar, ST, efD, 1.0, DLd * 1000,
+                     DW * 1000, ssfmax, ssf_n, zi_n, ExfiltSatWater);
+  const double zi = pymin(zi_n, ST);  // :702
+  const double Sat = (ST - zi) * dneff;
+  ssfp[i] = (float)ssf_n;
+  m.h_ssf[i] = ssf_n;  // gathered by the downstream cell one tick later
+  m.f[F_zi][i] = (float)zi;
+
+  // post-ssf column tail, :707-821
+  double thick[ML], tops[ML + 1];
+  layer_geometry<ML>(m, ST, thick, tops);
+  const int mc_old = unsat_layers<ML>(zi_old, tops);
+  const int nL = (mc_old > 1) ? mc_old : 1;
+  const int mc_new = unsat_layers<ML>(zi, tops);
+  const int nLn = (mc_new > 1) ? mc_new : 1;
+  double L_new[ML];
+#pragma unroll
+  for (int k = 0; k < ML; k++)
+    L_new[k] = (k < nLn - 1) ? thick[k] : ((k == nLn - 1) ? ((mc_new > 1) ? zi - tops[k] : zi) : 0.0);
+  double ExfiltFromUstore = 0.0;
+  bool changed = false;
+#pragma unroll
+  for (int k = ML - 1; k >= 0; k--) {
+    if (k < nL) {
+      if (k < mc_new) ExfiltFromUstore = pymax(0.0, U[k] - L_new[k] * dneff);
+      else ExfiltFromUstore = U[k];
+      changed |= (ExfiltFromUstore != 0.0);
+      U[k] = U[k] - ExfiltFromUstore;
+      if (k > 0) U[k - 1] = U[k - 1] + ExfiltFromUstore;
+    }
+  }
+  if (changed) {
+#pragma unroll
+    for (int k = 0; k < ML; k++) m.f[F_UStoreLayerDepth_0 + k][i] = (float)U[k];
+  }
+  const double ExfiltWater = ExfiltSatWater + ExfiltFromUstore;
+  // InwaterO :774 -- ExfiltWater + [ExcessWater + InfiltExcess + RunoffLandCells - ActEvapOpenWaterLand]
+  const double InwaterO = pymax(ExfiltWater + surplus, 0.0) * xlyl * 0.001 / m.dt;
+  m.h_inwO[i] = InwaterO;
+
+  double sumU = 0.0;
+#pragma unroll
+  for (int k = 0; k < ML; k++) sumU += U[k];
+  OUTF(SatWaterDepth, Sat); OUTF(UStoreDepth, sumU);
+  OUTF(ssf_toriver, riverMap ? ssf_tr / (1000 * 1000 * 1000) / m.dt : 0.0);
+  OUTF(ExfiltWater, ExfiltWater); OUTF(ExfiltFromUstore, ExfiltFromUstore); OUTF(ExfiltFromSat, ExfiltSatWater);
+  OUTF(InwaterL, InwaterO); OUTF(CellInFlow, ssf_in);
+#pragma unroll
+  for (int k = 0; k < ML; k++) {
+    float *vw = m.f[F_vwc_0 + k];
+    if (vw) {  // :792-803
+      if (k < mc_new) {
+        if (thick[k] > 0) vw[i] = (float)((U[k] + (thick[k] - L_new[k]) * dneff) / thick[k] + thetaR);
+      } else {
+        vw[i] = (float)thetaS;
+      }
+    }
+  }
+  if (m.f[F_RootStore_unsat]) {  // :809-821
+    const double ActRoot = (double)fminf(LD(SoilThickness) * 0.99f, LD(RootingDepth));
+    double rsu = 0.0;
+#pragma unroll
+    for (int k = 0; k < ML; k++)
+      if (k < nLn && L_new[k] > 0) rsu = rsu + (pymax(0.0, ActRoot - tops[k]) / L_new[k]) * U[k];
+    m.f[F_RootStore_unsat][i] = (float)rsu;
+  }
+  if (m.f[F_SoilWatbal] && m.h_wb) {  // :885-898; h_wb holds the cell-local terms (vertical kernel)
+    const double wb = m.h_wb[i] - (Sat + sumU) + (ssf_in - ssf_n) / (DW * DLd * 1000 * 1000) - ExfiltWater;
+    m.f[F_SoilWatbal][i] = (float)wb;
+    if (m.f[F_watbal] && m.f[F_SurfaceWatbal]) m.f[F_watbal][i] = (float)wb + m.f[F_SurfaceWatbal][i];
+  }
+}
+
+// ---- task 2: overland flow of one cell, all sub-steps (wflow_sbm.py:830-879) -----------------
+__device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i) {
+  const uint8_t tp = __ldg(m.topo + i);
+  const int nup = tp >> 4;
+  const int myldd = tp & 15;
+  const uint32_t us = __ldg(m.up_start + i);
+  const int32_t rs = __ldg(m.river_slot + i);
+  const bool riverMap = rs >= 0;
+  const int itL = m.itL;
+  const double SW = LD(SW), AlphaL = LD(AlphaL), Beta = m.beta, DLd = LD(DL);
+  const double dts = m.dt / itL;
+  const double q = __ldcg(m.h_inwO + i) / DLd;
+  double Qold = m.f[F_LandRunoffsub][i];
+  double chanperc[8];
+  if (riverMap) {
+    const double slope_i = LD(landSlope);
+#pragma unroll 1
+    for (int j = 0; j < nup; j++) chanperc[j] = chan_perc(m, (int64_t)us + j, myldd, slope_i);
+  }
+  double acc_flow = 0.0, acc_h = 0.0, Qo_in_acc = 0.0, qo_toriver_acc = 0.0;
+  double wlsub = 0.0;  // dyn["WaterLevelLsub"] starts at 0 and is only written where SW > 0 (:873-878)
+#pragma unroll 1
+  for (int v = 0; v < itL; v++) {
+    float *qbuf = (v == itL - 1) ? m.f[F_LandRunoffsub] : m.qo_sub + (int64_t)v * m.n;
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (riverMap) {
+#pragma unroll 1
+      for (int j = 0; j < nup; j++) {
+        const double qv = (double)__ldcg(qbuf + (int64_t)us + j);
+        s1 = s1 + (1 - chanperc[j]) * qv;
+        s2 = s2 + chanperc[j] * qv;
+        s3 = s3 + qv;
+      }
+    } else {
+#pragma unroll 1
+      for (int j = 0; j < nup; j++) s1 = s1 + (double)__ldcg(qbuf + (int64_t)us + j);
+    }
+    double qo_in, qo_toriver_vol;
+    if (riverMap) {
+      if (SW > 0.0) { qo_in = s1; qo_toriver_vol = s2 * dts; }
+      else { qo_in = 0.0; qo_toriver_vol = s3 * dts; }
+    } else {
+      qo_in = s1; qo_toriver_vol = 0.0;
+    }
+    double qbeta;
+    const double qn = kinematic_wave(qo_in, Qold, q, AlphaL, Beta, dts, DLd, qbeta);
+    acc_flow = acc_flow + qn * dts;
+    Qo_in_acc = Qo_in_acc + qo_in * dts;
+    qo_toriver_acc = qo_toriver_acc + qo_toriver_vol;
+    if (SW > 0) wlsub = (AlphaL * qbeta) / SW;
+    acc_h = acc_h + wlsub;
+    Qold = qn;
+    qbuf[i] = (float)qn;
+  }
+  m.f[F_WaterLevelLsub][i] = (float)wlsub;
+  m.f[F_LandRunoff][i] = (float)(acc_flow / m.dt);
+  m.f[F_WaterLevelL][i] = (float)(acc_h / itL);
+  const float qo_toriver_f = (float)(qo_toriver_acc / m.dt);
+  OUTF(qo_toriver, qo_toriver_f);
+  OUTF(InflowKinWaveCellLand, Qo_in_acc / m.dt);
+
+  if (riverMap) {  // lateral inflow of the channel, wflow_sbm.py:3052-3065, 3144
+    const float dtf = (float)m.dt;
+    const float ToCubic = ((LD(xl) * LD(yl)) * 0.001f) / dtf;  // :1998
+    float Inwater = ((m.h_inwaterMM[rs] * ToCubic) + qo_toriver_f) + __ldcg(m.h_ssf_tr + rs);
+    if (m.f[F_Inflow]) Inwater = Inwater + m.f[F_Inflow][rs];
+    m.h_inwater[rs] = Inwater;
+    if (m.f[F_Inwater]) m.f[F_Inwater][rs] = Inwater;
+    if (rs >= m.nrnet) {  // river-map cell outside the river network: kin_wave never visits it (zeros)
+      m.f[F_RiverRunoff][rs] = 0.0f; m.f[F_WaterLevelR][rs] = 0.0f;
+      m.f[F_RiverRunoffsub][rs] = 0.0f; m.f[F_WaterLevelRsub][rs] = 0.0f;
+    }
+  }
+}
+
+// ---- task 3: one sub-step of the river kinematic wave for one river cell (river order) -------
+// kin_wave, wflow/wflow_funcs.py:155-207; caller glue wflow_sbm.py:3152-3201.
+__device__ __forceinline__ void task_river(const DevModel &m, const int32_t rs, const int v) {
+  const int itR = m.itR;
+  const int nup = __ldg(m.r_nup + rs);
+  const uint32_t us = __ldg(m.r_up_start + rs);
+  float *qbuf = (v == itR - 1) ? m.f[F_RiverRunoffsub] : m.qr_sub + (int64_t)v * m.nr;
+  double Qin = 0.0;
+#pragma unroll 1
+  for (int j = 0; j < nup; j++) Qin = Qin + (double)__ldcg(qbuf + us + j);
+  const float DCLf = __ldg(m.f[F_DCL] + rs);
+  const double qr = (double)(__ldcg(m.h_inwater + rs) / DCLf);  // :3152 (REAL4 division)
+  const double A = __ldg(m.f[F_AlphaR] + rs), Bw = __ldg(m.f[F_Bw] + rs);
+  const double dtr = m.dt / itR;
+  // Qold: the previous sub-step's outflow of this cell, or the state at the first sub-step (:199)
+  const double Qo = (v == 0) ? (double)m.f[F_RiverRunoffsub][rs]
+                             : (double)__ldcg(((v - 1 == itR - 1) ? m.f[F_RiverRunoffsub] : m.qr_sub + (int64_t)(v - 1) * m.nr) + rs);
+  double qbeta;
+  const double qn = kinematic_wave(Qin, Qo, qr, A, m.beta, dtr, (double)DCLf, qbeta);
+  const double wl = (A * qbeta) / Bw;
+  double racc = qn * dtr, rh = wl;
+  if (v > 0) { racc = __ldcg(m.h_racc + rs) + racc; rh = __ldcg(m.h_rh + rs) + rh; }
+  qbuf[rs] = (float)qn;
+  if (v == itR - 1) {
+    m.f[F_RiverRunoff][rs] = (float)(racc / m.dt);
+    m.f[F_WaterLevelR][rs] = (float)(rh / itR);
+    m.f[F_WaterLevelRsub][rs] = (float)wl;
+  } else {
+    m.h_racc[rs] = racc;
+    m.h_rh[rs] = rh;
+  }
+}
+
+// The first sub-step reads its own cell's Qold from the state array that the LAST sub-step
+// overwrites: with it_kinR sub-steps in flight on different levels that is safe, because a cell's
+// sub-step v runs at tick level+2+v, strictly after its sub-step v-1 and before anyone reads v.
+
+// ---- the wavefront -------------------------------------------------------------------------------
+template <int ML>
+__global__ void __launch_bounds__(256) k_lateral_wave(const DevModel m) {
+  cg::grid_group grid = cg::this_grid();
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t gsize = (int64_t)gridDim.x * blockDim.x;
+  const int D = m.nlev, itR = m.itR;
+  const int nticks = D + 1 + ((m.nrnet > 0) ? itR : 0);
+  for (int t = 0; t < nticks; t++) {
+    // item space of this tick: [subsurface cells of level t][overland cells of level t-1]
+    //                          [river cells of full level t-2-v, sub-step v, v = 0..itR-1]
+    int64_t base = 0;
+    if (t < D) {
+      const int64_t beg = m.lev_off[t], cnt = m.lev_off[t + 1] - beg;
+      for (int64_t k = gtid; k < cnt; k += gsize) task_subsurface<ML>(m, beg + k);
+      base += cnt;
+    }
+    if (t >= 1 && t - 1 < D) {
+      const int64_t beg = m.lev_off[t - 1], cnt = m.lev_off[t] - beg;
+      // rotate the thread assignment so that this task lands on other warps than the subsurface one
+      for (int64_t k = (gtid + gsize - (base % gsize)) % gsize; k < cnt; k += gsize) task_overland(m, beg + k);
+      base += cnt;
+    }
+    if (m.nrnet > 0) {
+      for (int v = 0; v < itR; v++) {
+        const int lr = (t - 2 - v) - m.rlev_shift;  // river level solved for sub-step v at this tick
+        if (lr < 0 || lr >= m.nrlev) continue;
+        const int64_t beg = m.rlev_off[lr], cnt = m.rlev_off[lr + 1] - beg;
+        for (int64_t k = (gtid + gsize - (base % gsize)) % gsize; k < cnt; k += gsize) task_river(m, (int32_t)(beg + k), v);
+        base += cnt;
+      }
+    }
+    if (t + 1 < nticks) grid.sync();
+  }
+}
+
+// ---- batched solver kernels (wf_kinematic_wave_batch / wf_kinematic_wave_ssf_batch) -----------
+__global__ void k_kinwave_batch(int64_t n, const double *a, double *out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double qb;
+  out[i] = kinematic_wave(a[i], a[n + i], a[2 * n + i], a[3 * n + i], a[4 * n + i], a[5 * n + i], a[6 * n + i], qb);
+}
+__global__ void k_kinwave_ssf_batch(int64_t n, const double *a, double *out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double f = a[8 * n + i], D = a[9 * n + i];
+  double s, z, e;
+  kinematic_wave_ssf(a[i], a[n + i], a[2 * n + i], a[3 * n + i], a[4 * n + i], a[5 * n + i], a[6 * n + i], a[7 * n + i], f, D,
+                     exp(-f * D), a[10 * n + i], a[11 * n + i], a[12 * n + i], a[13 * n + i], s, z, e);
+  out[3 * i] = s; out[3 * i + 1] = z; out[3 * i + 2] = e;
+}
+
+}  // namespace wf
