@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -309,6 +310,13 @@ int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint
   dm.dt = cfg->timestepsecs;
   dm.basetimestep = 86400.0;  // wflow_sbm.py:1222
   dm.beta = m->cfg.beta;
+  dm.task_mask = 7;
+  if (const char *tm = std::getenv("WF_LATERAL_TASKS")) dm.task_mask = std::atoi(tm);
+  if (std::getenv("WF_TICK_PROFILE")) {
+    const size_t nt = (size_t)(m->net.nlevels() + 2 + cfg->it_kin_r) * 4;
+    CUDA_OK(cudaMallocManaged(&dm.dbg, sizeof(long long) * nt));
+    std::memset(dm.dbg, 0, sizeof(long long) * nt);
+  }
 
   auto upload = [&](const void *src, size_t bytes, void **dst) -> int {
     CUDA_OK(cudaMalloc(dst, std::max<size_t>(bytes, 16)));
@@ -378,6 +386,17 @@ void wf_destroy(wf_model *m) {
   if (!m) return;
   cudaSetDevice(m->cfg.device);
   cudaStreamSynchronize(m->stream);
+  if (m->dm.dbg) {  // development aid: per-tick critical path of the last step
+    const char *path = std::getenv("WF_TICK_PROFILE");
+    if (FILE *fp = std::fopen(path, "w")) {
+      const int nt = m->dm.nlev + 1 + (m->nrnet > 0 ? m->dm.itR : 0);
+      std::fprintf(fp, "tick,subsurface_cyc,overland_cyc,river_cyc,clock_at_end\n");
+      for (int t = 0; t < nt; t++)
+        std::fprintf(fp, "%d,%lld,%lld,%lld,%lld\n", t, m->dm.dbg[4 * t], m->dm.dbg[4 * t + 1], m->dm.dbg[4 * t + 2], m->dm.dbg[4 * t + 3]);
+      std::fclose(fp);
+    }
+    cudaFree(m->dm.dbg);
+  }
   for (int id = 0; id < F_COUNT; id++) {
     if (m->external[id]) cudaFree(m->owned[id]);
     else cudaFree(m->dm.f[id]);

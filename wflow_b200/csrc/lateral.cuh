@@ -23,57 +23,78 @@ namespace wf {
 // result to ~1e-15 relative -- three times cheaper than pow()'s correctly rounded path, far inside
 // the 1e-9 the float64 quantities are held to.  x = 0 gives 0 (b > 0) or inf (b < 0) like pow.
 __device__ __forceinline__ double pow_el(double x, double b) { return exp(b * log(x)); }
+// float32 x^b on the special-function unit (ex2.approx / lg2.approx), ~1e-6 relative: first guesses only.
+__device__ __forceinline__ float pow_fast(float x, float b) { return exp2f(b * __log2f(x)); }
 
 // kinematic_wave, wflow/wflow_funcs.py:119-152.
 // The reference's Newton iteration converges to the root of  dT/dX*Q + alpha*Q^beta = C  to
 // rounding (it only stops on |f| <= 1e-12 or its 3000-iteration cap), so the result is a property
-// of the equation, not of the path.  Here: float64 constant term C, a float32 Newton run from the
-// reference's own first guess to get within ~1e-6, then float64 Newton steps until |f| <= 1e-12
-// or the step falls below 2 ulp (the reference's iterates only wander in rounding noise from
-// there).  Agreement with the reference: a few ulp (tests: 1e-12 relative).
-// Also returns Q^beta at the solution (for the water level), by first-order correction.
+// of the equation, not of the path.  Here:
+//   1. a float32 Newton run from the reference's own first guess, to ~1e-6 (cheap; its constant
+//      term is formed in float32 too, so it does not wait for the float64 one);
+//   2. float64 Newton steps from there.  Q^beta is evaluated once in full (exp(beta*log Q)) and
+//      then carried along the tiny steps by its Taylor series; a relative step below 1e-8 proves
+//      the next iterate is converged to rounding (quadratic convergence), so 2 steps are typical.
+// Agreement with the reference: a few ulp (tests/test_gpu_parity.py asserts 1e-9 on its golden set).
+// Also returns Q^beta at the solution (the water level needs it).
 __device__ __noinline__ double kinematic_wave(double Qin, double Qold, double q, double alpha, double beta,
                                               double deltaT, double deltaX, double &Qbeta) {
   Qbeta = 0.0;
   if ((Qin + Qold + q) == 0.0) return 0.0;
   const double deltaTX = deltaT / deltaX;
   const double C = deltaTX * Qin + alpha * pow_el(Qold, beta) + deltaT * q;
-  // first guess and float32 iterations
-  const float a32 = (float)alpha, b32 = (float)beta, dtx32 = (float)deltaTX, C32 = (float)C;
-  const float ab_pQ = a32 * b32 * powf((float)((Qold + Qin) / 2.0), b32 - 1.0f);
-  float Qf = ((float)(deltaTX * Qin) + (float)Qold * ab_pQ + (float)(deltaT * q)) / (dtx32 + ab_pQ);
+  // float32 phase
+  const float a32 = (float)alpha, b32 = (float)beta, dtx32 = (float)deltaTX;
+  const float qin32 = (float)Qin, qold32 = (float)Qold, lat32 = (float)(deltaT * q);
+  // (this phase only has to land within ~1e-5 of the root: hardware exp2/log2 and fast division)
+  const float C32 = dtx32 * qin32 + a32 * pow_fast(qold32, b32) + lat32;
+  const float ab_pQ = a32 * b32 * pow_fast((qold32 + qin32) * 0.5f, b32 - 1.0f);
+  float Qf = __fdividef(dtx32 * qin32 + qold32 * ab_pQ + lat32, dtx32 + ab_pQ);
   if (isnan(Qf)) Qf = 0.0f;
   Qf = fmaxf(Qf, 1e-30f);
 #pragma unroll 1
   for (int it = 0; it < 12; it++) {
-    const float qb = powf(Qf, b32);
+    const float qb = pow_fast(Qf, b32);
     const float f = dtx32 * Qf + a32 * qb - C32;
-    const float df = dtx32 + a32 * b32 * (qb / Qf);
-    const float Qn = fmaxf(Qf - f / df, 1e-30f);
-    const bool done = fabsf(Qn - Qf) <= 2e-6f * Qn;
+    const float df = dtx32 + a32 * b32 * __fdividef(qb, Qf);
+    const float Qn = fmaxf(Qf - __fdividef(f, df), 1e-30f);
+    const bool done = fabsf(Qn - Qf) <= 1e-5f * Qn;
     Qf = Qn;
     if (done) break;
   }
+  // float64 phase
   double Qkx = (double)Qf;
-  double qb = 0.0, Qprev = Qkx;
+  double qb = pow_el(Qkx, beta);
 #pragma unroll 1
   for (int it = 0; it < 60; it++) {
-    qb = pow_el(Qkx, beta);
     const double f = deltaTX * Qkx + alpha * qb - C;
-    const double df = deltaTX + alpha * beta * (qb / Qkx);
+    const double dqb = beta * (qb / Qkx);  // d(Q^beta)/dQ
+    const double df = deltaTX + alpha * dqb;
     const double Qn = fmax(Qkx - f / df, 1e-30);
-    const bool stalled = fabs(Qn - Qkx) <= 4.440892098500626e-16 * Qn;
-    Qprev = Qkx;
+    const double d = (Qn - Qkx) / Qkx;
+    const double ad = fabs(d);
+    // Q^beta at the new iterate
+    if (ad < 1e-3) qb = qb * (1.0 + d * (beta + d * (0.5 * beta * (beta - 1.0) + d * (beta * (beta - 1.0) * (beta - 2.0) / 6.0))));
+    else qb = pow_el(Qn, beta);
     Qkx = Qn;
-    if (fabs(f) <= 1e-12 || stalled) break;
+    if (fabs(f) <= 1e-12 || ad <= 1e-8) break;
   }
-  Qbeta = qb + beta * (qb / Qprev) * (Qkx - Qprev);  // Q^beta at Qkx, O((dQ/Q)^2) accurate
+  Qbeta = qb;
   return Qkx;
 }
 
-// kinematic_wave_ssf, wflow/wflow_funcs.py:210-292.  Literal iteration (the returned zi is the one
-// computed from the LAST-BUT-ONE iterate, so the path matters); only loop-invariant quotients are
-// hoisted and the loop also stops when the Newton step falls below 2 ulp.
+// kinematic_wave_ssf, wflow/wflow_funcs.py:210-292.
+// The reference runs Newton's method on the continuity residual
+//     F(s) = dt/dx*(s - ssf_in) - dt*(r - (zi_old - zi(s))*neff*w),   zi(s) = -log(f*s/den + exp(-f*D))/f,
+// from the poor first guess (ssf_old+ssf_in)/2 (up to ~23 iterations on the bench workload, and a
+// level waits for its slowest cell), stops once |F| <= 1e-3 at the previous iterate and returns that
+// iterate's zi.  Because |F| <= 1e-3 bounds the distance to the root, the result is pinned to the
+// root itself: zi to 1e-3/(neff*w) ~ 4e-9 mm and s to 1e-3/F' mm^3, whatever the path.  So the same
+// loop is started from a much better point: the root of F written in u = log(x) = -f*zi,
+//     F(u) = A*e^u + B*u + C0   (convex, increasing),
+// found by a few Halley steps from the previous water table u = -f*zi_old.  The reference loop then
+// needs one or two iterations; exit tests, NaN guard, 1e-30 floor and the returned (stale) zi are the
+// reference's.  exp(-f*zi) inside the loop is the log's own argument x (saves an exp; ~1e-14 rel).
 __device__ __noinline__ void kinematic_wave_ssf(double ssf_in, double ssf_old, double zi_old, double r,
                                                 double Ks_hor, double Ks, double slope, double neff, double f,
                                                 double D, double efD, double dt, double dx, double w, double ssf_max,
@@ -84,35 +105,48 @@ __device__ __noinline__ void kinematic_wave_ssf(double ssf_in, double ssf_old, d
     ssf_out = 0.0; zi_out = D; exfilt_out = 0.0;
     return;
   }
-  double ssf_n = (ssf_old + ssf_in) / 2.0;
-  int count = 0;
   const double den = w * Ks_hor * Ks * slope;
   const double dtdx = dt / dx;
-  const double khs = Ks_hor * Ks;
-  double zi = log((f * ssf_n) / den + efD) / -f;
-  double Cn = (khs * exp(-f * zi) * slope) / neff;
-  double invCn = 1.0 / Cn;
-  double c = dtdx * ssf_in + invCn * ssf_n + dt * (r - (zi_old - zi) * neff * w);
-  double fQ = dtdx * ssf_n + invCn * ssf_n - c;
-  double dfQ = dtdx + 1 / Cn;
-  ssf_n = ssf_n - (fQ / dfQ);
-  if (isnan(ssf_n)) ssf_n = 0.0;
-  ssf_n = pymax(ssf_n, 1e-30);
-  while (fabs(fQ) > epsilon && count < MAX_ITERS) {
-    zi = log((f * ssf_n) / den + efD) / -f;
-    Cn = (khs * exp(-f * zi) * slope) / neff;
-    invCn = 1.0 / Cn;
-    c = dtdx * ssf_in + invCn * ssf_n + dt * (r - (zi_old - zi) * neff * w);
+  const double fden = f / den;
+  const double nf = -1.0 / f;
+  const double K1 = neff / (Ks_hor * Ks * slope);  // 1/Cn = K1 / exp(-f*zi)
+  double ssf_n;
+  {
+    const double A = dtdx / fden;
+    const double B = dt * neff * w / f;
+    const double C0 = -A * efD - dtdx * ssf_in - dt * (r - zi_old * neff * w);
+    double u = -f * fmin(fmax(zi_old, 0.0), D);
+    double e = exp(u);
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+      const double Fu = A * e + B * u + C0;
+      const double d1 = A * e + B, d2 = A * e;
+      const double du = 2.0 * Fu * d1 / (2.0 * d1 * d1 - Fu * d2);
+      u = u - du;
+      e = exp(u);
+      if (!(fabs(du) > 1e-10)) break;
+    }
+    ssf_n = (e - efD) / fden;
+    if (!(ssf_n == ssf_n) || isinf(ssf_n)) ssf_n = (ssf_old + ssf_in) / 2.0;  // the reference's first guess
+    ssf_n = pymax(ssf_n, 1e-30);
+  }
+  int count = 0;
+  double zi, fQ;
+  bool stalled = false;
+  do {
+    const double x = ssf_n * fden + efD;
+    zi = log(x) * nf;
+    const double invCn = K1 / x;
+    const double c = dtdx * ssf_in + invCn * ssf_n + dt * (r - (zi_old - zi) * neff * w);
     fQ = dtdx * ssf_n + invCn * ssf_n - c;
-    dfQ = dtdx + invCn;
+    const double dfQ = dtdx + invCn;
     double sn = ssf_n - (fQ / dfQ);
     if (isnan(sn)) sn = 0.0;
     sn = pymax(sn, 1e-30);
-    const bool stalled = fabs(sn - ssf_n) <= 4.440892098500626e-16 * sn;
+    stalled = fabs(sn - ssf_n) <= 4.440892098500626e-16 * sn;
     ssf_n = sn;
     count++;
-    if (stalled) break;
-  }
+  } while (fabs(fQ) > epsilon && count <= MAX_ITERS && !stalled);
   ssf_n = pymin(ssf_n, (ssf_max * w));
   const double rest = zi_old - (ssf_in + r * dx - ssf_n) / (w * dx) / neff;
   exfilt_out = pymin(rest, 0.0) * -neff;
@@ -157,19 +191,21 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
 
   // inflow gather, reference summation order (wflow_sbm.py:395-410)
   double ssf_in = 0.0, ssf_tr = 0.0;
+  double sv[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) sv[j] = (j < nup) ? __ldcg(m.h_ssf + (int64_t)us + j) : 0.0;  // all loads in flight at once
   if (riverMap) {
 #pragma unroll 1
     for (int j = 0; j < nup; j++) {
-      const int64_t nb = (int64_t)us + j;
-      const double sv = __ldcg(m.h_ssf + nb);
-      const double cp = chan_perc(m, nb, myldd, slope_i);
-      ssf_in = ssf_in + (1 - cp) * sv;
-      ssf_tr = ssf_tr + cp * sv;
+      const double cp = chan_perc(m, (int64_t)us + j, myldd, slope_i);
+      ssf_in = ssf_in + (1 - cp) * sv[j];
+      ssf_tr = ssf_tr + cp * sv[j];
     }
     m.h_ssf_tr[rs] = (float)(ssf_tr / (1000 * 1000 * 1000) / m.dt);
   } else {
-#pragma unroll 1
-    for (int j = 0; j < nup; j++) ssf_in = ssf_in + __ldcg(m.h_ssf + (int64_t)us + j);
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (j < nup) ssf_in = ssf_in + sv[j];
   }
 
   const double neff = (double)neff_f;
@@ -285,8 +321,12 @@ __device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i
         s3 = s3 + qv;
       }
     } else {
-#pragma unroll 1
-      for (int j = 0; j < nup; j++) s1 = s1 + (double)__ldcg(qbuf + (int64_t)us + j);
+      float qv[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) qv[j] = (j < nup) ? __ldcg(qbuf + (int64_t)us + j) : 0.0f;
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        if (j < nup) s1 = s1 + (double)qv[j];
     }
     double qo_in, qo_toriver_vol;
     if (riverMap) {
@@ -334,8 +374,14 @@ __device__ __forceinline__ void task_river(const DevModel &m, const int32_t rs, 
   const uint32_t us = __ldg(m.r_up_start + rs);
   float *qbuf = (v == itR - 1) ? m.f[F_RiverRunoffsub] : m.qr_sub + (int64_t)v * m.nr;
   double Qin = 0.0;
-#pragma unroll 1
-  for (int j = 0; j < nup; j++) Qin = Qin + (double)__ldcg(qbuf + us + j);
+  {
+    float qv[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) qv[j] = (j < nup) ? __ldcg(qbuf + us + j) : 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (j < nup) Qin = Qin + (double)qv[j];
+  }
   const float DCLf = __ldg(m.f[F_DCL] + rs);
   const double qr = (double)(__ldcg(m.h_inwater + rs) / DCLf);  // :3152 (REAL4 division)
   const double A = __ldg(m.f[F_AlphaR] + rs), Bw = __ldg(m.f[F_Bw] + rs);
@@ -375,26 +421,35 @@ __global__ void __launch_bounds__(256) k_lateral_wave(const DevModel m) {
     // item space of this tick: [subsurface cells of level t][overland cells of level t-1]
     //                          [river cells of full level t-2-v, sub-step v, v = 0..itR-1]
     int64_t base = 0;
-    if (t < D) {
+    long long c0 = 0;
+    if (m.dbg) c0 = clock64();
+    if (t < D && (m.task_mask & 1)) {
       const int64_t beg = m.lev_off[t], cnt = m.lev_off[t + 1] - beg;
-      for (int64_t k = gtid; k < cnt; k += gsize) task_subsurface<ML>(m, beg + k);
+      bool any = false;
+      for (int64_t k = gtid; k < cnt; k += gsize) { task_subsurface<ML>(m, beg + k); any = true; }
       base += cnt;
+      if (m.dbg && any) { atomicMax((unsigned long long *)&m.dbg[4 * t + 0], (unsigned long long)(clock64() - c0)); c0 = clock64(); }
     }
-    if (t >= 1 && t - 1 < D) {
+    if (t >= 1 && t - 1 < D && (m.task_mask & 2)) {
       const int64_t beg = m.lev_off[t - 1], cnt = m.lev_off[t] - beg;
+      bool any = false;
       // rotate the thread assignment so that this task lands on other warps than the subsurface one
-      for (int64_t k = (gtid + gsize - (base % gsize)) % gsize; k < cnt; k += gsize) task_overland(m, beg + k);
+      for (int64_t k = (gtid + gsize - (base % gsize)) % gsize; k < cnt; k += gsize) { task_overland(m, beg + k); any = true; }
       base += cnt;
+      if (m.dbg && any) { atomicMax((unsigned long long *)&m.dbg[4 * t + 1], (unsigned long long)(clock64() - c0)); c0 = clock64(); }
     }
-    if (m.nrnet > 0) {
+    if (m.nrnet > 0 && (m.task_mask & 4)) {
       for (int v = 0; v < itR; v++) {
         const int lr = (t - 2 - v) - m.rlev_shift;  // river level solved for sub-step v at this tick
         if (lr < 0 || lr >= m.nrlev) continue;
         const int64_t beg = m.rlev_off[lr], cnt = m.rlev_off[lr + 1] - beg;
-        for (int64_t k = (gtid + gsize - (base % gsize)) % gsize; k < cnt; k += gsize) task_river(m, (int32_t)(beg + k), v);
+        bool any = false;
+        for (int64_t k = (gtid + gsize - (base % gsize)) % gsize; k < cnt; k += gsize) { task_river(m, (int32_t)(beg + k), v); any = true; }
         base += cnt;
+        if (m.dbg && any) { atomicMax((unsigned long long *)&m.dbg[4 * t + 2], (unsigned long long)(clock64() - c0)); c0 = clock64(); }
       }
     }
+    if (m.dbg && gtid == 0) m.dbg[4 * t + 3] = clock64();
     if (t + 1 < nticks) grid.sync();
   }
 }
