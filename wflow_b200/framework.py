@@ -1,0 +1,546 @@
+"""Host-side mirror of the reference's framework surface for the wflow_sbm hot path.
+
+`WflowSbm` plays the roles of the reference's `WflowModel` (``wflow/wflow_sbm.py:903-3528``) and of
+`wf_DynamicFramework` (``wflow/wf_DynamicFramework.py:502-3548``) for this one model: ini-driven
+set-up, static maps and lookup tables, state files, the time loop and the per-step outputs -- same
+method names, argument meaning and error behaviour -- while every per-timestep computation runs in
+libwflowsbm on the GPU (`core.SbmModel`).  Nothing here is executed per cell per step on the host.
+
+Covered: case directory layout (staticmaps/, intbl/, inmaps/ map stacks, instate/, <runId>/outstate,
+outmaps), [run] [model] [layout] [inputmapstacks] [outputmaps] [outputcsv_N] [outputtss_N] [API],
+cold start (reinit = 1) and warm start, wf_suspend / wf_resume, wf_setValues*, wf_supplyMapAsNumpy,
+wf_supplyVariableNamesAndRoles, wf_QuickSuspend/Resume.  Not covered (out of scope):
+netCDF I/O, reservoirs/lakes, irrigation, state updating, LAI, [summary*] maps, variable_change_*.
+
+The derivations of `initial()` that need PCRaster neighbourhood operators (slope from the DEM, window
+average for the river width) are restated in numpy and are NOT pinned against PCRaster (it cannot be
+installed in the build environment); supply `Slope.map` / `RiverWidth.map` to bypass them.
+"""
+import configparser
+import datetime as _dt
+import logging
+import os
+
+import numpy as np
+
+from . import csf, params, tbl
+from .core import Schedule, SbmModel
+
+F32 = np.float32
+MV = -999.0
+
+# reference defaults of the parameter tables (wflow_sbm.py:1458-1790)
+TABLE_DEFAULTS = {
+    "MaxCanopyStorage": 1.0, "CanopyGapFraction": 0.1, "EoverR": 0.1, "RootingDepth": 750.0, "AirEntryPressure": 10.0,
+    "rootdistpar": -8000.0, "InfiltCapSoil": 100.0, "CapScale": 100.0, "InfiltCapPath": 10.0, "MaxLeakage": 0.0,
+    "PathFrac": 0.01, "SoilThickness": 2000.0, "thetaR": 0.01, "thetaS": 0.6, "SoilMinThickness": 500.0,
+    "KsatVer": 3000.0, "KsatHorFrac": 1.0, "M": 300.0, "N": 0.072, "N_River": 0.036, "WaterFrac": 0.0,
+    "et_reftopot": 1.0, "TTI": 1.0, "TT": -1.41934, "TTM": -1.41934, "Cfmax": 3.75653, "WHC": 0.1, "w_soil": 0.1125,
+    "cf_soil": 0.038,
+}
+
+STATE_FILES = ["RiverRunoffsub", "RiverRunoff", "WaterLevelR", "WaterLevelRsub", "LandRunoff", "LandRunoffsub",
+               "WaterLevelL", "WaterLevelLsub", "SatWaterDepth", "Snow", "TSoil", "UStoreLayerDepth", "SnowWater",
+               "CanopyStorage", "SubsurfaceFlow"]  # stateVariables(), wflow_sbm.py:955-1010
+
+
+def configget(config, section, var, default):
+    """wflow_lib.configget (wflow/wflow_lib.py:141-168): missing options take and record the default."""
+    try:
+        return config.get(section, var)
+    except (configparser.NoSectionError, configparser.NoOptionError):
+        if not config.has_section(section):
+            config.add_section(section)
+        config.set(section, var, str(default))
+        return str(default)
+
+
+def generate_name_t(prefix, step):
+    """PCRaster map-stack file name (8.3), e.g. ('inmaps/P', 1) -> 'inmaps/P0000000.001'."""
+    d, stem = os.path.split(prefix)
+    digits = "%0*d" % (11 - len(stem), step)
+    full = stem + digits
+    return os.path.join(d, full[:8] + "." + full[8:])
+
+
+def lattometres(lat):
+    """Length of a degree of latitude and longitude in metres (wflow/pcrut.py:17-50), REAL4."""
+    r = np.deg2rad(lat.astype(np.float64))
+    latlen = 111132.92 + (-559.82 * np.cos(2.0 * r)) + (1.175 * np.cos(4.0 * r)) + (-0.0023 * np.cos(6.0 * r))
+    longlen = (111412.84 * np.cos(r)) + (-93.5 * np.cos(3.0 * r)) + (0.118 * np.cos(5.0 * r))
+    return latlen.astype(F32), longlen.astype(F32)
+
+
+def slope_from_dem(dem, cellsize):
+    """pcr.slope restated (third-order finite difference / Horn on the 3x3 window, edges and missing
+    neighbours replaced by the centre value).  NOT pinned against PCRaster."""
+    z = dem.astype(np.float64)
+    zc = np.where(np.isnan(z), 0.0, z)
+    valid = ~np.isnan(z)
+    zp = np.pad(zc, 1, mode="edge")
+    vp = np.pad(valid, 1, mode="constant", constant_values=False)
+
+    def nb(dr, dc):
+        zz = zp[1 + dr: 1 + dr + z.shape[0], 1 + dc: 1 + dc + z.shape[1]]
+        vv = vp[1 + dr: 1 + dr + z.shape[0], 1 + dc: 1 + dc + z.shape[1]]
+        return np.where(vv, zz, zc)
+
+    dzdx = ((nb(-1, 1) + 2 * nb(0, 1) + nb(1, 1)) - (nb(-1, -1) + 2 * nb(0, -1) + nb(1, -1))) / (8.0 * cellsize)
+    dzdy = ((nb(1, -1) + 2 * nb(1, 0) + nb(1, 1)) - (nb(-1, -1) + 2 * nb(-1, 0) + nb(-1, 1))) / (8.0 * cellsize)
+    s = np.sqrt(dzdx * dzdx + dzdy * dzdy)
+    return np.where(valid, s, np.nan).astype(F32)
+
+
+def window_average(a, ncells):
+    """pcr.windowaverage(a, ncells * celllength) restated: square window centred on the cell, cells cut
+    by the window edge weighted by their covered fraction, missing values skipped.  NOT pinned."""
+    half = ncells / 2.0
+    k = int(np.ceil(half - 0.5))
+    w1 = np.array([min(1.0, half - (abs(d) - 0.5)) for d in range(-k, k + 1)])
+    w1 = np.clip(w1, 0.0, 1.0)
+    valid = ~np.isnan(a)
+    v = np.where(valid, a, 0.0).astype(np.float64)
+    vp, mp = np.pad(v, k), np.pad(valid.astype(np.float64), k)
+    num = np.zeros(a.shape)
+    den = np.zeros(a.shape)
+    for i, wi in enumerate(w1):
+        for j, wj in enumerate(w1):
+            w = wi * wj
+            if w > 0:
+                num += w * vp[i:i + a.shape[0], j:j + a.shape[1]]
+                den += w * mp[i:i + a.shape[0], j:j + a.shape[1]]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return np.where(den > 0, num / den, np.nan).astype(F32)
+
+
+class WflowSbm:
+    """One wflow_sbm run on one GPU, driven like the reference's WflowModel + wf_DynamicFramework."""
+
+    def __init__(self, cloneMap="wflow_subcatch.map", Dir=".", RunDir="run_default", configfile="wflow_sbm.ini",
+                 device=0):
+        self.Dir = Dir
+        self.caseName = Dir
+        self.runId = RunDir
+        self.configfile = configfile
+        self.cloneMap = cloneMap
+        self.device = device
+        self.SaveDir = os.path.join(Dir, RunDir)
+        self.logger = logging.getLogger("wflow_b200")
+        self.config = configparser.ConfigParser()
+        self.config.optionxform = str
+        ini = os.path.join(Dir, configfile)
+        if not os.path.isfile(ini):
+            raise FileNotFoundError("Cannot open config file: " + ini)  # reference: logger.error + sys.exit(1)
+        self.config.read(ini)
+        self._api_values = {}      # forcing set through the API overrides the map stack for one step
+        self._currentTimeStep = 0
+        self._mod = None
+        self._outputs = []
+        self._files = {}
+
+    # ---- configuration -------------------------------------------------------------------------
+    def _read_time(self):
+        run = lambda k, d: configget(self.config, "run", k, d)
+        self.timestepsecs = int(run("timestepsecs", configget(self.config, "model", "timestepsecs", "86400")))
+        self.reinit = int(run("reinit", configget(self.config, "model", "reinit", "0")))
+        fmt = "%Y-%m-%d %H:%M:%S"
+        st = run("starttime", "None").replace(" GMT", "").strip()
+        et = run("endtime", "None").replace(" GMT", "").strip()
+        if st != "None" and et != "None":
+            self.datetime_start = _dt.datetime.strptime(st, fmt)
+            self.datetime_end = _dt.datetime.strptime(et, fmt)
+            # 'steps' mode: the state time is one step before the first forcing (wf_DynamicFramework.py:1282-1390)
+            self.nrTimeSteps = int((self.datetime_end - self.datetime_start).total_seconds() // self.timestepsecs) + 1
+        else:
+            self.datetime_start = _dt.datetime(1990, 1, 1)
+            self.nrTimeSteps = int(run("laststep", "1"))
+            self.datetime_end = self.datetime_start + _dt.timedelta(seconds=self.timestepsecs * (self.nrTimeSteps - 1))
+
+    def createRunId(self, **kw):
+        """Run directory layout (wf_DynamicFramework.py:1175-1280)."""
+        for sub in ("outmaps", "outstate", "outsum", "intbl", "runinfo"):
+            os.makedirs(os.path.join(self.SaveDir, sub), exist_ok=True)
+        self._read_time()
+
+    # ---- initial() -------------------------------------------------------------------------------
+    def _staticmap(self, name, default=None, fail=False):
+        path = os.path.join(self.Dir, name)
+        if os.path.isfile(path):
+            a, info = csf.read_map(path)
+            if not hasattr(self, "_info"):
+                self._info = info
+            elif not info.same_grid(self._info):
+                raise ValueError("map %s does not match the clone grid" % path)
+            return a
+        if fail:
+            raise ValueError("Could not find required map: " + path)  # wf_DynamicFramework.py:3372
+        return None if default is None else np.full(self.shape, default, F32)
+
+    def _runInitial(self):
+        cfg = lambda k, d: configget(self.config, "model", k, d)
+        mapname = lambda k: cfg(k, "staticmaps/%s.map" % k)
+        self.modelSnow = int(cfg("ModelSnow", "1"))
+        self.soilInfReduction = int(cfg("soilInfRedu", "0"))
+        self.TransferMethod = int(cfg("transfermethod", "0"))
+        self.UST = int(cfg("Whole_UST_Avail", "0"))
+        self.kinwaveIters = int(cfg("kinwaveIters", "0"))
+        self.kinwaveRiverTstep = int(cfg("kinwaveRiverTstep", "0"))
+        self.kinwaveLandTstep = int(cfg("kinwaveLandTstep", "0"))
+        self.intbl = cfg("intbl", "intbl")
+        sizeinmetres = int(configget(self.config, "layout", "sizeinmetres", "0"))
+        WIMaxScale = float(cfg("WIMaxScale", "0.8"))
+        thick = cfg("UStoreLayerThickness", "0")
+        self.layer_thickness = tuple(float(t) for t in thick.split(",")) if thick != "0" else ()
+        self.maxLayers = len(self.layer_thickness) + 1 if self.layer_thickness else 1
+
+        sub = self._staticmap(mapname("wflow_subcatch"), fail=True)
+        self.shape = sub.shape
+        info = self._info
+        active = sub > 0
+        self.TopoId = np.where(active, sub, 0).astype(np.int32)
+        ldd = self._staticmap(mapname("wflow_ldd"), fail=True)
+        dem = self._staticmap(mapname("wflow_dem"), fail=True).astype(F32)
+        river = self._staticmap(mapname("wflow_river"), fail=True)
+        landuse = self._staticmap(mapname("wflow_landuse"), fail=True)
+        soil = self._staticmap(mapname("wflow_soil"), fail=True)
+        gauges = self._staticmap(mapname("wflow_gauges"), fail=True)
+        landuse = np.where(landuse <= -999, active.astype(np.int32), landuse)
+        soil = np.where(soil <= -999, active.astype(np.int32), soil)
+        self.OutputLoc = np.where(gauges > 0, gauges, 0).astype(np.int32)
+        self.LandUse, self.Soil = landuse, soil
+        # lddmask(TopoLdd, TopoId): the network lives on the subcatchment cells; cells that drain out of
+        # the mask become pits (wflow_sbm.py:1969)
+        ldd = np.where(active & (ldd >= 1) & (ldd <= 9), ldd, 0).astype(np.uint8)
+        ldd = _repair_ldd(ldd)
+        self.ldd = ldd
+        river_b = (np.nan_to_num(river.astype(np.float64), nan=0.0) > 0) & active
+
+        base = {}
+        T = lambda name, key=None: tbl.read_tbl_default(self.Dir, self.intbl, name, landuse, sub, soil,
+                                                        TABLE_DEFAULTS[key or name])
+        base["Cmax"] = T("MaxCanopyStorage")
+        for n in ("CanopyGapFraction", "EoverR", "RootingDepth", "AirEntryPressure", "rootdistpar", "InfiltCapSoil",
+                  "CapScale", "InfiltCapPath", "MaxLeakage", "PathFrac", "SoilThickness", "thetaR", "thetaS",
+                  "KsatVer", "KsatHorFrac", "M", "N", "N_River", "WaterFrac"):
+            base[n] = T(n)
+        base["et_RefToPot"] = T("et_reftopot")
+        soil_min = T("SoilMinThickness")
+        if self.modelSnow:
+            for n in ("TTI", "TT", "TTM", "Cfmax", "WHC", "w_soil"):
+                base[n] = T(n)
+            if self.soilInfReduction:
+                base["cf_soil"] = T("cf_soil")
+        for k in range(self.maxLayers):
+            base["c_%d" % k] = tbl.read_tbl_default(self.Dir, self.intbl, "c", landuse, sub, soil, 10.0, layer=k)
+            base["KsatVerFrac_%d" % k] = tbl.read_tbl_default(self.Dir, self.intbl, "KsatVerFrac", landuse, sub, soil, 1.0, layer=k)
+        tc = self._staticmap(cfg("TemperatureCorrectionMap", "staticmaps/wflow_tempcor.map"))
+        base["TempCor"] = np.zeros(self.shape, F32) if tc is None else np.nan_to_num(tc, nan=0.0).astype(F32)
+
+        # cell sizes, wflow/pcrut.py:53-73
+        if sizeinmetres:
+            xl = yl = np.full(self.shape, info.cellsize, F32)
+        else:
+            latlen, longlen = lattometres(np.repeat(info.ycoordinate()[:, None], self.shape[1], 1).astype(F32))
+            xl, yl = (longlen * F32(info.cellsize)).astype(F32), (latlen * F32(info.cellsize)).astype(F32)
+        reallength = ((xl + yl) * F32(0.5)).astype(F32)
+        base["xl"], base["yl"] = xl, yl
+        slope_map = self._staticmap("staticmaps/Slope.map")
+        slope = slope_map if slope_map is not None else slope_from_dem(np.where(active, dem, np.nan), info.cellsize)
+        slope = np.maximum(F32(0.00001), np.nan_to_num(slope, nan=0.0) * F32(info.cellsize) / reallength).astype(F32)  # :1800
+        base["landSlope"] = slope
+        # soil thickness scaled by the topographic wetness index, wflow_sbm.py:1926-1933
+        sched = Schedule(ldd)
+        upcells = sched.catchment_total(None).astype(F32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            WI = np.log(np.where(active, upcells / np.maximum(slope, F32(0.00001)), np.nan)).astype(F32)
+            WIMax = np.zeros(self.shape, F32)
+            for i in np.unique(self.TopoId[active]):
+                m = self.TopoId == i
+                WIMax[m] = np.nanmax(WI[m]) * F32(WIMaxScale)
+            st = np.maximum(np.minimum(base["SoilThickness"], (WI / WIMax) * base["SoilThickness"]), soil_min)
+        base["SoilThickness"] = np.where(active, st, base["SoilThickness"]).astype(F32)
+        # river geometry, wflow_sbm.py:2044-2105
+        rlf = self._staticmap(mapname("wflow_riverlength_fact"))
+        base["RiverLengthFac"] = np.ones(self.shape, F32) if rlf is None else np.nan_to_num(rlf, nan=1.0).astype(F32)
+        rl = self._staticmap(mapname("wflow_riverlength"))
+        if rl is not None:
+            base["DCL"] = np.nan_to_num(rl, nan=0.0).astype(F32)
+        dl = params.drain_length(ldd, xl, yl)
+        dcl = base.get("DCL", (dl * np.maximum(F32(1.0), base["RiverLengthFac"])).astype(F32))
+        rslope = self._staticmap("staticmaps/RiverSlope.map")
+        base["riverSlope"] = (slope * (dl / np.maximum(dcl, F32(1e-6)))).astype(F32) if rslope is None else rslope
+        rw = self._staticmap(mapname("wflow_riverwidth"))
+        rw = np.zeros(self.shape, F32) if rw is None else np.nan_to_num(rw, nan=0.0).astype(F32)
+        if (rw[river_b] <= 0).any():  # Q-scaled width, wflow_sbm.py:2073-2086 (window average restated, unpinned)
+            alf = float(cfg("Alpha", "60"))
+            Qmax = float(cfg("AnnualDischarge", "300"))
+            Qscale = upcells / max(float(upcells.max()), 1.0) * Qmax
+            W = ((alf * (alf + 2.0) ** 0.6666666667) ** 0.375 * Qscale ** 0.375
+                 * np.maximum(0.0001, np.nan_to_num(window_average(np.where(active, base["riverSlope"], np.nan), 4.0), nan=0.0001)) ** (-0.1875)
+                 * base["N_River"] ** 0.375).astype(F32)
+            rw = np.where(rw <= 0.0, W, rw).astype(F32)
+        base["RiverWidth"] = rw
+        bf = self._staticmap(mapname("wflow_bankfulldepth"))
+        bf = np.ones(self.shape, F32) if bf is None else np.nan_to_num(bf, nan=0.0).astype(F32)
+        base["BankfullDepth"] = np.where(river_b, bf, F32(0.0)).astype(F32)
+
+        self.static = params.derive_static(base, ldd, river_b, self.timestepsecs, cellsize=info.cellsize,
+                                           n_layers=self.maxLayers)
+        self.River = river_b
+        it_l = it_r = 1
+        if self.kinwaveIters == 1:  # wflow_sbm.py:2911-2923, 3159-3171 (fixed sub-steps only)
+            if self.kinwaveLandTstep > 0:
+                it_l = int(np.ceil(self.timestepsecs / self.kinwaveLandTstep))
+            if self.kinwaveRiverTstep > 0:
+                it_r = int(np.ceil(self.timestepsecs / self.kinwaveRiverTstep))
+            if self.kinwaveLandTstep == 0 or self.kinwaveRiverTstep == 0:
+                raise NotImplementedError("kinwaveIters=1 needs fixed kinwaveLandTstep / kinwaveRiverTstep here "
+                                          "(the Courant estimate of estimate_iterations_kin_wave is not restated)")
+        self._mod = SbmModel(ldd, river_b, schedule=sched, timestepsecs=self.timestepsecs,
+                             layer_thickness=self.layer_thickness, model_snow=self.modelSnow,
+                             soil_inf_redu=self.soilInfReduction, transfer_method=self.TransferMethod, ust=self.UST,
+                             it_kin_l=it_l, it_kin_r=it_r, device=self.device)
+        for k, v in self.static.items():
+            if k not in ("River", "Beta"):
+                self._mod.set(k, np.where(np.isnan(v), F32(0.0), v))
+        self._mod.request("SatWaterDepth")
+        self._setup_outputs()
+
+    # ---- resume / suspend ------------------------------------------------------------------------
+    def _state_names(self):
+        out = []
+        for s in STATE_FILES:
+            if s == "UStoreLayerDepth":
+                out += ["UStoreLayerDepth_%d" % k for k in range(self.maxLayers)]
+            elif s in ("Snow", "SnowWater", "TSoil") and not self.modelSnow and False:
+                continue
+            else:
+                out.append(s)
+        return out
+
+    def _runResume(self):
+        if self.reinit == 1:
+            state = params.cold_state(self.static, self.maxLayers)
+            self._load_state(state)
+        else:
+            self.wf_resume(os.path.join(self.Dir, "instate"))
+
+    def _load_state(self, state):
+        st, neff = self.static["SoilThickness"], (self.static["thetaS"] - self.static["thetaR"]).astype(F32)
+        if "SatWaterDepth" in state:  # zi is the live saturated-zone state, wflow_sbm.py:2512
+            state = dict(state)
+            state["zi"] = np.maximum(F32(0.0), st - state["SatWaterDepth"] / neff).astype(F32)
+        for k, v in state.items():
+            if k == "SatWaterDepth":
+                continue
+            self._mod.set(k, np.nan_to_num(np.where(v == F32(MV), np.nan, v), nan=0.0).astype(F32))
+
+    def wf_resume(self, directory):
+        """Read the state maps (wf_DynamicFramework.py:2065-2129): list-valued states as Name_<k>.map."""
+        state = {}
+        for name in self._state_names():
+            path = os.path.join(directory, name + ".map")
+            if not os.path.isfile(path):
+                # wf_readmap(path, 0.0) hands back the default map for a missing file (:2109)
+                self.logger.warning("state file %s not found, using 0.0" % path)
+                state[name] = np.zeros(self.shape, F32)
+                continue
+            a, _ = csf.read_map(path)
+            state[name] = np.nan_to_num(a.astype(F32), nan=0.0)
+        self._load_state(state)
+
+    def wf_suspend(self, directory):
+        """Write one REAL4 map per state (wf_DynamicFramework.py:1780-1827)."""
+        os.makedirs(directory, exist_ok=True)
+        for name in self._state_names():
+            csf.write_map(os.path.join(directory, name + ".map"), self._mod.get(name, MV), self._info, mv=MV)
+
+    def _runSuspend(self):
+        self.wf_suspend(os.path.join(self.SaveDir, "outstate"))
+        if int(configget(self.config, "model", "OverWriteInit", "0")):
+            self.wf_suspend(os.path.join(self.Dir, "instate"))
+
+    def wf_QuickSuspend(self):
+        self._mod.quick_suspend()
+
+    def wf_QuickResume(self):
+        self._mod.quick_resume()
+
+    # ---- dynamic ----------------------------------------------------------------------------------
+    def _forcing(self, var, stack_key, default_stack, step, default):
+        if var in self._api_values:  # set through the API: skip the disk for this step (:3300-3306)
+            return self._api_values.pop(var)
+        prefix = configget(self.config, "inputmapstacks", stack_key, default_stack).lstrip("/")
+        path = generate_name_t(os.path.join(self.Dir, prefix), step)
+        if os.path.isfile(path):
+            a, _ = csf.read_map(path)
+            return np.nan_to_num(a.astype(F32), nan=default)
+        return np.full(self.shape, default, F32)
+
+    def _runDynamic(self, firststep, laststep):
+        """The time loop (wf_DynamicFramework.py:2968-3042); steps are 1-based like the map stacks."""
+        first = max(int(firststep), 1) if firststep else self._currentTimeStep + 1
+        last = int(laststep) if laststep else self.nrTimeSteps
+        for step in range(first, last + 1):
+            self._currentTimeStep = step
+            self._mod.set("P", self._forcing("P", "Precipitation", "/inmaps/P", step, 0.0))
+            self._mod.set("PET", self._forcing("PET", "EvapoTranspiration", "/inmaps/PET", step, 0.0))
+            if self.modelSnow:
+                self._mod.set("TEMP", self._forcing("TEMP", "Temperature", "/inmaps/TEMP", step, 10.0))
+            self.wf_QuickSuspend()
+            self._mod.step()
+            self._write_outputs(step)
+
+    def currentTimeStep(self):
+        return self._currentTimeStep
+
+    # ---- API (wf_DynamicFramework.py:2203-2327, 2582-2760) -------------------------------------------------
+    _ALIAS = {"Precipitation": "P", "PotenEvap": "PET", "Temperature": "TEMP"}
+
+    def wf_supplyVariableNamesAndRoles(self):
+        """[API] section: name = role,unit (0 in, 1 out, 2 state, 3 parameter)."""
+        res = []
+        if self.config.has_section("API"):
+            for k, v in self.config.items("API"):
+                role, unit = (v.split(",") + ["-"])[:2]
+                res.append([k, int(role), unit])
+        return res
+
+    def wf_supplyMapAsNumpy(self, name):
+        """float32 (nrow, ncol), flipped south-up, -999 for missing (wf_DynamicFramework.py:2582-2613);
+        Name_k addresses element k of a list-valued variable."""
+        if name in ("timestepsecs",):
+            return np.array(getattr(self, name))
+        field = self._ALIAS.get(name, name)
+        try:
+            a = self._mod.get(field, MV)
+        except Exception:
+            self.logger.error("%s is not defined in the model" % name)
+            return None
+        return np.flipud(a).copy()
+
+    def wf_setValuesAsNumpy(self, name, values):
+        field = self._ALIAS.get(name, name)
+        a = np.flipud(np.asarray(values, dtype=F32)).copy()
+        a = np.where(a == F32(MV), F32(0.0), a)
+        if field in ("P", "PET", "TEMP"):
+            self._api_values[field] = a
+        else:
+            self._mod.set(field, a)
+
+    def wf_setValues(self, name, values):
+        """Scalar -> uniform map; list/array -> map WITHOUT the south-up flip (:2284-2327)."""
+        field = self._ALIAS.get(name, name)
+        v = np.asarray(values, dtype=F32)
+        a = np.full(self.shape, float(v), F32) if v.size == 1 else v.reshape(self.shape)
+        if field in ("P", "PET", "TEMP"):
+            self._api_values[field] = a
+        else:
+            self._mod.set(field, a)
+
+    # ---- outputs ----------------------------------------------------------------------------------
+    def _setup_outputs(self):
+        """[outputcsv_N] / [outputtss_N]: samplemap, function, self.Var = file (wf_DynamicFramework.py:1709-1778)."""
+        for kind in ("csv", "tss"):
+            n = 0
+            while self.config.has_section("output%s_%d" % (kind, n)):
+                sec = "output%s_%d" % (kind, n)
+                n += 1
+                samplemap = self.config.get(sec, "samplemap")
+                func = configget(self.config, sec, "function", "average")
+                ids, _ = csf.read_map(os.path.join(self.Dir, samplemap))
+                ids = np.where(ids > 0, ids, 0).astype(np.int32)
+                # the reference samples np.unique(pcr2numpy(area, 0)): missing cells show up as a first column "0"
+                zero_col = bool((ids == 0).any())
+                area, uniq = self._mod.area_create(ids)
+                for var, fname in self.config.items(sec):
+                    if var in ("samplemap", "function", "timeformat"):
+                        continue
+                    terms = [t.strip().replace("self.", "") for t in var.split("+")]
+                    try:
+                        for t in terms:
+                            self._mod.request(self._ALIAS.get(t, t))
+                    except Exception as ex:
+                        self.logger.warning("output %s skipped: %s" % (var, ex))
+                        continue
+                    self._outputs.append(dict(kind=kind, area=area, ids=uniq, func=func, terms=terms, zero_col=zero_col,
+                                              path=os.path.join(self.SaveDir, fname)))
+        self._outmaps = []
+        if self.config.has_section("outputmaps"):
+            for var, prefix in self.config.items("outputmaps"):
+                name = var.replace("self.", "")
+                try:
+                    self._mod.request(self._ALIAS.get(name, name))
+                    self._mod.device_ptr(self._ALIAS.get(name, name))
+                except Exception as ex:
+                    self.logger.warning("output map %s skipped: %s" % (var, ex))
+                    continue
+                self._outmaps.append((name, prefix))
+
+    def _write_outputs(self, step):
+        for o in self._outputs:
+            vals = None
+            for t in o["terms"]:
+                v = self._mod.area_reduce(o["area"], self._ALIAS.get(t, t), o["func"] if o["func"] != "majority" else "maximum")
+                vals = v if vals is None else vals + v
+            ids = ([0] if o["zero_col"] else []) + [int(i) for i in o["ids"]]
+            vals = ([0.0] if o["zero_col"] else []) + [float(x) for x in vals]
+            fh = self._files.get(o["path"])
+            if fh is None:
+                fh = self._files[o["path"]] = open(o["path"], "w")
+                if o["kind"] == "csv":
+                    fh.write("# Timestep," + ",".join(str(i) for i in ids) + "\n")
+                else:  # PCRaster timeseries header
+                    fh.write("timeseries scalar\n%d\ntimestep\n" % (len(ids) + 1))
+                    fh.write("".join("%d\n" % i for i in ids))
+            sep = "," if o["kind"] == "csv" else " "
+            fh.write(str(step - 1) + sep + sep.join(repr(x) for x in vals) + "\n")  # row label = step-1 (:494)
+        for name, prefix in self._outmaps:
+            path = generate_name_t(os.path.join(self.SaveDir, "outmaps", prefix), step)
+            csf.write_map(path, self._mod.get(self._ALIAS.get(name, name), MV), self._info, mv=MV)
+
+    def _wf_shutdown(self):
+        for fh in self._files.values():
+            fh.close()
+        self._files = {}
+        with open(os.path.join(self.SaveDir, "runinfo", "configofrun.ini"), "w") as fh:
+            self.config.write(fh)
+        if self._mod is not None:
+            self._mod.close()
+            self._mod = None
+
+
+def _repair_ldd(ldd):
+    """Cells whose receiver is missing or outside the map become pits (pcr.lddrepair / lddmask)."""
+    from .synth import LDD_DC, LDD_DR
+    nrow, ncol = ldd.shape
+    out = ldd.copy()
+    rr, cc = np.nonzero((ldd >= 1) & (ldd <= 9) & (ldd != 5))
+    for r, c in zip(rr, cc):
+        k = int(ldd[r, c])
+        r2, c2 = r + LDD_DR[k], c + LDD_DC[k]
+        if not (0 <= r2 < nrow and 0 <= c2 < ncol) or ldd[r2, c2] == 0:
+            out[r, c] = 5
+    return out
+
+
+def main(argv=None):
+    """python -m wflow_b200.framework -C case [-R runId] [-c ini] -- the reference's CLI for the path
+    (wflow/wflow_sbm.py:3531-3645), minus the options that address subsystems out of scope."""
+    import getopt
+    import sys
+    opts, _ = getopt.getopt(sys.argv[1:] if argv is None else argv, "C:R:c:T:S:I")
+    o = dict(opts)
+    m = WflowSbm(Dir=o.get("-C", "."), RunDir=o.get("-R", "run_default"), configfile=o.get("-c", "wflow_sbm.ini"))
+    m.createRunId()
+    if "-I" in o:
+        m.reinit = 1
+    m._runInitial()
+    m._runResume()
+    m._runDynamic(int(o.get("-S", 1)), int(o.get("-T", 0)) or m.nrTimeSteps)
+    m._runSuspend()
+    m._wf_shutdown()
+
+
+if __name__ == "__main__":
+    main()

@@ -290,3 +290,99 @@ def make_case(nrow, ncol, *, kind="pits", tile=1024, seed=42, timestepsecs=86400
     else:
         state = random_state(static, n_layers, layer_thickness, seed=seed + 7)
     return ldd, river, static, state
+
+
+def write_case_dir(path, nrow=24, ncol=24, *, kind="tiles", tile=12, nsteps=6, timestepsecs=86400, seed=3,
+                   layer_thickness=(100, 300, 800), model_snow=1, river_area=6):
+    """Write a small but complete wflow_sbm case directory (staticmaps/, intbl/, inmaps/ map stacks,
+    wflow_sbm.ini) in the reference's on-disk layout, for exercising the framework / BMI mirror."""
+    import os
+
+    from . import csf
+    from .framework import generate_name_t
+    os.makedirs(os.path.join(path, "staticmaps"), exist_ok=True)
+    os.makedirs(os.path.join(path, "intbl"), exist_ok=True)
+    os.makedirs(os.path.join(path, "inmaps"), exist_ok=True)
+    rng = np.random.default_rng(seed)
+    ldd = ldd_basin_tiles(nrow, ncol, tile=tile) if kind == "tiles" else ldd_random_forest(nrow, ncol, seed=seed)
+    up = upstream_count(ldd)
+    river = (up >= river_area).astype(np.int32)
+    info = csf.MapInfo(nrow, ncol, x_ul=100000.0, y_ul=500000.0, cellsize=1000.0, projection=1)
+    sub = np.where(ldd > 0, 1 + (np.arange(nrow)[:, None] >= nrow // 2) * 1, 0).astype(np.int32)
+    w = lambda name, a, vs=None: csf.write_map(os.path.join(path, "staticmaps", name), a, info, value_scale=vs,
+                                               mv=-999 if a.dtype.kind != "f" else -999.0)
+    w("wflow_ldd.map", np.where(ldd > 0, ldd, -999).astype(np.int32), csf.VS_LDD)
+    w("wflow_subcatch.map", np.where(sub > 0, sub, -999).astype(np.int32), csf.VS_ORDINAL)
+    w("wflow_river.map", np.where(river > 0, 1, -999).astype(np.int32), csf.VS_ORDINAL)
+    w("wflow_landuse.map", np.where(ldd > 0, 1 + rng.integers(0, 3, (nrow, ncol)), -999).astype(np.int32), csf.VS_ORDINAL)
+    w("wflow_soil.map", np.where(ldd > 0, 1 + rng.integers(0, 2, (nrow, ncol)), -999).astype(np.int32), csf.VS_ORDINAL)
+    gauges = np.full((nrow, ncol), -999, np.int32)
+    pits = np.argwhere(ldd == 5)
+    for i, (r, c) in enumerate(pits[:8]):
+        gauges[r, c] = i + 1
+    w("wflow_gauges.map", gauges, csf.VS_ORDINAL)
+    dem = (_smooth_noise(rng, nrow, ncol, 8) * F32(500.0) + F32(10.0)).astype(F32)
+    w("wflow_dem.map", np.where(ldd > 0, dem, F32(np.nan)).astype(F32))
+    w("RiverWidth.map", np.where(river > 0, F32(2.0) * np.power(np.maximum(up, 1).astype(F32), F32(0.35)), F32(0.0)).astype(F32))
+    tables = {
+        "KsatVer": ["[1,1] <,> [1,1] 600", "[2,2] <,> [1,1] 1500", "[3,> <,> [1,1] 250", "<,> <,> [2,> 900"],
+        "M": ["<,> <,> [1,1] 250", "<,> <,> [2,> 900"], "thetaS": ["<,> <,> <,> 0.48"], "thetaR": ["<,> <,> <,> 0.05"],
+        "SoilThickness": ["<,> [1,1] <,> 1800", "<,> [2,2] <,> 900"], "SoilMinThickness": ["<,> <,> <,> 400"],
+        "RootingDepth": ["[1,1] <,> <,> 300", "[2,> <,> <,> 600"], "MaxCanopyStorage": ["[1,1] <,> <,> 0.0", "[2,> <,> <,> 0.6"],
+        "CanopyGapFraction": ["<,2] <,> <,> 0.6", "<2,> <,> <,> 0.2"], "EoverR": ["<,> <,> <,> 0.1"],
+        "PathFrac": ["<,> <,> <,> 0.15"], "InfiltCapSoil": ["<,> <,> <,> 200"], "InfiltCapPath": ["<,> <,> <,> 8"],
+        "N": ["<,> <,> <,> 0.2"], "N_River": ["<,> <,> <,> 0.04"], "MaxLeakage": ["<,> <,> <,> 0.1"],
+        "KsatHorFrac": ["<,> <,> <,> 20"],
+        "c": ["<,> <,> <,> [0,0] 9.5", "<,> <,> <,> [1,1] 10.5", "<,> <,> <,> [2,> 11"],
+    }
+    for name, rows in tables.items():
+        with open(os.path.join(path, "intbl", name + ".tbl"), "w") as fh:
+            fh.write("\n".join(rows) + "\n")
+    forc = Forcing(nrow, ncol, seed=seed, timestepsecs=timestepsecs, rain_mean=12.0)
+    for t in range(nsteps):
+        P, PET, T = forc.step(t)
+        for stem, a in (("P", P), ("PET", PET), ("TEMP", T)):
+            csf.write_map(generate_name_t(os.path.join(path, "inmaps", stem), t + 1), a, info)
+    import datetime
+    start = datetime.datetime(2000, 1, 1)
+    end = start + datetime.timedelta(seconds=timestepsecs * (nsteps - 1))
+    with open(os.path.join(path, "wflow_sbm.ini"), "w") as fh:
+        fh.write("""[inputmapstacks]
+Precipitation = /inmaps/P
+EvapoTranspiration = /inmaps/PET
+Temperature = /inmaps/TEMP
+[run]
+starttime = %s
+endtime = %s
+timestepsecs = %d
+reinit = 1
+[layout]
+sizeinmetres = 1
+[model]
+modeltype = sbm
+ModelSnow = %d
+UStoreLayerThickness = %s
+[API]
+P = 0,mm
+PET = 0,mm
+TEMP = 0,oC
+zi = 2,mm
+SubsurfaceFlow = 2,mm3
+RiverRunoff = 2,m3/s
+LandRunoff = 2,m3/s
+UStoreLayerDepth_0 = 2,mm
+SatWaterDepth = 1,mm
+KsatVer = 3,mm
+[outputmaps]
+self.RiverRunoff = run
+[outputcsv_0]
+samplemap = staticmaps/wflow_subcatch.map
+self.InwaterMM = specrun.csv
+self.Precipitation = prec.csv
+self.ActEvap+self.Interception = teact.csv
+[outputtss_0]
+samplemap = staticmaps/wflow_gauges.map
+self.RiverRunoff = run.tss
+""" % (start.strftime("%Y-%m-%d %H:%M:%S"), end.strftime("%Y-%m-%d %H:%M:%S"), timestepsecs, model_snow,
+       ",".join(str(int(t)) for t in layer_thickness) if layer_thickness else "0"))
+    return ldd, river
