@@ -297,9 +297,9 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         dist.all_reduce(cells, op=dist.ReduceOp.SUM)
-        gl = torch.from_numpy(gq.astype(np.float32)).cuda()
-        out = [torch.empty_like(gl) for _ in range(world)]
-        dist.all_gather(out, gl)
+        from wflow_b200 import parallel
+        gathered = parallel.gather_series(gq)  # the path's only collective: outlet discharges of all ranks
+        assert len(gathered) == world
     ms, ms_e2e, ms_v, ms_l = [float(x) for x in tms.tolist()]
     total_cells = float(cells.item())
 
