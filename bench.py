@@ -111,7 +111,7 @@ def make_model_inputs(args, rank, nrow, ncol, schedule_factory):
     base["RiverWidth"] = np.where(river != 0, np.float32(2.0) * np.power(np.maximum(upf, 1), np.float32(0.35)), 0).astype(np.float32)
     base["BankfullDepth"] = np.where(river != 0, np.float32(1.0), np.float32(0.0)).astype(np.float32)
     static = params.derive_static(base, ldd, river, args.timestepsecs, cellsize=1000.0, n_layers=4)
-    state = synth.random_state(static, 4, lt, seed=99 + rank)
+    state = synth.random_state(static, 4, lt, seed=99 + rank, smooth=48)
     return ldd, river, sched, static, state, lt
 
 
@@ -182,7 +182,8 @@ def workload_config(args, it_l, it_r, **extra):
                        "(8 GPUs = the 16384x16384 grid)" % (args.tile, args.tile, args.timestepsecs, args.basins, nrow, ncol),
            "basins_per_gpu": args.basins, "tile": args.tile, "timestepsecs": args.timestepsecs,
            "it_kinL": it_l, "it_kinR": it_r, "layers": 4, "snow": 1,
-           "state": "well-mixed random initial state + warm-up steps (synth.random_state)",
+           "state": "spatially correlated random initial state (synth.random_state, 48-cell correlation length: water "
+                    "tables from surface to bottom, partly filled layers, snow, flowing rivers) + warm-up steps",
            "l2": "inputs larger than L2 (per-step working set >> 126 MB), no flush needed"}
     cfg.update(extra)
     return cfg

@@ -220,11 +220,31 @@ class Forcing:
         return p.astype(F32), pet.astype(F32), temp.astype(F32)
 
 
-def random_state(static, n_layers, layer_thickness, seed=0):
+class _SmoothRng:
+    """Drop-in for the few Generator methods random_state uses, returning spatially smooth fields
+    (bilinear noise, ~`coarse` cells correlation length) instead of white noise: neighbouring cells
+    then have similar water tables, snow packs ... like a real landscape."""
+
+    def __init__(self, seed, coarse):
+        self.rng = np.random.default_rng(seed)
+        self.coarse = coarse
+
+    def random(self, shape):
+        f = _smooth_noise(self.rng, shape[0], shape[1], self.coarse)
+        lo, hi = float(f.min()), float(f.max())
+        return ((f - lo) / max(hi - lo, 1e-6) * 0.999).astype(np.float64)  # stretched to [0, 1)
+
+    def uniform(self, lo, hi, shape):
+        return lo + (hi - lo) * self.random(shape)
+
+
+def random_state(static, n_layers, layer_thickness, seed=0, smooth=0):
     """A physically consistent but well-mixed initial state (instead of the cold start): water
     tables from the surface to the bottom, partly filled unsaturated layers, snow packs, wet
-    canopies, flowing rivers and land.  Exercises the branches a cold start never reaches."""
-    rng = np.random.default_rng(seed)
+    canopies, flowing rivers and land.  Exercises the branches a cold start never reaches.
+    smooth > 0: spatially correlated fields with that correlation length in cells (benchmarks);
+    0: white noise, every cell independent (tests: maximal branch coverage on small grids)."""
+    rng = _SmoothRng(seed, smooth) if smooth else np.random.default_rng(seed)
     st = static["SoilThickness"]
     shape = st.shape
     neff = (static["thetaS"] - static["thetaR"]).astype(F32)
