@@ -222,6 +222,7 @@ int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint
   if (cfg->n_layer_thickness < 0 || cfg->n_layer_thickness + 1 > WF_MAX_LAYERS)
     return fail(WF_EINVAL, "too many soil layers");
   if (cfg->it_kin_l < 1 || cfg->it_kin_r < 1) return fail(WF_EINVAL, "it_kin_l / it_kin_r must be >= 1");
+  if (cfg->it_kin_r > 8) return fail(WF_EUNSUPPORTED, "more than 8 river sub-steps are not supported");
   if (!(cfg->timestepsecs > 0)) return fail(WF_EINVAL, "timestepsecs must be > 0");
   const int64_t N = (int64_t)cfg->nrow * cfg->ncol;
   if (N >= (int64_t)1 << 31) return fail(WF_EUNSUPPORTED, "grids of 2^31 cells or more are not supported");
@@ -313,7 +314,7 @@ int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint
   dm.task_mask = 7;
   if (const char *tm = std::getenv("WF_LATERAL_TASKS")) dm.task_mask = std::atoi(tm);
   if (std::getenv("WF_TICK_PROFILE")) {
-    const size_t nt = (size_t)(m->net.nlevels() + 2 + cfg->it_kin_r) * 4;
+    const size_t nt = (size_t)(m->net.nlevels() + 8 + cfg->it_kin_r) * 8;
     CUDA_OK(cudaMallocManaged(&dm.dbg, sizeof(long long) * nt));
     std::memset(dm.dbg, 0, sizeof(long long) * nt);
   }
@@ -390,9 +391,11 @@ void wf_destroy(wf_model *m) {
     const char *path = std::getenv("WF_TICK_PROFILE");
     if (FILE *fp = std::fopen(path, "w")) {
       const int nt = m->dm.nlev + 1 + (m->nrnet > 0 ? m->dm.itR : 0);
-      std::fprintf(fp, "tick,subsurface_cyc,overland_cyc,river_cyc,clock_at_end\n");
+      std::fprintf(fp, "tick,subsurface_cyc,overland_cyc,river_cyc,clock_at_end,s0,s1,s2,s3\n");
+      const long long *s = m->dm.dbg + 4 * (m->dm.nlev + 8 + m->dm.itR);
       for (int t = 0; t < nt; t++)
-        std::fprintf(fp, "%d,%lld,%lld,%lld,%lld\n", t, m->dm.dbg[4 * t], m->dm.dbg[4 * t + 1], m->dm.dbg[4 * t + 2], m->dm.dbg[4 * t + 3]);
+        std::fprintf(fp, "%d,%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld\n", t, m->dm.dbg[4 * t], m->dm.dbg[4 * t + 1], m->dm.dbg[4 * t + 2],
+                     m->dm.dbg[4 * t + 3], s[4 * t], s[4 * t + 1], s[4 * t + 2], s[4 * t + 3]);
       std::fclose(fp);
     }
     cudaFree(m->dm.dbg);

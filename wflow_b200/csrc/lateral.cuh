@@ -156,16 +156,31 @@ __device__ __noinline__ void kinematic_wave_ssf(double ssf_in, double ssf_old, d
 
 // Fraction of an upstream neighbour's outflow that a river cell takes straight into the channel
 // (wflow_sbm.py:395-398, 843-846): slope-weighted for neighbours that drain in another direction.
-__device__ __forceinline__ double chan_perc(const DevModel &m, int64_t nb, int myldd, double slope_i) {
-  const int lnb = __ldg(m.topo + nb) & 15;
-  if (lnb == myldd) return 0.0;
-  const double slnb = (double)__ldg(m.f[F_landSlope] + nb);
-  return slnb / (slope_i + slnb);
+// All (up to 8) neighbours' ldd codes and slopes are fetched together -- one memory round trip --
+// and the fractions stay in registers (fully unrolled, no indexed local array).
+struct ChanPerc {
+  double cp[8];
+};
+__device__ __forceinline__ void chan_perc_all(const DevModel &m, int64_t us, int nup, int myldd, double slope_i,
+                                              ChanPerc &out) {
+  uint8_t tb[8];
+  float sl[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    tb[j] = (j < nup) ? __ldg(m.topo + us + j) : (uint8_t)0;
+    sl[j] = (j < nup) ? __ldg(m.f[F_landSlope] + us + j) : 0.0f;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const double slnb = (double)sl[j];
+    out.cp[j] = (j < nup && (tb[j] & 15) != myldd) ? slnb / (slope_i + slnb) : 0.0;
+  }
 }
 
 // ---- task 1: subsurface flow + post-ssf column tail of one cell ------------------------------
 template <int ML>
-__device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t i) {
+__device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t i, long long *stamp = nullptr) {
+  if (stamp) stamp[0] = clock64();
   const uint8_t tp = __ldg(m.topo + i);
   const int nup = tp >> 4;
   const int myldd = tp & 15;
@@ -195,11 +210,14 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
 #pragma unroll
   for (int j = 0; j < 8; j++) sv[j] = (j < nup) ? __ldcg(m.h_ssf + (int64_t)us + j) : 0.0;  // all loads in flight at once
   if (riverMap) {
-#pragma unroll 1
-    for (int j = 0; j < nup; j++) {
-      const double cp = chan_perc(m, (int64_t)us + j, myldd, slope_i);
-      ssf_in = ssf_in + (1 - cp) * sv[j];
-      ssf_tr = ssf_tr + cp * sv[j];
+    ChanPerc c;
+    chan_perc_all(m, (int64_t)us, nup, myldd, slope_i, c);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      if (j < nup) {
+        ssf_in = ssf_in + (1 - c.cp[j]) * sv[j];
+        ssf_tr = ssf_tr + c.cp[j] * sv[j];
+      }
     }
     m.h_ssf_tr[rs] = (float)(ssf_tr / (1000 * 1000 * 1000) / m.dt);
   } else {
@@ -208,6 +226,7 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
       if (j < nup) ssf_in = ssf_in + sv[j];
   }
 
+  if (stamp) { stamp[1] = clock64() + (long long)(ssf_in * 0.0) + (long long)(U[0] * 0.0) + (long long)(xlyl * 0.0) + (long long)(ssf_old * 0.0); }
   const double neff = (double)neff_f;
   const double dneff = thetaS - thetaR;
   const double r = rsum * DW * 1000;                                   // :674
@@ -216,6 +235,7 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
   double ssf_n, zi_n, ExfiltSatWater;
   kinematic_wave_ssf(ssf_in, ssf_old, zi_old, r, Kh, KsatVer, slope_i, neff, fpar, ST, efD, 1.0, DLd * 1000,
                      DW * 1000, ssfmax, ssf_n, zi_n, ExfiltSatWater);
+  if (stamp) stamp[2] = clock64() + (long long)(ssf_n * 0.0);
   const double zi = pymin(zi_n, ST);  // :702
   const double Sat = (ST - zi) * dneff;
   ssfp[i] = (float)ssf_n;
@@ -285,10 +305,12 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
     m.f[F_SoilWatbal][i] = (float)wb;
     if (m.f[F_watbal] && m.f[F_SurfaceWatbal]) m.f[F_watbal][i] = (float)wb + m.f[F_SurfaceWatbal][i];
   }
+  if (stamp) stamp[3] = clock64() + (long long)(InwaterO * 0.0);
 }
 
 // ---- task 2: overland flow of one cell, all sub-steps (wflow_sbm.py:830-879) -----------------
-__device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i) {
+__device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i, long long *stamp = nullptr) {
+  if (stamp) stamp[0] = clock64();
   const uint8_t tp = __ldg(m.topo + i);
   const int nup = tp >> 4;
   const int myldd = tp & 15;
@@ -300,30 +322,28 @@ __device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i
   const double dts = m.dt / itL;
   const double q = __ldcg(m.h_inwO + i) / DLd;
   double Qold = m.f[F_LandRunoffsub][i];
-  double chanperc[8];
-  if (riverMap) {
-    const double slope_i = LD(landSlope);
-#pragma unroll 1
-    for (int j = 0; j < nup; j++) chanperc[j] = chan_perc(m, (int64_t)us + j, myldd, slope_i);
-  }
+  ChanPerc c;
+  if (riverMap) chan_perc_all(m, (int64_t)us, nup, myldd, (double)LD(landSlope), c);
   double acc_flow = 0.0, acc_h = 0.0, Qo_in_acc = 0.0, qo_toriver_acc = 0.0;
   double wlsub = 0.0;  // dyn["WaterLevelLsub"] starts at 0 and is only written where SW > 0 (:873-878)
 #pragma unroll 1
   for (int v = 0; v < itL; v++) {
     float *qbuf = (v == itL - 1) ? m.f[F_LandRunoffsub] : m.qo_sub + (int64_t)v * m.n;
     double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    float qv[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) qv[j] = (j < nup) ? __ldcg(qbuf + (int64_t)us + j) : 0.0f;
     if (riverMap) {
-#pragma unroll 1
-      for (int j = 0; j < nup; j++) {
-        const double qv = (double)__ldcg(qbuf + (int64_t)us + j);
-        s1 = s1 + (1 - chanperc[j]) * qv;
-        s2 = s2 + chanperc[j] * qv;
-        s3 = s3 + qv;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        if (j < nup) {
+          const double q1 = (double)qv[j];
+          s1 = s1 + (1 - c.cp[j]) * q1;
+          s2 = s2 + c.cp[j] * q1;
+          s3 = s3 + q1;
+        }
       }
     } else {
-      float qv[8];
-#pragma unroll
-      for (int j = 0; j < 8; j++) qv[j] = (j < nup) ? __ldcg(qbuf + (int64_t)us + j) : 0.0f;
 #pragma unroll
       for (int j = 0; j < 8; j++)
         if (j < nup) s1 = s1 + (double)qv[j];
@@ -336,7 +356,9 @@ __device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i
       qo_in = s1; qo_toriver_vol = 0.0;
     }
     double qbeta;
+    if (stamp) stamp[1] = clock64() + (long long)(qo_in * 0.0) + (long long)(q * 0.0) + (long long)(Qold * 0.0) + (long long)(AlphaL * 0.0);
     const double qn = kinematic_wave(qo_in, Qold, q, AlphaL, Beta, dts, DLd, qbeta);
+    if (stamp) stamp[2] = clock64() + (long long)(qn * 0.0);
     acc_flow = acc_flow + qn * dts;
     Qo_in_acc = Qo_in_acc + qo_in * dts;
     qo_toriver_acc = qo_toriver_acc + qo_toriver_vol;
@@ -364,6 +386,7 @@ __device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i
       m.f[F_RiverRunoffsub][rs] = 0.0f; m.f[F_WaterLevelRsub][rs] = 0.0f;
     }
   }
+  if (stamp) stamp[3] = clock64();
 }
 
 // ---- task 3: one sub-step of the river kinematic wave for one river cell (river order) -------
@@ -373,6 +396,13 @@ __device__ __forceinline__ void task_river(const DevModel &m, const int32_t rs, 
   const int nup = __ldg(m.r_nup + rs);
   const uint32_t us = __ldg(m.r_up_start + rs);
   float *qbuf = (v == itR - 1) ? m.f[F_RiverRunoffsub] : m.qr_sub + (int64_t)v * m.nr;
+  // own-cell operands: all independent, issued together with the topology (one round trip)
+  const float DCLf = __ldg(m.f[F_DCL] + rs);
+  const float inw = __ldcg(m.h_inwater + rs);
+  const double A = __ldg(m.f[F_AlphaR] + rs), Bw = __ldg(m.f[F_Bw] + rs);
+  const double Qo = (v == 0) ? (double)m.f[F_RiverRunoffsub][rs] : (double)__ldcg(m.qr_sub + (int64_t)(v - 1) * m.nr + rs);
+  double racc0 = 0.0, rh0 = 0.0;
+  if (v > 0) { racc0 = __ldcg(m.h_racc + rs); rh0 = __ldcg(m.h_rh + rs); }
   double Qin = 0.0;
   {
     float qv[8];
@@ -382,18 +412,13 @@ __device__ __forceinline__ void task_river(const DevModel &m, const int32_t rs, 
     for (int j = 0; j < 8; j++)
       if (j < nup) Qin = Qin + (double)qv[j];
   }
-  const float DCLf = __ldg(m.f[F_DCL] + rs);
-  const double qr = (double)(__ldcg(m.h_inwater + rs) / DCLf);  // :3152 (REAL4 division)
-  const double A = __ldg(m.f[F_AlphaR] + rs), Bw = __ldg(m.f[F_Bw] + rs);
+  const double qr = (double)(inw / DCLf);  // :3152 (REAL4 division)
   const double dtr = m.dt / itR;
-  // Qold: the previous sub-step's outflow of this cell, or the state at the first sub-step (:199)
-  const double Qo = (v == 0) ? (double)m.f[F_RiverRunoffsub][rs]
-                             : (double)__ldcg(((v - 1 == itR - 1) ? m.f[F_RiverRunoffsub] : m.qr_sub + (int64_t)(v - 1) * m.nr) + rs);
+  // Qo: the previous sub-step's outflow of this cell, or the state at the first sub-step (:199)
   double qbeta;
   const double qn = kinematic_wave(Qin, Qo, qr, A, m.beta, dtr, (double)DCLf, qbeta);
   const double wl = (A * qbeta) / Bw;
-  double racc = qn * dtr, rh = wl;
-  if (v > 0) { racc = __ldcg(m.h_racc + rs) + racc; rh = __ldcg(m.h_rh + rs) + rh; }
+  const double racc = racc0 + qn * dtr, rh = rh0 + wl;
   qbuf[rs] = (float)qn;
   if (v == itR - 1) {
     m.f[F_RiverRunoff][rs] = (float)(racc / m.dt);
@@ -410,47 +435,78 @@ __device__ __forceinline__ void task_river(const DevModel &m, const int32_t rs, 
 // sub-step v runs at tick level+2+v, strictly after its sub-step v-1 and before anyone reads v.
 
 // ---- the wavefront -------------------------------------------------------------------------------
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Pull the operands of the cell this thread will most likely solve next tick into L2 while the
+// current tick is still waiting at the barrier (they are cold DRAM lines otherwise: every array is
+// touched once per timestep).
+__device__ __forceinline__ void prefetch_subsurface(const DevModel &m, const int64_t i) {
+  prefetch_l2(m.topo + i); prefetch_l2(m.up_start + i); prefetch_l2(m.river_slot + i);
+  prefetch_l2(m.h_r + i); prefetch_l2(m.h_surplus + i); prefetch_l2(m.f[F_zi] + i); prefetch_l2(m.f[F_SubsurfaceFlow] + i);
+  prefetch_l2(m.f[F_landSlope] + i); prefetch_l2(m.f[F_SoilThickness] + i); prefetch_l2(m.f[F_thetaS] + i);
+  prefetch_l2(m.f[F_thetaR] + i); prefetch_l2(m.f[F_KsatVer] + i); prefetch_l2(m.f[F_f] + i);
+  prefetch_l2(m.f[F_KsatHorFrac] + i); prefetch_l2(m.f[F_DW] + i); prefetch_l2(m.f[F_DL] + i);
+  prefetch_l2(m.f[F_xl] + i); prefetch_l2(m.f[F_yl] + i);
+  for (int k = 0; k < m.ML; k++) { prefetch_l2(m.f[F_UStoreLayerDepth_0 + k] + i); prefetch_l2(m.h_ulo + (int64_t)k * m.n + i); }
+  // the overland solve of the same cell follows one tick later
+  prefetch_l2(m.f[F_SW] + i); prefetch_l2(m.f[F_AlphaL] + i); prefetch_l2(m.f[F_LandRunoffsub] + i);
+}
+
 template <int ML>
 __global__ void __launch_bounds__(256) k_lateral_wave(const DevModel m) {
   cg::grid_group grid = cg::this_grid();
-  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t gsize = (int64_t)gridDim.x * blockDim.x;
+  const int gtid = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  const int gsize = (int)(gridDim.x * blockDim.x);
   const int D = m.nlev, itR = m.itR;
+  const bool rivers = m.nrnet > 0 && (m.task_mask & 4);
   const int nticks = D + 1 + ((m.nrnet > 0) ? itR : 0);
   for (int t = 0; t < nticks; t++) {
-    // item space of this tick: [subsurface cells of level t][overland cells of level t-1]
-    //                          [river cells of full level t-2-v, sub-step v, v = 0..itR-1]
-    int64_t base = 0;
+    // Item space of this tick, one flat index j over
+    //   [subsurface cells of level t][overland cells of level t-1][river cells of level t-2-v, sub-step v = 0..itR-1]
+    // consecutive threads take consecutive items, so a warp almost always runs a single task type and
+    // the three solves of a tick proceed concurrently on different warps.
     long long c0 = 0;
     if (m.dbg) c0 = clock64();
-    if (t < D && (m.task_mask & 1)) {
-      const int64_t beg = m.lev_off[t], cnt = m.lev_off[t + 1] - beg;
-      bool any = false;
-      for (int64_t k = gtid; k < cnt; k += gsize) { task_subsurface<ML>(m, beg + k); any = true; }
-      base += cnt;
-      if (m.dbg && any) { atomicMax((unsigned long long *)&m.dbg[4 * t + 0], (unsigned long long)(clock64() - c0)); c0 = clock64(); }
-    }
-    if (t >= 1 && t - 1 < D && (m.task_mask & 2)) {
-      const int64_t beg = m.lev_off[t - 1], cnt = m.lev_off[t] - beg;
-      bool any = false;
-      // rotate the thread assignment so that this task lands on other warps than the subsurface one
-      for (int64_t k = (gtid + gsize - (base % gsize)) % gsize; k < cnt; k += gsize) { task_overland(m, beg + k); any = true; }
-      base += cnt;
-      if (m.dbg && any) { atomicMax((unsigned long long *)&m.dbg[4 * t + 1], (unsigned long long)(clock64() - c0)); c0 = clock64(); }
-    }
-    if (m.nrnet > 0 && (m.task_mask & 4)) {
-      for (int v = 0; v < itR; v++) {
+    int64_t beg0 = 0, beg1 = 0;
+    int cnt0 = 0, cnt1 = 0;
+    if (t < D && (m.task_mask & 1)) { beg0 = m.lev_off[t]; cnt0 = (int)(m.lev_off[t + 1] - beg0); }
+    if (t >= 1 && t - 1 < D && (m.task_mask & 2)) { beg1 = m.lev_off[t - 1]; cnt1 = (int)(m.lev_off[t] - beg1); }
+    int rbeg[8], rcnt[8], total = cnt0 + cnt1;
+    const int nv = rivers ? (itR < 8 ? itR : 8) : 0;
+#pragma unroll
+    for (int v = 0; v < 8; v++) {
+      rbeg[v] = 0; rcnt[v] = 0;
+      if (v < nv) {
         const int lr = (t - 2 - v) - m.rlev_shift;  // river level solved for sub-step v at this tick
-        if (lr < 0 || lr >= m.nrlev) continue;
-        const int64_t beg = m.rlev_off[lr], cnt = m.rlev_off[lr + 1] - beg;
-        bool any = false;
-        for (int64_t k = (gtid + gsize - (base % gsize)) % gsize; k < cnt; k += gsize) { task_river(m, (int32_t)(beg + k), v); any = true; }
-        base += cnt;
-        if (m.dbg && any) { atomicMax((unsigned long long *)&m.dbg[4 * t + 2], (unsigned long long)(clock64() - c0)); c0 = clock64(); }
+        if (lr >= 0 && lr < m.nrlev) { rbeg[v] = (int)m.rlev_off[lr]; rcnt[v] = (int)(m.rlev_off[lr + 1] - m.rlev_off[lr]); }
+      }
+      total += rcnt[v];
+    }
+    for (int j = gtid; j < total; j += gsize) {
+      if (j < cnt0) {
+        task_subsurface<ML>(m, beg0 + j, nullptr);
+        if (m.dbg) atomicMax((unsigned long long *)&m.dbg[4 * t + 0], (unsigned long long)(clock64() - c0));
+      } else if (j < cnt0 + cnt1) {
+        task_overland(m, beg1 + (j - cnt0), (m.dbg && j == cnt0) ? m.dbg + 4 * (m.nlev + 8 + m.itR) + 4 * t : nullptr);
+        if (m.dbg) atomicMax((unsigned long long *)&m.dbg[4 * t + 1], (unsigned long long)(clock64() - c0));
+      } else {
+        int jj = j - cnt0 - cnt1;
+#pragma unroll
+        for (int v = 0; v < 8; v++) {
+          if (jj >= 0 && jj < rcnt[v]) { task_river(m, rbeg[v] + jj, v); jj = -1; }
+          else if (jj >= 0) jj -= rcnt[v];
+        }
+        if (m.dbg) atomicMax((unsigned long long *)&m.dbg[4 * t + 2], (unsigned long long)(clock64() - c0));
       }
     }
     if (m.dbg && gtid == 0) m.dbg[4 * t + 3] = clock64();
-    if (t + 1 < nticks) grid.sync();
+    if (t + 1 < nticks) {
+      if (t + 1 < D) {  // warm L2 with next tick's operands while we wait
+        const int64_t nb = m.lev_off[t + 1], ne = m.lev_off[t + 2];
+        if (nb + gtid < ne) prefetch_subsurface(m, nb + gtid);
+      }
+      grid.sync();
+    }
   }
 }
 
