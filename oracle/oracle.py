@@ -56,7 +56,13 @@ def lib():
 
 def set_threads(n):
     """Threads used by Oracle.step (OpenMP over the cells of a level); returns the count in use."""
-    n = max(1, min(int(n), lib().wfo_max_threads()))
+    # cap by the CPUs this process may run on, not by OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1);
+    # the OpenMP loops carry an explicit num_threads() clause
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    n = max(1, min(int(n), avail)) if lib().wfo_has_openmp() else 1
     lib().wfo_set_threads(n)
     return n
 

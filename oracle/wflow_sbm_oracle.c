@@ -100,6 +100,14 @@ int wfo_max_threads(void) {
 #endif
 }
 
+int wfo_has_openmp(void) {
+#ifdef _OPENMP
+  return 1;
+#else
+  return 0;
+#endif
+}
+
 int wfo_nfields(void) { return WFO_NFIELDS; }
 const char *wfo_field_name(int i) { return (i >= 0 && i < WFO_NFIELDS) ? wfo_names[i] : 0; }
 
