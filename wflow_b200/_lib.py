@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwflowsbm.so")
+LIB_PATH = os.environ.get("WFLOW_B200_LIB", os.path.join(_HERE, "libwflowsbm.so"))  # override: development aid
 
 WF_MAX_LAYERS = 8
 

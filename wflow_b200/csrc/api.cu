@@ -110,7 +110,7 @@ int launch_step(wf_model *m) {
     m->tev_used += 3;
   }
   if (m->timed) cudaEventRecord(e0, m->stream);
-  const int tb = 128;
+  const int tb = WF_VERT_THREADS;
   k_vertical<ML><<<(unsigned)((n + tb - 1) / tb), tb, 0, m->stream>>>(m->dm);
   m->launches++;
   if (m->timed) cudaEventRecord(e1, m->stream);
