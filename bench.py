@@ -328,6 +328,7 @@ def run_b200(args):
                          "full_step_gbs_at_333B": ncell * BYTES_FULL / ((ms_v + ms_l) / max(nst, 1) / 1e3) / 1e9},
             "kernels_ms_per_step": {"vertical": ms_v / max(nst, 1), "lateral": ms_l / max(nst, 1),
                                     "lateral_us_per_level": ms_l / max(nst, 1) * 1e3 / max(mod.num_levels, 1)},
+            "lateral_plan": mod.lateral_plan,
             "clocks": clk.summary(),
         }
         if world == 1 and not args.no_cpu_baseline:

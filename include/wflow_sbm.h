@@ -85,6 +85,16 @@ int wf_schedule_catchment_total(const wf_schedule *s, const float *values, doubl
 int wf_create_from_schedule(const wf_config *cfg, wf_schedule *s, const uint8_t *ldd, const uint8_t *river,
                             wf_model **out);
 
+/* Storage layout (host-only, no GPU needed).  The device arrays are stored group-major: a group is
+ * a set of whole basins (cells draining to the same pit) that one thread-block cluster sweeps on
+ * its own, level by level; set_dd's walk over all basins at once (wflow/wflow_funcs.py:79-95) is
+ * thereby split along its independent trees.  Packs the basins of `s` into at most `ngroups` groups
+ * and returns the number used.  Outputs (any may be NULL): storage_order[ncells] flat grid index of
+ * each storage position; group_off[ngroups+1] storage range of each group; up_start[ncells] /
+ * nup[ncells] the contiguous run of upstream neighbours of each cell, in storage positions. */
+int wf_schedule_partition(const wf_schedule *s, int ngroups, int64_t *storage_order, int64_t *group_off,
+                          int64_t *up_start, uint8_t *nup);
+
 int64_t wf_num_cells(const wf_model *m);        /* cells in the drainage network */
 int64_t wf_num_levels(const wf_model *m);
 int64_t wf_num_river_cells(const wf_model *m);  /* cells of the river network (rnodes) */
@@ -138,6 +148,10 @@ int wf_last_step_ms(wf_model *m, float ms[3]);
  * *nsteps = steps covered.  wf_timing_get synchronises the stream. */
 int wf_timing_reset(wf_model *m);
 int wf_timing_get(wf_model *m, double ms[3], int64_t *nsteps);
+/* How the lateral sweep is launched for this network: out[0] = 0 cooperative grid (one group),
+ * 1 thread-block clusters, 2 single blocks; out[1] = blocks per cluster; out[2] = groups;
+ * out[3] = blocks launched (0 before the first step). */
+int wf_lateral_plan(const wf_model *m, int32_t out[4]);
 /* Number of kernel launches issued by the model since creation. */
 int64_t wf_launch_count(const wf_model *m);
 /* The CUDA stream (cudaStream_t) the model launches on. */

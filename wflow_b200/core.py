@@ -80,6 +80,17 @@ class Schedule:
         _lib.check(self._l.wf_schedule_catchment_total(self._h, None if v is None else v.ctypes.data, out.ctypes.data))
         return out
 
+    def partition(self, ngroups):
+        """Storage layout for `ngroups` groups of whole basins: (storage_order, group_off, up_start, nup)."""
+        n = self.num_cells
+        order = np.zeros(max(n, 1), np.int64)
+        goff = np.zeros(int(ngroups) + 1, np.int64)
+        ups = np.zeros(max(n, 1), np.int64)
+        nup = np.zeros(max(n, 1), np.uint8)
+        g = _lib.check(self._l.wf_schedule_partition(self._h, int(ngroups), order.ctypes.data, goff.ctypes.data,
+                                                     ups.ctypes.data, nup.ctypes.data))
+        return order[:n], goff[: g + 1], ups[:n], nup[:n]
+
     def _release(self):
         h, self._h = self._h, None
         return h
@@ -221,6 +232,14 @@ class SbmModel:
         ms = (C.c_float * 3)()
         _lib.check(self._l.wf_last_step_ms(self._h, ms))
         return tuple(ms)
+
+    @property
+    def lateral_plan(self):
+        """How the lateral sweep runs: dict(mode=grid|cluster|cta, cluster_size, groups, blocks)."""
+        out = (C.c_int32 * 4)()
+        _lib.check(self._l.wf_lateral_plan(self._h, out))
+        return {"mode": ("grid", "cluster", "cta")[out[0]], "cluster_size": int(out[1]), "groups": int(out[2]),
+                "blocks": int(out[3])}
 
     @property
     def launch_count(self):

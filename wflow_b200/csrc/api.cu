@@ -62,7 +62,13 @@ struct wf_schedule {
 
 struct wf_model {
   wf_config cfg;
-  Network net, rnet;                 // full and river-only schedules (reference form recoverable)
+  Network net, rnet;                 // full and river-only schedules in the reference's (level-major) form
+  Network snet, srnet;               // the same forests in storage order (group-major, network.h)
+  GroupLayout lay, rlay;
+  int lat_mode = 0, cluster_size = 1, lat_blocks = 0;  // how the lateral sweep is launched (plan_lateral)
+  size_t lat_smem = 0;
+  GroupDesc *d_groups = nullptr;
+  uint32_t *d_lev_off = nullptr, *d_rlev_off = nullptr;
   std::vector<int32_t> river_slot;   // network order -> river order (or -1)
   std::vector<int64_t> river_flat;   // river order -> flat grid index (first nrnet: rnet.order)
   int64_t n = 0;
@@ -71,12 +77,11 @@ struct wf_model {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_last[3] = {nullptr, nullptr, nullptr};
-  int64_t *d_order = nullptr, *d_rorder = nullptr, *d_lev_off = nullptr;
+  int64_t *d_order = nullptr, *d_rorder = nullptr;
   float *d_stage = nullptr;          // nrow*ncol staging raster
   std::vector<float *> snapshot;     // quick-suspend copies of the state arrays
   std::vector<AreaSet> areas;
   int64_t launches = 0;
-  int coop_blocks = 0;
   int64_t max_tick_items = 1;
   bool timed = false;
   int ML = 1;
@@ -100,6 +105,113 @@ int ensure_field(wf_model *m, int id) {
   return WF_OK;
 }
 
+// ---- lateral sweep: plan and launch ---------------------------------------------------------------
+// The sweep of a group is latency-bound (one barrier + one Newton solve per level), so the plan
+// maximises the number of groups swept concurrently while keeping a tick to one or two passes:
+//   * many basins          -> one group per thread block (__syncthreads per tick)
+//   * a few wide basins    -> one group per thread-block cluster of 2..8 blocks (cluster barrier)
+//   * one basin wider than a cluster can hold -> cooperative launch over the whole GPU (grid barrier)
+// Cycle figures are measured on B200; WF_LATERAL_MODE / WF_CLUSTER_SIZE /
+// WF_GROUPS override the choice (development aid).
+struct LateralPlan {
+  int mode = WF_GRID, cs = 1, groups = 1;
+  double cost = 0;
+};
+
+template <int ML>
+int resident_clusters(int mode, int cs, size_t smem) {
+  if (mode == WF_CTA) {
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lateral_wave<ML, WF_CTA>, WF_GROUP_THREADS, smem);
+    return sms * per_sm;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)cs * 64);
+  cfg.blockDim = dim3(WF_GROUP_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cs;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int nc = 0;
+  if (cudaOccupancyMaxActiveClusters(&nc, k_lateral_wave<ML, WF_CLUSTER>, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return nc;
+}
+
+template <int ML>
+LateralPlan plan_lateral(int64_t n, int64_t D, int64_t nbasins, int sms) {
+  const double items = 2.1 * (double)n / (double)std::max<int64_t>(D, 1);  // per tick, whole network
+  LateralPlan best;
+  {  // grid: barrier ~2800 cycles, post-barrier load chain + solve ~9000, ~3500 per pass of one item per thread
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lateral_wave<ML, WF_GRID>, 256, 0);
+    const double threads = (double)sms * std::max(per_sm, 1) * 256;
+    best.mode = WF_GRID; best.cs = 1; best.groups = 1;
+    best.cost = (double)D * (2800 + 9000 + std::ceil(items / threads) * 3500);
+  }
+  const int sizes[] = {1, 2, 4, 8};
+  for (int cs : sizes) {
+    const int mode = (cs == 1) ? WF_CTA : WF_CLUSTER;
+    const int res = resident_clusters<ML>(mode, cs, 0);
+    if (res < 1) continue;
+    const int64_t G = std::min<int64_t>(nbasins, res);
+    if (G < 1) continue;
+    const double per_group = items / (double)G;
+    const double sync = (cs == 1) ? 60 : 450;
+    const double cost = (double)D * (sync + 4500 + std::ceil(per_group / (cs * (double)WF_GROUP_THREADS)) * 3500);
+    if (cost < best.cost) { best.mode = mode; best.cs = cs; best.groups = (int)G; best.cost = cost; }
+  }
+  return best;
+}
+
+template <int ML>
+int launch_lateral(wf_model *m) {
+  void *args[] = {(void *)&m->dm};
+  if (m->lat_mode == WF_GRID) {
+    if (m->lat_blocks == 0) {
+      int dev = 0, sms = 0, per_sm = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lateral_wave<ML, WF_GRID>, 256, 0);
+      if (per_sm < 1) return fail(WF_ENODEVICE, "k_lateral_wave does not fit on an SM");
+      // no more blocks than the busiest tick can use (subsurface + overland + river items)
+      m->lat_blocks = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * per_sm, (m->max_tick_items + 255) / 256));
+    }
+    CUDA_OK(cudaLaunchCooperativeKernel((void *)k_lateral_wave<ML, WF_GRID>, dim3(m->lat_blocks), dim3(256), args, 0, m->stream));
+    return WF_OK;
+  }
+  const bool cta = m->lat_mode == WF_CTA;
+  void *fn = cta ? (void *)k_lateral_wave<ML, WF_CTA> : (void *)k_lateral_wave<ML, WF_CLUSTER>;
+  if (m->lat_blocks == 0) {
+    if (m->lat_smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->lat_smem));
+    const int res = resident_clusters<ML>(m->lat_mode, m->cluster_size, m->lat_smem);
+    if (res < 1) return fail(WF_ENODEVICE, "k_lateral_wave does not fit on the device");
+    m->lat_blocks = std::min(res, m->dm.ngroups) * m->cluster_size;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)m->lat_blocks);
+  cfg.blockDim = dim3(WF_GROUP_THREADS);
+  cfg.dynamicSmemBytes = m->lat_smem;
+  cfg.stream = m->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)m->cluster_size;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = cta ? 0 : 1;
+  CUDA_OK(cudaLaunchKernelExC(&cfg, fn, args));
+  return WF_OK;
+}
+
 template <int ML>
 int launch_step(wf_model *m) {
   const int64_t n = m->n;
@@ -114,20 +226,7 @@ int launch_step(wf_model *m) {
   k_vertical<ML><<<(unsigned)((n + tb - 1) / tb), tb, 0, m->stream>>>(m->dm);
   m->launches++;
   if (m->timed) cudaEventRecord(e1, m->stream);
-  {
-    if (m->coop_blocks == 0) {
-      int dev = 0, sms = 0, per_sm = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lateral_wave<ML>, 256, 0);
-      if (per_sm < 1) return fail(WF_ENODEVICE, "k_lateral_wave does not fit on an SM");
-      m->coop_blocks = sms * per_sm;
-    }
-    // no more blocks than the busiest tick can use (subsurface + overland + river items)
-    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(m->coop_blocks, (m->max_tick_items + 255) / 256));
-    void *args[] = {(void *)&m->dm};
-    CUDA_OK(cudaLaunchCooperativeKernel((void *)k_lateral_wave<ML>, dim3(blocks), dim3(256), args, 0, m->stream));
-  }
+  if (int rc = launch_lateral<ML>(m)) return rc;
   m->launches++;
   if (m->timed) cudaEventRecord(e2, m->stream);
   m->ev_last[0] = e0; m->ev_last[1] = e1; m->ev_last[2] = e2;
@@ -147,6 +246,19 @@ int dispatch_step(wf_model *m) {
     case 8: return launch_step<8>(m);
   }
   return fail(WF_EINVAL, "unsupported number of soil layers");
+}
+
+LateralPlan dispatch_plan(int ML, int64_t n, int64_t D, int64_t nbasins, int sms) {
+  switch (ML) {
+    case 1: return plan_lateral<1>(n, D, nbasins, sms);
+    case 2: return plan_lateral<2>(n, D, nbasins, sms);
+    case 3: return plan_lateral<3>(n, D, nbasins, sms);
+    case 4: return plan_lateral<4>(n, D, nbasins, sms);
+    case 5: return plan_lateral<5>(n, D, nbasins, sms);
+    case 6: return plan_lateral<6>(n, D, nbasins, sms);
+    case 7: return plan_lateral<7>(n, D, nbasins, sms);
+    default: return plan_lateral<8>(n, D, nbasins, sms);
+  }
 }
 
 const int kRequired[] = {F_P, F_PET, F_Cmax, F_EoverR, F_CanopyGapFraction, F_et_RefToPot, F_WaterFrac,
@@ -262,30 +374,77 @@ int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint
   }
   m->n = m->net.ncells;
   const int64_t n = m->n;
-  // river order: river-network cells in rnodes order, then river-map cells kin_wave never visits
+  // ---- storage layout: groups of whole basins, one sweep each (network.h, plan_lateral) ----
+  {
+    std::vector<int32_t> basin, gob;
+    std::vector<int64_t> bcells;
+    const int64_t nbasins = label_basins(m->net, basin, bcells);
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+    LateralPlan plan = dispatch_plan(m->ML, n, m->net.nlevels(), nbasins, sms);
+    if (const char *e = std::getenv("WF_LATERAL_MODE")) {
+      const std::string v(e);
+      if (v == "grid") { plan.mode = WF_GRID; plan.cs = 1; plan.groups = 1; }
+      else if (v == "cta") { plan.mode = WF_CTA; plan.cs = 1; plan.groups = (int)std::min<int64_t>(std::max<int64_t>(nbasins, 1), sms); }
+      else if (v == "cluster") {
+        plan.mode = WF_CLUSTER;
+        if (plan.cs < 2) plan.cs = 4;
+        plan.groups = (int)std::min<int64_t>(std::max<int64_t>(nbasins, 1), sms / plan.cs);
+      }
+    }
+    if (const char *e = std::getenv("WF_CLUSTER_SIZE")) {
+      const int cs = std::atoi(e);
+      if (plan.mode == WF_CLUSTER && (cs == 2 || cs == 4 || cs == 8)) {
+        plan.cs = cs;
+        plan.groups = (int)std::min<int64_t>(std::max<int64_t>(nbasins, 1), sms / cs);
+      }
+    }
+    if (const char *e = std::getenv("WF_GROUPS"))
+      if (plan.mode != WF_GRID && std::atoi(e) >= 1) plan.groups = std::atoi(e);
+    if (plan.mode == WF_GRID) plan.groups = 1;
+    const int G = pack_basins(bcells, plan.groups, gob);
+    std::vector<int32_t> group_of((size_t)std::max<int64_t>(n, 1), 0);
+    for (int64_t k = 0; k < n; k++) group_of[(size_t)k] = gob.empty() ? 0 : gob[(size_t)basin[(size_t)k]];
+    std::vector<int64_t> newpos;
+    regroup(m->net, group_of, G, m->snet, m->lay, newpos);
+    // river network: a river cell belongs to the group of its basin
+    std::vector<int32_t> grp_of_flat;
+    {
+      std::vector<int32_t> tmp((size_t)N, 0);
+      for (int64_t k = 0; k < n; k++) tmp[(size_t)m->net.order[(size_t)k]] = group_of[(size_t)k];
+      grp_of_flat.swap(tmp);
+    }
+    std::vector<int32_t> rgroup_of((size_t)std::max<int64_t>(m->rnet.ncells, 1), 0);
+    for (int64_t k = 0; k < m->rnet.ncells; k++) rgroup_of[(size_t)k] = grp_of_flat[(size_t)m->rnet.order[(size_t)k]];
+    std::vector<int64_t> rnewpos;
+    regroup(m->rnet, rgroup_of, G, m->srnet, m->rlay, rnewpos);
+    m->lat_mode = plan.mode;
+    m->cluster_size = plan.cs;
+  }
+  const Network &snet = m->snet, &srnet = m->srnet;
+  // river order: river-network cells in storage order, then river-map cells kin_wave never visits
   m->river_slot.assign((size_t)std::max<int64_t>(n, 1), -1);
   {
     std::vector<int32_t> slot_of_flat((size_t)N, -1);
     std::vector<int32_t> pos_of_flat((size_t)N, -1);
-    for (int64_t k = 0; k < n; k++) pos_of_flat[(size_t)m->net.order[(size_t)k]] = (int32_t)k;
+    for (int64_t k = 0; k < n; k++) pos_of_flat[(size_t)snet.order[(size_t)k]] = (int32_t)k;
     int32_t s = 0;
-    for (int64_t k = 0; k < m->rnet.ncells; k++) {
-      const int64_t fl = m->rnet.order[(size_t)k];
-      if (pos_of_flat[(size_t)fl] < 0) continue;  // cannot happen: river network is a sub-forest
-      slot_of_flat[(size_t)fl] = s++;
+    for (int64_t k = 0; k < srnet.ncells; k++) {
+      const int64_t fl = srnet.order[(size_t)k];
+      slot_of_flat[(size_t)fl] = s++;  // the river network is a sub-forest of the full one
       m->river_flat.push_back(fl);
     }
     m->nrnet = s;
     if (river)
       for (int64_t k = 0; k < n; k++) {
-        const int64_t fl = m->net.order[(size_t)k];
+        const int64_t fl = snet.order[(size_t)k];
         if (river[fl] && slot_of_flat[(size_t)fl] < 0) {
           slot_of_flat[(size_t)fl] = s++;
           m->river_flat.push_back(fl);
         }
       }
     m->nr = s;
-    for (int64_t k = 0; k < n; k++) m->river_slot[(size_t)k] = slot_of_flat[(size_t)m->net.order[(size_t)k]];
+    for (int64_t k = 0; k < n; k++) m->river_slot[(size_t)k] = slot_of_flat[(size_t)snet.order[(size_t)k]];
   }
 
   CUDA_OK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
@@ -313,12 +472,13 @@ int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint
   dm.beta = m->cfg.beta;
   dm.task_mask = 7;
   if (const char *tm = std::getenv("WF_LATERAL_TASKS")) dm.task_mask = std::atoi(tm);
+#ifdef WF_PROFILE
   if (std::getenv("WF_TICK_PROFILE")) {
-    const size_t nt = (size_t)(m->net.nlevels() + 8 + cfg->it_kin_r) * 8;
-    CUDA_OK(cudaMallocManaged(&dm.dbg, sizeof(long long) * nt));
-    std::memset(dm.dbg, 0, sizeof(long long) * nt);
+    const size_t nt = (size_t)(m->net.nlevels() + 16 + cfg->it_kin_r) * 16;
+    CUDA_OK(cudaMallocManaged(&dm.prof, sizeof(unsigned long long) * nt));
+    std::memset(dm.prof, 0, sizeof(unsigned long long) * nt);
   }
-
+#endif
   auto upload = [&](const void *src, size_t bytes, void **dst) -> int {
     CUDA_OK(cudaMalloc(dst, std::max<size_t>(bytes, 16)));
     if (bytes) CUDA_OK(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
@@ -327,14 +487,37 @@ int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint
   int rc;
   std::vector<uint8_t> topo((size_t)std::max<int64_t>(n, 1));
   for (int64_t k = 0; k < n; k++)
-    topo[(size_t)k] = (uint8_t)((m->net.nup[(size_t)k] << 4) | (ldd[m->net.order[(size_t)k]] & 15));
-  if ((rc = upload(m->net.order.data(), sizeof(int64_t) * n, (void **)&m->d_order))) return rc;
+    topo[(size_t)k] = (uint8_t)((snet.nup[(size_t)k] << 4) | (ldd[snet.order[(size_t)k]] & 15));
+  if ((rc = upload(snet.order.data(), sizeof(int64_t) * n, (void **)&m->d_order))) return rc;
   if ((rc = upload(m->river_flat.data(), sizeof(int64_t) * m->nr, (void **)&m->d_rorder))) return rc;
-  if ((rc = upload(m->net.lev_off.data(), sizeof(int64_t) * m->net.lev_off.size(), (void **)&m->d_lev_off))) return rc;
-  if ((rc = upload(m->net.up_start.data(), sizeof(uint32_t) * n, (void **)&dm.up_start))) return rc;
+  if ((rc = upload(m->lay.lev_off.data(), sizeof(uint32_t) * m->lay.lev_off.size(), (void **)&m->d_lev_off))) return rc;
+  if ((rc = upload(m->rlay.lev_off.data(), sizeof(uint32_t) * m->rlay.lev_off.size(), (void **)&m->d_rlev_off))) return rc;
+  if ((rc = upload(snet.up_start.data(), sizeof(uint32_t) * n, (void **)&dm.up_start))) return rc;
   if ((rc = upload(topo.data(), n, (void **)&dm.topo))) return rc;
   if ((rc = upload(m->river_slot.data(), sizeof(int32_t) * n, (void **)&dm.river_slot))) return rc;
   dm.lev_off = m->d_lev_off;
+  dm.rlev_off = m->d_rlev_off;
+  {
+    const int G = m->lay.ngroups;
+    std::vector<GroupDesc> gd((size_t)G);
+    int64_t most = 0;
+    for (int g = 0; g < G; g++) {
+      gd[(size_t)g].lev_idx = (uint32_t)m->lay.lev_idx[(size_t)g];
+      gd[(size_t)g].rlev_idx = (uint32_t)m->rlay.lev_idx[(size_t)g];
+      gd[(size_t)g].lev0 = m->lay.lev0[(size_t)g];
+      gd[(size_t)g].rlev0 = m->rlay.lev0[(size_t)g];
+      most = std::max(most, (m->lay.lev_idx[(size_t)g + 1] - m->lay.lev_idx[(size_t)g]) +
+                                (m->rlay.lev_idx[(size_t)g + 1] - m->rlay.lev_idx[(size_t)g]));
+    }
+    if ((rc = upload(gd.data(), sizeof(GroupDesc) * (size_t)G, (void **)&m->d_groups))) return rc;
+    dm.groups = m->d_groups;
+    dm.ngroups = G;
+    // a group's level offsets live in shared memory during its sweep when they fit
+    if (m->lat_mode != WF_GRID && most * 4 <= 160 * 1024) {
+      dm.lev_cache = (int32_t)most;
+      m->lat_smem = (size_t)most * 4;
+    }
+  }
   CUDA_OK(cudaMalloc(&dm.h_r, sizeof(double) * std::max<int64_t>(n, 1)));
   CUDA_OK(cudaMalloc(&dm.h_surplus, sizeof(float) * std::max<int64_t>(n, 1)));
   CUDA_OK(cudaMalloc(&dm.h_ssf, sizeof(double) * std::max<int64_t>(n, 1)));
@@ -346,12 +529,9 @@ int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint
   CUDA_OK(cudaMalloc(&dm.h_racc, sizeof(double) * std::max<int32_t>(m->nr, 1)));
   CUDA_OK(cudaMalloc(&dm.h_rh, sizeof(double) * std::max<int32_t>(m->nr, 1)));
   {
-    // river schedule in river order (= rnet order for the first nrnet cells)
-    int64_t *d_rlev = nullptr;
-    if ((rc = upload(m->rnet.lev_off.data(), sizeof(int64_t) * m->rnet.lev_off.size(), (void **)&d_rlev))) return rc;
-    dm.rlev_off = d_rlev;
-    if ((rc = upload(m->rnet.up_start.data(), sizeof(uint32_t) * m->rnet.ncells, (void **)&dm.r_up_start))) return rc;
-    if ((rc = upload(m->rnet.nup.data(), m->rnet.ncells, (void **)&dm.r_nup))) return rc;
+    // river schedule in river order (= storage order of the river network for the first nrnet cells)
+    if ((rc = upload(srnet.up_start.data(), sizeof(uint32_t) * srnet.ncells, (void **)&dm.r_up_start))) return rc;
+    if ((rc = upload(srnet.nup.data(), srnet.ncells, (void **)&dm.r_nup))) return rc;
     dm.nrlev = (int32_t)m->rnet.nlevels();
     dm.rlev_shift = dm.nlev - dm.nrlev;
     // busiest tick of the wavefront
@@ -387,19 +567,22 @@ void wf_destroy(wf_model *m) {
   if (!m) return;
   cudaSetDevice(m->cfg.device);
   cudaStreamSynchronize(m->stream);
-  if (m->dm.dbg) {  // development aid: per-tick critical path of the last step
-    const char *path = std::getenv("WF_TICK_PROFILE");
-    if (FILE *fp = std::fopen(path, "w")) {
-      const int nt = m->dm.nlev + 1 + (m->nrnet > 0 ? m->dm.itR : 0);
-      std::fprintf(fp, "tick,subsurface_cyc,overland_cyc,river_cyc,clock_at_end,s0,s1,s2,s3\n");
-      const long long *s = m->dm.dbg + 4 * (m->dm.nlev + 8 + m->dm.itR);
-      for (int t = 0; t < nt; t++)
-        std::fprintf(fp, "%d,%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld\n", t, m->dm.dbg[4 * t], m->dm.dbg[4 * t + 1], m->dm.dbg[4 * t + 2],
-                     m->dm.dbg[4 * t + 3], s[4 * t], s[4 * t + 1], s[4 * t + 2], s[4 * t + 3]);
+#ifdef WF_PROFILE
+  if (m->dm.prof) {  // max over the steps run so far, per tick of the first group
+    if (FILE *fp = std::fopen(std::getenv("WF_TICK_PROFILE"), "w")) {
+      const int nt = m->dm.nlev + 1 + m->dm.itR;
+      std::fprintf(fp, "tick,sub_loaded,sub_gathered,sub_solved,sub_done,ovl_loaded,ovl_gathered,ovl_solved,ovl_done,"
+                       "riv_loaded,riv_gathered,riv_solved,riv_done,last_arrival,last_release,start_ns\n");
+      for (int t = 0; t < nt; t++) {
+        std::fprintf(fp, "%d", t);
+        for (int k = 0; k < 15; k++) std::fprintf(fp, ",%llu", m->dm.prof[16 * (size_t)t + k]);
+        std::fprintf(fp, "\n");
+      }
       std::fclose(fp);
     }
-    cudaFree(m->dm.dbg);
+    cudaFree(m->dm.prof);
   }
+#endif
   for (int id = 0; id < F_COUNT; id++) {
     if (m->external[id]) cudaFree(m->owned[id]);
     else cudaFree(m->dm.f[id]);
@@ -409,7 +592,7 @@ void wf_destroy(wf_model *m) {
   for (auto &a : m->areas) { cudaFree(a.d_perm); cudaFree(a.d_seg); }
   cudaFree(m->dm.h_r); cudaFree(m->dm.h_surplus); cudaFree(m->dm.h_ulo); cudaFree(m->dm.h_ssf);
   cudaFree(m->dm.h_inwO); cudaFree(m->dm.h_ssf_tr); cudaFree(m->dm.h_inwater); cudaFree(m->dm.h_racc); cudaFree(m->dm.h_rh);
-  cudaFree((void *)m->dm.rlev_off); cudaFree((void *)m->dm.r_up_start); cudaFree((void *)m->dm.r_nup); cudaFree(m->dm.h_inwaterMM); cudaFree(m->dm.h_wb);
+  cudaFree(m->d_rlev_off); cudaFree(m->d_groups); cudaFree((void *)m->dm.r_up_start); cudaFree((void *)m->dm.r_nup); cudaFree(m->dm.h_inwaterMM); cudaFree(m->dm.h_wb);
   cudaFree(m->dm.qo_sub); cudaFree(m->dm.qr_sub);
   cudaFree((void *)m->dm.up_start); cudaFree((void *)m->dm.topo); cudaFree((void *)m->dm.river_slot);
   cudaFree(m->d_order); cudaFree(m->d_rorder); cudaFree(m->d_lev_off); cudaFree(m->d_stage);
@@ -443,6 +626,33 @@ int64_t wf_schedule_num_levels(const wf_schedule *s) { return s ? s->net.nlevels
 int wf_schedule_get(const wf_schedule *s, int64_t *nodes, int64_t *nodes_up, int64_t *lev_off) {
   if (!s) return fail(WF_EINVAL, "null schedule");
   network_to_reference_form(s->net, nodes, nodes_up, lev_off);
+  return WF_OK;
+}
+
+int wf_schedule_partition(const wf_schedule *s, int ngroups, int64_t *storage_order, int64_t *group_off,
+                          int64_t *up_start, uint8_t *nup) {
+  if (!s || ngroups < 1) return fail(WF_EINVAL, "bad argument");
+  std::vector<int32_t> basin, gob;
+  std::vector<int64_t> bcells, newpos;
+  label_basins(s->net, basin, bcells);
+  const int G = pack_basins(bcells, ngroups, gob);
+  const int64_t n = s->net.ncells;
+  std::vector<int32_t> group_of((size_t)std::max<int64_t>(n, 1), 0);
+  for (int64_t k = 0; k < n; k++) group_of[(size_t)k] = gob.empty() ? 0 : gob[(size_t)basin[(size_t)k]];
+  Network out;
+  GroupLayout lay;
+  regroup(s->net, group_of, G, out, lay, newpos);
+  if (storage_order) std::copy(out.order.begin(), out.order.end(), storage_order);
+  if (group_off) std::copy(lay.cell_off.begin(), lay.cell_off.end(), group_off);
+  if (up_start)
+    for (int64_t k = 0; k < n; k++) up_start[k] = out.up_start[(size_t)k];
+  if (nup) std::copy(out.nup.begin(), out.nup.end(), nup);
+  return G;
+}
+
+int wf_lateral_plan(const wf_model *m, int32_t out[4]) {
+  if (!m || !out) return fail(WF_EINVAL, "null argument");
+  out[0] = m->lat_mode; out[1] = m->cluster_size; out[2] = m->dm.ngroups; out[3] = m->lat_blocks;
   return WF_OK;
 }
 
@@ -581,7 +791,7 @@ int wf_field_device_ptr(wf_model *m, const char *name, void **dptr, int64_t *n) 
 
 int wf_cell_order(const wf_model *m, int64_t *flat_index) {
   if (!m || !flat_index) return fail(WF_EINVAL, "null argument");
-  std::copy(m->net.order.begin(), m->net.order.end(), flat_index);
+  std::copy(m->snet.order.begin(), m->snet.order.end(), flat_index);
   return WF_OK;
 }
 
@@ -669,7 +879,7 @@ int wf_area_create(wf_model *m, const int32_t *idmap) {
   std::vector<std::pair<int32_t, int32_t>> pairs;  // (id, network index)
   pairs.reserve((size_t)m->n);
   for (int64_t k = 0; k < m->n; k++) {
-    const int32_t id = idmap[m->net.order[(size_t)k]];
+    const int32_t id = idmap[m->snet.order[(size_t)k]];
     if (id > 0) pairs.emplace_back(id, (int32_t)k);
   }
   std::stable_sort(pairs.begin(), pairs.end(),
@@ -734,7 +944,7 @@ int wf_sample(wf_model *m, const char *field, const int64_t *flat_index, int64_t
   std::map<int64_t, int32_t> want;
   for (int64_t i = 0; i < n; i++) want[flat_index[i]] = -1;
   for (int64_t k = 0; k < m->n; k++) {
-    auto it = want.find(m->net.order[(size_t)k]);
+    auto it = want.find(m->snet.order[(size_t)k]);
     if (it != want.end()) it->second = (int32_t)k;
   }
   const bool riv = g_fields[id].kind & K_RIVER;

@@ -26,6 +26,41 @@ __device__ __forceinline__ double pow_el(double x, double b) { return exp(b * lo
 // float32 x^b on the special-function unit (ex2.approx / lg2.approx), ~1e-6 relative: first guesses only.
 __device__ __forceinline__ float pow_fast(float x, float b) { return exp2f(b * __log2f(x)); }
 
+// Development aid (-DWF_PROFILE, a separate build): per tick, the latest time since the tick began at
+// which any thread passed four points of each task (operands loaded, inflow gathered, solved, done).
+#ifdef WF_PROFILE
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define WF_PARGS , unsigned long long *pslot, unsigned long long pc0
+#define WF_PPASS(type) , (pbase ? pbase + 4 * (type) : nullptr), c0
+__device__ __forceinline__ void prof_stamp(unsigned long long *slot, unsigned long long c0, long long dep) {
+  const unsigned mask = __activemask();
+  const unsigned d = (unsigned)(gtimer() - c0) + (unsigned)(dep & 0ll);
+  const unsigned mx = __reduce_max_sync(mask, d);
+  if ((threadIdx.x & 31) == (__ffs(mask) - 1)) atomicMax(slot, (unsigned long long)mx);
+}
+#define WF_STAMP(k, dep)                                                          \
+  do {                                                                            \
+    if (pslot) prof_stamp(pslot + (k), pc0, __double_as_longlong((double)(dep))); \
+  } while (0)
+#else
+#define WF_PARGS
+#define WF_PPASS(type)
+#define WF_STAMP(k, dep)
+#endif
+
+// Load of a value another thread of the sweep wrote one tick earlier.  Across blocks (grid or
+// cluster barrier) it is read from L2 (ld.global.cg); inside one block (__syncthreads) an ordinary
+// load is coherent.
+template <int MODE, typename T>
+__device__ __forceinline__ T ldx(const T *p) {
+  if (MODE == 2) return *(const volatile T *)p;
+  return __ldcg(p);
+}
+
 // kinematic_wave, wflow/wflow_funcs.py:119-152.
 // The reference's Newton iteration converges to the root of  dT/dX*Q + alpha*Q^beta = C  to
 // rounding (it only stops on |f| <= 1e-12 or its 3000-iteration cap), so the result is a property
@@ -178,9 +213,8 @@ __device__ __forceinline__ void chan_perc_all(const DevModel &m, int64_t us, int
 }
 
 // ---- task 1: subsurface flow + post-ssf column tail of one cell ------------------------------
-template <int ML>
-__device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t i, long long *stamp = nullptr) {
-  if (stamp) stamp[0] = clock64();
+template <int ML, int MODE>
+__device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t i WF_PARGS) {
   const uint8_t tp = __ldg(m.topo + i);
   const int nup = tp >> 4;
   const int myldd = tp & 15;
@@ -204,11 +238,12 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
   for (int k = 0; k < ML; k++)
     U[k] = (double)m.f[F_UStoreLayerDepth_0 + k][i] + (double)m.h_ulo[(int64_t)k * m.n + i];
 
+  WF_STAMP(0, U[0] + xlyl + ssf_old + rsum + surplus + DW + Kh + zi_old);
   // inflow gather, reference summation order (wflow_sbm.py:395-410)
   double ssf_in = 0.0, ssf_tr = 0.0;
   double sv[8];
 #pragma unroll
-  for (int j = 0; j < 8; j++) sv[j] = (j < nup) ? __ldcg(m.h_ssf + (int64_t)us + j) : 0.0;  // all loads in flight at once
+  for (int j = 0; j < 8; j++) sv[j] = (j < nup) ? ldx<MODE>(m.h_ssf + (int64_t)us + j) : 0.0;  // all loads in flight at once
   if (riverMap) {
     ChanPerc c;
     chan_perc_all(m, (int64_t)us, nup, myldd, slope_i, c);
@@ -226,7 +261,7 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
       if (j < nup) ssf_in = ssf_in + sv[j];
   }
 
-  if (stamp) { stamp[1] = clock64() + (long long)(ssf_in * 0.0) + (long long)(U[0] * 0.0) + (long long)(xlyl * 0.0) + (long long)(ssf_old * 0.0); }
+  WF_STAMP(1, ssf_in);
   const double neff = (double)neff_f;
   const double dneff = thetaS - thetaR;
   const double r = rsum * DW * 1000;                                   // :674
@@ -235,7 +270,7 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
   double ssf_n, zi_n, ExfiltSatWater;
   kinematic_wave_ssf(ssf_in, ssf_old, zi_old, r, Kh, KsatVer, slope_i, neff, fpar, ST, efD, 1.0, DLd * 1000,
                      DW * 1000, ssfmax, ssf_n, zi_n, ExfiltSatWater);
-  if (stamp) stamp[2] = clock64() + (long long)(ssf_n * 0.0);
+  WF_STAMP(2, ssf_n);
   const double zi = pymin(zi_n, ST);  // :702
   const double Sat = (ST - zi) * dneff;
   ssfp[i] = (float)ssf_n;
@@ -305,12 +340,12 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
     m.f[F_SoilWatbal][i] = (float)wb;
     if (m.f[F_watbal] && m.f[F_SurfaceWatbal]) m.f[F_watbal][i] = (float)wb + m.f[F_SurfaceWatbal][i];
   }
-  if (stamp) stamp[3] = clock64() + (long long)(InwaterO * 0.0);
+  WF_STAMP(3, InwaterO);
 }
 
 // ---- task 2: overland flow of one cell, all sub-steps (wflow_sbm.py:830-879) -----------------
-__device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i, long long *stamp = nullptr) {
-  if (stamp) stamp[0] = clock64();
+template <int MODE>
+__device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i WF_PARGS) {
   const uint8_t tp = __ldg(m.topo + i);
   const int nup = tp >> 4;
   const int myldd = tp & 15;
@@ -320,7 +355,7 @@ __device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i
   const int itL = m.itL;
   const double SW = LD(SW), AlphaL = LD(AlphaL), Beta = m.beta, DLd = LD(DL);
   const double dts = m.dt / itL;
-  const double q = __ldcg(m.h_inwO + i) / DLd;
+  const double q = ldx<MODE>(m.h_inwO + i) / DLd;
   double Qold = m.f[F_LandRunoffsub][i];
   ChanPerc c;
   if (riverMap) chan_perc_all(m, (int64_t)us, nup, myldd, (double)LD(landSlope), c);
@@ -332,7 +367,7 @@ __device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i
     double s1 = 0.0, s2 = 0.0, s3 = 0.0;
     float qv[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) qv[j] = (j < nup) ? __ldcg(qbuf + (int64_t)us + j) : 0.0f;
+    for (int j = 0; j < 8; j++) qv[j] = (j < nup) ? ldx<MODE>(qbuf + (int64_t)us + j) : 0.0f;
     if (riverMap) {
 #pragma unroll
       for (int j = 0; j < 8; j++) {
@@ -356,9 +391,10 @@ __device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i
       qo_in = s1; qo_toriver_vol = 0.0;
     }
     double qbeta;
-    if (stamp) stamp[1] = clock64() + (long long)(qo_in * 0.0) + (long long)(q * 0.0) + (long long)(Qold * 0.0) + (long long)(AlphaL * 0.0);
+    WF_STAMP(0, q + Qold + AlphaL + SW);
+    WF_STAMP(1, qo_in);
     const double qn = kinematic_wave(qo_in, Qold, q, AlphaL, Beta, dts, DLd, qbeta);
-    if (stamp) stamp[2] = clock64() + (long long)(qn * 0.0);
+    WF_STAMP(2, qn);
     acc_flow = acc_flow + qn * dts;
     Qo_in_acc = Qo_in_acc + qo_in * dts;
     qo_toriver_acc = qo_toriver_acc + qo_toriver_vol;
@@ -377,7 +413,7 @@ __device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i
   if (riverMap) {  // lateral inflow of the channel, wflow_sbm.py:3052-3065, 3144
     const float dtf = (float)m.dt;
     const float ToCubic = ((LD(xl) * LD(yl)) * 0.001f) / dtf;  // :1998
-    float Inwater = ((m.h_inwaterMM[rs] * ToCubic) + qo_toriver_f) + __ldcg(m.h_ssf_tr + rs);
+    float Inwater = ((m.h_inwaterMM[rs] * ToCubic) + qo_toriver_f) + ldx<MODE>(m.h_ssf_tr + rs);
     if (m.f[F_Inflow]) Inwater = Inwater + m.f[F_Inflow][rs];
     m.h_inwater[rs] = Inwater;
     if (m.f[F_Inwater]) m.f[F_Inwater][rs] = Inwater;
@@ -386,28 +422,29 @@ __device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i
       m.f[F_RiverRunoffsub][rs] = 0.0f; m.f[F_WaterLevelRsub][rs] = 0.0f;
     }
   }
-  if (stamp) stamp[3] = clock64();
+  WF_STAMP(3, acc_flow);
 }
 
 // ---- task 3: one sub-step of the river kinematic wave for one river cell (river order) -------
 // kin_wave, wflow/wflow_funcs.py:155-207; caller glue wflow_sbm.py:3152-3201.
-__device__ __forceinline__ void task_river(const DevModel &m, const int32_t rs, const int v) {
+template <int MODE>
+__device__ __forceinline__ void task_river(const DevModel &m, const int32_t rs, const int v WF_PARGS) {
   const int itR = m.itR;
   const int nup = __ldg(m.r_nup + rs);
   const uint32_t us = __ldg(m.r_up_start + rs);
   float *qbuf = (v == itR - 1) ? m.f[F_RiverRunoffsub] : m.qr_sub + (int64_t)v * m.nr;
   // own-cell operands: all independent, issued together with the topology (one round trip)
   const float DCLf = __ldg(m.f[F_DCL] + rs);
-  const float inw = __ldcg(m.h_inwater + rs);
+  const float inw = ldx<MODE>(m.h_inwater + rs);
   const double A = __ldg(m.f[F_AlphaR] + rs), Bw = __ldg(m.f[F_Bw] + rs);
-  const double Qo = (v == 0) ? (double)m.f[F_RiverRunoffsub][rs] : (double)__ldcg(m.qr_sub + (int64_t)(v - 1) * m.nr + rs);
+  const double Qo = (v == 0) ? (double)m.f[F_RiverRunoffsub][rs] : (double)ldx<MODE>(m.qr_sub + (int64_t)(v - 1) * m.nr + rs);
   double racc0 = 0.0, rh0 = 0.0;
-  if (v > 0) { racc0 = __ldcg(m.h_racc + rs); rh0 = __ldcg(m.h_rh + rs); }
+  if (v > 0) { racc0 = ldx<MODE>(m.h_racc + rs); rh0 = ldx<MODE>(m.h_rh + rs); }
   double Qin = 0.0;
   {
     float qv[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) qv[j] = (j < nup) ? __ldcg(qbuf + us + j) : 0.0f;
+    for (int j = 0; j < 8; j++) qv[j] = (j < nup) ? ldx<MODE>(qbuf + us + j) : 0.0f;
 #pragma unroll
     for (int j = 0; j < 8; j++)
       if (j < nup) Qin = Qin + (double)qv[j];
@@ -416,7 +453,10 @@ __device__ __forceinline__ void task_river(const DevModel &m, const int32_t rs, 
   const double dtr = m.dt / itR;
   // Qo: the previous sub-step's outflow of this cell, or the state at the first sub-step (:199)
   double qbeta;
+  WF_STAMP(0, qr + A + Bw + Qo + racc0);
+  WF_STAMP(1, Qin);
   const double qn = kinematic_wave(Qin, Qo, qr, A, m.beta, dtr, (double)DCLf, qbeta);
+  WF_STAMP(2, qn);
   const double wl = (A * qbeta) / Bw;
   const double racc = racc0 + qn * dtr, rh = rh0 + wl;
   qbuf[rs] = (float)qn;
@@ -428,6 +468,7 @@ __device__ __forceinline__ void task_river(const DevModel &m, const int32_t rs, 
     m.h_racc[rs] = racc;
     m.h_rh[rs] = rh;
   }
+  WF_STAMP(3, racc);
 }
 
 // The first sub-step reads its own cell's Qold from the state array that the LAST sub-step
@@ -452,61 +493,122 @@ __device__ __forceinline__ void prefetch_subsurface(const DevModel &m, const int
   prefetch_l2(m.f[F_SW] + i); prefetch_l2(m.f[F_AlphaL] + i); prefetch_l2(m.f[F_LandRunoffsub] + i);
 }
 
-template <int ML>
-__global__ void __launch_bounds__(256) k_lateral_wave(const DevModel m) {
-  cg::grid_group grid = cg::this_grid();
-  const int gtid = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-  const int gsize = (int)(gridDim.x * blockDim.x);
+// Who sweeps a group (a set of whole basins, GroupLayout in network.h), and with which barrier:
+//   WF_GRID     all blocks of a cooperative launch, grid barrier     (one wide group)
+//   WF_CLUSTER  one thread-block cluster per group, cluster barrier  (several basins, wide levels)
+//   WF_CTA      one thread block per group, __syncthreads            (many small basins / a narrow network)
+// Groups never exchange data, so clusters / blocks of different groups never wait for each other.
+enum { WF_GRID = 0, WF_CLUSTER = 1, WF_CTA = 2 };
+
+template <int MODE>
+__device__ __forceinline__ void wave_barrier() {
+  if (MODE == WF_GRID) cg::this_grid().sync();
+  else if (MODE == WF_CLUSTER) cg::this_cluster().sync();
+  else __syncthreads();
+}
+
+// One group's wavefront.  Tick t (level L = lev0 + t) runs, concurrently on different warps,
+//   [subsurface cells of level L][overland cells of level L-1][river cells of level L-2-v, sub-step v = 0..itR-1]
+// as one flat item space: consecutive threads take consecutive items, so a warp almost always runs
+// a single task type.  lo / ro: the group's level offsets (shared memory when they fit).
+template <int ML, int MODE>
+__device__ __forceinline__ void sweep_group(const DevModel &m, const GroupDesc gd, const uint32_t *lo, const uint32_t *ro,
+                                            const int tid, const int nthreads) {
   const int D = m.nlev, itR = m.itR;
-  const bool rivers = m.nrnet > 0 && (m.task_mask & 4);
-  const int nticks = D + 1 + ((m.nrnet > 0) ? itR : 0);
+  const int nl = D - gd.lev0;                        // levels of the group
+  const bool rivers = gd.rlev0 < m.nrlev && (m.task_mask & 4);
+  const int nrl = rivers ? m.nrlev - gd.rlev0 : 0;   // river levels of the group
+  const int nticks = nl + 1 + ((gd.rlev0 < m.nrlev) ? itR : 0);
+  // river level (group-local) solved for sub-step 0 at tick 0; sub-step v lags v levels behind
+  const int q0 = (gd.lev0 - 2) - m.rlev_shift - gd.rlev0;
   for (int t = 0; t < nticks; t++) {
-    // Item space of this tick, one flat index j over
-    //   [subsurface cells of level t][overland cells of level t-1][river cells of level t-2-v, sub-step v = 0..itR-1]
-    // consecutive threads take consecutive items, so a warp almost always runs a single task type and
-    // the three solves of a tick proceed concurrently on different warps.
-    long long c0 = 0;
-    if (m.dbg) c0 = clock64();
-    int64_t beg0 = 0, beg1 = 0;
+#ifdef WF_PROFILE
+    unsigned long long *pbase = (m.prof && gd.lev_idx == 0) ? m.prof + 16 * (size_t)t : nullptr;
+    const unsigned long long c0 = gtimer();
+    if (pbase && tid == 0) pbase[14] = c0;
+#endif
+    uint32_t beg0 = 0, beg1 = 0;
     int cnt0 = 0, cnt1 = 0;
-    if (t < D && (m.task_mask & 1)) { beg0 = m.lev_off[t]; cnt0 = (int)(m.lev_off[t + 1] - beg0); }
-    if (t >= 1 && t - 1 < D && (m.task_mask & 2)) { beg1 = m.lev_off[t - 1]; cnt1 = (int)(m.lev_off[t] - beg1); }
-    int rbeg[8], rcnt[8], total = cnt0 + cnt1;
-    const int nv = rivers ? (itR < 8 ? itR : 8) : 0;
-#pragma unroll
-    for (int v = 0; v < 8; v++) {
-      rbeg[v] = 0; rcnt[v] = 0;
-      if (v < nv) {
-        const int lr = (t - 2 - v) - m.rlev_shift;  // river level solved for sub-step v at this tick
-        if (lr >= 0 && lr < m.nrlev) { rbeg[v] = (int)m.rlev_off[lr]; rcnt[v] = (int)(m.rlev_off[lr + 1] - m.rlev_off[lr]); }
+    if (t < nl && (m.task_mask & 1)) { beg0 = lo[t]; cnt0 = (int)(lo[t + 1] - beg0); }
+    if (t >= 1 && t - 1 < nl && (m.task_mask & 2)) { beg1 = lo[t - 1]; cnt1 = (int)(lo[t] - beg1); }
+    int total = cnt0 + cnt1;
+    if (rivers) {
+#pragma unroll 1
+      for (int v = 0; v < itR; v++) {
+        const int q = q0 + t - v;
+        if (q >= 0 && q < nrl) total += (int)(ro[q + 1] - ro[q]);
       }
-      total += rcnt[v];
     }
-    for (int j = gtid; j < total; j += gsize) {
+    for (int j = tid; j < total; j += nthreads) {
       if (j < cnt0) {
-        task_subsurface<ML>(m, beg0 + j, nullptr);
-        if (m.dbg) atomicMax((unsigned long long *)&m.dbg[4 * t + 0], (unsigned long long)(clock64() - c0));
+        task_subsurface<ML, MODE>(m, (int64_t)beg0 + j WF_PPASS(0));
       } else if (j < cnt0 + cnt1) {
-        task_overland(m, beg1 + (j - cnt0), (m.dbg && j == cnt0) ? m.dbg + 4 * (m.nlev + 8 + m.itR) + 4 * t : nullptr);
-        if (m.dbg) atomicMax((unsigned long long *)&m.dbg[4 * t + 1], (unsigned long long)(clock64() - c0));
+        task_overland<MODE>(m, (int64_t)beg1 + (j - cnt0) WF_PPASS(1));
       } else {
-        int jj = j - cnt0 - cnt1;
-#pragma unroll
-        for (int v = 0; v < 8; v++) {
-          if (jj >= 0 && jj < rcnt[v]) { task_river(m, rbeg[v] + jj, v); jj = -1; }
-          else if (jj >= 0) jj -= rcnt[v];
+        int jj = j - cnt0 - cnt1, vsel = 0;
+        uint32_t ridx = 0;
+#pragma unroll 1
+        for (int v = 0; v < itR; v++) {
+          const int q = q0 + t - v;
+          if (q < 0 || q >= nrl) continue;
+          const uint32_t rb = ro[q];
+          const int rc = (int)(ro[q + 1] - rb);
+          if (jj < rc) { vsel = v; ridx = rb + (uint32_t)jj; break; }
+          jj -= rc;
         }
-        if (m.dbg) atomicMax((unsigned long long *)&m.dbg[4 * t + 2], (unsigned long long)(clock64() - c0));
+        task_river<MODE>(m, (int32_t)ridx, vsel WF_PPASS(2));
       }
     }
-    if (m.dbg && gtid == 0) m.dbg[4 * t + 3] = clock64();
     if (t + 1 < nticks) {
-      if (t + 1 < D) {  // warm L2 with next tick's operands while we wait
-        const int64_t nb = m.lev_off[t + 1], ne = m.lev_off[t + 2];
-        if (nb + gtid < ne) prefetch_subsurface(m, nb + gtid);
+      if (t + 1 < nl) {  // warm L2 with next tick's operands while we wait
+        const uint32_t nb = lo[t + 1], ne = lo[t + 2];
+        if (nb + (uint32_t)tid < ne) prefetch_subsurface(m, (int64_t)nb + tid);
       }
-      grid.sync();
+#ifdef WF_PROFILE
+      if (pbase) prof_stamp(pbase + 12, c0, 0);
+#endif
+      wave_barrier<MODE>();
+#ifdef WF_PROFILE
+      if (pbase) prof_stamp(pbase + 13, c0, 0);
+#endif
     }
+  }
+}
+
+template <int ML, int MODE>
+__global__ void __launch_bounds__(MODE == WF_GRID ? 256 : WF_GROUP_THREADS, 1) k_lateral_wave(const DevModel m) {
+  extern __shared__ uint32_t s_lev[];
+  if (MODE == WF_GRID) {
+    // one group (the whole network); offsets straight from global memory (L2-resident, prefetched by use)
+    const GroupDesc gd = m.groups[0];
+    sweep_group<ML, MODE>(m, gd, m.lev_off + gd.lev_idx, m.rlev_off + gd.rlev_idx, (int)(blockIdx.x * blockDim.x + threadIdx.x),
+                          (int)(gridDim.x * blockDim.x));
+    return;
+  }
+  int crank = 0, csize = 1;
+  if (MODE == WF_CLUSTER) {
+    cg::cluster_group cl = cg::this_cluster();
+    crank = (int)cl.block_rank();
+    csize = (int)cl.num_blocks();
+  }
+  const int nclusters = (int)gridDim.x / csize;
+  const int tid = crank * (int)blockDim.x + (int)threadIdx.x;
+  const int nthreads = csize * (int)blockDim.x;
+  for (int g = (int)blockIdx.x / csize; g < m.ngroups; g += nclusters) {
+    const GroupDesc gd = m.groups[g];
+    const int nlo = m.nlev - gd.lev0 + 1;
+    const int nro = (gd.rlev0 < m.nrlev) ? m.nrlev - gd.rlev0 + 1 : 0;
+    const uint32_t *lo = m.lev_off + gd.lev_idx, *ro = m.rlev_off + gd.rlev_idx;
+    if (nlo + nro <= m.lev_cache) {  // level offsets of the group into shared memory (every block its own copy)
+      __syncthreads();
+      for (int k = threadIdx.x; k < nlo; k += blockDim.x) s_lev[k] = lo[k];
+      for (int k = threadIdx.x; k < nro; k += blockDim.x) s_lev[nlo + k] = ro[k];
+      __syncthreads();
+      lo = s_lev;
+      ro = s_lev + nlo;
+    }
+    sweep_group<ML, MODE>(m, gd, lo, ro, tid, nthreads);
+    // the next group of this cluster touches other cells only: no barrier needed in between
   }
 }
 
