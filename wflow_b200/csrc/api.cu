@@ -84,6 +84,8 @@ struct wf_model {
   int64_t launches = 0;
   int64_t max_tick_items = 1;
   bool timed = false;
+  bool derived_dirty = true;          // d_efT / d_efST must be recomputed before the next step
+  bool vert_attr_set = false;
   int ML = 1;
   bool external[F_COUNT] = {};        // field bound to a caller-owned device array
   float *owned[F_COUNT] = {};         // our own allocation while an external one is bound
@@ -223,7 +225,40 @@ int launch_step(wf_model *m) {
   }
   if (m->timed) cudaEventRecord(e0, m->stream);
   const int tb = WF_VERT_THREADS;
-  k_vertical<ML><<<(unsigned)((n + tb - 1) / tb), tb, 0, m->stream>>>(m->dm);
+  if (m->derived_dirty) {  // statics changed since the derived ones were computed
+    k_derive<ML><<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->dm);
+    k_derive_lateral<ML><<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->dm);
+    m->launches += 2;
+    m->derived_dirty = false;
+  }
+  {  // sources of the staged inputs (VLayout); pointers may have been re-bound since the last step
+    using VL = VLayout<ML>;
+    static_assert(VL::nslots(true) <= WF_MAX_VSLOTS, "WF_MAX_VSLOTS too small");
+    DevModel &dm = m->dm;
+    const int nsl = VL::nslots(dm.glacier != 0);
+    int cnt = 0;
+    for (int s = 0; s < WF_MAX_VSLOTS; s++) {
+      const float *src = nullptr;
+      if (s < VS_NFIX) src = (s == VS_river_slot) ? reinterpret_cast<const float *>(dm.river_slot) : dm.f[kVSlotField[s]];
+      else if (s < VL::S_C) src = dm.f[F_UStoreLayerDepth_0 + (s - VL::S_U)];
+      else if (s < VL::S_KVF) src = dm.f[F_c_0 + (s - VL::S_C)];
+      else if (s < VL::S_GL) src = dm.f[F_KsatVerFrac_0 + (s - VL::S_KVF)];
+      else if (s < nsl) {
+        const int g = s - VL::S_GL;
+        src = dm.f[g == 0 ? F_GlacierFrac : g == 1 ? F_GlacierStore : g == 2 ? F_G_SIfrac : g == 3 ? F_G_TT : F_G_Cfmax];
+      }
+      if (s >= nsl) src = nullptr;
+      dm.vsrc[s] = src;
+      cnt += src != nullptr;
+    }
+    dm.vsrc_count = cnt;
+  }
+  const size_t vsmem = WF_VERT_STAGE ? VLayout<ML>::bytes(m->dm.glacier != 0) : 0;
+  if (vsmem > 48 * 1024 && !m->vert_attr_set) {
+    CUDA_OK(cudaFuncSetAttribute((void *)k_vertical<ML>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
+    m->vert_attr_set = true;
+  }
+  k_vertical<ML><<<(unsigned)((n + tb - 1) / tb), tb, vsmem, m->stream>>>(m->dm);
   m->launches++;
   if (m->timed) cudaEventRecord(e1, m->stream);
   if (int rc = launch_lateral<ML>(m)) return rc;
@@ -518,6 +553,11 @@ int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint
       m->lat_smem = (size_t)most * 4;
     }
   }
+  dm.npad = (n + WF_VERT_THREADS - 1) / WF_VERT_THREADS * WF_VERT_THREADS;
+  CUDA_OK(cudaMalloc(&dm.d_efT, sizeof(double) * (size_t)m->ML * std::max<int64_t>(dm.npad, 1)));
+  CUDA_OK(cudaMalloc(&dm.d_efST, sizeof(double) * std::max<int64_t>(dm.npad, 1)));
+  CUDA_OK(cudaMalloc(&dm.d_cpd, sizeof(double) * std::max<int64_t>(n, 1)));
+  CUDA_OK(cudaMemsetAsync(dm.d_cpd, 0, sizeof(double) * std::max<int64_t>(n, 1), m->stream));
   CUDA_OK(cudaMalloc(&dm.h_r, sizeof(double) * std::max<int64_t>(n, 1)));
   CUDA_OK(cudaMalloc(&dm.h_surplus, sizeof(float) * std::max<int64_t>(n, 1)));
   CUDA_OK(cudaMalloc(&dm.h_ssf, sizeof(double) * std::max<int64_t>(n, 1)));
@@ -590,6 +630,7 @@ void wf_destroy(wf_model *m) {
   for (cudaEvent_t e : m->tev) cudaEventDestroy(e);
   for (float *p : m->snapshot) cudaFree(p);
   for (auto &a : m->areas) { cudaFree(a.d_perm); cudaFree(a.d_seg); }
+  cudaFree(m->dm.d_efT); cudaFree(m->dm.d_efST); cudaFree(m->dm.d_cpd);
   cudaFree(m->dm.h_r); cudaFree(m->dm.h_surplus); cudaFree(m->dm.h_ulo); cudaFree(m->dm.h_ssf);
   cudaFree(m->dm.h_inwO); cudaFree(m->dm.h_ssf_tr); cudaFree(m->dm.h_inwater); cudaFree(m->dm.h_racc); cudaFree(m->dm.h_rh);
   cudaFree(m->d_rlev_off); cudaFree(m->d_groups); cudaFree((void *)m->dm.r_up_start); cudaFree((void *)m->dm.r_nup); cudaFree(m->dm.h_inwaterMM); cudaFree(m->dm.h_wb);
@@ -680,6 +721,7 @@ static int stage(wf_model *m) {
 
 static int gather_into(wf_model *m, int id, const float *dgrid) {
   if (int rc = ensure_field(m, id)) return rc;
+  if ((g_fields[id].kind & 0xff) == K_STATIC) m->derived_dirty = true;
   const bool riv = g_fields[id].kind & K_RIVER;
   const int64_t len = riv ? m->nr : m->n;
   if (len > 0) {
@@ -715,6 +757,7 @@ int wf_set_field_uniform(wf_model *m, const char *name, float value) {
   if (id < 0) return fail(WF_EINVAL, std::string("unknown field: ") + (name ? name : "(null)"));
   CUDA_OK(cudaSetDevice(m->cfg.device));
   if (int rc = ensure_field(m, id)) return rc;
+  if ((g_fields[id].kind & 0xff) == K_STATIC) m->derived_dirty = true;
   const int64_t len = field_len(m, id);
   if (len > 0) {
     k_fill<<<(unsigned)((len + 255) / 256), 256, 0, m->stream>>>(m->dm.f[id], value, len);
@@ -784,6 +827,7 @@ int wf_field_device_ptr(wf_model *m, const char *name, void **dptr, int64_t *n) 
   if (id < 0) return fail(WF_EINVAL, std::string("unknown field: ") + (name ? name : "(null)"));
   CUDA_OK(cudaSetDevice(m->cfg.device));
   if (int rc = ensure_field(m, id)) return rc;
+  if ((g_fields[id].kind & 0xff) == K_STATIC) m->derived_dirty = true;  // the caller may write through the pointer
   *dptr = m->dm.f[id];
   if (n) *n = field_len(m, id);
   return WF_OK;
@@ -856,6 +900,7 @@ int wf_bind_field(wf_model *m, const char *name, float *dptr) {
   if (!m) return fail(WF_EINVAL, "null model");
   const int id = field_index(name);
   if (id < 0) return fail(WF_EINVAL, std::string("unknown field: ") + (name ? name : "(null)"));
+  if ((g_fields[id].kind & 0xff) == K_STATIC) m->derived_dirty = true;
   if (dptr) {
     if (!m->external[id]) m->owned[id] = m->dm.f[id];
     m->dm.f[id] = dptr;

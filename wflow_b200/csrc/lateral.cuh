@@ -22,7 +22,7 @@ namespace wf {
 // x^b for x >= 0 as exp(b*log(x)): the two CUDA double routines are each accurate to ~1 ulp, the
 // result to ~1e-15 relative -- three times cheaper than pow()'s correctly rounded path, far inside
 // the 1e-9 the float64 quantities are held to.  x = 0 gives 0 (b > 0) or inf (b < 0) like pow.
-__device__ __forceinline__ double pow_el(double x, double b) { return exp(b * log(x)); }
+__device__ __forceinline__ double pow_el(double x, double b) { return wf_exp(b * wf_log(x)); }
 // float32 x^b on the special-function unit (ex2.approx / lg2.approx), ~1e-6 relative: first guesses only.
 __device__ __forceinline__ float pow_fast(float x, float b) { return exp2f(b * __log2f(x)); }
 
@@ -76,7 +76,7 @@ __device__ __noinline__ double kinematic_wave(double Qin, double Qold, double q,
                                               double deltaT, double deltaX, double &Qbeta) {
   Qbeta = 0.0;
   if ((Qin + Qold + q) == 0.0) return 0.0;
-  const double deltaTX = deltaT / deltaX;
+  const double deltaTX = qdiv(deltaT, deltaX);
   const double C = deltaTX * Qin + alpha * pow_el(Qold, beta) + deltaT * q;
   // float32 phase
   const float a32 = (float)alpha, b32 = (float)beta, dtx32 = (float)deltaTX;
@@ -97,19 +97,21 @@ __device__ __noinline__ double kinematic_wave(double Qin, double Qold, double q,
     Qf = Qn;
     if (done) break;
   }
-  // float64 phase
+  // float64 phase (Q >= 1e-30 and df > 0 are ordinary numbers: reciprocal-based quotients)
   double Qkx = (double)Qf;
   double qb = pow_el(Qkx, beta);
+  const double t2 = 0.5 * beta * (beta - 1.0), t3 = beta * (beta - 1.0) * (beta - 2.0) * (1.0 / 6.0);
 #pragma unroll 1
   for (int it = 0; it < 60; it++) {
+    const double rQ = qrcp(Qkx);
     const double f = deltaTX * Qkx + alpha * qb - C;
-    const double dqb = beta * (qb / Qkx);  // d(Q^beta)/dQ
+    const double dqb = beta * (qb * rQ);  // d(Q^beta)/dQ
     const double df = deltaTX + alpha * dqb;
-    const double Qn = fmax(Qkx - f / df, 1e-30);
-    const double d = (Qn - Qkx) / Qkx;
+    const double Qn = fmax(Qkx - qdiv(f, df), 1e-30);
+    const double d = (Qn - Qkx) * rQ;
     const double ad = fabs(d);
     // Q^beta at the new iterate
-    if (ad < 1e-3) qb = qb * (1.0 + d * (beta + d * (0.5 * beta * (beta - 1.0) + d * (beta * (beta - 1.0) * (beta - 2.0) / 6.0))));
+    if (ad < 1e-3) qb = qb * (1.0 + d * (beta + d * (t2 + d * t3)));
     else qb = pow_el(Qn, beta);
     Qkx = Qn;
     if (fabs(f) <= 1e-12 || ad <= 1e-8) break;
@@ -140,50 +142,63 @@ __device__ __noinline__ void kinematic_wave_ssf(double ssf_in, double ssf_old, d
     ssf_out = 0.0; zi_out = D; exfilt_out = 0.0;
     return;
   }
+  // quotients of positive parameters (slope >= 1e-5, f > 0, Ks > 0, dx > 0): ordinary numbers
   const double den = w * Ks_hor * Ks * slope;
-  const double dtdx = dt / dx;
-  const double fden = f / den;
-  const double nf = -1.0 / f;
-  const double K1 = neff / (Ks_hor * Ks * slope);  // 1/Cn = K1 / exp(-f*zi)
+  const double dtdx = qdiv(dt, dx);
+  const double fden = qdiv(f, den);
+  const double nf = -qrcp(f);
+  const double K1 = qdiv(neff, Ks_hor * Ks * slope);  // 1/Cn = K1 / exp(-f*zi)
   double ssf_n;
   {
-    const double A = dtdx / fden;
-    const double B = dt * neff * w / f;
+    const double A = qdiv(dtdx, fden);
+    const double B = qdiv(dt * neff * w, f);
     const double C0 = -A * efD - dtdx * ssf_in - dt * (r - zi_old * neff * w);
     double u = -f * fmin(fmax(zi_old, 0.0), D);
-    double e = exp(u);
+    double e = wf_exp(u);
 #pragma unroll 1
     for (int k = 0; k < 4; k++) {
       const double Fu = A * e + B * u + C0;
       const double d1 = A * e + B, d2 = A * e;
-      const double du = 2.0 * Fu * d1 / (2.0 * d1 * d1 - Fu * d2);
+      const double du = qdiv(2.0 * Fu * d1, 2.0 * d1 * d1 - Fu * d2);
       u = u - du;
-      e = exp(u);
+      // e^u follows a small step by its series (|du| < 1/64: truncation below 1e-19)
+      const double t = -du;
+      if (fabs(du) < 0.015625)
+        e = e * (1.0 + t * (1.0 + t * (0.5 + t * (1.0 / 6 + t * (1.0 / 24 + t * (1.0 / 120 + t * (1.0 / 720 + t * (1.0 / 5040))))))));
+      else
+        e = wf_exp(u);
       if (!(fabs(du) > 1e-10)) break;
     }
-    ssf_n = (e - efD) / fden;
+    ssf_n = qdiv(e - efD, fden);
     if (!(ssf_n == ssf_n) || isinf(ssf_n)) ssf_n = (ssf_old + ssf_in) / 2.0;  // the reference's first guess
     ssf_n = pymax(ssf_n, 1e-30);
   }
   int count = 0;
   double zi, fQ;
-  bool stalled = false;
-  do {
-    const double x = ssf_n * fden + efD;
-    zi = log(x) * nf;
-    const double invCn = K1 / x;
+  double x = ssf_n * fden + efD;  // exp(-f*zi) at the iterate (saves the reference's exp; ~1e-14 rel)
+  double lx = wf_log(x);
+  for (;;) {
+    zi = lx * nf;
+    const double invCn = qdiv(K1, x);
     const double c = dtdx * ssf_in + invCn * ssf_n + dt * (r - (zi_old - zi) * neff * w);
     fQ = dtdx * ssf_n + invCn * ssf_n - c;
     const double dfQ = dtdx + invCn;
-    double sn = ssf_n - (fQ / dfQ);
+    double sn = ssf_n - qdiv(fQ, dfQ);
     if (isnan(sn)) sn = 0.0;
     sn = pymax(sn, 1e-30);
-    stalled = fabs(sn - ssf_n) <= 4.440892098500626e-16 * sn;
+    const bool stalled = fabs(sn - ssf_n) <= 4.440892098500626e-16 * sn;
     ssf_n = sn;
     count++;
-  } while (fabs(fQ) > epsilon && count <= MAX_ITERS && !stalled);
+    if (!(fabs(fQ) > epsilon && count <= MAX_ITERS && !stalled)) break;
+    // log of the next iterate's x from this one's: log1p(d) by its series for a small relative step
+    const double xn = sn * fden + efD;
+    const double d = qdiv(xn - x, x);
+    if (fabs(d) < 1e-4) lx = lx + d * (1.0 + d * (-0.5 + d * (1.0 / 3 - 0.25 * d)));
+    else lx = wf_log(xn);
+    x = xn;
+  }
   ssf_n = pymin(ssf_n, (ssf_max * w));
-  const double rest = zi_old - (ssf_in + r * dx - ssf_n) / (w * dx) / neff;
+  const double rest = zi_old - qdiv(qdiv(ssf_in + r * dx - ssf_n, w * dx), neff);
   exfilt_out = pymin(rest, 0.0) * -neff;
   zi_out = pymax(0.0, zi);
   ssf_out = ssf_n;
@@ -191,24 +206,30 @@ __device__ __noinline__ void kinematic_wave_ssf(double ssf_in, double ssf_old, d
 
 // Fraction of an upstream neighbour's outflow that a river cell takes straight into the channel
 // (wflow_sbm.py:395-398, 843-846): slope-weighted for neighbours that drain in another direction.
-// All (up to 8) neighbours' ldd codes and slopes are fetched together -- one memory round trip --
-// and the fractions stay in registers (fully unrolled, no indexed local array).
+// It depends on statics only, and every cell has exactly one receiver: k_derive_lateral stores it
+// per UPSTREAM cell (d_cpd), so a river cell reads the fractions of its (contiguous) upstream run.
 struct ChanPerc {
   double cp[8];
 };
-__device__ __forceinline__ void chan_perc_all(const DevModel &m, int64_t us, int nup, int myldd, double slope_i,
-                                              ChanPerc &out) {
-  uint8_t tb[8];
-  float sl[8];
+__device__ __forceinline__ void chan_perc_all(const DevModel &m, int64_t us, int nup, ChanPerc &out) {
 #pragma unroll
-  for (int j = 0; j < 8; j++) {
-    tb[j] = (j < nup) ? __ldg(m.topo + us + j) : (uint8_t)0;
-    sl[j] = (j < nup) ? __ldg(m.f[F_landSlope] + us + j) : 0.0f;
-  }
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    const double slnb = (double)sl[j];
-    out.cp[j] = (j < nup && (tb[j] & 15) != myldd) ? slnb / (slope_i + slnb) : 0.0;
+  for (int j = 0; j < 8; j++) out.cp[j] = (j < nup) ? __ldg(m.d_cpd + us + j) : 0.0;
+}
+
+template <int ML>
+__global__ void k_derive_lateral(const DevModel m) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m.n) return;
+  const uint8_t tp = __ldg(m.topo + i);
+  const int nup = tp >> 4;
+  const int myldd = tp & 15;
+  const int64_t us = __ldg(m.up_start + i);
+  const double slope_i = LD(landSlope);
+  const bool riverMap = __ldg(m.river_slot + i) >= 0;
+  for (int j = 0; j < nup; j++) {
+    const double slnb = (double)__ldg(m.f[F_landSlope] + us + j);
+    const int nbldd = __ldg(m.topo + us + j) & 15;
+    m.d_cpd[us + j] = (riverMap && nbldd != myldd) ? slnb / (slope_i + slnb) : 0.0;
   }
 }
 
@@ -217,7 +238,6 @@ template <int ML, int MODE>
 __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t i WF_PARGS) {
   const uint8_t tp = __ldg(m.topo + i);
   const int nup = tp >> 4;
-  const int myldd = tp & 15;
   const uint32_t us = __ldg(m.up_start + i);
   const int32_t rs = __ldg(m.river_slot + i);
   const bool riverMap = rs >= 0;
@@ -246,7 +266,7 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
   for (int j = 0; j < 8; j++) sv[j] = (j < nup) ? ldx<MODE>(m.h_ssf + (int64_t)us + j) : 0.0;  // all loads in flight at once
   if (riverMap) {
     ChanPerc c;
-    chan_perc_all(m, (int64_t)us, nup, myldd, slope_i, c);
+    chan_perc_all(m, (int64_t)us, nup, c);
 #pragma unroll
     for (int j = 0; j < 8; j++) {
       if (j < nup) {
@@ -254,7 +274,7 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
         ssf_tr = ssf_tr + c.cp[j] * sv[j];
       }
     }
-    m.h_ssf_tr[rs] = (float)(ssf_tr / (1000 * 1000 * 1000) / m.dt);
+    m.h_ssf_tr[rs] = (float)qdiv(ssf_tr / (1000 * 1000 * 1000), m.dt);
   } else {
 #pragma unroll
     for (int j = 0; j < 8; j++)
@@ -265,8 +285,8 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
   const double neff = (double)neff_f;
   const double dneff = thetaS - thetaR;
   const double r = rsum * DW * 1000;                                   // :674
-  const double efD = exp(-fpar * ST);
-  const double ssfmax = ((Kh * KsatVer * slope_i) / fpar) * (1.0 - efD);  // :2291-2299
+  const double efD = __ldg(m.d_efST + i);  // exp(-f * SoilThickness), derived static
+  const double ssfmax = qdiv(Kh * KsatVer * slope_i, fpar) * (1.0 - efD);  // :2291-2299
   double ssf_n, zi_n, ExfiltSatWater;
   kinematic_wave_ssf(ssf_in, ssf_old, zi_old, r, Kh, KsatVer, slope_i, neff, fpar, ST, efD, 1.0, DLd * 1000,
                      DW * 1000, ssfmax, ssf_n, zi_n, ExfiltSatWater);
@@ -306,14 +326,14 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
   }
   const double ExfiltWater = ExfiltSatWater + ExfiltFromUstore;
   // InwaterO :774 -- ExfiltWater + [ExcessWater + InfiltExcess + RunoffLandCells - ActEvapOpenWaterLand]
-  const double InwaterO = pymax(ExfiltWater + surplus, 0.0) * xlyl * 0.001 / m.dt;
+  const double InwaterO = qdiv(pymax(ExfiltWater + surplus, 0.0) * xlyl * 0.001, m.dt);
   m.h_inwO[i] = InwaterO;
 
   double sumU = 0.0;
 #pragma unroll
   for (int k = 0; k < ML; k++) sumU += U[k];
   OUTF(SatWaterDepth, Sat); OUTF(UStoreDepth, sumU);
-  OUTF(ssf_toriver, riverMap ? ssf_tr / (1000 * 1000 * 1000) / m.dt : 0.0);
+  OUTF(ssf_toriver, riverMap ? qdiv(ssf_tr / (1000 * 1000 * 1000), m.dt) : 0.0);
   OUTF(ExfiltWater, ExfiltWater); OUTF(ExfiltFromUstore, ExfiltFromUstore); OUTF(ExfiltFromSat, ExfiltSatWater);
   OUTF(InwaterL, InwaterO); OUTF(CellInFlow, ssf_in);
 #pragma unroll
@@ -321,7 +341,7 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
     float *vw = m.f[F_vwc_0 + k];
     if (vw) {  // :792-803
       if (k < mc_new) {
-        if (thick[k] > 0) vw[i] = (float)((U[k] + (thick[k] - L_new[k]) * dneff) / thick[k] + thetaR);
+        if (thick[k] > 0) vw[i] = (float)(qdiv(U[k] + (thick[k] - L_new[k]) * dneff, thick[k]) + thetaR);
       } else {
         vw[i] = (float)thetaS;
       }
@@ -332,11 +352,11 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
     double rsu = 0.0;
 #pragma unroll
     for (int k = 0; k < ML; k++)
-      if (k < nLn && L_new[k] > 0) rsu = rsu + (pymax(0.0, ActRoot - tops[k]) / L_new[k]) * U[k];
+      if (k < nLn && L_new[k] > 0) rsu = rsu + qdiv(pymax(0.0, ActRoot - tops[k]), L_new[k]) * U[k];
     m.f[F_RootStore_unsat][i] = (float)rsu;
   }
   if (m.f[F_SoilWatbal] && m.h_wb) {  // :885-898; h_wb holds the cell-local terms (vertical kernel)
-    const double wb = m.h_wb[i] - (Sat + sumU) + (ssf_in - ssf_n) / (DW * DLd * 1000 * 1000) - ExfiltWater;
+    const double wb = m.h_wb[i] - (Sat + sumU) + qdiv(ssf_in - ssf_n, DW * DLd * 1000 * 1000) - ExfiltWater;
     m.f[F_SoilWatbal][i] = (float)wb;
     if (m.f[F_watbal] && m.f[F_SurfaceWatbal]) m.f[F_watbal][i] = (float)wb + m.f[F_SurfaceWatbal][i];
   }
@@ -348,17 +368,16 @@ template <int MODE>
 __device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i WF_PARGS) {
   const uint8_t tp = __ldg(m.topo + i);
   const int nup = tp >> 4;
-  const int myldd = tp & 15;
   const uint32_t us = __ldg(m.up_start + i);
   const int32_t rs = __ldg(m.river_slot + i);
   const bool riverMap = rs >= 0;
   const int itL = m.itL;
   const double SW = LD(SW), AlphaL = LD(AlphaL), Beta = m.beta, DLd = LD(DL);
-  const double dts = m.dt / itL;
-  const double q = ldx<MODE>(m.h_inwO + i) / DLd;
+  const double dts = qdiv(m.dt, (double)itL);
+  const double q = qdiv(ldx<MODE>(m.h_inwO + i), DLd);
   double Qold = m.f[F_LandRunoffsub][i];
   ChanPerc c;
-  if (riverMap) chan_perc_all(m, (int64_t)us, nup, myldd, (double)LD(landSlope), c);
+  if (riverMap) chan_perc_all(m, (int64_t)us, nup, c);
   double acc_flow = 0.0, acc_h = 0.0, Qo_in_acc = 0.0, qo_toriver_acc = 0.0;
   double wlsub = 0.0;  // dyn["WaterLevelLsub"] starts at 0 and is only written where SW > 0 (:873-878)
 #pragma unroll 1
@@ -398,17 +417,17 @@ __device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i
     acc_flow = acc_flow + qn * dts;
     Qo_in_acc = Qo_in_acc + qo_in * dts;
     qo_toriver_acc = qo_toriver_acc + qo_toriver_vol;
-    if (SW > 0) wlsub = (AlphaL * qbeta) / SW;
+    if (SW > 0) wlsub = qdiv(AlphaL * qbeta, SW);
     acc_h = acc_h + wlsub;
     Qold = qn;
     qbuf[i] = (float)qn;
   }
   m.f[F_WaterLevelLsub][i] = (float)wlsub;
-  m.f[F_LandRunoff][i] = (float)(acc_flow / m.dt);
-  m.f[F_WaterLevelL][i] = (float)(acc_h / itL);
-  const float qo_toriver_f = (float)(qo_toriver_acc / m.dt);
+  m.f[F_LandRunoff][i] = (float)qdiv(acc_flow, m.dt);
+  m.f[F_WaterLevelL][i] = (float)qdiv(acc_h, (double)itL);
+  const float qo_toriver_f = (float)qdiv(qo_toriver_acc, m.dt);
   OUTF(qo_toriver, qo_toriver_f);
-  OUTF(InflowKinWaveCellLand, Qo_in_acc / m.dt);
+  OUTF(InflowKinWaveCellLand, qdiv(Qo_in_acc, m.dt));
 
   if (riverMap) {  // lateral inflow of the channel, wflow_sbm.py:3052-3065, 3144
     const float dtf = (float)m.dt;
@@ -450,19 +469,19 @@ __device__ __forceinline__ void task_river(const DevModel &m, const int32_t rs, 
       if (j < nup) Qin = Qin + (double)qv[j];
   }
   const double qr = (double)(inw / DCLf);  // :3152 (REAL4 division)
-  const double dtr = m.dt / itR;
+  const double dtr = qdiv(m.dt, (double)itR);
   // Qo: the previous sub-step's outflow of this cell, or the state at the first sub-step (:199)
   double qbeta;
   WF_STAMP(0, qr + A + Bw + Qo + racc0);
   WF_STAMP(1, Qin);
   const double qn = kinematic_wave(Qin, Qo, qr, A, m.beta, dtr, (double)DCLf, qbeta);
   WF_STAMP(2, qn);
-  const double wl = (A * qbeta) / Bw;
+  const double wl = qdiv(A * qbeta, Bw);
   const double racc = racc0 + qn * dtr, rh = rh0 + wl;
   qbuf[rs] = (float)qn;
   if (v == itR - 1) {
-    m.f[F_RiverRunoff][rs] = (float)(racc / m.dt);
-    m.f[F_WaterLevelR][rs] = (float)(rh / itR);
+    m.f[F_RiverRunoff][rs] = (float)qdiv(racc, m.dt);
+    m.f[F_WaterLevelR][rs] = (float)qdiv(rh, (double)itR);
     m.f[F_WaterLevelRsub][rs] = (float)wl;
   } else {
     m.h_racc[rs] = racc;
