@@ -149,7 +149,7 @@ int wf_last_step_ms(wf_model *m, float ms[3]);
 int wf_timing_reset(wf_model *m);
 int wf_timing_get(wf_model *m, double ms[3], int64_t *nsteps);
 /* How the lateral sweep is launched for this network: out[0] = 0 cooperative grid (one group),
- * 1 thread-block clusters, 2 single blocks; out[1] = blocks per cluster; out[2] = groups;
+ * 1 thread-block clusters, 2 single blocks, 3 clusters of wider blocks; out[1] = blocks per cluster; out[2] = groups;
  * out[3] = blocks launched (0 before the first step). */
 int wf_lateral_plan(const wf_model *m, int32_t out[4]);
 /* Number of kernel launches issued by the model since creation. */
@@ -168,6 +168,13 @@ int wf_area_ids(wf_model *m, int area, int32_t *ids);
 int wf_area_reduce(wf_model *m, int area, const char *field, int op, float *out /* [num_ids] */);
 /* Sample a field at cells (gauges): out[i] = field[flat_index[i]] (mv outside the network). */
 int wf_sample(wf_model *m, const char *field, const int64_t *flat_index, int64_t n, float *out, float mv);
+
+/* Persistent gauge set: the cells are resolved once; sampling is then one small kernel and one copy
+ * on the model's stream (the per-step read of wf_OutputTimeSeriesArea's sampled cells).  With
+ * async != 0 the call returns without waiting: `out` (ideally pinned memory) is valid after
+ * wf_synchronize or any later blocking call on the model. */
+int wf_gauges_create(wf_model *m, const int64_t *flat_index, int64_t n);
+int wf_gauges_sample(wf_model *m, int gauges, const char *field, float *out /* [n] */, float mv, int async);
 
 /* --- batched solvers ----------------------------------------------------------------------
  * The two Newton solvers of the path, exposed on their own so that they can be checked against

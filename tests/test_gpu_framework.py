@@ -106,3 +106,22 @@ def test_bmi_contract(case):
     bmi.save_state(os.path.join(case, "bmistate"))
     assert os.path.isfile(os.path.join(case, "bmistate", "TSoil.map"))  # tests/test_BMI.py:104
     bmi.finalize()
+
+
+@pytest.mark.gpu
+def test_gauge_set_matches_sample():
+    """wf_gauges_* (persistent, asynchronous) returns what wf_sample returns, for cell and river fields."""
+    from tests import common
+    orc, mod, ldd, river = common.make_pair(48, 64, kind="tiles", tile=16, layer_thickness=(100, 300), dt=86400, river_area=8)
+    from wflow_b200 import synth
+    forc = synth.Forcing(48, 64, seed=3, timestepsecs=86400, rain_mean=15.0)
+    P, PET, T = forc.step(0)
+    mod.set("P", P); mod.set("PET", PET); mod.set("TEMP", T)
+    mod.step(2)
+    idx = np.array([0, 5, 17 * 64 + 3, 47 * 64 + 63, 20 * 64 + 20], np.int64)
+    h = mod.gauges_create(idx)
+    for field in ("zi", "RiverRunoff", "LandRunoff"):
+        out = np.full(idx.size, 7.0, np.float32)
+        mod.gauges_sample(h, field, out.ctypes.data, wait=True)
+        np.testing.assert_array_equal(out, mod.sample(field, idx))
+    mod.close()

@@ -41,7 +41,7 @@ SYMBOLS = [
     "wf_schedule_create", "wf_schedule_destroy", "wf_schedule_num_cells", "wf_schedule_num_levels",
     "wf_schedule_get", "wf_schedule_catchment_total", "wf_create_from_schedule", "wf_bind_field",
     "wf_timing_reset", "wf_timing_get", "wf_kinematic_wave_batch", "wf_kinematic_wave_ssf_batch",
-    "wf_schedule_partition", "wf_lateral_plan",
+    "wf_schedule_partition", "wf_lateral_plan", "wf_gauges_create", "wf_gauges_sample",
 ]
 
 
@@ -108,6 +108,8 @@ def lib():
     l.wf_kinematic_wave_ssf_batch.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
     l.wf_schedule_partition.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.wf_lateral_plan.argtypes = [C.c_void_p, C.c_void_p]
+    l.wf_gauges_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    l.wf_gauges_sample.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_float, C.c_int]
     l.wf_quick_suspend.argtypes = [C.c_void_p]
     l.wf_quick_resume.argtypes = [C.c_void_p]
     _lib = l

@@ -238,7 +238,7 @@ class SbmModel:
         """How the lateral sweep runs: dict(mode=grid|cluster|cta, cluster_size, groups, blocks)."""
         out = (C.c_int32 * 4)()
         _lib.check(self._l.wf_lateral_plan(self._h, out))
-        return {"mode": ("grid", "cluster", "cta")[out[0]], "cluster_size": int(out[1]), "groups": int(out[2]),
+        return {"mode": ("grid", "cluster", "cta", "cluster-wide")[out[0]], "cluster_size": int(out[1]), "groups": int(out[2]),
                 "blocks": int(out[3])}
 
     @property
@@ -271,6 +271,16 @@ class SbmModel:
         out = np.zeros(max(n, 1), np.float32)
         _lib.check(self._l.wf_area_reduce(self._h, area, field.encode(), AREA_OPS[op], out.ctypes.data))
         return out[:n]
+
+    def gauges_create(self, flat_index):
+        """Persistent gauge set (cells resolved once); returns a handle for gauges_sample."""
+        idx = np.ascontiguousarray(flat_index, dtype=np.int64)
+        return _lib.check(self._l.wf_gauges_create(self._h, idx.ctypes.data, idx.size))
+
+    def gauges_sample(self, handle, field, out_ptr, mv=-999.0, wait=True):
+        """Sample `field` at the gauge set into the caller's float32 buffer (raw pointer; pinned memory
+        when wait=False, valid after synchronize())."""
+        _lib.check(self._l.wf_gauges_sample(self._h, int(handle), field.encode(), out_ptr, float(mv), 0 if wait else 1))
 
     def sample(self, field, flat_index, mv=-999.0):
         idx = np.ascontiguousarray(flat_index, dtype=np.int64)

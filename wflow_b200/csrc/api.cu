@@ -78,7 +78,23 @@ struct wf_model {
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_last[3] = {nullptr, nullptr, nullptr};
   int64_t *d_order = nullptr, *d_rorder = nullptr;
-  float *d_stage = nullptr;          // nrow*ncol staging raster
+  float *d_stage = nullptr;          // nrow*ncol staging raster (wf_get_field)
+  // host -> device staging of wf_set_field: a ring of rasters filled on a copy stream, so that the
+  // upload of the next step's forcing overlaps the running step's kernels
+  static const int kStageRing = 6;
+  float *d_ring[kStageRing] = {};
+  cudaEvent_t ring_copied[kStageRing] = {}, ring_free[kStageRing] = {};
+  int ring_next = 0;
+  cudaStream_t copy_stream = nullptr;
+  std::vector<int32_t> pos_of_flat;  // flat grid index -> storage position (-1 outside the network)
+  struct GaugeSet {
+    int64_t n = 0;
+    int32_t *d_pos = nullptr;        // storage position (river order for river fields is resolved per call)
+    int32_t *d_rpos = nullptr;       // river-order position or -1
+    float *d_out = nullptr;
+    std::vector<int32_t> pos, rpos;
+  };
+  std::vector<GaugeSet> gauges;
   std::vector<float *> snapshot;     // quick-suspend copies of the state arrays
   std::vector<AreaSet> areas;
   int64_t launches = 0;
@@ -131,7 +147,7 @@ int resident_clusters(int mode, int cs, size_t smem) {
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)cs * 64);
-  cfg.blockDim = dim3(WF_GROUP_THREADS);
+  cfg.blockDim = dim3((unsigned)wf_block_threads(mode));
   cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -141,7 +157,9 @@ int resident_clusters(int mode, int cs, size_t smem) {
   cfg.attrs = at;
   cfg.numAttrs = 1;
   int nc = 0;
-  if (cudaOccupancyMaxActiveClusters(&nc, k_lateral_wave<ML, WF_CLUSTER>, &cfg) != cudaSuccess) {
+  const cudaError_t e = (mode == WF_CLUSTER_WIDE) ? cudaOccupancyMaxActiveClusters(&nc, k_lateral_wave<ML, WF_CLUSTER_WIDE>, &cfg)
+                                                  : cudaOccupancyMaxActiveClusters(&nc, k_lateral_wave<ML, WF_CLUSTER>, &cfg);
+  if (e != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
@@ -150,15 +168,14 @@ int resident_clusters(int mode, int cs, size_t smem) {
 
 template <int ML>
 LateralPlan plan_lateral(int64_t n, int64_t D, int64_t nbasins, int sms) {
-  const double items = 2.1 * (double)n / (double)std::max<int64_t>(D, 1);  // per tick, whole network
+  // Time of one tick, calibrated on B200 (bench workload): a fixed critical
+  // path (barrier + one gather + one solve) plus a share that grows with the items an SM holds,
+  //   block / cluster sweep:  5.0 us + 9.0 ns per item and SM
+  //   grid sweep:             6.0 us + 13.5 ns per item and SM (256-thread blocks, grid barrier)
+  const double items = 2.3 * (double)n / (double)std::max<int64_t>(D, 1);  // per tick, whole network
   LateralPlan best;
-  {  // grid: barrier ~2800 cycles, post-barrier load chain + solve ~9000, ~3500 per pass of one item per thread
-    int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lateral_wave<ML, WF_GRID>, 256, 0);
-    const double threads = (double)sms * std::max(per_sm, 1) * 256;
-    best.mode = WF_GRID; best.cs = 1; best.groups = 1;
-    best.cost = (double)D * (2800 + 9000 + std::ceil(items / threads) * 3500);
-  }
+  best.mode = WF_GRID; best.cs = 1; best.groups = 1;
+  best.cost = (double)D * (6.0e3 + 13.5 * items / sms);
   const int sizes[] = {1, 2, 4, 8};
   for (int cs : sizes) {
     const int mode = (cs == 1) ? WF_CTA : WF_CLUSTER;
@@ -166,9 +183,8 @@ LateralPlan plan_lateral(int64_t n, int64_t D, int64_t nbasins, int sms) {
     if (res < 1) continue;
     const int64_t G = std::min<int64_t>(nbasins, res);
     if (G < 1) continue;
-    const double per_group = items / (double)G;
-    const double sync = (cs == 1) ? 60 : 450;
-    const double cost = (double)D * (sync + 4500 + std::ceil(per_group / (cs * (double)WF_GROUP_THREADS)) * 3500);
+    const double per_sm = items / (double)G / cs;
+    const double cost = (double)D * (5.0e3 + 9.0 * per_sm);
     if (cost < best.cost) { best.mode = mode; best.cs = cs; best.groups = (int)G; best.cost = cost; }
   }
   return best;
@@ -187,11 +203,13 @@ int launch_lateral(wf_model *m) {
       // no more blocks than the busiest tick can use (subsurface + overland + river items)
       m->lat_blocks = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * per_sm, (m->max_tick_items + 255) / 256));
     }
-    CUDA_OK(cudaLaunchCooperativeKernel((void *)k_lateral_wave<ML, WF_GRID>, dim3(m->lat_blocks), dim3(256), args, 0, m->stream));
+    CUDA_OK(cudaMemsetAsync(m->dm.grid_counter, 0, sizeof(unsigned int), m->stream));
+    CUDA_OK(cudaLaunchCooperativeKernel((void *)k_lateral_wave<ML, WF_GRID>, dim3(m->lat_blocks), dim3(256), args, m->lat_smem, m->stream));
     return WF_OK;
   }
   const bool cta = m->lat_mode == WF_CTA;
-  void *fn = cta ? (void *)k_lateral_wave<ML, WF_CTA> : (void *)k_lateral_wave<ML, WF_CLUSTER>;
+  void *fn = cta ? (void *)k_lateral_wave<ML, WF_CTA>
+                 : (m->lat_mode == WF_CLUSTER_WIDE ? (void *)k_lateral_wave<ML, WF_CLUSTER_WIDE> : (void *)k_lateral_wave<ML, WF_CLUSTER>);
   if (m->lat_blocks == 0) {
     if (m->lat_smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->lat_smem));
     const int res = resident_clusters<ML>(m->lat_mode, m->cluster_size, m->lat_smem);
@@ -200,7 +218,7 @@ int launch_lateral(wf_model *m) {
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)m->lat_blocks);
-  cfg.blockDim = dim3(WF_GROUP_THREADS);
+  cfg.blockDim = dim3((unsigned)wf_block_threads(m->lat_mode));
   cfg.dynamicSmemBytes = m->lat_smem;
   cfg.stream = m->stream;
   cudaLaunchAttribute at[1];
@@ -455,13 +473,44 @@ int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint
     regroup(m->rnet, rgroup_of, G, m->srnet, m->rlay, rnewpos);
     m->lat_mode = plan.mode;
     m->cluster_size = plan.cs;
+    if (plan.mode == WF_CLUSTER) {
+      // passes (items / threads of the cluster, rounded up) summed over the ticks of the slowest group, for the
+      // regular and the wide block: the wide block has fewer registers per thread (a pass costs ~6 % more)
+      double worst_reg = 0, worst_wide = 0;
+      const int Dn = (int)m->net.nlevels(), Dr = (int)m->rnet.nlevels(), shift = Dn - Dr;
+      for (int g = 0; g < m->lay.ngroups; g++) {
+        const uint32_t *lo = m->lay.lev_off.data() + m->lay.lev_idx[(size_t)g];
+        const uint32_t *ro = m->rlay.lev_off.data() + m->rlay.lev_idx[(size_t)g];
+        const int l0 = m->lay.lev0[(size_t)g], r0 = m->rlay.lev0[(size_t)g];
+        const int nl = Dn - l0, nrl = Dr - r0;
+        double preg = 0, pwide = 0;
+        for (int t = 0; t < nl + 1 + cfg->it_kin_r; t++) {
+          int64_t items = 0;
+          if (t < nl) items += ((int64_t)(lo[t + 1] - lo[t]) + 31) & ~31LL;
+          if (t >= 1 && t - 1 < nl) items += ((int64_t)(lo[t] - lo[t - 1]) + 31) & ~31LL;
+          for (int v = 0; v < cfg->it_kin_r; v++) {
+            const int q = (l0 - 2) - shift - r0 + t - v;
+            if (q >= 0 && q < nrl) items += ro[q + 1] - ro[q];
+          }
+          const int64_t treg = (int64_t)plan.cs * WF_GROUP_THREADS, twide = (int64_t)plan.cs * WF_GROUP_THREADS_WIDE;
+          preg += (double)std::max<int64_t>(1, (items + treg - 1) / treg);
+          pwide += (double)std::max<int64_t>(1, (items + twide - 1) / twide);
+        }
+        worst_reg = std::max(worst_reg, preg);
+        worst_wide = std::max(worst_wide, pwide);
+      }
+      bool wide = worst_wide * 1.06 < worst_reg;
+      if (const char *e = std::getenv("WF_CLUSTER_WIDE")) wide = std::atoi(e) != 0;
+      if (wide) m->lat_mode = WF_CLUSTER_WIDE;
+    }
   }
   const Network &snet = m->snet, &srnet = m->srnet;
   // river order: river-network cells in storage order, then river-map cells kin_wave never visits
   m->river_slot.assign((size_t)std::max<int64_t>(n, 1), -1);
   {
     std::vector<int32_t> slot_of_flat((size_t)N, -1);
-    std::vector<int32_t> pos_of_flat((size_t)N, -1);
+    std::vector<int32_t> &pos_of_flat = m->pos_of_flat;
+    pos_of_flat.assign((size_t)N, -1);
     for (int64_t k = 0; k < n; k++) pos_of_flat[(size_t)snet.order[(size_t)k]] = (int32_t)k;
     int32_t s = 0;
     for (int64_t k = 0; k < srnet.ncells; k++) {
@@ -548,7 +597,7 @@ int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint
     dm.groups = m->d_groups;
     dm.ngroups = G;
     // a group's level offsets live in shared memory during its sweep when they fit
-    if (m->lat_mode != WF_GRID && most * 4 <= 160 * 1024) {
+    if (most * 4 <= ((m->lat_mode == WF_GRID) ? 40 : 160) * 1024) {  // (most: level-offset entries of the largest group)
       dm.lev_cache = (int32_t)most;
       m->lat_smem = (size_t)most * 4;
     }
@@ -561,6 +610,10 @@ int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint
   CUDA_OK(cudaMalloc(&dm.h_r, sizeof(double) * std::max<int64_t>(n, 1)));
   CUDA_OK(cudaMalloc(&dm.h_surplus, sizeof(float) * std::max<int64_t>(n, 1)));
   CUDA_OK(cudaMalloc(&dm.h_ssf, sizeof(double) * std::max<int64_t>(n, 1)));
+  CUDA_OK(cudaMalloc(&dm.h_ssf_riv, sizeof(double) * std::max<int64_t>(n, 1)));
+  CUDA_OK(cudaMalloc(&dm.h_qa, sizeof(double) * (size_t)dm.itL * std::max<int64_t>(n, 1)));
+  CUDA_OK(cudaMalloc(&dm.h_qb, sizeof(double) * (size_t)dm.itL * std::max<int64_t>(n, 1)));
+  CUDA_OK(cudaMalloc(&dm.grid_counter, 256));
   CUDA_OK(cudaMalloc(&dm.h_ulo, sizeof(float) * (size_t)m->ML * std::max<int64_t>(n, 1)));
   CUDA_OK(cudaMalloc(&dm.h_inwaterMM, sizeof(float) * std::max<int32_t>(m->nr, 1)));
   CUDA_OK(cudaMalloc(&dm.h_inwO, sizeof(double) * std::max<int64_t>(n, 1)));
@@ -587,7 +640,7 @@ int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint
       }
       best = std::max(best, items);
     }
-    m->max_tick_items = best;
+    m->max_tick_items = best + 64;  // two warp-boundary paddings of the item space
   }
   if (dm.itL > 1) CUDA_OK(cudaMalloc(&dm.qo_sub, sizeof(float) * (size_t)(dm.itL - 1) * std::max<int64_t>(n, 1)));
   if (dm.itR > 1) CUDA_OK(cudaMalloc(&dm.qr_sub, sizeof(float) * (size_t)(dm.itR - 1) * std::max<int32_t>(m->nr, 1)));
@@ -627,10 +680,18 @@ void wf_destroy(wf_model *m) {
     if (m->external[id]) cudaFree(m->owned[id]);
     else cudaFree(m->dm.f[id]);
   }
+  for (int b = 0; b < wf_model::kStageRing; b++) {
+    cudaFree(m->d_ring[b]);
+    if (m->ring_copied[b]) cudaEventDestroy(m->ring_copied[b]);
+    if (m->ring_free[b]) cudaEventDestroy(m->ring_free[b]);
+  }
+  if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+  for (auto &g : m->gauges) { cudaFree(g.d_pos); cudaFree(g.d_rpos); cudaFree(g.d_out); }
   for (cudaEvent_t e : m->tev) cudaEventDestroy(e);
   for (float *p : m->snapshot) cudaFree(p);
   for (auto &a : m->areas) { cudaFree(a.d_perm); cudaFree(a.d_seg); }
   cudaFree(m->dm.d_efT); cudaFree(m->dm.d_efST); cudaFree(m->dm.d_cpd);
+  cudaFree(m->dm.h_ssf_riv); cudaFree(m->dm.h_qa); cudaFree(m->dm.h_qb); cudaFree(m->dm.grid_counter);
   cudaFree(m->dm.h_r); cudaFree(m->dm.h_surplus); cudaFree(m->dm.h_ulo); cudaFree(m->dm.h_ssf);
   cudaFree(m->dm.h_inwO); cudaFree(m->dm.h_ssf_tr); cudaFree(m->dm.h_inwater); cudaFree(m->dm.h_racc); cudaFree(m->dm.h_rh);
   cudaFree(m->d_rlev_off); cudaFree(m->d_groups); cudaFree((void *)m->dm.r_up_start); cudaFree((void *)m->dm.r_nup); cudaFree(m->dm.h_inwaterMM); cudaFree(m->dm.h_wb);
@@ -737,10 +798,26 @@ int wf_set_field(wf_model *m, const char *name, const float *grid) {
   const int id = field_index(name);
   if (id < 0) return fail(WF_EINVAL, std::string("unknown field: ") + (name ? name : "(null)"));
   CUDA_OK(cudaSetDevice(m->cfg.device));
-  if (int rc = stage(m)) return rc;
   const size_t bytes = sizeof(float) * (size_t)m->cfg.nrow * m->cfg.ncol;
-  CUDA_OK(cudaMemcpyAsync(m->d_stage, grid, bytes, cudaMemcpyHostToDevice, m->stream));
-  return gather_into(m, id, m->d_stage);
+  // next slot of the staging ring: copy on the copy stream (waits only for the gather that last read
+  // the slot), gather on the model's stream (waits for the copy) -- the copy of step s+1's forcing
+  // runs while step s computes, as long as the host enqueues ahead
+  const int b = m->ring_next;
+  m->ring_next = (b + 1) % wf_model::kStageRing;
+  if (!m->copy_stream) CUDA_OK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  if (!m->d_ring[b]) {
+    CUDA_OK(cudaMalloc(&m->d_ring[b], bytes));
+    CUDA_OK(cudaEventCreateWithFlags(&m->ring_copied[b], cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&m->ring_free[b], cudaEventDisableTiming));
+  } else {
+    CUDA_OK(cudaStreamWaitEvent(m->copy_stream, m->ring_free[b], 0));
+  }
+  CUDA_OK(cudaMemcpyAsync(m->d_ring[b], grid, bytes, cudaMemcpyHostToDevice, m->copy_stream));
+  CUDA_OK(cudaEventRecord(m->ring_copied[b], m->copy_stream));
+  CUDA_OK(cudaStreamWaitEvent(m->stream, m->ring_copied[b], 0));
+  const int rc = gather_into(m, id, m->d_ring[b]);
+  CUDA_OK(cudaEventRecord(m->ring_free[b], m->stream));
+  return rc;
 }
 
 int wf_set_field_from_device(wf_model *m, const char *name, const float *dgrid) {
@@ -852,6 +929,7 @@ int wf_step(wf_model *m, int nsteps) {
 int wf_synchronize(wf_model *m) {
   if (!m) return fail(WF_EINVAL, "null model");
   CUDA_OK(cudaSetDevice(m->cfg.device));
+  if (m->copy_stream) CUDA_OK(cudaStreamSynchronize(m->copy_stream));
   CUDA_OK(cudaStreamSynchronize(m->stream));
   return WF_OK;
 }
@@ -986,17 +1064,13 @@ int wf_sample(wf_model *m, const char *field, const int64_t *flat_index, int64_t
   CUDA_OK(cudaSetDevice(m->cfg.device));
   // translate flat grid indices to array positions on the host (gauge lists are short)
   static thread_local std::vector<int32_t> pos;
-  std::map<int64_t, int32_t> want;
-  for (int64_t i = 0; i < n; i++) want[flat_index[i]] = -1;
-  for (int64_t k = 0; k < m->n; k++) {
-    auto it = want.find(m->snet.order[(size_t)k]);
-    if (it != want.end()) it->second = (int32_t)k;
-  }
+  const int64_t N = (int64_t)m->cfg.nrow * m->cfg.ncol;
   const bool riv = g_fields[id].kind & K_RIVER;
   pos.assign((size_t)n, -1);
   std::vector<int> zero((size_t)n, 0);
   for (int64_t i = 0; i < n; i++) {
-    int32_t k = want[flat_index[i]];
+    const int64_t fl = flat_index[i];
+    int32_t k = (fl >= 0 && fl < N) ? m->pos_of_flat[(size_t)fl] : -1;
     if (k >= 0 && riv) {
       const int32_t s = m->river_slot[(size_t)k];
       if (s < 0) zero[(size_t)i] = 1;
@@ -1019,6 +1093,48 @@ int wf_sample(wf_model *m, const char *field, const int64_t *flat_index, int64_t
     if (zero[(size_t)i]) out[i] = 0.0f;
   cudaFree(d_pos);
   cudaFree(d_out);
+  return WF_OK;
+}
+
+// Persistent gauge sets: positions resolved once, sampling is one small kernel + one copy.
+int wf_gauges_create(wf_model *m, const int64_t *flat_index, int64_t n) {
+  if (!m || !flat_index || n < 0) return fail(WF_EINVAL, "bad argument");
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  wf_model::GaugeSet g;
+  g.n = n;
+  const int64_t N = (int64_t)m->cfg.nrow * m->cfg.ncol;
+  g.pos.assign((size_t)std::max<int64_t>(n, 1), -1);
+  g.rpos.assign((size_t)std::max<int64_t>(n, 1), -1);
+  for (int64_t i = 0; i < n; i++) {
+    const int64_t fl = flat_index[i];
+    const int32_t k = (fl >= 0 && fl < N) ? m->pos_of_flat[(size_t)fl] : -1;
+    g.pos[(size_t)i] = k;
+    g.rpos[(size_t)i] = (k >= 0) ? m->river_slot[(size_t)k] : -1;
+  }
+  const size_t nb = sizeof(int32_t) * (size_t)std::max<int64_t>(n, 1);
+  CUDA_OK(cudaMalloc(&g.d_pos, nb));
+  CUDA_OK(cudaMalloc(&g.d_rpos, nb));
+  CUDA_OK(cudaMalloc(&g.d_out, sizeof(float) * (size_t)std::max<int64_t>(n, 1)));
+  CUDA_OK(cudaMemcpy(g.d_pos, g.pos.data(), nb, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(g.d_rpos, g.rpos.data(), nb, cudaMemcpyHostToDevice));
+  m->gauges.push_back(std::move(g));
+  return (int)m->gauges.size() - 1;
+}
+
+int wf_gauges_sample(wf_model *m, int gauges, const char *field, float *out, float mv, int async) {
+  if (!m || !out || gauges < 0 || gauges >= (int)m->gauges.size()) return fail(WF_EINVAL, "bad gauge-set handle");
+  const int id = field_index(field);
+  if (id < 0 || !m->dm.f[id]) return fail(WF_EINVAL, std::string("field has no data: ") + (field ? field : "(null)"));
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  wf_model::GaugeSet &g = m->gauges[(size_t)gauges];
+  if (g.n == 0) return WF_OK;
+  const bool riv = g_fields[id].kind & K_RIVER;
+  // river-only fields hold 0 at the other cells of the network (wflow_funcs.py:172-182), mv outside it
+  k_sample_gauges<<<(unsigned)((g.n + 127) / 128), 128, 0, m->stream>>>(m->dm.f[id], g.d_pos, riv ? g.d_rpos : nullptr, g.d_out, g.n, mv);
+  m->launches++;
+  CUDA_OK(cudaMemcpyAsync(out, g.d_out, sizeof(float) * (size_t)g.n, cudaMemcpyDeviceToHost, m->stream));
+  if (!async) CUDA_OK(cudaStreamSynchronize(m->stream));
+  CUDA_OK(cudaGetLastError());
   return WF_OK;
 }
 

@@ -206,16 +206,10 @@ __device__ __noinline__ void kinematic_wave_ssf(double ssf_in, double ssf_old, d
 
 // Fraction of an upstream neighbour's outflow that a river cell takes straight into the channel
 // (wflow_sbm.py:395-398, 843-846): slope-weighted for neighbours that drain in another direction.
-// It depends on statics only, and every cell has exactly one receiver: k_derive_lateral stores it
-// per UPSTREAM cell (d_cpd), so a river cell reads the fractions of its (contiguous) upstream run.
-struct ChanPerc {
-  double cp[8];
-};
-__device__ __forceinline__ void chan_perc_all(const DevModel &m, int64_t us, int nup, ChanPerc &out) {
-#pragma unroll
-  for (int j = 0; j < 8; j++) out.cp[j] = (j < nup) ? __ldg(m.d_cpd + us + j) : 0.0;
-}
-
+// It depends on statics only and every cell has exactly one receiver, so k_derive_lateral stores it
+// per UPSTREAM cell (d_cpd; -1 when the receiver is not a river cell) and the SENDER splits its
+// outflow into the land share (1-cp)*Q and the channel share cp*Q -- the very products the reference
+// forms in the receiver -- so the receiver's gather is two plain contiguous sums.
 template <int ML>
 __global__ void k_derive_lateral(const DevModel m) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -229,34 +223,98 @@ __global__ void k_derive_lateral(const DevModel m) {
   for (int j = 0; j < nup; j++) {
     const double slnb = (double)__ldg(m.f[F_landSlope] + us + j);
     const int nbldd = __ldg(m.topo + us + j) & 15;
-    m.d_cpd[us + j] = (riverMap && nbldd != myldd) ? slnb / (slope_i + slnb) : 0.0;
+    m.d_cpd[us + j] = riverMap ? ((nbldd != myldd) ? slnb / (slope_i + slnb) : 0.0) : -1.0;
   }
+  if (myldd == 5) m.d_cpd[i] = -1.0;  // a pit has no receiver
+}
+
+// ---- operands of the three tasks --------------------------------------------------------------
+// Everything a task reads from its OWN cell (statics, its states, the column kernel's hand-offs) is
+// known before the tick starts: the thread fetches it for its next item BEFORE the barrier of the
+// running tick, so that after the barrier only the neighbours' fresh outflows remain to be read
+// (one L2 round trip instead of a DRAM-deep dependent chain).  None of these values is written by
+// another thread during the sweep.
+template <int ML>
+struct SubOps {
+  uint32_t us;
+  int32_t rs;
+  int nup;
+  float slope, ST, thetaS, thetaR, KsatVer, f, Kh, DW, DL, zi, ssf_old, surplus, xl, yl;
+  double rsum, efD, cpd;
+  float Uhi[ML], Ulo[ML];
+};
+struct OvlOps {
+  uint32_t us;
+  int32_t rs;
+  int nup;
+  float SW, AlphaL, DL, Qold;
+  double cpd;
+};
+struct RivOps {
+  uint32_t us;
+  int nup;
+  float DCL, A, Bw;
+};
+
+template <int ML>
+__device__ __forceinline__ void load_sub(const DevModel &m, const int64_t i, SubOps<ML> &o) {
+  const uint8_t tp = __ldg(m.topo + i);
+  o.nup = tp >> 4;
+  o.us = __ldg(m.up_start + i);
+  o.rs = __ldg(m.river_slot + i);
+  o.slope = LD(landSlope); o.ST = LD(SoilThickness); o.thetaS = LD(thetaS); o.thetaR = LD(thetaR);
+  o.KsatVer = LD(KsatVer); o.f = LD(f); o.Kh = LD(KsatHorFrac); o.DW = LD(DW); o.DL = LD(DL);
+  o.xl = LD(xl); o.yl = LD(yl);
+  o.zi = m.f[F_zi][i];
+  o.ssf_old = m.f[F_SubsurfaceFlow][i];
+  o.surplus = m.h_surplus[i];
+  o.rsum = m.h_r[i];
+  o.efD = __ldg(m.d_efST + i);  // exp(-f * SoilThickness), derived static
+  o.cpd = __ldg(m.d_cpd + i);
+#pragma unroll
+  for (int k = 0; k < ML; k++) {
+    o.Uhi[k] = m.f[F_UStoreLayerDepth_0 + k][i];
+    o.Ulo[k] = m.h_ulo[(int64_t)k * m.n + i];
+  }
+}
+__device__ __forceinline__ void load_ovl(const DevModel &m, const int64_t i, OvlOps &o) {
+  const uint8_t tp = __ldg(m.topo + i);
+  o.nup = tp >> 4;
+  o.us = __ldg(m.up_start + i);
+  o.rs = __ldg(m.river_slot + i);
+  o.SW = LD(SW); o.AlphaL = LD(AlphaL); o.DL = LD(DL);
+  o.Qold = m.f[F_LandRunoffsub][i];
+  o.cpd = __ldg(m.d_cpd + i);
+}
+__device__ __forceinline__ void load_riv(const DevModel &m, const int32_t rs, RivOps &o) {
+  o.nup = __ldg(m.r_nup + rs);
+  o.us = __ldg(m.r_up_start + rs);
+  o.DCL = __ldg(m.f[F_DCL] + rs);
+  o.A = __ldg(m.f[F_AlphaR] + rs);
+  o.Bw = __ldg(m.f[F_Bw] + rs);
 }
 
 // ---- task 1: subsurface flow + post-ssf column tail of one cell ------------------------------
 template <int ML, int MODE>
-__device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t i WF_PARGS) {
-  const uint8_t tp = __ldg(m.topo + i);
-  const int nup = tp >> 4;
-  const uint32_t us = __ldg(m.up_start + i);
-  const int32_t rs = __ldg(m.river_slot + i);
+__device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t i, const SubOps<ML> &o WF_PARGS) {
+  const int nup = o.nup;
+  const uint32_t us = o.us;
+  const int32_t rs = o.rs;
   const bool riverMap = rs >= 0;
-  const double slope_i = LD(landSlope);
-  // own-cell operands first (independent of the gather): the loads overlap the inflow latency
-  const double ST = LD(SoilThickness), thetaS = LD(thetaS), thetaR = LD(thetaR);
-  const float neff_f = LD(thetaS) - LD(thetaR);
-  const double KsatVer = LD(KsatVer), fpar = LD(f), Kh = LD(KsatHorFrac);
-  const double DW = LD(DW), DLd = LD(DL);
-  const double zi_old = m.f[F_zi][i];
-  const double rsum = m.h_r[i];
+  const double slope_i = o.slope;
+  const double ST = o.ST, thetaS = o.thetaS, thetaR = o.thetaR;
+  const float neff_f = o.thetaS - o.thetaR;
+  const double KsatVer = o.KsatVer, fpar = o.f, Kh = o.Kh;
+  const double DW = o.DW, DLd = o.DL;
+  const double zi_old = o.zi;
+  const double rsum = o.rsum;
   float *const ssfp = m.f[F_SubsurfaceFlow];
-  const double ssf_old = ssfp[i];
-  const double surplus = m.h_surplus[i];
-  const double xlyl = (double)LD(xl) * (double)LD(yl);
+  const double ssf_old = o.ssf_old;
+  const double surplus = o.surplus;
+  const double xlyl = (double)o.xl * (double)o.yl;
   double U[ML];
 #pragma unroll
-  for (int k = 0; k < ML; k++)
-    U[k] = (double)m.f[F_UStoreLayerDepth_0 + k][i] + (double)m.h_ulo[(int64_t)k * m.n + i];
+  for (int k = 0; k < ML; k++) U[k] = (double)o.Uhi[k] + (double)o.Ulo[k];
 
   WF_STAMP(0, U[0] + xlyl + ssf_old + rsum + surplus + DW + Kh + zi_old);
   // inflow gather, reference summation order (wflow_sbm.py:395-410)
@@ -265,13 +323,14 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
 #pragma unroll
   for (int j = 0; j < 8; j++) sv[j] = (j < nup) ? ldx<MODE>(m.h_ssf + (int64_t)us + j) : 0.0;  // all loads in flight at once
   if (riverMap) {
-    ChanPerc c;
-    chan_perc_all(m, (int64_t)us, nup, c);
+    double tv[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) tv[j] = (j < nup) ? ldx<MODE>(m.h_ssf_riv + (int64_t)us + j) : 0.0;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
       if (j < nup) {
-        ssf_in = ssf_in + (1 - c.cp[j]) * sv[j];
-        ssf_tr = ssf_tr + c.cp[j] * sv[j];
+        ssf_in = ssf_in + sv[j];  // (1 - chanperc) * ssf of the neighbour
+        ssf_tr = ssf_tr + tv[j];  // chanperc * ssf
       }
     }
     m.h_ssf_tr[rs] = (float)qdiv(ssf_tr / (1000 * 1000 * 1000), m.dt);
@@ -285,7 +344,7 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
   const double neff = (double)neff_f;
   const double dneff = thetaS - thetaR;
   const double r = rsum * DW * 1000;                                   // :674
-  const double efD = __ldg(m.d_efST + i);  // exp(-f * SoilThickness), derived static
+  const double efD = o.efD;
   const double ssfmax = qdiv(Kh * KsatVer * slope_i, fpar) * (1.0 - efD);  // :2291-2299
   double ssf_n, zi_n, ExfiltSatWater;
   kinematic_wave_ssf(ssf_in, ssf_old, zi_old, r, Kh, KsatVer, slope_i, neff, fpar, ST, efD, 1.0, DLd * 1000,
@@ -294,7 +353,13 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
   const double zi = pymin(zi_n, ST);  // :702
   const double Sat = (ST - zi) * dneff;
   ssfp[i] = (float)ssf_n;
-  m.h_ssf[i] = ssf_n;  // gathered by the downstream cell one tick later
+  // gathered by the downstream cell one tick later; a river receiver gets the two shares
+  if (o.cpd >= 0.0) {
+    m.h_ssf[i] = (1 - o.cpd) * ssf_n;
+    m.h_ssf_riv[i] = o.cpd * ssf_n;
+  } else {
+    m.h_ssf[i] = ssf_n;
+  }
   m.f[F_zi][i] = (float)zi;
 
   // post-ssf column tail, :707-821
@@ -365,19 +430,16 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
 
 // ---- task 2: overland flow of one cell, all sub-steps (wflow_sbm.py:830-879) -----------------
 template <int MODE>
-__device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i WF_PARGS) {
-  const uint8_t tp = __ldg(m.topo + i);
-  const int nup = tp >> 4;
-  const uint32_t us = __ldg(m.up_start + i);
-  const int32_t rs = __ldg(m.river_slot + i);
+__device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i, const OvlOps &o WF_PARGS) {
+  const int nup = o.nup;
+  const uint32_t us = o.us;
+  const int32_t rs = o.rs;
   const bool riverMap = rs >= 0;
   const int itL = m.itL;
-  const double SW = LD(SW), AlphaL = LD(AlphaL), Beta = m.beta, DLd = LD(DL);
+  const double SW = o.SW, AlphaL = o.AlphaL, Beta = m.beta, DLd = o.DL;
   const double dts = qdiv(m.dt, (double)itL);
   const double q = qdiv(ldx<MODE>(m.h_inwO + i), DLd);
-  double Qold = m.f[F_LandRunoffsub][i];
-  ChanPerc c;
-  if (riverMap) chan_perc_all(m, (int64_t)us, nup, c);
+  double Qold = o.Qold;
   double acc_flow = 0.0, acc_h = 0.0, Qo_in_acc = 0.0, qo_toriver_acc = 0.0;
   double wlsub = 0.0;  // dyn["WaterLevelLsub"] starts at 0 and is only written where SW > 0 (:873-878)
 #pragma unroll 1
@@ -388,13 +450,18 @@ __device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i
 #pragma unroll
     for (int j = 0; j < 8; j++) qv[j] = (j < nup) ? ldx<MODE>(qbuf + (int64_t)us + j) : 0.0f;
     if (riverMap) {
+      double av[8], bv[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        av[j] = (j < nup) ? ldx<MODE>(m.h_qa + (int64_t)v * m.n + us + j) : 0.0;
+        bv[j] = (j < nup) ? ldx<MODE>(m.h_qb + (int64_t)v * m.n + us + j) : 0.0;
+      }
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         if (j < nup) {
-          const double q1 = (double)qv[j];
-          s1 = s1 + (1 - c.cp[j]) * q1;
-          s2 = s2 + c.cp[j] * q1;
-          s3 = s3 + q1;
+          s1 = s1 + av[j];  // (1 - chanperc) * qo of the neighbour
+          s2 = s2 + bv[j];  // chanperc * qo
+          s3 = s3 + (double)qv[j];
         }
       }
     } else {
@@ -420,7 +487,12 @@ __device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i
     if (SW > 0) wlsub = qdiv(AlphaL * qbeta, SW);
     acc_h = acc_h + wlsub;
     Qold = qn;
-    qbuf[i] = (float)qn;
+    const float qn_f = (float)qn;
+    qbuf[i] = qn_f;
+    if (o.cpd >= 0.0) {  // the receiver is a river cell: hand it the two shares
+      m.h_qa[(int64_t)v * m.n + i] = (1 - o.cpd) * (double)qn_f;
+      m.h_qb[(int64_t)v * m.n + i] = o.cpd * (double)qn_f;
+    }
   }
   m.f[F_WaterLevelLsub][i] = (float)wlsub;
   m.f[F_LandRunoff][i] = (float)qdiv(acc_flow, m.dt);
@@ -447,15 +519,14 @@ __device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i
 // ---- task 3: one sub-step of the river kinematic wave for one river cell (river order) -------
 // kin_wave, wflow/wflow_funcs.py:155-207; caller glue wflow_sbm.py:3152-3201.
 template <int MODE>
-__device__ __forceinline__ void task_river(const DevModel &m, const int32_t rs, const int v WF_PARGS) {
+__device__ __forceinline__ void task_river(const DevModel &m, const int32_t rs, const int v, const RivOps &o WF_PARGS) {
   const int itR = m.itR;
-  const int nup = __ldg(m.r_nup + rs);
-  const uint32_t us = __ldg(m.r_up_start + rs);
+  const int nup = o.nup;
+  const uint32_t us = o.us;
   float *qbuf = (v == itR - 1) ? m.f[F_RiverRunoffsub] : m.qr_sub + (int64_t)v * m.nr;
-  // own-cell operands: all independent, issued together with the topology (one round trip)
-  const float DCLf = __ldg(m.f[F_DCL] + rs);
+  const float DCLf = o.DCL;
   const float inw = ldx<MODE>(m.h_inwater + rs);
-  const double A = __ldg(m.f[F_AlphaR] + rs), Bw = __ldg(m.f[F_Bw] + rs);
+  const double A = o.A, Bw = o.Bw;
   const double Qo = (v == 0) ? (double)m.f[F_RiverRunoffsub][rs] : (double)ldx<MODE>(m.qr_sub + (int64_t)(v - 1) * m.nr + rs);
   double racc0 = 0.0, rh0 = 0.0;
   if (v > 0) { racc0 = ldx<MODE>(m.h_racc + rs); rh0 = ldx<MODE>(m.h_rh + rs); }
@@ -517,22 +588,69 @@ __device__ __forceinline__ void prefetch_subsurface(const DevModel &m, const int
 //   WF_CLUSTER  one thread-block cluster per group, cluster barrier  (several basins, wide levels)
 //   WF_CTA      one thread block per group, __syncthreads            (many small basins / a narrow network)
 // Groups never exchange data, so clusters / blocks of different groups never wait for each other.
-enum { WF_GRID = 0, WF_CLUSTER = 1, WF_CTA = 2 };
+enum { WF_GRID = 0, WF_CLUSTER = 1, WF_CTA = 2, WF_CLUSTER_WIDE = 3 };
+// WF_CLUSTER_WIDE: the cluster sweep with WF_GROUP_THREADS_WIDE threads per block (fewer registers per
+// thread), chosen when it lets every item of a tick have its own thread
+#ifndef WF_GROUP_THREADS_WIDE
+#define WF_GROUP_THREADS_WIDE 640
+#endif
+__host__ __device__ constexpr bool wf_is_cluster(int mode) { return mode == WF_CLUSTER || mode == WF_CLUSTER_WIDE; }
+__host__ __device__ constexpr int wf_block_threads(int mode) {
+  return mode == WF_GRID ? 256 : (mode == WF_CLUSTER_WIDE ? WF_GROUP_THREADS_WIDE : WF_GROUP_THREADS);
+}
 
+// Split barrier of a sweep: arrive once the tick's outflows are stored, fetch the next item's own
+// operands while the others arrive, then wait.
+//   grid     per-launch counter in global memory (zeroed before the launch): one atomic per block
+//   cluster  hardware cluster barrier, arrive.release / wait.acquire
+//   block    __syncthreads at the wait (loads in flight cross it)
+struct WaveSync {
+  unsigned int *counter;
+  unsigned int nblocks, target;
+};
 template <int MODE>
-__device__ __forceinline__ void wave_barrier() {
-  if (MODE == WF_GRID) cg::this_grid().sync();
-  else if (MODE == WF_CLUSTER) cg::this_cluster().sync();
-  else __syncthreads();
+__device__ __forceinline__ void wave_arrive(WaveSync &ws) {
+  if (MODE == WF_GRID) {
+    __syncthreads();
+    ws.target += ws.nblocks;
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(ws.counter, 1u);
+    }
+  } else if (wf_is_cluster(MODE)) {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  }
+}
+template <int MODE>
+__device__ __forceinline__ void wave_wait(WaveSync &ws) {
+  if (MODE == WF_GRID) {
+    if (threadIdx.x == 0) {
+      unsigned int seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ws.counter) : "memory");
+      } while ((int)(seen - ws.target) < 0);
+    }
+    __syncthreads();
+  } else if (wf_is_cluster(MODE)) {
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  } else {
+    __syncthreads();
+  }
 }
 
 // One group's wavefront.  Tick t (level L = lev0 + t) runs, concurrently on different warps,
 //   [subsurface cells of level L][overland cells of level L-1][river cells of level L-2-v, sub-step v = 0..itR-1]
 // as one flat item space: consecutive threads take consecutive items, so a warp almost always runs
 // a single task type.  lo / ro: the group's level offsets (shared memory when they fit).
+struct WaveItem {
+  int type;      // -1 none, 0 subsurface, 1 overland, 2 river
+  uint32_t idx;  // storage position (river order for type 2)
+  int v;         // river sub-step
+};
+
 template <int ML, int MODE>
 __device__ __forceinline__ void sweep_group(const DevModel &m, const GroupDesc gd, const uint32_t *lo, const uint32_t *ro,
-                                            const int tid, const int nthreads) {
+                                            const int tid, const int nthreads, WaveSync &ws) {
   const int D = m.nlev, itR = m.itR;
   const int nl = D - gd.lev0;                        // levels of the group
   const bool rivers = gd.rlev0 < m.nrlev && (m.task_mask & 4);
@@ -540,17 +658,13 @@ __device__ __forceinline__ void sweep_group(const DevModel &m, const GroupDesc g
   const int nticks = nl + 1 + ((gd.rlev0 < m.nrlev) ? itR : 0);
   // river level (group-local) solved for sub-step 0 at tick 0; sub-step v lags v levels behind
   const int q0 = (gd.lev0 - 2) - m.rlev_shift - gd.rlev0;
-  for (int t = 0; t < nticks; t++) {
-#ifdef WF_PROFILE
-    unsigned long long *pbase = (m.prof && gd.lev_idx == 0) ? m.prof + 16 * (size_t)t : nullptr;
-    const unsigned long long c0 = gtimer();
-    if (pbase && tid == 0) pbase[14] = c0;
-#endif
-    uint32_t beg0 = 0, beg1 = 0;
-    int cnt0 = 0, cnt1 = 0;
-    if (t < nl && (m.task_mask & 1)) { beg0 = lo[t]; cnt0 = (int)(lo[t + 1] - beg0); }
-    if (t >= 1 && t - 1 < nl && (m.task_mask & 2)) { beg1 = lo[t - 1]; cnt1 = (int)(lo[t] - beg1); }
-    int total = cnt0 + cnt1;
+  // Item space of tick t, every task type starting on a warp boundary (a warp that straddled two
+  // types would run both solves one after the other and the whole tick would wait for it):
+  //   [subsurface cells of level t | pad][overland cells of level t-1 | pad][river cells, sub-step 0..itR-1]
+  auto tick_items = [&](int t) -> int {
+    int total = 0;
+    if (t < nl && (m.task_mask & 1)) total += ((int)(lo[t + 1] - lo[t]) + 31) & ~31;
+    if (t >= 1 && t - 1 < nl && (m.task_mask & 2)) total += ((int)(lo[t] - lo[t - 1]) + 31) & ~31;
     if (rivers) {
 #pragma unroll 1
       for (int v = 0; v < itR; v++) {
@@ -558,35 +672,89 @@ __device__ __forceinline__ void sweep_group(const DevModel &m, const GroupDesc g
         if (q >= 0 && q < nrl) total += (int)(ro[q + 1] - ro[q]);
       }
     }
-    for (int j = tid; j < total; j += nthreads) {
-      if (j < cnt0) {
-        task_subsurface<ML, MODE>(m, (int64_t)beg0 + j WF_PPASS(0));
-      } else if (j < cnt0 + cnt1) {
-        task_overland<MODE>(m, (int64_t)beg1 + (j - cnt0) WF_PPASS(1));
-      } else {
-        int jj = j - cnt0 - cnt1, vsel = 0;
-        uint32_t ridx = 0;
+    return total;
+  };
+  auto decode_item = [&](int j, int t) -> WaveItem {
+    WaveItem it;
+    it.type = -1; it.idx = 0; it.v = 0;
+    int cnt0 = 0, cnt1 = 0;
+    if (t < nl && (m.task_mask & 1)) cnt0 = (int)(lo[t + 1] - lo[t]);
+    if (t >= 1 && t - 1 < nl && (m.task_mask & 2)) cnt1 = (int)(lo[t] - lo[t - 1]);
+    const int c0p = (cnt0 + 31) & ~31, c1p = (cnt1 + 31) & ~31;
+    if (j < c0p) {
+      if (j < cnt0) { it.type = 0; it.idx = lo[t] + (uint32_t)j; }
+    } else if (j < c0p + c1p) {
+      if (j - c0p < cnt1) { it.type = 1; it.idx = lo[t - 1] + (uint32_t)(j - c0p); }
+    } else if (rivers) {
+      int jj = j - c0p - c1p;
 #pragma unroll 1
-        for (int v = 0; v < itR; v++) {
-          const int q = q0 + t - v;
-          if (q < 0 || q >= nrl) continue;
-          const uint32_t rb = ro[q];
-          const int rc = (int)(ro[q + 1] - rb);
-          if (jj < rc) { vsel = v; ridx = rb + (uint32_t)jj; break; }
-          jj -= rc;
-        }
-        task_river<MODE>(m, (int32_t)ridx, vsel WF_PPASS(2));
+      for (int v = 0; v < itR; v++) {
+        const int q = q0 + t - v;
+        if (q < 0 || q >= nrl) continue;
+        const uint32_t rb = ro[q];
+        const int rc = (int)(ro[q + 1] - rb);
+        if (jj < rc) { it.type = 2; it.v = v; it.idx = rb + (uint32_t)jj; break; }
+        jj -= rc;
+      }
+    }
+    return it;
+  };
+  // Operand fetch ahead of the barrier where registers allow it (grid sweep: 256 threads per block);
+  // the 512-thread cluster / block sweeps are capped at 128 registers and would spill the operands.
+  constexpr bool PRELOAD = (MODE == WF_GRID);
+  SubOps<ML> sub;
+  OvlOps ovl;
+  RivOps riv;
+  // first item of this thread in the coming tick, with its operands
+  auto prepare = [&](int t) -> WaveItem {
+    WaveItem it;
+    it.type = -1; it.idx = 0; it.v = 0;
+    if (t < nticks && tid < tick_items(t)) {
+      it = decode_item(tid, t);
+      if (PRELOAD) {
+        if (it.type == 0) load_sub<ML>(m, (int64_t)it.idx, sub);
+        else if (it.type == 1) load_ovl(m, (int64_t)it.idx, ovl);
+        else if (it.type == 2) load_riv(m, (int32_t)it.idx, riv);
+      }
+    }
+    return it;
+  };
+  WaveItem nxt = prepare(0);
+  for (int t = 0; t < nticks; t++) {
+#ifdef WF_PROFILE
+    unsigned long long *pbase = (m.prof && gd.lev_idx == 0) ? m.prof + 16 * (size_t)t : nullptr;
+    const unsigned long long c0 = gtimer();
+    if (pbase && tid == 0) pbase[14] = c0;
+#endif
+    const int total = tick_items(t);
+    bool first = true;
+    for (int j = tid; j < total; j += nthreads, first = false) {
+      WaveItem it;
+      if (first) it = nxt;                // decoded (grid sweep: operands fetched too) before the barrier
+      else it = decode_item(j, t);
+      if (it.type == 0) {
+        if (!first || !PRELOAD) load_sub<ML>(m, (int64_t)it.idx, sub);
+        task_subsurface<ML, MODE>(m, (int64_t)it.idx, sub WF_PPASS(0));
+      } else if (it.type == 1) {
+        if (!first || !PRELOAD) load_ovl(m, (int64_t)it.idx, ovl);
+        task_overland<MODE>(m, (int64_t)it.idx, ovl WF_PPASS(1));
+      } else if (it.type == 2) {
+        if (!first || !PRELOAD) load_riv(m, (int32_t)it.idx, riv);
+        task_river<MODE>(m, (int32_t)it.idx, it.v, riv WF_PPASS(2));
       }
     }
     if (t + 1 < nticks) {
-      if (t + 1 < nl) {  // warm L2 with next tick's operands while we wait
-        const uint32_t nb = lo[t + 1], ne = lo[t + 2];
-        if (nb + (uint32_t)tid < ne) prefetch_subsurface(m, (int64_t)nb + tid);
+      const int pd = PRELOAD ? 2 : 1;  // L2 warm-up distance: the tick after the one whose operands are fetched below
+      if (t + pd < nl) {
+        const uint32_t nb = lo[t + pd], ne = lo[t + pd + 1];
+        if (nb + (uint32_t)tid < ne && !(m.task_mask & 8)) prefetch_subsurface(m, (int64_t)nb + tid);
       }
 #ifdef WF_PROFILE
       if (pbase) prof_stamp(pbase + 12, c0, 0);
 #endif
-      wave_barrier<MODE>();
+      wave_arrive<MODE>(ws);
+      nxt = prepare(t + 1);
+      wave_wait<MODE>(ws);
 #ifdef WF_PROFILE
       if (pbase) prof_stamp(pbase + 13, c0, 0);
 #endif
@@ -595,25 +763,24 @@ __device__ __forceinline__ void sweep_group(const DevModel &m, const GroupDesc g
 }
 
 template <int ML, int MODE>
-__global__ void __launch_bounds__(MODE == WF_GRID ? 256 : WF_GROUP_THREADS, 1) k_lateral_wave(const DevModel m) {
+__global__ void __launch_bounds__(wf_block_threads(MODE), 1) k_lateral_wave(const DevModel m) {
   extern __shared__ uint32_t s_lev[];
-  if (MODE == WF_GRID) {
-    // one group (the whole network); offsets straight from global memory (L2-resident, prefetched by use)
-    const GroupDesc gd = m.groups[0];
-    sweep_group<ML, MODE>(m, gd, m.lev_off + gd.lev_idx, m.rlev_off + gd.rlev_idx, (int)(blockIdx.x * blockDim.x + threadIdx.x),
-                          (int)(gridDim.x * blockDim.x));
-    return;
-  }
   int crank = 0, csize = 1;
-  if (MODE == WF_CLUSTER) {
+  if (wf_is_cluster(MODE)) {
     cg::cluster_group cl = cg::this_cluster();
     crank = (int)cl.block_rank();
     csize = (int)cl.num_blocks();
   }
-  const int nclusters = (int)gridDim.x / csize;
-  const int tid = crank * (int)blockDim.x + (int)threadIdx.x;
-  const int nthreads = csize * (int)blockDim.x;
-  for (int g = (int)blockIdx.x / csize; g < m.ngroups; g += nclusters) {
+  // grid: every block sweeps the one group; otherwise cluster (or block) c takes groups c, c + nclusters, ...
+  const int nclusters = (MODE == WF_GRID) ? 1 : (int)gridDim.x / csize;
+  const int cid = (MODE == WF_GRID) ? 0 : (int)blockIdx.x / csize;
+  const int tid = (MODE == WF_GRID) ? (int)(blockIdx.x * blockDim.x + threadIdx.x) : crank * (int)blockDim.x + (int)threadIdx.x;
+  const int nthreads = (MODE == WF_GRID) ? (int)(gridDim.x * blockDim.x) : csize * (int)blockDim.x;
+  WaveSync ws;
+  ws.counter = m.grid_counter;
+  ws.nblocks = gridDim.x;
+  ws.target = 0;
+  for (int g = cid; g < m.ngroups; g += nclusters) {
     const GroupDesc gd = m.groups[g];
     const int nlo = m.nlev - gd.lev0 + 1;
     const int nro = (gd.rlev0 < m.nrlev) ? m.nrlev - gd.rlev0 + 1 : 0;
@@ -626,8 +793,9 @@ __global__ void __launch_bounds__(MODE == WF_GRID ? 256 : WF_GROUP_THREADS, 1) k
       lo = s_lev;
       ro = s_lev + nlo;
     }
-    sweep_group<ML, MODE>(m, gd, lo, ro, tid, nthreads);
+    sweep_group<ML, MODE>(m, gd, lo, ro, tid, nthreads, ws);
     // the next group of this cluster touches other cells only: no barrier needed in between
+    if (MODE == WF_GRID) break;
   }
 }
 

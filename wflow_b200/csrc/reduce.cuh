@@ -61,4 +61,15 @@ __global__ void k_sample(const float *__restrict__ field, const int32_t *__restr
   if (i < n) out[i] = (pos[i] >= 0) ? field[pos[i]] : mv;
 }
 
+// gauge sets: pos = storage position (-1 outside the network); rpos (river-only fields) = river-order
+// position or -1 for a network cell that is not a river cell (the reference holds 0 there)
+__global__ void k_sample_gauges(const float *__restrict__ field, const int32_t *__restrict__ pos,
+                                const int32_t *__restrict__ rpos, float *__restrict__ out, int64_t n, float mv) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (pos[i] < 0) out[i] = mv;
+  else if (rpos) out[i] = (rpos[i] >= 0) ? field[rpos[i]] : 0.0f;
+  else out[i] = field[pos[i]];
+}
+
 }  // namespace wf
