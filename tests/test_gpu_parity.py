@@ -225,3 +225,39 @@ def test_newton_solvers_match_reference_golden():
     scale = np.maximum(np.abs(ref[ok]), [1.0, 1e-3, 1e-6])
     rel = np.abs(out[ok] - ref[ok]) / scale
     assert rel.max() < 1e-9, rel.max(axis=0)
+
+
+def test_every_lateral_sweep_mode_gives_the_same_states(monkeypatch):
+    """The grid, cluster (regular / wide blocks) and single-block sweeps run the same per-cell arithmetic in
+    the same summation order: their states must agree bit for bit, and with the oracle within tolerance."""
+    from wflow_b200 import synth
+    kw = dict(kind="tiles", tile=16, layer_thickness=(100, 300, 800), dt=3600, itL=2, itR=3)
+    results = {}
+    for mode, env in (("grid", {"WF_LATERAL_MODE": "grid"}), ("cta", {"WF_LATERAL_MODE": "cta"}),
+                      ("cluster", {"WF_LATERAL_MODE": "cluster", "WF_CLUSTER_SIZE": "2", "WF_CLUSTER_WIDE": "0"}),
+                      ("cluster-wide", {"WF_LATERAL_MODE": "cluster", "WF_CLUSTER_SIZE": "4", "WF_CLUSTER_WIDE": "1"})):
+        for k in ("WF_LATERAL_MODE", "WF_CLUSTER_SIZE", "WF_CLUSTER_WIDE", "WF_GROUPS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        orc, mod, ldd, river = common.make_pair(48, 64, oracle=(mode == "grid"), **kw)
+        assert mod.lateral_plan["mode"] == mode
+        forc = synth.Forcing(48, 64, seed=5, timestepsecs=3600, rain_mean=RAIN_MEAN)
+        states = common.state_names(4)
+        for t in range(4):
+            P, PET, T = forc.step(t)
+            for m in (orc, mod):
+                if m is not None:
+                    m.set("P", P); m.set("PET", PET); m.set("TEMP", T)
+            mod.step()
+            if orc is not None:
+                orc.step()
+        results[mode] = {k: mod.get(k) for k in states}
+        if orc is not None:
+            mask = common.network_mask(orc)
+            for k in states:
+                assert common.compare(results[mode][k], orc[k], mask, 1e-4, 10 * ATOL.get(k, ATOL["default"])) <= 1.0, k
+        mod.close()
+    for mode in ("cta", "cluster", "cluster-wide"):
+        for k, v in results["grid"].items():
+            np.testing.assert_array_equal(results[mode][k], v, err_msg="%s differs between grid and %s" % (k, mode))

@@ -50,3 +50,32 @@ def test_empty_and_degenerate_inputs():
     # a cycle is unreachable from any pit: left out, exactly as the reference does
     nodes, up, off = core.build_schedule(np.array([[6, 4, 5]], np.uint8))
     assert list(nodes) == [2]
+
+
+def test_partition_keeps_basins_whole_and_upstream_runs_in_reference_order():
+    """Storage layout (wf_schedule_partition): every group holds whole basins, level-major; the upstream
+    neighbours of every cell stay one contiguous run in set_dd's neighbour order (reference goldens of
+    nodes_up: wflow/wflow_funcs.py:43-95)."""
+    from wflow_b200 import core, synth
+    for ldd in (synth.ldd_basin_tiles(64, 96, tile=32, seed=3), synth.ldd_random_forest(40, 56, seed=11)):
+        sched = core.Schedule(ldd)
+        nodes, up, off = core.build_schedule(ldd)
+        refup = {int(nodes[k]): [int(x) for x in up[k] if x >= 0] for k in range(len(nodes))}
+        # basin (pit) of every cell, from the reference-form schedule
+        pit_of = {}
+        for k in range(len(nodes) - 1, -1, -1):
+            c = int(nodes[k])
+            pit_of.setdefault(c, c)
+            for u in refup[c]:
+                pit_of[u] = pit_of[c]
+        for G in (1, 2, 3, 5, 1000):
+            order, goff, ups, nup = sched.partition(G)
+            assert sorted(order.tolist()) == sorted(nodes.tolist())
+            assert goff[0] == 0 and goff[-1] == len(order) and np.all(np.diff(goff) >= 0)
+            group_of = np.repeat(np.arange(len(goff) - 1), np.diff(goff))
+            pits = {}
+            for k, c in enumerate(order.tolist()):
+                pits.setdefault(pit_of[c], set()).add(int(group_of[k]))
+                assert [int(order[ups[k] + j]) for j in range(nup[k])] == refup[c]
+                assert all(ups[k] + j < k for j in range(nup[k]))       # upstream cells come earlier (level-major)
+            assert all(len(g) == 1 for g in pits.values())                # a basin never straddles groups

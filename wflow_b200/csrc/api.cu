@@ -614,6 +614,17 @@ int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint
   CUDA_OK(cudaMalloc(&dm.h_qa, sizeof(double) * (size_t)dm.itL * std::max<int64_t>(n, 1)));
   CUDA_OK(cudaMalloc(&dm.h_qb, sizeof(double) * (size_t)dm.itL * std::max<int64_t>(n, 1)));
   CUDA_OK(cudaMalloc(&dm.grid_counter, 256));
+  {  // carried powers start invalid (NaN): the first solve computes the full power
+    const size_t nb = sizeof(double) * (size_t)std::max<int64_t>(n, 1), rb = sizeof(double) * (size_t)std::max<int32_t>(m->nr, 1);
+    CUDA_OK(cudaMalloc(&dm.h_lq, nb));
+    CUDA_OK(cudaMalloc(&dm.h_lqb, nb));
+    CUDA_OK(cudaMalloc(&dm.h_rq, rb));
+    CUDA_OK(cudaMalloc(&dm.h_rqb, rb));
+    CUDA_OK(cudaMemsetAsync(dm.h_lq, 0xff, nb, m->stream));
+    CUDA_OK(cudaMemsetAsync(dm.h_lqb, 0xff, nb, m->stream));
+    CUDA_OK(cudaMemsetAsync(dm.h_rq, 0xff, rb, m->stream));
+    CUDA_OK(cudaMemsetAsync(dm.h_rqb, 0xff, rb, m->stream));
+  }
   CUDA_OK(cudaMalloc(&dm.h_ulo, sizeof(float) * (size_t)m->ML * std::max<int64_t>(n, 1)));
   CUDA_OK(cudaMalloc(&dm.h_inwaterMM, sizeof(float) * std::max<int32_t>(m->nr, 1)));
   CUDA_OK(cudaMalloc(&dm.h_inwO, sizeof(double) * std::max<int64_t>(n, 1)));
@@ -691,6 +702,7 @@ void wf_destroy(wf_model *m) {
   for (float *p : m->snapshot) cudaFree(p);
   for (auto &a : m->areas) { cudaFree(a.d_perm); cudaFree(a.d_seg); }
   cudaFree(m->dm.d_efT); cudaFree(m->dm.d_efST); cudaFree(m->dm.d_cpd);
+  cudaFree(m->dm.h_lq); cudaFree(m->dm.h_lqb); cudaFree(m->dm.h_rq); cudaFree(m->dm.h_rqb);
   cudaFree(m->dm.h_ssf_riv); cudaFree(m->dm.h_qa); cudaFree(m->dm.h_qb); cudaFree(m->dm.grid_counter);
   cudaFree(m->dm.h_r); cudaFree(m->dm.h_surplus); cudaFree(m->dm.h_ulo); cudaFree(m->dm.h_ssf);
   cudaFree(m->dm.h_inwO); cudaFree(m->dm.h_ssf_tr); cudaFree(m->dm.h_inwater); cudaFree(m->dm.h_racc); cudaFree(m->dm.h_rh);

@@ -61,6 +61,19 @@ __device__ __forceinline__ T ldx(const T *p) {
   return __ldcg(p);
 }
 
+// Qold^beta for the constant term of the kinematic wave.  Qold is the float32-rounded outflow of the solve
+// one (sub-)step earlier, which left its float64 solution q64 and q64^beta behind: when the state still
+// is that value, Qold^beta = q64^beta * (1 + d)^beta with d = (Qold - q64)/q64 ~ 1e-8 (two series terms
+// are exact to rounding); otherwise (cold start, a state set from outside) the full power.
+__device__ __forceinline__ double carried_pow(double Qold, double q64, double qb64, double beta) {
+  if (Qold == 0.0 && beta > 0.0) return 0.0;
+  if (q64 > 0.0 && (float)q64 == (float)Qold) {
+    const double d = (Qold - q64) * qrcp(q64);
+    return qb64 * (1.0 + d * (beta + d * (0.5 * beta * (beta - 1.0))));
+  }
+  return pow_el(Qold, beta);
+}
+
 // kinematic_wave, wflow/wflow_funcs.py:119-152.
 // The reference's Newton iteration converges to the root of  dT/dX*Q + alpha*Q^beta = C  to
 // rounding (it only stops on |f| <= 1e-12 or its 3000-iteration cap), so the result is a property
@@ -72,12 +85,13 @@ __device__ __forceinline__ T ldx(const T *p) {
 //      the next iterate is converged to rounding (quadratic convergence), so 2 steps are typical.
 // Agreement with the reference: a few ulp (tests/test_gpu_parity.py asserts 1e-9 on its golden set).
 // Also returns Q^beta at the solution (the water level needs it).
-__device__ __noinline__ double kinematic_wave(double Qin, double Qold, double q, double alpha, double beta,
+// QoldBeta = Qold^beta (the caller usually carries it over from the solve that produced Qold, carried_pow).
+__device__ __noinline__ double kinematic_wave(double Qin, double Qold, double QoldBeta, double q, double alpha, double beta,
                                               double deltaT, double deltaX, double &Qbeta) {
   Qbeta = 0.0;
   if ((Qin + Qold + q) == 0.0) return 0.0;
   const double deltaTX = qdiv(deltaT, deltaX);
-  const double C = deltaTX * Qin + alpha * pow_el(Qold, beta) + deltaT * q;
+  const double C = deltaTX * Qin + alpha * QoldBeta + deltaT * q;
   // float32 phase
   const float a32 = (float)alpha, b32 = (float)beta, dtx32 = (float)deltaTX;
   const float qin32 = (float)Qin, qold32 = (float)Qold, lat32 = (float)(deltaT * q);
@@ -86,6 +100,13 @@ __device__ __noinline__ double kinematic_wave(double Qin, double Qold, double q,
   const float ab_pQ = a32 * b32 * pow_fast((qold32 + qin32) * 0.5f, b32 - 1.0f);
   float Qf = __fdividef(dtx32 * qin32 + qold32 * ab_pQ + lat32, dtx32 + ab_pQ);
   if (isnan(Qf)) Qf = 0.0f;
+  {
+    // The root lies in (ub/4, ub], ub = min(C/dtx, (C/alpha)^(1/beta)) (each term alone reaches C at its
+    // bound).  The reference's linearised guess collapses towards 0 when Qold + Qin is tiny, and Newton
+    // then creeps up the steep side of Q^beta for ~9 iterations; clamped into the bracket it needs ~3.
+    const float ub = fminf(__fdividef(C32, dtx32), pow_fast(__fdividef(C32, a32), __fdividef(1.0f, b32)));
+    if (ub > 0.0f && ub < 3.0e38f) Qf = fminf(fmaxf(Qf, 0.25f * ub), ub);
+  }
   Qf = fmaxf(Qf, 1e-30f);
 #pragma unroll 1
   for (int it = 0; it < 12; it++) {
@@ -248,7 +269,7 @@ struct OvlOps {
   int32_t rs;
   int nup;
   float SW, AlphaL, DL, Qold;
-  double cpd;
+  double cpd, q64, qb64;
 };
 struct RivOps {
   uint32_t us;
@@ -285,6 +306,8 @@ __device__ __forceinline__ void load_ovl(const DevModel &m, const int64_t i, Ovl
   o.SW = LD(SW); o.AlphaL = LD(AlphaL); o.DL = LD(DL);
   o.Qold = m.f[F_LandRunoffsub][i];
   o.cpd = __ldg(m.d_cpd + i);
+  o.q64 = m.h_lq[i];
+  o.qb64 = m.h_lqb[i];
 }
 __device__ __forceinline__ void load_riv(const DevModel &m, const int32_t rs, RivOps &o) {
   o.nup = __ldg(m.r_nup + rs);
@@ -440,6 +463,7 @@ __device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i
   const double dts = qdiv(m.dt, (double)itL);
   const double q = qdiv(ldx<MODE>(m.h_inwO + i), DLd);
   double Qold = o.Qold;
+  double QoldBeta = carried_pow(Qold, o.q64, o.qb64, Beta);
   double acc_flow = 0.0, acc_h = 0.0, Qo_in_acc = 0.0, qo_toriver_acc = 0.0;
   double wlsub = 0.0;  // dyn["WaterLevelLsub"] starts at 0 and is only written where SW > 0 (:873-878)
 #pragma unroll 1
@@ -479,16 +503,21 @@ __device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i
     double qbeta;
     WF_STAMP(0, q + Qold + AlphaL + SW);
     WF_STAMP(1, qo_in);
-    const double qn = kinematic_wave(qo_in, Qold, q, AlphaL, Beta, dts, DLd, qbeta);
+    const double qn = kinematic_wave(qo_in, Qold, QoldBeta, q, AlphaL, Beta, dts, DLd, qbeta);
     WF_STAMP(2, qn);
     acc_flow = acc_flow + qn * dts;
     Qo_in_acc = Qo_in_acc + qo_in * dts;
     qo_toriver_acc = qo_toriver_acc + qo_toriver_vol;
     if (SW > 0) wlsub = qdiv(AlphaL * qbeta, SW);
     acc_h = acc_h + wlsub;
-    Qold = qn;
     const float qn_f = (float)qn;
     qbuf[i] = qn_f;
+    if (v == itL - 1) {  // for the next timestep's constant term
+      m.h_lq[i] = qn;
+      m.h_lqb[i] = qbeta;
+    }
+    Qold = qn;          // (the reference keeps float64 between sub-steps, wflow_sbm.py:879)
+    QoldBeta = qbeta;
     if (o.cpd >= 0.0) {  // the receiver is a river cell: hand it the two shares
       m.h_qa[(int64_t)v * m.n + i] = (1 - o.cpd) * (double)qn_f;
       m.h_qb[(int64_t)v * m.n + i] = o.cpd * (double)qn_f;
@@ -545,7 +574,10 @@ __device__ __forceinline__ void task_river(const DevModel &m, const int32_t rs, 
   double qbeta;
   WF_STAMP(0, qr + A + Bw + Qo + racc0);
   WF_STAMP(1, Qin);
-  const double qn = kinematic_wave(Qin, Qo, qr, A, m.beta, dtr, (double)DCLf, qbeta);
+  const double QoBeta = carried_pow(Qo, ldx<MODE>(m.h_rq + rs), ldx<MODE>(m.h_rqb + rs), m.beta);
+  const double qn = kinematic_wave(Qin, Qo, QoBeta, qr, A, m.beta, dtr, (double)DCLf, qbeta);
+  m.h_rq[rs] = qn;
+  m.h_rqb[rs] = qbeta;
   WF_STAMP(2, qn);
   const double wl = qdiv(A * qbeta, Bw);
   const double racc = racc0 + qn * dtr, rh = rh0 + wl;
@@ -804,7 +836,8 @@ __global__ void k_kinwave_batch(int64_t n, const double *a, double *out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double qb;
-  out[i] = kinematic_wave(a[i], a[n + i], a[2 * n + i], a[3 * n + i], a[4 * n + i], a[5 * n + i], a[6 * n + i], qb);
+  out[i] = kinematic_wave(a[i], a[n + i], pow_el(a[n + i], a[4 * n + i]), a[2 * n + i], a[3 * n + i], a[4 * n + i], a[5 * n + i],
+                          a[6 * n + i], qb);
 }
 __global__ void k_kinwave_ssf_batch(int64_t n, const double *a, double *out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
