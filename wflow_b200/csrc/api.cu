@@ -249,6 +249,10 @@ int launch_step(wf_model *m) {
     m->launches += 2;
     m->derived_dirty = false;
   }
+  m->dm.any_diag = 0;
+  for (int id = 0; id < F_COUNT; id++)
+    if ((g_fields[id].kind & 0xff) == K_DIAG && m->dm.f[id]) m->dm.any_diag = 1;
+  if (m->dm.h_wb) m->dm.any_diag = 1;
   {  // sources of the staged inputs (VLayout); pointers may have been re-bound since the last step
     using VL = VLayout<ML>;
     static_assert(VL::nslots(true) <= WF_MAX_VSLOTS, "WF_MAX_VSLOTS too small");

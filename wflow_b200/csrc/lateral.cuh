@@ -420,6 +420,7 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
   double sumU = 0.0;
 #pragma unroll
   for (int k = 0; k < ML; k++) sumU += U[k];
+  if (m.any_diag) {
   OUTF(SatWaterDepth, Sat); OUTF(UStoreDepth, sumU);
   OUTF(ssf_toriver, riverMap ? qdiv(ssf_tr / (1000 * 1000 * 1000), m.dt) : 0.0);
   OUTF(ExfiltWater, ExfiltWater); OUTF(ExfiltFromUstore, ExfiltFromUstore); OUTF(ExfiltFromSat, ExfiltSatWater);
@@ -447,6 +448,7 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
     const double wb = m.h_wb[i] - (Sat + sumU) + qdiv(ssf_in - ssf_n, DW * DLd * 1000 * 1000) - ExfiltWater;
     m.f[F_SoilWatbal][i] = (float)wb;
     if (m.f[F_watbal] && m.f[F_SurfaceWatbal]) m.f[F_watbal][i] = (float)wb + m.f[F_SurfaceWatbal][i];
+  }
   }
   WF_STAMP(3, InwaterO);
 }
@@ -527,8 +529,10 @@ __device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i
   m.f[F_LandRunoff][i] = (float)qdiv(acc_flow, m.dt);
   m.f[F_WaterLevelL][i] = (float)qdiv(acc_h, (double)itL);
   const float qo_toriver_f = (float)qdiv(qo_toriver_acc, m.dt);
-  OUTF(qo_toriver, qo_toriver_f);
-  OUTF(InflowKinWaveCellLand, qdiv(Qo_in_acc, m.dt));
+  if (m.any_diag) {
+    OUTF(qo_toriver, qo_toriver_f);
+    OUTF(InflowKinWaveCellLand, qdiv(Qo_in_acc, m.dt));
+  }
 
   if (riverMap) {  // lateral inflow of the channel, wflow_sbm.py:3052-3065, 3144
     const float dtf = (float)m.dt;
