@@ -68,7 +68,7 @@ struct wf_model {
   int lat_mode = 0, cluster_size = 1, lat_blocks = 0;  // how the lateral sweep is launched (plan_lateral)
   size_t lat_smem = 0;
   GroupDesc *d_groups = nullptr;
-  uint32_t *d_lev_off = nullptr, *d_rlev_off = nullptr;
+  uint32_t *d_lev_off = nullptr, *d_rlev_off = nullptr, *d_tick_total = nullptr;
   std::vector<int32_t> river_slot;   // network order -> river order (or -1)
   std::vector<int64_t> river_flat;   // river order -> flat grid index (first nrnet: rnet.order)
   int64_t n = 0;
@@ -588,15 +588,38 @@ int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint
   {
     const int G = m->lay.ngroups;
     std::vector<GroupDesc> gd((size_t)G);
+    std::vector<uint32_t> tick_total;  // items of every tick of every group (lateral.cuh: tick item space)
     int64_t most = 0;
+    const int Dn = (int)m->net.nlevels(), Dr = (int)m->rnet.nlevels(), shift = Dn - Dr;
     for (int g = 0; g < G; g++) {
       gd[(size_t)g].lev_idx = (uint32_t)m->lay.lev_idx[(size_t)g];
       gd[(size_t)g].rlev_idx = (uint32_t)m->rlay.lev_idx[(size_t)g];
       gd[(size_t)g].lev0 = m->lay.lev0[(size_t)g];
       gd[(size_t)g].rlev0 = m->rlay.lev0[(size_t)g];
+      const uint32_t *lo = m->lay.lev_off.data() + m->lay.lev_idx[(size_t)g];
+      const uint32_t *ro = m->rlay.lev_off.data() + m->rlay.lev_idx[(size_t)g];
+      const int l0 = m->lay.lev0[(size_t)g], r0 = m->rlay.lev0[(size_t)g];
+      const int nl = Dn - l0, nrl = Dr - r0;
+      const bool rivers = r0 < Dr && (dm.task_mask & 4);
+      const int nticks = nl + 1 + ((r0 < Dr) ? cfg->it_kin_r : 0);
+      gd[(size_t)g].tick_idx = (uint32_t)tick_total.size();
+      gd[(size_t)g].nticks = nticks;
+      for (int t = 0; t < nticks; t++) {
+        uint32_t items = 0;
+        if (t < nl && (dm.task_mask & 1)) items += ((lo[t + 1] - lo[t]) + 31u) & ~31u;
+        if (t >= 1 && t - 1 < nl && (dm.task_mask & 2)) items += ((lo[t] - lo[t - 1]) + 31u) & ~31u;
+        if (rivers)
+          for (int v = 0; v < cfg->it_kin_r; v++) {
+            const int q = (l0 - 2) - shift - r0 + t - v;
+            if (q >= 0 && q < nrl) items += ro[q + 1] - ro[q];
+          }
+        tick_total.push_back(items);
+      }
       most = std::max(most, (m->lay.lev_idx[(size_t)g + 1] - m->lay.lev_idx[(size_t)g]) +
-                                (m->rlay.lev_idx[(size_t)g + 1] - m->rlay.lev_idx[(size_t)g]));
+                                (m->rlay.lev_idx[(size_t)g + 1] - m->rlay.lev_idx[(size_t)g]) + (int64_t)nticks);
     }
+    if ((rc = upload(tick_total.data(), sizeof(uint32_t) * tick_total.size(), (void **)&m->d_tick_total))) return rc;
+    dm.tick_total = m->d_tick_total;
     if ((rc = upload(gd.data(), sizeof(GroupDesc) * (size_t)G, (void **)&m->d_groups))) return rc;
     dm.groups = m->d_groups;
     dm.ngroups = G;
@@ -710,7 +733,7 @@ void wf_destroy(wf_model *m) {
   cudaFree(m->dm.h_ssf_riv); cudaFree(m->dm.h_qa); cudaFree(m->dm.h_qb); cudaFree(m->dm.grid_counter);
   cudaFree(m->dm.h_r); cudaFree(m->dm.h_surplus); cudaFree(m->dm.h_ulo); cudaFree(m->dm.h_ssf);
   cudaFree(m->dm.h_inwO); cudaFree(m->dm.h_ssf_tr); cudaFree(m->dm.h_inwater); cudaFree(m->dm.h_racc); cudaFree(m->dm.h_rh);
-  cudaFree(m->d_rlev_off); cudaFree(m->d_groups); cudaFree((void *)m->dm.r_up_start); cudaFree((void *)m->dm.r_nup); cudaFree(m->dm.h_inwaterMM); cudaFree(m->dm.h_wb);
+  cudaFree(m->d_rlev_off); cudaFree(m->d_tick_total); cudaFree(m->d_groups); cudaFree((void *)m->dm.r_up_start); cudaFree((void *)m->dm.r_nup); cudaFree(m->dm.h_inwaterMM); cudaFree(m->dm.h_wb);
   cudaFree(m->dm.qo_sub); cudaFree(m->dm.qr_sub);
   cudaFree((void *)m->dm.up_start); cudaFree((void *)m->dm.topo); cudaFree((void *)m->dm.river_slot);
   cudaFree(m->d_order); cudaFree(m->d_rorder); cudaFree(m->d_lev_off); cudaFree(m->d_stage);

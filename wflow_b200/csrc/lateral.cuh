@@ -686,30 +686,18 @@ struct WaveItem {
 
 template <int ML, int MODE>
 __device__ __forceinline__ void sweep_group(const DevModel &m, const GroupDesc gd, const uint32_t *lo, const uint32_t *ro,
-                                            const int tid, const int nthreads, WaveSync &ws) {
+                                            const uint32_t *tt, const int tid, const int nthreads, WaveSync &ws) {
   const int D = m.nlev, itR = m.itR;
   const int nl = D - gd.lev0;                        // levels of the group
   const bool rivers = gd.rlev0 < m.nrlev && (m.task_mask & 4);
   const int nrl = rivers ? m.nrlev - gd.rlev0 : 0;   // river levels of the group
-  const int nticks = nl + 1 + ((gd.rlev0 < m.nrlev) ? itR : 0);
+  const int nticks = gd.nticks;  // nl + 1 (+ itR with rivers)
   // river level (group-local) solved for sub-step 0 at tick 0; sub-step v lags v levels behind
   const int q0 = (gd.lev0 - 2) - m.rlev_shift - gd.rlev0;
   // Item space of tick t, every task type starting on a warp boundary (a warp that straddled two
   // types would run both solves one after the other and the whole tick would wait for it):
   //   [subsurface cells of level t | pad][overland cells of level t-1 | pad][river cells, sub-step 0..itR-1]
-  auto tick_items = [&](int t) -> int {
-    int total = 0;
-    if (t < nl && (m.task_mask & 1)) total += ((int)(lo[t + 1] - lo[t]) + 31) & ~31;
-    if (t >= 1 && t - 1 < nl && (m.task_mask & 2)) total += ((int)(lo[t] - lo[t - 1]) + 31) & ~31;
-    if (rivers) {
-#pragma unroll 1
-      for (int v = 0; v < itR; v++) {
-        const int q = q0 + t - v;
-        if (q >= 0 && q < nrl) total += (int)(ro[q + 1] - ro[q]);
-      }
-    }
-    return total;
-  };
+  auto tick_items = [&](int t) -> int { return (int)tt[t]; };  // precomputed on the host (api.cu)
   auto decode_item = [&](int j, int t) -> WaveItem {
     WaveItem it;
     it.type = -1; it.idx = 0; it.v = 0;
@@ -820,16 +808,18 @@ __global__ void __launch_bounds__(wf_block_threads(MODE), 1) k_lateral_wave(cons
     const GroupDesc gd = m.groups[g];
     const int nlo = m.nlev - gd.lev0 + 1;
     const int nro = (gd.rlev0 < m.nrlev) ? m.nrlev - gd.rlev0 + 1 : 0;
-    const uint32_t *lo = m.lev_off + gd.lev_idx, *ro = m.rlev_off + gd.rlev_idx;
-    if (nlo + nro <= m.lev_cache) {  // level offsets of the group into shared memory (every block its own copy)
+    const uint32_t *lo = m.lev_off + gd.lev_idx, *ro = m.rlev_off + gd.rlev_idx, *tt = m.tick_total + gd.tick_idx;
+    if (nlo + nro + gd.nticks <= m.lev_cache) {  // level offsets and tick sizes of the group into shared memory
       __syncthreads();
       for (int k = threadIdx.x; k < nlo; k += blockDim.x) s_lev[k] = lo[k];
       for (int k = threadIdx.x; k < nro; k += blockDim.x) s_lev[nlo + k] = ro[k];
+      for (int k = threadIdx.x; k < gd.nticks; k += blockDim.x) s_lev[nlo + nro + k] = tt[k];
       __syncthreads();
       lo = s_lev;
       ro = s_lev + nlo;
+      tt = s_lev + nlo + nro;
     }
-    sweep_group<ML, MODE>(m, gd, lo, ro, tid, nthreads, ws);
+    sweep_group<ML, MODE>(m, gd, lo, ro, tt, tid, nthreads, ws);
     // the next group of this cluster touches other cells only: no barrier needed in between
     if (MODE == WF_GRID) break;
   }
