@@ -176,6 +176,16 @@ int wf_sample(wf_model *m, const char *field, const int64_t *flat_index, int64_t
 int wf_gauges_create(wf_model *m, const int64_t *flat_index, int64_t n);
 int wf_gauges_sample(wf_model *m, int gauges, const char *field, float *out /* [n] */, float mv, int async);
 
+/* --- kinematic-wave sub-steps --------------------------------------------------------------------
+ * estimate_iterations_kin_wave(Q, Beta, alpha, timestepsecs, dx, mv) (wflow/wflow_funcs.py:103-116):
+ * it_kin = ceil(1.25 * 95th percentile of the Courant number over the cells with Q > 0), 1 when no cell
+ * flows.  which = 0: overland (LandRunoffsub, AlphaL, DL; wflow_sbm.py:2911-2921), 1: river
+ * (RiverRunoffsub, AlphaR, DCL; :3159-3169).  A device-wide radix select; synchronises the stream. */
+int wf_estimate_iterations(wf_model *m, int which, int32_t *it_kin);
+/* Sub-step counts of the following steps ([model] kinwaveIters = 1: per step from the estimate above or
+ * ceil(timestepsecs / kinwave*Tstep), wflow_sbm.py:2911-2923, 3159-3171). */
+int wf_set_substeps(wf_model *m, int it_kin_l, int it_kin_r);
+
 /* --- batched solvers ----------------------------------------------------------------------
  * The two Newton solvers of the path, exposed on their own so that they can be checked against
  * the reference's scalar functions: kinematic_wave(Qin, Qold, q, alpha, beta, deltaT, deltaX)

@@ -168,3 +168,30 @@ class Oracle:
                             self.net.ldd.ctypes.data_as(C.c_void_p), self.active.ctypes.data_as(C.c_void_p), tab)
         if rc != 0:
             raise RuntimeError("wfo_step failed with code %d" % rc)
+
+    # -- estimate_iterations_kin_wave, wflow/wflow_funcs.py:103-116 --------------------------------
+    # PCRaster half of the reference (REAL4 map algebra + np.nanpercentile on the float32 raster):
+    # restated with float32 numpy, parity unpinned (PCRaster cannot be installed here).
+    def estimate_iterations(self, which):
+        """which = "land": LandRunoffsub / AlphaL / DL (wflow_sbm.py:2911-2921);
+        "river": RiverRunoffsub / AlphaR / DCL (:3159-3169)."""
+        f32 = np.float32
+        qn, an, dn = {"land": ("LandRunoffsub", "AlphaL", "DL"), "river": ("RiverRunoffsub", "AlphaR", "DCL")}[which]
+        valid = np.zeros(self.shape, bool)
+        valid.flat[self.net.flat_nodes] = True                # cells of the model domain; MV elsewhere
+        Q = np.where(valid, self.fields[qn], f32(0)).astype(f32)
+        if not (Q.max() > 0):
+            return 1                                          # all-NaN percentile raises: it_kin = 1 (:113-114)
+        beta = f32(0.6)                                        # self.Beta, REAL4 (wflow_sbm.py:1643)
+        flow = Q > 0
+        with np.errstate(all="ignore"):
+            cel = f32(1.0) / ((self.fields[an].astype(f32) * beta) * np.power(Q, beta - f32(1.0), dtype=f32))
+            courant = (f32(self.p.timestepsecs) / self.fields[dn].astype(f32)) * cel
+        c = np.where(flow, courant, f32(np.nan)).astype(f32)
+        try:
+            return int(np.ceil(f32(1.25) * np.nanpercentile(c, 95)))
+        except Exception:
+            return 1
+
+    def set_substeps(self, it_kinL, it_kinR):
+        self.p.it_kinL, self.p.it_kinR = int(it_kinL), int(it_kinR)

@@ -261,3 +261,38 @@ def test_every_lateral_sweep_mode_gives_the_same_states(monkeypatch):
     for mode in ("cta", "cluster", "cluster-wide"):
         for k, v in results["grid"].items():
             np.testing.assert_array_equal(results[mode][k], v, err_msg="%s differs between grid and %s" % (k, mode))
+
+
+def test_estimate_iterations_and_changing_substeps():
+    """estimate_iterations_kin_wave (wflow/wflow_funcs.py:103-116) on the device (radix select of the 95th
+    percentile) against the float32 numpy restatement, and steps whose sub-step counts change in between
+    (kinwaveIters = 1 without fixed sub-steps, wflow_sbm.py:2911-2923, 3159-3171)."""
+    from wflow_b200 import synth
+    kw = dict(kind="tiles", tile=16, layer_thickness=(100, 300, 800), dt=3600)
+    orc, mod, ldd, river = common.make_pair(48, 64, **kw)
+    mask = common.network_mask(orc)
+    forc = synth.Forcing(48, 64, seed=5, timestepsecs=3600, rain_mean=RAIN_MEAN)
+    states = common.state_names(4)
+    seen = set()
+    for t in range(5):
+        P, PET, T = forc.step(t)
+        for m in (orc, mod):
+            m.set("P", P); m.set("PET", PET); m.set("TEMP", T)
+        for k in states:
+            mod.set(k, orc[k])
+        itl, itr = orc.estimate_iterations("land"), orc.estimate_iterations("river")
+        assert mod.estimate_iterations("land") == itl
+        assert mod.estimate_iterations("river") == itr
+        itl, itr = min(itl, 5) + (t % 2), min(itr, 7)   # keep the oracle quick; still changes from step to step
+        seen.add((itl, itr))
+        orc.set_substeps(itl, itr)
+        mod.set_substeps(itl, itr)
+        orc.step()
+        mod.step()
+        for k in states:
+            assert common.compare(mod.get(k), orc[k], mask, RTOL, ATOL.get(k, ATOL["default"])) <= 1.0, (t, k)
+    assert len(seen) > 1
+    # no flow anywhere: the reference's percentile fails and it falls back to one sub-step
+    mod.set("LandRunoffsub", np.zeros((48, 64), np.float32))
+    assert mod.estimate_iterations("land") == 1
+    mod.close()

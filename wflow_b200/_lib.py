@@ -42,6 +42,7 @@ SYMBOLS = [
     "wf_schedule_get", "wf_schedule_catchment_total", "wf_create_from_schedule", "wf_bind_field",
     "wf_timing_reset", "wf_timing_get", "wf_kinematic_wave_batch", "wf_kinematic_wave_ssf_batch",
     "wf_schedule_partition", "wf_lateral_plan", "wf_gauges_create", "wf_gauges_sample",
+    "wf_estimate_iterations", "wf_set_substeps",
 ]
 
 
@@ -110,6 +111,8 @@ def lib():
     l.wf_lateral_plan.argtypes = [C.c_void_p, C.c_void_p]
     l.wf_gauges_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     l.wf_gauges_sample.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_float, C.c_int]
+    l.wf_estimate_iterations.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]
+    l.wf_set_substeps.argtypes = [C.c_void_p, C.c_int, C.c_int]
     l.wf_quick_suspend.argtypes = [C.c_void_p]
     l.wf_quick_resume.argtypes = [C.c_void_p]
     _lib = l

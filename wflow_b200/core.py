@@ -221,6 +221,16 @@ class SbmModel:
         _lib.check(self._l.wf_field_device_ptr(self._h, name.encode(), C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    # -- kinematic-wave sub-steps ---------------------------------------------------------
+    def estimate_iterations(self, which):
+        """estimate_iterations_kin_wave (wflow/wflow_funcs.py:103-116); which = "land" | "river"."""
+        it = C.c_int32(1)
+        _lib.check(self._l.wf_estimate_iterations(self._h, {"land": 0, "river": 1}[which], C.byref(it)))
+        return int(it.value)
+
+    def set_substeps(self, it_kin_l, it_kin_r):
+        _lib.check(self._l.wf_set_substeps(self._h, int(it_kin_l), int(it_kin_r)))
+
     # -- stepping --------------------------------------------------------------------------
     def step(self, nsteps=1):
         _lib.check(self._l.wf_step(self._h, int(nsteps)))

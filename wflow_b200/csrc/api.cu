@@ -305,6 +305,93 @@ int dispatch_step(wf_model *m) {
   return fail(WF_EINVAL, "unsupported number of soil layers");
 }
 
+// Everything of the sweep that depends on the sub-step counts: ticks per group, items per tick, the
+// busiest tick, shared-memory need.  Called at creation and by wf_set_substeps.
+int setup_sweep(wf_model *m) {
+  DevModel &dm = m->dm;
+  const int itR = dm.itR;
+  const int G = m->lay.ngroups;
+  std::vector<GroupDesc> gd((size_t)G);
+  std::vector<uint32_t> tick_total;  // items of every tick of every group (lateral.cuh: tick item space)
+  int64_t most = 0;
+  const int Dn = (int)m->net.nlevels(), Dr = (int)m->rnet.nlevels(), shift = Dn - Dr;
+  for (int g = 0; g < G; g++) {
+    gd[(size_t)g].lev_idx = (uint32_t)m->lay.lev_idx[(size_t)g];
+    gd[(size_t)g].rlev_idx = (uint32_t)m->rlay.lev_idx[(size_t)g];
+    gd[(size_t)g].lev0 = m->lay.lev0[(size_t)g];
+    gd[(size_t)g].rlev0 = m->rlay.lev0[(size_t)g];
+    const uint32_t *lo = m->lay.lev_off.data() + m->lay.lev_idx[(size_t)g];
+    const uint32_t *ro = m->rlay.lev_off.data() + m->rlay.lev_idx[(size_t)g];
+    const int l0 = m->lay.lev0[(size_t)g], r0 = m->rlay.lev0[(size_t)g];
+    const int nl = Dn - l0, nrl = Dr - r0;
+    const bool rivers = r0 < Dr && (dm.task_mask & 4);
+    const int nticks = nl + 1 + ((r0 < Dr) ? itR : 0);
+    gd[(size_t)g].tick_idx = (uint32_t)tick_total.size();
+    gd[(size_t)g].nticks = nticks;
+    for (int t = 0; t < nticks; t++) {
+      uint32_t items = 0;
+      if (t < nl && (dm.task_mask & 1)) items += ((lo[t + 1] - lo[t]) + 31u) & ~31u;
+      if (t >= 1 && t - 1 < nl && (dm.task_mask & 2)) items += ((lo[t] - lo[t - 1]) + 31u) & ~31u;
+      if (rivers)
+        for (int v = 0; v < itR; v++) {
+          const int q = (l0 - 2) - shift - r0 + t - v;
+          if (q >= 0 && q < nrl) items += ro[q + 1] - ro[q];
+        }
+      tick_total.push_back(items);
+    }
+    most = std::max(most, (m->lay.lev_idx[(size_t)g + 1] - m->lay.lev_idx[(size_t)g]) +
+                              (m->rlay.lev_idx[(size_t)g + 1] - m->rlay.lev_idx[(size_t)g]) + (int64_t)nticks);
+  }
+  cudaFree(m->d_tick_total);
+  cudaFree(m->d_groups);
+  m->d_tick_total = nullptr;
+  m->d_groups = nullptr;
+  CUDA_OK(cudaMalloc(&m->d_tick_total, std::max<size_t>(sizeof(uint32_t) * tick_total.size(), 16)));
+  CUDA_OK(cudaMemcpy(m->d_tick_total, tick_total.data(), sizeof(uint32_t) * tick_total.size(), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMalloc(&m->d_groups, std::max<size_t>(sizeof(GroupDesc) * (size_t)G, 16)));
+  CUDA_OK(cudaMemcpy(m->d_groups, gd.data(), sizeof(GroupDesc) * (size_t)G, cudaMemcpyHostToDevice));
+  dm.tick_total = m->d_tick_total;
+  dm.groups = m->d_groups;
+  dm.ngroups = G;
+  // a group's level offsets and tick sizes live in shared memory during its sweep when they fit
+  dm.lev_cache = 0;
+  m->lat_smem = 0;
+  if (most * 4 <= ((m->lat_mode == WF_GRID) ? 40 : 160) * 1024) {
+    dm.lev_cache = (int32_t)most;
+    m->lat_smem = (size_t)most * 4;
+  }
+  m->lat_blocks = 0;  // re-derived at the next launch
+  // busiest tick of the whole network (grid sweep: no more blocks than it can use)
+  const int D = dm.nlev;
+  int64_t best = 1;
+  for (int t = 0; t < D + 1 + itR; t++) {
+    int64_t items = 0;
+    if (t < D) items += m->net.lev_off[(size_t)t + 1] - m->net.lev_off[(size_t)t];
+    if (t >= 1 && t - 1 < D) items += m->net.lev_off[(size_t)t] - m->net.lev_off[(size_t)t - 1];
+    for (int v = 0; v < itR; v++) {
+      const int lr = (t - 2 - v) - dm.rlev_shift;
+      if (lr >= 0 && lr < dm.nrlev) items += m->rnet.lev_off[(size_t)lr + 1] - m->rnet.lev_off[(size_t)lr];
+    }
+    best = std::max(best, items);
+  }
+  m->max_tick_items = best + 64;  // two warp-boundary paddings of the item space
+  return WF_OK;
+}
+
+// Buffers sized by the sub-step counts: outflows of the earlier sub-steps and the shares handed to river receivers.
+int setup_substep_buffers(wf_model *m) {
+  DevModel &dm = m->dm;
+  const size_t n = (size_t)std::max<int64_t>(m->n, 1), nr = (size_t)std::max<int32_t>(m->nr, 1);
+  cudaFree(dm.qo_sub); cudaFree(dm.qr_sub); cudaFree(dm.h_qa); cudaFree(dm.h_qb);
+  dm.qo_sub = dm.qr_sub = nullptr;
+  dm.h_qa = dm.h_qb = nullptr;
+  CUDA_OK(cudaMalloc(&dm.h_qa, sizeof(double) * (size_t)dm.itL * n));
+  CUDA_OK(cudaMalloc(&dm.h_qb, sizeof(double) * (size_t)dm.itL * n));
+  if (dm.itL > 1) CUDA_OK(cudaMalloc(&dm.qo_sub, sizeof(float) * (size_t)(dm.itL - 1) * n));
+  if (dm.itR > 1) CUDA_OK(cudaMalloc(&dm.qr_sub, sizeof(float) * (size_t)(dm.itR - 1) * nr));
+  return WF_OK;
+}
+
 LateralPlan dispatch_plan(int ML, int64_t n, int64_t D, int64_t nbasins, int sms) {
   switch (ML) {
     case 1: return plan_lateral<1>(n, D, nbasins, sms);
@@ -391,7 +478,7 @@ int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint
   if (cfg->n_layer_thickness < 0 || cfg->n_layer_thickness + 1 > WF_MAX_LAYERS)
     return fail(WF_EINVAL, "too many soil layers");
   if (cfg->it_kin_l < 1 || cfg->it_kin_r < 1) return fail(WF_EINVAL, "it_kin_l / it_kin_r must be >= 1");
-  if (cfg->it_kin_r > 8) return fail(WF_EUNSUPPORTED, "more than 8 river sub-steps are not supported");
+  if (cfg->it_kin_l > 1024 || cfg->it_kin_r > 1024) return fail(WF_EUNSUPPORTED, "more than 1024 sub-steps are not supported");
   if (!(cfg->timestepsecs > 0)) return fail(WF_EINVAL, "timestepsecs must be > 0");
   const int64_t N = (int64_t)cfg->nrow * cfg->ncol;
   if (N >= (int64_t)1 << 31) return fail(WF_EUNSUPPORTED, "grids of 2^31 cells or more are not supported");
@@ -544,6 +631,8 @@ int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint
   dm.nr = m->nr;
   dm.nrnet = m->nrnet;
   dm.nlev = (int32_t)m->net.nlevels();
+  dm.nrlev = (int32_t)m->rnet.nlevels();
+  dm.rlev_shift = dm.nlev - dm.nrlev;
   dm.ML = m->ML;
   dm.nrLayers = (cfg->n_layer_thickness > 0) ? cfg->n_layer_thickness : 1;
   for (int k = 0; k < WF_MAXL; k++) dm.layerThickness[k] = (k < cfg->n_layer_thickness) ? cfg->layer_thickness[k] : 0.0;
@@ -585,50 +674,7 @@ int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint
   if ((rc = upload(m->river_slot.data(), sizeof(int32_t) * n, (void **)&dm.river_slot))) return rc;
   dm.lev_off = m->d_lev_off;
   dm.rlev_off = m->d_rlev_off;
-  {
-    const int G = m->lay.ngroups;
-    std::vector<GroupDesc> gd((size_t)G);
-    std::vector<uint32_t> tick_total;  // items of every tick of every group (lateral.cuh: tick item space)
-    int64_t most = 0;
-    const int Dn = (int)m->net.nlevels(), Dr = (int)m->rnet.nlevels(), shift = Dn - Dr;
-    for (int g = 0; g < G; g++) {
-      gd[(size_t)g].lev_idx = (uint32_t)m->lay.lev_idx[(size_t)g];
-      gd[(size_t)g].rlev_idx = (uint32_t)m->rlay.lev_idx[(size_t)g];
-      gd[(size_t)g].lev0 = m->lay.lev0[(size_t)g];
-      gd[(size_t)g].rlev0 = m->rlay.lev0[(size_t)g];
-      const uint32_t *lo = m->lay.lev_off.data() + m->lay.lev_idx[(size_t)g];
-      const uint32_t *ro = m->rlay.lev_off.data() + m->rlay.lev_idx[(size_t)g];
-      const int l0 = m->lay.lev0[(size_t)g], r0 = m->rlay.lev0[(size_t)g];
-      const int nl = Dn - l0, nrl = Dr - r0;
-      const bool rivers = r0 < Dr && (dm.task_mask & 4);
-      const int nticks = nl + 1 + ((r0 < Dr) ? cfg->it_kin_r : 0);
-      gd[(size_t)g].tick_idx = (uint32_t)tick_total.size();
-      gd[(size_t)g].nticks = nticks;
-      for (int t = 0; t < nticks; t++) {
-        uint32_t items = 0;
-        if (t < nl && (dm.task_mask & 1)) items += ((lo[t + 1] - lo[t]) + 31u) & ~31u;
-        if (t >= 1 && t - 1 < nl && (dm.task_mask & 2)) items += ((lo[t] - lo[t - 1]) + 31u) & ~31u;
-        if (rivers)
-          for (int v = 0; v < cfg->it_kin_r; v++) {
-            const int q = (l0 - 2) - shift - r0 + t - v;
-            if (q >= 0 && q < nrl) items += ro[q + 1] - ro[q];
-          }
-        tick_total.push_back(items);
-      }
-      most = std::max(most, (m->lay.lev_idx[(size_t)g + 1] - m->lay.lev_idx[(size_t)g]) +
-                                (m->rlay.lev_idx[(size_t)g + 1] - m->rlay.lev_idx[(size_t)g]) + (int64_t)nticks);
-    }
-    if ((rc = upload(tick_total.data(), sizeof(uint32_t) * tick_total.size(), (void **)&m->d_tick_total))) return rc;
-    dm.tick_total = m->d_tick_total;
-    if ((rc = upload(gd.data(), sizeof(GroupDesc) * (size_t)G, (void **)&m->d_groups))) return rc;
-    dm.groups = m->d_groups;
-    dm.ngroups = G;
-    // a group's level offsets live in shared memory during its sweep when they fit
-    if (most * 4 <= ((m->lat_mode == WF_GRID) ? 40 : 160) * 1024) {  // (most: level-offset entries of the largest group)
-      dm.lev_cache = (int32_t)most;
-      m->lat_smem = (size_t)most * 4;
-    }
-  }
+  if ((rc = setup_sweep(m))) return rc;
   dm.npad = (n + WF_VERT_THREADS - 1) / WF_VERT_THREADS * WF_VERT_THREADS;
   CUDA_OK(cudaMalloc(&dm.d_efT, sizeof(double) * (size_t)m->ML * std::max<int64_t>(dm.npad, 1)));
   CUDA_OK(cudaMalloc(&dm.d_efST, sizeof(double) * std::max<int64_t>(dm.npad, 1)));
@@ -638,8 +684,6 @@ int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint
   CUDA_OK(cudaMalloc(&dm.h_surplus, sizeof(float) * std::max<int64_t>(n, 1)));
   CUDA_OK(cudaMalloc(&dm.h_ssf, sizeof(double) * std::max<int64_t>(n, 1)));
   CUDA_OK(cudaMalloc(&dm.h_ssf_riv, sizeof(double) * std::max<int64_t>(n, 1)));
-  CUDA_OK(cudaMalloc(&dm.h_qa, sizeof(double) * (size_t)dm.itL * std::max<int64_t>(n, 1)));
-  CUDA_OK(cudaMalloc(&dm.h_qb, sizeof(double) * (size_t)dm.itL * std::max<int64_t>(n, 1)));
   CUDA_OK(cudaMalloc(&dm.grid_counter, 256));
   {  // carried powers start invalid (NaN): the first solve computes the full power
     const size_t nb = sizeof(double) * (size_t)std::max<int64_t>(n, 1), rb = sizeof(double) * (size_t)std::max<int32_t>(m->nr, 1);
@@ -665,23 +709,8 @@ int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint
     if ((rc = upload(srnet.nup.data(), srnet.ncells, (void **)&dm.r_nup))) return rc;
     dm.nrlev = (int32_t)m->rnet.nlevels();
     dm.rlev_shift = dm.nlev - dm.nrlev;
-    // busiest tick of the wavefront
-    const int D = dm.nlev;
-    int64_t best = 1;
-    for (int t = 0; t < D + 1 + dm.itR; t++) {
-      int64_t items = 0;
-      if (t < D) items += m->net.lev_off[(size_t)t + 1] - m->net.lev_off[(size_t)t];
-      if (t >= 1 && t - 1 < D) items += m->net.lev_off[(size_t)t] - m->net.lev_off[(size_t)t - 1];
-      for (int v = 0; v < dm.itR; v++) {
-        const int lr = (t - 2 - v) - dm.rlev_shift;
-        if (lr >= 0 && lr < dm.nrlev) items += m->rnet.lev_off[(size_t)lr + 1] - m->rnet.lev_off[(size_t)lr];
-      }
-      best = std::max(best, items);
-    }
-    m->max_tick_items = best + 64;  // two warp-boundary paddings of the item space
   }
-  if (dm.itL > 1) CUDA_OK(cudaMalloc(&dm.qo_sub, sizeof(float) * (size_t)(dm.itL - 1) * std::max<int64_t>(n, 1)));
-  if (dm.itR > 1) CUDA_OK(cudaMalloc(&dm.qr_sub, sizeof(float) * (size_t)(dm.itR - 1) * std::max<int32_t>(m->nr, 1)));
+  if ((rc = setup_substep_buffers(m))) return rc;
   // states exist from the start (zero = the reference's cold ZeroMap)
   for (int id = 0; id < F_COUNT; id++) {
     if ((g_fields[id].kind & 0xff) != K_STATE) continue;
@@ -1175,6 +1204,89 @@ int wf_gauges_sample(wf_model *m, int gauges, const char *field, float *out, flo
   if (!async) CUDA_OK(cudaStreamSynchronize(m->stream));
   CUDA_OK(cudaGetLastError());
   return WF_OK;
+}
+
+// ---- kinematic-wave sub-steps ---------------------------------------------------------------------
+int wf_set_substeps(wf_model *m, int it_kin_l, int it_kin_r) {
+  if (!m) return fail(WF_EINVAL, "null model");
+  if (it_kin_l < 1 || it_kin_r < 1) return fail(WF_EINVAL, "it_kin_l / it_kin_r must be >= 1");
+  if (it_kin_l > 1024 || it_kin_r > 1024) return fail(WF_EUNSUPPORTED, "more than 1024 sub-steps are not supported");
+  if (it_kin_l == m->dm.itL && it_kin_r == m->dm.itR) return WF_OK;
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  CUDA_OK(cudaStreamSynchronize(m->stream));
+  m->dm.itL = it_kin_l;
+  m->dm.itR = it_kin_r;
+  m->cfg.it_kin_l = it_kin_l;
+  m->cfg.it_kin_r = it_kin_r;
+  if (int rc = setup_sweep(m)) return rc;
+  return setup_substep_buffers(m);
+}
+
+int wf_estimate_iterations(wf_model *m, int which, int32_t *it_kin) {
+  if (!m || !it_kin) return fail(WF_EINVAL, "null argument");
+  if (which != 0 && which != 1) return fail(WF_EINVAL, "which must be 0 (overland) or 1 (river)");
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  *it_kin = 1;
+  const int64_t len = which ? m->nr : m->n;
+  const float *Q = m->dm.f[which ? F_RiverRunoffsub : F_LandRunoffsub];
+  const float *alpha = m->dm.f[which ? F_AlphaR : F_AlphaL];
+  const float *dx = m->dm.f[which ? F_DCL : F_DL];
+  if (len == 0) return WF_OK;  // no cell with Q > 0: the reference's percentile fails and it falls back to 1
+  if (!Q || !alpha || !dx) return fail(WF_EINVAL, "fields of the Courant estimate are not set");
+  uint32_t *keys = nullptr;
+  unsigned long long *d_cnt = nullptr;  // [0] valid count, [1..256] histogram
+  CUDA_OK(cudaMalloc(&keys, sizeof(uint32_t) * (size_t)len));
+  CUDA_OK(cudaMalloc(&d_cnt, sizeof(unsigned long long) * 257));
+  CUDA_OK(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * 257, m->stream));
+  k_courant_keys<<<(unsigned)((len + 255) / 256), 256, 0, m->stream>>>(Q, alpha, dx, (float)m->dm.beta, (float)m->dm.dt, keys, d_cnt, len);
+  m->launches++;
+  unsigned long long h[257];
+  CUDA_OK(cudaMemcpyAsync(h, d_cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
+  CUDA_OK(cudaStreamSynchronize(m->stream));
+  const unsigned long long nvalid = h[0];
+  int rc = WF_OK;
+  if (nvalid > 0) {
+    // k-th smallest valid key, most significant digit first
+    auto select = [&](unsigned long long k, uint32_t &out) -> int {
+      uint32_t prefix = 0, mask = 0;
+      for (int shift = 24; shift >= 0; shift -= 8) {
+        CUDA_OK(cudaMemsetAsync(d_cnt + 1, 0, sizeof(unsigned long long) * 256, m->stream));
+        k_select_hist<<<(unsigned)std::min<int64_t>((len + 255) / 256, 2048), 256, 0, m->stream>>>(keys, len, mask, prefix, shift, d_cnt + 1);
+        m->launches++;
+        CUDA_OK(cudaMemcpyAsync(h + 1, d_cnt + 1, sizeof(unsigned long long) * 256, cudaMemcpyDeviceToHost, m->stream));
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+        int d = 0;
+        for (; d < 255; d++) {
+          if (k < h[1 + d]) break;
+          k -= h[1 + d];
+        }
+        prefix |= (uint32_t)d << shift;
+        mask |= 0xffu << shift;
+      }
+      out = prefix;
+      return WF_OK;
+    };
+    // np.nanpercentile(a, 95), linear interpolation, float32 like the array (wflow_funcs.py:112)
+    const double vidx = 0.95 * (double)(nvalid - 1);
+    const unsigned long long lo = (unsigned long long)std::floor(vidx);
+    const unsigned long long hi = std::min<unsigned long long>(lo + 1, nvalid - 1);
+    const float g = (float)(vidx - (double)lo);
+    uint32_t klo = 0, khi = 0;
+    rc = select(lo, klo);
+    if (rc == WF_OK) rc = (hi == lo) ? (khi = klo, WF_OK) : select(hi, khi);
+    if (rc == WF_OK) {
+      float a, b;
+      std::memcpy(&a, &klo, 4);
+      std::memcpy(&b, &khi, 4);
+      const float diff = b - a;
+      float p95 = (g >= 0.5f) ? b - diff * (1.0f - g) : a + diff * g;
+      const float v = std::ceil(1.25f * p95);  // int(np.ceil(1.25 * p95)); a failing conversion means 1 (:113-114)
+      if (v == v && v >= 1.0f && v < 2.0e9f) *it_kin = (int32_t)v;
+    }
+  }
+  cudaFree(keys);
+  cudaFree(d_cnt);
+  return rc;
 }
 
 // ---- batched solvers -----------------------------------------------------------------------

@@ -61,6 +61,45 @@ __global__ void k_sample(const float *__restrict__ field, const int32_t *__restr
   if (i < n) out[i] = (pos[i] >= 0) ? field[pos[i]] : mv;
 }
 
+// ---- estimate_iterations_kin_wave (wflow/wflow_funcs.py:103-116) -------------------------------------
+// Courant number of every cell with Q > 0, as REAL4 map algebra evaluates it:
+//   celerity = 1 / (alpha * Beta * Q ** (Beta - 1));  courant = (timestepsecs / dx) * celerity
+// Keys are the float bits (positive floats order like unsigned integers); cells without flow get the
+// all-ones key and are not counted.  The 95th percentile is then two order statistics found by a
+// most-significant-digit-first radix select (k_select_hist: one 8-bit digit per pass).
+__global__ void k_courant_keys(const float *__restrict__ Q, const float *__restrict__ alpha, const float *__restrict__ dx,
+                               float beta, float timestepsecs, uint32_t *__restrict__ keys, unsigned long long *count,
+                               int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t key = 0xffffffffu;
+  if (i < n) {
+    const float q = Q[i];
+    if (q > 0.0f) {
+      const float p = powf(q, beta - 1.0f);
+      const float cel = 1.0f / ((alpha[i] * beta) * p);
+      const float courant = (timestepsecs / dx[i]) * cel;
+      if (courant == courant && courant >= 0.0f) key = __float_as_uint(courant);
+    }
+    keys[i] = key;
+  }
+  const unsigned valid = __ballot_sync(0xffffffffu, key != 0xffffffffu);
+  if ((threadIdx.x & 31) == 0 && valid) atomicAdd(count, (unsigned long long)__popc(valid));
+}
+// histogram of the digit at `shift` over the keys whose higher digits equal `prefix` (mask selects them)
+__global__ void k_select_hist(const uint32_t *__restrict__ keys, int64_t n, uint32_t mask, uint32_t prefix, int shift,
+                              unsigned long long *__restrict__ hist) {
+  __shared__ unsigned int sh[256];
+  for (int k = threadIdx.x; k < 256; k += blockDim.x) sh[k] = 0;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t key = keys[i];
+    if (key != 0xffffffffu && (key & mask) == prefix) atomicAdd(&sh[(key >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < 256; k += blockDim.x)
+    if (sh[k]) atomicAdd(&hist[k], (unsigned long long)sh[k]);
+}
+
 // gauge sets: pos = storage position (-1 outside the network); rpos (river-only fields) = river-order
 // position or -1 for a network cell that is not a river cell (the reference holds 0 there)
 __global__ void k_sample_gauges(const float *__restrict__ field, const int32_t *__restrict__ pos,

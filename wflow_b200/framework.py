@@ -293,9 +293,10 @@ class WflowSbm:
                 it_l = int(np.ceil(self.timestepsecs / self.kinwaveLandTstep))
             if self.kinwaveRiverTstep > 0:
                 it_r = int(np.ceil(self.timestepsecs / self.kinwaveRiverTstep))
-            if self.kinwaveLandTstep == 0 or self.kinwaveRiverTstep == 0:
-                raise NotImplementedError("kinwaveIters=1 needs fixed kinwaveLandTstep / kinwaveRiverTstep here "
-                                          "(the Courant estimate of estimate_iterations_kin_wave is not restated)")
+        # kinwaveIters = 1 without a fixed sub-step: estimated from the Courant number before every step
+        self._estimate_l = self.kinwaveIters == 1 and self.kinwaveLandTstep == 0
+        self._estimate_r = self.kinwaveIters == 1 and self.kinwaveRiverTstep == 0
+        self._it_fixed = (it_l, it_r)
         self._mod = SbmModel(ldd, river_b, schedule=sched, timestepsecs=self.timestepsecs,
                              layer_thickness=self.layer_thickness, model_snow=self.modelSnow,
                              soil_inf_redu=self.soilInfReduction, transfer_method=self.TransferMethod, ust=self.UST,
@@ -388,6 +389,10 @@ class WflowSbm:
             if self.modelSnow:
                 self._mod.set("TEMP", self._forcing("TEMP", "Temperature", "/inmaps/TEMP", step, 10.0))
             self.wf_QuickSuspend()
+            if self._estimate_l or self._estimate_r:  # wflow_sbm.py:2911-2923, 3159-3171
+                it_l = self._mod.estimate_iterations("land") if self._estimate_l else self._it_fixed[0]
+                it_r = self._mod.estimate_iterations("river") if self._estimate_r else self._it_fixed[1]
+                self._mod.set_substeps(it_l, it_r)
             self._mod.step()
             self._write_outputs(step)
 
