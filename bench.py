@@ -29,6 +29,10 @@ sys.path.insert(0, ROOT)
 
 BYTES_VERTICAL = 236  # algorithmic bytes per cell-step of the vertical kernel, 4 layers, snow on
 BYTES_FULL = 333      # full step incl. lateral statics, routing states and topology
+# DRAM traffic of one k_vertical launch per cell, from the round's `ncu --set full` capture of the default
+# workload (profiles/r1_vertical_ncu_details.txt: dram__bytes_read.sum + dram__bytes_write.sum = 13.52 GB for
+# 33 554 431 cells).  Above the algorithmic 236 B: float64 hand-offs, derived statics, register spills.
+TRAFFIC_VERTICAL_PER_CELL = 403.0
 
 
 def parse():
@@ -332,7 +336,10 @@ def run_b200(args):
             "roofline": {"bound": "hbm", "kernel": "k_vertical<4> (SBM vertical column)", "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "bytes_per_cell": BYTES_VERTICAL, "cells_per_launch": ncell, "ms_per_launch": v_launch_ms,
-                         "traffic": None,
+                         "traffic": TRAFFIC_VERTICAL_PER_CELL * ncell,
+                         "traffic_source": "ncu --set full, profiles/r1_vertical_ncu_details.txt (per cell x cells of this launch)",
+                         "bound_note": "the kernel is instruction-issue bound (ncu: issue slots busy 57 %, DRAM 30 %), "
+                                       "not HBM-bound; the HBM fraction is reported as the contract asks",
                          "full_step_gbs_at_333B": ncell * BYTES_FULL / ((ms_v + ms_l) / max(nst, 1) / 1e3) / 1e9},
             "kernels_ms_per_step": {"vertical": ms_v / max(nst, 1), "lateral": ms_l / max(nst, 1),
                                     "lateral_us_per_level": ms_l / max(nst, 1) * 1e3 / max(mod.num_levels, 1)},

@@ -453,6 +453,7 @@ static void catchment_total(const Network &net, const float *values, double *out
 }
 
 extern "C" {
+static int create_impl(wf_model *m, const wf_config *cfg, wf_schedule *sched, const uint8_t *ldd, const uint8_t *river);
 
 const char *wf_last_error(void) { return g_err.c_str(); }
 const char *wf_version(void) { return "wflow_b200 0.1 (sm_100a)"; }
@@ -490,20 +491,30 @@ int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint
   CUDA_OK(cudaSetDevice(cfg->device));
 
   wf_model *m = new wf_model();
+  const int rc = create_impl(m, cfg, sched, ldd, river);
+  if (rc != WF_OK) {  // release whatever the failed construction had allocated; keep its message
+    const std::string msg = g_err;
+    wf_destroy(m);
+    g_err = msg;
+    return rc;
+  }
+  *out = m;
+  return WF_OK;
+}
+
+static int create_impl(wf_model *m, const wf_config *cfg, wf_schedule *sched, const uint8_t *ldd, const uint8_t *river) {
+  const int64_t N = (int64_t)cfg->nrow * cfg->ncol;
   m->cfg = *cfg;
   if (m->cfg.beta == 0.0) m->cfg.beta = (double)0.6f;  // REAL4 0.6, wflow_sbm.py:1643
   // wflow_sbm.py:1757-1766
   m->ML = (cfg->n_layer_thickness > 0) ? cfg->n_layer_thickness + 1 : 1;
 
   if (sched) {
-    if (sched->net.nrow != cfg->nrow || sched->net.ncol != cfg->ncol) {
-      delete m;
+    if (sched->net.nrow != cfg->nrow || sched->net.ncol != cfg->ncol)
       return fail(WF_EINVAL, "schedule and config disagree on the grid size");
-    }
     m->net = std::move(sched->net);
     delete sched;
   } else if (build_network(ldd, cfg->nrow, cfg->ncol, m->net) != 0) {
-    delete m;
     return fail(WF_ECYCLE, "could not build the drainage network");
   }
   // river-only ldd: non-river cells -> missing (wflow_sbm.py:2387-2389)
@@ -511,10 +522,8 @@ int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint
     std::vector<uint8_t> lr((size_t)N, 0);
     if (river)
       for (int64_t i = 0; i < N; i++) lr[(size_t)i] = river[i] ? ldd[i] : 0;
-    if (build_network(lr.data(), cfg->nrow, cfg->ncol, m->rnet) != 0) {
-      delete m;
+    if (build_network(lr.data(), cfg->nrow, cfg->ncol, m->rnet) != 0)
       return fail(WF_ECYCLE, "could not build the river network");
-    }
   }
   m->n = m->net.ncells;
   const int64_t n = m->n;
@@ -719,14 +728,13 @@ int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint
     if ((rc = ensure_field(m, id))) return rc;
   }
   CUDA_OK(cudaStreamSynchronize(m->stream));
-  *out = m;
   return WF_OK;
 }
 
 void wf_destroy(wf_model *m) {
   if (!m) return;
   cudaSetDevice(m->cfg.device);
-  cudaStreamSynchronize(m->stream);
+  if (m->stream) cudaStreamSynchronize(m->stream);
 #ifdef WF_PROFILE
   if (m->dm.prof) {  // max over the steps run so far, per tick of the first group
     if (FILE *fp = std::fopen(std::getenv("WF_TICK_PROFILE"), "w")) {
@@ -766,8 +774,10 @@ void wf_destroy(wf_model *m) {
   cudaFree(m->dm.qo_sub); cudaFree(m->dm.qr_sub);
   cudaFree((void *)m->dm.up_start); cudaFree((void *)m->dm.topo); cudaFree((void *)m->dm.river_slot);
   cudaFree(m->d_order); cudaFree(m->d_rorder); cudaFree(m->d_lev_off); cudaFree(m->d_stage);
-  for (auto &e : m->ev) cudaEventDestroy(e);
-  cudaStreamDestroy(m->stream);
+  for (auto &e : m->ev)
+    if (e) cudaEventDestroy(e);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  cudaGetLastError();  // a partially constructed model may have handed null handles to the calls above
   delete m;
 }
 
