@@ -24,16 +24,23 @@ def state_names(max_layers, snow=True):
 
 
 def make_pair(nrow, ncol, *, kind="forest", tile=16, layer_thickness=(100, 300, 800), dt=86400, snow=1, itL=1, itR=1,
-              seed=3, river_area=8, tm=0, ust=0, sir=0, oracle=True, gpu=True, init="random", block=4):
+              seed=3, river_area=8, tm=0, ust=0, sir=0, oracle=True, gpu=True, init="random", block=4, mask_frac=0.0,
+              glacier=0):
     """Returns (oracle_model or None, cuda_model or None, ldd, river)."""
     ldd, river, static, state = synth.make_case(nrow, ncol, kind=kind, tile=tile, seed=seed, timestepsecs=dt,
                                                 layer_thickness=layer_thickness, river_area=river_area, init=init,
-                                                block=block)
+                                                block=block, mask_frac=mask_frac)
+    if glacier:  # glacierHBV inputs (wflow/wflow_funcs.py:549-603; wflow_sbm.py:2715-2743): a third of the cells glaciated
+        rng = np.random.default_rng(seed + 77)
+        gf = np.where(rng.random((nrow, ncol)) < 0.35, rng.uniform(0.05, 1.0, (nrow, ncol)), 0.0).astype(np.float32)
+        static = dict(static, GlacierFrac=gf, G_TT=np.float32(1.3), G_Cfmax=np.float32(5.3 * dt / 86400.0),
+                      G_SIfrac=np.float32(0.002 * dt / 86400.0))
+        state = dict(state, GlacierStore=np.where(gf > 0, rng.uniform(0.0, 5500.0, (nrow, ncol)), 0.0).astype(np.float32))
     orc = mod = None
     if oracle:
         from oracle import oracle as O
         orc = O.Oracle(ldd, river, timestepsecs=dt, layer_thickness=layer_thickness, modelSnow=snow, it_kinL=itL,
-                       it_kinR=itR, transferMethod=tm, ust=ust, soilInfRedu=sir)
+                       it_kinR=itR, transferMethod=tm, ust=ust, soilInfRedu=sir, glacier=glacier)
         for k, v in static.items():
             orc.set(k, v)
         for k, v in state.items():
@@ -41,7 +48,7 @@ def make_pair(nrow, ncol, *, kind="forest", tile=16, layer_thickness=(100, 300, 
     if gpu:
         from wflow_b200.core import SbmModel
         mod = SbmModel(ldd, river, timestepsecs=dt, layer_thickness=layer_thickness, model_snow=snow, it_kin_l=itL,
-                       it_kin_r=itR, transfer_method=tm, ust=ust, soil_inf_redu=sir)
+                       it_kin_r=itR, transfer_method=tm, ust=ust, soil_inf_redu=sir, glacier=glacier)
         skip = {"River", "Beta", "SatWaterDepth"}
         for k, v in static.items():
             if k not in skip:

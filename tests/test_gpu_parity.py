@@ -25,6 +25,9 @@ CASES = [
     dict(kind="forest", layer_thickness=(100, 300), snow=0, itL=2, itR=2, dt=21600),
     dict(kind="pits", layer_thickness=(100, 300, 800)),
     dict(kind="tiles", layer_thickness=(100, 300, 800), init="cold"),
+    dict(kind="tiles", layer_thickness=(100, 300, 800), glacier=1),                       # glacierHBV
+    dict(kind="tiles", layer_thickness=(100, 300, 800), mask_frac=0.1, dt=3600, itR=2),  # missing cells inside the tiles
+    dict(kind="forest", layer_thickness=(50, 100, 150, 200, 300, 400, 600)),              # 8 soil layers (the maximum)
 ]
 
 
@@ -39,7 +42,7 @@ def run_case(nrow, ncol, nsteps, kw, resync):
     orc, mod, ldd, river = common.make_pair(nrow, ncol, **kw)
     mask = common.network_mask(orc)
     forc = synth.Forcing(nrow, ncol, seed=5, timestepsecs=kw.get("dt", 86400), rain_mean=RAIN_MEAN)
-    states = common.state_names(orc.maxLayers, kw.get("snow", 1))
+    states = common.state_names(orc.maxLayers, kw.get("snow", 1)) + (["GlacierStore"] if kw.get("glacier") else [])
     names = states + common.DIAGS
     orc.want(*common.DIAGS)
     mod.request(*common.DIAGS)
