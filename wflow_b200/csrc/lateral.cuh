@@ -773,16 +773,18 @@ __device__ __forceinline__ void sweep_group(const DevModel &m, const GroupDesc g
       }
     }
     if (t + 1 < nticks) {
-      const int pd = PRELOAD ? 2 : 1;  // L2 warm-up distance: the tick after the one whose operands are fetched below
-      if (t + pd < nl) {
-        const uint32_t nb = lo[t + pd], ne = lo[t + pd + 1];
-        if (nb + (uint32_t)tid < ne && !(m.task_mask & 8)) prefetch_subsurface(m, (int64_t)nb + tid);
-      }
 #ifdef WF_PROFILE
       if (pbase) prof_stamp(pbase + 12, c0, 0);
 #endif
       wave_arrive<MODE>(ws);
+      // while the others arrive: this thread's next item (and, in the grid sweep, its operands) ...
       nxt = prepare(t + 1);
+      // ... and the operands of the tick after into L2
+      const int pd = PRELOAD ? 2 : 1;
+      if (t + pd < nl) {
+        const uint32_t nb = lo[t + pd], ne = lo[t + pd + 1];
+        if (nb + (uint32_t)tid < ne && !(m.task_mask & 8)) prefetch_subsurface(m, (int64_t)nb + tid);
+      }
       wave_wait<MODE>(ws);
 #ifdef WF_PROFILE
       if (pbase) prof_stamp(pbase + 13, c0, 0);
