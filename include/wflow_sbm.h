@@ -140,6 +140,32 @@ int wf_bind_field(wf_model *m, const char *name, float *dptr);
  * like the reference's numpy2pcr copies.  nsteps > 1 repeats with the same forcing. */
 int wf_step(wf_model *m, int nsteps);
 int wf_synchronize(wf_model *m);
+
+/* --- several timesteps per launch ------------------------------------------------------
+ * Replaces a run of consecutive passes of the time loop, wf_DynamicFramework._runDynamic
+ * (wflow/wf_DynamicFramework.py:2968-3042) calling WflowModel.dynamic() (wflow/wflow_sbm.py:2518-3528),
+ * when the forcing of the coming steps is known (map stacks / netCDF on disk, BMI update_until):
+ * timestep s+1 follows timestep s down the drainage network at a distance of 3 + it_kin_r levels
+ * inside ONE kernel, instead of waiting for s to reach the outlet.  Results are bit-identical to
+ * `nsteps` calls of wf_step with the same forcing.
+ *   wf_pipeline_reserve      room for the forcing of `max_steps` steps per launch
+ *   wf_pipeline_set_forcing  host raster of P, PET or TEMP for step `step` (0-based) of the next launch;
+ *                            asynchronous like wf_set_field (keep the buffer alive until the launch
+ *                            has consumed it)
+ *   wf_pipeline_forcing_ptr  the device buffer itself, [max_steps][*stride] float32 in storage order
+ *                            (wf_cell_order), for forcing produced on the device
+ *   wf_pipeline_capture      gauge set (wf_gauges_create; -1 = none) at which every step's RiverRunoff is
+ *                            kept -- the one output a step must hand over before the next overwrites it
+ *                            (wf_OutputTimeSeriesArea's sampled discharge, wf_DynamicFramework.py:446-499)
+ *   wf_step_pipelined        runs `nsteps` steps; gauge_out (may be NULL) receives [nsteps][gauges] values
+ *                            (0 at network cells outside the river, mv outside the network); async != 0
+ *                            returns without waiting (pinned gauge_out, valid after wf_synchronize).
+ * All other fields hold, after the call, what they hold after the last of the steps. */
+int wf_pipeline_reserve(wf_model *m, int max_steps);
+int wf_pipeline_set_forcing(wf_model *m, const char *name, int step, const float *grid);
+int wf_pipeline_forcing_ptr(wf_model *m, const char *name, void **dptr, int64_t *stride);
+int wf_pipeline_capture(wf_model *m, int gauges);
+int wf_step_pipelined(wf_model *m, int nsteps, float *gauge_out, float mv, int async);
 /* Device time of the kernels of the last wf_step call, milliseconds (CUDA events on the
  * model's stream): [0] vertical column, [1] lateral sweep, [2] whole step. */
 int wf_last_step_ms(wf_model *m, float ms[3]);

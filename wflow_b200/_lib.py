@@ -42,7 +42,8 @@ SYMBOLS = [
     "wf_schedule_get", "wf_schedule_catchment_total", "wf_create_from_schedule", "wf_bind_field",
     "wf_timing_reset", "wf_timing_get", "wf_kinematic_wave_batch", "wf_kinematic_wave_ssf_batch",
     "wf_schedule_partition", "wf_lateral_plan", "wf_gauges_create", "wf_gauges_sample",
-    "wf_estimate_iterations", "wf_set_substeps",
+    "wf_estimate_iterations", "wf_set_substeps", "wf_pipeline_reserve", "wf_pipeline_set_forcing",
+    "wf_pipeline_forcing_ptr", "wf_pipeline_capture", "wf_step_pipelined",
 ]
 
 
@@ -113,6 +114,11 @@ def lib():
     l.wf_gauges_sample.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_float, C.c_int]
     l.wf_estimate_iterations.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]
     l.wf_set_substeps.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    l.wf_pipeline_reserve.argtypes = [C.c_void_p, C.c_int]
+    l.wf_pipeline_set_forcing.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p]
+    l.wf_pipeline_forcing_ptr.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    l.wf_pipeline_capture.argtypes = [C.c_void_p, C.c_int]
+    l.wf_step_pipelined.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_int]
     l.wf_quick_suspend.argtypes = [C.c_void_p]
     l.wf_quick_resume.argtypes = [C.c_void_p]
     _lib = l

@@ -238,6 +238,42 @@ class SbmModel:
     def synchronize(self):
         _lib.check(self._l.wf_synchronize(self._h))
 
+    # -- several timesteps per launch (include/wflow_sbm.h: wf_step_pipelined) ---------------
+    def pipeline_reserve(self, max_steps):
+        _lib.check(self._l.wf_pipeline_reserve(self._h, int(max_steps)))
+
+    def pipeline_set_forcing(self, name, step, value, wait=True):
+        """Forcing raster (P, PET or TEMP) of step `step` of the next pipelined launch.  `value` is a
+        numpy raster, or (wait=False) a raw pointer to a caller-owned pinned nrow*ncol float32 buffer."""
+        if isinstance(value, int):
+            _lib.check(self._l.wf_pipeline_set_forcing(self._h, name.encode(), int(step), value))
+            return
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=np.float32), self.shape))
+        _lib.check(self._l.wf_pipeline_set_forcing(self._h, name.encode(), int(step), a.ctypes.data))
+        _lib.check(self._l.wf_synchronize(self._h))  # the copy is asynchronous: `a` must outlive it
+
+    def pipeline_forcing_ptr(self, name):
+        """(device pointer, stride): the [max_steps][stride] float32 forcing buffer in storage order."""
+        p, st = C.c_void_p(), C.c_int64()
+        _lib.check(self._l.wf_pipeline_forcing_ptr(self._h, name.encode(), C.byref(p), C.byref(st)))
+        return p.value, int(st.value)
+
+    def pipeline_capture(self, gauges):
+        _lib.check(self._l.wf_pipeline_capture(self._h, -1 if gauges is None else int(gauges)))
+
+    def step_pipelined(self, nsteps, gauge_out=None, mv=-999.0, wait=True):
+        """Run `nsteps` timesteps in one launch, step s+1 trailing step s down the network.
+        gauge_out: None, a numpy float32 array [nsteps, ngauges] (filled on return), or a raw pointer."""
+        if gauge_out is None:
+            ptr = None
+        elif isinstance(gauge_out, int):
+            ptr = gauge_out
+        else:
+            if gauge_out.dtype != np.float32 or not gauge_out.flags.c_contiguous:
+                raise ValueError("gauge_out must be a C-contiguous float32 array")
+            ptr, wait = gauge_out.ctypes.data, True
+        _lib.check(self._l.wf_step_pipelined(self._h, int(nsteps), ptr, float(mv), 0 if wait else 1))
+
     def last_step_ms(self):
         ms = (C.c_float * 3)()
         _lib.check(self._l.wf_last_step_ms(self._h, ms))

@@ -14,6 +14,7 @@
 #include "fields.h"
 #include "kernels.cuh"
 #include "lateral.cuh"
+#include "pipeline.cuh"
 #include "network.h"
 #include "reduce.cuh"
 
@@ -107,6 +108,17 @@ struct wf_model {
   float *owned[F_COUNT] = {};         // our own allocation while an external one is bound
   std::vector<cudaEvent_t> tev;       // timing window: 3 events per step
   size_t tev_used = 0;
+  int64_t tev_extra_steps = 0;        // steps beyond the first of every pipelined launch in the timing window
+  // pipelined multi-step sweep (pipeline.cuh)
+  float *pipe_forc[3] = {nullptr, nullptr, nullptr};  // P, PET, TEMP of the coming steps: [pipe_cap][npad], storage order
+  bool pipe_has[3] = {false, false, false};
+  int pipe_cap = 0;
+  int pipe_gauges = -1;               // gauge set whose river discharge is captured per step
+  int32_t *d_cap_slot = nullptr, *d_cap_col = nullptr;
+  float *d_cap_out = nullptr, *d_cap_exp = nullptr;
+  int32_t cap_n = 0;
+  int pipe_blocks = 0;
+  bool pipe_attr_set = false;
 };
 
 namespace {
@@ -232,17 +244,11 @@ int launch_lateral(wf_model *m) {
   return WF_OK;
 }
 
+// What every step needs before its kernels: derived statics up to date, the diagnostics flag, the
+// source array of every input slot of the column (pointers may have been re-bound since the last step).
 template <int ML>
-int launch_step(wf_model *m) {
+void prepare_step(wf_model *m) {
   const int64_t n = m->n;
-  if (n == 0) return WF_OK;
-  cudaEvent_t e0 = m->ev[0], e1 = m->ev[1], e2 = m->ev[2];
-  if (m->tev_used + 3 <= m->tev.size()) {
-    e0 = m->tev[m->tev_used]; e1 = m->tev[m->tev_used + 1]; e2 = m->tev[m->tev_used + 2];
-    m->tev_used += 3;
-  }
-  if (m->timed) cudaEventRecord(e0, m->stream);
-  const int tb = WF_VERT_THREADS;
   if (m->derived_dirty) {  // statics changed since the derived ones were computed
     k_derive<ML><<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->dm);
     k_derive_lateral<ML><<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->dm);
@@ -275,6 +281,20 @@ int launch_step(wf_model *m) {
     }
     dm.vsrc_count = cnt;
   }
+}
+
+template <int ML>
+int launch_step(wf_model *m) {
+  const int64_t n = m->n;
+  if (n == 0) return WF_OK;
+  cudaEvent_t e0 = m->ev[0], e1 = m->ev[1], e2 = m->ev[2];
+  if (m->tev_used + 3 <= m->tev.size()) {
+    e0 = m->tev[m->tev_used]; e1 = m->tev[m->tev_used + 1]; e2 = m->tev[m->tev_used + 2];
+    m->tev_used += 3;
+  }
+  if (m->timed) cudaEventRecord(e0, m->stream);
+  const int tb = WF_VERT_THREADS;
+  prepare_step<ML>(m);
   const size_t vsmem = WF_VERT_STAGE ? VLayout<ML>::bytes(m->dm.glacier != 0) : 0;
   if (vsmem > 48 * 1024 && !m->vert_attr_set) {
     CUDA_OK(cudaFuncSetAttribute((void *)k_vertical<ML>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
@@ -361,6 +381,7 @@ int setup_sweep(wf_model *m) {
     m->lat_smem = (size_t)most * 4;
   }
   m->lat_blocks = 0;  // re-derived at the next launch
+  m->pipe_blocks = 0;
   // busiest tick of the whole network (grid sweep: no more blocks than it can use)
   const int D = dm.nlev;
   int64_t best = 1;
@@ -436,6 +457,131 @@ int check_ready(wf_model *m) {
     for (int id : kRequiredGlacier)
       if (int rc = need(id)) return rc;
   return WF_OK;
+}
+
+
+// ---- pipelined multi-step sweep (pipeline.cuh) -------------------------------------------------------
+__global__ void k_expand_capture(const float *__restrict__ cap, const int32_t *__restrict__ col, const int32_t *__restrict__ pos,
+                                 float *__restrict__ out, int64_t ngauges, int32_t cap_n, int64_t total, float mv) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= total) return;
+  const int64_t s = k / ngauges, g = k - s * ngauges;
+  const int32_t c = col[g];
+  // river-only field: 0 at the cells of the network that kin_wave does not visit (wflow_funcs.py:172-182), mv outside it
+  out[k] = (c >= 0) ? cap[s * cap_n + c] : ((pos[g] >= 0) ? 0.0f : mv);
+}
+
+template <int ML>
+int launch_pipeline(wf_model *m, const DevModel &dmp, const PipeArgs &pa) {
+  void *args[] = {(void *)&dmp, (void *)&pa};
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (m->lat_mode == WF_GRID) {
+    void *fn = (void *)k_pipeline<ML, WF_GRID>;
+    if (m->pipe_blocks == 0) {
+      int per_sm = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pipeline<ML, WF_GRID>, wf_pipe_threads(WF_GRID), m->lat_smem);
+      if (per_sm < 1) return fail(WF_ENODEVICE, "k_pipeline does not fit on an SM");
+      m->pipe_blocks = sms * per_sm;
+    }
+    CUDA_OK(cudaMemsetAsync(m->dm.grid_counter, 0, sizeof(unsigned int), m->stream));
+    CUDA_OK(cudaLaunchCooperativeKernel(fn, dim3((unsigned)m->pipe_blocks), dim3((unsigned)wf_pipe_threads(WF_GRID)), args, m->lat_smem,
+                                        m->stream));
+    return WF_OK;
+  }
+  const bool cta = m->lat_mode == WF_CTA;
+  void *fn = cta ? (void *)k_pipeline<ML, WF_CTA> : (void *)k_pipeline<ML, WF_CLUSTER>;
+  const int threads = cta ? wf_pipe_threads(WF_CTA) : wf_block_threads(m->lat_mode);
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = m->lat_smem;
+  cfg.stream = m->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)m->cluster_size;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = cta ? 0 : 1;
+  if (m->pipe_blocks == 0) {
+    if (m->lat_smem > 48 * 1024 && !m->pipe_attr_set) {
+      CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->lat_smem));
+      m->pipe_attr_set = true;
+    }
+    int res = 0;
+    if (cta) {
+      int per_sm = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pipeline<ML, WF_CTA>, threads, m->lat_smem);
+      res = sms * per_sm;
+    } else {
+      cfg.gridDim = dim3((unsigned)m->cluster_size * 64);
+      if (cudaOccupancyMaxActiveClusters(&res, k_pipeline<ML, WF_CLUSTER>, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        res = 0;
+      }
+    }
+    if (res < 1) return fail(WF_ENODEVICE, "k_pipeline does not fit on the device");
+    m->pipe_blocks = std::min(res, m->dm.ngroups) * m->cluster_size;
+  }
+  cfg.gridDim = dim3((unsigned)m->pipe_blocks);
+  CUDA_OK(cudaLaunchKernelExC(&cfg, fn, args));
+  return WF_OK;
+}
+
+template <int ML>
+int run_pipeline(wf_model *m, int nsteps) {
+  if (m->n == 0) return WF_OK;
+  cudaEvent_t e0 = m->ev[0], e1 = m->ev[1], e2 = m->ev[2];
+  if (m->tev_used + 3 <= m->tev.size()) {
+    e0 = m->tev[m->tev_used]; e1 = m->tev[m->tev_used + 1]; e2 = m->tev[m->tev_used + 2];
+    m->tev_used += 3;
+    m->tev_extra_steps += nsteps - 1;
+  }
+  // the column's forcing slots point at the multi-step buffers for this launch
+  float *saved[3] = {m->dm.f[F_P], m->dm.f[F_PET], m->dm.f[F_TEMP]};
+  m->dm.f[F_P] = m->pipe_forc[0];
+  m->dm.f[F_PET] = m->pipe_forc[1];
+  if (m->pipe_has[2]) m->dm.f[F_TEMP] = m->pipe_forc[2];
+  int rc = check_ready(m);
+  if (rc == WF_OK) {
+    if (m->timed) { cudaEventRecord(e0, m->stream); cudaEventRecord(e1, m->stream); }
+    prepare_step<ML>(m);
+    DevModel dmp = m->dm;
+    if (m->pipe_gauges >= 0 && m->cap_n > 0) {
+      dmp.cap_slot = m->d_cap_slot;
+      dmp.cap_out = m->d_cap_out;
+      dmp.cap_n = m->cap_n;
+    }
+    PipeArgs pa;
+    pa.nsteps = nsteps;
+    pa.lag = 3 + m->dm.itR;
+    pa.fstride = m->dm.npad;
+    rc = launch_pipeline<ML>(m, dmp, pa);
+    if (rc == WF_OK) {
+      m->launches++;
+      if (m->timed) cudaEventRecord(e2, m->stream);
+      m->ev_last[0] = e0; m->ev_last[1] = e1; m->ev_last[2] = e2;
+    }
+  }
+  m->dm.f[F_P] = saved[0]; m->dm.f[F_PET] = saved[1]; m->dm.f[F_TEMP] = saved[2];
+  if (rc != WF_OK) return rc;
+  CUDA_OK(cudaGetLastError());
+  return WF_OK;
+}
+
+int dispatch_pipeline(wf_model *m, int nsteps) {
+  switch (m->ML) {
+    case 1: return run_pipeline<1>(m, nsteps);
+    case 2: return run_pipeline<2>(m, nsteps);
+    case 3: return run_pipeline<3>(m, nsteps);
+    case 4: return run_pipeline<4>(m, nsteps);
+    case 5: return run_pipeline<5>(m, nsteps);
+    case 6: return run_pipeline<6>(m, nsteps);
+    case 7: return run_pipeline<7>(m, nsteps);
+    case 8: return run_pipeline<8>(m, nsteps);
+  }
+  return fail(WF_EINVAL, "unsupported number of soil layers");
 }
 
 }  // namespace
@@ -760,6 +906,8 @@ void wf_destroy(wf_model *m) {
     if (m->ring_copied[b]) cudaEventDestroy(m->ring_copied[b]);
     if (m->ring_free[b]) cudaEventDestroy(m->ring_free[b]);
   }
+  for (float *p : m->pipe_forc) cudaFree(p);
+  cudaFree(m->d_cap_slot); cudaFree(m->d_cap_col); cudaFree(m->d_cap_out); cudaFree(m->d_cap_exp);
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   for (auto &g : m->gauges) { cudaFree(g.d_pos); cudaFree(g.d_rpos); cudaFree(g.d_out); }
   for (cudaEvent_t e : m->tev) cudaEventDestroy(e);
@@ -871,15 +1019,12 @@ static int gather_into(wf_model *m, int id, const float *dgrid) {
   return WF_OK;
 }
 
-int wf_set_field(wf_model *m, const char *name, const float *grid) {
-  if (!m || !grid) return fail(WF_EINVAL, "null argument");
-  const int id = field_index(name);
-  if (id < 0) return fail(WF_EINVAL, std::string("unknown field: ") + (name ? name : "(null)"));
-  CUDA_OK(cudaSetDevice(m->cfg.device));
+// Host raster -> next slot of the staging ring: the copy runs on the copy stream (it waits only for the
+// gather that last read the slot), the model's stream waits for the copy -- so the upload of the next
+// step's forcing overlaps the running step's kernels as long as the host enqueues ahead.  The caller
+// enqueues its gather from d_ring[*slot] on the model's stream and then calls ring_release.
+static int ring_upload(wf_model *m, const float *grid, int *slot) {
   const size_t bytes = sizeof(float) * (size_t)m->cfg.nrow * m->cfg.ncol;
-  // next slot of the staging ring: copy on the copy stream (waits only for the gather that last read
-  // the slot), gather on the model's stream (waits for the copy) -- the copy of step s+1's forcing
-  // runs while step s computes, as long as the host enqueues ahead
   const int b = m->ring_next;
   m->ring_next = (b + 1) % wf_model::kStageRing;
   if (!m->copy_stream) CUDA_OK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
@@ -893,8 +1038,23 @@ int wf_set_field(wf_model *m, const char *name, const float *grid) {
   CUDA_OK(cudaMemcpyAsync(m->d_ring[b], grid, bytes, cudaMemcpyHostToDevice, m->copy_stream));
   CUDA_OK(cudaEventRecord(m->ring_copied[b], m->copy_stream));
   CUDA_OK(cudaStreamWaitEvent(m->stream, m->ring_copied[b], 0));
+  *slot = b;
+  return WF_OK;
+}
+static int ring_release(wf_model *m, int slot) {
+  CUDA_OK(cudaEventRecord(m->ring_free[slot], m->stream));
+  return WF_OK;
+}
+
+int wf_set_field(wf_model *m, const char *name, const float *grid) {
+  if (!m || !grid) return fail(WF_EINVAL, "null argument");
+  const int id = field_index(name);
+  if (id < 0) return fail(WF_EINVAL, std::string("unknown field: ") + (name ? name : "(null)"));
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  int b = 0;
+  if (int rc = ring_upload(m, grid, &b)) return rc;
   const int rc = gather_into(m, id, m->d_ring[b]);
-  CUDA_OK(cudaEventRecord(m->ring_free[b], m->stream));
+  if (int rc2 = ring_release(m, b)) return rc2;
   return rc;
 }
 
@@ -1004,6 +1164,130 @@ int wf_step(wf_model *m, int nsteps) {
   return WF_OK;
 }
 
+
+// ---- pipelined multi-step stepping ---------------------------------------------------------------------
+static int pipe_forcing_index(const char *name) {
+  const int id = field_index(name);
+  return id == F_P ? 0 : (id == F_PET ? 1 : (id == F_TEMP ? 2 : -1));
+}
+
+int wf_pipeline_reserve(wf_model *m, int max_steps) {
+  if (!m || max_steps < 1) return fail(WF_EINVAL, "bad argument");
+  if (max_steps > 4096) return fail(WF_EUNSUPPORTED, "more than 4096 steps per launch are not supported");
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  if (max_steps <= m->pipe_cap) return WF_OK;
+  CUDA_OK(cudaStreamSynchronize(m->stream));
+  const size_t per = (size_t)std::max<int64_t>(m->dm.npad, 1);
+  for (int k = 0; k < 3; k++) {
+    float *p = nullptr;
+    CUDA_OK(cudaMalloc(&p, sizeof(float) * per * (size_t)max_steps));
+    CUDA_OK(cudaMemsetAsync(p, 0, sizeof(float) * per * (size_t)max_steps, m->stream));
+    if (m->pipe_forc[k]) {
+      CUDA_OK(cudaMemcpyAsync(p, m->pipe_forc[k], sizeof(float) * per * (size_t)m->pipe_cap, cudaMemcpyDeviceToDevice, m->stream));
+      CUDA_OK(cudaStreamSynchronize(m->stream));
+      cudaFree(m->pipe_forc[k]);
+    }
+    m->pipe_forc[k] = p;
+  }
+  if (m->cap_n > 0) {
+    cudaFree(m->d_cap_out);
+    m->d_cap_out = nullptr;
+    CUDA_OK(cudaMalloc(&m->d_cap_out, sizeof(float) * (size_t)m->cap_n * (size_t)max_steps));
+  }
+  if (m->pipe_gauges >= 0) {
+    cudaFree(m->d_cap_exp);
+    m->d_cap_exp = nullptr;
+    CUDA_OK(cudaMalloc(&m->d_cap_exp, sizeof(float) * (size_t)std::max<int64_t>(m->gauges[(size_t)m->pipe_gauges].n, 1) * (size_t)max_steps));
+  }
+  m->pipe_cap = max_steps;
+  return WF_OK;
+}
+
+int wf_pipeline_set_forcing(wf_model *m, const char *name, int step, const float *grid) {
+  if (!m || !grid) return fail(WF_EINVAL, "null argument");
+  const int k = pipe_forcing_index(name);
+  if (k < 0) return fail(WF_EINVAL, "pipelined forcing is P, PET or TEMP");
+  if (step < 0 || step >= m->pipe_cap) return fail(WF_EINVAL, "step outside the reserved window (wf_pipeline_reserve)");
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  int b = 0;
+  if (int rc = ring_upload(m, grid, &b)) return rc;
+  if (m->n > 0) {
+    k_gather<<<(unsigned)((m->n + 255) / 256), 256, 0, m->stream>>>(m->d_ring[b], m->d_order, m->pipe_forc[k] + (size_t)step * m->dm.npad, m->n);
+    m->launches++;
+  }
+  m->pipe_has[k] = true;
+  if (int rc = ring_release(m, b)) return rc;
+  CUDA_OK(cudaGetLastError());
+  return WF_OK;
+}
+
+int wf_pipeline_forcing_ptr(wf_model *m, const char *name, void **dptr, int64_t *stride) {
+  if (!m || !dptr) return fail(WF_EINVAL, "null argument");
+  const int k = pipe_forcing_index(name);
+  if (k < 0) return fail(WF_EINVAL, "pipelined forcing is P, PET or TEMP");
+  if (m->pipe_cap < 1) return fail(WF_EINVAL, "call wf_pipeline_reserve first");
+  *dptr = m->pipe_forc[k];
+  if (stride) *stride = m->dm.npad;
+  m->pipe_has[k] = true;  // the caller fills it
+  return WF_OK;
+}
+
+int wf_pipeline_capture(wf_model *m, int gauges) {
+  if (!m || gauges >= (int)m->gauges.size()) return fail(WF_EINVAL, "bad gauge-set handle");
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  CUDA_OK(cudaStreamSynchronize(m->stream));
+  cudaFree(m->d_cap_slot); cudaFree(m->d_cap_col); cudaFree(m->d_cap_out); cudaFree(m->d_cap_exp);
+  m->d_cap_slot = m->d_cap_col = nullptr;
+  m->d_cap_out = m->d_cap_exp = nullptr;
+  m->cap_n = 0;
+  m->pipe_gauges = gauges < 0 ? -1 : gauges;
+  if (gauges < 0) return WF_OK;
+  const wf_model::GaugeSet &g = m->gauges[(size_t)gauges];
+  std::vector<int32_t> slot((size_t)std::max<int32_t>(m->nr, 1), -1), col((size_t)std::max<int64_t>(g.n, 1), -1);
+  int32_t ncol = 0;
+  for (int64_t i = 0; i < g.n; i++) {
+    const int32_t r = g.rpos[(size_t)i];
+    if (r < 0 || r >= m->nrnet) continue;  // not a cell of the river network: 0 (inside the network) or mv
+    if (slot[(size_t)r] < 0) slot[(size_t)r] = ncol++;
+    col[(size_t)i] = slot[(size_t)r];
+  }
+  m->cap_n = ncol;
+  CUDA_OK(cudaMalloc(&m->d_cap_slot, sizeof(int32_t) * slot.size()));
+  CUDA_OK(cudaMalloc(&m->d_cap_col, sizeof(int32_t) * col.size()));
+  CUDA_OK(cudaMemcpy(m->d_cap_slot, slot.data(), sizeof(int32_t) * slot.size(), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(m->d_cap_col, col.data(), sizeof(int32_t) * col.size(), cudaMemcpyHostToDevice));
+  const size_t steps = (size_t)std::max(m->pipe_cap, 1);
+  CUDA_OK(cudaMalloc(&m->d_cap_out, sizeof(float) * (size_t)std::max<int32_t>(ncol, 1) * steps));
+  CUDA_OK(cudaMalloc(&m->d_cap_exp, sizeof(float) * (size_t)std::max<int64_t>(g.n, 1) * steps));
+  return WF_OK;
+}
+
+int wf_step_pipelined(wf_model *m, int nsteps, float *gauge_out, float mv, int async) {
+  if (!m) return fail(WF_EINVAL, "null model");
+  if (nsteps < 1) return fail(WF_EINVAL, "nsteps must be >= 1");
+  if (nsteps > m->pipe_cap) return fail(WF_EINVAL, "more steps than reserved (wf_pipeline_reserve)");
+  if (!m->pipe_has[0] || !m->pipe_has[1]) return fail(WF_EINVAL, "pipelined forcing not set: P and PET (wf_pipeline_set_forcing)");
+  if (m->cfg.model_snow && !m->pipe_has[2]) return fail(WF_EINVAL, "pipelined forcing not set: TEMP");
+  if (m->dm.task_mask != 7) return fail(WF_EUNSUPPORTED, "WF_LATERAL_TASKS is a development aid of the per-step sweep");
+  if (gauge_out && m->pipe_gauges < 0) return fail(WF_EINVAL, "no gauge set registered (wf_pipeline_capture)");
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  m->timed = true;
+  if (int rc = dispatch_pipeline(m, nsteps)) return rc;
+  if (gauge_out) {
+    const wf_model::GaugeSet &g = m->gauges[(size_t)m->pipe_gauges];
+    const int64_t total = g.n * (int64_t)nsteps;
+    if (total > 0) {
+      k_expand_capture<<<(unsigned)((total + 255) / 256), 256, 0, m->stream>>>(m->d_cap_out, m->d_cap_col, g.d_pos, m->d_cap_exp, g.n,
+                                                                               m->cap_n, total, mv);
+      m->launches++;
+      CUDA_OK(cudaMemcpyAsync(gauge_out, m->d_cap_exp, sizeof(float) * (size_t)total, cudaMemcpyDeviceToHost, m->stream));
+    }
+    if (!async) CUDA_OK(cudaStreamSynchronize(m->stream));
+  }
+  CUDA_OK(cudaGetLastError());
+  return WF_OK;
+}
+
 int wf_synchronize(wf_model *m) {
   if (!m) return fail(WF_EINVAL, "null model");
   CUDA_OK(cudaSetDevice(m->cfg.device));
@@ -1034,6 +1318,7 @@ int wf_timing_reset(wf_model *m) {
     m->tev.push_back(e);
   }
   m->tev_used = 0;
+  m->tev_extra_steps = 0;
   return WF_OK;
 }
 
@@ -1048,7 +1333,7 @@ int wf_timing_get(wf_model *m, double ms[3], int64_t *nsteps) {
     CUDA_OK(cudaEventElapsedTime(&b, m->tev[i + 1], m->tev[i + 2]));
     ms[0] += a; ms[1] += b; ms[2] += a + b;
   }
-  if (nsteps) *nsteps = (int64_t)(m->tev_used / 3);
+  if (nsteps) *nsteps = (int64_t)(m->tev_used / 3) + m->tev_extra_steps;
   return WF_OK;
 }
 

@@ -554,7 +554,7 @@ __device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i
 // ---- task 3: one sub-step of the river kinematic wave for one river cell (river order) -------
 // kin_wave, wflow/wflow_funcs.py:155-207; caller glue wflow_sbm.py:3152-3201.
 template <int MODE>
-__device__ __forceinline__ void task_river(const DevModel &m, const int32_t rs, const int v, const RivOps &o WF_PARGS) {
+__device__ __forceinline__ void task_river(const DevModel &m, const int32_t rs, const int v, const RivOps &o, const int step WF_PARGS) {
   const int itR = m.itR;
   const int nup = o.nup;
   const uint32_t us = o.us;
@@ -589,7 +589,12 @@ __device__ __forceinline__ void task_river(const DevModel &m, const int32_t rs, 
   const double racc = racc0 + qn * dtr, rh = rh0 + wl;
   qbuf[rs] = (float)qn;
   if (v == itR - 1) {
-    m.f[F_RiverRunoff][rs] = (float)qdiv(racc, m.dt);
+    const float rr = (float)qdiv(racc, m.dt);
+    m.f[F_RiverRunoff][rs] = rr;
+    if (m.cap_slot) {  // pipelined sweep: the step's discharge at a gauge, before the next step overwrites it
+      const int32_t g = __ldg(m.cap_slot + rs);
+      if (g >= 0) m.cap_out[(int64_t)step * m.cap_n + g] = rr;
+    }
     m.f[F_WaterLevelR][rs] = (float)qdiv(rh, (double)itR);
     m.f[F_WaterLevelRsub][rs] = (float)wl;
   } else {
@@ -769,7 +774,7 @@ __device__ __forceinline__ void sweep_group(const DevModel &m, const GroupDesc g
         task_overland<MODE>(m, (int64_t)it.idx, ovl WF_PPASS(1));
       } else if (it.type == 2) {
         if (!first || !PRELOAD_SMALL) load_riv(m, (int32_t)it.idx, riv);
-        task_river<MODE>(m, (int32_t)it.idx, it.v, riv WF_PPASS(2));
+        task_river<MODE>(m, (int32_t)it.idx, it.v, riv, 0 WF_PPASS(2));
       }
     }
     if (t + 1 < nticks) {
