@@ -26,6 +26,9 @@ CASES = [
     ("cta", (40, 40), 12, dict(kind="forest", layer_thickness=(100, 300), snow=0, itL=2, itR=2, dt=21600)),
     ("cluster", (64, 64), 5, dict(kind="tiles", tile=32, layer_thickness=(100, 300, 800), glacier=1, mask_frac=0.1)),
     ("grid", (32, 32), 40, dict(kind="tiles", tile=32, layer_thickness=(100, 300, 800), dt=3600, itR=4)),  # more steps than levels
+    # one basin under a single-block / cluster plan: the pipelined launch sweeps it with the whole grid
+    ("cta", (32, 32), 9, dict(kind="tiles", tile=32, layer_thickness=(100, 300, 800), dt=3600, itR=4)),
+    ("cluster", (32, 32), 9, dict(kind="tiles", tile=32, layer_thickness=(100, 300), dt=3600, itL=2, itR=2)),
 ]
 
 

@@ -471,28 +471,39 @@ __global__ void k_expand_capture(const float *__restrict__ cap, const int32_t *_
   out[k] = (c >= 0) ? cap[s * cap_n + c] : ((pos[g] >= 0) ? 0.0f : mv);
 }
 
+// Which sweep runs the pipelined launch.  With several groups it is the per-step plan's (the storage layout
+// is built for it).  A single group (one basin, or a network swept as a whole) has the same layout under
+// every plan, and the pipelined sweep wants throughput, not a short barrier: the cooperative grid sweep
+// over all SMs, whatever the per-step plan chose (a Rhine-sized basin is a single-block sweep there).
+static int pipeline_mode(const wf_model *m) { return (m->dm.ngroups == 1) ? WF_GRID : m->lat_mode; }
+
 template <int ML>
-int launch_pipeline(wf_model *m, const DevModel &dmp, const PipeArgs &pa) {
+int launch_pipeline(wf_model *m, DevModel &dmp, const PipeArgs &pa) {
   void *args[] = {(void *)&dmp, (void *)&pa};
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (m->lat_mode == WF_GRID) {
+  const int pmode = pipeline_mode(m);
+  if (pmode == WF_GRID) {
     void *fn = (void *)k_pipeline<ML, WF_GRID>;
+    // level offsets of the one group in shared memory when they fit beside three blocks per SM
+    const size_t entries = (size_t)(m->dm.nlev + 1) + (size_t)(m->dm.nrlev + 1);
+    const size_t smem = (entries * 4 <= 40 * 1024) ? entries * 4 : 0;
+    dmp.lev_cache = smem ? (int32_t)entries : 0;
     if (m->pipe_blocks == 0) {
       int per_sm = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pipeline<ML, WF_GRID>, wf_pipe_threads(WF_GRID), m->lat_smem);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pipeline<ML, WF_GRID>, wf_pipe_threads(WF_GRID), smem);
       if (per_sm < 1) return fail(WF_ENODEVICE, "k_pipeline does not fit on an SM");
       m->pipe_blocks = sms * per_sm;
     }
     CUDA_OK(cudaMemsetAsync(m->dm.grid_counter, 0, sizeof(unsigned int), m->stream));
-    CUDA_OK(cudaLaunchCooperativeKernel(fn, dim3((unsigned)m->pipe_blocks), dim3((unsigned)wf_pipe_threads(WF_GRID)), args, m->lat_smem,
+    CUDA_OK(cudaLaunchCooperativeKernel(fn, dim3((unsigned)m->pipe_blocks), dim3((unsigned)wf_pipe_threads(WF_GRID)), args, smem,
                                         m->stream));
     return WF_OK;
   }
-  const bool cta = m->lat_mode == WF_CTA;
+  const bool cta = pmode == WF_CTA;
   void *fn = cta ? (void *)k_pipeline<ML, WF_CTA> : (void *)k_pipeline<ML, WF_CLUSTER>;
-  const int threads = cta ? wf_pipe_threads(WF_CTA) : wf_block_threads(m->lat_mode);
+  const int threads = cta ? wf_pipe_threads(WF_CTA) : wf_block_threads(pmode);
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3((unsigned)threads);
   cfg.dynamicSmemBytes = m->lat_smem;

@@ -13,7 +13,7 @@
 // at tick t the kernel runs, for every step s in flight (tau = t - s*lag),
 //     the column of level tau, subsurface flow of level tau-1, overland flow of level tau-2 and
 //     river sub-step v of level tau-3-v,
-// all in one flat item space, one barrier per tick.  K steps cost D + 2 + it_kinR + (K-1)*lag ticks
+// all in one flat item space (type-major, see pipe_group), one barrier per tick.  K steps cost D + 2 + it_kinR + (K-1)*lag ticks
 // instead of K*(D + 1 + it_kinR): the Rhine case advances 29 days in 470 ticks instead of 7 800, and
 // on wide networks a tick carries the work of ~D/lag steps, so the sweep is bound by instruction
 // throughput like the column kernel, not by barrier + solve latency.
@@ -45,7 +45,10 @@ namespace wf {
 __host__ __device__ constexpr int wf_pipe_threads(int mode) {
   return mode == WF_GRID ? 256 : (mode == WF_CTA ? WF_GROUP_THREADS : WF_GROUP_THREADS_WIDE);
 }
-__host__ __device__ constexpr int wf_pipe_minblocks(int mode) { return mode == WF_GRID ? 3 : 1; }
+#ifndef WF_PIPE_GRID_MINBLOCKS
+#define WF_PIPE_GRID_MINBLOCKS 3
+#endif
+__host__ __device__ constexpr int wf_pipe_minblocks(int mode) { return mode == WF_GRID ? WF_PIPE_GRID_MINBLOCKS : 1; }
 
 struct PipeArgs {
   int32_t nsteps;   // timesteps of this launch
@@ -53,38 +56,41 @@ struct PipeArgs {
   int64_t fstride;  // elements between the forcing rasters of consecutive steps
 };
 
-// item j of the lateral part of local tick t (the item space of lateral.cuh's sweep_group)
-__device__ __forceinline__ WaveItem decode_lateral(int j, const int t, const uint32_t *lo, const uint32_t *ro, const int nl,
-                                                   const int nrl, const int q0, const int itR) {
+// river item j of local lateral tick t: sub-step v = 0 .. itR-1 works on river level q0 + t - v
+__device__ __forceinline__ WaveItem decode_river(int jj, const int t, const uint32_t *ro, const int nrl, const int q0,
+                                                 const int itR) {
   WaveItem it;
   it.type = -1; it.idx = 0; it.v = 0;
-  int cnt0 = 0, cnt1 = 0;
-  if (t < nl) cnt0 = (int)(lo[t + 1] - lo[t]);
-  if (t >= 1 && t - 1 < nl) cnt1 = (int)(lo[t] - lo[t - 1]);
-  const int c0p = (cnt0 + 31) & ~31, c1p = (cnt1 + 31) & ~31;
-  if (j < c0p) {
-    if (j < cnt0) { it.type = 0; it.idx = lo[t] + (uint32_t)j; }
-  } else if (j < c0p + c1p) {
-    if (j - c0p < cnt1) { it.type = 1; it.idx = lo[t - 1] + (uint32_t)(j - c0p); }
-  } else if (nrl > 0) {
-    int jj = j - c0p - c1p;
 #pragma unroll 1
-    for (int v = 0; v < itR; v++) {
-      const int q = q0 + t - v;
-      if (q < 0 || q >= nrl) continue;
-      const uint32_t rb = ro[q];
-      const int rc = (int)(ro[q + 1] - rb);
-      if (jj < rc) { it.type = 2; it.v = v; it.idx = rb + (uint32_t)jj; break; }
-      jj -= rc;
-    }
+  for (int v = 0; v < itR; v++) {
+    const int q = q0 + t - v;
+    if (q < 0 || q >= nrl) continue;
+    const uint32_t rb = ro[q];
+    const int rc = (int)(ro[q + 1] - rb);
+    if (jj < rc) { it.type = 2; it.v = v; it.idx = rb + (uint32_t)jj; break; }
+    jj -= rc;
   }
   return it;
 }
+__device__ __forceinline__ int river_items(const int t, const uint32_t *ro, const int nrl, const int q0, const int itR) {
+  int n = 0;
+#pragma unroll 1
+  for (int v = 0; v < itR; v++) {
+    const int q = q0 + t - v;
+    if (q >= 0 && q < nrl) n += (int)(ro[q + 1] - ro[q]);
+  }
+  return n;
+}
 
+// One group's pipelined sweep.  The item space of a tick is laid out TYPE-major over the steps in flight,
+//     [columns of every step | subsurface of every step | overland of every step | river of every step],
+// every (type, step) segment starting on a warp boundary, and thread k takes items k, k + nthreads, ...:
+// every thread gets its share of each task type (a step-major layout whose period is close to the thread
+// count hands some threads nothing but columns, four times the work of a river cell, and the tick waits
+// for them), and at any moment most warps of an SM run the same task's code.
 template <int ML, int MODE>
 __device__ __forceinline__ void pipe_group(const DevModel &m, const PipeArgs pa, const GroupDesc gd, const uint32_t *lo,
-                                           const uint32_t *ro, const uint32_t *tt, const int tid, const int nthreads,
-                                           WaveSync &ws) {
+                                           const uint32_t *ro, const int tid, const int nthreads, WaveSync &ws) {
   const int itR = m.itR;
   const int nl = m.nlev - gd.lev0;                                      // levels of the group
   const int nrl = (gd.rlev0 < m.nrlev) ? m.nrlev - gd.rlev0 : 0;        // river levels of the group
@@ -96,40 +102,66 @@ __device__ __forceinline__ void pipe_group(const DevModel &m, const PipeArgs pa,
   OvlOps ovl;
   RivOps riv;
   for (int t = 0; t < total; t++) {
-    // steps in flight: 0 <= t - s*lag < nt1
+    // steps in flight: 0 <= tau = t - s*lag < nt1
     int s_hi = t / lag;
     if (s_hi > pa.nsteps - 1) s_hi = pa.nsteps - 1;
     int s_lo = t - nt1 + 1;
     s_lo = (s_lo <= 0) ? 0 : (s_lo + lag - 1) / lag;
-    int base = 0;  // items of the steps already laid out in this tick, modulo the thread count
-    for (int s = s_lo; s <= s_hi; s++) {
-      const int tau = t - s * lag;
-      int cntV = 0;
-      uint32_t v0 = 0;
-      if (tau < nl) { v0 = lo[tau]; cntV = (int)(lo[tau + 1] - v0); }
-      const int cVp = (cntV + 31) & ~31;  // every task type starts on a warp boundary
-      const int cntL = (tau >= 1) ? (int)tt[tau - 1] : 0;
-      const int cnt = cVp + ((cntL + 31) & ~31);
+    int base = 0;  // items laid out so far in this tick, modulo the thread count
+    // first item of this thread in a segment that starts at `base`; advances base past the segment
+    auto first_item = [&](const int cnt) -> int {
       int j = tid - base;
       if (j < 0) j += nthreads;
-      for (; j < cnt; j += nthreads) {
-        if (j < cVp) {
-          if (j < cntV) column_cell<ML, 1>(m, (int64_t)v0 + j, nullptr, nullptr, 0, (int64_t)s * pa.fstride);
-          continue;
-        }
-        const WaveItem it = decode_lateral(j - cVp, tau - 1, lo, ro, nl, nrl, q0, itR);
-        if (it.type == 0) {
-          load_sub<ML>(m, (int64_t)it.idx, sub);
-          task_subsurface<ML, MODE>(m, (int64_t)it.idx, sub WF_PNONE);
-        } else if (it.type == 1) {
-          load_ovl(m, (int64_t)it.idx, ovl);
-          task_overland<MODE>(m, (int64_t)it.idx, ovl WF_PNONE);
-        } else if (it.type == 2) {
-          load_riv(m, (int32_t)it.idx, riv);
-          task_river<MODE>(m, (int32_t)it.idx, it.v, riv, s WF_PNONE);
+      base += (cnt + 31) & ~31;
+      if (base >= nthreads) base %= nthreads;
+      return j;
+    };
+    // columns: level tau
+    for (int s = s_lo; s <= s_hi; s++) {
+      const int lev = t - s * lag;
+      if (lev >= nl) continue;
+      const uint32_t b0 = lo[lev];
+      const int cnt = (int)(lo[lev + 1] - b0);
+      for (int j = first_item(cnt); j < cnt; j += nthreads)
+        column_cell<ML, 1>(m, (int64_t)b0 + j, nullptr, nullptr, 0, (int64_t)s * pa.fstride);
+    }
+    // subsurface flow: level tau - 1
+    for (int s = s_lo; s <= s_hi; s++) {
+      const int lev = t - s * lag - 1;
+      if (lev < 0 || lev >= nl) continue;
+      const uint32_t b0 = lo[lev];
+      const int cnt = (int)(lo[lev + 1] - b0);
+      for (int j = first_item(cnt); j < cnt; j += nthreads) {
+        load_sub<ML>(m, (int64_t)b0 + j, sub);
+        task_subsurface<ML, MODE>(m, (int64_t)b0 + j, sub WF_PNONE);
+      }
+    }
+    // overland flow: level tau - 2
+    for (int s = s_lo; s <= s_hi; s++) {
+      const int lev = t - s * lag - 2;
+      if (lev < 0 || lev >= nl) continue;
+      const uint32_t b0 = lo[lev];
+      const int cnt = (int)(lo[lev + 1] - b0);
+      for (int j = first_item(cnt); j < cnt; j += nthreads) {
+        load_ovl(m, (int64_t)b0 + j, ovl);
+        task_overland<MODE>(m, (int64_t)b0 + j, ovl WF_PNONE);
+      }
+    }
+    // river: sub-step v on river level q0 + (tau - 1) - v
+    if (nrl > 0) {
+      for (int s = s_lo; s <= s_hi; s++) {
+        const int tl = t - s * lag - 1;
+        if (tl < 0) continue;
+        const int cnt = river_items(tl, ro, nrl, q0, itR);
+        if (cnt == 0) continue;
+        for (int j = first_item(cnt); j < cnt; j += nthreads) {
+          const WaveItem it = decode_river(j, tl, ro, nrl, q0, itR);
+          if (it.type == 2) {
+            load_riv(m, (int32_t)it.idx, riv);
+            task_river<MODE>(m, (int32_t)it.idx, it.v, riv, s WF_PNONE);
+          }
         }
       }
-      base = (base + cnt) % nthreads;
     }
     if (t + 1 < total) {
       wave_arrive<MODE>(ws);
@@ -159,18 +191,16 @@ __global__ void __launch_bounds__(wf_pipe_threads(MODE), wf_pipe_minblocks(MODE)
     const GroupDesc gd = m.groups[g];
     const int nlo = m.nlev - gd.lev0 + 1;
     const int nro = (gd.rlev0 < m.nrlev) ? m.nrlev - gd.rlev0 + 1 : 0;
-    const uint32_t *lo = m.lev_off + gd.lev_idx, *ro = m.rlev_off + gd.rlev_idx, *tt = m.tick_total + gd.tick_idx;
-    if (nlo + nro + gd.nticks <= m.lev_cache) {  // level offsets and tick sizes of the group into shared memory
+    const uint32_t *lo = m.lev_off + gd.lev_idx, *ro = m.rlev_off + gd.rlev_idx;
+    if (nlo + nro <= m.lev_cache) {  // level offsets of the group into shared memory
       __syncthreads();
       for (int k = threadIdx.x; k < nlo; k += blockDim.x) s_lev[k] = lo[k];
       for (int k = threadIdx.x; k < nro; k += blockDim.x) s_lev[nlo + k] = ro[k];
-      for (int k = threadIdx.x; k < gd.nticks; k += blockDim.x) s_lev[nlo + nro + k] = tt[k];
       __syncthreads();
       lo = s_lev;
       ro = s_lev + nlo;
-      tt = s_lev + nlo + nro;
     }
-    pipe_group<ML, MODE>(m, pa, gd, lo, ro, tt, tid, nthreads, ws);
+    pipe_group<ML, MODE>(m, pa, gd, lo, ro, tid, nthreads, ws);
     if (MODE == WF_GRID) break;
   }
 }
