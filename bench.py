@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--timestepsecs", type=int, default=3600)
     ap.add_argument("--cpu-sample-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-single-basin", action="store_true", help="skip the auxiliary single-basin per-step / pipelined measurement")
     return ap.parse_args()
 
 
@@ -191,6 +192,53 @@ def workload_config(args, it_l, it_r, **extra):
            "l2": "inputs larger than L2 (per-step working set >> 126 MB), no flush needed"}
     cfg.update(extra)
     return cfg
+
+
+def single_basin_pipelined(args, local, steps_per_launch=50):
+    """Auxiliary measurement (not the headline): ONE basin tile of the workload -- the regime of a typical
+    single-catchment model, where a per-step sweep leaves most of the GPU idle -- stepped one timestep per
+    launch and `steps_per_launch` timesteps per launch (wf_step_pipelined: step s+1 trails step s down the
+    network inside one kernel; bit-identical results, tests/test_gpu_pipeline.py)."""
+    import torch
+    from wflow_b200 import core, synth
+    n = args.tile
+    ldd, river, sched, static, state, lt = make_model_inputs(args, 0, n, n, core.Schedule)
+    it_l, it_r = it_substeps(args)
+    mod = core.SbmModel(ldd, river, schedule=sched, timestepsecs=args.timestepsecs, layer_thickness=lt, model_snow=1,
+                        it_kin_l=it_l, it_kin_r=it_r, device=local)
+    for k, v in {**static, **state}.items():
+        if k not in ("River", "Beta", "SatWaterDepth"):
+            mod.set(k, v)
+    forc = synth.Forcing(n, n, seed=5, timestepsecs=args.timestepsecs, rain_mean=20.0)
+    trips = [forc.step(f) for f in range(4)]
+    K = steps_per_launch
+    mod.pipeline_reserve(K)
+    for s in range(K):
+        for name, a in zip(("P", "PET", "TEMP"), trips[s % 4]):
+            mod.pipeline_set_forcing(name, s, a)
+    for name, a in zip(("P", "PET", "TEMP"), trips[0]):
+        mod.set(name, a)
+    stream = torch.cuda.ExternalStream(mod.stream)
+    mod.step(3)
+    mod.step_pipelined(K)
+    mod.synchronize()
+
+    def timed(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        fn()
+        e1.record(stream)
+        mod.synchronize()
+        return e0.elapsed_time(e1)
+    ms_step = timed(lambda: mod.step(10)) / 10
+    ms_pipe = timed(lambda: mod.step_pipelined(K)) / K
+    cells = mod.num_cells
+    out = {"workload": "one %dx%d basin of the same workload (%d cells, %d levels)" % (n, n, cells, mod.num_levels),
+           "per_step": {"ms_per_step": ms_step, "value": cells / ms_step * 1e3},
+           "pipelined": {"steps_per_launch": K, "ms_per_step": ms_pipe, "value": cells / ms_pipe * 1e3},
+           "unit": "cell-timesteps/s"}
+    mod.close()
+    return out
 
 
 def run_b200(args):
@@ -352,6 +400,11 @@ def run_b200(args):
                 line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
             except Exception as ex:  # the checker must never take the product number down with it
                 line["cpu_baseline"] = {"error": repr(ex)}
+        if world == 1 and not args.no_single_basin:
+            try:
+                line["single_basin"] = single_basin_pipelined(args, local)
+            except Exception as ex:  # auxiliary: never takes the headline down
+                line["single_basin"] = {"error": repr(ex)}
         print(json.dumps(line), flush=True)
     mod.close()
     if world > 1:
