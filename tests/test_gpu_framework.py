@@ -67,6 +67,30 @@ def test_suspend_resume_continues_identically(case):
     c._wf_shutdown()
 
 
+def test_run_pipelined_matches_the_time_loop(case):
+    """WflowSbm.run_pipelined (several timesteps per launch, forcing read ahead from the map stacks) leaves the
+    states of _runDynamic's time loop (wf_DynamicFramework.py:2968-3042), bit for bit, and returns the discharge
+    the loop would have sampled at the gauges after every step."""
+    from wflow_b200.framework import WflowSbm
+    a = WflowSbm(Dir=case, RunDir="runA"); a.createRunId(); a._runInitial(); a._runResume()
+    gauges = np.flatnonzero(a.OutputLoc.ravel() > 0)
+    assert gauges.size > 0
+    want = []
+    for ts in range(1, 7):
+        a._runDynamic(ts, ts)
+        want.append(a._mod.sample("RiverRunoff", gauges))
+    names = ("zi", "SubsurfaceFlow", "RiverRunoff", "LandRunoff", "UStoreLayerDepth_1", "Snow", "CanopyStorage")
+    ref = {k: a._mod.get(k) for k in names}
+    a._wf_shutdown()
+    b = WflowSbm(Dir=case, RunDir="runB"); b.createRunId(); b._runInitial(); b._runResume()
+    got = b.run_pipelined(1, 6, chunk=4)  # two launches: 4 + 2 steps
+    assert b.currentTimeStep() == 6
+    np.testing.assert_array_equal(got, np.asarray(want, np.float32))
+    for k, v in ref.items():
+        np.testing.assert_array_equal(b._mod.get(k), v, err_msg=k)
+    b._wf_shutdown()
+
+
 def test_bmi_contract(case):
     from wflow_b200.bmi import wflowbmi_csdms
     bmi = wflowbmi_csdms()

@@ -396,6 +396,40 @@ class WflowSbm:
             self._mod.step()
             self._write_outputs(step)
 
+    def run_pipelined(self, firststep=None, laststep=None, gauges=None, chunk=64):
+        """Extension without a counterpart in the reference: the same timesteps as _runDynamic, but `chunk`
+        of them per kernel launch, timestep s+1 following s down the drainage network (SbmModel.step_pipelined;
+        bit-identical states).  The forcing of a chunk is read ahead from the map stacks.  Per-step outputs
+        other than the river discharge cannot leave a pipelined launch, so [outputcsv] / [outputtss] /
+        [outputmaps] are NOT written; returns RiverRunoff [steps, gauges] at `gauges` (flat cell indices;
+        default: the cells of the gauges map), each row what _runDynamic would have sampled after that step.
+        Needs fixed kinematic-wave sub-steps (kinwaveIters = 0, or kinwaveRiverTstep / kinwaveLandTstep set)."""
+        if self._estimate_l or self._estimate_r:
+            raise ValueError("run_pipelined needs fixed kinematic-wave sub-steps (they are re-estimated per step otherwise)")
+        first = max(int(firststep), 1) if firststep else self._currentTimeStep + 1
+        last = int(laststep) if laststep else self.nrTimeSteps
+        if gauges is None:
+            g = getattr(self, "OutputLoc", None)
+            gauges = np.flatnonzero(np.asarray(g).ravel() > 0) if g is not None else np.zeros(0, np.int64)
+        gauges = np.ascontiguousarray(gauges, dtype=np.int64)
+        handle = self._mod.gauges_create(gauges)
+        chunk = max(1, min(int(chunk), last - first + 1))
+        self._mod.pipeline_reserve(chunk)
+        self._mod.pipeline_capture(handle)
+        rows = []
+        for lo in range(first, last + 1, chunk):
+            hi = min(lo + chunk - 1, last)
+            for step in range(lo, hi + 1):
+                self._mod.pipeline_set_forcing("P", step - lo, self._forcing("P", "Precipitation", "/inmaps/P", step, 0.0))
+                self._mod.pipeline_set_forcing("PET", step - lo, self._forcing("PET", "EvapoTranspiration", "/inmaps/PET", step, 0.0))
+                if self.modelSnow:
+                    self._mod.pipeline_set_forcing("TEMP", step - lo, self._forcing("TEMP", "Temperature", "/inmaps/TEMP", step, 10.0))
+            out = np.zeros((hi - lo + 1, max(gauges.size, 1)), F32)
+            self._mod.step_pipelined(hi - lo + 1, out, mv=MV)
+            rows.append(out[:, : gauges.size])
+            self._currentTimeStep = hi
+        return np.concatenate(rows, axis=0) if rows else np.zeros((0, gauges.size), F32)
+
     def currentTimeStep(self):
         return self._currentTimeStep
 
