@@ -69,7 +69,7 @@ __device__ __forceinline__ double carried_pow(double Qold, double q64, double qb
   if (Qold == 0.0 && beta > 0.0) return 0.0;
   if (q64 > 0.0 && (float)q64 == (float)Qold) {
     const double d = (Qold - q64) * qrcp(q64);
-    return qb64 * (1.0 + d * (beta + d * (0.5 * beta * (beta - 1.0))));
+    return qb64 * fma(d, fma(d, 0.5 * beta * (beta - 1.0), beta), 1.0);  // (series of this file: explicit FMAs)
   }
   return pow_el(Qold, beta);
 }
@@ -132,7 +132,7 @@ __device__ __noinline__ double kinematic_wave(double Qin, double Qold, double Qo
     const double d = (Qn - Qkx) * rQ;
     const double ad = fabs(d);
     // Q^beta at the new iterate
-    if (ad < 1e-3) qb = qb * (1.0 + d * (beta + d * (t2 + d * t3)));
+    if (ad < 1e-3) qb = qb * fma(d, fma(d, fma(d, t3, t2), beta), 1.0);
     else qb = pow_el(Qn, beta);
     Qkx = Qn;
     // Newton on this concave f converges quadratically, relative error after a step ~ 0.2 * (step)^2:
@@ -187,7 +187,7 @@ __device__ __noinline__ void kinematic_wave_ssf(double ssf_in, double ssf_old, d
       // e^u follows a small step by its series (|du| < 1/64: truncation below 1e-19)
       const double t = -du;
       if (fabs(du) < 0.015625)
-        e = e * (1.0 + t * (1.0 + t * (0.5 + t * (1.0 / 6 + t * (1.0 / 24 + t * (1.0 / 120 + t * (1.0 / 720 + t * (1.0 / 5040))))))));
+        e = e * fma(t, fma(t, fma(t, fma(t, fma(t, fma(t, fma(t, 1.0 / 5040, 1.0 / 720), 1.0 / 120), 1.0 / 24), 1.0 / 6), 0.5), 1.0), 1.0);
       else
         e = wf_exp(u);
       if (!(fabs(du) > 1e-10)) break;
@@ -216,7 +216,7 @@ __device__ __noinline__ void kinematic_wave_ssf(double ssf_in, double ssf_old, d
     // log of the next iterate's x from this one's: log1p(d) by its series for a small relative step
     const double xn = sn * fden + efD;
     const double d = qdiv(xn - x, x);
-    if (fabs(d) < 1e-4) lx = lx + d * (1.0 + d * (-0.5 + d * (1.0 / 3 - 0.25 * d)));
+    if (fabs(d) < 1e-4) lx = fma(d, fma(d, fma(d, fma(d, -0.25, 1.0 / 3), -0.5), 1.0), lx);
     else lx = wf_log(xn);
     x = xn;
   }
