@@ -30,9 +30,9 @@ sys.path.insert(0, ROOT)
 BYTES_VERTICAL = 236  # algorithmic bytes per cell-step of the vertical kernel, 4 layers, snow on
 BYTES_FULL = 333      # full step incl. lateral statics, routing states and topology
 # DRAM traffic of one k_vertical launch per cell, from the round's `ncu --set full` capture of the default
-# workload (profiles/r1_vertical_ncu_details.txt: dram__bytes_read.sum + dram__bytes_write.sum = 13.52 GB for
+# workload (profiles/r1_vertical_ncu_details.txt: dram__bytes_read.sum + dram__bytes_write.sum = 13.62 GB for
 # 33 554 431 cells).  Above the algorithmic 236 B: float64 hand-offs, derived statics, register spills.
-TRAFFIC_VERTICAL_PER_CELL = 403.0
+TRAFFIC_VERTICAL_PER_CELL = 405.8
 
 
 def parse():

@@ -96,9 +96,10 @@ __device__ __noinline__ double kinematic_wave(double Qin, double Qold, double Qo
   const float a32 = (float)alpha, b32 = (float)beta, dtx32 = (float)deltaTX;
   const float qin32 = (float)Qin, qold32 = (float)Qold, lat32 = (float)(deltaT * q);
   // (this phase only has to land within ~1e-5 of the root: hardware exp2/log2 and fast division)
-  const float C32 = dtx32 * qin32 + a32 * pow_fast(qold32, b32) + lat32;
+  // (own iteration from here to the float64 Newton loop's end: explicit FMAs, it converges to the same root)
+  const float C32 = fmaf(dtx32, qin32, fmaf(a32, pow_fast(qold32, b32), lat32));
   const float ab_pQ = a32 * b32 * pow_fast((qold32 + qin32) * 0.5f, b32 - 1.0f);
-  float Qf = __fdividef(dtx32 * qin32 + qold32 * ab_pQ + lat32, dtx32 + ab_pQ);
+  float Qf = __fdividef(fmaf(dtx32, qin32, fmaf(qold32, ab_pQ, lat32)), dtx32 + ab_pQ);
   if (isnan(Qf)) Qf = 0.0f;
   {
     // The root lies in (ub/4, ub], ub = min(C/dtx, (C/alpha)^(1/beta)) (each term alone reaches C at its
@@ -111,8 +112,8 @@ __device__ __noinline__ double kinematic_wave(double Qin, double Qold, double Qo
 #pragma unroll 1
   for (int it = 0; it < 12; it++) {
     const float qb = pow_fast(Qf, b32);
-    const float f = dtx32 * Qf + a32 * qb - C32;
-    const float df = dtx32 + a32 * b32 * __fdividef(qb, Qf);
+    const float f = fmaf(dtx32, Qf, fmaf(a32, qb, -C32));
+    const float df = fmaf(a32 * b32, __fdividef(qb, Qf), dtx32);
     const float Qn = fmaxf(Qf - __fdividef(f, df), 1e-30f);
     const bool done = fabsf(Qn - Qf) <= 1e-5f * Qn;
     Qf = Qn;
@@ -125,9 +126,9 @@ __device__ __noinline__ double kinematic_wave(double Qin, double Qold, double Qo
 #pragma unroll 1
   for (int it = 0; it < 60; it++) {
     const double rQ = qrcp(Qkx);
-    const double f = deltaTX * Qkx + alpha * qb - C;
+    const double f = fma(deltaTX, Qkx, fma(alpha, qb, -C));
     const double dqb = beta * (qb * rQ);  // d(Q^beta)/dQ
-    const double df = deltaTX + alpha * dqb;
+    const double df = fma(alpha, dqb, deltaTX);
     const double Qn = fmax(Qkx - qdiv(f, df), 1e-30);
     const double d = (Qn - Qkx) * rQ;
     const double ad = fabs(d);
@@ -180,9 +181,10 @@ __device__ __noinline__ void kinematic_wave_ssf(double ssf_in, double ssf_old, d
     double e = wf_exp(u);
 #pragma unroll 1
     for (int k = 0; k < 4; k++) {
-      const double Fu = A * e + B * u + C0;
-      const double d1 = A * e + B, d2 = A * e;
-      const double du = qdiv(2.0 * Fu * d1, 2.0 * d1 * d1 - Fu * d2);
+      const double d2 = A * e;  // (own first-guess iteration: explicit FMAs)
+      const double Fu = fma(B, u, d2 + C0);
+      const double d1 = d2 + B;
+      const double du = qdiv(2.0 * Fu * d1, fma(2.0 * d1, d1, -Fu * d2));
       u = u - du;
       // e^u follows a small step by its series (|du| < 1/64: truncation below 1e-19)
       const double t = -du;
