@@ -157,7 +157,7 @@ int wf_synchronize(wf_model *m);
  *   wf_pipeline_capture      gauge set (wf_gauges_create; -1 = none) at which every step's RiverRunoff is
  *                            kept -- the one output a step must hand over before the next overwrites it
  *                            (wf_OutputTimeSeriesArea's sampled discharge, wf_DynamicFramework.py:446-499)
- *   wf_step_pipelined        runs `nsteps` steps; gauge_out (may be NULL) receives [nsteps][gauges] values
+ *   wf_step_pipelined        runs `nsteps` (<= 64) steps; gauge_out (may be NULL) receives [nsteps][gauges] values
  *                            (0 at network cells outside the river, mv outside the network); async != 0
  *                            returns without waiting (pinned gauge_out, valid after wf_synchronize).
  * All other fields hold, after the call, what they hold after the last of the steps. */

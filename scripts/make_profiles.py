@@ -73,11 +73,18 @@ if __name__ == "__main__":
     details(rep, "k_lateral_wave", "r1_lateral_ncu_details.txt",
             "# ncu --set full --clock-control none --import-source on, one launch of k_lateral_wave (round 1, default bench workload: "
             "32 basins of 1024^2 = 33.5 M cells)\n# command: %s ; report read with: ncu -i prof_r1_final.ncu-rep --page details" % cmd)
-    pipe = os.path.join(G, "prof_pipe_grid.ncu-rep")
+    pipe = os.path.join(G, "prof_pipe_full2.ncu-rep")
     if os.path.isfile(pipe):
         details(pipe, "k_pipeline", "r1_pipeline_ncu_details.txt",
-                "# ncu --set full --clock-control none --import-source on, one launch of k_pipeline (round 1): 8 timesteps in one launch, "
-                "8 basins of 1024^2 swept as one group by the cooperative grid kernel (type-major item space)\n"
+                "# ncu --set full --clock-control none --import-source on, one launch of k_pipeline (round 1): 20 timesteps in one launch, "
+                "the default bench shard (32 basins of 1024^2 = 33.5 M cells) swept as one group by the cooperative grid kernel,\n"
+                "# chunks dealt on demand inside a block; development build with 1024 threads per block (64 registers; the default is 768 / 80)\n"
+                "# command: python scripts/pipe_bench.py --basins 32 --modes grid+lib:libwflowsbm_pfh.so --ks 20")
+    old = os.path.join(G, "prof_pipe_grid.ncu-rep")
+    if os.path.isfile(old):
+        details(old, "k_pipeline", "r1_pipeline_static_ncu_details.txt",
+                "# ncu --set full, one launch of k_pipeline BEFORE chunks were dealt on demand (fixed item -> thread map, 3 blocks of 256 threads "
+                "per SM): 8 timesteps, 8 basins of 1024^2; 57 % of the stall cycles at the block barrier ahead of the grid barrier\n"
                 "# command: python scripts/pipe_bench.py --basins 8 --modes grid --ks 8")
     launches(os.path.join(G, "launches_r1.csv"), "r1_launches_ncu.csv",
              "# ncu launch list (round 1): %s  (32 basins of 1024^2, default workload)\n"

@@ -66,12 +66,15 @@ def main():
         mod.synchronize()
         ncell = mod.num_cells
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        mod.timing_reset()
         e0.record(stream)
         mod.step(10)
         e1.record(stream)
         mod.synchronize()
         ms = e0.elapsed_time(e1) / 10
-        print("  per-step: %.3f ms/step  %.3f G cell-steps/s" % (ms, ncell / ms / 1e6), flush=True)
+        (ms_v, ms_l, _), nst = mod.timing_get()
+        print("  per-step: %.3f ms/step  %.3f G cell-steps/s  (column %.3f ms, sweep %.3f ms)"
+              % (ms, ncell / ms / 1e6, ms_v / max(nst, 1), ms_l / max(nst, 1)), flush=True)
         for K in ks:
             mod.step_pipelined(K)  # warm
             mod.synchronize()

@@ -1277,6 +1277,7 @@ int wf_step_pipelined(wf_model *m, int nsteps, float *gauge_out, float mv, int a
   if (!m) return fail(WF_EINVAL, "null model");
   if (nsteps < 1) return fail(WF_EINVAL, "nsteps must be >= 1");
   if (nsteps > m->pipe_cap) return fail(WF_EINVAL, "more steps than reserved (wf_pipeline_reserve)");
+  if (nsteps > WF_PIPE_MAX_INFLIGHT) return fail(WF_EUNSUPPORTED, "at most 64 timesteps per pipelined launch");
   if (!m->pipe_has[0] || !m->pipe_has[1]) return fail(WF_EINVAL, "pipelined forcing not set: P and PET (wf_pipeline_set_forcing)");
   if (m->cfg.model_snow && !m->pipe_has[2]) return fail(WF_EINVAL, "pipelined forcing not set: TEMP");
   if (m->dm.task_mask != 7) return fail(WF_EUNSUPPORTED, "WF_LATERAL_TASKS is a development aid of the per-step sweep");

@@ -611,7 +611,6 @@ __device__ __forceinline__ void task_river(const DevModel &m, const int32_t rs, 
 // sub-step v runs at tick level+2+v, strictly after its sub-step v-1 and before anyone reads v.
 
 // ---- the wavefront -------------------------------------------------------------------------------
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Pull the operands of the cell this thread will most likely solve next tick into L2 while the
 // current tick is still waiting at the barrier (they are cold DRAM lines otherwise: every array is

@@ -40,13 +40,17 @@ namespace wf {
 #define WF_PNONE
 #endif
 
-// block size and launch bounds of the pipelined sweep per barrier kind.  The sweep is throughput-bound,
-// so the grid sweep asks for three 256-thread blocks per SM (<= 85 registers) instead of one.
+// block size and launch bounds of the pipelined sweep per barrier kind.  The sweep is throughput-bound, so the
+// grid sweep runs ONE block of 768 threads per SM (<= 85 registers): 24 warps that share the block's chunk
+// counters (see pipe_group).
+#ifndef WF_PIPE_GRID_THREADS
+#define WF_PIPE_GRID_THREADS 768
+#endif
 __host__ __device__ constexpr int wf_pipe_threads(int mode) {
-  return mode == WF_GRID ? 256 : (mode == WF_CTA ? WF_GROUP_THREADS : WF_GROUP_THREADS_WIDE);
+  return mode == WF_GRID ? WF_PIPE_GRID_THREADS : (mode == WF_CTA ? WF_GROUP_THREADS : WF_GROUP_THREADS_WIDE);
 }
 #ifndef WF_PIPE_GRID_MINBLOCKS
-#define WF_PIPE_GRID_MINBLOCKS 3
+#define WF_PIPE_GRID_MINBLOCKS 1
 #endif
 __host__ __device__ constexpr int wf_pipe_minblocks(int mode) { return mode == WF_GRID ? WF_PIPE_GRID_MINBLOCKS : 1; }
 
@@ -84,13 +88,22 @@ __device__ __forceinline__ int river_items(const int t, const uint32_t *ro, cons
 
 // One group's pipelined sweep.  The item space of a tick is laid out TYPE-major over the steps in flight,
 //     [columns of every step | subsurface of every step | overland of every step | river of every step],
-// every (type, step) segment starting on a warp boundary, and thread k takes items k, k + nthreads, ...:
-// every thread gets its share of each task type (a step-major layout whose period is close to the thread
-// count hands some threads nothing but columns, four times the work of a river cell, and the tick waits
-// for them), and at any moment most warps of an SM run the same task's code.
+// as segments (type, step) cut into chunks of 32 consecutive items = one warp's worth.  Chunks are dealt round
+// robin to the blocks of the sweep (so every block gets its share of every task type), and INSIDE a block the
+// warps take the block's chunks of a segment from a shared-memory counter, segment after segment:
+//   * a tick ends when its slowest warp ends, and items differ widely (a column is ~4 river cells; sub-step
+//     loops are data dependent): with a fixed item -> thread map 24 % of all stall cycles of the bench shard
+//     were spent at the tick barrier; dealing chunks on demand lets the block's warps finish together;
+//   * the warps of a block move through the segments together, so at any moment an SM runs mostly ONE task's
+//     code (all four together, ~100 KB, do not fit the instruction cache: 17 % "no instruction" stalls with
+//     the fixed map).
+// Counters are double-buffered by tick parity: a tick zeroes the other parity's counters, which every warp
+// has left behind when it passed the previous tick's barrier.
+#define WF_PIPE_MAX_INFLIGHT 64
 template <int ML, int MODE>
 __device__ __forceinline__ void pipe_group(const DevModel &m, const PipeArgs pa, const GroupDesc gd, const uint32_t *lo,
-                                           const uint32_t *ro, const int tid, const int nthreads, WaveSync &ws) {
+                                           const uint32_t *ro, const int brank, const int nblocks, int (*ctr)[4 * WF_PIPE_MAX_INFLIGHT],
+                                           WaveSync &ws) {
   const int itR = m.itR;
   const int nl = m.nlev - gd.lev0;                                      // levels of the group
   const int nrl = (gd.rlev0 < m.nrlev) ? m.nrlev - gd.rlev0 : 0;        // river levels of the group
@@ -98,23 +111,36 @@ __device__ __forceinline__ void pipe_group(const DevModel &m, const PipeArgs pa,
   const int q0 = (gd.lev0 - 2) - m.rlev_shift - gd.rlev0;
   const int lag = pa.lag;
   const int total = nt1 + (pa.nsteps - 1) * lag;
+  const int lane = (int)threadIdx.x & 31;
   SubOps<ML> sub;
   OvlOps ovl;
   RivOps riv;
   for (int t = 0; t < total; t++) {
-    // steps in flight: 0 <= tau = t - s*lag < nt1
+    int *const cnt_now = ctr[t & 1];
+    {  // the next tick's counters
+      int *const cnt_next = ctr[(t + 1) & 1];
+      for (int k = (int)threadIdx.x; k < 4 * WF_PIPE_MAX_INFLIGHT; k += (int)blockDim.x) cnt_next[k] = 0;
+    }
+    // steps in flight: 0 <= tau = t - s*lag < nt1  (at most WF_PIPE_MAX_INFLIGHT, checked by the host)
     int s_hi = t / lag;
     if (s_hi > pa.nsteps - 1) s_hi = pa.nsteps - 1;
     int s_lo = t - nt1 + 1;
     s_lo = (s_lo <= 0) ? 0 : (s_lo + lag - 1) / lag;
-    int base = 0;  // items laid out so far in this tick, modulo the thread count
-    // first item of this thread in a segment that starts at `base`; advances base past the segment
-    auto first_item = [&](const int cnt) -> int {
-      int j = tid - base;
-      if (j < 0) j += nthreads;
-      base += (cnt + 31) & ~31;
-      if (base >= nthreads) base %= nthreads;
-      return j;
+    int gchunk = 0;  // chunks laid out so far in this tick, modulo the number of blocks
+    // The block's chunks of a segment of `cnt` items: c0, c0 + nblocks, ... ; a warp takes the next one.
+    // Returns the first item of the chunk taken, or -1 when the block's share of the segment is used up.
+    auto seg_begin = [&](const int cnt, int &c0) {
+      c0 = brank - gchunk;
+      if (c0 < 0) c0 += nblocks;
+      gchunk += (cnt + 31) >> 5;
+      if (gchunk >= nblocks) gchunk %= nblocks;
+    };
+    auto take = [&](int *counter, const int c0, const int cnt) -> int {
+      int k = 0;
+      if (lane == 0) k = atomicAdd(counter, 1);
+      k = __shfl_sync(0xffffffffu, k, 0);
+      const int j = ((c0 + k * nblocks) << 5) + lane;
+      return ((c0 + k * nblocks) << 5) < cnt ? j : -1;
     };
     // columns: level tau
     for (int s = s_lo; s <= s_hi; s++) {
@@ -122,8 +148,13 @@ __device__ __forceinline__ void pipe_group(const DevModel &m, const PipeArgs pa,
       if (lev >= nl) continue;
       const uint32_t b0 = lo[lev];
       const int cnt = (int)(lo[lev + 1] - b0);
-      for (int j = first_item(cnt); j < cnt; j += nthreads)
-        column_cell<ML, 1>(m, (int64_t)b0 + j, nullptr, nullptr, 0, (int64_t)s * pa.fstride);
+      int c0;
+      seg_begin(cnt, c0);
+      int *counter = cnt_now + (s - s_lo);
+      for (int j = take(counter, c0, cnt); j >= 0; j = take(counter, c0, cnt)) {
+        if (j < cnt) column_cell<ML, 1>(m, (int64_t)b0 + j, nullptr, nullptr, 0, (int64_t)s * pa.fstride);
+        __syncwarp();
+      }
     }
     // subsurface flow: level tau - 1
     for (int s = s_lo; s <= s_hi; s++) {
@@ -131,9 +162,15 @@ __device__ __forceinline__ void pipe_group(const DevModel &m, const PipeArgs pa,
       if (lev < 0 || lev >= nl) continue;
       const uint32_t b0 = lo[lev];
       const int cnt = (int)(lo[lev + 1] - b0);
-      for (int j = first_item(cnt); j < cnt; j += nthreads) {
-        load_sub<ML>(m, (int64_t)b0 + j, sub);
-        task_subsurface<ML, MODE>(m, (int64_t)b0 + j, sub WF_PNONE);
+      int c0;
+      seg_begin(cnt, c0);
+      int *counter = cnt_now + WF_PIPE_MAX_INFLIGHT + (s - s_lo);
+      for (int j = take(counter, c0, cnt); j >= 0; j = take(counter, c0, cnt)) {
+        if (j < cnt) {
+          load_sub<ML>(m, (int64_t)b0 + j, sub);
+          task_subsurface<ML, MODE>(m, (int64_t)b0 + j, sub WF_PNONE);
+        }
+        __syncwarp();
       }
     }
     // overland flow: level tau - 2
@@ -142,9 +179,15 @@ __device__ __forceinline__ void pipe_group(const DevModel &m, const PipeArgs pa,
       if (lev < 0 || lev >= nl) continue;
       const uint32_t b0 = lo[lev];
       const int cnt = (int)(lo[lev + 1] - b0);
-      for (int j = first_item(cnt); j < cnt; j += nthreads) {
-        load_ovl(m, (int64_t)b0 + j, ovl);
-        task_overland<MODE>(m, (int64_t)b0 + j, ovl WF_PNONE);
+      int c0;
+      seg_begin(cnt, c0);
+      int *counter = cnt_now + 2 * WF_PIPE_MAX_INFLIGHT + (s - s_lo);
+      for (int j = take(counter, c0, cnt); j >= 0; j = take(counter, c0, cnt)) {
+        if (j < cnt) {
+          load_ovl(m, (int64_t)b0 + j, ovl);
+          task_overland<MODE>(m, (int64_t)b0 + j, ovl WF_PNONE);
+        }
+        __syncwarp();
       }
     }
     // river: sub-step v on river level q0 + (tau - 1) - v
@@ -154,18 +197,26 @@ __device__ __forceinline__ void pipe_group(const DevModel &m, const PipeArgs pa,
         if (tl < 0) continue;
         const int cnt = river_items(tl, ro, nrl, q0, itR);
         if (cnt == 0) continue;
-        for (int j = first_item(cnt); j < cnt; j += nthreads) {
-          const WaveItem it = decode_river(j, tl, ro, nrl, q0, itR);
-          if (it.type == 2) {
-            load_riv(m, (int32_t)it.idx, riv);
-            task_river<MODE>(m, (int32_t)it.idx, it.v, riv, s WF_PNONE);
+        int c0;
+        seg_begin(cnt, c0);
+        int *counter = cnt_now + 3 * WF_PIPE_MAX_INFLIGHT + (s - s_lo);
+        for (int j = take(counter, c0, cnt); j >= 0; j = take(counter, c0, cnt)) {
+          if (j < cnt) {
+            const WaveItem it = decode_river(j, tl, ro, nrl, q0, itR);
+            if (it.type == 2) {
+              load_riv(m, (int32_t)it.idx, riv);
+              task_river<MODE>(m, (int32_t)it.idx, it.v, riv, s WF_PNONE);
+            }
           }
+          __syncwarp();
         }
       }
     }
     if (t + 1 < total) {
       wave_arrive<MODE>(ws);
       wave_wait<MODE>(ws);
+    } else if (MODE == WF_CTA || wf_is_cluster(MODE)) {
+      __syncthreads();  // the next group of this block starts with fresh counters
     }
   }
 }
@@ -173,6 +224,7 @@ __device__ __forceinline__ void pipe_group(const DevModel &m, const PipeArgs pa,
 template <int ML, int MODE>
 __global__ void __launch_bounds__(wf_pipe_threads(MODE), wf_pipe_minblocks(MODE)) k_pipeline(const DevModel m, const PipeArgs pa) {
   extern __shared__ uint32_t s_lev[];
+  __shared__ int s_ctr[2][4 * WF_PIPE_MAX_INFLIGHT];
   int crank = 0, csize = 1;
   if (wf_is_cluster(MODE)) {
     cg::cluster_group cl = cg::this_cluster();
@@ -181,12 +233,15 @@ __global__ void __launch_bounds__(wf_pipe_threads(MODE), wf_pipe_minblocks(MODE)
   }
   const int nclusters = (MODE == WF_GRID) ? 1 : (int)gridDim.x / csize;
   const int cid = (MODE == WF_GRID) ? 0 : (int)blockIdx.x / csize;
-  const int tid = (MODE == WF_GRID) ? (int)(blockIdx.x * blockDim.x + threadIdx.x) : crank * (int)blockDim.x + (int)threadIdx.x;
-  const int nthreads = (MODE == WF_GRID) ? (int)(gridDim.x * blockDim.x) : csize * (int)blockDim.x;
+  // blocks that sweep a group together, and this block's rank among them
+  const int brank = (MODE == WF_GRID) ? (int)blockIdx.x : crank;
+  const int nblocks = (MODE == WF_GRID) ? (int)gridDim.x : csize;
   WaveSync ws;
   ws.counter = m.grid_counter;
   ws.nblocks = gridDim.x;
   ws.target = 0;
+  for (int k = (int)threadIdx.x; k < 2 * 4 * WF_PIPE_MAX_INFLIGHT; k += (int)blockDim.x) (&s_ctr[0][0])[k] = 0;
+  __syncthreads();
   for (int g = cid; g < m.ngroups; g += nclusters) {
     const GroupDesc gd = m.groups[g];
     const int nlo = m.nlev - gd.lev0 + 1;
@@ -200,8 +255,14 @@ __global__ void __launch_bounds__(wf_pipe_threads(MODE), wf_pipe_minblocks(MODE)
       lo = s_lev;
       ro = s_lev + nlo;
     }
-    pipe_group<ML, MODE>(m, pa, gd, lo, ro, tid, nthreads, ws);
-    if (MODE == WF_GRID) break;
+    pipe_group<ML, MODE>(m, pa, gd, lo, ro, brank, nblocks, s_ctr, ws);
+    if (MODE != WF_GRID) {
+      // both parities clean for the next group (its tick 0 zeroes parity 1 itself; parity 0 here)
+      for (int k = (int)threadIdx.x; k < 4 * WF_PIPE_MAX_INFLIGHT; k += (int)blockDim.x) s_ctr[0][k] = 0;
+      __syncthreads();
+    } else {
+      g = m.ngroups;  // the grid sweeps the one group
+    }
   }
 }
 

@@ -413,7 +413,7 @@ class WflowSbm:
             gauges = np.flatnonzero(np.asarray(g).ravel() > 0) if g is not None else np.zeros(0, np.int64)
         gauges = np.ascontiguousarray(gauges, dtype=np.int64)
         handle = self._mod.gauges_create(gauges)
-        chunk = max(1, min(int(chunk), last - first + 1))
+        chunk = max(1, min(int(chunk), 64, last - first + 1))  # a launch holds at most 64 steps
         self._mod.pipeline_reserve(chunk)
         self._mod.pipeline_capture(handle)
         rows = []
