@@ -158,10 +158,55 @@ def gen_kinwave():
     print("wrote kinwave.npz, kinwave_ssf.npz")
 
 
+def gen_kinwave_ssf_dry():
+    """kinwave_ssf_dry.npz: reference kinematic_wave_ssf on dry and almost dry columns (water table at or near
+    the soil bottom, no or vanishing subsurface flow, vanishing recharge) up to f*D ~ 200 -- the regime where the
+    reference returns from its first-guess evaluation before the Newton loop starts (wflow_funcs.py:224-253) or
+    sits at its 1e-30 floor for all 3000 iterations.  Found by the full-size config 2 parity test."""
+    funcs, _ = refload.load()
+    rng = np.random.default_rng(20261020)
+    n = 3000
+    D = rng.uniform(400, 7000, n).astype(np.float32).astype(np.float64)
+    z = rng.random(n)
+    zi_old = D.copy()
+    sel = (z > 0.70) & (z <= 0.85)
+    zi_old[sel] = (D[sel] * (1.0 - np.exp(rng.uniform(np.log(1e-7), np.log(1e-3), sel.sum())))).astype(np.float32)
+    sel = z > 0.85
+    zi_old[sel] = (D[sel] * rng.uniform(0.8, 1.0, sel.sum())).astype(np.float32)
+    z = rng.random(n)
+    ssf_old = np.zeros(n)
+    sel = (z > 0.40) & (z <= 0.70)
+    ssf_old[sel] = float(np.float32(1e-30))
+    sel = z > 0.70
+    ssf_old[sel] = np.exp(rng.uniform(np.log(1e-40), np.log(1e3), sel.sum())).astype(np.float32)
+    z = rng.random(n)
+    ssf_in = np.zeros(n)
+    sel = z > 0.70
+    ssf_in[sel] = np.exp(rng.uniform(np.log(1e-30), np.log(1e3), sel.sum()))
+    z = rng.random(n)
+    r = np.exp(rng.uniform(np.log(1e-14), np.log(1e4), n))
+    r[(z > 0.70) & (z <= 0.85)] *= -1e-3
+    r[z > 0.85] = 0.0
+    Kh = np.exp(rng.uniform(0, np.log(100), n)); Ks = np.exp(rng.uniform(np.log(5), np.log(8000), n))
+    slope = np.exp(rng.uniform(np.log(1e-3), np.log(0.3), n)); neff = rng.uniform(0.3, 0.55, n)
+    f = neff / np.exp(rng.uniform(np.log(17), np.log(12000), n)); dx = rng.choice([1e6, 1.4142e6], n); w = 1e12 / dx
+    with np.errstate(all="ignore"):
+        ssfmax = (Kh * Ks * slope) / f * (1.0 - np.exp(-f * D))
+    args = [ssf_in, ssf_old, zi_old, r, Kh, Ks, slope, neff, f, D, np.ones(n), dx, w, ssfmax]
+    out = np.array([funcs.kinematic_wave_ssf(*a) for a in zip(*args)])
+    np.savez_compressed(os.path.join(GOLD, "kinwave_ssf_dry.npz"), args=np.array(args), out=out)
+    print("wrote kinwave_ssf_dry.npz: f*D up to %.0f, %d early-outs, %d at the floor" %
+          ((f * D).max(), int((out[:, 0] == 0).sum()), int((out[:, 0] == 1e-30).sum())))
+
+
 if __name__ == "__main__":
     if not refload.available():
         raise SystemExit("reference checkout not found; goldens can only be generated in the build container")
     os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "dry":  # add the dry-column set without touching the others
+        gen_kinwave_ssf_dry()
+        raise SystemExit(0)
     gen_set_dd()
     gen_kinwave()
+    gen_kinwave_ssf_dry()
     gen_steps()

@@ -230,6 +230,31 @@ def test_newton_solvers_match_reference_golden():
     assert rel.max() < 1e-9, rel.max(axis=0)
 
 
+def test_subsurface_solver_on_dry_columns_matches_reference_golden():
+    """kinematic_wave_ssf where the reference's result is NOT pinned to the root of its continuity equation: dry
+    and almost dry columns with f*D up to ~200, where it returns from the first-guess evaluation before the loop
+    starts, or stays at its 1e-30 floor for 3000 iterations (wflow_funcs.py:224-277; found by the full-size
+    config 2 test)."""
+    from wflow_b200 import core
+    g = np.load(common.GOLD + "/kinwave_ssf_dry.npz")
+    out = core.kinematic_wave_ssf(*g["args"])
+    ref = g["out"]
+    ssf_in, ssf_old, zi_old, r, Kh, Ks, slope, neff, f, D, dt, dx, w, smax = g["args"]
+    # water table and exfiltration: rel 1e-9 like the other golden set
+    relz = np.abs(out[:, 1] - ref[:, 1]) / np.maximum(np.abs(ref[:, 1]), 1e-3)
+    assert relz.max() < 1e-9, float(relz.max())
+    assert np.abs(out[:, 2] - ref[:, 2]).max() < 1e-9
+    # outflow: the reference stops once |F| <= 1e-3, which pins ssf only to 1e-3 / F'(ssf), F' = dt/dx + 1/Cn -- for
+    # these nearly dry columns that is 1e-5 .. 1e-2 mm3 (on flowing cells, ssf ~ 1e6 .. 1e9, it is below 1e-9
+    # relative).  Twice that bound, plus 1e-9 relative.
+    with np.errstate(all="ignore"):
+        inv_cn = neff / (Kh * Ks * np.exp(-f * ref[:, 1]) * slope)
+    tol = 2e-3 / (dt / dx + inv_cn) + 1e-9 * np.abs(ref[:, 0]) + 1e-30
+    bad = np.flatnonzero(np.abs(out[:, 0] - ref[:, 0]) > tol)
+    assert bad.size == 0, (bad.size, bad[:5], out[bad[:5]], ref[bad[:5]])
+    assert np.array_equal(out[:, 0] == 0, ref[:, 0] == 0)  # the exact-zero early-out
+
+
 def test_every_lateral_sweep_mode_gives_the_same_states(monkeypatch):
     """The grid, cluster (regular / wide blocks) and single-block sweeps run the same per-cell arithmetic in
     the same summation order: their states must agree bit for bit, and with the oracle within tolerance."""

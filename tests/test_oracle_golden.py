@@ -38,6 +38,15 @@ def test_kinematic_wave_ssf_golden():
     assert np.array_equal(out, g["out"], equal_nan=True)
 
 
+def test_kinematic_wave_ssf_dry_column_golden():
+    """Dry and almost dry columns up to f*D ~ 200: the reference leaves before its Newton loop, or sits at its
+    1e-30 floor for all 3000 iterations (wflow_funcs.py:224-277).  Bit for bit."""
+    g = np.load(common.GOLD + "/kinwave_ssf_dry.npz")
+    out = np.array([O.kinematic_wave_ssf(*a) for a in zip(*g["args"])])
+    assert np.array_equal(out, g["out"], equal_nan=True)
+    assert (g["out"][:, 0] == 1e-30).sum() > 100 and (g["out"][:, 0] == 0).sum() > 100
+
+
 @pytest.mark.parametrize("name", common.golden_step_cases())
 def test_step_trajectory_golden(name):
     g, kw, orc, _ = common.load_golden_case(name)

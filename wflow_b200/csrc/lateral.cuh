@@ -166,6 +166,30 @@ __device__ __noinline__ void kinematic_wave_ssf(double ssf_in, double ssf_old, d
     ssf_out = 0.0; zi_out = D; exfilt_out = 0.0;
     return;
   }
+  if (zi_old >= D) {
+    // A dry column.  The reference evaluates its residual at the first guess (ssf_old + ssf_in)/2 BEFORE the loop
+    // (:224-244) and, when that is already within epsilon -- no inflow, (almost) no recharge: the guess sits at
+    // zi = D like the state -- returns after that single update, with the zi of the guess.  The start from the
+    // root below cannot reproduce this exit (with f*D ~ 100 the 1e-30 floor on ssf alone stands for a water table
+    // metres above D), so this one evaluation is done literally, in the reference's own arithmetic.
+    double s0 = (ssf_old + ssf_in) / 2.0;
+    const double z0 = wf_div(wf_log(wf_div(f * s0, w * Ks_hor * Ks * slope) + efD), -f);
+    const double Cn0 = wf_div(Ks_hor * Ks * wf_exp(-f * z0) * slope, neff);
+    const double iC = wf_div(1.0, Cn0);
+    const double c0 = wf_div(dt, dx) * ssf_in + iC * s0 + dt * (r - (zi_old - z0) * neff * w);
+    const double fQ0 = wf_div(dt, dx) * s0 + iC * s0 - c0;
+    if (!(fabs(fQ0) > epsilon)) {
+      s0 = s0 - wf_div(fQ0, wf_div(dt, dx) + iC);
+      if (isnan(s0)) s0 = 0.0;
+      s0 = pymax(s0, 1e-30);
+      s0 = pymin(s0, (ssf_max * w));
+      const double rest0 = zi_old - wf_div(wf_div(ssf_in + r * dx - s0, w * dx), neff);
+      exfilt_out = pymin(rest0, 0.0) * -neff;
+      zi_out = pymax(0.0, z0);
+      ssf_out = s0;
+      return;
+    }
+  }
   // quotients of positive parameters (slope >= 1e-5, f > 0, Ks > 0, dx > 0): ordinary numbers
   const double den = w * Ks_hor * Ks * slope;
   const double dtdx = qdiv(dt, dx);
