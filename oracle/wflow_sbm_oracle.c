@@ -12,10 +12,16 @@
  *     in the build container (oracle/gen_golden.py -> tests/golden/*.npz,
  *     tests/test_oracle_vs_reference.py).
  *   * PCRaster half (interception, snow, evap split, river inflow glue of
- *     WflowModel.dynamic): PARITY UNPINNED -- PCRaster cannot be installed here; the
+ *     WflowModel.dynamic): PINNED ONLY AT THE REFERENCE'S OWN ACCEPTANCE NUMBERS --
+ *     PCRaster cannot be installed here, so there is no element-wise check; the
  *     restatement follows the reference source line by line with REAL4 (float)
- *     arithmetic and is pinned only by water-balance closure (as the reference's own
- *     tests do, tests/test_wflow_sbm.py:60-65).
+ *     arithmetic.  What the reference's tests hold at this boundary, the oracle
+ *     reproduces when driven through the framework mirror
+ *     (tests/test_reference_cases.py): tests/test_wflow_sbm.py:60-68 (wbsurf / wbsoil /
+ *     P sums of the tests/wflow_sbm case) and tests/test_wflow_sbm_example.py:54
+ *     (specrun.csv sum of the Rhine example: 0.0432266 here, 0.0432277 there).
+ *     Snow, glacier and the modified-Rutter branch are not exercised by those two
+ *     cases and remain element-wise UNPINNED.
  *
  * Each function cites the reference file:line it follows (paths relative to the
  * reference checkout).  Written from the behaviour of that code, not copied from it.

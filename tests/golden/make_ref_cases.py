@@ -1,0 +1,40 @@
+"""Copies the INPUT DATA (maps, tables, ini -- no source code) of the reference's own acceptance
+cases to where the tests find them.  Run in the build container, where /root/reference exists:
+
+    python tests/golden/make_ref_cases.py
+
+* tests/wflow_sbm (the case of the reference's tests/test_wflow_sbm.py; forcing comes through the
+  API, so only 8 static maps + the lookup tables + the ini are needed, ~1 MB)
+      -> tests/golden/ref_cases/wflow_sbm/           (committed)
+* examples/wflow_rhine_sbm (the case of tests/test_wflow_sbm_example.py; 132 MB with its forcing)
+      -> baseline/_ref/wflow_rhine_sbm/              (git-ignored; travels to the GPU box with gpurun)
+"""
+import os
+import shutil
+import sys
+
+REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+MAPS = ["wflow_subcatch", "wflow_ldd", "wflow_dem", "wflow_river", "wflow_landuse", "wflow_soil", "wflow_gauges",
+        "wflow_riverlength_fact"]
+
+
+def main():
+    src = os.path.join(REF, "tests", "wflow_sbm")
+    dst = os.path.join(ROOT, "tests", "golden", "ref_cases", "wflow_sbm")
+    os.makedirs(os.path.join(dst, "staticmaps"), exist_ok=True)
+    for m in MAPS:
+        shutil.copyfile(os.path.join(src, "staticmaps", m + ".map"), os.path.join(dst, "staticmaps", m + ".map"))
+    shutil.copytree(os.path.join(src, "intbl"), os.path.join(dst, "intbl"), dirs_exist_ok=True)
+    shutil.copyfile(os.path.join(src, "wflow_sbm.ini"), os.path.join(dst, "wflow_sbm.ini"))
+    rh = os.path.join(ROOT, "baseline", "_ref", "wflow_rhine_sbm")
+    if not os.path.isdir(rh):
+        shutil.copytree(os.path.join(REF, "examples", "wflow_rhine_sbm"), rh)
+    for d in (dst, rh):
+        os.system("chmod -R u+w '%s'" % d)
+    print("wrote", dst, "and", rh)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,105 @@
+"""The reference's own acceptance tests, re-run through the framework mirror.
+
+* tests/test_wflow_sbm.py (reference): case tests/wflow_sbm, 29 steps, forcing through wf_setValues;
+  asserts sum(wbsurf.csv[:, 2]) = -1.0039e-06, sum(wbsoil.csv[:, 2]) = 0.00060653 (4 places), sum(P.csv[:, 2]) = 30.
+* tests/test_wflow_sbm_example.py (reference): examples/wflow_rhine_sbm as shipped, 29 steps;
+  asserts sum(specrun.csv[:, 2]) = 0.043227685448073316 (4 places).
+
+Each runs twice: with the CPU oracle behind the framework (not gpu: this PINS THE ORACLE's full step,
+PCRaster-phase restatement included, to the only numbers the reference holds at that boundary,
+SURVEY.md §8c) and with the CUDA library (gpu).  Input data: tests/golden/make_ref_cases.py."""
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CASE_SBM = os.path.join(HERE, "golden", "ref_cases", "wflow_sbm")
+CASE_RHINE = os.path.join(os.path.dirname(HERE), "baseline", "_ref", "wflow_rhine_sbm")
+
+needs_rhine = pytest.mark.skipif(not os.path.isfile(os.path.join(CASE_RHINE, "wflow_sbm.ini")),
+                                 reason="the 132 MB Rhine example is not in baseline/_ref (tests/golden/make_ref_cases.py)")
+
+
+def _csv_sum(case, run, name):
+    d = np.genfromtxt(os.path.join(case, run, name), delimiter=",")
+    assert d.shape[0] == 29
+    return d[:, 2].sum()
+
+
+def run_test_wflow_sbm(tmp_path):
+    """tests/test_wflow_sbm.py:16-68 of the reference, call for call."""
+    from wflow_b200.framework import WflowSbm
+    case = str(tmp_path / "wflow_sbm")
+    shutil.copytree(CASE_SBM, case)
+    m = WflowSbm("wflow_catchment.map", case, "unittestsbm", "wflow_sbm.ini")
+    m.createRunId(NoOverWrite=False)
+    m._runInitial()
+    m._runResume()
+    sump = 0.0
+    for ts in range(1, 30):
+        if ts < 10:
+            m.wf_setValues("P", 0.0)
+        elif ts <= 15:
+            m.wf_setValues("P", 5.0)
+            sump += 5.0
+        else:
+            m.wf_setValues("P", 0.0)
+        m.wf_setValues("PET", 3.0)
+        m.wf_setValues("TEMP", 10.0)
+        m._runDynamic(ts, ts)
+    m._runSuspend()
+    m._wf_shutdown()
+    assert _csv_sum(case, "unittestsbm", "wbsurf.csv") == pytest.approx(-1.003901559215592e-06, abs=5e-5)
+    assert _csv_sum(case, "unittestsbm", "wbsoil.csv") == pytest.approx(0.0006065327197575243, abs=5e-5)
+    assert _csv_sum(case, "unittestsbm", "P.csv") == pytest.approx(sump, abs=1e-7)
+    # function=total of [outputcsv_1] and the tss of [outputtss_0] are written as well
+    assert _csv_sum(case, "unittestsbm", "1P.csv") > sump
+    tss = open(os.path.join(case, "unittestsbm", "runmm.tss")).read().splitlines()
+    assert tss[0] == "timeseries scalar" and tss[2] == "timestep"
+
+
+def run_test_wflow_sbm_example(tmp_path):
+    """tests/test_wflow_sbm_example.py:14-54 of the reference (instate/ resume, map-stack forcing)."""
+    from wflow_b200.framework import WflowSbm
+    run = "unittest_%s" % os.path.basename(str(tmp_path))
+    m = WflowSbm("wflow_subcatch.map", CASE_RHINE, run, "wflow_sbm.ini")
+    try:
+        m.createRunId(NoOverWrite=False)
+        m._runInitial()
+        m._runResume()
+        for ts in range(1, 30):
+            m._runDynamic(ts, ts)
+        m._runSuspend()
+        m._wf_shutdown()
+        assert _csv_sum(CASE_RHINE, run, "specrun.csv") == pytest.approx(0.043227685448073316, abs=5e-5)
+    finally:
+        shutil.rmtree(os.path.join(CASE_RHINE, run), ignore_errors=True)
+
+
+@pytest.fixture()
+def oracle_engine(monkeypatch):
+    import wflow_b200.framework as fw
+    from tests.oracle_backend import OracleSbmModel
+    monkeypatch.setattr(fw, "SbmModel", OracleSbmModel)
+
+
+def test_oracle_reproduces_reference_test_wflow_sbm(oracle_engine, tmp_path):
+    run_test_wflow_sbm(tmp_path)
+
+
+@needs_rhine
+def test_oracle_reproduces_reference_rhine_example(oracle_engine, tmp_path):
+    run_test_wflow_sbm_example(tmp_path)
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_reference_test_wflow_sbm(tmp_path):
+    run_test_wflow_sbm(tmp_path)
+
+
+@pytest.mark.gpu
+@needs_rhine
+def test_cuda_reproduces_reference_rhine_example(tmp_path):
+    run_test_wflow_sbm_example(tmp_path)
