@@ -216,14 +216,22 @@ int launch_lateral(wf_model *m) {
       m->lat_blocks = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * per_sm, (m->max_tick_items + 255) / 256));
     }
     CUDA_OK(cudaMemsetAsync(m->dm.grid_counter, 0, sizeof(unsigned int), m->stream));
-    CUDA_OK(cudaLaunchCooperativeKernel((void *)k_lateral_wave<ML, WF_GRID>, dim3(m->lat_blocks), dim3(256), args, m->lat_smem, m->stream));
+    void *gfn = m->dm.any_diag ? (void *)k_lateral_wave<ML, WF_GRID, true> : (void *)k_lateral_wave<ML, WF_GRID, false>;
+    CUDA_OK(cudaLaunchCooperativeKernel(gfn, dim3(m->lat_blocks), dim3(256), args, m->lat_smem, m->stream));
     return WF_OK;
   }
   const bool cta = m->lat_mode == WF_CTA;
-  void *fn = cta ? (void *)k_lateral_wave<ML, WF_CTA>
-                 : (m->lat_mode == WF_CLUSTER_WIDE ? (void *)k_lateral_wave<ML, WF_CLUSTER_WIDE> : (void *)k_lateral_wave<ML, WF_CLUSTER>);
+  // two builds of every sweep: with the diagnostic outputs (some K_DIAG field requested) and without
+  void *fnD = cta ? (void *)k_lateral_wave<ML, WF_CTA, true>
+                  : (m->lat_mode == WF_CLUSTER_WIDE ? (void *)k_lateral_wave<ML, WF_CLUSTER_WIDE, true> : (void *)k_lateral_wave<ML, WF_CLUSTER, true>);
+  void *fnP = cta ? (void *)k_lateral_wave<ML, WF_CTA, false>
+                  : (m->lat_mode == WF_CLUSTER_WIDE ? (void *)k_lateral_wave<ML, WF_CLUSTER_WIDE, false> : (void *)k_lateral_wave<ML, WF_CLUSTER, false>);
+  void *fn = m->dm.any_diag ? fnD : fnP;
   if (m->lat_blocks == 0) {
-    if (m->lat_smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->lat_smem));
+    if (m->lat_smem > 48 * 1024) {
+      CUDA_OK(cudaFuncSetAttribute(fnD, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->lat_smem));
+      CUDA_OK(cudaFuncSetAttribute(fnP, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->lat_smem));
+    }
     const int res = resident_clusters<ML>(m->lat_mode, m->cluster_size, m->lat_smem);
     if (res < 1) return fail(WF_ENODEVICE, "k_lateral_wave does not fit on the device");
     m->lat_blocks = std::min(res, m->dm.ngroups) * m->cluster_size;
@@ -296,11 +304,21 @@ int launch_step(wf_model *m) {
   const int tb = WF_VERT_THREADS;
   prepare_step<ML>(m);
   const size_t vsmem = WF_VERT_STAGE ? VLayout<ML>::bytes(m->dm.glacier != 0) : 0;
-  if (vsmem > 48 * 1024 && !m->vert_attr_set) {
-    CUDA_OK(cudaFuncSetAttribute((void *)k_vertical<ML>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
+  if (!m->vert_attr_set) {
+    if (vsmem > 48 * 1024) {
+      CUDA_OK(cudaFuncSetAttribute((void *)k_vertical<ML, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
+      CUDA_OK(cudaFuncSetAttribute((void *)k_vertical<ML, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
+    }
+    if (VScratch<ML>::enabled) {  // WF_VERT_MINBLOCKS blocks with their scratch must fit the shared-memory carve-out
+      CUDA_OK(cudaFuncSetAttribute((void *)k_vertical<ML, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      CUDA_OK(cudaFuncSetAttribute((void *)k_vertical<ML, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
     m->vert_attr_set = true;
   }
-  k_vertical<ML><<<(unsigned)((n + tb - 1) / tb), tb, vsmem, m->stream>>>(m->dm);
+  if (m->dm.any_diag)
+    k_vertical<ML, true><<<(unsigned)((n + tb - 1) / tb), tb, vsmem, m->stream>>>(m->dm);
+  else
+    k_vertical<ML, false><<<(unsigned)((n + tb - 1) / tb), tb, vsmem, m->stream>>>(m->dm);
   m->launches++;
   if (m->timed) cudaEventRecord(e1, m->stream);
   if (int rc = launch_lateral<ML>(m)) return rc;

@@ -346,7 +346,8 @@ __device__ __forceinline__ void load_riv(const DevModel &m, const int32_t rs, Ri
 }
 
 // ---- task 1: subsurface flow + post-ssf column tail of one cell ------------------------------
-template <int ML, int MODE>
+// DIAG = false compiles the diagnostic outputs out (and with them the values they keep alive): the production sweep
+template <int ML, int MODE, bool DIAG = true>
 __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t i, const SubOps<ML> &o WF_PARGS) {
   const int nup = o.nup;
   const uint32_t us = o.us;
@@ -448,7 +449,7 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
   double sumU = 0.0;
 #pragma unroll
   for (int k = 0; k < ML; k++) sumU += U[k];
-  if (m.any_diag) {
+  if (DIAG && m.any_diag) {
   OUTF(SatWaterDepth, Sat); OUTF(UStoreDepth, sumU);
   OUTF(ssf_toriver, riverMap ? qdiv(ssf_tr / (1000 * 1000 * 1000), m.dt) : 0.0);
   OUTF(ExfiltWater, ExfiltWater); OUTF(ExfiltFromUstore, ExfiltFromUstore); OUTF(ExfiltFromSat, ExfiltSatWater);
@@ -482,7 +483,7 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
 }
 
 // ---- task 2: overland flow of one cell, all sub-steps (wflow_sbm.py:830-879) -----------------
-template <int MODE>
+template <int MODE, bool DIAG = true>
 __device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i, const OvlOps &o WF_PARGS) {
   const int nup = o.nup;
   const uint32_t us = o.us;
@@ -557,7 +558,7 @@ __device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i
   m.f[F_LandRunoff][i] = (float)qdiv(acc_flow, m.dt);
   m.f[F_WaterLevelL][i] = (float)qdiv(acc_h, (double)itL);
   const float qo_toriver_f = (float)qdiv(qo_toriver_acc, m.dt);
-  if (m.any_diag) {
+  if (DIAG && m.any_diag) {
     OUTF(qo_toriver, qo_toriver_f);
     OUTF(InflowKinWaveCellLand, qdiv(Qo_in_acc, m.dt));
   }
@@ -716,7 +717,7 @@ struct WaveItem {
   int v;         // river sub-step
 };
 
-template <int ML, int MODE>
+template <int ML, int MODE, bool DIAG>
 __device__ __forceinline__ void sweep_group(const DevModel &m, const GroupDesc gd, const uint32_t *lo, const uint32_t *ro,
                                             const uint32_t *tt, const int tid, const int nthreads, WaveSync &ws) {
   const int D = m.nlev, itR = m.itR;
@@ -793,10 +794,10 @@ __device__ __forceinline__ void sweep_group(const DevModel &m, const GroupDesc g
       else it = decode_item(j, t);
       if (it.type == 0) {
         if (!first || !PRELOAD) load_sub<ML>(m, (int64_t)it.idx, sub);
-        task_subsurface<ML, MODE>(m, (int64_t)it.idx, sub WF_PPASS(0));
+        task_subsurface<ML, MODE, DIAG>(m, (int64_t)it.idx, sub WF_PPASS(0));
       } else if (it.type == 1) {
         if (!first || !PRELOAD_SMALL) load_ovl(m, (int64_t)it.idx, ovl);
-        task_overland<MODE>(m, (int64_t)it.idx, ovl WF_PPASS(1));
+        task_overland<MODE, DIAG>(m, (int64_t)it.idx, ovl WF_PPASS(1));
       } else if (it.type == 2) {
         if (!first || !PRELOAD_SMALL) load_riv(m, (int32_t)it.idx, riv);
         task_river<MODE>(m, (int32_t)it.idx, it.v, riv, 0 WF_PPASS(2));
@@ -823,7 +824,7 @@ __device__ __forceinline__ void sweep_group(const DevModel &m, const GroupDesc g
   }
 }
 
-template <int ML, int MODE>
+template <int ML, int MODE, bool DIAG = true>
 __global__ void __launch_bounds__(wf_block_threads(MODE), 1) k_lateral_wave(const DevModel m) {
   extern __shared__ uint32_t s_lev[];
   int crank = 0, csize = 1;
@@ -856,7 +857,7 @@ __global__ void __launch_bounds__(wf_block_threads(MODE), 1) k_lateral_wave(cons
       ro = s_lev + nlo;
       tt = s_lev + nlo + nro;
     }
-    sweep_group<ML, MODE>(m, gd, lo, ro, tt, tid, nthreads, ws);
+    sweep_group<ML, MODE, DIAG>(m, gd, lo, ro, tt, tid, nthreads, ws);
     // the next group of this cluster touches other cells only: no barrier needed in between
     if (MODE == WF_GRID) break;
   }
