@@ -61,6 +61,7 @@
   /* static, lateral */ \
   X(KsatHorFrac) X(landSlope) X(DL) X(DW) X(SW) X(AlphaL) X(Beta) X(River) X(AlphaR) X(DCL) X(Bw) \
   /* glacier (optional) */ X(GlacierFrac) X(G_TT) X(G_Cfmax) X(G_SIfrac) \
+  /* dynamic vegetation (optional: present when LAI is) */ X(LAI) X(Sl) X(Swood) X(Kext) \
   /* states (in/out) */ \
   X(CanopyStorage) X(Snow) X(SnowWater) X(TSoil) X(zi) X(SatWaterDepth) \
   X(UStoreLayerDepth_0) X(UStoreLayerDepth_1) X(UStoreLayerDepth_2) X(UStoreLayerDepth_3) \
@@ -434,10 +435,17 @@ int wfo_step(const wfo_params *p, const wfo_network *net, const wfo_network *rne
     OldCanopy[i] = CanopyStorage;
     float PotEvap = PotenEvap;
     float CGF = F(CanopyGapFraction)[i], Cmax = F(Cmax)[i];
+    float EoverR = F(EoverR) ? F(EoverR)[i] : 0.0f;
+    if (F(LAI)) { /* LAI-driven canopy, wflow_sbm.py:2587-2603 (PotenEvap is still the raw forcing there) */
+      const float LAI = F(LAI)[i], Kext = F(Kext)[i];
+      Cmax = F(Sl)[i] * LAI + F(Swood)[i];                            /* :2590 */
+      CGF = (float)exp((double)((-Kext) * LAI));                      /* :2591 */
+      const float Ewet = (1.0f - CGF) * F(PET)[i];                    /* :2595 */
+      EoverR = (Precipitation > 0.0f) ? fminf(0.25f, Ewet / fmaxf(0.0001f, Precipitation)) : 0.0f; /* :2596-2603 */
+    }
     float ThroughFall, Interception, StemFlow, PotTransSoil;
     if (gash) {
       /* rainfall_interception_gash, wflow_funcs.py:321-373 */
-      float EoverR = F(EoverR)[i];
       float pt = 0.1f * CGF;
       float one_m = (1.0f - CGF) - pt;
       float P_sat = 0.0f;

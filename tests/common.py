@@ -25,7 +25,7 @@ def state_names(max_layers, snow=True):
 
 def make_pair(nrow, ncol, *, kind="forest", tile=16, layer_thickness=(100, 300, 800), dt=86400, snow=1, itL=1, itR=1,
               seed=3, river_area=8, tm=0, ust=0, sir=0, oracle=True, gpu=True, init="random", block=4, mask_frac=0.0,
-              glacier=0):
+              glacier=0, lai=0):
     """Returns (oracle_model or None, cuda_model or None, ldd, river)."""
     ldd, river, static, state = synth.make_case(nrow, ncol, kind=kind, tile=tile, seed=seed, timestepsecs=dt,
                                                 layer_thickness=layer_thickness, river_area=river_area, init=init,
@@ -36,6 +36,11 @@ def make_pair(nrow, ncol, *, kind="forest", tile=16, layer_thickness=(100, 300, 
         static = dict(static, GlacierFrac=gf, G_TT=np.float32(1.3), G_Cfmax=np.float32(5.3 * dt / 86400.0),
                       G_SIfrac=np.float32(0.002 * dt / 86400.0))
         state = dict(state, GlacierStore=np.where(gf > 0, rng.uniform(0.0, 5500.0, (nrow, ncol)), 0.0).astype(np.float32))
+    if lai:  # LAI-driven canopy parameters (wflow_sbm.py:2587-2603): land-cover style blocks, some cells bare (LAI = 0)
+        rng = np.random.default_rng(seed + 99)
+        blk = lambda lo, hi: np.kron(rng.uniform(lo, hi, ((nrow + 7) // 8, (ncol + 7) // 8)), np.ones((8, 8)))[:nrow, :ncol].astype(np.float32)
+        static = dict(static, LAI=np.where(rng.random((nrow, ncol)) < 0.1, 0.0, blk(0.1, 6.0)).astype(np.float32),
+                      Sl=blk(0.03, 0.13), Swood=blk(0.0, 0.5), Kext=blk(0.4, 0.8))
     orc = mod = None
     if oracle:
         from oracle import oracle as O

@@ -4,7 +4,8 @@ cases to where the tests find them.  Run in the build container, where /root/ref
     python tests/golden/make_ref_cases.py
 
 * tests/wflow_sbm (the case of the reference's tests/test_wflow_sbm.py; forcing comes through the
-  API, so only 8 static maps + the lookup tables + the ini are needed, ~1 MB)
+  API, so only 8 static maps + the lookup tables + the ini are needed, ~1 MB; plus what its dynamic-vegetation
+  variant, tests/test_wflow_sbm_dynveg.py, reads: 3 tables, the land-cover map, 2 months of LAI)
       -> tests/golden/ref_cases/wflow_sbm/           (committed)
 * examples/wflow_rhine_sbm (the case of tests/test_wflow_sbm_example.py; 132 MB with its forcing)
       -> baseline/_ref/wflow_rhine_sbm/              (git-ignored; travels to the GPU box with gpurun)
@@ -28,6 +29,13 @@ def main():
         shutil.copyfile(os.path.join(src, "staticmaps", m + ".map"), os.path.join(dst, "staticmaps", m + ".map"))
     shutil.copytree(os.path.join(src, "intbl"), os.path.join(dst, "intbl"), dirs_exist_ok=True)
     shutil.copyfile(os.path.join(src, "wflow_sbm.ini"), os.path.join(dst, "wflow_sbm.ini"))
+    # the dynamic-vegetation variant of the same case (tests/test_wflow_sbm_dynveg.py): its ini, the land-cover
+    # lookup tables and the LAI climatology of the two months the 29 steps touch
+    shutil.copyfile(os.path.join(src, "wflow_sbm_dynveg.ini"), os.path.join(dst, "wflow_sbm_dynveg.ini"))
+    os.makedirs(os.path.join(dst, "inmaps", "clim"), exist_ok=True)
+    for f in ("LC.map", "LCtoBranchTrunkStorage.tbl", "LCtoExtinctionCoefficient.tbl", "LCtoSpecificLeafStorage.tbl",
+              "LAI00000.001", "LAI00000.002"):
+        shutil.copyfile(os.path.join(src, "inmaps", "clim", f), os.path.join(dst, "inmaps", "clim", f))
     rh = os.path.join(ROOT, "baseline", "_ref", "wflow_rhine_sbm")
     if not os.path.isdir(rh):
         shutil.copytree(os.path.join(REF, "examples", "wflow_rhine_sbm"), rh)

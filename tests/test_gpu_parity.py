@@ -28,6 +28,8 @@ CASES = [
     dict(kind="tiles", layer_thickness=(100, 300, 800), glacier=1),                       # glacierHBV
     dict(kind="tiles", layer_thickness=(100, 300, 800), mask_frac=0.1, dt=3600, itR=2),  # missing cells inside the tiles
     dict(kind="forest", layer_thickness=(50, 100, 150, 200, 300, 400, 600)),              # 8 soil layers (the maximum)
+    dict(kind="tiles", layer_thickness=(100, 300, 800), lai=1),                           # LAI-driven canopy, Gash (daily)
+    dict(kind="forest", layer_thickness=(100, 300), lai=1, dt=3600, itR=2),               # LAI-driven canopy, modified Rutter
 ]
 
 

@@ -2,6 +2,7 @@
 
 * tests/test_wflow_sbm.py (reference): case tests/wflow_sbm, 29 steps, forcing through wf_setValues;
   asserts sum(wbsurf.csv[:, 2]) = -1.0039e-06, sum(wbsoil.csv[:, 2]) = 0.00060653 (4 places), sum(P.csv[:, 2]) = 30.
+* tests/test_wflow_sbm_dynveg.py (reference): the same case with LAI-driven canopy parameters; wbsoil sum 0.00061054.
 * tests/test_wflow_sbm_example.py (reference): examples/wflow_rhine_sbm as shipped, 29 steps;
   asserts sum(specrun.csv[:, 2]) = 0.043227685448073316 (4 places).
 
@@ -60,6 +61,40 @@ def run_test_wflow_sbm(tmp_path):
     assert tss[0] == "timeseries scalar" and tss[2] == "timestep"
 
 
+def run_test_wflow_sbm_dynveg(tmp_path):
+    """tests/test_wflow_sbm_dynveg.py:15-68 of the reference: the same case with LAI-driven canopy parameters
+    ([modelparameters]: Sl / Kext / Swood from land-cover tables, LAI as a monthly climatology; wflow_sbm.py:2587-2603)."""
+    from wflow_b200.framework import WflowSbm
+    case = str(tmp_path / "wflow_sbm")
+    shutil.copytree(CASE_SBM, case)
+    m = WflowSbm("wflow_catchment.map", case, "unittest", "wflow_sbm_dynveg.ini")
+    m.createRunId(NoOverWrite=False)
+    m._runInitial()
+    m._runResume()
+    assert {p["name"] for p in m._modelparameters} == {"Sl", "Kext", "Swood", "LAI"}
+    lai = m._mod.get("LAI")
+    assert np.nanmax(np.where(lai > -999, lai, np.nan)) > 0.5  # the January map, not the default
+    sump = 0.0
+    for ts in range(1, 30):
+        if ts < 10:
+            m.wf_setValues("P", 0.0)
+        elif ts <= 15:
+            m.wf_setValues("P", 10.0)
+            sump += 10.0
+        else:
+            m.wf_setValues("P", 0.0)
+        m.wf_setValues("PET", 2.0)
+        m.wf_setValues("TEMP", 10.0)
+        m._runDynamic(ts, ts)
+    assert m._par_loaded["LAI"][1].endswith("LAI00000.002")  # February by the end of the run
+    m._runSuspend()
+    m._wf_shutdown()
+    assert _csv_sum(case, "unittest", "wbsurf.csv") == pytest.approx(-1.003901559215592e-06, abs=5e-5)
+    assert _csv_sum(case, "unittest", "wbsoil.csv") == pytest.approx(0.0006105408792791422, abs=5e-5)
+    assert _csv_sum(case, "unittest", "P.csv") == pytest.approx(sump, abs=1e-7)
+    return case
+
+
 def run_test_wflow_sbm_example(tmp_path):
     """tests/test_wflow_sbm_example.py:14-54 of the reference (instate/ resume, map-stack forcing)."""
     from wflow_b200.framework import WflowSbm
@@ -89,6 +124,10 @@ def test_oracle_reproduces_reference_test_wflow_sbm(oracle_engine, tmp_path):
     run_test_wflow_sbm(tmp_path)
 
 
+def test_oracle_reproduces_reference_test_wflow_sbm_dynveg(oracle_engine, tmp_path):
+    run_test_wflow_sbm_dynveg(tmp_path)
+
+
 @needs_rhine
 def test_oracle_reproduces_reference_rhine_example(oracle_engine, tmp_path):
     run_test_wflow_sbm_example(tmp_path)
@@ -97,6 +136,11 @@ def test_oracle_reproduces_reference_rhine_example(oracle_engine, tmp_path):
 @pytest.mark.gpu
 def test_cuda_reproduces_reference_test_wflow_sbm(tmp_path):
     run_test_wflow_sbm(tmp_path)
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_reference_test_wflow_sbm_dynveg(tmp_path):
+    run_test_wflow_sbm_dynveg(tmp_path)
 
 
 @pytest.mark.gpu

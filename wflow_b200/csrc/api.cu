@@ -451,6 +451,7 @@ const int kRequired[] = {F_P, F_PET, F_Cmax, F_EoverR, F_CanopyGapFraction, F_et
 const int kRequiredSnow[] = {F_TEMP, F_TempCor, F_TTI, F_TT, F_TTM, F_Cfmax, F_WHC, F_w_soil};
 const int kRequiredRiver[] = {F_RiverFrac, F_AlphaR, F_DCL, F_Bw};
 const int kRequiredGlacier[] = {F_GlacierFrac, F_G_TT, F_G_Cfmax, F_G_SIfrac};
+const int kRequiredLAI[] = {F_Sl, F_Swood, F_Kext};  // wflow_sbm.py:1426-1452: needed because LAI is defined
 
 int check_ready(wf_model *m) {
   auto need = [&](int id) -> int {
@@ -473,6 +474,9 @@ int check_ready(wf_model *m) {
       if (int rc = need(id)) return rc;
   if (m->cfg.glacier)
     for (int id : kRequiredGlacier)
+      if (int rc = need(id)) return rc;
+  if (m->dm.f[F_LAI])
+    for (int id : kRequiredLAI)
       if (int rc = need(id)) return rc;
   return WF_OK;
 }

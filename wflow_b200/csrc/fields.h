@@ -32,6 +32,8 @@ enum FieldKind : int { K_FORCING = 0, K_STATIC = 1, K_STATE = 2, K_DIAG = 3, K_R
   X(AlphaR, K_STATIC | K_RIVER) X(DCL, K_STATIC | K_RIVER) X(Bw, K_STATIC | K_RIVER)               \
   /* glacier */                                                                                    \
   X(GlacierFrac, K_STATIC) X(G_TT, K_STATIC) X(G_Cfmax, K_STATIC) X(G_SIfrac, K_STATIC)            \
+  /* dynamic vegetation (wflow_sbm.py:2587-2603): present when LAI is */                           \
+  X(LAI, K_STATIC) X(Sl, K_STATIC) X(Swood, K_STATIC) X(Kext, K_STATIC)                            \
   /* states (stateVariables(), wflow_sbm.py:955-1010; zi is the live saturated-zone state) */      \
   X(CanopyStorage, K_STATE) X(Snow, K_STATE) X(SnowWater, K_STATE) X(TSoil, K_STATE)               \
   X(zi, K_STATE)                                                                                   \

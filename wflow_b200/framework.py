@@ -284,6 +284,11 @@ class WflowSbm:
         bf = np.ones(self.shape, F32) if bf is None else np.nan_to_num(bf, nan=0.0).astype(F32)
         base["BankfullDepth"] = np.where(river_b, bf, F32(0.0)).astype(F32)
 
+        # [modelparameters] of static type replace the table-derived rasters before the derivations (:719-764)
+        self._read_modelparameters()
+        for par in self._modelparameters:
+            if par["type"] in self._STATIC_TYPES and par["name"] in base:
+                base[par["name"]] = self._parameter_raster(par, 0)
         self.static = params.derive_static(base, ldd, river_b, self.timestepsecs, cellsize=info.cellsize,
                                            n_layers=self.maxLayers)
         self.River = river_b
@@ -305,6 +310,7 @@ class WflowSbm:
             if k not in ("River", "Beta"):
                 self._mod.set(k, np.where(np.isnan(v), F32(0.0), v))
         self._mod.request("SatWaterDepth")
+        self._update_parameters(0, initial=True)
         self._setup_outputs()
 
     # ---- resume / suspend ------------------------------------------------------------------------
@@ -368,6 +374,98 @@ class WflowSbm:
         self._mod.quick_resume()
 
     # ---- dynamic ----------------------------------------------------------------------------------
+    # ---- [modelparameters] (wf_updateparameters, wf_DynamicFramework.py:708-874, 1624-1690) ---------------
+    _STATIC_TYPES = ("staticmap", "statictbl", "tbl", "tblsparse")
+    _DYNAMIC_TYPES = ("timeseries", "monthlyclim", "dailyclim", "tblmonthlyclim")
+    # parameters that are library fields as they stand (no derived static depends on them)
+    _DIRECT = ("LAI", "Sl", "Swood", "Kext", "RootingDepth", "Cmax", "CanopyGapFraction", "EoverR", "et_RefToPot",
+               "PathFrac", "rootdistpar", "CapScale", "AirEntryPressure", "MaxLeakage", "WaterFrac", "TempCor")
+
+    def _read_modelparameters(self):
+        """name = stack,type,default,verbose[,lookupmap_1,...]"""
+        self._modelparameters = []
+        self._par_loaded = {}
+        if not self.config.has_section("modelparameters"):
+            return
+        for name, line in self.config.items("modelparameters"):
+            vals = [v.strip() for v in line.split(",")]
+            if len(vals) < 4:
+                self.logger.error("Parameter line in ini not valid: " + line)  # :1688
+                continue
+            self._modelparameters.append(dict(name=name, stack=vals[0], type=vals[1], default=float(vals[2]),
+                                              verbose=vals[3], lookupmaps=vals[4:]))
+
+    def _climate_datetime(self, step):
+        """DT.currentDateTime inside dynamic(): in 'steps' mode the clock starts at the state time, one step before
+        starttime, and is advanced AFTER each step (wf_DynamicFramework.py:136-171, 2991-3021)."""
+        return self.datetime_start + _dt.timedelta(seconds=self.timestepsecs * (max(step, 1) - 2))
+
+    def _parameter_source(self, par, step):
+        """(kind, path) the parameter is read from at this step."""
+        t, stack = par["type"], par["stack"].lstrip("/")
+        if t in ("tbl", "tblsparse", "statictbl"):
+            return "tbl", os.path.join(self.Dir, stack)
+        if t == "staticmap":
+            return "map", os.path.join(self.Dir, stack)
+        if t == "timeseries":
+            return "map", generate_name_t(os.path.join(self.Dir, stack), max(step, 1))
+        if t == "monthlyclim":
+            return "map", generate_name_t(os.path.join(self.Dir, stack), self._climate_datetime(step).month)
+        if t == "dailyclim":
+            return "map", generate_name_t(os.path.join(self.Dir, stack), self._climate_datetime(step).timetuple().tm_yday)
+        if t == "tblmonthlyclim":
+            root, ext = os.path.splitext(stack)
+            return "tbl", os.path.join(self.Dir, "%s_%d%s" % (root, self._climate_datetime(step).month, ext))
+        return None, None
+
+    def _parameter_raster(self, par, step):
+        kind, path = self._parameter_source(par, step)
+        default = np.float32(par["default"])
+        if kind == "map":
+            if os.path.isfile(path):
+                a, _ = csf.read_map(path)
+                return np.nan_to_num(a.astype(F32), nan=float(default)).astype(F32)  # pcr.cover(map, default)
+            if par["verbose"] not in ("0", ""):
+                self.logger.warning("map %s not found, using default %g" % (path, default))
+            return np.full(self.shape, default, F32)
+        if kind == "tbl":
+            if not os.path.isfile(path):  # readtblFlexDefault: the default
+                return np.full(self.shape, default, F32)
+            if par["type"] == "statictbl":  # readtblDefault: landuse, subcatchment, soil
+                keys = [self.LandUse, self.TopoId, self.Soil]
+            else:                           # readtblFlexDefault: the listed lookup maps
+                keys = []
+                for lm in par["lookupmaps"]:
+                    lp = os.path.join(self.Dir, lm)
+                    if not os.path.isfile(lp):
+                        return np.full(self.shape, default, F32)
+                    keys.append(csf.read_map(lp)[0])
+            a = tbl.lookupscalar(path, *keys)
+            return np.nan_to_num(a, nan=float(default)).astype(F32)
+        return None
+
+    def _update_parameters(self, step, initial=False):
+        """Static types once (initial), time-dependent types whenever their source file changes."""
+        for par in self._modelparameters:
+            name, t = par["name"], par["type"]
+            if t in self._STATIC_TYPES:
+                if not initial or name not in self._DIRECT:
+                    continue
+            elif t in self._DYNAMIC_TYPES:
+                if name not in self._DIRECT:
+                    if initial:
+                        self.logger.warning("[modelparameters] %s: time-dependent values of this parameter are not supported" % name)
+                    continue
+            else:
+                if initial:
+                    self.logger.warning("[modelparameters] %s: type %s is not supported" % (name, t))
+                continue
+            src = self._parameter_source(par, step)
+            if self._par_loaded.get(name) == src:
+                continue
+            self._par_loaded[name] = src
+            self._mod.set(name, self._parameter_raster(par, step))
+
     def _forcing(self, var, stack_key, default_stack, step, default):
         if var in self._api_values:  # set through the API: skip the disk for this step (:3300-3306)
             return self._api_values.pop(var)
@@ -384,6 +482,7 @@ class WflowSbm:
         last = int(laststep) if laststep else self.nrTimeSteps
         for step in range(first, last + 1):
             self._currentTimeStep = step
+            self._update_parameters(step)
             self._mod.set("P", self._forcing("P", "Precipitation", "/inmaps/P", step, 0.0))
             self._mod.set("PET", self._forcing("PET", "EvapoTranspiration", "/inmaps/PET", step, 0.0))
             if self.modelSnow:
