@@ -53,6 +53,7 @@ def test_one_full_basin_matches_the_oracle():
     mask = common.network_mask(orc)
     forc = synth.Forcing(n, n, seed=5, timestepsecs=args.timestepsecs, rain_mean=20.0)
     states = common.state_names(4)
+    n_out = 0
     for t in range(3):
         P, PET, T = forc.step(t)
         for m in (orc, mod):
@@ -78,10 +79,10 @@ def test_one_full_basin_matches_the_oracle():
                   "SoilThickness", float(orc["SoilThickness"].ravel()[i]))
         # The reference's algorithm is discontinuous at the float32-ulp level (exact-zero early-out of
         # kinematic_wave_ssf, its = ceil(..), zi > top layer membership: tests/test_reference_sensitivity.py);
-        # among 16.8 M cells a handful sit on such an edge in any given step.  All others: rel 1e-5.
+        # among a million cells a handful sit on such an edge in any given step.  All others: rel 1e-5.
         assert idx.size <= 16, "step %d: %d cells outside rel 1e-5" % (t, idx.size)
         n_out += idx.size
-    print("config 2: %d of %d cell-steps outside rel 1e-5" % (n_out, 2 * mod.num_cells))
+    print("one 1024^2 basin: %d of %d cell-steps outside rel 1e-5" % (n_out, 3 * mod.num_cells))
     assert float(orc["RiverRunoff"][mask].max()) > 1.0  # the rivers carry water
     mod.close()
 

@@ -204,6 +204,7 @@ LateralPlan plan_lateral(int64_t n, int64_t D, int64_t nbasins, int sms) {
 
 template <int ML>
 int launch_lateral(wf_model *m) {
+  if (const char *iv = std::getenv("WF_LAT_INTERLEAVE")) m->dm.lat_interleave = std::atoi(iv);  // development aid
   void *args[] = {(void *)&m->dm};
   if (m->lat_mode == WF_GRID) {
     if (m->lat_blocks == 0) {
@@ -837,6 +838,7 @@ static int create_impl(wf_model *m, const wf_config *cfg, wf_schedule *sched, co
   dm.beta = m->cfg.beta;
   dm.task_mask = 7;
   if (const char *tm = std::getenv("WF_LATERAL_TASKS")) dm.task_mask = std::atoi(tm);
+  dm.lat_interleave = 1;
 #ifdef WF_PROFILE
   if (std::getenv("WF_TICK_PROFILE")) {
     const size_t nt = (size_t)(m->net.nlevels() + 16 + cfg->it_kin_r) * 16;

@@ -836,7 +836,12 @@ __global__ void __launch_bounds__(wf_block_threads(MODE), 1) k_lateral_wave(cons
   // grid: every block sweeps the one group; otherwise cluster (or block) c takes groups c, c + nclusters, ...
   const int nclusters = (MODE == WF_GRID) ? 1 : (int)gridDim.x / csize;
   const int cid = (MODE == WF_GRID) ? 0 : (int)blockIdx.x / csize;
-  const int tid = (MODE == WF_GRID) ? (int)(blockIdx.x * blockDim.x + threadIdx.x) : crank * (int)blockDim.x + (int)threadIdx.x;
+  // Position in the flat item space of a tick.  The item space is type-major ([subsurface | overland | river], the
+  // subsurface items the longest), so with block-major positions the first block of a cluster ran nothing but
+  // subsurface solves and the last one a few river cells: consecutive item warps are dealt round robin to the blocks
+  // instead, and every SM of the cluster gets the same mix.
+  int tid = (MODE == WF_GRID) ? (int)(blockIdx.x * blockDim.x + threadIdx.x) : crank * (int)blockDim.x + (int)threadIdx.x;
+  if (wf_is_cluster(MODE) && m.lat_interleave) tid = (((int)threadIdx.x >> 5) * csize + crank) * 32 + ((int)threadIdx.x & 31);
   const int nthreads = (MODE == WF_GRID) ? (int)(gridDim.x * blockDim.x) : csize * (int)blockDim.x;
   WaveSync ws;
   ws.counter = m.grid_counter;
