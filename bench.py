@@ -30,9 +30,9 @@ sys.path.insert(0, ROOT)
 BYTES_VERTICAL = 236  # algorithmic bytes per cell-step of the vertical kernel, 4 layers, snow on
 BYTES_FULL = 333      # full step incl. lateral statics, routing states and topology
 # DRAM traffic of one k_vertical launch per cell, from the round's `ncu --set full` capture of the default
-# workload (profiles/r1_vertical_ncu_details.txt: dram__bytes_read.sum + dram__bytes_write.sum = 13.62 GB for
+# workload (profiles/r1_vertical_ncu_details.txt: dram__bytes_read.sum + dram__bytes_write.sum = 11.75 GB for
 # 33 554 431 cells).  Above the algorithmic 236 B: float64 hand-offs, derived statics, register spills.
-TRAFFIC_VERTICAL_PER_CELL = 405.8
+TRAFFIC_VERTICAL_PER_CELL = 350.1
 
 
 def parse():
@@ -386,7 +386,7 @@ def run_b200(args):
                          "bytes_per_cell": BYTES_VERTICAL, "cells_per_launch": ncell, "ms_per_launch": v_launch_ms,
                          "traffic": TRAFFIC_VERTICAL_PER_CELL * ncell,
                          "traffic_source": "ncu --set full, profiles/r1_vertical_ncu_details.txt (per cell x cells of this launch)",
-                         "bound_note": "the kernel is instruction-issue bound (ncu: issue slots busy 57 %, DRAM 30 %), "
+                         "bound_note": "the kernel is instruction-issue bound (ncu: issue slots busy 66 %, DRAM 31 %), "
                                        "not HBM-bound; the HBM fraction is reported as the contract asks",
                          "full_step_gbs_at_333B": ncell * BYTES_FULL / ((ms_v + ms_l) / max(nst, 1) / 1e3) / 1e9},
             "kernels_ms_per_step": {"vertical": ms_v / max(nst, 1), "lateral": ms_l / max(nst, 1),

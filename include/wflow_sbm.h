@@ -116,7 +116,12 @@ int wf_catchment_total(const wf_model *m, const float *values, double *out_grid)
 int wf_set_field(wf_model *m, const char *name, const float *grid);        /* host raster -> device */
 int wf_set_field_uniform(wf_model *m, const char *name, float value);
 int wf_get_field(wf_model *m, const char *name, float *grid, float mv);    /* device -> host raster */
-/* Enable (1) / disable (0) a diagnostic output so that the kernels materialise it. */
+/* Optional statics switch parts of the step on by being set: GlacierFrac / G_TT / G_Cfmax / G_SIfrac (with
+ * cfg.glacier; glacierHBV, wflow/wflow_funcs.py:549-603) and LAI / Sl / Swood / Kext (LAI-driven Cmax,
+ * CanopyGapFraction and EoverR, wflow/wflow_sbm.py:2587-2603; wf_step fails with WF_EINVAL if LAI is set and one of
+ * the other three is not). */
+/* Enable (1) / disable (0) a diagnostic output so that the kernels materialise it.  With no diagnostic requested
+ * the step runs builds of the kernels that have the outputs compiled out. */
 int wf_request_output(wf_model *m, const char *name, int enable);
 /* Number of known field names and the i-th name / kind (0 forcing, 1 static, 2 state, 3 diagnostic). */
 int wf_num_fields(void);

@@ -60,7 +60,7 @@ def launches(src, dest, header):
         for r in rows[1:]:
             v = float(r[vi].replace(",", ""))
             us = v / 1e3 if r[ui] in ("ns", "nsecond") else (v if r[ui] in ("us", "usecond") else v * 1e3)
-            fh.write("%s,%s,%s,%s,%.1f\n" % (r[0], r[ki].split("(")[0], r[bi].replace(",", " "), r[gi].replace(",", " "), us))
+            fh.write("%s,%s,%s,%s,%.1f\n" % (r[0], r[ki].split("(")[0].replace(", ", ";"), r[bi].replace(",", " "), r[gi].replace(",", " "), us))
     print("wrote", dest)
 
 
@@ -88,5 +88,6 @@ if __name__ == "__main__":
                 "# command: python scripts/pipe_bench.py --basins 8 --modes grid --ks 8")
     launches(os.path.join(G, "launches_r1.csv"), "r1_launches_ncu.csv",
              "# ncu launch list (round 1): %s  (32 basins of 1024^2, default workload)\n"
-             "# ncu --metrics gpu__time_duration.sum --clock-control none -c 80; per-launch times are cold-cache and serialised: compare SHARES\n"
-             "# (the first 76 launches are the k_gather uploads of the model's rasters; the last four are the first step)" % cmd)
+             "# ncu --metrics gpu__time_duration.sum --clock-control none -c 400; per-launch times are cold-cache and serialised: compare SHARES\n"
+             "# (k_gather = uploads of the model's rasters and of the forcing; k_vertical<4;0> + k_lateral_wave<4;3;0> = one timestep:\n"
+             "#  column 4.64-4.73 ms + sweep 7.90-8.05 ms here, 5.02 + 7.88 ms by CUDA events inside bench.py -- share of the step 37 %% / 63 %% vs 39 %% / 61 %%)" % cmd)
