@@ -1,0 +1,83 @@
+"""[modelparameters] of the ini (wf_updateparameters, reference wf_DynamicFramework.py:708-874, 1624-1690): every
+supported type on a synthetic case directory, with the CPU oracle behind the framework (host logic, no GPU)."""
+import os
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture()
+def case(tmp_path, monkeypatch):
+    import wflow_b200.framework as fw
+    from tests.oracle_backend import OracleSbmModel
+    from wflow_b200 import csf, synth
+    monkeypatch.setattr(fw, "SbmModel", OracleSbmModel)
+    d = str(tmp_path / "case")
+    synth.write_case_dir(d, nsteps=4)
+    _, info = csf.read_map(os.path.join(d, "staticmaps", "wflow_dem.map"))
+    shape = (info.nrow, info.ncol)
+    csf.write_map(os.path.join(d, "staticmaps", "myroot.map"), np.full(shape, 123.0, np.float32), info)
+    for step in (1, 2, 3, 4):                               # a map stack read every step
+        csf.write_map(fw.generate_name_t(os.path.join(d, "inmaps", "CM"), step), np.full(shape, 0.1 * step, np.float32), info)
+    for month in (1, 12):                                   # monthly climatology (the run is in January; the clock
+        a = np.full(shape, float(month), np.float32)        # starts one step before starttime: 31 December)
+        a[0, 0] = np.nan                                    # covered with the default
+        csf.write_map(fw.generate_name_t(os.path.join(d, "inmaps", "LAI"), month), a, info)
+    with open(os.path.join(d, "intbl", "Kext.tbl"), "w") as fh:   # lookup on one map: the land use
+        fh.write("[1,1] 0.5\n[2,> 0.7\n")
+    with open(os.path.join(d, "intbl", "KsatVer2.tbl"), "w") as fh:  # landuse, subcatchment, soil
+        fh.write("<,> [1,1] <,> 111\n<,> [2,2] <,> 222\n")
+    with open(os.path.join(d, "wflow_sbm.ini"), "a") as fh:
+        fh.write("\n[modelparameters]\n"
+                 "RootingDepth=staticmaps/myroot.map,staticmap,100,1\n"
+                 "KsatVer=intbl/KsatVer2.tbl,statictbl,500,1\n"
+                 "Cmax=inmaps/CM,timeseries,1.0,0\n"
+                 "LAI=inmaps/LAI,monthlyclim,2.5,1\n"
+                 "Kext=intbl/Kext.tbl,tbl,0.6,1,staticmaps/wflow_landuse.map\n"
+                 "Sl=intbl/nosuchtable.tbl,tbl,0.04,1,staticmaps/wflow_landuse.map\n"
+                 "Swood=intbl/nosuchtable.tbl,tbl,0.25,1,staticmaps/wflow_landuse.map\n"
+                 "Bogus=too,short\n")
+    return d
+
+
+def test_every_parameter_type_reaches_the_model(case):
+    from wflow_b200 import csf
+    from wflow_b200.framework import WflowSbm
+    m = WflowSbm(Dir=case, RunDir="run1")
+    m.createRunId()
+    m._runInitial()
+    m._runResume()
+    assert [p["name"] for p in m._modelparameters] == ["RootingDepth", "KsatVer", "Cmax", "LAI", "Kext", "Sl", "Swood"]
+    inside = m._mod._mask
+    get = lambda k: m._mod.get(k)
+    assert np.all(get("RootingDepth")[inside] == 123.0)                  # staticmap
+    sub, _ = csf.read_map(os.path.join(case, "staticmaps", "wflow_subcatch.map"))
+    # statictbl replaces the raster BEFORE the derivations: KsatVer is scaled by timestepsecs / basetimestep (= 1 here)
+    assert np.all(get("KsatVer")[inside & (sub == 1)] == 111.0) and np.all(get("KsatVer")[inside & (sub == 2)] == 222.0)
+    lu, _ = csf.read_map(os.path.join(case, "staticmaps", "wflow_landuse.map"))
+    assert np.allclose(get("Kext")[inside & (lu == 1)], 0.5) and np.allclose(get("Kext")[inside & (lu >= 2)], 0.7)  # tbl
+    assert np.allclose(get("Sl")[inside], 0.04) and np.allclose(get("Swood")[inside], 0.25)  # missing table: default
+    # the clock of dynamic() starts one step before starttime (1 January): 31 December for the first step
+    assert m._climate_datetime(1).month == 12 and m._climate_datetime(2).month == 1
+    for step, month in ((1, 12.0), (2, 1.0), (3, 1.0), (4, 1.0)):
+        m._runDynamic(step, step)
+        assert np.allclose(get("Cmax")[inside], 0.1 * step)             # timeseries: a new map every step
+        lai = get("LAI")
+        assert np.all(lai[inside][1:] == month)                          # monthlyclim
+        if inside[0, 0]:
+            assert lai[0, 0] == 2.5                                      # missing value -> default
+    m._runSuspend()
+    m._wf_shutdown()
+
+
+def test_unsupported_time_dependent_parameter_is_refused_loudly(case, caplog):
+    from wflow_b200.framework import WflowSbm
+    with open(os.path.join(case, "wflow_sbm.ini"), "a") as fh:
+        fh.write("M=inmaps/M,monthlyclim,300,1\n")   # M feeds derived statics (f, Kh): not updatable per step
+    m = WflowSbm(Dir=case, RunDir="run2")
+    m.createRunId()
+    import logging
+    with caplog.at_level(logging.WARNING, logger="wflow_b200"):
+        m._runInitial()
+    assert any("M: time-dependent values of this parameter are not supported" in r.message for r in caplog.records)
+    m._wf_shutdown()

@@ -59,6 +59,14 @@ def run_test_wflow_sbm(tmp_path):
     assert _csv_sum(case, "unittestsbm", "1P.csv") > sump
     tss = open(os.path.join(case, "unittestsbm", "runmm.tss")).read().splitlines()
     assert tss[0] == "timeseries scalar" and tss[2] == "timestep"
+    # [summary_sum] / [summary_max] / [summary_avg] of the ini (wf_savesummarymaps)
+    from wflow_b200 import csf
+    tot, _ = csf.read_map(os.path.join(case, "unittestsbm", "outsum", "Sumprecip.map"))
+    mx, _ = csf.read_map(os.path.join(case, "unittestsbm", "outsum", "maxprecip.map"))
+    avg, _ = csf.read_map(os.path.join(case, "unittestsbm", "outsum", "avgprecip.map"))
+    inside = ~np.isnan(tot)
+    assert inside.sum() == 15754
+    assert np.allclose(tot[inside], sump) and np.allclose(mx[inside], 5.0) and np.allclose(avg[inside], sump / 29.0)
 
 
 def run_test_wflow_sbm_dynveg(tmp_path):

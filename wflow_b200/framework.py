@@ -113,6 +113,15 @@ def window_average(a, ncells):
         return np.where(den > 0, num / den, np.nan).astype(F32)
 
 
+def area_majority(a, idmap, ids):
+    """pcr.areamajority: the value occurring most often within each area; of several such values the highest."""
+    out = np.zeros(len(ids), F32)
+    for k, i in enumerate(ids):
+        u, c = np.unique(a[idmap == i], return_counts=True)
+        out[k] = u[len(c) - 1 - int(np.argmax(c[::-1]))]
+    return out
+
+
 class WflowSbm:
     """One wflow_sbm run on one GPU, driven like the reference's WflowModel + wf_DynamicFramework."""
 
@@ -362,8 +371,27 @@ class WflowSbm:
         for name in self._state_names():
             csf.write_map(os.path.join(directory, name + ".map"), self._mod.get(name, MV), self._info, mv=MV)
 
+    def wf_savesummarymaps(self):
+        """[summary]: end values; [summary_*]: the statistics gathered over the run (wf_DynamicFramework.py:1886-1951)."""
+        os.makedirs(os.path.join(self.SaveDir, "outsum"), exist_ok=True)
+        if self.config.has_section("summary"):
+            for var, fname in self.config.items("summary"):
+                name = var.replace("self.", "")
+                try:
+                    a = self._mod.get(self._ALIAS.get(name, name), MV)
+                except Exception:
+                    self.logger.warning("Could not find or save the configured summary map:" + var)
+                    continue
+                csf.write_map(os.path.join(self.SaveDir, "outsum", fname), a, self._info, mv=MV)
+        for st in getattr(self, "_stats", []):
+            if st["count"] == 0:
+                continue
+            d = st["data"] / F32(st["count"]) if st["mode"] == "avg" else st["data"]
+            csf.write_map(st["path"], np.where(np.isnan(d), F32(MV), d).astype(F32), self._info, mv=MV)
+
     def _runSuspend(self):
         self.wf_suspend(os.path.join(self.SaveDir, "outstate"))
+        self.wf_savesummarymaps()
         if int(configget(self.config, "model", "OverWriteInit", "0")):
             self.wf_suspend(os.path.join(self.Dir, "instate"))
 
@@ -602,7 +630,25 @@ class WflowSbm:
                         self.logger.warning("output %s skipped: %s" % (var, ex))
                         continue
                     self._outputs.append(dict(kind=kind, area=area, ids=uniq, func=func, terms=terms, zero_col=zero_col,
-                                              path=os.path.join(self.SaveDir, fname)))
+                                              idmap=ids, path=os.path.join(self.SaveDir, fname)))
+        # [summary_sum] / [summary_avg] / [summary_min] / [summary_max]: wf_sumavg, wf_DynamicFramework.py:362-401, 1596-1617
+        self._stats = []
+        for mode in ("sum", "avg", "min", "max"):
+            sec = "summary_" + mode
+            if not self.config.has_section(sec):
+                continue
+            for var, fname in self.config.items(sec):
+                if "self." not in var:
+                    raise ValueError("Entry in ini invalid: " + var)
+                name = var.split("self.")[1]
+                try:
+                    self._mod.request(self._ALIAS.get(name, name))
+                    self._mod.device_ptr(self._ALIAS.get(name, name))
+                except Exception as ex:
+                    self.logger.warning("summary map %s skipped: %s" % (var, ex))
+                    continue
+                self._stats.append(dict(name=name, mode=mode, data=None, count=0,
+                                        path=os.path.join(self.SaveDir, "outsum", fname)))
         self._outmaps = []
         if self.config.has_section("outputmaps"):
             for var, prefix in self.config.items("outputmaps"):
@@ -618,9 +664,13 @@ class WflowSbm:
     def _write_outputs(self, step):
         for o in self._outputs:
             vals = None
-            for t in o["terms"]:
-                v = self._mod.area_reduce(o["area"], self._ALIAS.get(t, t), o["func"] if o["func"] != "majority" else "maximum")
-                vals = v if vals is None else vals + v
+            if o["func"] == "majority":  # pcr.areamajority of the (summed) raster: host side, rarely used
+                a = sum(self._mod.get(self._ALIAS.get(t, t), MV).astype(F32) for t in o["terms"])
+                vals = area_majority(a, o["idmap"], o["ids"])
+            else:
+                for t in o["terms"]:
+                    v = self._mod.area_reduce(o["area"], self._ALIAS.get(t, t), o["func"])
+                    vals = v if vals is None else vals + v
             ids = ([0] if o["zero_col"] else []) + [int(i) for i in o["ids"]]
             vals = ([0.0] if o["zero_col"] else []) + [float(x) for x in vals]
             fh = self._files.get(o["path"])
@@ -633,6 +683,18 @@ class WflowSbm:
                     fh.write("".join("%d\n" % i for i in ids))
             sep = "," if o["kind"] == "csv" else " "
             fh.write(str(step - 1) + sep + sep.join(repr(x) for x in vals) + "\n")  # row label = step-1 (:494)
+        for st in self._stats:  # add_one, after every timestep (:3010-3012)
+            a = self._mod.get(self._ALIAS.get(st["name"], st["name"]), MV)
+            a = np.where(a == F32(MV), F32(np.nan), a).astype(F32)
+            if st["count"] == 0:
+                st["data"] = a
+            elif st["mode"] in ("sum", "avg"):
+                st["data"] = (st["data"] + a).astype(F32)
+            elif st["mode"] == "max":
+                st["data"] = np.where(np.isnan(st["data"]) | np.isnan(a), F32(np.nan), np.maximum(st["data"], a))
+            else:
+                st["data"] = np.where(np.isnan(st["data"]) | np.isnan(a), F32(np.nan), np.minimum(st["data"], a))
+            st["count"] += 1
         for name, prefix in self._outmaps:
             path = generate_name_t(os.path.join(self.SaveDir, "outmaps", prefix), step)
             csf.write_map(path, self._mod.get(self._ALIAS.get(name, name), MV), self._info, mv=MV)
