@@ -305,21 +305,15 @@ int launch_step(wf_model *m) {
   const int tb = WF_VERT_THREADS;
   prepare_step<ML>(m);
   const size_t vsmem = WF_VERT_STAGE ? VLayout<ML>::bytes(m->dm.glacier != 0) : 0;
-  if (!m->vert_attr_set) {
-    if (vsmem > 48 * 1024) {
-      CUDA_OK(cudaFuncSetAttribute((void *)k_vertical<ML, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
-      CUDA_OK(cudaFuncSetAttribute((void *)k_vertical<ML, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
-    }
-    if (VScratch<ML>::enabled) {  // WF_VERT_MINBLOCKS blocks with their scratch must fit the shared-memory carve-out
-      CUDA_OK(cudaFuncSetAttribute((void *)k_vertical<ML, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-      CUDA_OK(cudaFuncSetAttribute((void *)k_vertical<ML, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    }
-    m->vert_attr_set = true;
-  }
-  if (m->dm.any_diag)
-    k_vertical<ML, true><<<(unsigned)((n + tb - 1) / tb), tb, vsmem, m->stream>>>(m->dm);
-  else
-    k_vertical<ML, false><<<(unsigned)((n + tb - 1) / tb), tb, vsmem, m->stream>>>(m->dm);
+  // four builds of the column: with / without the diagnostic outputs, with / without the LAI-driven canopy parameters
+  void (*kv)(const DevModel) = nullptr;
+  const bool lai = m->dm.f[F_LAI] != nullptr;
+  if (m->dm.any_diag) kv = lai ? k_vertical<ML, true, true> : k_vertical<ML, true, false>;
+  else kv = lai ? k_vertical<ML, false, true> : k_vertical<ML, false, false>;
+  if (vsmem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute((void *)kv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
+  if (VScratch<ML>::enabled)  // WF_VERT_MINBLOCKS blocks with their scratch must fit the shared-memory carve-out
+    CUDA_OK(cudaFuncSetAttribute((void *)kv, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  kv<<<(unsigned)((n + tb - 1) / tb), tb, vsmem, m->stream>>>(m->dm);
   m->launches++;
   if (m->timed) cudaEventRecord(e1, m->stream);
   if (int rc = launch_lateral<ML>(m)) return rc;

@@ -152,7 +152,7 @@ __device__ __forceinline__ void pipe_group(const DevModel &m, const PipeArgs pa,
       seg_begin(cnt, c0);
       int *counter = cnt_now + (s - s_lo);
       for (int j = take(counter, c0, cnt); j >= 0; j = take(counter, c0, cnt)) {
-        if (j < cnt) column_cell<ML, 1, false, true>(m, (int64_t)b0 + j, nullptr, nullptr, 0, (int64_t)s * pa.fstride, nullptr);
+        if (j < cnt) column_cell<ML, 1, false, true, true>(m, (int64_t)b0 + j, nullptr, nullptr, 0, (int64_t)s * pa.fstride, nullptr);
         __syncwarp();
       }
     }
