@@ -81,3 +81,25 @@ def test_unsupported_time_dependent_parameter_is_refused_loudly(case, caplog):
         m._runInitial()
     assert any("M: time-dependent values of this parameter are not supported" in r.message for r in caplog.records)
     m._wf_shutdown()
+
+
+def test_variable_change_sections(case):
+    """[variable_change_once] scales a parameter before the derivations, [variable_change_timestep] the forcing of every
+    step (wf_multparameters, wf_DynamicFramework.py:622-690)."""
+    from wflow_b200.framework import WflowSbm
+    ref = WflowSbm(Dir=case, RunDir="run_a")
+    ref.createRunId(); ref._runInitial(); ref._runResume()
+    with open(os.path.join(case, "wflow_sbm.ini"), "a") as fh:
+        fh.write("\n[variable_change_once]\nself.PathFrac = self.PathFrac * 2.0\nself.M = self.M * 0.5\nself.Nonsense = self.Nonsense * 3\n"
+                 "\n[variable_change_timestep]\nself.Precipitation = self.Precipitation * 3\n")
+    m = WflowSbm(Dir=case, RunDir="run_b")
+    m.createRunId(); m._runInitial(); m._runResume()
+    inside = m._mod._mask
+    assert np.allclose(m._mod.get("PathFrac")[inside], 2.0 * ref._mod.get("PathFrac")[inside])
+    # f = (thetaS - thetaR) / M is derived from the scaled M (wflow_sbm.py:2159)
+    assert np.allclose(m._mod.get("f")[inside], 2.0 * ref._mod.get("f")[inside], rtol=1e-6)
+    ref._mod.request("Precipitation"); m._mod.request("Precipitation")
+    ref._runDynamic(1, 1); m._runDynamic(1, 1)
+    assert np.allclose(m._mod.get("Precipitation")[inside], 3.0 * ref._mod.get("Precipitation")[inside])
+    assert ref._mod.get("Precipitation")[inside].max() > 0
+    ref._wf_shutdown(); m._wf_shutdown()

@@ -293,6 +293,16 @@ class WflowSbm:
         bf = np.ones(self.shape, F32) if bf is None else np.nan_to_num(bf, nan=0.0).astype(F32)
         base["BankfullDepth"] = np.where(river_b, bf, F32(0.0)).astype(F32)
 
+        # [variable_change_once]: self.X = self.X * c on the parameters read so far (wf_multparameters in initial(),
+        # wflow_sbm.py:1792; wf_DynamicFramework.py:651-690)
+        self._read_variable_changes()
+        for var, fac in self._changes_once:
+            key = {"MaxCanopyStorage": "Cmax", "et_reftopot": "et_RefToPot"}.get(var, var)
+            if key in base:
+                base[key] = (base[key] * F32(fac)).astype(F32)
+                self.logger.warning("Variable change (apply_once) applied to %s with factor %g" % (var, fac))
+            else:
+                self.logger.error("Variable change (apply_once) could not be applied to " + var)
         # [modelparameters] of static type replace the table-derived rasters before the derivations (:719-764)
         self._read_modelparameters()
         for par in self._modelparameters:
@@ -494,7 +504,34 @@ class WflowSbm:
             self._par_loaded[name] = src
             self._mod.set(name, self._parameter_raster(par, step))
 
+    def _read_variable_changes(self):
+        """[variable_change_once] / [variable_change_timestep]: 'self.X = self.X * c' (wf_DynamicFramework.py:1691-1707)."""
+        def section(name):
+            out = []
+            if self.config.has_section(name):
+                for key, val in self.config.items(name):
+                    try:
+                        out.append((key.replace("self.", "").strip(), float(val.split("*")[1])))
+                    except (IndexError, ValueError):
+                        self.logger.error("Variable change not understood: %s = %s" % (key, val))
+            return out
+        self._changes_once = section("variable_change_once")
+        # per timestep the reference multiplies the attribute right after the forcing corrections (wflow_sbm.py:2619);
+        # for the forcing that is a factor on the raster handed to the library (the corrections are products themselves)
+        self._changes_step = {}
+        for var, fac in section("variable_change_timestep"):
+            field = {"Precipitation": "P", "PotenEvap": "PET"}.get(var)
+            if field is None or fac < 0:
+                self.logger.error("Variable change (apply_timestep) could not be applied to " + var)
+            else:
+                self._changes_step[field] = self._changes_step.get(field, 1.0) * fac
+
     def _forcing(self, var, stack_key, default_stack, step, default):
+        a = self._forcing_raw(var, stack_key, default_stack, step, default)
+        fac = getattr(self, "_changes_step", {}).get(var)
+        return a if fac is None else (a * F32(fac)).astype(F32)
+
+    def _forcing_raw(self, var, stack_key, default_stack, step, default):
         if var in self._api_values:  # set through the API: skip the disk for this step (:3300-3306)
             return self._api_values.pop(var)
         prefix = configget(self.config, "inputmapstacks", stack_key, default_stack).lstrip("/")
