@@ -1,14 +1,16 @@
 """Copies the INPUT DATA (maps, tables, ini -- no source code) of the reference's own acceptance
-cases to where the tests find them.  Run in the build container, where /root/reference exists:
+cases to where the tests find them: baseline/_ref/, which is git-ignored (the repository holds no copy
+of reference files) but travels to the GPU box with gpurun.  Run in the build container, where
+/root/reference exists (__graft_entry__.build() does it when the data is missing):
 
     python tests/golden/make_ref_cases.py
 
 * tests/wflow_sbm (the case of the reference's tests/test_wflow_sbm.py; forcing comes through the
   API, so only 8 static maps + the lookup tables + the ini are needed, ~1 MB; plus what its dynamic-vegetation
   variant, tests/test_wflow_sbm_dynveg.py, reads: 3 tables, the land-cover map, 2 months of LAI)
-      -> tests/golden/ref_cases/wflow_sbm/           (committed)
+      -> baseline/_ref/ref_cases/wflow_sbm/
 * examples/wflow_rhine_sbm (the case of tests/test_wflow_sbm_example.py; 132 MB with its forcing)
-      -> baseline/_ref/wflow_rhine_sbm/              (git-ignored; travels to the GPU box with gpurun)
+      -> baseline/_ref/wflow_rhine_sbm/
 """
 import os
 import shutil
@@ -23,7 +25,7 @@ MAPS = ["wflow_subcatch", "wflow_ldd", "wflow_dem", "wflow_river", "wflow_landus
 
 def main():
     src = os.path.join(REF, "tests", "wflow_sbm")
-    dst = os.path.join(ROOT, "tests", "golden", "ref_cases", "wflow_sbm")
+    dst = os.path.join(ROOT, "baseline", "_ref", "ref_cases", "wflow_sbm")
     os.makedirs(os.path.join(dst, "staticmaps"), exist_ok=True)
     for m in MAPS:
         shutil.copyfile(os.path.join(src, "staticmaps", m + ".map"), os.path.join(dst, "staticmaps", m + ".map"))

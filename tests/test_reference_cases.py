@@ -8,7 +8,8 @@
 
 Each runs twice: with the CPU oracle behind the framework (not gpu: this PINS THE ORACLE's full step,
 PCRaster-phase restatement included, to the only numbers the reference holds at that boundary,
-SURVEY.md §8c) and with the CUDA library (gpu).  Input data: tests/golden/make_ref_cases.py."""
+SURVEY.md §8c) and with the CUDA library (gpu).  Input data: copied from the reference checkout into the git-ignored
+baseline/_ref/ by tests/golden/make_ref_cases.py (build() runs it); without it the tests skip."""
 import os
 import shutil
 
@@ -16,9 +17,11 @@ import numpy as np
 import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-CASE_SBM = os.path.join(HERE, "golden", "ref_cases", "wflow_sbm")
+CASE_SBM = os.path.join(os.path.dirname(HERE), "baseline", "_ref", "ref_cases", "wflow_sbm")
 CASE_RHINE = os.path.join(os.path.dirname(HERE), "baseline", "_ref", "wflow_rhine_sbm")
 
+needs_sbm = pytest.mark.skipif(not os.path.isfile(os.path.join(CASE_SBM, "wflow_sbm.ini")),
+                               reason="the reference's tests/wflow_sbm inputs are not in baseline/_ref (tests/golden/make_ref_cases.py)")
 needs_rhine = pytest.mark.skipif(not os.path.isfile(os.path.join(CASE_RHINE, "wflow_sbm.ini")),
                                  reason="the 132 MB Rhine example is not in baseline/_ref (tests/golden/make_ref_cases.py)")
 
@@ -128,10 +131,12 @@ def oracle_engine(monkeypatch):
     monkeypatch.setattr(fw, "SbmModel", OracleSbmModel)
 
 
+@needs_sbm
 def test_oracle_reproduces_reference_test_wflow_sbm(oracle_engine, tmp_path):
     run_test_wflow_sbm(tmp_path)
 
 
+@needs_sbm
 def test_oracle_reproduces_reference_test_wflow_sbm_dynveg(oracle_engine, tmp_path):
     run_test_wflow_sbm_dynveg(tmp_path)
 
@@ -142,11 +147,13 @@ def test_oracle_reproduces_reference_rhine_example(oracle_engine, tmp_path):
 
 
 @pytest.mark.gpu
+@needs_sbm
 def test_cuda_reproduces_reference_test_wflow_sbm(tmp_path):
     run_test_wflow_sbm(tmp_path)
 
 
 @pytest.mark.gpu
+@needs_sbm
 def test_cuda_reproduces_reference_test_wflow_sbm_dynveg(tmp_path):
     run_test_wflow_sbm_dynveg(tmp_path)
 
