@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--basins", type=int, default=32, help="1024^2 basins per GPU (32 = config 3's per-GPU share)")
     ap.add_argument("--tile", type=int, default=1024)
     ap.add_argument("--timestepsecs", type=int, default=3600)
-    ap.add_argument("--cpu-sample-steps", type=int, default=2)
+    ap.add_argument("--cpu-sample-steps", type=int, default=40, help="timesteps of one basin tile timed for cpu_baseline (~10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-single-basin", action="store_true", help="skip the auxiliary single-basin per-step / pipelined measurement")
     return ap.parse_args()
@@ -134,7 +134,7 @@ def it_substeps(args):
     return max(it_l, 1), max(it_r, 1)
 
 
-def cpu_baseline(args, steps, threads):
+def cpu_baseline(args, steps, threads, warmup=1):
     """The oracle port of the reference on ONE basin tile of the same workload (bounded sample)."""
     from oracle import oracle as O
     from wflow_b200 import core, synth
@@ -148,7 +148,8 @@ def cpu_baseline(args, steps, threads):
     forc = synth.Forcing(n, n, seed=5, timestepsecs=args.timestepsecs, rain_mean=20.0)
     P, PET, T = forc.step(0)
     orc.set("P", P); orc.set("PET", PET); orc.set("TEMP", T)
-    orc.step()  # warm-up (page faults, thread pool)
+    for _ in range(max(1, warmup)):
+        orc.step()  # warm-up (page faults, thread pool)
     t0 = time.time()
     for s in range(steps):
         orc.step()
@@ -165,12 +166,14 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    steps = max(1, min(args.steps, 3))
-    cb = cpu_baseline(args, steps, threads)
+    # every step of this arm is one timestep of ONE basin tile (1/32 of the GPU arm's per-GPU shard): K = 20 takes ~5 s
+    steps = max(1, min(args.steps, 200))
+    warm = max(1, min(args.warmup, 5))
+    cb = cpu_baseline(args, steps, threads, warm)
     it_l, it_r = it_substeps(args)
     line = {
         "impl": "reference", "metric": "cell-timesteps/sec (SBM+kinwave)", "value": cb["value"],
-        "unit": "cell-timesteps/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1,
+        "unit": "cell-timesteps/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64 (column, kinematic waves) + f32 (map-algebra phases)", "data": "synthetic",
         "config": workload_config(args, it_l, it_r, sample=cb["sample"]),
