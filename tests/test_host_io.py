@@ -72,3 +72,11 @@ def test_map_stack_names_and_cell_lengths():
     assert generate_name_t("inmaps/TEMP", 1000).endswith("TEMP0001.000")
     latlen, longlen = lattometres(np.array([0.0, 52.0], np.float32))
     assert abs(latlen[0] - 110574.3) < 1.0 and abs(longlen[1] - 68678.0) < 50.0
+
+
+def test_area_majority_takes_the_highest_of_tied_values():
+    """pcr.areamajority as used by wf_OutputTimeSeriesArea (wf_DynamicFramework.py:477-489)."""
+    from wflow_b200.framework import area_majority
+    a = np.array([[1, 1, 2, 2], [3, 3, 3, 5], [7, 8, 8, 7]], np.float32)
+    ids = np.array([[1, 1, 1, 1], [2, 2, 2, 2], [4, 4, 4, 4]])
+    assert list(area_majority(a, ids, [1, 2, 4])) == [2.0, 3.0, 8.0]
