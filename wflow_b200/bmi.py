@@ -9,12 +9,17 @@ role is 0 (input), 2 (state) or 3 (parameter) are served by ``get_value`` (other
 the epoch, UTC; ``update_until`` may step back exactly one step (device-side state snapshot).
 """
 import calendar
+import datetime
 import logging
 import os
 
 import numpy as np
 
 from .framework import WflowSbm, configget
+
+
+def _utc(seconds):
+    return datetime.datetime.fromtimestamp(seconds, datetime.timezone.utc).replace(tzinfo=None)
 
 
 class wflowbmi_csdms:
@@ -127,6 +132,40 @@ class wflowbmi_csdms:
 
     def get_time_step(self):
         return float(self.dynModel.timestepsecs)
+
+    def _set_run_period(self, start=None, end=None):
+        m = self.dynModel
+        if start is not None:  # get_start_time() is the state time, one step before the first forcing
+            m.datetime_start = _utc(start) + datetime.timedelta(seconds=m.timestepsecs)
+        if end is not None:
+            m.datetime_end = _utc(end)
+        m.nrTimeSteps = max(1, int((m.datetime_end - m.datetime_start).total_seconds() // m.timestepsecs) + 1)
+
+    def set_start_time(self, start_time):
+        """wflow_bmi.py:675-701: shift the start of the run (seconds since the epoch, UTC)."""
+        self._set_run_period(start=start_time)
+
+    def set_end_time(self, end_time):
+        """wflow_bmi.py:703-724."""
+        self._set_run_period(end=end_time)
+
+    # ---- attributes = options of the ini, 'section:option' (wflow_bmi.py:726-767) ---------------------
+    def get_attribute_names(self):
+        cfg = self.dynModel.config
+        return [sect + ":" + opt for sect in cfg.sections() for opt in cfg.options(sect)]
+
+    def get_attribute_value(self, attribute_name):
+        path = attribute_name.split(":")
+        if len(path) != 2:
+            raise Warning("attributes should follow the name:option  convention")
+        return self.dynModel.config.get(path[0], path[1])
+
+    def set_attribute_value(self, attribute_name, attribute_value):
+        path = attribute_name.split(":")
+        if len(path) != 2:
+            self.bmilogger.warning("Attributes should follow the name:option  convention")
+            raise Warning("attributes should follow the name:option  convention")
+        self.dynModel.config.set(path[0], path[1], attribute_value)
 
     def get_time_units(self):
         return "seconds since 1970-01-01 00:00:00.0 00:00"

@@ -330,6 +330,14 @@ class WflowSbm:
                 self._mod.set(k, np.where(np.isnan(v), F32(0.0), v))
         self._mod.request("SatWaterDepth")
         self._update_parameters(0, initial=True)
+        # initial() ends with wf_updateparameters(): the forcing of the first timestep is in place (and can be read
+        # back through the API) before the first step
+        saved, self._api_values = self._api_values, {}
+        self._mod.set("P", self._forcing("P", "Precipitation", "/inmaps/P", 1, 0.0))
+        self._mod.set("PET", self._forcing("PET", "EvapoTranspiration", "/inmaps/PET", 1, 0.0))
+        if self.modelSnow:
+            self._mod.set("TEMP", self._forcing("TEMP", "Temperature", "/inmaps/TEMP", 1, 10.0))
+        self._api_values = saved
         self._setup_outputs()
 
     # ---- resume / suspend ------------------------------------------------------------------------
