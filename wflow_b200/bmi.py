@@ -233,3 +233,9 @@ class wflowbmi_csdms:
 
     def get_grid_z(self, long_var_name):
         return np.zeros(self.dynModel.shape, np.float32)
+
+    def get_grid_connectivity(self, long_var_name):
+        raise NotImplementedError  # as the reference does (wflow_bmi.py:1330-1335)
+
+    def get_grid_offset(self, long_var_name):
+        raise NotImplementedError  # wflow_bmi.py:1337-1341
