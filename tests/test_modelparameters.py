@@ -103,3 +103,22 @@ def test_variable_change_sections(case):
     assert np.allclose(m._mod.get("Precipitation")[inside], 3.0 * ref._mod.get("Precipitation")[inside])
     assert ref._mod.get("Precipitation")[inside].max() > 0
     ref._wf_shutdown(); m._wf_shutdown()
+
+
+def test_output_rows_labelled_by_datetime(case):
+    """[outputcsv_N] timeformat = datetime (wf_DynamicFramework.py:493-496)."""
+    from wflow_b200.framework import WflowSbm
+    import configparser
+    cp = configparser.ConfigParser(); cp.optionxform = str
+    cp.read(os.path.join(case, "wflow_sbm.ini"))
+    n = 0
+    while cp.has_section("outputcsv_%d" % n):  # the sections are numbered consecutively (:1722-1778)
+        n += 1
+    with open(os.path.join(case, "wflow_sbm.ini"), "a") as fh:
+        fh.write("\n[outputcsv_%d]\nsamplemap = staticmaps/wflow_subcatch.map\nfunction = total\ntimeformat = datetime\nself.Precipitation = ptot.csv\n" % n)
+    m = WflowSbm(Dir=case, RunDir="run_c")
+    m.createRunId(); m._runInitial(); m._runResume()
+    m._runDynamic(1, 2)
+    m._runSuspend(); m._wf_shutdown()
+    rows = open(os.path.join(case, "run_c", "ptot.csv")).read().splitlines()
+    assert rows[0].startswith("# Timestep,") and rows[1].startswith("1999-12-31 00:00:00,") and rows[2].startswith("2000-01-01 00:00:00,")

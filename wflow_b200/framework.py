@@ -659,6 +659,7 @@ class WflowSbm:
                 n += 1
                 samplemap = self.config.get(sec, "samplemap")
                 func = configget(self.config, sec, "function", "average")
+                tformat = configget(self.config, sec, "timeformat", "steps")
                 ids, _ = csf.read_map(os.path.join(self.Dir, samplemap))
                 ids = np.where(ids > 0, ids, 0).astype(np.int32)
                 # the reference samples np.unique(pcr2numpy(area, 0)): missing cells show up as a first column "0"
@@ -675,7 +676,7 @@ class WflowSbm:
                         self.logger.warning("output %s skipped: %s" % (var, ex))
                         continue
                     self._outputs.append(dict(kind=kind, area=area, ids=uniq, func=func, terms=terms, zero_col=zero_col,
-                                              idmap=ids, path=os.path.join(self.SaveDir, fname)))
+                                              idmap=ids, tformat=tformat, path=os.path.join(self.SaveDir, fname)))
         # [summary_sum] / [summary_avg] / [summary_min] / [summary_max]: wf_sumavg, wf_DynamicFramework.py:362-401, 1596-1617
         self._stats = []
         for mode in ("sum", "avg", "min", "max"):
@@ -727,7 +728,9 @@ class WflowSbm:
                     fh.write("timeseries scalar\n%d\ntimestep\n" % (len(ids) + 1))
                     fh.write("".join("%d\n" % i for i in ids))
             sep = "," if o["kind"] == "csv" else " "
-            fh.write(str(step - 1) + sep + sep.join(repr(x) for x in vals) + "\n")  # row label = step-1 (:494)
+            # row label: currentTimeStep - 1, or with timeformat = datetime the clock of dynamic() (:493-496, 1879-1884)
+            label = str(self._climate_datetime(step)) if o["tformat"] == "datetime" else str(step - 1)
+            fh.write(label + sep + sep.join(repr(x) for x in vals) + "\n")
         for st in self._stats:  # add_one, after every timestep (:3010-3012)
             a = self._mod.get(self._ALIAS.get(st["name"], st["name"]), MV)
             a = np.where(a == F32(MV), F32(np.nan), a).astype(F32)
