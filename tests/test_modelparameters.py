@@ -122,3 +122,18 @@ def test_output_rows_labelled_by_datetime(case):
     m._runSuspend(); m._wf_shutdown()
     rows = open(os.path.join(case, "run_c", "ptot.csv")).read().splitlines()
     assert rows[0].startswith("# Timestep,") and rows[1].startswith("1999-12-31 00:00:00,") and rows[2].startswith("2000-01-01 00:00:00,")
+
+
+def test_command_line_like_the_reference(case):
+    """wflow_sbm.py:3559-3645: -S / -T are times, -P / -p feed the variable_change sections, -I forces a cold start."""
+    from wflow_b200 import framework
+    rc = framework.main(["-C", case, "-R", "cli", "-S", "2000-01-02 00:00:00", "-T", "2000-01-03 00:00:00", "-I",
+                         "-P", "self.PathFrac=self.PathFrac * 2.0", "-p", "self.Precipitation=self.Precipitation * 0.5", "-f"])
+    assert rc == 0
+    import configparser
+    cp = configparser.ConfigParser(); cp.optionxform = str
+    cp.read(os.path.join(case, "cli", "runinfo", "configofrun.ini"))
+    assert cp.get("run", "starttime") == "2000-01-02 00:00:00" and cp.get("run", "reinit") == "1"
+    assert cp.get("variable_change_once", "self.PathFrac") == "self.PathFrac * 2.0"
+    rows = [r for r in open(os.path.join(case, "cli", "specrun.csv")).read().splitlines() if not r.startswith("#")]
+    assert len(rows) == 2  # two timesteps between the two times

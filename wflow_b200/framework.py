@@ -773,21 +773,53 @@ def _repair_ldd(ldd):
 
 
 def main(argv=None):
-    """python -m wflow_b200.framework -C case [-R runId] [-c ini] -- the reference's CLI for the path
-    (wflow/wflow_sbm.py:3531-3645), minus the options that address subsystems out of scope."""
+    """python -m wflow_b200.framework -C case [-R runId] [-c ini] ... -- the reference's command line for the path
+    (wflow/wflow_sbm.py:3531-3645): -C case, -R run id, -c ini file, -S / -T start / end time ("YYYY-MM-DD HH:MM:SS"),
+    -s timestepsecs, -I cold start (reinit), -i intbl directory, -X overwrite instate with the end state,
+    -P / -p 'self.X=self.X * c' as [variable_change_once] / [variable_change_timestep], -l log level, -f overwrite the run.
+    Options that address subsystems out of scope here (-x, -M, -u, -U, -E, -W, -O, -v, -L) are accepted and ignored."""
     import getopt
     import sys
-    opts, _ = getopt.getopt(sys.argv[1:] if argv is None else argv, "C:R:c:T:S:I")
+    args = sys.argv[1:] if argv is None else argv
+    if "-h" in args:
+        print(main.__doc__)
+        return 0
+    opts, _ = getopt.getopt(args, "XL:hC:Ii:v:S:T:WR:u:s:EP:p:x:U:fOc:l:M")
     o = dict(opts)
     m = WflowSbm(Dir=o.get("-C", "."), RunDir=o.get("-R", "run_default"), configfile=o.get("-c", "wflow_sbm.ini"))
+
+    def configset(section, var, value):
+        if not m.config.has_section(section):
+            m.config.add_section(section)
+        m.config.set(section, var, value)
+
+    for k, a in opts:
+        if k in ("-P", "-p"):
+            left, right = a.split("=", 1)
+            configset("variable_change_once" if k == "-P" else "variable_change_timestep", left.strip(), right.strip())
+        elif k == "-X":
+            configset("model", "OverWriteInit", "1")
+        elif k == "-I":
+            configset("run", "reinit", "1")
+        elif k == "-i":
+            configset("model", "intbl", a)
+        elif k == "-s":
+            configset("run", "timestepsecs", a)
+        elif k == "-T":
+            configset("run", "endtime", a)
+        elif k == "-S":
+            configset("run", "starttime", a)
+        elif k == "-l":
+            m.logger.setLevel(getattr(logging, a, logging.INFO))
+        elif k in ("-x", "-M", "-u", "-U", "-E", "-W", "-O", "-v", "-L"):
+            m.logger.warning("option %s addresses a part of the reference that is out of scope here: ignored" % k)
     m.createRunId()
-    if "-I" in o:
-        m.reinit = 1
     m._runInitial()
     m._runResume()
-    m._runDynamic(int(o.get("-S", 1)), int(o.get("-T", 0)) or m.nrTimeSteps)
+    m._runDynamic(1, m.nrTimeSteps)
     m._runSuspend()
     m._wf_shutdown()
+    return 0
 
 
 if __name__ == "__main__":
