@@ -7,10 +7,12 @@ method names, argument meaning and error behaviour -- while every per-timestep c
 libwflowsbm on the GPU (`core.SbmModel`).  Nothing here is executed per cell per step on the host.
 
 Covered: case directory layout (staticmaps/, intbl/, inmaps/ map stacks, instate/, <runId>/outstate,
-outmaps), [run] [model] [layout] [inputmapstacks] [outputmaps] [outputcsv_N] [outputtss_N] [API],
+outmaps, outsum), [run] [model] [layout] [inputmapstacks] [modelparameters] [variable_change_once]
+[variable_change_timestep] [outputmaps] [outputcsv_N] [outputtss_N] [summary] [summary_sum|avg|min|max] [API],
 cold start (reinit = 1) and warm start, wf_suspend / wf_resume, wf_setValues*, wf_supplyMapAsNumpy,
-wf_supplyVariableNamesAndRoles, wf_QuickSuspend/Resume.  Not covered (out of scope):
-netCDF I/O, reservoirs/lakes, irrigation, state updating, LAI, [summary*] maps, variable_change_*.
+wf_supplyVariableNamesAndRoles, wf_QuickSuspend/Resume, LAI-driven canopy parameters, the command line.
+Not covered (out of scope): netCDF I/O (refused loudly), reservoirs / lakes, irrigation, state
+updating, [rollingmean].
 
 The derivations of `initial()` that need PCRaster neighbourhood operators (slope from the DEM, window
 average for the river width) are restated in numpy and are NOT pinned against PCRaster (it cannot be
@@ -187,6 +189,10 @@ class WflowSbm:
 
     def _runInitial(self):
         cfg = lambda k, d: configget(self.config, "model", k, d)
+        for opt in ("netcdfinput", "netcdfstaticinput", "netcdfstatesinput", "netcdfoutput", "netcdfstaticoutput",
+                    "netcdfstatesoutput"):
+            if configget(self.config, "framework", opt, "None") != "None":
+                raise ValueError("[framework] %s: netCDF I/O is not part of this implementation (PCRaster map stacks only)" % opt)
         mapname = lambda k: cfg(k, "staticmaps/%s.map" % k)
         self.modelSnow = int(cfg("ModelSnow", "1"))
         self.soilInfReduction = int(cfg("soilInfRedu", "0"))
