@@ -102,7 +102,6 @@ struct wf_model {
   int64_t max_tick_items = 1;
   bool timed = false;
   bool derived_dirty = true;          // d_efT / d_efST must be recomputed before the next step
-  bool vert_attr_set = false;
   int ML = 1;
   bool external[F_COUNT] = {};        // field bound to a caller-owned device array
   float *owned[F_COUNT] = {};         // our own allocation while an external one is bound
