@@ -171,7 +171,8 @@ class Oracle:
 
     # -- estimate_iterations_kin_wave, wflow/wflow_funcs.py:103-116 --------------------------------
     # PCRaster half of the reference (REAL4 map algebra + np.nanpercentile on the float32 raster):
-    # restated with float32 numpy, parity unpinned (PCRaster cannot be installed here).
+    # restated with float32 numpy; pinned against the reference's own function run through
+    # oracle/pcrshim.py (tests/golden/dyn_courant_hourly.npz, tests/test_oracle_dynamic_golden.py).
     def estimate_iterations(self, which):
         """which = "land": LandRunoffsub / AlphaL / DL (wflow_sbm.py:2911-2921);
         "river": RiverRunoffsub / AlphaR / DCL (:3159-3169)."""

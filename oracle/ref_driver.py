@@ -147,9 +147,9 @@ class ReferenceModel:
             inwater = (inwater + fl["Inflow"]).astype(F32)
         out["Inwater"] = inwater
         qr = (inwater / fl["DCL"]).astype(F32)
-        rr_sub = pre["RiverRunoffsub"].astype(np.float64).ravel().copy()
+        rr_sub = pre["RiverRunoffsub"].astype(F32).ravel().copy()  # pcr2numpy of a REAL4 map: float32 (:3157)
         acc, qnew, wl_r_av, wl_r = self.funcs.kin_wave(
-            self.rnodes, self.rnodes_up, rr_sub, qr.astype(np.float64).ravel(), st["AlphaR"], st["Beta"], st["DCL"],
+            self.rnodes, self.rnodes_up, rr_sub, qr.astype(F32).ravel(), st["AlphaR"], st["Beta"], st["DCL"],
             st["River"], st["Bw"], st["AlphaR"], st["Beta"], dt, int(p.it_kinR))
         out["RiverRunoff"] = (acc / dt).astype(F32).reshape(shape)
         out["WaterLevelR"] = wl_r_av.astype(F32).reshape(shape)

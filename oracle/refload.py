@@ -1,9 +1,10 @@
 """Stub-loader for the reference's numba kernels (TEST INFRASTRUCTURE ONLY).
 
 Loads ``wflow/wflow_funcs.py`` and ``wflow/wflow_sbm.py`` from the read-only
-reference checkout *by file path*, with empty stand-ins for the modules the
-reference imports but this container does not have (pcraster, osgeo, pyproj …;
-SURVEY.md §8c / Appendix D).  Nothing is copied; the reference files are executed
+reference checkout *by file path*, with stand-ins for the modules the reference
+imports but this container does not have: ``pcraster`` is the float32-numpy shim of
+oracle/pcrshim.py (so the reference's map algebra runs too, unmodified), osgeo /
+wflow_adapt are empty.  Nothing is copied; the reference files are executed
 where they lie.  Only usable where ``/root/reference`` exists (this container) —
 never on the GPU box, and never from the product path.
 
@@ -40,15 +41,20 @@ def load():
         return m
 
     if "pcraster" not in sys.modules:
-        pcr = _stub("pcraster")
+        # the float32-numpy shim (oracle/pcrshim.py): the reference's map algebra runs unmodified on it
+        from . import pcrshim
+        sys.modules["pcraster"] = pcrshim
         fw = _stub(
             "pcraster.framework",
             DynamicModel=type("DynamicModel", (), {"__init__": lambda s: None}),
         )
-        pcr.framework = fw
+        pcrshim.framework = fw
+    for name in ("osgeo", "osgeo.gdal", "osgeo.gdalconst", "osgeo.ogr", "osgeo.osr"):
+        if name not in sys.modules:
+            _stub(name)
+    sys.modules["osgeo"].gdal = sys.modules["osgeo.gdal"]
     if "wflow" not in sys.modules:
         _stub("wflow").__path__ = []
-        _stub("wflow.wf_DynamicFramework")
         _stub("wflow.wflow_adapt")
 
     def _load(name, path):
@@ -58,6 +64,11 @@ def load():
         spec.loader.exec_module(m)
         return m
 
+    # wflow_lib holds sum_list_cover / idtoid, which wflow_sbm receives through
+    # "from wflow.wf_DynamicFramework import *" (the framework itself is not loaded: it needs osgeo, netCDF4 ...)
+    wlib = _load("wflow.wflow_lib", os.path.join(REFERENCE_ROOT, "wflow", "wflow_lib.py"))
+    if "wflow.wf_DynamicFramework" not in sys.modules:
+        _stub("wflow.wf_DynamicFramework", **{k: v for k, v in vars(wlib).items() if not k.startswith("_")})
     funcs = _load("wflow.wflow_funcs", os.path.join(REFERENCE_ROOT, "wflow", "wflow_funcs.py"))
     sbm = _load("wflow.wflow_sbm", os.path.join(REFERENCE_ROOT, "wflow", "wflow_sbm.py"))
     _cache["mods"] = (funcs, sbm)

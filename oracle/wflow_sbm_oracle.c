@@ -11,17 +11,17 @@
  *     PINNED -- validated element-wise against the reference's own numba kernels run
  *     in the build container (oracle/gen_golden.py -> tests/golden/*.npz,
  *     tests/test_oracle_vs_reference.py).
- *   * PCRaster half (interception, snow, evap split, river inflow glue of
- *     WflowModel.dynamic): PINNED ONLY AT THE REFERENCE'S OWN ACCEPTANCE NUMBERS --
- *     PCRaster cannot be installed here, so there is no element-wise check; the
- *     restatement follows the reference source line by line with REAL4 (float)
- *     arithmetic.  What the reference's tests hold at this boundary, the oracle
- *     reproduces when driven through the framework mirror
- *     (tests/test_reference_cases.py): tests/test_wflow_sbm.py:60-68 (wbsurf / wbsoil /
- *     P sums of the tests/wflow_sbm case) and tests/test_wflow_sbm_example.py:54
- *     (specrun.csv sum of the Rhine example: 0.0432266 here, 0.0432277 there).
- *     Snow, glacier and the modified-Rutter branch are not exercised by those two
- *     cases and remain element-wise UNPINNED.
+ *   * PCRaster half (interception, snow, glacier, LAI-driven canopy parameters, evap split, river
+ *     inflow glue of WflowModel.dynamic): PINNED -- the reference's whole, UNMODIFIED dynamic() is
+ *     executed in the build container with `pcraster` = the float32-numpy shim of oracle/pcrshim.py
+ *     (oracle/ref_dynamic.py), and every state and output of this file is bit-identical to it on nine
+ *     trajectories that put the edge branches on the grid (oracle/gen_golden_dynamic.py ->
+ *     tests/golden/dyn_*.npz, tests/test_oracle_dynamic_golden.py; live re-check in
+ *     tests/test_oracle_vs_reference.py).  What the shim cannot verify about PCRaster itself is listed
+ *     in its header (float32 libm vs. rounded float64 for ln / exp / pow).
+ *     The first run of that pin found one deviation, fixed since: kin_wave receives a REAL4 array and
+ *     writes into it, so the river outflow is rounded to float32 BETWEEN sub-steps (see below).
+ *     The reference's acceptance numbers are reproduced as well (tests/test_reference_cases.py).
  *
  * Each function cites the reference file:line it follows (paths relative to the
  * reference checkout).  Written from the behaviour of that code, not copied from it.
@@ -952,7 +952,9 @@ int wfo_step(const wfo_params *p, const wfo_network *net, const wfo_network *rne
           racc[idx] = racc[idx] + qn * (dt / itR);
           rwl[idx] = (A * pow(qn, B)) / (double)F(Bw)[idx];
           racch[idx] = racch[idx] + rwl[idx];
-          Qold[idx] = qn;
+          /* the caller hands kin_wave a REAL4 array (pcr2numpy of the RiverRunoffsub map, wflow_sbm.py:3157) and
+             kin_wave stores into it (wflow_funcs.py:199): the outflow is rounded to float32 between sub-steps */
+          Qold[idx] = (double)(float)qn;
         }
       }
     }

@@ -117,3 +117,51 @@ def load_golden_case(name, oracle=True, gpu=False):
             if k not in ("River", "Beta", "SatWaterDepth"):
                 mod.set(k, v)
     return g, kw, orc, mod
+
+
+# ---- goldens of the reference's whole dynamic() (tests/golden/dyn_*.npz, oracle/gen_golden_dynamic.py) ----
+def golden_dyn_cases():
+    return sorted(os.path.basename(p)[4:-4] for p in glob.glob(os.path.join(GOLD, "dyn_*.npz")))
+
+
+def dyn_substeps(kw):
+    """(it_kinL, it_kinR) of a dyn golden with fixed sub-steps (wflow_sbm.py:2911-2923, 3159-3171)."""
+    dt = kw.get("dt", 86400)
+    if not kw.get("kinwaveIters", 0):
+        return 1, 1
+    itl = int(np.ceil(dt / kw["landTstep"])) if kw.get("landTstep", 0) else 1
+    itr = int(np.ceil(dt / kw["riverTstep"])) if kw.get("riverTstep", 0) else 1
+    return itl, itr
+
+
+def load_dyn_case(name, oracle=True, gpu=False):
+    """Rebuild the oracle / CUDA model of a dyn golden from its stored inputs.  Returns (g, kw, orc, mod)."""
+    g = np.load(os.path.join(GOLD, "dyn_%s.npz" % name))
+    kw = ast.literal_eval(str(g["meta"]))
+    lt = kw["layer_thickness"]
+    dt = kw.get("dt", 86400)
+    itl, itr = dyn_substeps(kw)
+    static = {k[7:]: g[k] for k in g.files if k.startswith("static/")}
+    state = {k[7:]: g[k] for k in g.files if k.startswith("state0/")}
+    glacier = int(kw.get("glacier", 0))
+    orc = mod = None
+    if oracle:
+        from oracle import oracle as O
+        orc = O.Oracle(g["ldd"], g["river"], timestepsecs=dt, layer_thickness=lt, modelSnow=kw.get("snow", 1), it_kinL=itl,
+                       it_kinR=itr, transferMethod=kw.get("tm", 0), ust=kw.get("ust", 0), soilInfRedu=kw.get("sir", 0),
+                       glacier=glacier)
+        for k, v in {**static, **state}.items():
+            orc.set(k, v)
+    if gpu:
+        from wflow_b200.core import SbmModel
+        mod = SbmModel(g["ldd"], g["river"], timestepsecs=dt, layer_thickness=lt, model_snow=kw.get("snow", 1),
+                       it_kin_l=itl, it_kin_r=itr, transfer_method=kw.get("tm", 0), ust=kw.get("ust", 0),
+                       soil_inf_redu=kw.get("sir", 0), glacier=glacier)
+        for k, v in {**static, **state}.items():
+            if k not in ("River", "Beta", "SatWaterDepth"):
+                mod.set(k, v)
+    return g, kw, orc, mod
+
+
+def dyn_outputs(g, t=0):
+    return sorted(k.split("/")[2] for k in g.files if k.startswith("out/%d/" % t))

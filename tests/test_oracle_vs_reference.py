@@ -33,3 +33,28 @@ def test_oracle_matches_reference_kernels_live():
         out = ref.step(pre, {k: orc[k] for k in gen_golden.PHASE_DIAGS})
         for f in outs:
             assert np.array_equal(orc[f][mask], out[f][mask]), (t, f)
+
+
+def test_oracle_matches_reference_dynamic_live():
+    """The reference's whole, unmodified dynamic() -- PCRaster half through oracle/pcrshim.py -- against the C oracle on a
+    case that is not among the committed goldens (hourly, modified Rutter, snow, sub-steps 2 / 3): bit for bit."""
+    from oracle import ref_dynamic
+    from tests import common
+    from wflow_b200 import synth
+    n = 18
+    orc, _, ldd, river = common.make_pair(n, n, kind="forest", layer_thickness=(120, 250), dt=3600, itL=2, itR=3, seed=9,
+                                          river_area=6, gpu=False)
+    ref = ref_dynamic.RefDynamic(ldd, river, {k: v.copy() for k, v in orc.fields.items()}, timestepsecs=3600,
+                                 layer_thickness=(120, 250), kinwaveIters=1, kinwaveLandTstep=1800, kinwaveRiverTstep=1200)
+    forc = synth.Forcing(n, n, seed=6, timestepsecs=3600, rain_mean=20.0)
+    mask = common.network_mask(orc)
+    names = common.state_names(orc.maxLayers) + ["ThroughFall", "StemFlow", "Interception", "SnowMelt", "RainFallPlusMelt",
+                                                 "PotSoilEvap", "PotTrans", "InwaterMM", "Inwater", "ActEvap", "SurfaceWatbal"]
+    orc.want(*[f for f in names if f not in orc.fields])
+    for t in range(4):
+        P, PET, T = forc.step(t)
+        orc.set("P", P); orc.set("PET", PET); orc.set("TEMP", T)
+        orc.step()
+        ref.step(P, PET, T)
+        for f in names:
+            assert np.array_equal(orc[f][mask], ref.get(f)[mask]), (t, f)

@@ -125,6 +125,12 @@ def lib():
     return l
 
 
+def field_names():
+    """Names of every field the library knows (forcing, statics, states, outputs on request)."""
+    l = lib()
+    return [l.wf_field_name(i).decode() for i in range(l.wf_num_fields())]
+
+
 def check(rc):
     if rc < 0:
         raise WflowLibError("libwflowsbm: %s (code %d)" % (lib().wf_last_error().decode(), rc))
