@@ -117,7 +117,7 @@ struct wf_model {
   float *d_cap_out = nullptr, *d_cap_exp = nullptr;
   int32_t cap_n = 0;
   int pipe_blocks = 0;
-  bool pipe_attr_set = false;
+  size_t pipe_attr_smem = 0;          // dynamic shared memory limit already raised for the pipelined kernel
 };
 
 namespace {
@@ -149,6 +149,11 @@ struct LateralPlan {
 
 template <int ML>
 int resident_clusters(int mode, int cs, size_t smem) {
+  if (smem > 48 * 1024) {  // the occupancy queries below refuse more than the default limit otherwise
+    cudaFuncSetAttribute(k_lateral_wave<ML, WF_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_lateral_wave<ML, WF_CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_lateral_wave<ML, WF_CLUSTER_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
   if (mode == WF_CTA) {
     int per_sm = 0, dev = 0, sms = 0;
     cudaGetDevice(&dev);
@@ -190,7 +195,7 @@ LateralPlan plan_lateral(int64_t n, int64_t D, int64_t nbasins, int sms) {
   const int sizes[] = {1, 2, 4, 8};
   for (int cs : sizes) {
     const int mode = (cs == 1) ? WF_CTA : WF_CLUSTER;
-    const int res = resident_clusters<ML>(mode, cs, 0);
+    const int res = resident_clusters<ML>(mode, cs, StageLayout<ML>::bytes(wf_block_threads(mode)));
     if (res < 1) continue;
     const int64_t G = std::min<int64_t>(nbasins, res);
     if (G < 1) continue;
@@ -221,6 +226,8 @@ int launch_lateral(wf_model *m) {
     return WF_OK;
   }
   const bool cta = m->lat_mode == WF_CTA;
+  // dynamic shared memory: the group's level offsets (when they fit) + the operand staging columns of the block's threads
+  const size_t smem = ((m->lat_smem + 15) & ~(size_t)15) + StageLayout<ML>::bytes(wf_block_threads(m->lat_mode));
   // two builds of every sweep: with the diagnostic outputs (some K_DIAG field requested) and without
   void *fnD = cta ? (void *)k_lateral_wave<ML, WF_CTA, true>
                   : (m->lat_mode == WF_CLUSTER_WIDE ? (void *)k_lateral_wave<ML, WF_CLUSTER_WIDE, true> : (void *)k_lateral_wave<ML, WF_CLUSTER, true>);
@@ -228,18 +235,18 @@ int launch_lateral(wf_model *m) {
                   : (m->lat_mode == WF_CLUSTER_WIDE ? (void *)k_lateral_wave<ML, WF_CLUSTER_WIDE, false> : (void *)k_lateral_wave<ML, WF_CLUSTER, false>);
   void *fn = m->dm.any_diag ? fnD : fnP;
   if (m->lat_blocks == 0) {
-    if (m->lat_smem > 48 * 1024) {
-      CUDA_OK(cudaFuncSetAttribute(fnD, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->lat_smem));
-      CUDA_OK(cudaFuncSetAttribute(fnP, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->lat_smem));
+    if (smem > 48 * 1024) {
+      CUDA_OK(cudaFuncSetAttribute(fnD, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_OK(cudaFuncSetAttribute(fnP, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    const int res = resident_clusters<ML>(m->lat_mode, m->cluster_size, m->lat_smem);
+    const int res = resident_clusters<ML>(m->lat_mode, m->cluster_size, smem);
     if (res < 1) return fail(WF_ENODEVICE, "k_lateral_wave does not fit on the device");
     m->lat_blocks = std::min(res, m->dm.ngroups) * m->cluster_size;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)m->lat_blocks);
   cfg.blockDim = dim3((unsigned)wf_block_threads(m->lat_mode));
-  cfg.dynamicSmemBytes = m->lat_smem;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = m->stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -357,16 +364,17 @@ int setup_sweep(wf_model *m) {
     const int l0 = m->lay.lev0[(size_t)g], r0 = m->rlay.lev0[(size_t)g];
     const int nl = Dn - l0, nrl = Dr - r0;
     const bool rivers = r0 < Dr && (dm.task_mask & 4);
-    const int nticks = nl + 1 + ((r0 < Dr) ? itR : 0);
+    const int nticks = wf_sweep_ticks(nl, r0 < Dr, itR);
     gd[(size_t)g].tick_idx = (uint32_t)tick_total.size();
     gd[(size_t)g].nticks = nticks;
-    for (int t = 0; t < nticks; t++) {
+    for (int t = 0; t < nticks; t++) {  // mirrors sweep_group's item space (lateral.cuh)
       uint32_t items = 0;
+      const int t1 = t - WF_OVL_LAG;
       if (t < nl && (dm.task_mask & 1)) items += ((lo[t + 1] - lo[t]) + 31u) & ~31u;
-      if (t >= 1 && t - 1 < nl && (dm.task_mask & 2)) items += ((lo[t] - lo[t - 1]) + 31u) & ~31u;
+      if (t1 >= 0 && t1 < nl && (dm.task_mask & 2)) items += ((lo[t1 + 1] - lo[t1]) + 31u) & ~31u;
       if (rivers)
         for (int v = 0; v < itR; v++) {
-          const int q = (l0 - 2) - shift - r0 + t - v;
+          const int q = wf_sweep_q0(l0, shift, r0) + t - v;
           if (q >= 0 && q < nrl) items += ro[q + 1] - ro[q];
         }
       tick_total.push_back(items);
@@ -388,7 +396,7 @@ int setup_sweep(wf_model *m) {
   // a group's level offsets and tick sizes live in shared memory during its sweep when they fit
   dm.lev_cache = 0;
   m->lat_smem = 0;
-  if (most * 4 <= ((m->lat_mode == WF_GRID) ? 40 : 160) * 1024) {
+  if (most * 4 <= ((m->lat_mode == WF_GRID) ? 40 : 96) * 1024) {
     dm.lev_cache = (int32_t)most;
     m->lat_smem = (size_t)most * 4;
   }
@@ -397,12 +405,13 @@ int setup_sweep(wf_model *m) {
   // busiest tick of the whole network (grid sweep: no more blocks than it can use)
   const int D = dm.nlev;
   int64_t best = 1;
-  for (int t = 0; t < D + 1 + itR; t++) {
+  for (int t = 0; t < D + 3 + itR; t++) {
     int64_t items = 0;
+    const int t1 = t - WF_OVL_LAG;
     if (t < D) items += m->net.lev_off[(size_t)t + 1] - m->net.lev_off[(size_t)t];
-    if (t >= 1 && t - 1 < D) items += m->net.lev_off[(size_t)t] - m->net.lev_off[(size_t)t - 1];
+    if (t1 >= 0 && t1 < D) items += m->net.lev_off[(size_t)t1 + 1] - m->net.lev_off[(size_t)t1];
     for (int v = 0; v < itR; v++) {
-      const int lr = (t - 2 - v) - dm.rlev_shift;
+      const int lr = (t - 4 - v) - dm.rlev_shift;
       if (lr >= 0 && lr < dm.nrlev) items += m->rnet.lev_off[(size_t)lr + 1] - m->rnet.lev_off[(size_t)lr];
     }
     best = std::max(best, items);
@@ -532,9 +541,9 @@ int launch_pipeline(wf_model *m, DevModel &dmp, const PipeArgs &pa) {
   cfg.attrs = at;
   cfg.numAttrs = cta ? 0 : 1;
   if (m->pipe_blocks == 0) {
-    if (m->lat_smem > 48 * 1024 && !m->pipe_attr_set) {
+    if (m->lat_smem > 48 * 1024 && m->lat_smem > m->pipe_attr_smem) {
       CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->lat_smem));
-      m->pipe_attr_set = true;
+      m->pipe_attr_smem = m->lat_smem;
     }
     int res = 0;
     if (cta) {
@@ -757,12 +766,13 @@ static int create_impl(wf_model *m, const wf_config *cfg, wf_schedule *sched, co
         const int l0 = m->lay.lev0[(size_t)g], r0 = m->rlay.lev0[(size_t)g];
         const int nl = Dn - l0, nrl = Dr - r0;
         double preg = 0, pwide = 0;
-        for (int t = 0; t < nl + 1 + cfg->it_kin_r; t++) {
+        for (int t = 0; t < wf_sweep_ticks(nl, r0 < Dr, cfg->it_kin_r); t++) {
           int64_t items = 0;
+          const int t1 = t - WF_OVL_LAG;
           if (t < nl) items += ((int64_t)(lo[t + 1] - lo[t]) + 31) & ~31LL;
-          if (t >= 1 && t - 1 < nl) items += ((int64_t)(lo[t] - lo[t - 1]) + 31) & ~31LL;
+          if (t1 >= 0 && t1 < nl) items += ((int64_t)(lo[t1 + 1] - lo[t1]) + 31) & ~31LL;
           for (int v = 0; v < cfg->it_kin_r; v++) {
-            const int q = (l0 - 2) - shift - r0 + t - v;
+            const int q = wf_sweep_q0(l0, shift, r0) + t - v;
             if (q >= 0 && q < nrl) items += ro[q + 1] - ro[q];
           }
           const int64_t treg = (int64_t)plan.cs * WF_GROUP_THREADS, twide = (int64_t)plan.cs * WF_GROUP_THREADS_WIDE;

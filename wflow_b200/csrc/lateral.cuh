@@ -283,6 +283,10 @@ __global__ void k_derive_lateral(const DevModel m) {
 // running tick, so that after the barrier only the neighbours' fresh outflows remain to be read
 // (one L2 round trip instead of a DRAM-deep dependent chain).  None of these values is written by
 // another thread during the sweep.
+#ifndef WF_GATHER_NEAR
+#define WF_GATHER_NEAR 3  // upstream neighbours gathered without a branch
+#endif
+
 template <int ML>
 struct SubOps {
   uint32_t us;
@@ -345,10 +349,94 @@ __device__ __forceinline__ void load_riv(const DevModel &m, const int32_t rs, Ri
   o.Bw = __ldg(m.f[F_Bw] + rs);
 }
 
+// ---- operand staging through shared memory (cluster / single-block sweeps) ------------------------
+// The operand sets above are DRAM-cold (every array is touched once per timestep) and the 96/128-register sweeps
+// cannot hold them across the barrier.  So the thread that will run an item next tick has the item's operands
+// copied into its own shared-memory column by cp.async -- no registers, no waiting -- BEFORE it waits at the
+// barrier; after the barrier they are a shared-memory read away and the tick's critical path starts with the
+// gather of the neighbours' fresh outflows instead of a DRAM round trip (r1 tick profile: 1.2 us of 7.9).
+// Layout: word w of thread x at sw[w * T + x] (conflict-free), doubles likewise behind the words.
+template <int ML>
+struct StageLayout {
+  static constexpr int NW = 16 + 2 * ML, ND = 3;  // 4-byte words, 8-byte words per thread
+  __host__ __device__ static constexpr size_t bytes(int threads) { return (size_t)threads * (NW * 4 + ND * 8); }
+};
+__device__ __forceinline__ void cp_async4(void *sdst, const void *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *sdst, const void *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int ML>
+__device__ __forceinline__ void stage_sub(const DevModel &m, const int64_t i, float *sw, double *sd, const int T) {
+  const int x = threadIdx.x;
+  int w = 0;
+#define WF_ST4(src) cp_async4(sw + (w++) * T + x, (src))
+  WF_ST4(m.up_start + i); WF_ST4(m.river_slot + i);
+  WF_ST4(m.f[F_landSlope] + i); WF_ST4(m.f[F_SoilThickness] + i); WF_ST4(m.f[F_thetaS] + i); WF_ST4(m.f[F_thetaR] + i);
+  WF_ST4(m.f[F_KsatVer] + i); WF_ST4(m.f[F_f] + i); WF_ST4(m.f[F_KsatHorFrac] + i); WF_ST4(m.f[F_DW] + i);
+  WF_ST4(m.f[F_DL] + i); WF_ST4(m.f[F_xl] + i); WF_ST4(m.f[F_yl] + i); WF_ST4(m.f[F_zi] + i);
+  WF_ST4(m.f[F_SubsurfaceFlow] + i); WF_ST4(m.h_surplus + i);
+#pragma unroll
+  for (int k = 0; k < ML; k++) { WF_ST4(m.f[F_UStoreLayerDepth_0 + k] + i); WF_ST4(m.h_ulo + (int64_t)k * m.n + i); }
+  cp_async8(sd + 0 * T + x, m.h_r + i); cp_async8(sd + 1 * T + x, m.d_efST + i); cp_async8(sd + 2 * T + x, m.d_cpd + i);
+}
+template <int ML>
+__device__ __forceinline__ void unstage_sub(const DevModel &m, const int64_t i, const float *sw, const double *sd, const int T,
+                                            SubOps<ML> &o) {
+  const int x = threadIdx.x;
+  int w = 0;
+#define WF_UF (sw[(w++) * T + x])
+  o.us = __float_as_uint(WF_UF); o.rs = __float_as_int(WF_UF);
+  o.slope = WF_UF; o.ST = WF_UF; o.thetaS = WF_UF; o.thetaR = WF_UF; o.KsatVer = WF_UF; o.f = WF_UF; o.Kh = WF_UF;
+  o.DW = WF_UF; o.DL = WF_UF; o.xl = WF_UF; o.yl = WF_UF; o.zi = WF_UF; o.ssf_old = WF_UF; o.surplus = WF_UF;
+#pragma unroll
+  for (int k = 0; k < ML; k++) { o.Uhi[k] = WF_UF; o.Ulo[k] = WF_UF; }
+  o.rsum = sd[0 * T + x]; o.efD = sd[1 * T + x]; o.cpd = sd[2 * T + x];
+}
+__device__ __forceinline__ void stage_ovl(const DevModel &m, const int64_t i, float *sw, double *sd, const int T) {
+  const int x = threadIdx.x;
+  int w = 0;
+  WF_ST4(m.up_start + i); WF_ST4(m.river_slot + i); WF_ST4(m.f[F_SW] + i); WF_ST4(m.f[F_AlphaL] + i); WF_ST4(m.f[F_DL] + i);
+  WF_ST4(m.f[F_LandRunoffsub] + i);
+  cp_async8(sd + 0 * T + x, m.d_cpd + i); cp_async8(sd + 1 * T + x, m.h_lq + i); cp_async8(sd + 2 * T + x, m.h_lqb + i);
+}
+__device__ __forceinline__ void unstage_ovl(const DevModel &m, const int64_t i, const float *sw, const double *sd, const int T, OvlOps &o) {
+  const int x = threadIdx.x;
+  int w = 0;
+  o.us = __float_as_uint(WF_UF); o.rs = __float_as_int(WF_UF);
+  o.SW = WF_UF; o.AlphaL = WF_UF; o.DL = WF_UF; o.Qold = WF_UF;
+  o.cpd = sd[0 * T + x]; o.q64 = sd[1 * T + x]; o.qb64 = sd[2 * T + x];
+}
+__device__ __forceinline__ void stage_riv(const DevModel &m, const int32_t rs, float *sw, const int T) {
+  const int x = threadIdx.x;
+  int w = 0;
+  WF_ST4(m.r_up_start + rs); WF_ST4(m.f[F_DCL] + rs); WF_ST4(m.f[F_AlphaR] + rs); WF_ST4(m.f[F_Bw] + rs);
+}
+__device__ __forceinline__ void unstage_riv(const DevModel &m, const int32_t rs, const float *sw, const int T, RivOps &o) {
+  const int x = threadIdx.x;
+  int w = 0;
+  o.us = __float_as_uint(WF_UF); o.DCL = WF_UF; o.A = WF_UF; o.Bw = WF_UF;
+}
+#undef WF_ST4
+#undef WF_UF
+
+// Arrival at the cluster barrier from inside a task (divergent code: the per-thread form of the instruction).
+// A task of the cluster sweeps arrives as soon as what the NEXT tick reads is stored -- the outflow its
+// downstream neighbour gathers -- and does the rest of its work (column tail, step means, the channel's lateral
+// inflow) behind the arrival, while the barrier collects the other warps: r1 profile, 28 % of all stall cycles were
+// warps waiting at the barrier for the subsurface tails, and the barrier itself takes 1.7 us from the last arrival.
+// What a task stores behind its arrival is released by the thread's NEXT arrival, so its readers run two ticks
+// later (sweep_group's schedule).
+__device__ __forceinline__ void wave_arrive_early() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
+
 // ---- task 1: subsurface flow + post-ssf column tail of one cell ------------------------------
 // DIAG = false compiles the diagnostic outputs out (and with them the values they keep alive): the production sweep
-template <int ML, int MODE, bool DIAG = true>
-__device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t i, const SubOps<ML> &o WF_PARGS) {
+// EARLY (cluster sweeps): `signal` = this is the thread's last item of the tick -> arrive at the barrier once the outflow is stored
+template <int ML, int MODE, bool DIAG = true, bool EARLY = false>
+__device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t i, const SubOps<ML> &o, const bool signal WF_PARGS) {
   const int nup = o.nup;
   const uint32_t us = o.us;
   const int32_t rs = o.rs;
@@ -371,26 +459,42 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
   WF_STAMP(0, U[0] + xlyl + ssf_old + rsum + surplus + DW + Kh + zi_old);
   // inflow gather, reference summation order (wflow_sbm.py:395-410)
   double ssf_in = 0.0, ssf_tr = 0.0;
-  double sv[8];
+  // All loads of a cell in flight at once.  Most cells have 0-3 upstream neighbours, so the loads of neighbours 3..7 sit
+  // behind a branch that a warp only takes when one of its cells needs them (predicated-off loads still cost an issue
+  // slot each: the 8-wide gathers were 10 % of the sweep's instructions).
+  double sv[8], tv[8];
 #pragma unroll
-  for (int j = 0; j < 8; j++) sv[j] = (j < nup) ? ldx<MODE>(m.h_ssf + (int64_t)us + j) : 0.0;  // all loads in flight at once
-  if (riverMap) {
-    double tv[8];
+  for (int j = 0; j < 8; j++) { sv[j] = 0.0; tv[j] = 0.0; }
 #pragma unroll
-    for (int j = 0; j < 8; j++) tv[j] = (j < nup) ? ldx<MODE>(m.h_ssf_riv + (int64_t)us + j) : 0.0;
+  for (int j = 0; j < WF_GATHER_NEAR; j++) {
+    if (j < nup) {
+      sv[j] = ldx<MODE>(m.h_ssf + (int64_t)us + j);
+      if (riverMap) tv[j] = ldx<MODE>(m.h_ssf_riv + (int64_t)us + j);
+    }
+  }
+  if (nup > WF_GATHER_NEAR) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
+    for (int j = WF_GATHER_NEAR; j < 8; j++) {
       if (j < nup) {
-        ssf_in = ssf_in + sv[j];  // (1 - chanperc) * ssf of the neighbour
-        ssf_tr = ssf_tr + tv[j];  // chanperc * ssf
+        sv[j] = ldx<MODE>(m.h_ssf + (int64_t)us + j);
+        if (riverMap) tv[j] = ldx<MODE>(m.h_ssf_riv + (int64_t)us + j);
       }
     }
-    m.h_ssf_tr[rs] = (float)qdiv(ssf_tr / (1000 * 1000 * 1000), m.dt);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; j++)
-      if (j < nup) ssf_in = ssf_in + sv[j];
   }
+  // reference summation order (wflow_sbm.py:395-410); the absent neighbours add +0.0, which changes nothing
+#pragma unroll
+  for (int j = 0; j < WF_GATHER_NEAR; j++) {
+    ssf_in = ssf_in + sv[j];  // (1 - chanperc) * ssf of the neighbour (the whole of it for a land receiver)
+    ssf_tr = ssf_tr + tv[j];  // chanperc * ssf
+  }
+  if (nup > WF_GATHER_NEAR) {
+#pragma unroll
+    for (int j = WF_GATHER_NEAR; j < 8; j++) {
+      ssf_in = ssf_in + sv[j];
+      ssf_tr = ssf_tr + tv[j];
+    }
+  }
+  if (riverMap) m.h_ssf_tr[rs] = (float)qdiv(ssf_tr / (1000 * 1000 * 1000), m.dt);
 
   WF_STAMP(1, ssf_in);
   const double neff = (double)neff_f;
@@ -412,6 +516,7 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
   } else {
     m.h_ssf[i] = ssf_n;
   }
+  if (EARLY && signal) wave_arrive_early();  // the downstream cell's gather is all the next tick needs
   m.f[F_zi][i] = (float)zi;
 
   // post-ssf column tail, :707-821
@@ -483,8 +588,8 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
 }
 
 // ---- task 2: overland flow of one cell, all sub-steps (wflow_sbm.py:830-879) -----------------
-template <int MODE, bool DIAG = true>
-__device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i, const OvlOps &o WF_PARGS) {
+template <int MODE, bool DIAG = true, bool EARLY = false>
+__device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i, const OvlOps &o, const bool signal WF_PARGS) {
   const int nup = o.nup;
   const uint32_t us = o.us;
   const int32_t rs = o.rs;
@@ -502,27 +607,45 @@ __device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i
     float *qbuf = (v == itL - 1) ? m.f[F_LandRunoffsub] : m.qo_sub + (int64_t)v * m.n;
     double s1 = 0.0, s2 = 0.0, s3 = 0.0;
     float qv[8];
+    double av[8], bv[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) qv[j] = (j < nup) ? ldx<MODE>(qbuf + (int64_t)us + j) : 0.0f;
-    if (riverMap) {
-      double av[8], bv[8];
+    for (int j = 0; j < 8; j++) { qv[j] = 0.0f; av[j] = 0.0; bv[j] = 0.0; }
+    const double *const qa = m.h_qa + (int64_t)v * m.n + us, *const qb = m.h_qb + (int64_t)v * m.n + us;
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        av[j] = (j < nup) ? ldx<MODE>(m.h_qa + (int64_t)v * m.n + us + j) : 0.0;
-        bv[j] = (j < nup) ? ldx<MODE>(m.h_qb + (int64_t)v * m.n + us + j) : 0.0;
+    for (int j = 0; j < WF_GATHER_NEAR; j++) {
+      if (j < nup) {
+        qv[j] = ldx<MODE>(qbuf + (int64_t)us + j);
+        if (riverMap) { av[j] = ldx<MODE>(qa + j); bv[j] = ldx<MODE>(qb + j); }
       }
+    }
+    if (nup > WF_GATHER_NEAR) {
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
+      for (int j = WF_GATHER_NEAR; j < 8; j++) {
         if (j < nup) {
-          s1 = s1 + av[j];  // (1 - chanperc) * qo of the neighbour
-          s2 = s2 + bv[j];  // chanperc * qo
-          s3 = s3 + (double)qv[j];
+          qv[j] = ldx<MODE>(qbuf + (int64_t)us + j);
+          if (riverMap) { av[j] = ldx<MODE>(qa + j); bv[j] = ldx<MODE>(qb + j); }
         }
+      }
+    }
+    // sums in the reference's neighbour order; absent neighbours add +0.0
+    if (riverMap) {
+#pragma unroll
+      for (int j = 0; j < WF_GATHER_NEAR; j++) {
+        s1 = s1 + av[j];  // (1 - chanperc) * qo of the neighbour
+        s2 = s2 + bv[j];  // chanperc * qo
+        s3 = s3 + (double)qv[j];
+      }
+      if (nup > WF_GATHER_NEAR) {
+#pragma unroll
+        for (int j = WF_GATHER_NEAR; j < 8; j++) { s1 = s1 + av[j]; s2 = s2 + bv[j]; s3 = s3 + (double)qv[j]; }
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; j++)
-        if (j < nup) s1 = s1 + (double)qv[j];
+      for (int j = 0; j < WF_GATHER_NEAR; j++) s1 = s1 + (double)qv[j];
+      if (nup > WF_GATHER_NEAR) {
+#pragma unroll
+        for (int j = WF_GATHER_NEAR; j < 8; j++) s1 = s1 + (double)qv[j];
+      }
     }
     double qo_in, qo_toriver_vol;
     if (riverMap) {
@@ -554,6 +677,7 @@ __device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i
       m.h_qb[(int64_t)v * m.n + i] = o.cpd * (double)qn_f;
     }
   }
+  if (EARLY && signal) wave_arrive_early();  // every sub-step's outflow is stored: the step means and the channel's inflow follow
   m.f[F_WaterLevelLsub][i] = (float)wlsub;
   m.f[F_LandRunoff][i] = (float)qdiv(acc_flow, m.dt);
   m.f[F_WaterLevelL][i] = (float)qdiv(acc_h, (double)itL);
@@ -596,10 +720,21 @@ __device__ __forceinline__ void task_river(const DevModel &m, const int32_t rs, 
   {
     float qv[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) qv[j] = (j < nup) ? ldx<MODE>(qbuf + us + j) : 0.0f;
+    for (int j = 0; j < 8; j++) qv[j] = 0.0f;
 #pragma unroll
-    for (int j = 0; j < 8; j++)
-      if (j < nup) Qin = Qin + (double)qv[j];
+    for (int j = 0; j < WF_GATHER_NEAR; j++)
+      if (j < nup) qv[j] = ldx<MODE>(qbuf + us + j);
+    if (nup > WF_GATHER_NEAR) {
+#pragma unroll
+      for (int j = WF_GATHER_NEAR; j < 8; j++)
+        if (j < nup) qv[j] = ldx<MODE>(qbuf + us + j);
+    }
+#pragma unroll
+    for (int j = 0; j < WF_GATHER_NEAR; j++) Qin = Qin + (double)qv[j];
+    if (nup > WF_GATHER_NEAR) {
+#pragma unroll
+      for (int j = WF_GATHER_NEAR; j < 8; j++) Qin = Qin + (double)qv[j];
+    }
   }
   const double qr = (double)(inw / DCLf);  // :3152 (REAL4 division)
   const double dtr = qdiv(m.dt, (double)itR);
@@ -648,8 +783,15 @@ __device__ __forceinline__ void prefetch_subsurface(const DevModel &m, const int
   prefetch_l2(m.f[F_KsatHorFrac] + i); prefetch_l2(m.f[F_DW] + i); prefetch_l2(m.f[F_DL] + i);
   prefetch_l2(m.f[F_xl] + i); prefetch_l2(m.f[F_yl] + i);
   for (int k = 0; k < m.ML; k++) { prefetch_l2(m.f[F_UStoreLayerDepth_0 + k] + i); prefetch_l2(m.h_ulo + (int64_t)k * m.n + i); }
-  // the overland solve of the same cell follows one tick later
+  prefetch_l2(m.d_efST + i); prefetch_l2(m.d_cpd + i);
+  // the overland solve of the same cell follows two ticks later
   prefetch_l2(m.f[F_SW] + i); prefetch_l2(m.f[F_AlphaL] + i); prefetch_l2(m.f[F_LandRunoffsub] + i);
+  prefetch_l2(m.h_lq + i); prefetch_l2(m.h_lqb + i);
+}
+// the same for a river cell that the first river sub-step reaches soon (the later sub-steps find the lines in L2)
+__device__ __forceinline__ void prefetch_river(const DevModel &m, const int64_t rs) {
+  prefetch_l2(m.r_up_start + rs); prefetch_l2(m.r_nup + rs); prefetch_l2(m.f[F_DCL] + rs); prefetch_l2(m.f[F_AlphaR] + rs);
+  prefetch_l2(m.f[F_Bw] + rs); prefetch_l2(m.f[F_RiverRunoffsub] + rs); prefetch_l2(m.h_rq + rs); prefetch_l2(m.h_rqb + rs);
 }
 
 // Who sweeps a group (a set of whole basins, GroupLayout in network.h), and with which barrier:
@@ -715,33 +857,50 @@ struct WaveItem {
   int type;      // -1 none, 0 subsurface, 1 overland, 2 river
   uint32_t idx;  // storage position (river order for type 2)
   int v;         // river sub-step
+  int nup;       // staged sweeps: number of upstream neighbours, fetched ahead of the barrier with the operands (a byte array:
+                 // not a cp.async size, and the gather of the next tick starts with it)
 };
+
+// Schedule of a group's sweep (local tick t; level = group-local level index):
+//     subsurface flow of level t, overland flow of level t-2, river sub-step v of the river level that is full level t-4-v.
+// The two-tick distances are what the early arrival needs (wave_arrive_early): InwaterO leaves the subsurface
+// task behind its arrival and reaches the overland task of the same cell two ticks later; the channel's lateral
+// inflow likewise from the overland task to the first river sub-step.  D + 3 + it_kinR ticks.
+__host__ __device__ constexpr int wf_sweep_ticks(int nl, bool rivers, int itR) { return rivers ? nl + 3 + itR : nl + 2; }
+// river level (group-local) that sub-step 0 solves at tick 0; sub-step v lags v levels behind
+__host__ __device__ constexpr int wf_sweep_q0(int lev0, int rlev_shift, int rlev0) { return (lev0 - 4) - rlev_shift - rlev0; }
+#define WF_OVL_LAG 2
 
 template <int ML, int MODE, bool DIAG>
 __device__ __forceinline__ void sweep_group(const DevModel &m, const GroupDesc gd, const uint32_t *lo, const uint32_t *ro,
-                                            const uint32_t *tt, const int tid, const int nthreads, WaveSync &ws) {
+                                            const uint32_t *tt, const int tid, const int nthreads, WaveSync &ws, float *stage) {
+  constexpr bool EARLY = wf_is_cluster(MODE);  // arrival as soon as the hand-off to the next tick is stored
+  constexpr bool STAGE = MODE != WF_GRID;      // operands of the coming tick's item through shared memory
   const int D = m.nlev, itR = m.itR;
   const int nl = D - gd.lev0;                        // levels of the group
   const bool rivers = gd.rlev0 < m.nrlev && (m.task_mask & 4);
   const int nrl = rivers ? m.nrlev - gd.rlev0 : 0;   // river levels of the group
-  const int nticks = gd.nticks;  // nl + 1 (+ itR with rivers)
-  // river level (group-local) solved for sub-step 0 at tick 0; sub-step v lags v levels behind
-  const int q0 = (gd.lev0 - 2) - m.rlev_shift - gd.rlev0;
+  const int nticks = gd.nticks;
+  const int q0 = wf_sweep_q0(gd.lev0, m.rlev_shift, gd.rlev0);
+  const int T = (int)blockDim.x;
+  float *const sw = stage;
+  double *const sd = reinterpret_cast<double *>(stage + (size_t)StageLayout<ML>::NW * T);
   // Item space of tick t, every task type starting on a warp boundary (a warp that straddled two
   // types would run both solves one after the other and the whole tick would wait for it):
-  //   [subsurface cells of level t | pad][overland cells of level t-1 | pad][river cells, sub-step 0..itR-1]
+  //   [subsurface cells of level t | pad][overland cells of level t-2 | pad][river cells, sub-step 0..itR-1]
   auto tick_items = [&](int t) -> int { return (int)tt[t]; };  // precomputed on the host (api.cu)
   auto decode_item = [&](int j, int t) -> WaveItem {
     WaveItem it;
-    it.type = -1; it.idx = 0; it.v = 0;
+    it.type = -1; it.idx = 0; it.v = 0; it.nup = 0;
     int cnt0 = 0, cnt1 = 0;
+    const int t1 = t - WF_OVL_LAG;
     if (t < nl && (m.task_mask & 1)) cnt0 = (int)(lo[t + 1] - lo[t]);
-    if (t >= 1 && t - 1 < nl && (m.task_mask & 2)) cnt1 = (int)(lo[t] - lo[t - 1]);
+    if (t1 >= 0 && t1 < nl && (m.task_mask & 2)) cnt1 = (int)(lo[t1 + 1] - lo[t1]);
     const int c0p = (cnt0 + 31) & ~31, c1p = (cnt1 + 31) & ~31;
     if (j < c0p) {
       if (j < cnt0) { it.type = 0; it.idx = lo[t] + (uint32_t)j; }
     } else if (j < c0p + c1p) {
-      if (j - c0p < cnt1) { it.type = 1; it.idx = lo[t - 1] + (uint32_t)(j - c0p); }
+      if (j - c0p < cnt1) { it.type = 1; it.idx = lo[t1] + (uint32_t)(j - c0p); }
     } else if (rivers) {
       int jj = j - c0p - c1p;
 #pragma unroll 1
@@ -756,25 +915,26 @@ __device__ __forceinline__ void sweep_group(const DevModel &m, const GroupDesc g
     }
     return it;
   };
-  // Operand fetch ahead of the barrier where registers allow it (grid sweep: 256 threads per block);
-  // the 512-thread cluster / block sweeps are capped at 128 registers and would spill the operands.
-  constexpr bool PRELOAD = (MODE == WF_GRID);  // subsurface operands (the large set)
-  constexpr bool PRELOAD_SMALL = (MODE != WF_CLUSTER_WIDE);  // overland / river operands (a dozen registers): every
-                                                             // sweep but the 96-register wide blocks (spills: +5 %)
+  // Grid sweep (256 threads per block, registers to spare): the operands of the thread's next item are fetched
+  // into registers ahead of the barrier.  Cluster / block sweeps: into the thread's shared-memory column.
+  constexpr bool PRELOAD = (MODE == WF_GRID);
   SubOps<ML> sub;
   OvlOps ovl;
   RivOps riv;
-  // first item of this thread in the coming tick, with its operands
+  // first item of this thread in the coming tick, with its operands on their way
   auto prepare = [&](int t) -> WaveItem {
     WaveItem it;
-    it.type = -1; it.idx = 0; it.v = 0;
+    it.type = -1; it.idx = 0; it.v = 0; it.nup = 0;
     if (t < nticks && tid < tick_items(t)) {
       it = decode_item(tid, t);
-      if (it.type == 0) {
-        if (PRELOAD) load_sub<ML>(m, (int64_t)it.idx, sub);
-      } else if (PRELOAD_SMALL) {
-        if (it.type == 1) load_ovl(m, (int64_t)it.idx, ovl);
+      if (PRELOAD) {
+        if (it.type == 0) load_sub<ML>(m, (int64_t)it.idx, sub);
+        else if (it.type == 1) load_ovl(m, (int64_t)it.idx, ovl);
         else if (it.type == 2) load_riv(m, (int32_t)it.idx, riv);
+      } else if (STAGE) {
+        if (it.type == 0) { stage_sub<ML>(m, (int64_t)it.idx, sw, sd, T); it.nup = __ldg(m.topo + it.idx) >> 4; }
+        else if (it.type == 1) { stage_ovl(m, (int64_t)it.idx, sw, sd, T); it.nup = __ldg(m.topo + it.idx) >> 4; }
+        else if (it.type == 2) { stage_riv(m, (int32_t)it.idx, sw, T); it.nup = __ldg(m.r_nup + it.idx); }
       }
     }
     return it;
@@ -787,34 +947,53 @@ __device__ __forceinline__ void sweep_group(const DevModel &m, const GroupDesc g
     if (pbase && tid == 0) pbase[14] = c0;
 #endif
     const int total = tick_items(t);
-    bool first = true;
+    const bool more = t + 1 < nticks;
+    bool first = true, arrived = false;
+    if (STAGE) cp_async_wait_all();
     for (int j = tid; j < total; j += nthreads, first = false) {
       WaveItem it;
-      if (first) it = nxt;                // decoded (grid sweep: operands fetched too) before the barrier
+      if (first) it = nxt;                // decoded, operands fetched, before the barrier
       else it = decode_item(j, t);
+      const bool signal = EARLY && more && (j + nthreads >= total);  // the thread's last item of the tick
       if (it.type == 0) {
-        if (!first || !PRELOAD) load_sub<ML>(m, (int64_t)it.idx, sub);
-        task_subsurface<ML, MODE, DIAG>(m, (int64_t)it.idx, sub WF_PPASS(0));
+        if (first && STAGE) { unstage_sub<ML>(m, (int64_t)it.idx, sw, sd, T, sub); sub.nup = it.nup; }
+        else if (!first || !PRELOAD) load_sub<ML>(m, (int64_t)it.idx, sub);
+        task_subsurface<ML, MODE, DIAG, EARLY>(m, (int64_t)it.idx, sub, signal WF_PPASS(0));
+        arrived = signal;
       } else if (it.type == 1) {
-        if (!first || !PRELOAD_SMALL) load_ovl(m, (int64_t)it.idx, ovl);
-        task_overland<MODE, DIAG>(m, (int64_t)it.idx, ovl WF_PPASS(1));
+        if (first && STAGE) { unstage_ovl(m, (int64_t)it.idx, sw, sd, T, ovl); ovl.nup = it.nup; }
+        else if (!first || !PRELOAD) load_ovl(m, (int64_t)it.idx, ovl);
+        task_overland<MODE, DIAG, EARLY>(m, (int64_t)it.idx, ovl, signal WF_PPASS(1));
+        arrived = signal;
       } else if (it.type == 2) {
-        if (!first || !PRELOAD_SMALL) load_riv(m, (int32_t)it.idx, riv);
+        if (first && STAGE) { unstage_riv(m, (int32_t)it.idx, sw, T, riv); riv.nup = it.nup; }
+        else if (!first || !PRELOAD) load_riv(m, (int32_t)it.idx, riv);
         task_river<MODE>(m, (int32_t)it.idx, it.v, riv, 0 WF_PPASS(2));
       }
     }
-    if (t + 1 < nticks) {
+    if (more) {
 #ifdef WF_PROFILE
       if (pbase) prof_stamp(pbase + 12, c0, 0);
 #endif
-      wave_arrive<MODE>(ws);
-      // while the others arrive: this thread's next item (and, in the grid sweep, its operands) ...
+      if (EARLY) {
+        if (!arrived) wave_arrive_early();
+      } else {
+        wave_arrive<MODE>(ws);
+      }
+      // while the others arrive: this thread's next item and its operands ...
       nxt = prepare(t + 1);
       // ... and the operands of the tick after into L2
-      const int pd = PRELOAD ? 2 : 1;
+      const int pd = 2;
       if (t + pd < nl) {
         const uint32_t nb = lo[t + pd], ne = lo[t + pd + 1];
         if (nb + (uint32_t)tid < ne && !(m.task_mask & 8)) prefetch_subsurface(m, (int64_t)nb + tid);
+      }
+      {
+        const int q = q0 + t + pd;  // river level of the first sub-step in two ticks
+        if (q >= 0 && q < nrl) {
+          const uint32_t rb = ro[q], re = ro[q + 1];
+          if (rb + (uint32_t)tid < re && !(m.task_mask & 8)) prefetch_river(m, (int64_t)rb + tid);
+        }
       }
       wave_wait<MODE>(ws);
 #ifdef WF_PROFILE
@@ -826,7 +1005,7 @@ __device__ __forceinline__ void sweep_group(const DevModel &m, const GroupDesc g
 
 template <int ML, int MODE, bool DIAG = true>
 __global__ void __launch_bounds__(wf_block_threads(MODE), 1) k_lateral_wave(const DevModel m) {
-  extern __shared__ uint32_t s_lev[];
+  extern __shared__ __align__(16) uint32_t s_lev[];
   int crank = 0, csize = 1;
   if (wf_is_cluster(MODE)) {
     cg::cluster_group cl = cg::this_cluster();
@@ -847,6 +1026,8 @@ __global__ void __launch_bounds__(wf_block_threads(MODE), 1) k_lateral_wave(cons
   ws.counter = m.grid_counter;
   ws.nblocks = gridDim.x;
   ws.target = 0;
+  // operand staging columns of the block's threads behind the level cache (16-byte aligned)
+  float *const stage = reinterpret_cast<float *>(s_lev + (((size_t)m.lev_cache + 3) & ~(size_t)3));
   for (int g = cid; g < m.ngroups; g += nclusters) {
     const GroupDesc gd = m.groups[g];
     const int nlo = m.nlev - gd.lev0 + 1;
@@ -862,8 +1043,13 @@ __global__ void __launch_bounds__(wf_block_threads(MODE), 1) k_lateral_wave(cons
       ro = s_lev + nlo;
       tt = s_lev + nlo + nro;
     }
-    sweep_group<ML, MODE, DIAG>(m, gd, lo, ro, tt, tid, nthreads, ws);
-    // the next group of this cluster touches other cells only: no barrier needed in between
+    sweep_group<ML, MODE, DIAG>(m, gd, lo, ro, tt, tid, nthreads, ws, stage);
+    // The next group of this cluster touches other cells only, but a thread's early arrival may still be pending:
+    // the cluster sweeps close a group with one full barrier so that the next group starts on a fresh phase.
+    if (wf_is_cluster(MODE) && g + nclusters < m.ngroups) {
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
     if (MODE == WF_GRID) break;
   }
 }

@@ -107,7 +107,7 @@ __device__ __forceinline__ void pipe_group(const DevModel &m, const PipeArgs pa,
   const int itR = m.itR;
   const int nl = m.nlev - gd.lev0;                                      // levels of the group
   const int nrl = (gd.rlev0 < m.nrlev) ? m.nrlev - gd.rlev0 : 0;        // river levels of the group
-  const int nt1 = gd.nticks + 1;                                        // local ticks of one step: the column's + the lateral sweep's
+  const int nt1 = nl + 2 + ((gd.rlev0 < m.nrlev) ? itR : 0);            // local ticks of one step: the column's + the lateral tasks' (own schedule, below)
   const int q0 = (gd.lev0 - 2) - m.rlev_shift - gd.rlev0;
   const int lag = pa.lag;
   const int total = nt1 + (pa.nsteps - 1) * lag;
@@ -168,7 +168,7 @@ __device__ __forceinline__ void pipe_group(const DevModel &m, const PipeArgs pa,
       for (int j = take(counter, c0, cnt); j >= 0; j = take(counter, c0, cnt)) {
         if (j < cnt) {
           load_sub<ML>(m, (int64_t)b0 + j, sub);
-          task_subsurface<ML, MODE>(m, (int64_t)b0 + j, sub WF_PNONE);
+          task_subsurface<ML, MODE>(m, (int64_t)b0 + j, sub, false WF_PNONE);
         }
         __syncwarp();
       }
@@ -185,7 +185,7 @@ __device__ __forceinline__ void pipe_group(const DevModel &m, const PipeArgs pa,
       for (int j = take(counter, c0, cnt); j >= 0; j = take(counter, c0, cnt)) {
         if (j < cnt) {
           load_ovl(m, (int64_t)b0 + j, ovl);
-          task_overland<MODE>(m, (int64_t)b0 + j, ovl WF_PNONE);
+          task_overland<MODE>(m, (int64_t)b0 + j, ovl, false WF_PNONE);
         }
         __syncwarp();
       }
