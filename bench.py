@@ -1,23 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- cell-timesteps/s of the full wflow_sbm step (SBM column + subsurface / overland /
-river kinematic wave) on synthetic independent D8 basins (BASELINE.json config 3).
+"""bench.py -- cell-timesteps/s of the wflow_sbm per-timestep hot path (SBM column + subsurface / overland / river
+kinematic wave) on the synthetic workloads of BASELINE.json.
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port of the
-                                                             # reference, all host threads
+    python bench.py --gpus N --steps K --warmup W                 # this repo's CUDA path, BASELINE config 3 (the headline)
+    python bench.py --config {2,3,5} [--basins B] ...             # the other synthetic configurations
+    python bench.py --impl reference --gpus N --steps K ...       # CPU arm: the reference's own code on the host
 
-Workload.  BASELINE config 3 is a 16384x16384 grid of 256 independent 1024x1024 basins, hourly
-steps (modified-Rutter interception, river sub-step 900 s => it_kinR = 4), sharded by basin over
-8 GPUs.  Each rank holds `--basins` (default 32 = the config's per-GPU share; 8 ranks = the
-full 16k x 16k grid) whole basins: weak scaling, no data-path collective; the only collective
-is the gather of the basin-outlet discharges (NCCL all_gather) once per timed region.
-
+Workloads (--config)
+  3  (default, the configuration the metric is quoted on) 16384x16384 grid = 256 independent 1024x1024 D8 basins, hourly
+     steps (modified-Rutter interception, it_kinR = 4), sharded by basin over 8 GPUs: each rank holds --basins basins
+     (default 32 = the per-GPU share; --basins 256 = the whole grid on one GPU).  Weak scaling, no data-path collective.
+  2  4096x4096 all-pit LDD (column only: one level, the lateral solves are cell-local), 4 layers, snow, daily steps, cold start.
+  5  32768x32768 / 8 GPUs = 128 basins of 1024x1024 per rank, 10 % of the cells missing, daily steps, one gauge per
+     basin outlet + 3 interior river cells; the gauge values of every --gather-every (10) steps are all-gathered over NCCL
+     from device memory INSIDE the end-to-end loop (the only collective of the path).
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
 """
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -27,12 +28,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BYTES_VERTICAL = 236  # algorithmic bytes per cell-step of the vertical kernel, 4 layers, snow on
-BYTES_FULL = 333      # full step incl. lateral statics, routing states and topology
-# DRAM traffic of one k_vertical launch per cell, from the round's `ncu --set full` capture of the default
-# workload (profiles/r1_vertical_ncu_details.txt: dram__bytes_read.sum + dram__bytes_write.sum = 11.75 GB for
-# 33 554 431 cells).  Above the algorithmic 236 B: float64 hand-offs, derived statics, register spills.
-TRAFFIC_VERTICAL_PER_CELL = 350.1
+# algorithmic bytes per cell-step (4 layers, snow on, float32 storage, every array touched once)
+BYTES_VERTICAL = 236   # the stand-alone column kernel
+BYTES_FULL = 333       # full step incl. lateral statics, routing states, upstream gathers and topology
+BYTES_LATERAL = BYTES_FULL - BYTES_VERTICAL
+METRIC = "cell-timesteps/sec (SBM+kinwave)"
 
 
 def parse():
@@ -41,13 +41,25 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--basins", type=int, default=32, help="1024^2 basins per GPU (32 = config 3's per-GPU share)")
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 5])
+    ap.add_argument("--basins", type=int, default=0, help="1024^2 basins per GPU (config 3: 32, config 5: 128)")
     ap.add_argument("--tile", type=int, default=1024)
-    ap.add_argument("--timestepsecs", type=int, default=3600)
+    ap.add_argument("--timestepsecs", type=int, default=0, help="0 = the configuration's own (3: 3600 s, 2 and 5: 86400 s)")
+    ap.add_argument("--gather-every", type=int, default=10, help="timesteps between the gauge gathers of the end-to-end loop")
+    ap.add_argument("--replicate", type=int, default=-1, help="1: one basin tile's inputs replicated over the shard (fast to "
+                    "generate; default for more than 64 basins), 0: every basin its own LDD and parameters")
     ap.add_argument("--cpu-sample-steps", type=int, default=40, help="timesteps of one basin tile timed for cpu_baseline (~10 s)")
+    ap.add_argument("--ref-tile", type=int, default=256, help="edge of the basin tile the reference arm steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-single-basin", action="store_true", help="skip the auxiliary single-basin per-step / pipelined measurement")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.timestepsecs == 0:
+        a.timestepsecs = 3600 if a.config == 3 else 86400
+    if a.basins == 0:
+        a.basins = {3: 32, 5: 128, 2: 16}[a.config]
+    if a.replicate < 0:
+        a.replicate = 1 if a.basins > 64 else 0
+    return a
 
 
 def shard_shape(basins, tile):
@@ -68,24 +80,43 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic():
+    """DRAM bytes per cell and launch of the two hot kernels from this round's `ncu --set full` capture of the default
+    workload (profiles/r2_traffic.json, written by scripts/make_profiles.py from the .ncu-rep): a static figure,
+    refreshed with every capture -- bench.py does not run under a profiler."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML every few milliseconds during the timed region."""
 
     def __init__(self, index):
-        self.samples, self.stop, self.index = [], False, index
+        self.samples, self.reasons, self.stop, self.index, self.max_mhz = [], set(), False, index, None
         self.t = threading.Thread(target=self.run, daemon=True)
 
     def run(self):
-        while not self.stop:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.samples.append([x.strip() for x in out.strip().split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                     "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                     "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            while not self.stop:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(0.004)
+        except Exception as ex:  # no NVML: the driver's own record stands
+            self.error = repr(ex)
 
     def __enter__(self):
         self.t.start()
@@ -96,18 +127,37 @@ class ClockSampler:
         self.t.join(timeout=6)
 
     def summary(self):
-        sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples if len(s) >= 6 for n, v in zip(names, s[2:6]) if v.lower() == "active"})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        if getattr(self, "error", None):
+            out["error"] = self.error
+        return out
 
 
-def make_model_inputs(args, rank, nrow, ncol, schedule_factory):
+# ---- workloads ------------------------------------------------------------------------------------------------
+LT = (100, 300, 800)  # UStoreLayerThickness = 100,300,800 => 4 soil layers
+
+
+def it_substeps(args):
+    # config 3: kinwaveIters=1, kinwaveRiverTstep=900, kinwaveLandTstep=3600; daily configurations: 1 / 1
+    if getattr(args, "config", 3) != 3:
+        return 1, 1
+    it_r = int(np.ceil(args.timestepsecs / 900.0))
+    it_l = int(np.ceil(args.timestepsecs / 3600.0))
+    return max(it_l, 1), max(it_r, 1)
+
+
+def make_model_inputs(args, rank, nrow, ncol, schedule_factory, kind=None, mask_frac=None, init="random"):
+    """(ldd, river, schedule, static, state, layer thickness) of a rank's shard (or of one tile of it)."""
     from wflow_b200 import params, synth
-    lt = (100, 300, 800)
-    ldd = synth.ldd_basin_tiles(nrow, ncol, tile=args.tile, seed=7 + 1000 * rank)
+    cfg = getattr(args, "config", 3)
+    kind = kind or ("pits" if cfg == 2 else "tiles")
+    if mask_frac is None:
+        mask_frac = 0.1 if cfg == 5 else 0.0
+    if kind == "pits":
+        ldd = synth.ldd_all_pits(nrow, ncol)
+    else:
+        ldd = synth.ldd_basin_tiles(nrow, ncol, tile=args.tile, seed=7 + 1000 * rank, mask_frac=mask_frac)
     sched = schedule_factory(ldd)
     up = sched.catchment_total(None)
     river = (up >= 500).astype(np.uint8)  # SURVEY.md 8d config 3: river = upstream area >= 500 cells
@@ -116,30 +166,106 @@ def make_model_inputs(args, rank, nrow, ncol, schedule_factory):
     base["RiverWidth"] = np.where(river != 0, np.float32(2.0) * np.power(np.maximum(upf, 1), np.float32(0.35)), 0).astype(np.float32)
     base["BankfullDepth"] = np.where(river != 0, np.float32(1.0), np.float32(0.0)).astype(np.float32)
     static = params.derive_static(base, ldd, river, args.timestepsecs, cellsize=1000.0, n_layers=4)
-    state = synth.random_state(static, 4, lt, seed=99 + rank, smooth=48)
-    return ldd, river, sched, static, state, lt
+    if cfg == 2 or init == "cold":
+        state = params.cold_state(static, 4)  # the reference's reinit = 1 defaults (wflow_sbm.py:2443-2488)
+    else:
+        state = synth.random_state(static, 4, LT, seed=99 + rank, smooth=48)
+    return ldd, river, sched, static, state, LT
 
 
-class _DevArray:
-    """Expose a raw device pointer to torch through __cuda_array_interface__."""
+class Shard:
+    """A rank's model: inputs generated for the whole shard, or for ONE basin tile and replicated over it."""
 
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+    def __init__(self, args, rank, local):
+        from wflow_b200 import core, synth
+        self.args = args
+        self.nrow, self.ncol = shard_shape(args.basins, args.tile) if args.config != 2 else (4096, 4096)
+        if args.config == 2 and args.basins != 16:  # --basins scales the all-pit grid in 1024^2 units (development aid)
+            self.nrow, self.ncol = shard_shape(args.basins, 1024)
+        nrow, ncol = self.nrow, self.ncol
+        it_l, it_r = it_substeps(args)
+        t0 = time.time()
+        rep = bool(args.replicate) and args.config != 2
+        if rep:
+            tr, tc = nrow // args.tile, ncol // args.tile
+            ldd1, river1, _, static, state, lt = make_model_inputs(args, rank, args.tile, args.tile, core.Schedule)
+            self.expand = lambda a: np.tile(np.broadcast_to(np.asarray(a), (args.tile, args.tile)), (tr, tc))
+            ldd, river, sched = self.expand(ldd1), self.expand(river1), None
+        else:
+            ldd, river, sched, static, state, lt = make_model_inputs(args, rank, nrow, ncol, core.Schedule)
+            self.expand = lambda a: a
+        self.gen_s = time.time() - t0
+        self.ldd, self.river = ldd, river
+        self.mod = core.SbmModel(ldd, river, schedule=sched, timestepsecs=args.timestepsecs, layer_thickness=lt, model_snow=1,
+                                 it_kin_l=it_l, it_kin_r=it_r, device=local)
+        for k, v in {**static, **state}.items():
+            if k not in ("River", "Beta", "SatWaterDepth"):
+                self.mod.set(k, v if np.ndim(v) == 0 else self.expand(v))
+        self.init_s = time.time() - t0
+        self.ncell = self.mod.num_cells
+        self.forc = synth.Forcing(args.tile if rep else nrow, args.tile if rep else ncol, seed=5 + rank,
+                                  timestepsecs=args.timestepsecs, rain_mean=20.0 if args.config == 3 else 8.0)
+        self.it = (it_l, it_r)
+
+    def forcing(self, f):
+        return [np.ascontiguousarray(self.expand(a), dtype=np.float32) for a in self.forc.step(f)]
+
+    def gauges(self):
+        """Flat indices of the cells whose discharge leaves the device every step."""
+        a = self.args
+        ldd = self.ldd
+        if a.config == 2:  # no river: a fixed sample of cells (their water table is the step's read-back)
+            return np.linspace(0, ldd.size - 1, 64).astype(np.int64), "zi"
+        pits = np.flatnonzero(ldd.ravel() == 5).astype(np.int64)
+        if a.config != 5:
+            return pits, "RiverRunoff"
+        # config 5: the outlet of every basin + 3 interior river cells of it (here: the first river cells of the tile rows
+        # a quarter, a half and three quarters up from the outlet)
+        riv = self.river
+        extra = []
+        for p in pits:
+            r, c = divmod(int(p), self.ncol)
+            r0, c0 = (r // a.tile) * a.tile, (c // a.tile) * a.tile
+            for frac in (0.25, 0.5, 0.75):
+                rr = r0 + int(a.tile * frac)
+                cols = np.flatnonzero(riv[rr, c0:c0 + a.tile])
+                extra.append(rr * self.ncol + c0 + (int(cols[len(cols) // 2]) if cols.size else a.tile // 2))
+        return np.concatenate([pits, np.array(extra, np.int64)]), "RiverRunoff"
 
 
-def it_substeps(args):
-    # kinwaveIters=1, kinwaveRiverTstep=900, kinwaveLandTstep=3600 (SURVEY.md 8d config 3)
-    it_r = int(np.ceil(args.timestepsecs / 900.0))
-    it_l = int(np.ceil(args.timestepsecs / 3600.0))
-    return max(it_l, 1), max(it_r, 1)
+def workload_config(args, it_l, it_r, **extra):
+    nrow, ncol = shard_shape(args.basins, args.tile) if args.config != 2 else (4096, 4096)
+    if args.config == 3:
+        w = ("BASELINE config 3: synthetic D8 grid of independent %dx%d basins, full SBM + subsurface/overland/river kinematic "
+             "wave, %d s steps, 4 soil layers, snow on; %d basins (%dx%d cells) per GPU (8 GPUs x 32 = the 16384x16384 grid)"
+             % (args.tile, args.tile, args.timestepsecs, args.basins, nrow, ncol))
+    elif args.config == 2:
+        w = ("BASELINE config 2: synthetic %dx%d grid, all-pit LDD (SBM vertical column; the lateral solves are cell-local), "
+             "4 soil layers (UStoreLayerThickness 100,300,800), snow on, %d s steps, cold start" % (nrow, ncol, args.timestepsecs))
+    else:
+        w = ("BASELINE config 5: continental-scale synthetic multi-basin grid, %d basins of %dx%d (%dx%d cells) per GPU "
+             "(8 GPUs x 128 = 32768x32768), 10 %% of the cells missing, reservoir / lake modules off, full SBM + routing, "
+             "%d s steps; gauge values (outlet + 3 interior per basin) all-gathered over NCCL every %d steps"
+             % (args.basins, args.tile, args.tile, nrow, ncol, args.timestepsecs, args.gather_every))
+    cfg = {"workload": w, "config": args.config, "basins_per_gpu": args.basins, "tile": args.tile,
+           "timestepsecs": args.timestepsecs, "it_kinL": it_l, "it_kinR": it_r, "layers": 4, "snow": 1,
+           "state": ("cold start (the reference's reinit = 1 defaults) + warm-up steps" if args.config == 2 else
+                     "spatially correlated random initial state (synth.random_state, 48-cell correlation length: water tables "
+                     "from surface to bottom, partly filled layers, snow, flowing rivers) + warm-up steps"),
+           "replicated_tile": bool(args.replicate) and args.config != 2,
+           "l2": "inputs larger than L2 (per-step working set >> 126 MB), no flush needed"}
+    cfg.update(extra)
+    return cfg
 
 
-def cpu_baseline(args, steps, threads, warmup=1):
-    """The oracle port of the reference on ONE basin tile of the same workload (bounded sample)."""
+# ---- CPU arms -----------------------------------------------------------------------------------------------------
+def cpu_baseline_port(args, steps, threads, warmup=1):
+    """The C oracle port of the reference on ONE basin tile of the same workload (bounded sample), OpenMP over the cells
+    of a level on all host threads."""
     from oracle import oracle as O
     from wflow_b200 import core, synth
     n = args.tile
-    ldd, river, sched, static, state, lt = make_model_inputs(args, 0, n, n, core.Schedule)
+    ldd, river, sched, static, state, lt = make_model_inputs(args, 0, n, n, _OracleSchedule if args.impl == "reference" else core.Schedule)
     it_l, it_r = it_substeps(args)
     orc = O.Oracle(ldd, river, timestepsecs=args.timestepsecs, layer_thickness=lt, modelSnow=1, it_kinL=it_l, it_kinR=it_r)
     for k, v in {**static, **state}.items():
@@ -161,40 +287,103 @@ def cpu_baseline(args, steps, threads, warmup=1):
             "ms_per_step": dt / steps * 1e3, "cells": cells}
 
 
+class _OracleSchedule:
+    """Upstream cell counts for the river mask WITHOUT the product library (the reference arm must not load it):
+    the oracle's own network + numpy."""
+
+    def __init__(self, ldd):
+        from oracle import oracle as O
+        self.net = O.Network(ldd)
+        self.shape = ldd.shape
+
+    def catchment_total(self, values=None):
+        net = self.net
+        acc = np.ones(self.shape[0] * self.shape[1], np.float64)
+        for lev in range(len(net.lev_off) - 1):  # upstream levels first: every cell is complete before its receiver
+            a, b = net.lev_off[lev], net.lev_off[lev + 1]
+            idx, up = net.flat_nodes[a:b], net.flat_up[a:b]
+            ok = up >= 0
+            add = np.where(ok, acc[np.where(ok, up, 0)], 0.0).sum(axis=1)
+            acc[idx] += add
+        out = np.zeros(self.shape[0] * self.shape[1], np.float64)
+        out[net.flat_nodes] = acc[net.flat_nodes]
+        return out.reshape(self.shape)
+
+    def _release(self):
+        return None
+
+
+def cpu_baseline_reference(args, steps, warmup):
+    """The REFERENCE itself: its unmodified WflowModel.dynamic() -- numba kernels sbm_cell / kin_wave and the map algebra
+    around them, the latter through the numpy stand-in for PCRaster (oracle/pcrshim.py) -- on one basin tile of the
+    workload.  Single-threaded by construction (no nogil, one global clone map)."""
+    from oracle import ref_dynamic, refload
+    from wflow_b200 import synth
+    if not refload.available():
+        raise RuntimeError("reference sources not present (baseline/_ref/wflow, copied by __graft_entry__.build())")
+    n = args.ref_tile
+    sub = argparse.Namespace(**vars(args))
+    sub.tile = n
+    ldd, river, sched, static, state, lt = make_model_inputs(sub, 0, n, n, _OracleSchedule)
+    it_l, it_r = it_substeps(args)
+    fields = {**static, **state}
+    fields["River"] = river.astype(np.float32)
+    kw = dict(timestepsecs=args.timestepsecs, layer_thickness=lt, modelSnow=1)
+    if args.config == 3:
+        kw.update(kinwaveIters=1, kinwaveLandTstep=3600, kinwaveRiverTstep=900)
+    ref = ref_dynamic.RefDynamic(ldd, river, fields, **kw)
+    forc = synth.Forcing(n, n, seed=5, timestepsecs=args.timestepsecs, rain_mean=20.0)
+    P, PET, T = forc.step(0)
+    for _ in range(max(1, warmup)):
+        ref.step(P, PET, T)  # numba compiles sbm_cell / kin_wave on the first call
+    t0 = time.time()
+    for s in range(steps):
+        ref.step(P, PET, T)
+    dt = time.time() - t0
+    cells = int(sum(len(a) for a in ref.m.nodes))
+    return {"value": cells * steps / dt, "unit": "cell-timesteps/s", "cores": 1, "kind": "reference",
+            "sample": "%d steps of one %dx%d basin tile (%d cells) of the same workload through the reference's own, unmodified "
+                      "WflowModel.dynamic() (numba sbm_cell / kin_wave + its map algebra on the numpy stand-in for PCRaster), "
+                      "1 thread: the reference is single-threaded by construction" % (steps, n, n, cells),
+            "ms_per_step": dt / steps * 1e3, "cells": cells}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    # every step of this arm is one timestep of ONE basin tile (1/32 of the GPU arm's per-GPU shard): K = 20 takes ~5 s
     steps = max(1, min(args.steps, 200))
     warm = max(1, min(args.warmup, 5))
-    cb = cpu_baseline(args, steps, threads, warm)
+    extra = {}
+    try:
+        cb = cpu_baseline_reference(args, steps, warm)
+        try:  # the multi-threaded C port beside it, for scale (not the arm's value)
+            pb = cpu_baseline_port(args, min(steps, 20), os.cpu_count() or 1, 1)
+            extra["cpu_baseline_port"] = {k: pb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as ex:
+            extra["cpu_baseline_port"] = {"error": repr(ex)}
+    except Exception as ex:  # reference sources or numba not available on this box: the C port of it
+        extra["reference_unavailable"] = repr(ex)
+        cb = cpu_baseline_port(args, steps, os.cpu_count() or 1, warm)
     it_l, it_r = it_substeps(args)
     line = {
-        "impl": "reference", "metric": "cell-timesteps/sec (SBM+kinwave)", "value": cb["value"],
-        "unit": "cell-timesteps/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-        "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64 (column, kinematic waves) + f32 (map-algebra phases)", "data": "synthetic",
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "cell-timesteps/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64 (column, kinematic waves) + f32 (map-algebra phases)", "data": "synthetic",
         "config": workload_config(args, it_l, it_r, sample=cb["sample"]),
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": "cell-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    line.update(extra)
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, it_l, it_r, **extra):
-    nrow, ncol = shard_shape(args.basins, args.tile)
-    cfg = {"workload": "BASELINE config 3: synthetic D8 grid of independent %dx%d basins, full SBM + subsurface/overland/"
-                       "river kinematic wave, %d s steps, 4 soil layers, snow on; %d basins (%dx%d cells) per GPU "
-                       "(8 GPUs = the 16384x16384 grid)" % (args.tile, args.tile, args.timestepsecs, args.basins, nrow, ncol),
-           "basins_per_gpu": args.basins, "tile": args.tile, "timestepsecs": args.timestepsecs,
-           "it_kinL": it_l, "it_kinR": it_r, "layers": 4, "snow": 1,
-           "state": "spatially correlated random initial state (synth.random_state, 48-cell correlation length: water "
-                    "tables from surface to bottom, partly filled layers, snow, flowing rivers) + warm-up steps",
-           "l2": "inputs larger than L2 (per-step working set >> 126 MB), no flush needed"}
-    cfg.update(extra)
-    return cfg
+# ---- the CUDA arm ---------------------------------------------------------------------------------------------------
+class _DevArray:
+    """Expose a raw device pointer to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
 
 
 def single_basin_pipelined(args, local, steps_per_launch=50):
@@ -247,7 +436,6 @@ def single_basin_pipelined(args, local, steps_per_launch=50):
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from wflow_b200 import core, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -257,41 +445,29 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    nrow, ncol = shard_shape(args.basins, args.tile)
-    it_l, it_r = it_substeps(args)
 
-    t0 = time.time()
-    ldd, river, sched, static, state, lt = make_model_inputs(args, rank, nrow, ncol, core.Schedule)
-    t_gen = time.time() - t0
-    mod = core.SbmModel(ldd, river, schedule=sched, timestepsecs=args.timestepsecs, layer_thickness=lt, model_snow=1,
-                        it_kin_l=it_l, it_kin_r=it_r, device=local)
-    for k, v in {**static, **state}.items():
-        if k not in ("River", "Beta", "SatWaterDepth"):
-            mod.set(k, v)
-    del static, state
-    ncell = mod.num_cells
-    # gauges: the basin outlets (pits)
-    gauges = np.flatnonzero(ldd.ravel() == 5).astype(np.int64)
-    t_init = time.time() - t0
+    sh = Shard(args, rank, local)
+    mod, nrow, ncol, ncell = sh.mod, sh.nrow, sh.ncol, sh.ncell
+    it_l, it_r = sh.it
+    gauges, gfield = sh.gauges()
+    G = int(gauges.size)
 
-    # forcing: a ring of F distinct steps; host copies pinned (e2e), device copies in network order (value)
+    # forcing: a ring of F distinct steps; host copies pinned (e2e), device copies in storage order (value)
     F = 4
-    forc = synth.Forcing(nrow, ncol, seed=5 + rank, timestepsecs=args.timestepsecs, rain_mean=20.0)
     host_ring, dev_ring = [], []
     for f in range(F):
-        trip = forc.step(f)
-        pinned = [torch.from_numpy(a).pin_memory() for a in trip]
-        host_ring.append(pinned)
+        trip = sh.forcing(f)
+        host_ring.append([torch.from_numpy(a).pin_memory() for a in trip])
         devs = []
         for name, a in zip(("P", "PET", "TEMP"), trip):
             mod.set(name, a)
             ptr, n = mod.device_ptr(name)
             mod.synchronize()
-            # clone the model's network-order array into our ring slot (plumbing only)
-            t = torch.as_tensor(_DevArray(ptr, n), device="cuda").clone()
+            t = torch.as_tensor(_DevArray(ptr, n), device="cuda").clone()  # the model's storage-order array (plumbing only)
             torch.cuda.synchronize()
             devs.append(t)
         dev_ring.append(devs)
+        del trip
     mod.synchronize()
     stream = torch.cuda.ExternalStream(mod.stream)
 
@@ -305,7 +481,7 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (also relaxes the random initial state) ----
+    # ---- warm-up (also relaxes the initial state) ----
     for s in range(max(args.warmup, 3)):
         bind(s)
         mod.step()
@@ -330,88 +506,133 @@ def run_b200(args):
     for name in ("P", "PET", "TEMP"):
         mod.bind(name, None)
 
-    # ---- e2e: host forcing in pinned memory -> set_field -> step -> gauge read-back, every step ----
-    # Public API only.  Nothing blocks the host inside the loop: the uploads run on the library's copy
-    # stream through its staging ring (so step s+1's forcing crosses PCIe while step s computes) and the
-    # gauge values of every step land in pinned host memory; one synchronize closes the timed region.
+    # ---- e2e: host forcing in pinned memory -> set_field -> step -> gauge values, every step; gathered every T steps ----
+    # Public API only.  Nothing blocks the host inside the loop: the uploads run on the library's copy stream through its
+    # staging ring (step s+1's forcing crosses PCIe while step s computes); every step's gauge values are sampled into a
+    # device buffer [T][G]; every T steps that block is all-gathered over NCCL from device memory (no host bounce) on the
+    # model's stream and copied to pinned host memory.  One synchronize closes the timed region.
+    T = max(1, min(args.gather_every, args.steps))
     gh = mod.gauges_create(gauges)
-    gq_all = torch.zeros((args.steps, max(int(gauges.size), 1)), dtype=torch.float32).pin_memory()
-    mod.gauges_sample(gh, "RiverRunoff", gq_all[0].data_ptr(), wait=True)  # warm the path
+    gbuf = torch.zeros((T, max(G, 1)), dtype=torch.float32, device="cuda")
+    gall = torch.zeros((world, T, max(G, 1)), dtype=torch.float32, device="cuda")
+    nblocks = (args.steps + T - 1) // T
+    ghost = torch.zeros((nblocks, world, T, max(G, 1)), dtype=torch.float32).pin_memory()
+    mod.gauges_sample_device(gh, gfield, gbuf[0].data_ptr())  # warm the path
+    if world > 1:
+        with torch.cuda.stream(stream):
+            dist.all_gather_into_tensor(gall.view(-1), gbuf.view(-1))
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    collectives = 0
     e2.record(stream)
     for s in range(args.steps):
         for name, t in zip(("P", "PET", "TEMP"), host_ring[s % F]):
             mod.set_pinned(name, t.data_ptr())
         mod.step()
-        mod.gauges_sample(gh, "RiverRunoff", gq_all[s].data_ptr(), wait=False)
+        mod.gauges_sample_device(gh, gfield, gbuf[s % T].data_ptr())
+        if (s + 1) % T == 0 or s == args.steps - 1:
+            with torch.cuda.stream(stream):
+                if world > 1:
+                    dist.all_gather_into_tensor(gall.view(-1), gbuf.view(-1))
+                    collectives += 1
+                    ghost[s // T].copy_(gall, non_blocking=True)
+                else:
+                    ghost[s // T, 0].copy_(gbuf, non_blocking=True)
     e3.record(stream)
     mod.synchronize()
+    torch.cuda.synchronize()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
-    gq = gq_all[args.steps - 1].numpy()[: int(gauges.size)].copy()
-    if not np.all(np.isfinite(gq_all.numpy())):
-        raise SystemExit("bench.py: non-finite outlet discharge in the e2e run")
+    if not np.all(np.isfinite(ghost.numpy())):
+        raise SystemExit("bench.py: non-finite gauge value in the e2e run")
     h2d = 3 * nrow * ncol * 4
-    d2h = int(gauges.size) * 4
+    d2h = world * G * 4  # every rank receives all ranks' gauge values (averaged over the gather interval: per step)
 
-    # max over ranks; gather gauge series (the only collective of the path)
+    # max over ranks
     tms = torch.tensor([ms, ms_e2e, ms_v, ms_l], device="cuda", dtype=torch.float64)
     cells = torch.tensor([float(ncell)], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         dist.all_reduce(cells, op=dist.ReduceOp.SUM)
-        from wflow_b200 import parallel
-        gathered = parallel.gather_series(gq)  # the path's only collective: outlet discharges of all ranks
-        assert len(gathered) == world
     ms, ms_e2e, ms_v, ms_l = [float(x) for x in tms.tolist()]
     total_cells = float(cells.item())
 
     if rank == 0:
         peak, peak_src = peaks()
+        traffic = measured_traffic()
         value = total_cells * args.steps / (ms / 1e3)
         e2e_v = total_cells * args.steps / (ms_e2e / 1e3)
-        v_launch_ms = ms_v / max(nst, 1)
-        achieved = ncell * BYTES_VERTICAL / (v_launch_ms / 1e3) / 1e9
+        nst = max(nst, 1)
+        kern = []
+        for name, key, msk, bpc in (("k_vertical<4> (SBM vertical column)", "k_vertical", ms_v / nst, BYTES_VERTICAL),
+                                    ("k_lateral_wave<4> (subsurface / overland / river kinematic waves, level wavefront)",
+                                     "k_lateral_wave", ms_l / nst, BYTES_LATERAL)):
+            ach = ncell * bpc / (msk / 1e3) / 1e9 if msk > 0 else 0.0
+            tr = traffic.get(key, {})
+            kern.append({"kernel": name, "ms_per_launch": msk, "share_of_step": msk / max((ms_v + ms_l) / nst, 1e-9),
+                         "bytes_per_cell": bpc, "achieved": ach, "frac": ach / peak,
+                         "traffic": (tr["bytes_per_cell"] * ncell) if "bytes_per_cell" in tr else None,
+                         "traffic_source": tr.get("source")})
+        dom = max(kern, key=lambda k: k["ms_per_launch"])
         line = {
-            "metric": "cell-timesteps/sec (SBM+kinwave)", "value": value, "unit": "cell-timesteps/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64 (column, kinematic waves) + f32 (map-algebra phases, storage)", "data": "synthetic",
+            "metric": METRIC, "value": value, "unit": "cell-timesteps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64 (column, kinematic waves) + f32 (map-algebra phases, storage)",
+            "data": "synthetic",
             "config": workload_config(args, it_l, it_r, cells_per_gpu=ncell, levels=mod.num_levels,
-                                      river_cells=mod.num_river_cells, init_s=round(t_init, 1), gen_s=round(t_gen, 1)),
+                                      river_cells=mod.num_river_cells, gauges_per_gpu=G, init_s=round(sh.init_s, 1),
+                                      gen_s=round(sh.gen_s, 1)),
             "e2e": {"value": e2e_v, "unit": "cell-timesteps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps,
-                    "path": "SbmModel.set_pinned(P,PET,TEMP) from pinned host rasters (staging ring, copy stream) -> step() -> gauges_sample(RiverRunoff at the basin outlets) into pinned host memory, every step; one synchronize at the end of the timed region"},
+                    "ms_per_step": ms_e2e / args.steps, "gather_every": T, "collectives_in_timed_region": collectives,
+                    "path": "SbmModel.set_pinned(P,PET,TEMP) from pinned host rasters (staging ring, copy stream) -> step() -> "
+                            "gauges_sample_device(%s) into a device block [T][gauges], every step; every T steps the block is "
+                            "all-gathered over NCCL from device memory on the model's stream and copied to pinned host memory; "
+                            "one synchronize at the end of the timed region" % gfield},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_vertical<4> (SBM vertical column)", "achieved": achieved,
-                         "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                         "bytes_per_cell": BYTES_VERTICAL, "cells_per_launch": ncell, "ms_per_launch": v_launch_ms,
-                         "traffic": TRAFFIC_VERTICAL_PER_CELL * ncell,
-                         "traffic_source": "ncu --set full, profiles/r1_vertical_ncu_details.txt (per cell x cells of this launch)",
-                         "bound_note": "the kernel is instruction-issue bound (ncu: issue slots busy 66 %, DRAM 31 %), "
-                                       "not HBM-bound; the HBM fraction is reported as the contract asks",
-                         "full_step_gbs_at_333B": ncell * BYTES_FULL / ((ms_v + ms_l) / max(nst, 1) / 1e3) / 1e9},
-            "kernels_ms_per_step": {"vertical": ms_v / max(nst, 1), "lateral": ms_l / max(nst, 1),
-                                    "lateral_us_per_level": ms_l / max(nst, 1) * 1e3 / max(mod.num_levels, 1)},
+            "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak,
+                         "peak_source": peak_src, "unit": "GB/s", "frac": dom["frac"], "bytes_per_cell": dom["bytes_per_cell"],
+                         "cells_per_launch": ncell, "ms_per_launch": dom["ms_per_launch"], "traffic": dom["traffic"],
+                         "traffic_source": dom["traffic_source"],
+                         "bound_note": "the dominant kernel is the level wavefront: bound by per-level latency and instruction "
+                                       "issue, not by HBM; the HBM fraction is reported as the contract asks",
+                         "kernels": kern,
+                         "full_step": {"bytes_per_cell": BYTES_FULL,
+                                       "achieved": ncell * BYTES_FULL / ((ms_v + ms_l) / nst / 1e3) / 1e9,
+                                       "frac": ncell * BYTES_FULL / ((ms_v + ms_l) / nst / 1e3) / 1e9 / peak}},
+            "kernels_ms_per_step": {"vertical": ms_v / nst, "lateral": ms_l / nst,
+                                    "lateral_us_per_level": ms_l / nst * 1e3 / max(mod.num_levels, 1)},
             "lateral_plan": mod.lateral_plan,
             "clocks": clk.summary(),
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
-                cb = cpu_baseline(args, args.cpu_sample_steps, os.cpu_count() or 1)
+                cb = cpu_baseline_port(args, args.cpu_sample_steps, os.cpu_count() or 1)
                 line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
             except Exception as ex:  # the checker must never take the product number down with it
                 line["cpu_baseline"] = {"error": repr(ex)}
-        if world == 1 and not args.no_single_basin:
+        if world == 1 and not args.no_single_basin and args.config == 3:
             try:
                 line["single_basin"] = single_basin_pipelined(args, local)
             except Exception as ex:  # auxiliary: never takes the headline down
                 line["single_basin"] = {"error": repr(ex)}
         print(json.dumps(line), flush=True)
+    # Pinned host blocks that were the target of copies on the model's stream must be gone before the library
+    # destroys that stream (torch's host allocator records an event on the stream a block was last used on).
+    del ghost, gall, gbuf, host_ring, dev_ring
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    try:
+        torch._C._host_emptyCache()
+    except Exception:
+        pass
+    torch.cuda.empty_cache()
     mod.close()
     if world > 1:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)  # the result line is out; skip interpreter teardown (CUDA context vs. torch's static destructors)
 
 
 if __name__ == "__main__":

@@ -206,6 +206,10 @@ int wf_sample(wf_model *m, const char *field, const int64_t *flat_index, int64_t
  * wf_synchronize or any later blocking call on the model. */
 int wf_gauges_create(wf_model *m, const int64_t *flat_index, int64_t n);
 int wf_gauges_sample(wf_model *m, int gauges, const char *field, float *out /* [n] */, float mv, int async);
+/* The same sample into a caller-owned DEVICE array (e.g. one row of a [T][n] block that is all-gathered over NCCL every
+ * T timesteps: the gauge time series of wf_saveTimeSeries, wflow/wf_DynamicFramework.py:1829-1884, without a host
+ * bounce).  Enqueued on the model's stream (wf_stream); returns at once. */
+int wf_gauges_sample_device(wf_model *m, int gauges, const char *field, float *dout /* device, [n] */, float mv);
 
 /* --- kinematic-wave sub-steps --------------------------------------------------------------------
  * estimate_iterations_kin_wave(Q, Beta, alpha, timestepsecs, dx, mv) (wflow/wflow_funcs.py:103-116):

@@ -150,11 +150,25 @@ class Oracle:
         self.fields[name] = a
         return a
 
+    # maps that the end-of-dynamic() outputs are formed from (wflow_sbm.py:3310-3526): requested along with them
+    END_DEPS = {
+        "MassBalKinWaveR": ["Inwater"], "MassBalKinWaveL": ["InwaterL", "InflowKinWaveCellLand"],
+        "RunoffCoeff": ["RainFallPlusMelt"], "CellStorage": ["SatWaterDepth"], "DeltaStorage": ["SatWaterDepth"],
+        "RootStore": ["RootStore_unsat"], "vwcRoot": ["RootStore_unsat"], "vwc_percRoot": ["RootStore_unsat"],
+        "ExfiltWaterCubic": ["ExfiltWater"], "InfiltExcessCubic": ["InfiltExcess"], "CumActInfilt": ["ActInfilt"],
+        "CumCellInFlow": ["CellInFlow"], "CumPrec": ["Precipitation"], "CumEvap": ["ActEvap"], "CumPotenEvap": ["PotenEvap"],
+        "CumInt": ["Interception"], "CumLeakage": ["ActLeakage"], "CumExfiltWater": ["ExfiltWater"],
+    }
+
     def want(self, *names):
         """Request diagnostic outputs."""
         for n in names:
-            if n not in self.fields:
-                self.fields[n] = np.zeros(self.shape, np.float32)
+            deps = list(self.END_DEPS.get(n, []))
+            if n.startswith("vwc_perc_"):
+                deps.append("vwc_" + n.rsplit("_", 1)[1])
+            for d in deps + [n]:
+                if d not in self.fields:
+                    self.fields[d] = np.zeros(self.shape, np.float32)
 
     def __getitem__(self, name):
         return self.fields[name]

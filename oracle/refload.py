@@ -16,7 +16,12 @@ import os
 import sys
 import types
 
+# the reference checkout (build container), or the copy of the three files this loader executes that
+# __graft_entry__.build() puts under the git-ignored baseline/_ref/ so that the GPU box can time the reference itself
+_HERE = os.path.dirname(os.path.abspath(__file__))
 REFERENCE_ROOT = os.environ.get("WFLOW_REFERENCE_ROOT", "/root/reference")
+if not os.path.isfile(os.path.join(REFERENCE_ROOT, "wflow", "wflow_sbm.py")):
+    REFERENCE_ROOT = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")
 
 
 def available() -> bool:

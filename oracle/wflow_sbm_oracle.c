@@ -80,7 +80,15 @@
   X(ExfiltFromUstore) X(ExfiltFromSat) X(InwaterL) X(InflowKinWaveCellLand) X(CellInFlow) \
   X(SoilWatbal) X(InterceptionWatBal) X(SurfaceWatbal) X(watbal) X(RootStore_unsat) \
   X(vwc_0) X(vwc_1) X(vwc_2) X(vwc_3) X(vwc_4) X(vwc_5) X(vwc_6) X(vwc_7) \
-  X(Snow2Glacier) X(GlacierMelt)
+  X(Snow2Glacier) X(GlacierMelt) \
+  /* end of dynamic(), wflow_sbm.py:3310-3312, 3348-3370, 3429-3526 (out, optional; the Cum* maps accumulate in place) */ \
+  X(KinWaveVolumeR) X(KinWaveVolumeL) X(OldKinWaveVolumeR) X(OldKinWaveVolumeL) X(MassBalKinWaveR) X(MassBalKinWaveL) \
+  X(InflowKinWaveCell) X(RiverRunoffMM) X(LandRunoffMM) X(QCatchmentMM) X(RunoffCoeff) X(CellStorage) X(DeltaStorage) \
+  X(SatWaterFlux) X(sumUstore) X(SnowCover) X(RootStore) X(RootStore_sat) X(vwcRoot) X(vwc_percRoot) \
+  X(vwc_perc_0) X(vwc_perc_1) X(vwc_perc_2) X(vwc_perc_3) X(vwc_perc_4) X(vwc_perc_5) X(vwc_perc_6) X(vwc_perc_7) \
+  X(SumEvapSat) X(SumEvapUstore) X(ExfiltWaterCubic) X(InfiltExcessCubic) X(SurfaceWaterSupply) \
+  X(CumOutFlow) X(CumActInfilt) X(CumCellInFlow) X(CumPrec) X(CumEvap) X(CumPotenEvap) X(CumInt) X(CumLeakage) \
+  X(CumExfiltWater) X(CumSurfaceWater)
 
 enum {
 #define X(n) WFO_##n,
@@ -423,10 +431,25 @@ int wfo_step(const wfo_params *p, const wfo_network *net, const wfo_network *rne
          *WLLsubD = LandRunoffsubD + N, *InwaterMMf = WLLsubD + N, *RainPlusMeltD = InwaterMMf + N,
          *OldCanopy = RainPlusMeltD + N, *RunoffRiverD = OldCanopy + N;
 
+  /* values of BEFORE the step that the end-of-dynamic() outputs need (only when one of them is requested) */
+  int want_end = 0;
+  for (int k = WFO_KinWaveVolumeR; k <= WFO_CumSurfaceWater; k++) want_end |= fields[k] != 0;
+  float *pre = want_end ? (float *)calloc((size_t)N * 4, sizeof(float)) : 0;
+  if (want_end && !pre) { free(W); free(Ul); return -4; }
+  float *preWLR = pre, *preWLRsub = pre ? pre + N : 0, *preWLLsub = pre ? pre + 2 * N : 0, *preOrg = pre ? pre + 3 * N : 0;
+
   /* ---------------- P0-P3: PCRaster REAL4 phases (wflow_sbm.py:2583-2819) ---------------- */
 #pragma omp parallel for schedule(static) num_threads(g_threads)
   for (int64_t i = 0; i < N; i++) {
     if (!active[i]) continue;
+    if (pre) {
+      preWLR[i] = F(WaterLevelR)[i]; preWLRsub[i] = F(WaterLevelRsub)[i]; preWLLsub[i] = F(WaterLevelLsub)[i];
+      float su = 0.0f;                                                /* sum_list_cover, wflow_lib.py:65-78 */
+      for (int k = 0; k < ML; k++) su = su + Uf[k][i];
+      /* OrgStorage :2627-2629: the SatWaterDepth MAP of the end of the previous step (or of resume()) */
+      preOrg[i] = su + (F(SatWaterDepth) ? F(SatWaterDepth)[i]
+                                         : (F(thetaS)[i] - F(thetaR)[i]) * (F(SoilThickness)[i] - F(zi)[i]));
+    }
     float Precipitation = fmaxf(0.0f, F(P)[i]);                       /* :2584 */
     float PotenEvap = F(PET)[i] * F(et_RefToPot)[i];                  /* :2615 */
     float Temperature = F(TEMP) ? F(TEMP)[i] : 0.0f;
@@ -813,11 +836,14 @@ int wfo_step(const wfo_params *p, const wfo_network *net, const wfo_network *rne
       for (int k = 0; k < ML; k++) {
         float *vw = fields[WFO_vwc_0 + k];
         if (!vw) continue;
+        double vwc = vw[idx];  /* layer["vwc"] keeps its value where neither branch writes (:792-803) */
         if (k < m_new) {
-          if (thick[k] > 0) vw[idx] = (float)((*U[k] + (thick[k] - L_new[k]) * (thetaS - thetaR)) / thick[k] + thetaR);
+          if (thick[k] > 0) vwc = (*U[k] + (thick[k] - L_new[k]) * (thetaS - thetaR)) / thick[k] + thetaR;
         } else {
-          vw[idx] = (float)thetaS;
+          vwc = thetaS;
         }
+        vw[idx] = (float)vwc;
+        if (fields[WFO_vwc_perc_0 + k]) fields[WFO_vwc_perc_0 + k][idx] = (float)((vwc / thetaS) * 100.0); /* :805-807 */
       }
       double rootStore_unsat = 0;
       for (int k = 0; k < nLn; k++)
@@ -853,6 +879,8 @@ int wfo_step(const wfo_params *p, const wfo_network *net, const wfo_network *rne
       OUT(ExfiltFromUstore, idx, ExfiltFromUstore); OUT(ExfiltFromSat, idx, ExfiltSatWater);
       OUT(InwaterL, idx, InwaterO[idx]); OUT(CellInFlow, idx, CellInFlow);
       OUT(SoilWatbal, idx, SoilWatbal); OUT(RootStore_unsat, idx, rootStore_unsat);
+      OUT(SumEvapSat, idx, (float)soilevapsat + (float)ActEvapSat);          /* :3118-3122 */
+      OUT(SumEvapUstore, idx, (float)soilevapunsat + (float)ActEvapUStore);  /* :3123-3127 */
       if (F(SurfaceWatbal) || F(watbal)) { /* :3515-3526 (REAL4) */
         float sw = (float)RainPlusMeltD[idx] + 0.0f;
         sw = sw - (float)InfiltExcess; sw = sw - (float)ExcessWater; sw = sw - (float)RunoffRiverD[idx];
@@ -930,7 +958,7 @@ int wfo_step(const wfo_params *p, const wfo_network *net, const wfo_network *rne
       float str_ = (float)ssf_toriverD[i];
       float Inwater = (((float)InwaterMMf[i] * ToCubic) + qtr) + str_;  /* :3063 */
       float Inflow = F(Inflow) ? F(Inflow)[i] : 0.0f;
-      if (Inflow < 0.0f) { free(W); free(Ul); return -5; }             /* abstraction loop not restated */
+      if (Inflow < 0.0f) { free(W); free(Ul); free(pre); return -5; }             /* abstraction loop not restated */
       Inwater = Inwater + Inflow;                                       /* :3144 (SurfaceWaterSupply == 0) */
       OUT(Inwater, i, Inwater);
       qr[i] = (double)(Inwater / F(DCL)[i]);                            /* :3152 */
@@ -966,6 +994,116 @@ int wfo_step(const wfo_params *p, const wfo_network *net, const wfo_network *rne
       F(WaterLevelRsub)[i] = (float)rwl[i];
     }
   }
-  free(W); free(Ul);
+  /* ---------------- end of dynamic(): kinematic-wave volumes and mass balances, unit conversions, storage change,
+   * root-zone water content, cumulative sums (wflow_sbm.py:3310-3312, 3348-3370, 3429-3526; updateKinWaveVolume :946-953).
+   * REAL4 map algebra on the float32 maps of this step; the maps it reads must be requested with the outputs
+   * (oracle.py does that).  A division by zero is a missing value in PCRaster: -999 here. ---------------- */
+  if (want_end) {
+    const float MV = -999.0f;
+    float *ct1 = (float *)calloc((size_t)N * 3, sizeof(float));
+    if (!ct1) { free(W); free(Ul); free(pre); return -4; }
+    float *ctR = ct1 + N, *inflowKW = ct1 + 2 * N;
+    const int need_ct = F(QCatchmentMM) || F(RunoffCoeff);
+    for (int64_t kk = 0; kk < net->ncells; kk++) { /* pcr.upstream(TopoLdd, RiverRunoff) :3349, neighbour order of _up_nb */
+      const int64_t idx = net->nodes[kk];
+      const int64_t *nbs = net->nodes_up + 8 * kk;
+      float up = 0.0f;
+      for (int j = 0; j < 8; j++)
+        if (nbs[j] >= 0) up = up + F(RiverRunoff)[nbs[j]];
+      inflowKW[idx] = up;
+    }
+    if (need_ct) {
+      /* pcr.catchmenttotal over the LDD MAP (:3467-3469, :1989): every cell with a valid ldd code counts, also the cells
+       * that set_dd's flat-index-0 quirk leaves out of the network (wflow_funcs.py:88).  Kahn order, float32 sums. */
+      static const int dr[10] = {0, 1, 1, 1, 0, 0, 0, -1, -1, -1}, dc[10] = {0, -1, 0, 1, -1, 0, 1, -1, 0, 1};
+      int64_t *ds = (int64_t *)malloc(sizeof(int64_t) * (size_t)N * 2);
+      int32_t *indeg = (int32_t *)calloc((size_t)N, sizeof(int32_t));
+      if (!ds || !indeg) { free(ds); free(indeg); free(ct1); free(W); free(Ul); free(pre); return -4; }
+      int64_t *queue = ds + N;
+      for (int64_t i = 0; i < N; i++) {
+        ds[i] = -1;
+        ct1[i] = 1.0f;
+        ctR[i] = F(RainFallPlusMelt) ? F(RainFallPlusMelt)[i] : 0.0f;
+        const int c = ldd[i];
+        if (c < 1 || c > 9 || c == 5) continue;
+        const int64_t r2 = i / p->ncol + dr[c], c2 = i % p->ncol + dc[c];
+        if (r2 < 0 || r2 >= p->nrow || c2 < 0 || c2 >= p->ncol) continue;
+        const int64_t d = r2 * p->ncol + c2;
+        if (ldd[d] < 1 || ldd[d] > 9) continue;
+        ds[i] = d;
+        indeg[d]++;
+      }
+      int64_t qh = 0, qt = 0;
+      for (int64_t i = 0; i < N; i++)
+        if (ldd[i] >= 1 && ldd[i] <= 9 && indeg[i] == 0) queue[qt++] = i;
+      while (qh < qt) {
+        const int64_t c = queue[qh++], d = ds[c];
+        if (d < 0) continue;
+        ct1[d] = ct1[d] + ct1[c];
+        ctR[d] = ctR[d] + ctR[c];
+        if (--indeg[d] == 0) queue[qt++] = d;
+      }
+      free(ds); free(indeg);
+    }
+#pragma omp parallel for schedule(static) num_threads(g_threads)
+    for (int64_t i = 0; i < N; i++) {
+      if (!active[i]) continue;
+      const float xl = F(xl)[i], yl = F(yl)[i], thS = F(thetaS)[i], thR = F(thetaR)[i];
+      const float ToCubic = ((xl * yl) * 0.001f) / dtf;                 /* :1998 */
+      const float QMMConv = dtf / ((xl * yl) * 0.001f);                 /* :1985 */
+      const float RR = F(RiverRunoff)[i], LR = F(LandRunoff)[i];
+      const float KWVR = (F(WaterLevelRsub)[i] * F(Bw)[i]) * F(DCL)[i]; /* :950-953 */
+      const float KWVL = (F(WaterLevelLsub)[i] * F(SW)[i]) * F(DL)[i];
+      const float OldKWVR = (preWLRsub[i] * F(Bw)[i]) * F(DCL)[i], OldKWVL = (preWLLsub[i] * F(SW)[i]) * F(DL)[i];
+      OUT(KinWaveVolumeR, i, KWVR); OUT(KinWaveVolumeL, i, KWVL);
+      OUT(OldKinWaveVolumeR, i, OldKWVR); OUT(OldKinWaveVolumeL, i, OldKWVL);
+      OUT(InflowKinWaveCell, i, inflowKW[i]);
+      if (F(MassBalKinWaveR))                                           /* :3351-3356 */
+        F(MassBalKinWaveR)[i] = (((((-KWVR) + OldKWVR) / dtf) + inflowKW[i]) + F(Inwater)[i]) - RR;
+      if (F(MassBalKinWaveL))                                           /* :3365-3370 */
+        F(MassBalKinWaveL)[i] = (((((-KWVL) + OldKWVL) / dtf) + F(InflowKinWaveCellLand)[i]) + F(InwaterL)[i]) - LR;
+      OUT(RiverRunoffMM, i, RR * QMMConv); OUT(LandRunoffMM, i, LR * QMMConv);   /* :3305-3312 */
+      if (need_ct) {
+        const float temp = (((ct1[i] * xl) * 0.001f) * 0.001f) * yl;    /* :1989-1997 */
+        const float QMMConvUp = (temp != 0.0f) ? (float)(p->timestepsecs * 0.001) / temp : MV;
+        const float QC = (QMMConvUp != MV) ? RR * QMMConvUp : MV;       /* :3465 */
+        OUT(QCatchmentMM, i, QC);
+        OUT(RunoffCoeff, i, (QC != MV && ctR[i] != 0.0f) ? (QC / ctR[i]) / ct1[i] : MV); /* :3466-3470 */
+      }
+      float su = 0.0f;
+      for (int k = 0; k < ML; k++) su = su + Uf[k][i];
+      const float Sat = F(SatWaterDepth) ? F(SatWaterDepth)[i] : (float)SatD[i];
+      const float CellStorage = su + Sat;                               /* :3473-3475 */
+      OUT(sumUstore, i, su); OUT(CellStorage, i, CellStorage); OUT(DeltaStorage, i, CellStorage - preOrg[i]);
+      const float SatWaterFlux = F(SubsurfaceFlow)[i] / (((xl * 1000.0f) * yl) * 1000.0f); /* :3480 */
+      OUT(SatWaterFlux, i, SatWaterFlux);
+      if (F(SnowCover)) F(SnowCover)[i] = (F(Snow) && F(Snow)[i] > 0.0f) ? 1.0f : 0.0f;  /* :3499-3501 */
+      const float ActRoot = fminf(F(SoilThickness)[i] * 0.99f, F(RootingDepth)[i]);      /* :2783 */
+      const float RSsat = fmaxf(0.0f, ActRoot - F(zi)[i]) * (thS - thR);                 /* :3431-3433 */
+      OUT(RootStore_sat, i, RSsat);
+      if (F(RootStore) || F(vwcRoot) || F(vwc_percRoot)) {
+        const float RS = RSsat + F(RootStore_unsat)[i];                 /* :3456 */
+        const float vwcRoot = (ActRoot != 0.0f) ? (RS / ActRoot) + thR : MV;
+        OUT(RootStore, i, RS); OUT(vwcRoot, i, vwcRoot);
+        OUT(vwc_percRoot, i, (vwcRoot != MV && thS != 0.0f) ? (vwcRoot / thS) * 100.0f : MV);
+      }
+      if (F(ExfiltWaterCubic)) F(ExfiltWaterCubic)[i] = F(ExfiltWater)[i] * ToCubic;     /* :3128-3129 */
+      if (F(InfiltExcessCubic)) F(InfiltExcessCubic)[i] = F(InfiltExcess)[i] * ToCubic;
+      OUT(SurfaceWaterSupply, i, 0.0f);                                 /* no abstraction: Inflow >= 0 (:3138-3140) */
+      /* cumulative sums, :3487-3504 and :3058 */
+      if (F(CumOutFlow)) F(CumOutFlow)[i] = F(CumOutFlow)[i] + SatWaterFlux;
+      if (F(CumActInfilt)) F(CumActInfilt)[i] = F(CumActInfilt)[i] + F(ActInfilt)[i];
+      if (F(CumCellInFlow)) F(CumCellInFlow)[i] = F(CumCellInFlow)[i] + F(CellInFlow)[i];
+      if (F(CumPrec)) F(CumPrec)[i] = F(CumPrec)[i] + F(Precipitation)[i];
+      if (F(CumEvap)) F(CumEvap)[i] = F(CumEvap)[i] + F(ActEvap)[i];
+      if (F(CumPotenEvap)) F(CumPotenEvap)[i] = F(CumPotenEvap)[i] + F(PotenEvap)[i];
+      if (F(CumInt)) F(CumInt)[i] = F(CumInt)[i] + F(Interception)[i];
+      if (F(CumLeakage)) F(CumLeakage)[i] = F(CumLeakage)[i] + F(ActLeakage)[i];
+      if (F(CumExfiltWater)) F(CumExfiltWater)[i] = F(CumExfiltWater)[i] + F(ExfiltWater)[i];
+      if (F(CumSurfaceWater)) F(CumSurfaceWater)[i] = F(CumSurfaceWater)[i] + (preWLR[i] / 1000.0f);
+    }
+    free(ct1);
+  }
+  free(W); free(Ul); free(pre);
   return 0;
 }

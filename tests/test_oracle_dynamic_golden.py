@@ -10,6 +10,9 @@ from tests import common
 
 # cancellation residuals of ~1e3 mm terms: the reference forms them in another association than the oracle
 RESIDUALS = {"SoilWatbal": 1e-9, "watbal": 2e-4, "SurfaceWatbal": 0.0, "InterceptionWatBal": 0.0}
+# float32 sums over a whole catchment (pcr.catchmenttotal): the order in which the cells of a catchment are added is
+# PCRaster's own and not documented; the shim and the oracle both use a topological (Kahn) order
+SUM_ORDER = {"RunoffCoeff": 1e-6, "QCatchmentMM": 1e-6}
 
 
 @pytest.mark.parametrize("name", common.golden_dyn_cases())
@@ -20,7 +23,7 @@ def test_dynamic_trajectory_golden(name):
     outs = [f for f in common.dyn_outputs(g) if f in orc.names and f not in ("Cmax", "CanopyGapFraction", "EoverR")]
     missing = [f for f in common.dyn_outputs(g) if f not in orc.names]
     orc.want(*[f for f in outs if f not in orc.fields])
-    assert len(outs) >= 60, missing
+    assert len(outs) >= 100 and not missing, missing
     for t in range(kw["steps"]):
         for f in ("P", "PET", "TEMP", "Inflow"):
             key = "forcing/%d/%s" % (t, f)
@@ -35,6 +38,8 @@ def test_dynamic_trajectory_golden(name):
             a, b = orc[f][mask], g["out/%d/%s" % (t, f)][mask]
             if RESIDUALS.get(f, 0.0) > 0.0:
                 assert np.allclose(a, b, rtol=0, atol=RESIDUALS[f]), (name, t, f)
+            elif f in SUM_ORDER:
+                assert np.allclose(a, b, rtol=SUM_ORDER[f], atol=0), (name, t, f)
             else:
                 assert np.array_equal(a, b), (name, t, f, int((a != b).sum()), float(np.abs(a - b).max()))
 

@@ -43,7 +43,7 @@ SYMBOLS = [
     "wf_timing_reset", "wf_timing_get", "wf_kinematic_wave_batch", "wf_kinematic_wave_ssf_batch",
     "wf_schedule_partition", "wf_lateral_plan", "wf_gauges_create", "wf_gauges_sample",
     "wf_estimate_iterations", "wf_set_substeps", "wf_pipeline_reserve", "wf_pipeline_set_forcing",
-    "wf_pipeline_forcing_ptr", "wf_pipeline_capture", "wf_step_pipelined",
+    "wf_pipeline_forcing_ptr", "wf_pipeline_capture", "wf_step_pipelined", "wf_gauges_sample_device",
 ]
 
 
@@ -112,6 +112,7 @@ def lib():
     l.wf_lateral_plan.argtypes = [C.c_void_p, C.c_void_p]
     l.wf_gauges_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     l.wf_gauges_sample.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_float, C.c_int]
+    l.wf_gauges_sample_device.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_float]
     l.wf_estimate_iterations.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]
     l.wf_set_substeps.argtypes = [C.c_void_p, C.c_int, C.c_int]
     l.wf_pipeline_reserve.argtypes = [C.c_void_p, C.c_int]

@@ -328,6 +328,10 @@ class SbmModel:
         when wait=False, valid after synchronize())."""
         _lib.check(self._l.wf_gauges_sample(self._h, int(handle), field.encode(), out_ptr, float(mv), 0 if wait else 1))
 
+    def gauges_sample_device(self, handle, field, dev_ptr, mv=-999.0):
+        """Sample `field` at the gauge set into a caller-owned DEVICE float32 array (raw pointer), on the model's stream."""
+        _lib.check(self._l.wf_gauges_sample_device(self._h, int(handle), field.encode(), dev_ptr, float(mv)))
+
     def sample(self, field, flat_index, mv=-999.0):
         idx = np.ascontiguousarray(flat_index, dtype=np.int64)
         out = np.zeros(max(idx.size, 1), np.float32)

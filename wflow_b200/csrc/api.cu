@@ -87,6 +87,19 @@ struct wf_model {
   cudaEvent_t ring_copied[kStageRing] = {}, ring_free[kStageRing] = {};
   int ring_next = 0;
   cudaStream_t copy_stream = nullptr;
+  // Forcing rasters set from the host (wf_set_field on P / PET / TEMP / Inflow) are put into storage order ON THE COPY
+  // STREAM, into a ring of storage-order arrays per field: the model's stream only waits for the event of the array it is
+  // about to read, so upload AND re-ordering of step s+1's forcing overlap the kernels of step s (the three k_gather
+  // launches used to sit on the model's stream between the kernels: 0.45 ms of a 13.8 ms step, r1).
+  static const int kForcSlots = 3;
+  struct ForcRing {
+    float *slot[kForcSlots] = {};
+    cudaEvent_t ready[kForcSlots] = {}, freed[kForcSlots] = {};
+    bool used[kForcSlots] = {};        // a step has been launched that reads the slot since it was filled
+    int cur = -1;                      // slot dm.f[id] points at (-1: the field's own array)
+    bool pending = false;              // the model's stream has not waited for ready[cur] yet
+  };
+  std::map<int, ForcRing> forc;
   std::vector<int32_t> pos_of_flat;  // flat grid index -> storage position (-1 outside the network)
   struct GaugeSet {
     int64_t n = 0;
@@ -209,6 +222,8 @@ LateralPlan plan_lateral(int64_t n, int64_t D, int64_t nbasins, int sms) {
 template <int ML>
 int launch_lateral(wf_model *m) {
   if (const char *iv = std::getenv("WF_LAT_INTERLEAVE")) m->dm.lat_interleave = std::atoi(iv);  // development aid
+  if (const char *iv = std::getenv("WF_LAT_PREFETCH"))  // development aid: 0 = no L2 warm-up of the coming ticks' operands
+    m->dm.task_mask = std::atoi(iv) ? (m->dm.task_mask & ~8) : (m->dm.task_mask | 8);
   void *args[] = {(void *)&m->dm};
   if (m->lat_mode == WF_GRID) {
     if (m->lat_blocks == 0) {
@@ -635,6 +650,8 @@ static void catchment_total(const Network &net, const float *values, double *out
 }
 
 extern "C" {
+static int forcing_acquire(wf_model *m);
+static int forcing_release(wf_model *m);
 static int create_impl(wf_model *m, const wf_config *cfg, wf_schedule *sched, const uint8_t *ldd, const uint8_t *river);
 
 const char *wf_last_error(void) { return g_err.c_str(); }
@@ -935,10 +952,18 @@ void wf_destroy(wf_model *m) {
     cudaFree(m->dm.prof);
   }
 #endif
+  if (m->copy_stream) cudaStreamSynchronize(m->copy_stream);
   for (int id = 0; id < F_COUNT; id++) {
+    if (m->forc.count(id)) continue;  // the ring owns every array the field ever pointed at (below)
     if (m->external[id]) cudaFree(m->owned[id]);
     else cudaFree(m->dm.f[id]);
   }
+  for (auto &kv : m->forc)
+    for (int k = 0; k < wf_model::kForcSlots; k++) {
+      cudaFree(kv.second.slot[k]);
+      if (kv.second.ready[k]) cudaEventDestroy(kv.second.ready[k]);
+      if (kv.second.freed[k]) cudaEventDestroy(kv.second.freed[k]);
+    }
   for (int b = 0; b < wf_model::kStageRing; b++) {
     cudaFree(m->d_ring[b]);
     if (m->ring_copied[b]) cudaEventDestroy(m->ring_copied[b]);
@@ -1084,11 +1109,83 @@ static int ring_release(wf_model *m, int slot) {
   return WF_OK;
 }
 
+// The model's stream waits for the forcing arrays filled on the copy stream that it has not seen yet.
+// Called by everything that reads a forcing field on the model's stream.
+static int forcing_acquire(wf_model *m) {
+  for (auto &kv : m->forc) {
+    wf_model::ForcRing &r = kv.second;
+    if (r.pending && r.cur >= 0) {
+      CUDA_OK(cudaStreamWaitEvent(m->stream, r.ready[r.cur], 0));
+      r.pending = false;
+    }
+  }
+  return WF_OK;
+}
+// After the kernels of a step have been enqueued: the forcing arrays they read may be refilled once they are done.
+static int forcing_release(wf_model *m) {
+  for (auto &kv : m->forc) {
+    wf_model::ForcRing &r = kv.second;
+    if (r.cur >= 0 && !m->external[kv.first]) {
+      CUDA_OK(cudaEventRecord(r.freed[r.cur], m->stream));
+      r.used[r.cur] = true;
+    }
+  }
+  return WF_OK;
+}
+// wf_set_field of a forcing raster: host -> staging ring -> next storage-order slot, all on the copy stream.
+static int set_forcing_async(wf_model *m, int id, const float *grid) {
+  const bool riv = g_fields[id].kind & K_RIVER;
+  const int64_t len = riv ? m->nr : m->n;
+  const bool fresh = m->forc.find(id) == m->forc.end();
+  wf_model::ForcRing &r = m->forc[id];
+  if (fresh && m->dm.f[id]) {
+    // the field's own array becomes slot 0 of the ring; steps already enqueued may still read it
+    r.slot[0] = m->dm.f[id];
+    CUDA_OK(cudaEventCreateWithFlags(&r.ready[0], cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&r.freed[0], cudaEventDisableTiming));
+    CUDA_OK(cudaEventRecord(r.freed[0], m->stream));
+    r.used[0] = true;
+    r.cur = 0;
+  }
+  const int k = (r.cur + 1) % wf_model::kForcSlots;
+  if (!r.slot[k]) {
+    CUDA_OK(cudaMalloc(&r.slot[k], sizeof(float) * (size_t)std::max<int64_t>(len, 1)));
+    CUDA_OK(cudaEventCreateWithFlags(&r.ready[k], cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&r.freed[k], cudaEventDisableTiming));
+  }
+  const size_t bytes = sizeof(float) * (size_t)m->cfg.nrow * m->cfg.ncol;
+  const int b = m->ring_next;
+  m->ring_next = (b + 1) % wf_model::kStageRing;
+  if (!m->copy_stream) CUDA_OK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  if (!m->d_ring[b]) {
+    CUDA_OK(cudaMalloc(&m->d_ring[b], bytes));
+    CUDA_OK(cudaEventCreateWithFlags(&m->ring_copied[b], cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&m->ring_free[b], cudaEventDisableTiming));
+  } else {
+    CUDA_OK(cudaStreamWaitEvent(m->copy_stream, m->ring_free[b], 0));  // the gather that last read the staging raster
+  }
+  if (r.used[k]) CUDA_OK(cudaStreamWaitEvent(m->copy_stream, r.freed[k], 0));  // the step that last read the slot
+  r.used[k] = false;
+  CUDA_OK(cudaMemcpyAsync(m->d_ring[b], grid, bytes, cudaMemcpyHostToDevice, m->copy_stream));
+  if (len > 0) {
+    k_gather<<<(unsigned)((len + 255) / 256), 256, 0, m->copy_stream>>>(m->d_ring[b], riv ? m->d_rorder : m->d_order, r.slot[k], len);
+    m->launches++;
+  }
+  CUDA_OK(cudaEventRecord(m->ring_free[b], m->copy_stream));
+  CUDA_OK(cudaEventRecord(r.ready[k], m->copy_stream));
+  r.cur = k;
+  r.pending = true;
+  m->dm.f[id] = r.slot[k];
+  CUDA_OK(cudaGetLastError());
+  return WF_OK;
+}
+
 int wf_set_field(wf_model *m, const char *name, const float *grid) {
   if (!m || !grid) return fail(WF_EINVAL, "null argument");
   const int id = field_index(name);
   if (id < 0) return fail(WF_EINVAL, std::string("unknown field: ") + (name ? name : "(null)"));
   CUDA_OK(cudaSetDevice(m->cfg.device));
+  if ((g_fields[id].kind & 0xff) == K_FORCING && !m->external[id]) return set_forcing_async(m, id, grid);
   int b = 0;
   if (int rc = ring_upload(m, grid, &b)) return rc;
   const int rc = gather_into(m, id, m->d_ring[b]);
@@ -1101,6 +1198,7 @@ int wf_set_field_from_device(wf_model *m, const char *name, const float *dgrid) 
   const int id = field_index(name);
   if (id < 0) return fail(WF_EINVAL, std::string("unknown field: ") + (name ? name : "(null)"));
   CUDA_OK(cudaSetDevice(m->cfg.device));
+  if (int rc = forcing_acquire(m)) return rc;
   return gather_into(m, id, dgrid);
 }
 
@@ -1109,6 +1207,7 @@ int wf_set_field_uniform(wf_model *m, const char *name, float value) {
   const int id = field_index(name);
   if (id < 0) return fail(WF_EINVAL, std::string("unknown field: ") + (name ? name : "(null)"));
   CUDA_OK(cudaSetDevice(m->cfg.device));
+  if (int rc = forcing_acquire(m)) return rc;
   if (int rc = ensure_field(m, id)) return rc;
   if ((g_fields[id].kind & 0xff) == K_STATIC) m->derived_dirty = true;
   const int64_t len = field_len(m, id);
@@ -1126,6 +1225,7 @@ int wf_get_field(wf_model *m, const char *name, float *grid, float mv) {
   if (id < 0) return fail(WF_EINVAL, std::string("unknown field: ") + (name ? name : "(null)"));
   if (!m->dm.f[id]) return fail(WF_EINVAL, std::string("field has no data (not set / not requested): ") + name);
   CUDA_OK(cudaSetDevice(m->cfg.device));
+  if (int rc = forcing_acquire(m)) return rc;
   if (int rc = stage(m)) return rc;
   const int64_t N = (int64_t)m->cfg.nrow * m->cfg.ncol;
   const bool riv = g_fields[id].kind & K_RIVER;
@@ -1134,13 +1234,8 @@ int wf_get_field(wf_model *m, const char *name, float *grid, float mv) {
   if (riv && m->n > 0) {
     // river-only arrays: the reference holds 0 at the other cells of the network (np.zeros outputs,
     // wflow_funcs.py:172-182), missing value outside it
-    float *tmp = nullptr;
-    CUDA_OK(cudaMalloc(&tmp, sizeof(float) * m->n));
-    CUDA_OK(cudaMemsetAsync(tmp, 0, sizeof(float) * m->n, m->stream));
-    k_scatter<<<(unsigned)((m->n + 255) / 256), 256, 0, m->stream>>>(tmp, m->d_order, m->d_stage, m->n);
+    k_scatter_const<<<(unsigned)((m->n + 255) / 256), 256, 0, m->stream>>>(0.0f, m->d_order, m->d_stage, m->n);
     m->launches++;
-    CUDA_OK(cudaStreamSynchronize(m->stream));
-    cudaFree(tmp);
   }
   const int64_t len = riv ? m->nr : m->n;
   if (len > 0) {
@@ -1179,6 +1274,7 @@ int wf_field_device_ptr(wf_model *m, const char *name, void **dptr, int64_t *n) 
   const int id = field_index(name);
   if (id < 0) return fail(WF_EINVAL, std::string("unknown field: ") + (name ? name : "(null)"));
   CUDA_OK(cudaSetDevice(m->cfg.device));
+  if (int rc = forcing_acquire(m)) return rc;
   if (int rc = ensure_field(m, id)) return rc;
   if ((g_fields[id].kind & 0xff) == K_STATIC) m->derived_dirty = true;  // the caller may write through the pointer
   *dptr = m->dm.f[id];
@@ -1195,11 +1291,12 @@ int wf_cell_order(const wf_model *m, int64_t *flat_index) {
 int wf_step(wf_model *m, int nsteps) {
   if (!m) return fail(WF_EINVAL, "null model");
   CUDA_OK(cudaSetDevice(m->cfg.device));
+  if (int rc = forcing_acquire(m)) return rc;
   if (int rc = check_ready(m)) return rc;
   m->timed = true;
   for (int s = 0; s < nsteps; s++)
     if (int rc = dispatch_step(m)) return rc;
-  return WF_OK;
+  return forcing_release(m);
 }
 
 
@@ -1310,6 +1407,7 @@ int wf_step_pipelined(wf_model *m, int nsteps, float *gauge_out, float mv, int a
   if (m->dm.task_mask != 7) return fail(WF_EUNSUPPORTED, "WF_LATERAL_TASKS is a development aid of the per-step sweep");
   if (gauge_out && m->pipe_gauges < 0) return fail(WF_EINVAL, "no gauge set registered (wf_pipeline_capture)");
   CUDA_OK(cudaSetDevice(m->cfg.device));
+  if (int rc = forcing_acquire(m)) return rc;
   m->timed = true;
   if (int rc = dispatch_pipeline(m, nsteps)) return rc;
   if (gauge_out) {
@@ -1445,6 +1543,7 @@ int wf_area_reduce(wf_model *m, int area, const char *field, int op, float *out)
   if (id < 0 || !m->dm.f[id]) return fail(WF_EINVAL, std::string("field has no data: ") + (field ? field : "(null)"));
   if (op < 0 || op > 3) return fail(WF_EINVAL, "bad reduction op");
   CUDA_OK(cudaSetDevice(m->cfg.device));
+  if (int rc = forcing_acquire(m)) return rc;
   AreaSet &a = m->areas[(size_t)area];
   const int nids = (int)a.ids.size();
   if (nids == 0) return WF_OK;
@@ -1464,6 +1563,7 @@ int wf_sample(wf_model *m, const char *field, const int64_t *flat_index, int64_t
   const int id = field_index(field);
   if (id < 0 || !m->dm.f[id]) return fail(WF_EINVAL, std::string("field has no data: ") + (field ? field : "(null)"));
   CUDA_OK(cudaSetDevice(m->cfg.device));
+  if (int rc = forcing_acquire(m)) return rc;
   // translate flat grid indices to array positions on the host (gauge lists are short)
   static thread_local std::vector<int32_t> pos;
   const int64_t N = (int64_t)m->cfg.nrow * m->cfg.ncol;
@@ -1528,6 +1628,7 @@ int wf_gauges_sample(wf_model *m, int gauges, const char *field, float *out, flo
   const int id = field_index(field);
   if (id < 0 || !m->dm.f[id]) return fail(WF_EINVAL, std::string("field has no data: ") + (field ? field : "(null)"));
   CUDA_OK(cudaSetDevice(m->cfg.device));
+  if (int rc = forcing_acquire(m)) return rc;
   wf_model::GaugeSet &g = m->gauges[(size_t)gauges];
   if (g.n == 0) return WF_OK;
   const bool riv = g_fields[id].kind & K_RIVER;
@@ -1536,6 +1637,21 @@ int wf_gauges_sample(wf_model *m, int gauges, const char *field, float *out, flo
   m->launches++;
   CUDA_OK(cudaMemcpyAsync(out, g.d_out, sizeof(float) * (size_t)g.n, cudaMemcpyDeviceToHost, m->stream));
   if (!async) CUDA_OK(cudaStreamSynchronize(m->stream));
+  CUDA_OK(cudaGetLastError());
+  return WF_OK;
+}
+
+int wf_gauges_sample_device(wf_model *m, int gauges, const char *field, float *dout, float mv) {
+  if (!m || !dout || gauges < 0 || gauges >= (int)m->gauges.size()) return fail(WF_EINVAL, "bad gauge-set handle");
+  const int id = field_index(field);
+  if (id < 0 || !m->dm.f[id]) return fail(WF_EINVAL, std::string("field has no data: ") + (field ? field : "(null)"));
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  if (int rc = forcing_acquire(m)) return rc;
+  wf_model::GaugeSet &g = m->gauges[(size_t)gauges];
+  if (g.n == 0) return WF_OK;
+  const bool riv = g_fields[id].kind & K_RIVER;
+  k_sample_gauges<<<(unsigned)((g.n + 127) / 128), 128, 0, m->stream>>>(m->dm.f[id], g.d_pos, riv ? g.d_rpos : nullptr, dout, g.n, mv);
+  m->launches++;
   CUDA_OK(cudaGetLastError());
   return WF_OK;
 }

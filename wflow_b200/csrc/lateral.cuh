@@ -216,7 +216,7 @@ __device__ __noinline__ void kinematic_wave_ssf(double ssf_in, double ssf_old, d
         e = e * fma(t, fma(t, fma(t, fma(t, fma(t, fma(t, fma(t, 1.0 / 5040, 1.0 / 720), 1.0 / 120), 1.0 / 24), 1.0 / 6), 0.5), 1.0), 1.0);
       else
         e = wf_exp(u);
-      if (!(fabs(du) > 1e-10)) break;
+      if (!(fabs(du) > 1e-6)) break;  // cubic convergence: the step after one below 1e-6 would be below 1e-17
     }
     ssf_n = qdiv(e - efD, fden);
     if (!(ssf_n == ssf_n) || isinf(ssf_n)) ssf_n = (ssf_old + ssf_in) / 2.0;  // the reference's first guess
@@ -784,8 +784,10 @@ __device__ __forceinline__ void prefetch_subsurface(const DevModel &m, const int
   prefetch_l2(m.f[F_xl] + i); prefetch_l2(m.f[F_yl] + i);
   for (int k = 0; k < m.ML; k++) { prefetch_l2(m.f[F_UStoreLayerDepth_0 + k] + i); prefetch_l2(m.h_ulo + (int64_t)k * m.n + i); }
   prefetch_l2(m.d_efST + i); prefetch_l2(m.d_cpd + i);
-  // the overland solve of the same cell follows two ticks later
-  prefetch_l2(m.f[F_SW] + i); prefetch_l2(m.f[F_AlphaL] + i); prefetch_l2(m.f[F_LandRunoffsub] + i);
+}
+__device__ __forceinline__ void prefetch_overland(const DevModel &m, const int64_t i) {
+  prefetch_l2(m.topo + i); prefetch_l2(m.up_start + i); prefetch_l2(m.river_slot + i); prefetch_l2(m.d_cpd + i);
+  prefetch_l2(m.f[F_SW] + i); prefetch_l2(m.f[F_AlphaL] + i); prefetch_l2(m.f[F_LandRunoffsub] + i); prefetch_l2(m.f[F_DL] + i);
   prefetch_l2(m.h_lq + i); prefetch_l2(m.h_lqb + i);
 }
 // the same for a river cell that the first river sub-step reaches soon (the later sub-steps find the lines in L2)
@@ -982,13 +984,28 @@ __device__ __forceinline__ void sweep_group(const DevModel &m, const GroupDesc g
       }
       // while the others arrive: this thread's next item and its operands ...
       nxt = prepare(t + 1);
-      // ... and the operands of the tick after into L2
-      const int pd = 2;
-      if (t + pd < nl) {
-        const uint32_t nb = lo[t + pd], ne = lo[t + pd + 1];
-        if (nb + (uint32_t)tid < ne && !(m.task_mask & 8)) prefetch_subsurface(m, (int64_t)nb + tid);
-      }
-      {
+      if (STAGE) {
+        // ... (staged sweeps) nothing else for the thread's FIRST item of a tick: its cp.async copies are issued a barrier
+        // wait ahead of their use, which covers the DRAM latency (measured: the L2 warm-up of the coming ticks' operands
+        // made no difference once the operands were staged, WF_LAT_PREFETCH, and cost 9 % of the instructions).  Items
+        // beyond the first (levels wider than the sweep has threads) are not staged: their lines are pulled into L2.
+        const int t2 = t + 2;
+        if (t2 < nticks && !(m.task_mask & 8)) {
+          const int total2 = tick_items(t2);
+          for (int j = tid + nthreads; j < total2; j += nthreads) {
+            const WaveItem it = decode_item(j, t2);
+            if (it.type == 0) prefetch_subsurface(m, (int64_t)it.idx);
+            else if (it.type == 1) prefetch_overland(m, (int64_t)it.idx);
+            else if (it.type == 2 && it.v == 0) prefetch_river(m, (int64_t)it.idx);
+          }
+        }
+      } else {
+        // ... (grid sweep) and the operands of the tick after into L2
+        const int pd = 2;
+        if (t + pd < nl) {
+          const uint32_t nb = lo[t + pd], ne = lo[t + pd + 1];
+          if (nb + (uint32_t)tid < ne && !(m.task_mask & 8)) prefetch_subsurface(m, (int64_t)nb + tid);
+        }
         const int q = q0 + t + pd;  // river level of the first sub-step in two ticks
         if (q >= 0 && q < nrl) {
           const uint32_t rb = ro[q], re = ro[q + 1];
