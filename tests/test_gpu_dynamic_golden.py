@@ -12,7 +12,29 @@ from tests import common
 pytestmark = pytest.mark.gpu
 
 ATOL = {"SubsurfaceFlow": 1e3, "SoilWatbal": 1e-3, "watbal": 1e-3, "SurfaceWatbal": 1e-4, "InterceptionWatBal": 1e-4,
-        "CellInFlow": 1e3}
+        "CellInFlow": 1e3, "CumCellInFlow": 1e3, "DeltaStorage": 2e-4, "MassBalKinWaveR": 1e-4, "MassBalKinWaveL": 1e-4,
+        "KinWaveVolumeR": 1e-2, "OldKinWaveVolumeR": 1e-2, "KinWaveVolumeL": 1e-2, "OldKinWaveVolumeL": 1e-2}
+# pcr.catchmenttotal runs over the LDD map, the device over the network set_dd built: they differ downstream of a cell that
+# set_dd's flat-index-0 quirk drops (wflow_funcs.py:88) -- such a cell is not on the device at all
+CATCHMENT = ("QCatchmentMM", "RunoffCoeff")
+
+
+def _downstream_of_dropped(ldd, mask):
+    """cells of the network that have a valid-ldd cell OUTSIDE the network somewhere upstream"""
+    nrow, ncol = ldd.shape
+    dr = {7: (-1, -1), 8: (-1, 0), 9: (-1, 1), 4: (0, -1), 6: (0, 1), 1: (1, -1), 2: (1, 0), 3: (1, 1)}
+    tainted = (ldd >= 1) & (ldd <= 9) & ~mask
+    hit = np.zeros_like(mask)
+    for r, c in zip(*np.nonzero(tainted)):
+        while True:
+            code = int(ldd[r, c])
+            if code not in dr:
+                break
+            r, c = r + dr[code][0], c + dr[code][1]
+            if not (0 <= r < nrow and 0 <= c < ncol) or not (1 <= ldd[r, c] <= 9) or hit[r, c]:
+                break
+            hit[r, c] = True
+    return hit
 
 
 @pytest.mark.parametrize("name", common.golden_dyn_cases())
@@ -26,8 +48,9 @@ def test_cuda_matches_reference_dynamic(name):
         known = set(_lib.field_names())
         skip = {"Cmax", "CanopyGapFraction", "EoverR"}  # inputs here; the reference overwrites them from LAI
         outs = [f for f in common.dyn_outputs(g) if f in known and f not in skip]
-        states = [f for f in outs if "state0/" + f in g.files]
+        states = [f for f in outs if "state0/" + f in g.files and f != "SatWaterDepth"] + ["SatWaterDepth"]  # the map itself, last
         mod.request(*outs)
+        cmask = mask & ~_downstream_of_dropped(np.asarray(g["ldd"]), mask)
         worst = (0.0, "")
         for t in range(kw["steps"]):
             for f in ("P", "PET", "TEMP", "Inflow"):
@@ -42,7 +65,7 @@ def test_cuda_matches_reference_dynamic(name):
                 mod.set_substeps(itl, itr)
             mod.step()
             for f in outs:
-                e = common.compare(mod.get(f), g["out/%d/%s" % (t, f)], mask, 1e-5, ATOL.get(f, 2e-5))
+                e = common.compare(mod.get(f), g["out/%d/%s" % (t, f)], cmask if f in CATCHMENT else mask, 1e-5, ATOL.get(f, 2e-5))
                 if e > worst[0]:
                     worst = (e, "%s step %d" % (f, t))
                 assert e <= 1.0, (name, t, f, e)

@@ -17,6 +17,7 @@
 #include "pipeline.cuh"
 #include "network.h"
 #include "reduce.cuh"
+#include "outputs.cuh"
 
 namespace wf {
 
@@ -130,7 +131,11 @@ struct wf_model {
   float *d_cap_out = nullptr, *d_cap_exp = nullptr;
   int32_t cap_n = 0;
   int pipe_blocks = 0;
-  size_t pipe_attr_smem = 0;          // dynamic shared memory limit already raised for the pipelined kernel
+  size_t pipe_attr_smem = 0;
+  // end-of-dynamic() outputs (outputs.cuh): work arrays, allocated with the first request
+  EndArgs end = {};
+  float *d_ct1 = nullptr;
+  bool satwd_valid = false;           // the SatWaterDepth map holds the end of the previous step          // dynamic shared memory limit already raised for the pipelined kernel
 };
 
 namespace {
@@ -313,6 +318,44 @@ void prepare_step(wf_model *m) {
   }
 }
 
+// ---- end-of-dynamic() outputs (outputs.cuh) ----------------------------------------------------------
+bool end_outputs_requested(const wf_model *m) {
+  for (int id = F_KinWaveVolumeR; id <= F_CumSurfaceWater; id++) {
+    if (id >= F_vwc_perc_0 && id <= F_vwc_perc_7) continue;  // written by the sweep's column tail
+    if (id == F_SumEvapSat || id == F_SumEvapUstore) continue;  // written by the column kernel
+    if (m->dm.f[id]) return true;
+  }
+  return false;
+}
+int end_prepare(wf_model *m) {
+  const size_t n = (size_t)std::max<int64_t>(m->n, 1), nr = (size_t)std::max<int32_t>(m->nr, 1);
+  if (!m->end.preOrg) {
+    CUDA_OK(cudaMalloc(&m->end.preWLRsub, sizeof(float) * nr));
+    CUDA_OK(cudaMalloc(&m->end.preWLR, sizeof(float) * nr));
+    CUDA_OK(cudaMalloc(&m->end.preWLLsub, sizeof(float) * n));
+    CUDA_OK(cudaMalloc(&m->end.preOrg, sizeof(float) * n));
+    CUDA_OK(cudaMalloc(&m->end.ctR, sizeof(float) * n));
+  }
+  if (!m->d_ct1) {
+    // catchmenttotal(1): the cells of the network upstream of each cell, itself included (static).  Counted on the
+    // network set_dd built: a cell that set_dd's flat-index-0 quirk drops (wflow_funcs.py:88) is not on the device at all.
+    std::vector<double> grid((size_t)m->cfg.nrow * m->cfg.ncol);
+    std::vector<double> acc((size_t)std::max<int64_t>(m->net.ncells, 1));
+    std::vector<float> ct(n, 1.0f);
+    for (int64_t k = 0; k < m->net.ncells; k++) {
+      double v = 1.0;
+      for (int j = 0; j < m->net.nup[(size_t)k]; j++) v += acc[(size_t)m->net.up_start[(size_t)k] + j];
+      acc[(size_t)k] = v;
+      grid[(size_t)m->net.order[(size_t)k]] = v;
+    }
+    for (int64_t k = 0; k < m->n; k++) ct[(size_t)k] = (float)grid[(size_t)m->snet.order[(size_t)k]];
+    CUDA_OK(cudaMalloc(&m->d_ct1, sizeof(float) * n));
+    CUDA_OK(cudaMemcpy(m->d_ct1, ct.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+    m->end.ct1 = m->d_ct1;
+  }
+  return WF_OK;
+}
+
 template <int ML>
 int launch_step(wf_model *m) {
   const int64_t n = m->n;
@@ -325,6 +368,14 @@ int launch_step(wf_model *m) {
   if (m->timed) cudaEventRecord(e0, m->stream);
   const int tb = WF_VERT_THREADS;
   prepare_step<ML>(m);
+  const bool end_out = end_outputs_requested(m);
+  if (end_out) {
+    if (int rc = end_prepare(m)) return rc;
+    m->end.satwd_valid = m->satwd_valid ? 1 : 0;
+    const int64_t span = std::max<int64_t>(n, m->nr);
+    k_end_pre<ML><<<(unsigned)((span + 255) / 256), 256, 0, m->stream>>>(m->dm, m->end);
+    m->launches++;
+  }
   const size_t vsmem = WF_VERT_STAGE ? VLayout<ML>::bytes(m->dm.glacier != 0) : 0;
   // four builds of the column: with / without the diagnostic outputs, with / without the LAI-driven canopy parameters
   void (*kv)(const DevModel) = nullptr;
@@ -341,6 +392,15 @@ int launch_step(wf_model *m) {
   m->launches++;
   if (m->timed) cudaEventRecord(e2, m->stream);
   m->ev_last[0] = e0; m->ev_last[1] = e1; m->ev_last[2] = e2;
+  if (end_out) {
+    if (m->dm.f[F_QCatchmentMM] || m->dm.f[F_RunoffCoeff]) {
+      k_catchment_total<<<(unsigned)std::max(1, std::min(m->dm.ngroups, 1024)), 1024, 0, m->stream>>>(m->dm, m->dm.f[F_RainFallPlusMelt], m->end.ctR);
+      m->launches++;
+    }
+    k_end_outputs<ML><<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->dm, m->end);
+    m->launches++;
+  }
+  m->satwd_valid = m->dm.f[F_SatWaterDepth] != nullptr;
   CUDA_OK(cudaGetLastError());
   return WF_OK;
 }
@@ -976,6 +1036,7 @@ void wf_destroy(wf_model *m) {
   for (cudaEvent_t e : m->tev) cudaEventDestroy(e);
   for (float *p : m->snapshot) cudaFree(p);
   for (auto &a : m->areas) { cudaFree(a.d_perm); cudaFree(a.d_seg); }
+  cudaFree(m->end.preWLRsub); cudaFree(m->end.preWLR); cudaFree(m->end.preWLLsub); cudaFree(m->end.preOrg); cudaFree(m->end.ctR); cudaFree(m->d_ct1);
   cudaFree(m->dm.d_efT); cudaFree(m->dm.d_efST); cudaFree(m->dm.d_cpd);
   cudaFree(m->dm.h_lq); cudaFree(m->dm.h_lqb); cudaFree(m->dm.h_rq); cudaFree(m->dm.h_rqb);
   cudaFree(m->dm.h_ssf_riv); cudaFree(m->dm.h_qa); cudaFree(m->dm.h_qb); cudaFree(m->dm.grid_counter);
@@ -1072,6 +1133,8 @@ static int stage(wf_model *m) {
 static int gather_into(wf_model *m, int id, const float *dgrid) {
   if (int rc = ensure_field(m, id)) return rc;
   if ((g_fields[id].kind & 0xff) == K_STATIC) m->derived_dirty = true;
+  if (id == F_zi) m->satwd_valid = false;  // SatWaterDepth follows the water table that was set ...
+  if (id == F_SatWaterDepth) m->satwd_valid = true;  // ... unless the caller hands the map over itself (wf_resume reads SatWaterDepth.map)
   const bool riv = g_fields[id].kind & K_RIVER;
   const int64_t len = riv ? m->nr : m->n;
   if (len > 0) {
@@ -1255,6 +1318,22 @@ int wf_request_output(wf_model *m, const char *name, int enable) {
   CUDA_OK(cudaSetDevice(m->cfg.device));
   if (enable) {
     if (int rc = ensure_field(m, id)) return rc;
+    {  // maps an end-of-dynamic() output is formed from (outputs.cuh)
+      static const std::map<int, std::vector<int>> deps = {
+          {F_MassBalKinWaveR, {F_Inwater}}, {F_MassBalKinWaveL, {F_InwaterL, F_InflowKinWaveCellLand}},
+          {F_RunoffCoeff, {F_RainFallPlusMelt}}, {F_CellStorage, {F_SatWaterDepth}}, {F_DeltaStorage, {F_SatWaterDepth}},
+          {F_RootStore, {F_RootStore_unsat}}, {F_vwcRoot, {F_RootStore_unsat}}, {F_vwc_percRoot, {F_RootStore_unsat}},
+          {F_ExfiltWaterCubic, {F_ExfiltWater}}, {F_InfiltExcessCubic, {F_InfiltExcess}}, {F_CumActInfilt, {F_ActInfilt}},
+          {F_CumCellInFlow, {F_CellInFlow}}, {F_CumPrec, {F_Precipitation}}, {F_CumEvap, {F_ActEvap}},
+          {F_CumPotenEvap, {F_PotenEvap}}, {F_CumInt, {F_Interception}}, {F_CumLeakage, {F_ActLeakage}},
+          {F_CumExfiltWater, {F_ExfiltWater}}};
+      auto it = deps.find(id);
+      if (it != deps.end())
+        for (int d : it->second)
+          if (int rc = ensure_field(m, d)) return rc;
+      if (id >= F_vwc_perc_0 && id <= F_vwc_perc_7)
+        if (int rc = ensure_field(m, F_vwc_0 + (id - F_vwc_perc_0))) return rc;
+    }
     if (id == F_SoilWatbal || id == F_watbal) {
       if (!m->dm.h_wb) CUDA_OK(cudaMalloc(&m->dm.h_wb, sizeof(double) * std::max<int64_t>(m->n, 1)));
       if (int rc = ensure_field(m, F_SoilWatbal)) return rc;
@@ -1406,6 +1485,8 @@ int wf_step_pipelined(wf_model *m, int nsteps, float *gauge_out, float mv, int a
   if (m->cfg.model_snow && !m->pipe_has[2]) return fail(WF_EINVAL, "pipelined forcing not set: TEMP");
   if (m->dm.task_mask != 7) return fail(WF_EUNSUPPORTED, "WF_LATERAL_TASKS is a development aid of the per-step sweep");
   if (gauge_out && m->pipe_gauges < 0) return fail(WF_EINVAL, "no gauge set registered (wf_pipeline_capture)");
+  if (end_outputs_requested(m))
+    return fail(WF_EUNSUPPORTED, "the end-of-dynamic() outputs (mass balances, cumulative sums ...) need the per-step path (wf_step)");
   CUDA_OK(cudaSetDevice(m->cfg.device));
   if (int rc = forcing_acquire(m)) return rc;
   m->timed = true;

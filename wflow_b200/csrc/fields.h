@@ -64,7 +64,21 @@ enum FieldKind : int { K_FORCING = 0, K_STATIC = 1, K_STATE = 2, K_DIAG = 3, K_R
   X(RootStore_unsat, K_DIAG)                                                                       \
   X(vwc_0, K_DIAG) X(vwc_1, K_DIAG) X(vwc_2, K_DIAG) X(vwc_3, K_DIAG)                              \
   X(vwc_4, K_DIAG) X(vwc_5, K_DIAG) X(vwc_6, K_DIAG) X(vwc_7, K_DIAG)                              \
-  X(Snow2Glacier, K_DIAG) X(GlacierMelt, K_DIAG)
+  X(Snow2Glacier, K_DIAG) X(GlacierMelt, K_DIAG)                                                   \
+  /* end of dynamic(), wflow_sbm.py:3310-3312, 3348-3370, 3429-3526 (outputs.cuh; the Cum* maps accumulate) */ \
+  X(KinWaveVolumeR, K_DIAG) X(KinWaveVolumeL, K_DIAG) X(OldKinWaveVolumeR, K_DIAG)                 \
+  X(OldKinWaveVolumeL, K_DIAG) X(MassBalKinWaveR, K_DIAG) X(MassBalKinWaveL, K_DIAG)               \
+  X(InflowKinWaveCell, K_DIAG) X(RiverRunoffMM, K_DIAG) X(LandRunoffMM, K_DIAG)                    \
+  X(QCatchmentMM, K_DIAG) X(RunoffCoeff, K_DIAG) X(CellStorage, K_DIAG) X(DeltaStorage, K_DIAG)    \
+  X(SatWaterFlux, K_DIAG) X(sumUstore, K_DIAG) X(SnowCover, K_DIAG) X(RootStore, K_DIAG)           \
+  X(RootStore_sat, K_DIAG) X(vwcRoot, K_DIAG) X(vwc_percRoot, K_DIAG)                              \
+  X(vwc_perc_0, K_DIAG) X(vwc_perc_1, K_DIAG) X(vwc_perc_2, K_DIAG) X(vwc_perc_3, K_DIAG)          \
+  X(vwc_perc_4, K_DIAG) X(vwc_perc_5, K_DIAG) X(vwc_perc_6, K_DIAG) X(vwc_perc_7, K_DIAG)          \
+  X(SumEvapSat, K_DIAG) X(SumEvapUstore, K_DIAG) X(ExfiltWaterCubic, K_DIAG)                       \
+  X(InfiltExcessCubic, K_DIAG) X(SurfaceWaterSupply, K_DIAG)                                       \
+  X(CumOutFlow, K_DIAG) X(CumActInfilt, K_DIAG) X(CumCellInFlow, K_DIAG) X(CumPrec, K_DIAG)        \
+  X(CumEvap, K_DIAG) X(CumPotenEvap, K_DIAG) X(CumInt, K_DIAG) X(CumLeakage, K_DIAG)               \
+  X(CumExfiltWater, K_DIAG) X(CumSurfaceWater, K_DIAG)
 
 enum FieldId : int {
 #define X(n, k) F_##n,

@@ -562,12 +562,15 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
 #pragma unroll
   for (int k = 0; k < ML; k++) {
     float *vw = m.f[F_vwc_0 + k];
-    if (vw) {  // :792-803
+    if (vw) {  // :792-807 (layer["vwc"] keeps its value where neither branch writes)
+      double vwc = vw[i];
       if (k < mc_new) {
-        if (thick[k] > 0) vw[i] = (float)(qdiv(U[k] + (thick[k] - L_new[k]) * dneff, thick[k]) + thetaR);
+        if (thick[k] > 0) vwc = qdiv(U[k] + (thick[k] - L_new[k]) * dneff, thick[k]) + thetaR;
       } else {
-        vw[i] = (float)thetaS;
+        vwc = thetaS;
       }
+      vw[i] = (float)vwc;
+      if (m.f[F_vwc_perc_0 + k]) m.f[F_vwc_perc_0 + k][i] = (float)(qdiv(vwc, thetaS) * 100.0);
     }
   }
   if (m.f[F_RootStore_unsat]) {  // :809-821

@@ -327,6 +327,7 @@ class WflowSbm:
         self._estimate_l = self.kinwaveIters == 1 and self.kinwaveLandTstep == 0
         self._estimate_r = self.kinwaveIters == 1 and self.kinwaveRiverTstep == 0
         self._it_fixed = (it_l, it_r)
+        self._requested = set()  # diagnostic outputs the library materialises for this run (outputmaps, csv / tss, summary ...)
         self._mod = SbmModel(ldd, river_b, schedule=sched, timestepsecs=self.timestepsecs,
                              layer_thickness=self.layer_thickness, model_snow=self.modelSnow,
                              soil_inf_redu=self.soilInfReduction, transfer_method=self.TransferMethod, ust=self.UST,
@@ -334,7 +335,6 @@ class WflowSbm:
         for k, v in self.static.items():
             if k not in ("River", "Beta"):
                 self._mod.set(k, np.where(np.isnan(v), F32(0.0), v))
-        self._mod.request("SatWaterDepth")
         self._update_parameters(0, initial=True)
         # initial() ends with wf_updateparameters(): the forcing of the first timestep is in place (and can be read
         # back through the API) before the first step
@@ -375,6 +375,22 @@ class WflowSbm:
                 continue
             self._mod.set(k, np.nan_to_num(np.where(v == F32(MV), np.nan, v), nan=0.0).astype(F32))
 
+    def _get(self, name):
+        """A model map by (library) field name.  SatWaterDepth is not a stored state here -- zi is the live saturated-zone
+        state -- so unless an output asked the library to materialise it, it is what the reference forms from zi at the
+        start of every step: (thetaS - thetaR) * (SoilThickness - zi), REAL4 (wflow_sbm.py:2751)."""
+        if name == "SatWaterDepth" and "SatWaterDepth" not in self._requested:
+            zi = self._mod.get("zi", MV)
+            ok = zi != F32(MV)
+            neff = (self.static["thetaS"] - self.static["thetaR"]).astype(F32)
+            sat = (neff * (self.static["SoilThickness"] - zi)).astype(F32)
+            return np.where(ok, sat, F32(MV)).astype(F32)
+        return self._mod.get(name, MV)
+
+    def _request(self, name):
+        self._requested.add(name)
+        self._mod.request(name)
+
     def wf_resume(self, directory):
         """Read the state maps (wf_DynamicFramework.py:2065-2129): list-valued states as Name_<k>.map."""
         state = {}
@@ -393,7 +409,7 @@ class WflowSbm:
         """Write one REAL4 map per state (wf_DynamicFramework.py:1780-1827)."""
         os.makedirs(directory, exist_ok=True)
         for name in self._state_names():
-            csf.write_map(os.path.join(directory, name + ".map"), self._mod.get(name, MV), self._info, mv=MV)
+            csf.write_map(os.path.join(directory, name + ".map"), self._get(name), self._info, mv=MV)
 
     def wf_savesummarymaps(self):
         """[summary]: end values; [summary_*]: the statistics gathered over the run (wf_DynamicFramework.py:1886-1951)."""
@@ -402,7 +418,7 @@ class WflowSbm:
             for var, fname in self.config.items("summary"):
                 name = var.replace("self.", "")
                 try:
-                    a = self._mod.get(self._ALIAS.get(name, name), MV)
+                    a = self._get(self._ALIAS.get(name, name))
                 except Exception:
                     self.logger.warning("Could not find or save the configured summary map:" + var)
                     continue
@@ -630,7 +646,7 @@ class WflowSbm:
             return np.array(getattr(self, name))
         field = self._ALIAS.get(name, name)
         try:
-            a = self._mod.get(field, MV)
+            a = self._get(field)
         except Exception:
             self.logger.error("%s is not defined in the model" % name)
             return None
@@ -677,7 +693,7 @@ class WflowSbm:
                     terms = [t.strip().replace("self.", "") for t in var.split("+")]
                     try:
                         for t in terms:
-                            self._mod.request(self._ALIAS.get(t, t))
+                            self._request(self._ALIAS.get(t, t))
                     except Exception as ex:
                         self.logger.warning("output %s skipped: %s" % (var, ex))
                         continue
@@ -694,7 +710,7 @@ class WflowSbm:
                     raise ValueError("Entry in ini invalid: " + var)
                 name = var.split("self.")[1]
                 try:
-                    self._mod.request(self._ALIAS.get(name, name))
+                    self._request(self._ALIAS.get(name, name))
                     self._mod.device_ptr(self._ALIAS.get(name, name))
                 except Exception as ex:
                     self.logger.warning("summary map %s skipped: %s" % (var, ex))
@@ -706,7 +722,7 @@ class WflowSbm:
             for var, prefix in self.config.items("outputmaps"):
                 name = var.replace("self.", "")
                 try:
-                    self._mod.request(self._ALIAS.get(name, name))
+                    self._request(self._ALIAS.get(name, name))
                     self._mod.device_ptr(self._ALIAS.get(name, name))
                 except Exception as ex:
                     self.logger.warning("output map %s skipped: %s" % (var, ex))
@@ -717,7 +733,7 @@ class WflowSbm:
         for o in self._outputs:
             vals = None
             if o["func"] == "majority":  # pcr.areamajority of the (summed) raster: host side, rarely used
-                a = sum(self._mod.get(self._ALIAS.get(t, t), MV).astype(F32) for t in o["terms"])
+                a = sum(self._get(self._ALIAS.get(t, t)).astype(F32) for t in o["terms"])
                 vals = area_majority(a, o["idmap"], o["ids"])
             else:
                 for t in o["terms"]:
@@ -738,7 +754,7 @@ class WflowSbm:
             label = str(self._climate_datetime(step)) if o["tformat"] == "datetime" else str(step - 1)
             fh.write(label + sep + sep.join(repr(x) for x in vals) + "\n")
         for st in self._stats:  # add_one, after every timestep (:3010-3012)
-            a = self._mod.get(self._ALIAS.get(st["name"], st["name"]), MV)
+            a = self._get(self._ALIAS.get(st["name"], st["name"]))
             a = np.where(a == F32(MV), F32(np.nan), a).astype(F32)
             if st["count"] == 0:
                 st["data"] = a
@@ -751,7 +767,7 @@ class WflowSbm:
             st["count"] += 1
         for name, prefix in self._outmaps:
             path = generate_name_t(os.path.join(self.SaveDir, "outmaps", prefix), step)
-            csf.write_map(path, self._mod.get(self._ALIAS.get(name, name), MV), self._info, mv=MV)
+            csf.write_map(path, self._get(self._ALIAS.get(name, name)), self._info, mv=MV)
 
     def _wf_shutdown(self):
         for fh in self._files.values():
