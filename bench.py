@@ -11,6 +11,9 @@ Workloads (--config)
      steps (modified-Rutter interception, it_kinR = 4), sharded by basin over 8 GPUs: each rank holds --basins basins
      (default 32 = the per-GPU share; --basins 256 = the whole grid on one GPU).  Weak scaling, no data-path collective.
   2  4096x4096 all-pit LDD (column only: one level, the lateral solves are cell-local), 4 layers, snow, daily steps, cold start.
+  4  the Rhine example (169x187 grid, 15 754 cells, 266 levels, daily, as shipped) x 256 parameter trials (wflow_fit shapes:
+     factors in [0.5, 2] on M, KsatVer, N, N_River, SoilThickness, seed 11) as ONE device model per GPU, trials sharded
+     256 / G; every trial's discharge at the 14 gauges leaves the device.  Strong scaling (the ensemble is fixed).
   5  32768x32768 / 8 GPUs = 128 basins of 1024x1024 per rank, 10 % of the cells missing, daily steps, one gauge per
      basin outlet + 3 interior river cells; the gauge values of every --gather-every (10) steps are all-gathered over NCCL
      from device memory INSIDE the end-to-end loop (the only collective of the path).
@@ -32,6 +35,15 @@ sys.path.insert(0, ROOT)
 BYTES_VERTICAL = 236   # the stand-alone column kernel
 BYTES_FULL = 333       # full step incl. lateral statics, routing states, upstream gathers and topology
 BYTES_LATERAL = BYTES_FULL - BYTES_VERTICAL
+
+
+def algorithmic_bytes(layers, snow):
+    """SURVEY.md 8d's general formula: (column, lateral part) bytes per cell-step for `layers` soil layers."""
+    forcing = 3 if snow else 2
+    static = 28 + 2 * layers - (0 if snow else 8)   # the snow module's 8 parameter maps
+    s_in = (7 if snow else 4) + layers               # CanopyStorage, zi, WaterLevelL, WaterLevelR (+ Snow, SnowWater, TSoil), U[L]
+    s_out = (5 if snow else 2) + layers
+    return 4 * (forcing + static + s_in + s_out), BYTES_LATERAL
 METRIC = "cell-timesteps/sec (SBM+kinwave)"
 
 
@@ -41,7 +53,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 5])
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 4, 5])
+    ap.add_argument("--members", type=int, default=256, help="config 4: trials of the whole ensemble (sharded over the GPUs)")
     ap.add_argument("--basins", type=int, default=0, help="1024^2 basins per GPU (config 3: 32, config 5: 128)")
     ap.add_argument("--tile", type=int, default=1024)
     ap.add_argument("--timestepsecs", type=int, default=0, help="0 = the configuration's own (3: 3600 s, 2 and 5: 86400 s)")
@@ -56,7 +69,7 @@ def parse():
     if a.timestepsecs == 0:
         a.timestepsecs = 3600 if a.config == 3 else 86400
     if a.basins == 0:
-        a.basins = {3: 32, 5: 128, 2: 16}[a.config]
+        a.basins = {3: 32, 5: 128, 2: 16, 4: 0}[a.config]
     if a.replicate < 0:
         a.replicate = 1 if a.basins > 64 else 0
     return a
@@ -207,8 +220,62 @@ class Shard:
                                   timestepsecs=args.timestepsecs, rain_mean=20.0 if args.config == 3 else 8.0)
         self.it = (it_l, it_r)
 
+    names = ("P", "PET", "TEMP")
+    tile_ncol = 0   # forcing rasters cover the whole grid
+    scaling = "weak"
+
     def forcing(self, f):
         return [np.ascontiguousarray(self.expand(a), dtype=np.float32) for a in self.forc.step(f)]
+
+    def close(self):
+        self.mod.close()
+
+
+RHINE_CASE = os.path.join(ROOT, "baseline", "_ref", "wflow_rhine_sbm")
+
+
+class EnsembleShard:
+    """config 4: this rank's share of the 256 trials of the Rhine example, one device model (wflow_b200.ensemble)."""
+
+    scaling = "strong"
+
+    def __init__(self, args, rank, world, local):
+        from wflow_b200 import ensemble, parallel
+        if not os.path.isdir(RHINE_CASE):
+            raise SystemExit("bench.py --config 4: %s not present (python tests/golden/make_ref_cases.py in the build container)" % RHINE_CASE)
+        t0 = time.time()
+        rng = np.random.default_rng(11)
+        f = rng.uniform(0.5, 2.0, (args.members, 5)).astype(np.float32)
+        factors = dict(M=f[:, 0], KsatVer=f[:, 1], N=f[:, 2], N_River=f[:, 3], SoilThickness=f[:, 4])
+        members = list(parallel.shard_members(args.members, rank, world))
+        self.ce = ensemble.CaseEnsemble(RHINE_CASE, factors, members=members, run_dir="bench_ens_rank%d" % rank, device=local)
+        self.mod = self.ce.model
+        self.args = args
+        self.nrow, self.ncol = self.mod.shape
+        self.tile_ncol = self.ce.shape[1]
+        self.ncell = self.mod.num_cells
+        self.it = self.ce.fw._it_fixed
+        self.gen_s = self.init_s = time.time() - t0
+        self.nsteps_case = 29
+        f0 = self.ce.forcing(1)
+        self.names = tuple(n for n, _ in f0)
+        self.members = len(members)
+
+    def forcing(self, f):
+        return [np.ascontiguousarray(a, dtype=np.float32) for _, a in self.ce.forcing(1 + f % self.nsteps_case)]
+
+    def gauges(self):
+        fw = self.ce.fw
+        g = np.flatnonzero(np.nan_to_num(fw._staticmap("staticmaps/wflow_gauges.map"), nan=0.0).ravel() > 0).astype(np.int64)
+        nrow, nc = self.ce.shape
+        r, c = g // nc, g % nc
+        allg = np.concatenate([r * (nc * self.members) + m * nc + c for m in range(self.members)])
+        return allg, "RiverRunoff"
+
+    def close(self):
+        import shutil
+        self.ce.close()
+        shutil.rmtree(os.path.join(RHINE_CASE, self.ce.fw.runId), ignore_errors=True)
 
     def gauges(self):
         """Flat indices of the cells whose discharge leaves the device every step."""
@@ -234,7 +301,7 @@ class Shard:
 
 
 def workload_config(args, it_l, it_r, **extra):
-    nrow, ncol = shard_shape(args.basins, args.tile) if args.config != 2 else (4096, 4096)
+    nrow, ncol = shard_shape(args.basins, args.tile) if args.config not in (2, 4) else (4096, 4096)
     if args.config == 3:
         w = ("BASELINE config 3: synthetic D8 grid of independent %dx%d basins, full SBM + subsurface/overland/river kinematic "
              "wave, %d s steps, 4 soil layers, snow on; %d basins (%dx%d cells) per GPU (8 GPUs x 32 = the 16384x16384 grid)"
@@ -242,6 +309,10 @@ def workload_config(args, it_l, it_r, **extra):
     elif args.config == 2:
         w = ("BASELINE config 2: synthetic %dx%d grid, all-pit LDD (SBM vertical column; the lateral solves are cell-local), "
              "4 soil layers (UStoreLayerThickness 100,300,800), snow on, %d s steps, cold start" % (nrow, ncol, args.timestepsecs))
+    elif args.config == 4:
+        w = ("BASELINE config 4: Rhine SBM example as shipped (169x187 grid, daily steps, Gash interception, 1 soil layer, snow off) "
+             "x %d parameter trials (factors in [0.5, 2] on M, KsatVer, N, N_River, SoilThickness; seed 11), trials sharded over "
+             "the GPUs, each GPU's trials one device model; RiverRunoff of every trial at the 14 gauges, every step" % args.members)
     else:
         w = ("BASELINE config 5: continental-scale synthetic multi-basin grid, %d basins of %dx%d (%dx%d cells) per GPU "
              "(8 GPUs x 128 = 32768x32768), 10 %% of the cells missing, reservoir / lake modules off, full SBM + routing, "
@@ -446,8 +517,9 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    sh = Shard(args, rank, local)
+    sh = EnsembleShard(args, rank, world, local) if args.config == 4 else Shard(args, rank, local)
     mod, nrow, ncol, ncell = sh.mod, sh.nrow, sh.ncol, sh.ncell
+    fnames, tile_ncol = sh.names, sh.tile_ncol
     it_l, it_r = sh.it
     gauges, gfield = sh.gauges()
     G = int(gauges.size)
@@ -459,8 +531,11 @@ def run_b200(args):
         trip = sh.forcing(f)
         host_ring.append([torch.from_numpy(a).pin_memory() for a in trip])
         devs = []
-        for name, a in zip(("P", "PET", "TEMP"), trip):
-            mod.set(name, a)
+        for name, a in zip(fnames, trip):
+            if tile_ncol:
+                mod.set_tiled(name, a)
+            else:
+                mod.set(name, a)
             ptr, n = mod.device_ptr(name)
             mod.synchronize()
             t = torch.as_tensor(_DevArray(ptr, n), device="cuda").clone()  # the model's storage-order array (plumbing only)
@@ -472,7 +547,7 @@ def run_b200(args):
     stream = torch.cuda.ExternalStream(mod.stream)
 
     def bind(f):
-        for name, t in zip(("P", "PET", "TEMP"), dev_ring[f % F]):
+        for name, t in zip(fnames, dev_ring[f % F]):
             mod.bind(name, t.data_ptr())
 
     def barrier():
@@ -503,7 +578,7 @@ def run_b200(args):
     ms = e0.elapsed_time(e1)
     launches = mod.launch_count - l0
     (ms_v, ms_l, ms_tot), nst = mod.timing_get()
-    for name in ("P", "PET", "TEMP"):
+    for name in fnames:
         mod.bind(name, None)
 
     # ---- e2e: host forcing in pinned memory -> set_field -> step -> gauge values, every step; gathered every T steps ----
@@ -526,8 +601,11 @@ def run_b200(args):
     collectives = 0
     e2.record(stream)
     for s in range(args.steps):
-        for name, t in zip(("P", "PET", "TEMP"), host_ring[s % F]):
-            mod.set_pinned(name, t.data_ptr())
+        for name, t in zip(fnames, host_ring[s % F]):
+            if tile_ncol:
+                mod.set_pinned_tiled(name, t.data_ptr(), tile_ncol)
+            else:
+                mod.set_pinned(name, t.data_ptr())
         mod.step()
         mod.gauges_sample_device(gh, gfield, gbuf[s % T].data_ptr())
         if (s + 1) % T == 0 or s == args.steps - 1:
@@ -545,7 +623,7 @@ def run_b200(args):
     ms_e2e = e2.elapsed_time(e3)
     if not np.all(np.isfinite(ghost.numpy())):
         raise SystemExit("bench.py: non-finite gauge value in the e2e run")
-    h2d = 3 * nrow * ncol * 4
+    h2d = len(fnames) * nrow * (tile_ncol or ncol) * 4
     d2h = world * G * 4  # every rank receives all ranks' gauge values (averaged over the gather interval: per step)
 
     # max over ranks
@@ -564,9 +642,11 @@ def run_b200(args):
         e2e_v = total_cells * args.steps / (ms_e2e / 1e3)
         nst = max(nst, 1)
         kern = []
-        for name, key, msk, bpc in (("k_vertical<4> (SBM vertical column)", "k_vertical", ms_v / nst, BYTES_VERTICAL),
-                                    ("k_lateral_wave<4> (subsurface / overland / river kinematic waves, level wavefront)",
-                                     "k_lateral_wave", ms_l / nst, BYTES_LATERAL)):
+        layers = mod.max_layers
+        b_col, b_lat = algorithmic_bytes(layers, "TEMP" in fnames)
+        for name, key, msk, bpc in (("k_vertical<%d> (SBM vertical column)" % layers, "k_vertical", ms_v / nst, b_col),
+                                    ("k_lateral_wave<%d> (subsurface / overland / river kinematic waves, level wavefront)" % layers,
+                                     "k_lateral_wave", ms_l / nst, b_lat)):
             ach = ncell * bpc / (msk / 1e3) / 1e9 if msk > 0 else 0.0
             tr = traffic.get(key, {})
             kern.append({"kernel": name, "ms_per_launch": msk, "share_of_step": msk / max((ms_v + ms_l) / nst, 1e-9),
@@ -576,7 +656,7 @@ def run_b200(args):
         dom = max(kern, key=lambda k: k["ms_per_launch"])
         line = {
             "metric": METRIC, "value": value, "unit": "cell-timesteps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": sh.scaling,
             "vs_baseline": None, "dtype": "f64 (column, kinematic waves) + f32 (map-algebra phases, storage)",
             "data": "synthetic",
             "config": workload_config(args, it_l, it_r, cells_per_gpu=ncell, levels=mod.num_levels,
@@ -593,12 +673,13 @@ def run_b200(args):
                          "peak_source": peak_src, "unit": "GB/s", "frac": dom["frac"], "bytes_per_cell": dom["bytes_per_cell"],
                          "cells_per_launch": ncell, "ms_per_launch": dom["ms_per_launch"], "traffic": dom["traffic"],
                          "traffic_source": dom["traffic_source"],
-                         "bound_note": "the dominant kernel is the level wavefront: bound by per-level latency and instruction "
-                                       "issue, not by HBM; the HBM fraction is reported as the contract asks",
+                         "bound_note": "neither kernel is HBM-bound: the column is bound by instruction issue and exposed load latency "
+                                       "(ncu: issue slots ~64 % busy), the level wavefront by per-level latency; the HBM fraction is "
+                                       "reported as the contract asks",
                          "kernels": kern,
-                         "full_step": {"bytes_per_cell": BYTES_FULL,
-                                       "achieved": ncell * BYTES_FULL / ((ms_v + ms_l) / nst / 1e3) / 1e9,
-                                       "frac": ncell * BYTES_FULL / ((ms_v + ms_l) / nst / 1e3) / 1e9 / peak}},
+                         "full_step": {"bytes_per_cell": b_col + b_lat,
+                                       "achieved": ncell * (b_col + b_lat) / ((ms_v + ms_l) / nst / 1e3) / 1e9,
+                                       "frac": ncell * (b_col + b_lat) / ((ms_v + ms_l) / nst / 1e3) / 1e9 / peak}},
             "kernels_ms_per_step": {"vertical": ms_v / nst, "lateral": ms_l / nst,
                                     "lateral_us_per_level": ms_l / nst * 1e3 / max(mod.num_levels, 1)},
             "lateral_plan": mod.lateral_plan,
@@ -627,7 +708,7 @@ def run_b200(args):
     except Exception:
         pass
     torch.cuda.empty_cache()
-    mod.close()
+    sh.close()
     if world > 1:
         dist.destroy_process_group()
     sys.stdout.flush()

@@ -115,6 +115,10 @@ int wf_catchment_total(const wf_model *m, const float *values, double *out_grid)
  * (wflow/wf_DynamicFramework.py:2582, 2203) at the raster level. */
 int wf_set_field(wf_model *m, const char *name, const float *grid);        /* host raster -> device */
 int wf_set_field_uniform(wf_model *m, const char *name, float value);
+/* A raster of nrow x tile_ncol cells that repeats across the columns of the model grid (ncol a multiple of tile_ncol):
+ * parameter ensembles hold their members side by side in one grid (wflow/wflow_fit.py:235-257 reruns the model per
+ * trial), and everything the members share -- forcing, the parameters a trial does not touch -- crosses PCIe once. */
+int wf_set_field_tiled(wf_model *m, const char *name, const float *grid, int tile_ncol);
 int wf_get_field(wf_model *m, const char *name, float *grid, float mv);    /* device -> host raster */
 /* Optional statics switch parts of the step on by being set: GlacierFrac / G_TT / G_Cfmax / G_SIfrac (with
  * cfg.glacier; glacierHBV, wflow/wflow_funcs.py:549-603) and LAI / Sl / Swood / Kext (LAI-driven Cmax,

@@ -75,3 +75,57 @@ def test_members_match_stand_alone_runs(kind):
             differ += int(not np.array_equal(got["zi"][m], got["zi"][0]))
         one.close()
     assert differ == M - 1  # the trials really are different runs
+
+
+RHINE = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))),
+                                   "baseline", "_ref", "wflow_rhine_sbm")
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir(RHINE), reason="Rhine example data not present (tests/golden/make_ref_cases.py)")
+def test_rhine_ensemble_of_256_trials_matches_stand_alone_runs(tmp_path):
+    """BASELINE config 4: the Rhine example x 256 parameter trials (wflow_fit shapes: factors on M, KsatVer, N, N_River,
+    SoilThickness) as ONE device model on the real Rhine maps; trials picked from the ensemble are bit-identical to
+    stand-alone runs of the model with their parameters."""
+    import shutil
+    from wflow_b200 import core, ensemble
+    M, nsteps = 256, 5
+    rng = np.random.default_rng(11)
+    f = rng.uniform(0.5, 2.0, (M, 5)).astype(np.float32)
+    f[0] = 1.0
+    factors = dict(M=f[:, 0], KsatVer=f[:, 1], N=f[:, 2], N_River=f[:, 3], SoilThickness=f[:, 4])
+    run = "ens_%s" % tmp_path.name
+    ce = ensemble.CaseEnsemble(RHINE, factors, run_dir=run)
+    try:
+        fw = ce.fw
+        assert ce.members == M and ce.model.num_cells == M * fw._mod.num_cells
+        assert set(ce.varied) >= {"KsatVer", "f", "AlphaL", "SoilThickness"} and "thetaS" not in ce.varied
+        gauges = np.flatnonzero(np.nan_to_num(fw._staticmap("staticmaps/wflow_gauges.map"), nan=0.0).ravel() > 0)
+        ce.gauges(gauges)
+        names = common.state_names(fw.maxLayers, snow=bool(fw.modelSnow))
+        start = {k: ce.ens.get(k) for k in names}
+        forc = [ce.forcing(t + 1) for t in range(nsteps)]
+        series = ce.run(nsteps)
+        assert series.shape == (nsteps, M, gauges.size) and np.isfinite(series).all() and series.max() > 0
+        got = {k: ce.ens.get(k) for k in names}
+        it_l, it_r = fw._it_fixed
+        for m in (0, 100, 255):
+            one = core.SbmModel(fw.ldd, fw.River.astype(np.uint8), timestepsecs=fw.timestepsecs, layer_thickness=fw.layer_thickness,
+                                model_snow=fw.modelSnow, soil_inf_redu=fw.soilInfReduction, transfer_method=fw.TransferMethod,
+                                ust=fw.UST, it_kin_l=it_l, it_kin_r=it_r)
+            for k, v in ce.statics[m].items():
+                if k not in ("River", "Beta"):
+                    one.set(k, np.nan_to_num(np.broadcast_to(np.asarray(v, np.float32), fw.shape), nan=0.0))
+            for k in names:
+                one.set(k, np.where(start[k][m] == np.float32(-999.0), np.float32(0.0), start[k][m]))
+            for t in range(nsteps):
+                for name, a in forc[t]:
+                    one.set(name, a)
+                one.step()
+                np.testing.assert_array_equal(series[t][m], one.sample("RiverRunoff", gauges))
+            for k in names:
+                np.testing.assert_array_equal(got[k][m], one.get(k), err_msg="trial %d: %s" % (m, k))
+            one.close()
+        assert not np.array_equal(series[:, 100], series[:, 255])
+    finally:
+        ce.close()
+        shutil.rmtree(__import__("os").path.join(RHINE, run), ignore_errors=True)

@@ -186,6 +186,15 @@ class SbmModel:
         # the copy is asynchronous on the model's stream: keep the host buffer alive until it is consumed
         _lib.check(self._l.wf_synchronize(self._h))
 
+    def set_tiled(self, name, value, wait=True):
+        """A raster of tile_ncol = value.shape[1] columns that repeats across the model grid's columns (ensemble members)."""
+        a = np.ascontiguousarray(value, dtype=np.float32)
+        if a.ndim != 2 or a.shape[0] != self.shape[0] or self.shape[1] % a.shape[1]:
+            raise ValueError("raster %s of shape %s does not tile the model grid %s" % (name, a.shape, self.shape))
+        _lib.check(self._l.wf_set_field_tiled(self._h, name.encode(), a.ctypes.data, int(a.shape[1])))
+        if wait:
+            _lib.check(self._l.wf_synchronize(self._h))
+
     def set_many(self, fields):
         for k, v in fields.items():
             self.set(k, v)
@@ -193,6 +202,10 @@ class SbmModel:
     def set_pinned(self, name, host_ptr):
         """Asynchronous upload from a caller-owned (ideally pinned) nrow*ncol float32 buffer."""
         _lib.check(self._l.wf_set_field(self._h, name.encode(), host_ptr))
+
+    def set_pinned_tiled(self, name, host_ptr, tile_ncol):
+        """Asynchronous upload of a caller-owned (pinned) nrow*tile_ncol raster that repeats across the grid's columns."""
+        _lib.check(self._l.wf_set_field_tiled(self._h, name.encode(), host_ptr, int(tile_ncol)))
 
     def get(self, name, mv=-999.0):
         out = np.empty(self.shape, np.float32)

@@ -1130,7 +1130,7 @@ static int stage(wf_model *m) {
   return WF_OK;
 }
 
-static int gather_into(wf_model *m, int id, const float *dgrid) {
+static int gather_into(wf_model *m, int id, const float *dgrid, int tile_ncol = 0) {
   if (int rc = ensure_field(m, id)) return rc;
   if ((g_fields[id].kind & 0xff) == K_STATIC) m->derived_dirty = true;
   if (id == F_zi) m->satwd_valid = false;  // SatWaterDepth follows the water table that was set ...
@@ -1138,7 +1138,11 @@ static int gather_into(wf_model *m, int id, const float *dgrid) {
   const bool riv = g_fields[id].kind & K_RIVER;
   const int64_t len = riv ? m->nr : m->n;
   if (len > 0) {
-    k_gather<<<(unsigned)((len + 255) / 256), 256, 0, m->stream>>>(dgrid, riv ? m->d_rorder : m->d_order, m->dm.f[id], len);
+    if (tile_ncol > 0)
+      k_gather_tiled<<<(unsigned)((len + 255) / 256), 256, 0, m->stream>>>(dgrid, riv ? m->d_rorder : m->d_order, m->dm.f[id], len,
+                                                                           m->cfg.ncol, tile_ncol);
+    else
+      k_gather<<<(unsigned)((len + 255) / 256), 256, 0, m->stream>>>(dgrid, riv ? m->d_rorder : m->d_order, m->dm.f[id], len);
     m->launches++;
   }
   CUDA_OK(cudaGetLastError());
@@ -1149,13 +1153,13 @@ static int gather_into(wf_model *m, int id, const float *dgrid) {
 // gather that last read the slot), the model's stream waits for the copy -- so the upload of the next
 // step's forcing overlaps the running step's kernels as long as the host enqueues ahead.  The caller
 // enqueues its gather from d_ring[*slot] on the model's stream and then calls ring_release.
-static int ring_upload(wf_model *m, const float *grid, int *slot) {
-  const size_t bytes = sizeof(float) * (size_t)m->cfg.nrow * m->cfg.ncol;
+static int ring_upload(wf_model *m, const float *grid, int *slot, int tile_ncol = 0) {
+  const size_t bytes = sizeof(float) * (size_t)m->cfg.nrow * (tile_ncol > 0 ? tile_ncol : m->cfg.ncol);
   const int b = m->ring_next;
   m->ring_next = (b + 1) % wf_model::kStageRing;
   if (!m->copy_stream) CUDA_OK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
   if (!m->d_ring[b]) {
-    CUDA_OK(cudaMalloc(&m->d_ring[b], bytes));
+    CUDA_OK(cudaMalloc(&m->d_ring[b], sizeof(float) * (size_t)m->cfg.nrow * m->cfg.ncol));
     CUDA_OK(cudaEventCreateWithFlags(&m->ring_copied[b], cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&m->ring_free[b], cudaEventDisableTiming));
   } else {
@@ -1196,7 +1200,7 @@ static int forcing_release(wf_model *m) {
   return WF_OK;
 }
 // wf_set_field of a forcing raster: host -> staging ring -> next storage-order slot, all on the copy stream.
-static int set_forcing_async(wf_model *m, int id, const float *grid) {
+static int set_forcing_async(wf_model *m, int id, const float *grid, int tile_ncol = 0) {
   const bool riv = g_fields[id].kind & K_RIVER;
   const int64_t len = riv ? m->nr : m->n;
   const bool fresh = m->forc.find(id) == m->forc.end();
@@ -1216,12 +1220,13 @@ static int set_forcing_async(wf_model *m, int id, const float *grid) {
     CUDA_OK(cudaEventCreateWithFlags(&r.ready[k], cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&r.freed[k], cudaEventDisableTiming));
   }
-  const size_t bytes = sizeof(float) * (size_t)m->cfg.nrow * m->cfg.ncol;
+  const size_t full = sizeof(float) * (size_t)m->cfg.nrow * m->cfg.ncol;
+  const size_t bytes = tile_ncol > 0 ? sizeof(float) * (size_t)m->cfg.nrow * tile_ncol : full;
   const int b = m->ring_next;
   m->ring_next = (b + 1) % wf_model::kStageRing;
   if (!m->copy_stream) CUDA_OK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
   if (!m->d_ring[b]) {
-    CUDA_OK(cudaMalloc(&m->d_ring[b], bytes));
+    CUDA_OK(cudaMalloc(&m->d_ring[b], full));
     CUDA_OK(cudaEventCreateWithFlags(&m->ring_copied[b], cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&m->ring_free[b], cudaEventDisableTiming));
   } else {
@@ -1231,7 +1236,11 @@ static int set_forcing_async(wf_model *m, int id, const float *grid) {
   r.used[k] = false;
   CUDA_OK(cudaMemcpyAsync(m->d_ring[b], grid, bytes, cudaMemcpyHostToDevice, m->copy_stream));
   if (len > 0) {
-    k_gather<<<(unsigned)((len + 255) / 256), 256, 0, m->copy_stream>>>(m->d_ring[b], riv ? m->d_rorder : m->d_order, r.slot[k], len);
+    if (tile_ncol > 0)
+      k_gather_tiled<<<(unsigned)((len + 255) / 256), 256, 0, m->copy_stream>>>(m->d_ring[b], riv ? m->d_rorder : m->d_order, r.slot[k], len,
+                                                                                m->cfg.ncol, tile_ncol);
+    else
+      k_gather<<<(unsigned)((len + 255) / 256), 256, 0, m->copy_stream>>>(m->d_ring[b], riv ? m->d_rorder : m->d_order, r.slot[k], len);
     m->launches++;
   }
   CUDA_OK(cudaEventRecord(m->ring_free[b], m->copy_stream));
@@ -1252,6 +1261,20 @@ int wf_set_field(wf_model *m, const char *name, const float *grid) {
   int b = 0;
   if (int rc = ring_upload(m, grid, &b)) return rc;
   const int rc = gather_into(m, id, m->d_ring[b]);
+  if (int rc2 = ring_release(m, b)) return rc2;
+  return rc;
+}
+
+int wf_set_field_tiled(wf_model *m, const char *name, const float *grid, int tile_ncol) {
+  if (!m || !grid) return fail(WF_EINVAL, "null argument");
+  if (tile_ncol < 1 || m->cfg.ncol % tile_ncol) return fail(WF_EINVAL, "the grid's columns must be a whole number of tiles");
+  const int id = field_index(name);
+  if (id < 0) return fail(WF_EINVAL, std::string("unknown field: ") + (name ? name : "(null)"));
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  if ((g_fields[id].kind & 0xff) == K_FORCING && !m->external[id]) return set_forcing_async(m, id, grid, tile_ncol);
+  int b = 0;
+  if (int rc = ring_upload(m, grid, &b, tile_ncol)) return rc;
+  const int rc = gather_into(m, id, m->d_ring[b], tile_ncol);
   if (int rc2 = ring_release(m, b)) return rc2;
   return rc;
 }

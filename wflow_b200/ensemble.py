@@ -62,7 +62,7 @@ class SbmEnsemble:
         if a.ndim == 0 or a.size == 1:
             self.model.set(name, a)
         else:
-            self.model.set(name, np.tile(a, (1, self.members)))
+            self.model.set_tiled(name, a)  # one member's raster crosses PCIe; the device repeats it
 
     def set_members(self, name, per_member):
         self.model.set(name, self._mosaic(per_member))
@@ -99,3 +99,100 @@ class SbmEnsemble:
 
     def close(self):
         self.model.close()
+
+
+class CaseEnsemble:
+    """M parameter trials of a wflow_sbm CASE (ini, staticmaps, intbl, forcing stacks) advanced together on one GPU.
+
+    The reference calibrates by rerunning the whole model once per trial (wflow/wflow_fit.py:153-158 multiplies
+    the maps named in ``[fit] parameter_i`` by the trial's factors, :235-257 and :315-347 run it and collect the
+    discharge columns).  Here the trials are the members of one SbmEnsemble: ``factors[name][m]`` multiplies the base map
+    ``name`` (a table parameter of initial(): M, KsatVer, N, N_River, SoilThickness ...) of member m before the
+    derivations of initial(); forcing and every map the trials share cross PCIe once per step (wf_set_field_tiled).
+    ``members`` selects the trials this process holds (parallel.shard_members); results are member-major.
+    """
+
+    def __init__(self, case_dir, factors, members=None, inifile="wflow_sbm.ini", run_dir="ensemble", device=0):
+        from . import params
+        from .framework import WflowSbm
+        F32 = np.float32
+        fw = WflowSbm(Dir=case_dir, RunDir=run_dir, configfile=inifile, device=device)
+        fw.createRunId(NoOverWrite=False)
+        fw._runInitial()
+        fw._runResume()
+        self.fw = fw
+        names = sorted(factors)
+        nall = len(np.asarray(factors[names[0]]).reshape(-1)) if names else 1
+        self.member_ids = list(range(nall)) if members is None else list(members)
+        M = len(self.member_ids)
+        ldd, river = fw.ldd, fw.River.astype(np.uint8)
+        self.shape = ldd.shape
+        it_l, it_r = fw._it_fixed
+        self.ens = SbmEnsemble(ldd, river, M, timestepsecs=fw.timestepsecs, layer_thickness=fw.layer_thickness,
+                               model_snow=fw.modelSnow, soil_inf_redu=fw.soilInfReduction, transfer_method=fw.TransferMethod,
+                               ust=fw.UST, it_kin_l=it_l, it_kin_r=it_r, device=device)
+        # statics: derive per trial, upload what the trials share once
+        stat = []
+        for m in self.member_ids:
+            b = dict(fw._base)
+            for n in names:
+                b[n] = (np.asarray(b[n], F32) * F32(np.asarray(factors[n]).reshape(-1)[m])).astype(F32)
+            stat.append(params.derive_static(b, ldd, river != 0, fw.timestepsecs, cellsize=fw._cellsize, n_layers=fw.maxLayers))
+        self.statics = stat
+        self.varied = []
+        for k in stat[0]:
+            if k in ("River", "Beta"):
+                continue
+            a0 = np.broadcast_to(np.asarray(stat[0][k], F32), self.shape)
+            if all(np.array_equal(a0, np.broadcast_to(np.asarray(s[k], F32), self.shape), equal_nan=True) for s in stat[1:]):
+                self.ens.set(k, np.where(np.isnan(a0), F32(0.0), a0))
+            else:
+                self.varied.append(k)
+                self.ens.set_members(k, np.stack([np.nan_to_num(np.broadcast_to(np.asarray(s[k], F32), self.shape), nan=0.0) for s in stat]))
+        # states: the case's (instate/ or cold); the water table follows each trial's soil depth (resume(), :2503-2505)
+        for k in fw._state_names():
+            if k == "SatWaterDepth":
+                continue
+            self.ens.set(k, np.nan_to_num(np.where(fw._mod.get(k, -999.0) == F32(-999.0), np.nan, fw._mod.get(k, -999.0)), nan=0.0))
+        sat = fw._get("SatWaterDepth")
+        sat = np.where(sat == F32(-999.0), F32(0.0), sat)
+        zi = [np.maximum(F32(0.0), s["SoilThickness"] - sat / (s["thetaS"] - s["thetaR"]).astype(F32)).astype(F32) for s in stat]
+        self.ens.set_members("zi", np.stack([np.nan_to_num(z, nan=0.0) for z in zi]))
+        self.gauge_cells = None
+
+    @property
+    def members(self):
+        return len(self.member_ids)
+
+    @property
+    def model(self):
+        return self.ens.model
+
+    def forcing(self, step):
+        """(P, PET[, TEMP]) rasters of timestep `step` (1-based) of the case, as the framework reads them."""
+        fw = self.fw
+        out = [("P", fw._forcing("P", "Precipitation", "/inmaps/P", step, 0.0)),
+               ("PET", fw._forcing("PET", "EvapoTranspiration", "/inmaps/PET", step, 0.0))]
+        if fw.modelSnow:
+            out.append(("TEMP", fw._forcing("TEMP", "Temperature", "/inmaps/TEMP", step, 10.0)))
+        return [(n, np.nan_to_num(np.asarray(a, np.float32), nan=0.0)) for n, a in out]
+
+    def gauges(self, flat_index):
+        self.gauge_cells = np.asarray(flat_index, np.int64)
+        self._gh = self.ens.gauges_create(self.gauge_cells)
+        return self._gh
+
+    def run(self, nsteps, first_step=1, field="RiverRunoff"):
+        """Advance all trials `nsteps` timesteps; returns the gauge series [nsteps, members, gauges] (wflow_fit's Q columns)."""
+        out = []
+        for s in range(nsteps):
+            for name, a in self.forcing(first_step + s):
+                self.ens.set(name, a)
+            self.ens.step()
+            if self.gauge_cells is not None:
+                out.append(self.ens.gauges_sample(self._gh, field))
+        return np.stack(out) if out else None
+
+    def close(self):
+        self.ens.close()
+        self.fw._mod.close()

@@ -317,6 +317,7 @@ class WflowSbm:
         self.static = params.derive_static(base, ldd, river_b, self.timestepsecs, cellsize=info.cellsize,
                                            n_layers=self.maxLayers)
         self.River = river_b
+        self._base, self._cellsize = base, info.cellsize  # kept for parameter ensembles (ensemble.CaseEnsemble)
         it_l = it_r = 1
         if self.kinwaveIters == 1:  # wflow_sbm.py:2911-2923, 3159-3171 (fixed sub-steps only)
             if self.kinwaveLandTstep > 0:
