@@ -231,6 +231,29 @@ class Shard:
         self.mod.close()
 
 
+    def gauges(self):
+        """Flat indices of the cells whose discharge leaves the device every step."""
+        a = self.args
+        ldd = self.ldd
+        if a.config == 2:  # no river: a fixed sample of cells (their water table is the step's read-back)
+            return np.linspace(0, ldd.size - 1, 64).astype(np.int64), "zi"
+        pits = np.flatnonzero(ldd.ravel() == 5).astype(np.int64)
+        if a.config != 5:
+            return pits, "RiverRunoff"
+        # config 5: the outlet of every basin + 3 interior river cells of it (here: the first river cells of the tile rows
+        # a quarter, a half and three quarters up from the outlet)
+        riv = self.river
+        extra = []
+        for p in pits:
+            r, c = divmod(int(p), self.ncol)
+            r0, c0 = (r // a.tile) * a.tile, (c // a.tile) * a.tile
+            for frac in (0.25, 0.5, 0.75):
+                rr = r0 + int(a.tile * frac)
+                cols = np.flatnonzero(riv[rr, c0:c0 + a.tile])
+                extra.append(rr * self.ncol + c0 + (int(cols[len(cols) // 2]) if cols.size else a.tile // 2))
+        return np.concatenate([pits, np.array(extra, np.int64)]), "RiverRunoff"
+
+
 RHINE_CASE = os.path.join(ROOT, "baseline", "_ref", "wflow_rhine_sbm")
 
 
@@ -276,28 +299,6 @@ class EnsembleShard:
         import shutil
         self.ce.close()
         shutil.rmtree(os.path.join(RHINE_CASE, self.ce.fw.runId), ignore_errors=True)
-
-    def gauges(self):
-        """Flat indices of the cells whose discharge leaves the device every step."""
-        a = self.args
-        ldd = self.ldd
-        if a.config == 2:  # no river: a fixed sample of cells (their water table is the step's read-back)
-            return np.linspace(0, ldd.size - 1, 64).astype(np.int64), "zi"
-        pits = np.flatnonzero(ldd.ravel() == 5).astype(np.int64)
-        if a.config != 5:
-            return pits, "RiverRunoff"
-        # config 5: the outlet of every basin + 3 interior river cells of it (here: the first river cells of the tile rows
-        # a quarter, a half and three quarters up from the outlet)
-        riv = self.river
-        extra = []
-        for p in pits:
-            r, c = divmod(int(p), self.ncol)
-            r0, c0 = (r // a.tile) * a.tile, (c // a.tile) * a.tile
-            for frac in (0.25, 0.5, 0.75):
-                rr = r0 + int(a.tile * frac)
-                cols = np.flatnonzero(riv[rr, c0:c0 + a.tile])
-                extra.append(rr * self.ncol + c0 + (int(cols[len(cols) // 2]) if cols.size else a.tile // 2))
-        return np.concatenate([pits, np.array(extra, np.int64)]), "RiverRunoff"
 
 
 def workload_config(args, it_l, it_r, **extra):

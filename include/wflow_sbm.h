@@ -215,6 +215,23 @@ int wf_gauges_sample(wf_model *m, int gauges, const char *field, float *out /* [
  * bounce).  Enqueued on the model's stream (wf_stream); returns at once. */
 int wf_gauges_sample_device(wf_model *m, int gauges, const char *field, float *dout /* device, [n] */, float mv);
 
+/* --- reservoirs and lakes --------------------------------------------------------------
+ * simplereservoir (wflow/wflow_funcs.py:864-949) and naturalLake (:669-861), called by WflowModel.dynamic() before the
+ * soil column (wflow/wflow_sbm.py:2822-2883) on the states of the step before; their outflow enters the river cell below
+ * the object.  locs / linked / areas: nrow*ncol id rasters (<= 0: none) -- ReserVoirSimpleLocs / ReservoirSimpleAreas,
+ * LakeLocs / LinkedLakeLocs / LakeAreasMap; ldd_org: the LDD BEFORE initial() turned the objects into pits (:1899-1907).
+ * The parameter rasters (ResSimpleArea, ResMaxVolume, ResTargetFullFrac, ResMaxRelease, ResDemand, ResTargetMinFrac;
+ * LakeArea, LakeThreshold, LakeStorFunc, LakeOutflowFunc, Lake_b, Lake_e), the states ReservoirVolume / LakeWaterLevel and
+ * filter_P_PET (:1804-1843) are ordinary fields (wf_set_field).  Lake tables: n_sh storage curves (rows of H, S; Lake_SH_<id>.tbl)
+ * and n_hq rating curves (rows of H, Q(day 1) .. Q(day 366); Lake_HQ_<id>.tbl), concatenated, keyed by lake id.
+ * Return the number of objects found, or a negative status. */
+int wf_reservoirs_create(wf_model *m, const int32_t *locs, const int32_t *areas, const uint8_t *ldd_org);
+int wf_lakes_create(wf_model *m, const int32_t *locs, const int32_t *linked, const int32_t *areas, const uint8_t *ldd_org,
+                    int n_sh, const int32_t *sh_ids, const int32_t *sh_rows, const float *sh_data,
+                    int n_hq, const int32_t *hq_ids, const int32_t *hq_rows, const float *hq_data);
+/* Day of the year (1..366) of the coming steps: column of the lakes' rating tables (wf_supplyJulianDOY). */
+int wf_set_day_of_year(wf_model *m, int jdoy);
+
 /* --- kinematic-wave sub-steps --------------------------------------------------------------------
  * estimate_iterations_kin_wave(Q, Beta, alpha, timestepsecs, dx, mv) (wflow/wflow_funcs.py:103-116):
  * it_kin = ceil(1.25 * 95th percentile of the Courant number over the cells with Q > 0), 1 when no cell

@@ -48,10 +48,17 @@ CASES = {
     "masked_tiles_daily": dict(n=24, kind="tiles", tile=12, layer_thickness=(100, 300, 800), steps=4, mask_frac=0.1),
     # a positive lateral inflow at some river cells
     "inflow_daily": dict(n=24, kind="tiles", tile=12, layer_thickness=(100, 300, 800), steps=4, inflow=1),
+    # simple reservoirs on the river (simplereservoir, wflow_funcs.py:864-949): LDD cut at the dams, P / PET filtered over
+    # the reservoir areas, outflow into the cell below
+    "reservoirs_daily": dict(n=24, kind="tiles", tile=12, layer_thickness=(100, 300, 800), steps=6, reservoirs=1),
+    "reservoirs_6h": dict(n=24, kind="tiles", tile=12, layer_thickness=(100, 300), dt=21600, steps=5, reservoirs=1),
+    # natural lakes (naturalLake, :669-861): modified Puls, rating curve b (H - H0)^e with S = A H, S-H and H-Q tables, a linked pair
+    "lakes_daily": dict(n=24, kind="tiles", tile=12, layer_thickness=(100, 300, 800), steps=6, lakes=1),
 }
 
 STATES = ["CanopyStorage", "Snow", "SnowWater", "TSoil", "zi", "SubsurfaceFlow", "LandRunoff", "LandRunoffsub", "WaterLevelL",
-          "WaterLevelLsub", "RiverRunoff", "RiverRunoffsub", "WaterLevelR", "WaterLevelRsub", "GlacierStore"]
+          "WaterLevelLsub", "RiverRunoff", "RiverRunoffsub", "WaterLevelR", "WaterLevelRsub", "GlacierStore", "ReservoirVolume",
+          "LakeWaterLevel"]
 OUTPUTS = [
     # map-algebra phases
     "Precipitation", "PotenEvap", "Temperature", "ThroughFall", "StemFlow", "Interception", "PotTransSoil", "SnowMelt",
@@ -70,6 +77,9 @@ OUTPUTS = [
     "SatWaterFlux", "sumUstore", "SnowCover", "RootStore", "RootStore_sat", "vwcRoot", "vwc_percRoot", "SurfaceWaterSupply",
     "ExfiltWaterCubic", "InfiltExcessCubic", "SumEvapSat", "SumEvapUstore", "CumOutFlow", "CumActInfilt", "CumCellInFlow",
     "CumPrec", "CumEvap", "CumPotenEvap", "CumInt", "CumLeakage", "CumExfiltWater", "CumSurfaceWater",
+    # reservoirs / lakes
+    "OutflowSR", "ResPercFull", "ResPrecipSR", "ResEvapSR", "DemandRelease", "LakeOutflow", "LakeVolume", "LakePrecip",
+    "LakeEvap", "Inflow",
 ]
 
 
@@ -103,21 +113,107 @@ def build_inputs(n, kind, layer_thickness, dt=86400, seed=3, tile=12, mask_frac=
     return ldd, river, static, state
 
 
+def _river_spots(ldd, river, count, seed, avoid=()):
+    """`count` river cells that are not pits, spread over the basins, with the area (3x3 neighbourhood) around each."""
+    rng = np.random.default_rng(seed)
+    cand = np.argwhere((river != 0) & (ldd != 5) & (ldd > 0))
+    rng.shuffle(cand)
+    spots, taken = [], np.zeros(ldd.shape, bool)
+    for r, c in avoid:
+        taken[max(r - 2, 0):r + 3, max(c - 2, 0):c + 3] = True
+    for r, c in cand:
+        if len(spots) == count:
+            break
+        if taken[max(r - 2, 0):r + 3, max(c - 2, 0):c + 3].any():
+            continue
+        spots.append((int(r), int(c)))
+        taken[max(r - 2, 0):r + 3, max(c - 2, 0):c + 3] = True
+    return spots
+
+
+def object_inputs(kw, ldd, river, static):
+    """Reservoir / lake maps of a case: (cut ldd, reservoirs dict or None, lakes dict or None)."""
+    n = ldd.shape[0]
+    active = ldd > 0
+    rng = np.random.default_rng(77)
+    cut = ldd.copy()
+    res = lak = None
+    spots = []
+    if kw.get("reservoirs"):
+        spots = _river_spots(ldd, river, 4, 5)
+        locs, areas = np.zeros((n, n), np.int32), np.zeros((n, n), np.int32)
+        for k, (r, c) in enumerate(spots):
+            locs[r, c] = k + 1
+            areas[max(r - 1, 0):r + 2, max(c - 1, 0):c + 2] = k + 1
+        areas[~active] = 0
+        full = lambda lo, hi: rng.uniform(lo, hi, (n, n)).astype(F32)  # noqa: E731
+        res = dict(locs=locs, areas=areas, ResSimpleArea=full(1e6, 9e6), ResMaxVolume=full(2e7, 8e7),
+                   ResTargetFullFrac=full(0.5, 0.9), ResMaxRelease=full(2.0, 30.0), ResDemand=full(0.1, 2.0),
+                   ResTargetMinFrac=full(0.1, 0.4))
+        res["ReservoirVolume"] = (res["ResMaxVolume"] * rng.uniform(0.2, 1.05, (n, n))).astype(F32)
+        cut[locs > 0] = 5
+    if kw.get("lakes"):
+        lspots = _river_spots(ldd, river, 5, 9, avoid=spots)
+        locs, areas, linked = np.zeros((n, n), np.int32), np.zeros((n, n), np.int32), np.zeros((n, n), np.int32)
+        for k, (r, c) in enumerate(lspots):
+            locs[r, c] = k + 1
+            areas[max(r - 1, 0):r + 2, max(c - 1, 0):c + 2] = k + 1
+        areas[~active] = 0
+        if len(lspots) >= 5:  # lake 4 exchanges water with lake 5
+            linked[lspots[3]] = 5
+        full = lambda lo, hi: rng.uniform(lo, hi, (n, n)).astype(F32)  # noqa: E731
+        stor, outf = np.ones((n, n), F32), np.full((n, n), 3.0, F32)
+        e = np.full((n, n), 2.0, F32)
+        for k, (r, c) in enumerate(lspots):
+            stor[r, c] = [1, 1, 2, 1, 1][k % 5]
+            outf[r, c] = [3, 2, 1, 2, 2][k % 5]
+            e[r, c] = [2.0, 1.5, 2.0, 2.0, 2.0][k % 5]
+        lak = dict(locs=locs, areas=areas, linked=linked, LakeArea=full(2e7, 8e7), LakeThreshold=full(0.0, 0.5),
+                   LakeStorFunc=stor, LakeOutflowFunc=outf, Lake_b=full(1.0, 6.0), Lake_e=e,
+                   LakeWaterLevel=full(1.0, 3.0), sh={}, hq={})
+        for k, (r, c) in enumerate(lspots):
+            if stor[r, c] == 2:
+                H = np.linspace(0.0, 8.0, 9)
+                lak["sh"][k + 1] = np.stack([H, lak["LakeArea"][r, c] * H * (1.0 + 0.05 * H)], axis=1).astype(F32).astype(np.float64)
+            if outf[r, c] == 1:
+                H = np.linspace(0.0, 8.0, 9)
+                q = np.stack([H] + [4.0 * np.maximum(H - 0.5, 0.0) ** 1.7 * (1.0 + 0.2 * np.sin(2 * np.pi * d / 366.0)) for d in range(366)], axis=1)
+                lak["hq"][k + 1] = q.astype(F32).astype(np.float64)
+        cut[locs > 0] = 5
+    return cut, res, lak
+
+
 def gen_case(name, kw):
     funcs, _ = refload.load()
     n, dt = kw["n"], kw.get("dt", 86400)
     ldd, river, static, state = build_inputs(**kw)
+    ldd_org = ldd
+    ldd, res, lak = object_inputs(kw, ldd_org, river, static)
     fields = dict(static)
     fields.update(state)
     lai = fields.pop("LAI", None)
     courant = kw.get("courant", 0)
     ref = ref_dynamic.RefDynamic(
-        ldd, river, fields, timestepsecs=dt, layer_thickness=kw["layer_thickness"], modelSnow=kw.get("snow", 1),
+        ldd, river, fields, ldd_org=ldd_org, reservoirs=res, lakes=lak, timestepsecs=dt, layer_thickness=kw["layer_thickness"], modelSnow=kw.get("snow", 1),
         soilInfRedu=kw.get("sir", 0), transferMethod=kw.get("tm", 0), ust=kw.get("ust", 0),
         kinwaveIters=kw.get("kinwaveIters", 0), kinwaveLandTstep=kw.get("landTstep", 0),
         kinwaveRiverTstep=kw.get("riverTstep", 0))
     forc = synth.Forcing(n, n, seed=5, timestepsecs=dt, rain_mean=kw.get("rain_mean", 20.0))
     data = {"ldd": ldd, "river": river}
+    if res or lak:
+        data["ldd_org"] = ldd_org
+        data["static/filter_P_PET"] = ref.get("filter_P_PET")
+    for tag, d in (("res", res), ("lake", lak)):
+        for k, v in (d or {}).items():
+            if k in ("sh", "hq"):
+                for i, t in v.items():
+                    data["%s/%s/%d" % (tag, k, i)] = np.asarray(t, F32)
+            elif k in ("ReservoirVolume", "LakeWaterLevel"):
+                data["state0/" + k] = v
+            elif k in ("locs", "areas", "linked"):
+                data["%s/%s" % (tag, k)] = v
+            else:
+                data["static/" + k] = v
     for k, v in static.items():
         data["static/" + k] = v
     for k, v in state.items():

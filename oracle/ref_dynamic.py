@@ -61,7 +61,7 @@ class RefDynamic:
 
     def __init__(self, ldd, river, fields, *, timestepsecs=86400, layer_thickness=(), modelSnow=1, soilInfRedu=0,
                  transferMethod=0, ust=0, kinwaveIters=0, kinwaveLandTstep=0, kinwaveRiverTstep=0, massWasting=0,
-                 topo_id=None, extra=None):
+                 topo_id=None, extra=None, ldd_org=None, reservoirs=None, lakes=None):
         Model, self.sbm = _model_class()
         funcs, _ = refload.load()
         ldd = np.asarray(ldd)
@@ -142,6 +142,35 @@ class RefDynamic:
         for k in CUMULATIVE:
             setattr(m, k, m.ZeroMap)
         m.count = 0
+        # ---- reservoirs / lakes (initial(), :1804-1907): id maps are missing outside the objects / their areas ----
+        def idmap(a):
+            a = np.asarray(a, np.float64).copy()
+            a[(a <= 0) | ~active] = MV
+            return pcr.numpy2pcr(pcr.Nominal, a, MV)
+        if reservoirs or lakes:
+            lo = np.where(active, np.asarray(ldd if ldd_org is None else ldd_org), 0).astype(np.float64)
+            lo[lo == 0] = MV
+            m.TopoLddOrg = pcr.numpy2pcr(pcr.Ldd, lo, MV)
+            m.filter_P_PET = m.ZeroMap + 1.0
+        if reservoirs:
+            m.ReserVoirSimpleLocs, m.ReservoirSimpleAreas = idmap(reservoirs["locs"]), idmap(reservoirs["areas"])
+            m.nrresSimple = int((np.asarray(reservoirs["locs"]) > 0).sum())
+            for k in ("ResSimpleArea", "ResMaxVolume", "ResTargetFullFrac", "ResMaxRelease", "ResDemand", "ResTargetMinFrac"):
+                setattr(m, k, mp(reservoirs[k]))
+            m.ReservoirVolume = mp(reservoirs["ReservoirVolume"]) if "ReservoirVolume" in reservoirs else m.ResMaxVolume * m.ResTargetFullFrac
+            res_area = pcr.cover(pcr.scalar(m.ReservoirSimpleAreas), 0.0)
+            m.filter_P_PET = pcr.ifthenelse(pcr.boolean(pcr.cover(res_area, pcr.scalar(0.0))), res_area * 0.0, m.filter_P_PET)
+        if lakes:
+            m.LakeLocs, m.LakeAreasMap = idmap(lakes["locs"]), idmap(lakes["areas"])
+            m.LinkedLakeLocs = idmap(lakes.get("linked", np.zeros(self.shape)))
+            m.nrlake = int((np.asarray(lakes["locs"]) > 0).sum())
+            for k in ("LakeArea", "LakeThreshold", "LakeStorFunc", "LakeOutflowFunc", "Lake_b", "Lake_e", "LakeWaterLevel"):
+                setattr(m, k, mp(lakes[k]))
+            m.sh, m.hq = dict(lakes.get("sh", {})), dict(lakes.get("hq", {}))
+            lake_area = pcr.cover(pcr.scalar(m.LakeAreasMap), 0.0)
+            m.filter_P_PET = pcr.ifthenelse(lake_area > 0, lake_area * 0.0, m.filter_P_PET)
+        if reservoirs or lakes:
+            m.filterResArea = pcr.pcr2numpy(m.filter_P_PET, 1.0).min()
         for k, v in (extra or {}).items():
             setattr(m, k, v)
         # ---- numpy mirrors, :2176-2380 ----

@@ -15,7 +15,7 @@ RESIDUALS = {"SoilWatbal": 1e-9, "watbal": 2e-4, "SurfaceWatbal": 0.0, "Intercep
 SUM_ORDER = {"RunoffCoeff": 1e-6, "QCatchmentMM": 1e-6}
 
 
-@pytest.mark.parametrize("name", common.golden_dyn_cases())
+@pytest.mark.parametrize("name", common.golden_dyn_cases(objects=False))
 def test_dynamic_trajectory_golden(name):
     g, kw, orc, _ = common.load_dyn_case(name)
     mask = common.network_mask(orc)

@@ -234,6 +234,36 @@ class SbmModel:
         _lib.check(self._l.wf_field_device_ptr(self._h, name.encode(), C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    # -- reservoirs / lakes (wflow_sbm.py:2822-2883) ----------------------------------------
+    def reservoirs_create(self, locs, areas, ldd_org):
+        """Simple reservoirs: id rasters ReserVoirSimpleLocs / ReservoirSimpleAreas and the LDD before the objects were
+        turned into pits.  Returns the number of reservoirs."""
+        a = [np.ascontiguousarray(x, dtype=np.int32) for x in (locs, areas)]
+        l = np.ascontiguousarray(ldd_org, dtype=np.uint8)
+        return _lib.check(self._l.wf_reservoirs_create(self._h, a[0].ctypes.data, a[1].ctypes.data, l.ctypes.data))
+
+    def lakes_create(self, locs, linked, areas, ldd_org, sh=None, hq=None):
+        """Natural lakes: id rasters LakeLocs / LinkedLakeLocs / LakeAreasMap, the original LDD and the curve tables
+        sh = {lake id: array[rows, 2] (H, S)}, hq = {lake id: array[rows, 367] (H, Q per day of the year)}."""
+        a = [np.ascontiguousarray(x, dtype=np.int32) for x in (locs, linked, areas)]
+        l = np.ascontiguousarray(ldd_org, dtype=np.uint8)
+
+        def pack(d, ncol):
+            d = d or {}
+            ids = np.array(sorted(d), np.int32)
+            rows = np.array([np.asarray(d[k]).reshape(-1, ncol).shape[0] for k in ids], np.int32)
+            data = (np.concatenate([np.asarray(d[k], np.float32).reshape(-1, ncol) for k in ids]) if len(ids)
+                    else np.zeros((0, ncol), np.float32))
+            return ids, rows, np.ascontiguousarray(data, np.float32)
+        si, sr, sd = pack(sh, 2)
+        hi, hr, hd = pack(hq, 367)
+        return _lib.check(self._l.wf_lakes_create(self._h, a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, l.ctypes.data,
+                                                  len(si), si.ctypes.data, sr.ctypes.data, sd.ctypes.data,
+                                                  len(hi), hi.ctypes.data, hr.ctypes.data, hd.ctypes.data))
+
+    def set_day_of_year(self, jdoy):
+        _lib.check(self._l.wf_set_day_of_year(self._h, int(jdoy)))
+
     # -- kinematic-wave sub-steps ---------------------------------------------------------
     def estimate_iterations(self, which):
         """estimate_iterations_kin_wave (wflow/wflow_funcs.py:103-116); which = "land" | "river"."""

@@ -18,6 +18,7 @@
 #include "network.h"
 #include "reduce.cuh"
 #include "outputs.cuh"
+#include "objects.cuh"
 
 namespace wf {
 
@@ -132,6 +133,15 @@ struct wf_model {
   int32_t cap_n = 0;
   int pipe_blocks = 0;
   size_t pipe_attr_smem = 0;
+  // reservoirs / lakes (objects.cuh)
+  struct Objects {
+    ObjectSet dev = {};
+    std::vector<void *> owned;        // device allocations behind dev
+    bool lakes = false;
+  };
+  Objects reservoirs, lakes;
+  float *d_obj_inflow = nullptr;      // nr: Inflow map + outflow of the objects above each river cell
+  int jdoy = 1;                       // day of the year for the lakes' rating tables (wf_set_day_of_year)
   // end-of-dynamic() outputs (outputs.cuh): work arrays, allocated with the first request
   EndArgs end = {};
   float *d_ct1 = nullptr;
@@ -318,6 +328,91 @@ void prepare_step(wf_model *m) {
   }
 }
 
+// ---- reservoirs / lakes (objects.cuh): before the column, on the states of the step before (wflow_sbm.py:2822-2883) ----
+int launch_objects(wf_model *m) {
+  m->dm.obj_inflow = nullptr;
+  const int nres = m->reservoirs.dev.n, nlake = m->lakes.dev.n;
+  if (nres + nlake == 0) return WF_OK;
+  if (!m->d_obj_inflow) CUDA_OK(cudaMalloc(&m->d_obj_inflow, sizeof(float) * (size_t)std::max<int32_t>(m->nr, 1)));
+  int first = 1;
+  if (nres > 0) {
+    for (int id : {F_ResSimpleArea, F_ResMaxVolume, F_ResTargetFullFrac, F_ResMaxRelease, F_ResDemand, F_ResTargetMinFrac})
+      if (!m->dm.f[id]) return fail(WF_EINVAL, std::string("reservoir parameter map not set: ") + g_fields[id].name);
+    k_object_forcing<<<nres, 128, 0, m->stream>>>(m->dm, m->reservoirs.dev);
+    k_reservoirs<<<(nres + 127) / 128, 128, 0, m->stream>>>(m->dm, m->reservoirs.dev);
+    k_object_inflow<<<1, 256, 0, m->stream>>>(m->dm, m->reservoirs.dev, m->d_obj_inflow, first);
+    first = 0;
+    m->launches += 3;
+  }
+  if (nlake > 0) {
+    for (int id : {F_LakeArea, F_LakeThreshold, F_LakeStorFunc, F_LakeOutflowFunc, F_Lake_b, F_Lake_e})
+      if (!m->dm.f[id]) return fail(WF_EINVAL, std::string("lake parameter map not set: ") + g_fields[id].name);
+    k_object_forcing<<<nlake, 128, 0, m->stream>>>(m->dm, m->lakes.dev);
+    k_lakes<<<1, 256, sizeof(float) * 3 * (size_t)nlake, m->stream>>>(m->dm, m->lakes.dev, m->jdoy);
+    k_object_inflow<<<1, 256, 0, m->stream>>>(m->dm, m->lakes.dev, m->d_obj_inflow, first);
+    m->launches += 3;
+  }
+  m->dm.obj_inflow = m->d_obj_inflow;
+  CUDA_OK(cudaGetLastError());
+  return WF_OK;
+}
+
+// Objects of a location map: one per cell with an id > 0, in raster order.  areas: the map whose class AT the object's cell
+// is the object's area (pcr.areaaverage(.., areas) read at the object, wflow_funcs.py:710-713, 882-891); ldd_org: the LDD
+// before initial() cut it at the objects (TopoLddOrg), for the cell that receives the outflow.
+int build_objects(wf_model *m, const int32_t *locs, const int32_t *areas, const uint8_t *ldd_org, wf_model::Objects &ob,
+                  std::vector<int32_t> &ids_out, std::vector<int32_t> &pos_out) {
+  static const int dr[10] = {0, 1, 1, 1, 0, 0, 0, -1, -1, -1}, dc[10] = {0, -1, 0, 1, -1, 0, 1, -1, 0, 1};
+  const int nrow = m->cfg.nrow, ncol = m->cfg.ncol;
+  const int64_t N = (int64_t)nrow * ncol;
+  std::vector<int32_t> pos, down, seg(1, 0), perm, areaid;
+  for (int64_t fl = 0; fl < N; fl++) {
+    if (locs[fl] <= 0) continue;
+    const int32_t p = m->pos_of_flat[(size_t)fl];
+    if (p < 0) return fail(WF_EINVAL, "a reservoir / lake location lies outside the drainage network");
+    int32_t drs = -1;
+    const int c = ldd_org ? ldd_org[fl] : 5;
+    if (c >= 1 && c <= 9 && c != 5) {
+      const int64_t r2 = fl / ncol + dr[c], c2 = fl % ncol + dc[c];
+      if (r2 >= 0 && r2 < nrow && c2 >= 0 && c2 < ncol) {
+        const int32_t pd = m->pos_of_flat[(size_t)(r2 * ncol + c2)];
+        if (pd >= 0) drs = m->river_slot[(size_t)pd];
+      }
+    }
+    pos.push_back(p);
+    down.push_back(drs);
+    ids_out.push_back(locs[fl]);
+    areaid.push_back(areas ? areas[fl] : 0);
+  }
+  pos_out = pos;
+  const int n = (int)pos.size();
+  for (int k = 0; k < n; k++) {
+    if (areaid[(size_t)k] > 0)
+      for (int64_t q = 0; q < m->n; q++)
+        if (areas[m->snet.order[(size_t)q]] == areaid[(size_t)k]) perm.push_back((int32_t)q);
+    seg.push_back((int32_t)perm.size());
+  }
+  auto up = [&](const void *src, size_t bytes, const void **dst) -> int {
+    void *d = nullptr;
+    CUDA_OK(cudaMalloc(&d, std::max<size_t>(bytes, 16)));
+    if (bytes) CUDA_OK(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+    ob.owned.push_back(d);
+    *dst = d;
+    return WF_OK;
+  };
+  int rc;
+  ob.dev.n = n;
+  if ((rc = up(pos.data(), sizeof(int32_t) * n, (const void **)&ob.dev.pos))) return rc;
+  if ((rc = up(down.data(), sizeof(int32_t) * n, (const void **)&ob.dev.down_rs))) return rc;
+  if ((rc = up(seg.data(), sizeof(int32_t) * seg.size(), (const void **)&ob.dev.area_seg))) return rc;
+  if ((rc = up(perm.data(), sizeof(int32_t) * perm.size(), (const void **)&ob.dev.area_perm))) return rc;
+  std::vector<float> z((size_t)std::max(n, 1), 0.0f);
+  if ((rc = up(z.data(), sizeof(float) * n, (const void **)&ob.dev.prec_av))) return rc;
+  if ((rc = up(z.data(), sizeof(float) * n, (const void **)&ob.dev.pet_av))) return rc;
+  if ((rc = up(z.data(), sizeof(float) * n, (const void **)&ob.dev.outflow))) return rc;
+  return WF_OK;
+}
+
 // ---- end-of-dynamic() outputs (outputs.cuh) ----------------------------------------------------------
 bool end_outputs_requested(const wf_model *m) {
   for (int id = F_KinWaveVolumeR; id <= F_CumSurfaceWater; id++) {
@@ -376,6 +471,7 @@ int launch_step(wf_model *m) {
     k_end_pre<ML><<<(unsigned)((span + 255) / 256), 256, 0, m->stream>>>(m->dm, m->end);
     m->launches++;
   }
+  if (int rc = launch_objects(m)) return rc;
   const size_t vsmem = WF_VERT_STAGE ? VLayout<ML>::bytes(m->dm.glacier != 0) : 0;
   // four builds of the column: with / without the diagnostic outputs, with / without the LAI-driven canopy parameters
   void (*kv)(const DevModel) = nullptr;
@@ -986,6 +1082,7 @@ static int create_impl(wf_model *m, const wf_config *cfg, wf_schedule *sched, co
     if ((g_fields[id].kind & 0xff) != K_STATE) continue;
     if (id >= F_UStoreLayerDepth_0 && id <= F_UStoreLayerDepth_7 && id - F_UStoreLayerDepth_0 >= m->ML) continue;
     if (id == F_GlacierStore && !cfg->glacier) continue;
+    if (id == F_ReservoirVolume || id == F_LakeWaterLevel) continue;  // created with the objects
     if ((rc = ensure_field(m, id))) return rc;
   }
   CUDA_OK(cudaStreamSynchronize(m->stream));
@@ -1036,6 +1133,9 @@ void wf_destroy(wf_model *m) {
   for (cudaEvent_t e : m->tev) cudaEventDestroy(e);
   for (float *p : m->snapshot) cudaFree(p);
   for (auto &a : m->areas) { cudaFree(a.d_perm); cudaFree(a.d_seg); }
+  for (void *p : m->reservoirs.owned) cudaFree(p);
+  for (void *p : m->lakes.owned) cudaFree(p);
+  cudaFree(m->d_obj_inflow);
   cudaFree(m->end.preWLRsub); cudaFree(m->end.preWLR); cudaFree(m->end.preWLLsub); cudaFree(m->end.preOrg); cudaFree(m->end.ctR); cudaFree(m->d_ct1);
   cudaFree(m->dm.d_efT); cudaFree(m->dm.d_efST); cudaFree(m->dm.d_cpd);
   cudaFree(m->dm.h_lq); cudaFree(m->dm.h_lqb); cudaFree(m->dm.h_rq); cudaFree(m->dm.h_rqb);
@@ -1508,6 +1608,8 @@ int wf_step_pipelined(wf_model *m, int nsteps, float *gauge_out, float mv, int a
   if (m->cfg.model_snow && !m->pipe_has[2]) return fail(WF_EINVAL, "pipelined forcing not set: TEMP");
   if (m->dm.task_mask != 7) return fail(WF_EUNSUPPORTED, "WF_LATERAL_TASKS is a development aid of the per-step sweep");
   if (gauge_out && m->pipe_gauges < 0) return fail(WF_EINVAL, "no gauge set registered (wf_pipeline_capture)");
+  if (m->reservoirs.dev.n + m->lakes.dev.n > 0)
+    return fail(WF_EUNSUPPORTED, "reservoirs and lakes need the per-step path (wf_step)");
   if (end_outputs_requested(m))
     return fail(WF_EUNSUPPORTED, "the end-of-dynamic() outputs (mass balances, cumulative sums ...) need the per-step path (wf_step)");
   CUDA_OK(cudaSetDevice(m->cfg.device));
@@ -1757,6 +1859,85 @@ int wf_gauges_sample_device(wf_model *m, int gauges, const char *field, float *d
   k_sample_gauges<<<(unsigned)((g.n + 127) / 128), 128, 0, m->stream>>>(m->dm.f[id], g.d_pos, riv ? g.d_rpos : nullptr, dout, g.n, mv);
   m->launches++;
   CUDA_OK(cudaGetLastError());
+  return WF_OK;
+}
+
+// ---- reservoirs / lakes ------------------------------------------------------------------------------
+int wf_reservoirs_create(wf_model *m, const int32_t *locs, const int32_t *areas, const uint8_t *ldd_org) {
+  if (!m || !locs) return fail(WF_EINVAL, "null argument");
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  CUDA_OK(cudaStreamSynchronize(m->stream));
+  for (void *p : m->reservoirs.owned) cudaFree(p);
+  m->reservoirs = wf_model::Objects();
+  std::vector<int32_t> ids, pos;
+  if (int rc = build_objects(m, locs, areas, ldd_org, m->reservoirs, ids, pos)) return rc;
+  if (m->reservoirs.dev.n > 0)
+    if (int rc = ensure_field(m, F_ReservoirVolume)) return rc;
+  return m->reservoirs.dev.n;
+}
+
+int wf_lakes_create(wf_model *m, const int32_t *locs, const int32_t *linked, const int32_t *areas, const uint8_t *ldd_org,
+                    int n_sh, const int32_t *sh_ids, const int32_t *sh_rows, const float *sh_data, int n_hq,
+                    const int32_t *hq_ids, const int32_t *hq_rows, const float *hq_data) {
+  if (!m || !locs) return fail(WF_EINVAL, "null argument");
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  CUDA_OK(cudaStreamSynchronize(m->stream));
+  for (void *p : m->lakes.owned) cudaFree(p);
+  m->lakes = wf_model::Objects();
+  wf_model::Objects &ob = m->lakes;
+  std::vector<int32_t> ids, pos;
+  if (int rc = build_objects(m, locs, areas, ldd_org, ob, ids, pos)) return rc;
+  const int n = ob.dev.n;
+  if (n == 0) return 0;
+  // linked lakes: LinkedLakeLocs at a lake's cell holds the id of the lake it exchanges water with (wflow_funcs.py:766-777)
+  std::vector<int32_t> link((size_t)n, -1), sh_off((size_t)n + 1, 0), hq_off((size_t)n + 1, 0);
+  const int ncol = m->cfg.ncol;
+  (void)ncol;
+  for (int k = 0; k < n; k++) {
+    const int64_t fl = m->snet.order[(size_t)pos[(size_t)k]];
+    const int32_t want = linked ? linked[fl] : 0;
+    if (want > 0)
+      for (int j = 0; j < n; j++)
+        if (ids[(size_t)j] == want) link[(size_t)k] = j;
+  }
+  // curve tables, keyed by lake id: storage (rows of H, S) and rating (rows of H, Q(day 1..366))
+  std::vector<float> sh, hq;
+  for (int k = 0; k < n; k++) {
+    size_t off = 0;
+    for (int t = 0; t < n_sh; t++) {
+      if (sh_ids[t] == ids[(size_t)k]) sh.insert(sh.end(), sh_data + 2 * off, sh_data + 2 * (off + (size_t)sh_rows[t]));
+      off += (size_t)sh_rows[t];
+    }
+    sh_off[(size_t)k + 1] = (int32_t)(sh.size() / 2);
+    off = 0;
+    for (int t = 0; t < n_hq; t++) {
+      if (hq_ids[t] == ids[(size_t)k]) hq.insert(hq.end(), hq_data + 367 * off, hq_data + 367 * (off + (size_t)hq_rows[t]));
+      off += (size_t)hq_rows[t];
+    }
+    hq_off[(size_t)k + 1] = (int32_t)(hq.size() / 367);
+  }
+  auto up = [&](const void *src, size_t bytes, const void **dst) -> int {
+    void *d = nullptr;
+    CUDA_OK(cudaMalloc(&d, std::max<size_t>(bytes, 16)));
+    if (bytes) CUDA_OK(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+    ob.owned.push_back(d);
+    *dst = d;
+    return WF_OK;
+  };
+  int rc;
+  if ((rc = up(link.data(), sizeof(int32_t) * n, (const void **)&ob.dev.linked))) return rc;
+  if ((rc = up(sh.data(), sizeof(float) * sh.size(), (const void **)&ob.dev.sh_tab))) return rc;
+  if ((rc = up(sh_off.data(), sizeof(int32_t) * sh_off.size(), (const void **)&ob.dev.sh_off))) return rc;
+  if ((rc = up(hq.data(), sizeof(float) * hq.size(), (const void **)&ob.dev.hq_tab))) return rc;
+  if ((rc = up(hq_off.data(), sizeof(int32_t) * hq_off.size(), (const void **)&ob.dev.hq_off))) return rc;
+  ob.lakes = true;
+  if (int rc2 = ensure_field(m, F_LakeWaterLevel)) return rc2;
+  return n;
+}
+
+int wf_set_day_of_year(wf_model *m, int jdoy) {
+  if (!m || jdoy < 1 || jdoy > 366) return fail(WF_EINVAL, "day of the year must be 1..366");
+  m->jdoy = jdoy;
   return WF_OK;
 }
 

@@ -32,6 +32,11 @@ enum FieldKind : int { K_FORCING = 0, K_STATIC = 1, K_STATE = 2, K_DIAG = 3, K_R
   X(AlphaR, K_STATIC | K_RIVER) X(DCL, K_STATIC | K_RIVER) X(Bw, K_STATIC | K_RIVER)               \
   /* glacier */                                                                                    \
   X(GlacierFrac, K_STATIC) X(G_TT, K_STATIC) X(G_Cfmax, K_STATIC) X(G_SIfrac, K_STATIC)            \
+  /* reservoirs and lakes (wflow_sbm.py:1804-1907, 2822-2883; objects.cuh): rasters read at the objects' cells */   \
+  X(filter_P_PET, K_STATIC) X(ResSimpleArea, K_STATIC) X(ResMaxVolume, K_STATIC) X(ResTargetFullFrac, K_STATIC)     \
+  X(ResMaxRelease, K_STATIC) X(ResDemand, K_STATIC) X(ResTargetMinFrac, K_STATIC)                  \
+  X(LakeArea, K_STATIC) X(LakeThreshold, K_STATIC) X(LakeStorFunc, K_STATIC) X(LakeOutflowFunc, K_STATIC)          \
+  X(Lake_b, K_STATIC) X(Lake_e, K_STATIC)                                                          \
   /* dynamic vegetation (wflow_sbm.py:2587-2603): present when LAI is */                           \
   X(LAI, K_STATIC) X(Sl, K_STATIC) X(Swood, K_STATIC) X(Kext, K_STATIC)                            \
   /* states (stateVariables(), wflow_sbm.py:955-1010; zi is the live saturated-zone state) */      \
@@ -44,7 +49,7 @@ enum FieldKind : int { K_FORCING = 0, K_STATIC = 1, K_STATE = 2, K_DIAG = 3, K_R
   X(WaterLevelL, K_STATE) X(WaterLevelLsub, K_STATE)                                               \
   X(RiverRunoff, K_STATE | K_RIVER) X(RiverRunoffsub, K_STATE | K_RIVER)                           \
   X(WaterLevelR, K_STATE | K_RIVER) X(WaterLevelRsub, K_STATE | K_RIVER)                           \
-  X(GlacierStore, K_STATE)                                                                         \
+  X(GlacierStore, K_STATE) X(ReservoirVolume, K_STATE) X(LakeWaterLevel, K_STATE)                  \
   /* diagnostics, materialised only on request */                                                  \
   X(SatWaterDepth, K_DIAG) X(Precipitation, K_DIAG) X(PotenEvap, K_DIAG) X(Temperature, K_DIAG)    \
   X(ThroughFall, K_DIAG) X(StemFlow, K_DIAG) X(Interception, K_DIAG) X(PotTransSoil, K_DIAG)       \
@@ -78,7 +83,10 @@ enum FieldKind : int { K_FORCING = 0, K_STATIC = 1, K_STATE = 2, K_DIAG = 3, K_R
   X(InfiltExcessCubic, K_DIAG) X(SurfaceWaterSupply, K_DIAG)                                       \
   X(CumOutFlow, K_DIAG) X(CumActInfilt, K_DIAG) X(CumCellInFlow, K_DIAG) X(CumPrec, K_DIAG)        \
   X(CumEvap, K_DIAG) X(CumPotenEvap, K_DIAG) X(CumInt, K_DIAG) X(CumLeakage, K_DIAG)               \
-  X(CumExfiltWater, K_DIAG) X(CumSurfaceWater, K_DIAG)
+  X(CumExfiltWater, K_DIAG) X(CumSurfaceWater, K_DIAG)                                             \
+  X(OutflowSR, K_DIAG) X(ResPercFull, K_DIAG) X(ResPrecipSR, K_DIAG) X(ResEvapSR, K_DIAG)          \
+  X(DemandRelease, K_DIAG) X(LakeOutflow, K_DIAG) X(LakeVolume, K_DIAG) X(LakePrecip, K_DIAG)      \
+  X(LakeEvap, K_DIAG)
 
 enum FieldId : int {
 #define X(n, k) F_##n,

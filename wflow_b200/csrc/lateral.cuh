@@ -694,7 +694,9 @@ __device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i
     const float dtf = (float)m.dt;
     const float ToCubic = ((LD(xl) * LD(yl)) * 0.001f) / dtf;  // :1998
     float Inwater = ((m.h_inwaterMM[rs] * ToCubic) + qo_toriver_f) + ldx<MODE>(m.h_ssf_tr + rs);
-    if (m.f[F_Inflow]) Inwater = Inwater + m.f[F_Inflow][rs];
+    // self.Inflow: the external map, plus the outflow of the reservoirs / lakes above the cell (:2852, 2883, 3144)
+    if (m.obj_inflow) Inwater = Inwater + __ldg(m.obj_inflow + rs);
+    else if (m.f[F_Inflow]) Inwater = Inwater + m.f[F_Inflow][rs];
     m.h_inwater[rs] = Inwater;
     if (m.f[F_Inwater]) m.f[F_Inwater][rs] = Inwater;
     if (rs >= m.nrnet) {  // river-map cell outside the river network: kin_wave never visits it (zeros)
