@@ -450,6 +450,31 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def pin_to_gpu_numa_node(local):
+    """Run this rank on the CPUs of its GPU's NUMA node, so that the pinned forcing buffers it allocates afterwards are
+    local to the PCIe root the GPU hangs on (8 ranks x 403 MB per step cross the host: r1 lost 21 % end to end at N = 8)."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"numa_node": node, "cpus": len(cpus)}
+    except Exception as ex:
+        return {"error": repr(ex)}
+    return None
+
+
 # ---- the CUDA arm ---------------------------------------------------------------------------------------------------
 class _DevArray:
     """Expose a raw device pointer to torch through __cuda_array_interface__."""
@@ -515,6 +540,7 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = pin_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -685,6 +711,7 @@ def run_b200(args):
                                     "lateral_us_per_level": ms_l / nst * 1e3 / max(mod.num_levels, 1)},
             "lateral_plan": mod.lateral_plan,
             "clocks": clk.summary(),
+            "host_affinity": numa,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

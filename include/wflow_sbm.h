@@ -229,6 +229,13 @@ int wf_reservoirs_create(wf_model *m, const int32_t *locs, const int32_t *areas,
 int wf_lakes_create(wf_model *m, const int32_t *locs, const int32_t *linked, const int32_t *areas, const uint8_t *ldd_org,
                     int n_sh, const int32_t *sh_ids, const int32_t *sh_rows, const float *sh_data,
                     int n_hq, const int32_t *hq_ids, const int32_t *hq_rows, const float *hq_data);
+/* Options of [model] that switch optional parts of dynamic() on:
+ *   "MassWasting"  1: dry snow slides downslope after the snow pack (pcr.accucapacitystate, wflow/wflow_sbm.py:2700-2707)
+ *   "Abstractions" 1: a negative Inflow is a demand met from the river, with the reference's supply iteration (:3131-3146,
+ *                     3203-3308; reproduced with its re-routing quirk).  Off: Inflow is added as it is.
+ *   "maxitsupply"  iterations of that loop at most (default 5, :1241);  "breakoff" its stopping change (default 1e-4, :3206) */
+int wf_set_option(wf_model *m, const char *name, double value);
+int wf_supply_iterations(const wf_model *m);   /* self.nrit of the last step */
 /* Day of the year (1..366) of the coming steps: column of the lakes' rating tables (wf_supplyJulianDOY). */
 int wf_set_day_of_year(wf_model *m, int jdoy);
 

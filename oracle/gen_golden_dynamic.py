@@ -54,6 +54,12 @@ CASES = {
     "reservoirs_6h": dict(n=24, kind="tiles", tile=12, layer_thickness=(100, 300), dt=21600, steps=5, reservoirs=1),
     # natural lakes (naturalLake, :669-861): modified Puls, rating curve b (H - H0)^e with S = A H, S-H and H-Q tables, a linked pair
     "lakes_daily": dict(n=24, kind="tiles", tile=12, layer_thickness=(100, 300, 800), steps=6, lakes=1),
+    # snow mass wasting (pcr.accucapacitystate of the dry pack, wflow_sbm.py:2700-2707): deep packs on steep cells
+    "masswasting_daily": dict(n=24, kind="tiles", tile=12, layer_thickness=(100, 300, 800), steps=5, masswasting=1),
+    # abstractions: a negative Inflow at some river cells, met from the river through the supply iteration (:3131-3146, 3203-3308)
+    "abstraction_daily": dict(n=24, kind="tiles", tile=12, layer_thickness=(100, 300, 800), steps=5, inflow=-1),
+    "abstraction_hourly_substeps": dict(n=24, kind="tiles", tile=12, layer_thickness=(100, 300), dt=3600, kinwaveIters=1,
+                                        landTstep=3600, riverTstep=900, steps=5, inflow=-1),
 }
 
 STATES = ["CanopyStorage", "Snow", "SnowWater", "TSoil", "zi", "SubsurfaceFlow", "LandRunoff", "LandRunoffsub", "WaterLevelL",
@@ -107,6 +113,9 @@ def build_inputs(n, kind, layer_thickness, dt=86400, seed=3, tile=12, mask_frac=
         blk = lambda lo, hi: np.kron(rng.uniform(lo, hi, ((n + 3) // 4, (n + 3) // 4)), np.ones((4, 4)))[:n, :n].astype(F32)  # noqa: E731
         static.update(Sl=blk(0.03, 0.13), Swood=blk(0.0, 0.5), Kext=blk(0.4, 0.8))
         static["LAI"] = np.where(rng.random((n, n)) < 0.1, 0.0, blk(0.1, 6.0)).astype(F32)
+    if _.get("masswasting"):
+        state["Snow"] = np.where(rng.random((n, n)) < 0.7, rng.uniform(0, 6000, (n, n)), 0.0).astype(F32)
+        static["landSlope"] = np.where(rng.random((n, n)) < 0.5, rng.uniform(0.5, 4.0, (n, n)), static["landSlope"]).astype(F32)
     if _.get("land_boost"):  # fast overland flow: the Courant estimate of the land wave exceeds 1 sub-step
         state["LandRunoffsub"] = (state["LandRunoffsub"] * F32(_["land_boost"])).astype(F32)
         state["LandRunoff"] = state["LandRunoffsub"].copy()
@@ -197,7 +206,7 @@ def gen_case(name, kw):
         ldd, river, fields, ldd_org=ldd_org, reservoirs=res, lakes=lak, timestepsecs=dt, layer_thickness=kw["layer_thickness"], modelSnow=kw.get("snow", 1),
         soilInfRedu=kw.get("sir", 0), transferMethod=kw.get("tm", 0), ust=kw.get("ust", 0),
         kinwaveIters=kw.get("kinwaveIters", 0), kinwaveLandTstep=kw.get("landTstep", 0),
-        kinwaveRiverTstep=kw.get("riverTstep", 0))
+        kinwaveRiverTstep=kw.get("riverTstep", 0), massWasting=kw.get("masswasting", 0))
     forc = synth.Forcing(n, n, seed=5, timestepsecs=dt, rain_mean=kw.get("rain_mean", 20.0))
     data = {"ldd": ldd, "river": river}
     if res or lak:
@@ -223,8 +232,12 @@ def gen_case(name, kw):
         ["vwc_perc_%d" % k for k in range(nl)]
     rng = np.random.default_rng(99)
     inflow = None
-    if kw.get("inflow"):
+    if kw.get("inflow", 0) > 0:
         inflow = np.where((river != 0) & (rng.random((n, n)) < 0.3), rng.uniform(0.05, 3.0, (n, n)), 0.0).astype(F32)
+    elif kw.get("inflow", 0) < 0:  # demands: some small, some more than the river carries; a few sources beside them
+        u = rng.random((n, n))
+        inflow = np.where((river != 0) & (u < 0.25), -np.exp(rng.uniform(np.log(0.01), np.log(300.0), (n, n))), 0.0)
+        inflow = np.where((river != 0) & (u > 0.9), rng.uniform(0.05, 3.0, (n, n)), inflow).astype(F32)
     for t in range(kw["steps"]):
         P, PET, T = forc.step(t)
         if kw.get("lai") and t % 2 == 1:
@@ -239,6 +252,8 @@ def gen_case(name, kw):
             itr = funcs.estimate_iterations_kin_wave(m.RiverRunoffsub, m.Beta, m.AlphaR, m.timestepsecs, m.DCL, m.mv)
             data["it/%d" % t] = np.array([itl, itr], np.int64)
         ref.step(P, PET, T, Inflow=inflow, LAI=lai)
+        if kw.get("inflow", 0) < 0:
+            data["nrit/%d" % t] = np.array(ref.m.nrit, np.int64)
         for k in outs:
             if ref.has(k):
                 data["out/%d/%s" % (t, k)] = ref.get(k)

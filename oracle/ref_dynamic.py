@@ -90,7 +90,7 @@ class RefDynamic:
         m.filterResArea = 0
         m.updating = 0
         m.maxitsupply = 5
-        m.DemandReturnFlowFraction = pcr.scalar(0.0)
+        m.DemandReturnFlowFraction = pcr.scalar(0.0)  # defaults of the irrigation maps: none (:1096-1135, 1481-1482)
         nlay = len(layer_thickness)
         m.maxLayers = nlay + 1 if nlay > 0 else 1  # :1757-1766
         nrLayers = nlay if nlay > 0 else 1
@@ -139,6 +139,8 @@ class RefDynamic:
         m.OldKinWaveVolumeL = m.KinWaveVolumeL
         m.KinWaveVolumeR = m.WaterLevelRsub * m.Bw * m.DCL
         m.OldKinWaveVolumeR = m.KinWaveVolumeR
+        m.IrrigationSurfaceIntakes = m.IrrigationSurfaceReturn = m.ZeroMap
+        m.DemandReturnFlowFraction = m.ZeroMap
         for k in CUMULATIVE:
             setattr(m, k, m.ZeroMap)
         m.count = 0

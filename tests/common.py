@@ -121,10 +121,10 @@ def load_golden_case(name, oracle=True, gpu=False):
 
 # ---- goldens of the reference's whole dynamic() (tests/golden/dyn_*.npz, oracle/gen_golden_dynamic.py) ----
 def golden_dyn_cases(objects=True):
-    """objects=False: without the reservoir / lake cases (the C oracle does not restate those modules; the CUDA path is
-    checked against the reference's own goldens for them)."""
+    """objects=False: without the reservoir / lake / mass-wasting / abstraction cases (the C oracle does not restate those
+    optional modules; the CUDA path is checked against the reference's own goldens for them)."""
     names = sorted(os.path.basename(p)[4:-4] for p in glob.glob(os.path.join(GOLD, "dyn_*.npz")))
-    return [n for n in names if objects or not n.startswith(("reservoirs", "lakes"))]
+    return [n for n in names if objects or not n.startswith(("reservoirs", "lakes", "masswasting", "abstraction"))]
 
 
 def dyn_substeps(kw):
@@ -164,6 +164,10 @@ def load_dyn_case(name, oracle=True, gpu=False):
         for k, v in {**static, **state}.items():
             if k not in ("River", "Beta", "SatWaterDepth", "ReservoirVolume", "LakeWaterLevel"):
                 mod.set(k, v)
+        if kw.get("masswasting"):
+            mod.set_option("MassWasting", 1)
+        if kw.get("inflow", 0) < 0:
+            mod.set_option("Abstractions", 1)
         if "res/locs" in g.files:  # simple reservoirs (wflow_sbm.py:1804-1826, 2822-2852)
             assert mod.reservoirs_create(g["res/locs"], g["res/areas"], g["ldd_org"]) == int((g["res/locs"] > 0).sum())
             mod.set("ReservoirVolume", state["ReservoirVolume"])

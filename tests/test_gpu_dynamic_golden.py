@@ -68,6 +68,8 @@ def test_cuda_matches_reference_dynamic(name):
                 assert (itl, itr) == tuple(int(v) for v in g["it/%d" % t]), (name, t)
                 mod.set_substeps(itl, itr)
             mod.step()
+            if "nrit/%d" % t in g.files:  # iterations of the supply loop (self.nrit, wflow_sbm.py:3203-3300)
+                assert mod.supply_iterations == int(g["nrit/%d" % t]), (name, t)
             for f in outs:
                 ref = g["out/%d/%s" % (t, f)]
                 msk = cmask if f in CATCHMENT else mask

@@ -261,6 +261,14 @@ class SbmModel:
                                                   len(si), si.ctypes.data, sr.ctypes.data, sd.ctypes.data,
                                                   len(hi), hi.ctypes.data, hr.ctypes.data, hd.ctypes.data))
 
+    def set_option(self, name, value):
+        """[model] options that switch optional parts of dynamic() on: MassWasting, Abstractions, maxitsupply, breakoff."""
+        _lib.check(self._l.wf_set_option(self._h, name.encode(), float(value)))
+
+    @property
+    def supply_iterations(self):
+        return int(self._l.wf_supply_iterations(self._h))
+
     def set_day_of_year(self, jdoy):
         _lib.check(self._l.wf_set_day_of_year(self._h, int(jdoy)))
 

@@ -53,6 +53,11 @@ struct AreaSet {
   int32_t *d_perm = nullptr;  // cells (network order index) sorted by id
   int32_t *d_seg = nullptr;   // ids.size()+1 offsets into perm
   int64_t ncell = 0;
+  // two-pass reduction (reduce.cuh): chunks of the ids' runs, their partial results, the result row
+  int nchunks = 0;
+  int32_t *d_chunk_beg = nullptr, *d_chunk_end = nullptr, *d_id_chunk0 = nullptr;
+  AreaPartial *d_partial = nullptr;
+  float *d_out = nullptr;
 };
 
 }  // namespace wf
@@ -142,6 +147,14 @@ struct wf_model {
   Objects reservoirs, lakes;
   float *d_obj_inflow = nullptr;      // nr: Inflow map + outflow of the objects above each river cell
   int jdoy = 1;                       // day of the year for the lakes' rating tables (wf_set_day_of_year)
+  // options of wf_set_option
+  bool mass_wasting = false;          // [model] MassWasting
+  float *d_mw_flux = nullptr;         // n: snow flux of every cell (k_mass_wasting)
+  bool abstractions = false;          // negative Inflow = demand met from the river (supply iteration)
+  int maxitsupply = 5;                // [model] maxitsupply
+  double breakoff = 0.0001;           // wflow_sbm.py:3206
+  SupplyArgs sup = {};
+  int last_nrit = 0;                  // iterations of the supply loop in the last step (self.nrit)
   // end-of-dynamic() outputs (outputs.cuh): work arrays, allocated with the first request
   EndArgs end = {};
   float *d_ct1 = nullptr;
@@ -481,13 +494,41 @@ int launch_step(wf_model *m) {
   if (vsmem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute((void *)kv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
   if (VScratch<ML>::enabled)  // WF_VERT_MINBLOCKS blocks with their scratch must fit the shared-memory carve-out
     CUDA_OK(cudaFuncSetAttribute((void *)kv, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  if (m->abstractions && m->dm.f[F_Inflow]) CUDA_OK(cudaMemsetAsync(m->sup.any_neg, 0, sizeof(int32_t), m->stream));
   kv<<<(unsigned)((n + tb - 1) / tb), tb, vsmem, m->stream>>>(m->dm);
   m->launches++;
+  if (m->mass_wasting && m->dm.modelSnow) {  // between the snow pack and everything that reads Snow afterwards (:2700-2707)
+    if (!m->d_mw_flux) CUDA_OK(cudaMalloc(&m->d_mw_flux, sizeof(float) * (size_t)std::max<int64_t>(n, 1)));
+    k_mass_wasting<<<(unsigned)std::max(1, std::min(m->dm.ngroups, 1024)), 1024, 0, m->stream>>>(m->dm, m->d_mw_flux);
+    m->launches++;
+  }
   if (m->timed) cudaEventRecord(e1, m->stream);
   if (int rc = launch_lateral<ML>(m)) return rc;
   m->launches++;
   if (m->timed) cudaEventRecord(e2, m->stream);
   m->ev_last[0] = e0; m->ev_last[1] = e1; m->ev_last[2] = e2;
+  m->last_nrit = 0;
+  if (m->abstractions && m->dm.f[F_Inflow] && m->nr > 0) {  // wflow_sbm.py:3203-3308
+    int32_t any = 0;
+    CUDA_OK(cudaMemcpyAsync(&any, m->sup.any_neg, sizeof(int32_t), cudaMemcpyDeviceToHost, m->stream));
+    CUDA_OK(cudaStreamSynchronize(m->stream));
+    if (any) {
+      for (int k = 1;; k++) {
+        m->last_nrit = k;
+        CUDA_OK(cudaMemsetAsync(m->sup.delta, 0, sizeof(float), m->stream));
+        k_supply_estimate<<<(unsigned)((m->nr + 127) / 128), 128, 0, m->stream>>>(m->dm, m->sup);
+        m->launches++;
+        if (k >= 2) {  // (the loop's first kin_wave call repeats the sweep's result)
+          k_river_again<ML><<<(unsigned)std::max(1, std::min(m->dm.ngroups, 1024)), 512, 0, m->stream>>>(m->dm);
+          m->launches++;
+        }
+        float delta = 0.0f;
+        CUDA_OK(cudaMemcpyAsync(&delta, m->sup.delta, sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+        CUDA_OK(cudaStreamSynchronize(m->stream));
+        if ((double)delta < m->breakoff || k >= m->maxitsupply) break;
+      }
+    }
+  }
   if (end_out) {
     if (m->dm.f[F_QCatchmentMM] || m->dm.f[F_RunoffCoeff]) {
       k_catchment_total<<<(unsigned)std::max(1, std::min(m->dm.ngroups, 1024)), 1024, 0, m->stream>>>(m->dm, m->dm.f[F_RainFallPlusMelt], m->end.ctR);
@@ -1132,10 +1173,11 @@ void wf_destroy(wf_model *m) {
   for (auto &g : m->gauges) { cudaFree(g.d_pos); cudaFree(g.d_rpos); cudaFree(g.d_out); }
   for (cudaEvent_t e : m->tev) cudaEventDestroy(e);
   for (float *p : m->snapshot) cudaFree(p);
-  for (auto &a : m->areas) { cudaFree(a.d_perm); cudaFree(a.d_seg); }
+  for (auto &a : m->areas) { cudaFree(a.d_perm); cudaFree(a.d_seg); cudaFree(a.d_chunk_beg); cudaFree(a.d_chunk_end); cudaFree(a.d_id_chunk0); cudaFree(a.d_partial); cudaFree(a.d_out); }
   for (void *p : m->reservoirs.owned) cudaFree(p);
   for (void *p : m->lakes.owned) cudaFree(p);
-  cudaFree(m->d_obj_inflow);
+  cudaFree(m->d_obj_inflow); cudaFree(m->d_mw_flux);
+  cudaFree(m->sup.sws); cudaFree(m->sup.old_inwater); cudaFree(m->sup.delta); cudaFree(m->sup.any_neg);
   cudaFree(m->end.preWLRsub); cudaFree(m->end.preWLR); cudaFree(m->end.preWLLsub); cudaFree(m->end.preOrg); cudaFree(m->end.ctR); cudaFree(m->d_ct1);
   cudaFree(m->dm.d_efT); cudaFree(m->dm.d_efST); cudaFree(m->dm.d_cpd);
   cudaFree(m->dm.h_lq); cudaFree(m->dm.h_lqb); cudaFree(m->dm.h_rq); cudaFree(m->dm.h_rqb);
@@ -1608,8 +1650,8 @@ int wf_step_pipelined(wf_model *m, int nsteps, float *gauge_out, float mv, int a
   if (m->cfg.model_snow && !m->pipe_has[2]) return fail(WF_EINVAL, "pipelined forcing not set: TEMP");
   if (m->dm.task_mask != 7) return fail(WF_EUNSUPPORTED, "WF_LATERAL_TASKS is a development aid of the per-step sweep");
   if (gauge_out && m->pipe_gauges < 0) return fail(WF_EINVAL, "no gauge set registered (wf_pipeline_capture)");
-  if (m->reservoirs.dev.n + m->lakes.dev.n > 0)
-    return fail(WF_EUNSUPPORTED, "reservoirs and lakes need the per-step path (wf_step)");
+  if (m->reservoirs.dev.n + m->lakes.dev.n > 0 || m->mass_wasting || m->abstractions)
+    return fail(WF_EUNSUPPORTED, "reservoirs, lakes, mass wasting and abstractions need the per-step path (wf_step)");
   if (end_outputs_requested(m))
     return fail(WF_EUNSUPPORTED, "the end-of-dynamic() outputs (mass balances, cumulative sums ...) need the per-step path (wf_step)");
   CUDA_OK(cudaSetDevice(m->cfg.device));
@@ -1723,6 +1765,27 @@ int wf_area_create(wf_model *m, const int32_t *idmap) {
   }
   seg.push_back((int32_t)pairs.size());
   a.ncell = (int64_t)pairs.size();
+  {
+    std::vector<int32_t> cb, ce, c0(1, 0);
+    for (size_t b = 0; b + 1 < seg.size(); b++) {
+      for (int32_t p = seg[b]; p < seg[b + 1]; p += WF_AREA_CHUNK) {
+        cb.push_back(p);
+        ce.push_back(std::min<int32_t>(p + WF_AREA_CHUNK, seg[b + 1]));
+      }
+      c0.push_back((int32_t)cb.size());
+    }
+    a.nchunks = (int)cb.size();
+    CUDA_OK(cudaMalloc(&a.d_chunk_beg, sizeof(int32_t) * std::max<size_t>(cb.size(), 1)));
+    CUDA_OK(cudaMalloc(&a.d_chunk_end, sizeof(int32_t) * std::max<size_t>(ce.size(), 1)));
+    CUDA_OK(cudaMalloc(&a.d_id_chunk0, sizeof(int32_t) * c0.size()));
+    CUDA_OK(cudaMalloc(&a.d_partial, sizeof(AreaPartial) * std::max<size_t>(cb.size(), 1)));
+    CUDA_OK(cudaMalloc(&a.d_out, sizeof(float) * std::max<size_t>(a.ids.size(), 1)));
+    if (!cb.empty()) {
+      CUDA_OK(cudaMemcpy(a.d_chunk_beg, cb.data(), sizeof(int32_t) * cb.size(), cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(a.d_chunk_end, ce.data(), sizeof(int32_t) * ce.size(), cudaMemcpyHostToDevice));
+    }
+    CUDA_OK(cudaMemcpy(a.d_id_chunk0, c0.data(), sizeof(int32_t) * c0.size(), cudaMemcpyHostToDevice));
+  }
   CUDA_OK(cudaMalloc(&a.d_perm, sizeof(int32_t) * std::max<size_t>(perm.size(), 1)));
   CUDA_OK(cudaMalloc(&a.d_seg, sizeof(int32_t) * seg.size()));
   if (!perm.empty()) CUDA_OK(cudaMemcpy(a.d_perm, perm.data(), sizeof(int32_t) * perm.size(), cudaMemcpyHostToDevice));
@@ -1753,14 +1816,16 @@ int wf_area_reduce(wf_model *m, int area, const char *field, int op, float *out)
   AreaSet &a = m->areas[(size_t)area];
   const int nids = (int)a.ids.size();
   if (nids == 0) return WF_OK;
-  float *d_out = nullptr;
-  CUDA_OK(cudaMalloc(&d_out, sizeof(float) * nids));
   const bool riv = g_fields[id].kind & K_RIVER;
-  k_area_reduce<<<nids, 256, 0, m->stream>>>(m->dm.f[id], riv ? m->dm.river_slot : nullptr, a.d_perm, a.d_seg, op, d_out);
+  if (a.nchunks > 0) {
+    k_area_partial<<<a.nchunks, 256, 0, m->stream>>>(m->dm.f[id], riv ? m->dm.river_slot : nullptr, a.d_perm, a.d_chunk_beg,
+                                                     a.d_chunk_end, a.d_partial);
+    m->launches++;
+  }
+  k_area_combine<<<(nids + 127) / 128, 128, 0, m->stream>>>(a.d_partial, a.d_id_chunk0, a.d_seg, nids, op, a.d_out);
   m->launches++;
-  CUDA_OK(cudaMemcpyAsync(out, d_out, sizeof(float) * nids, cudaMemcpyDeviceToHost, m->stream));
+  CUDA_OK(cudaMemcpyAsync(out, a.d_out, sizeof(float) * nids, cudaMemcpyDeviceToHost, m->stream));
   CUDA_OK(cudaStreamSynchronize(m->stream));
-  cudaFree(d_out);
   return WF_OK;
 }
 
@@ -1934,6 +1999,42 @@ int wf_lakes_create(wf_model *m, const int32_t *locs, const int32_t *linked, con
   if (int rc2 = ensure_field(m, F_LakeWaterLevel)) return rc2;
   return n;
 }
+
+int wf_set_option(wf_model *m, const char *name, double value) {
+  if (!m || !name) return fail(WF_EINVAL, "null argument");
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  const std::string k(name);
+  if (k == "MassWasting") {
+    if (value != 0.0 && m->cfg.glacier)
+      return fail(WF_EUNSUPPORTED, "MassWasting together with the glacier module is not supported (the glacier reads the wasted pack)");
+    m->mass_wasting = value != 0.0;
+  } else if (k == "Abstractions") {
+    m->abstractions = value != 0.0;
+    if (m->abstractions && !m->sup.sws) {
+      const size_t nr = (size_t)std::max<int32_t>(m->nr, 1);
+      CUDA_OK(cudaMalloc(&m->sup.sws, sizeof(float) * nr));
+      CUDA_OK(cudaMalloc(&m->sup.old_inwater, sizeof(float) * nr));
+      CUDA_OK(cudaMalloc(&m->sup.delta, sizeof(float)));
+      CUDA_OK(cudaMalloc(&m->sup.any_neg, sizeof(int32_t)));
+      CUDA_OK(cudaMemset(m->sup.sws, 0, sizeof(float) * nr));
+      CUDA_OK(cudaMemset(m->sup.old_inwater, 0, sizeof(float) * nr));
+    }
+    m->dm.sup_sws = m->abstractions ? m->sup.sws : nullptr;
+    m->dm.sup_old_inwater = m->abstractions ? m->sup.old_inwater : nullptr;
+    m->dm.sup_any_neg = m->abstractions ? m->sup.any_neg : nullptr;
+    m->end.sws = m->dm.sup_sws;
+  } else if (k == "maxitsupply") {
+    if (value < 1) return fail(WF_EINVAL, "maxitsupply must be >= 1");
+    m->maxitsupply = (int)value;
+  } else if (k == "breakoff") {
+    m->breakoff = value;
+  } else {
+    return fail(WF_EINVAL, "unknown option: " + k);
+  }
+  return WF_OK;
+}
+
+int wf_supply_iterations(const wf_model *m) { return m ? m->last_nrit : 0; }
 
 int wf_set_day_of_year(wf_model *m, int jdoy) {
   if (!m || jdoy < 1 || jdoy > 366) return fail(WF_EINVAL, "day of the year must be 1..366");

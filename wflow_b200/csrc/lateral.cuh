@@ -695,8 +695,29 @@ __device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i
     const float ToCubic = ((LD(xl) * LD(yl)) * 0.001f) / dtf;  // :1998
     float Inwater = ((m.h_inwaterMM[rs] * ToCubic) + qo_toriver_f) + ldx<MODE>(m.h_ssf_tr + rs);
     // self.Inflow: the external map, plus the outflow of the reservoirs / lakes above the cell (:2852, 2883, 3144)
-    if (m.obj_inflow) Inwater = Inwater + __ldg(m.obj_inflow + rs);
-    else if (m.f[F_Inflow]) Inwater = Inwater + m.f[F_Inflow][rs];
+    if (m.obj_inflow || m.f[F_Inflow]) {
+      const float inflow = m.obj_inflow ? __ldg(m.obj_inflow + rs) : m.f[F_Inflow][rs];
+      float take = inflow;
+      if (m.sup_sws) {  // abstractions enabled (some Inflow may be negative): first estimate of the supply, :3131-3146
+        float sws = 0.0f;
+        if (inflow < 0.0f) {
+          // pcr.upstream(TopoLdd, RiverRunoff) of the step before: the river cells draining into this one are solved
+          // for this step ticks later, so their discharge still is the old one here
+          float up = 0.0f;
+          if (rs < m.nrnet) {
+            const int rn = __ldg(m.r_nup + rs);
+            const uint32_t ru = __ldg(m.r_up_start + rs);
+            for (int j = 0; j < rn; j++) up = up + m.f[F_RiverRunoff][ru + j];
+          }
+          sws = fminf(up + Inwater, -1.0f * inflow);
+          if (sws > 0.0f) take = -1.0f * sws;
+        }
+        m.sup_sws[rs] = sws;
+        m.sup_old_inwater[rs] = Inwater;
+        if (inflow < 0.0f) *m.sup_any_neg = 1;
+      }
+      Inwater = Inwater + take;
+    }
     m.h_inwater[rs] = Inwater;
     if (m.f[F_Inwater]) m.f[F_Inwater][rs] = Inwater;
     if (rs >= m.nrnet) {  // river-map cell outside the river network: kin_wave never visits it (zeros)

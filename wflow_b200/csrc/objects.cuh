@@ -11,7 +11,7 @@
 //                      (1: table by day of year, 2: b (H - H0)^e), storage S = A H or an S-H table, linked lakes
 //   k_object_inflow    one thread: outflow of every object added to the inflow of its downstream river cell, in object order
 #pragma once
-#include "kernels.cuh"
+#include "pipeline.cuh"
 
 namespace wf {
 
@@ -247,6 +247,91 @@ __global__ void k_object_inflow(const DevModel m, const ObjectSet o, float *__re
     for (int j = k; j < o.n; j++)
       if (o.down_rs[j] == r) up = up + o.outflow[j];
     inflow[r] = up + inflow[r];
+  }
+}
+
+// ---- snow mass wasting (wflow_sbm.py:2700-2707) -------------------------------------------------------
+// self.Snow = pcr.accucapacitystate(TopoLdd, Snow, MaxFlux): dry snow slides to the cell below, at most MaxFlux per cell
+// (a slope- and pack-dependent fraction of the cell's own pack); what leaves a pit leaves the map.  One more sweep over
+// the levels: one block per group of the storage layout, a block barrier per level, float32 like the map algebra.
+__global__ void k_mass_wasting(const DevModel m, float *__restrict__ flux) {
+  for (int g = blockIdx.x; g < m.ngroups; g += gridDim.x) {
+    const GroupDesc gd = m.groups[g];
+    const uint32_t *lo = m.lev_off + gd.lev_idx;
+    const int nl = m.nlev - gd.lev0;
+    for (int l = 0; l < nl; l++) {
+      const uint32_t b = lo[l], e = lo[l + 1];
+      for (uint32_t i = b + threadIdx.x; i < e; i += blockDim.x) {
+        const float snow = m.f[F_Snow][i];
+        const float frac = fminf(0.5f, m.f[F_landSlope][i] / 5.67f) * fminf(1.0f, snow / 10000.0f);  // 5.67 = tan 80 degrees
+        const float cap = frac * snow;
+        float tot = snow;
+        const int nup = m.topo[i] >> 4;
+        const uint32_t us = m.up_start[i];
+        for (int j = 0; j < nup; j++) tot = tot + flux[us + j];
+        const float out = fminf(tot, cap);
+        flux[i] = out;
+        m.f[F_Snow][i] = tot - out;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---- abstractions: Inflow < 0 (wflow_sbm.py:3131-3146, 3203-3308) ---------------------------------------
+// The demand of a river cell is met from what reaches it: SurfaceWaterSupply = min(upstream(RiverRunoff) + Inwater, -Inflow).
+// The first estimate is made inside the sweep (task_overland); the reference then repeats { new estimate from the routed
+// discharge; kin_wave } until the estimate stops changing.  Its kin_wave calls of the loop are handed the UNCHANGED lateral
+// inflow of the first call and a discharge array that the previous call of the loop has overwritten (:3242-3274, SURVEY.md
+// appendix A.4): the first call of the loop repeats the sweep's result, every further one routes the river once more with
+// the same lateral inflow.  Reproduced as such (k_supply_estimate + k_river_again), not "fixed".
+struct SupplyArgs {
+  float *sws;          // nr  SurfaceWaterSupply
+  float *old_inwater;  // nr  Inwater before the abstraction (self.OldInwater)
+  float *delta;        // 1   max |change of the estimate| (float bits, >= 0)
+  int32_t *any_neg;    // 1   some Inflow < 0
+};
+
+__global__ void k_supply_estimate(const DevModel m, const SupplyArgs a) {
+  const int rs = blockIdx.x * blockDim.x + threadIdx.x;
+  if (rs >= m.nr) return;
+  const float inflow = m.f[F_Inflow][rs];
+  float sws = 0.0f;
+  if (inflow < 0.0f) {
+    // pcr.upstream(TopoLdd, RiverRunoff): the river cells that drain into this one (river order: contiguous run)
+    float up = 0.0f;
+    if (rs < m.nrnet) {
+      const int nup = m.r_nup[rs];
+      const uint32_t us = m.r_up_start[rs];
+      for (int j = 0; j < nup; j++) up = up + m.f[F_RiverRunoff][us + j];
+    }
+    sws = fminf(up + a.old_inwater[rs], -1.0f * inflow);
+  }
+  const float d = fabsf(a.sws[rs] - sws);
+  if (d > 0.0f) atomicMax(reinterpret_cast<int *>(a.delta), __float_as_int(d));
+  a.sws[rs] = sws;
+  if (m.f[F_Inwater]) m.f[F_Inwater][rs] = a.old_inwater[rs] + ((sws > 0.0f) ? -1.0f * sws : inflow);
+}
+
+// the river kinematic wave once more (all sub-steps) from the current discharge, lateral inflow as the sweep left it
+template <int ML>
+__global__ void __launch_bounds__(512, 1) k_river_again(const DevModel m) {
+  for (int g = blockIdx.x; g < m.ngroups; g += gridDim.x) {
+    const GroupDesc gd = m.groups[g];
+    if (gd.rlev0 >= m.nrlev) continue;
+    const uint32_t *ro = m.rlev_off + gd.rlev_idx;
+    const int nrl = m.nrlev - gd.rlev0;
+    for (int v = 0; v < m.itR; v++) {
+      for (int q = 0; q < nrl; q++) {
+        const uint32_t b = ro[q], e = ro[q + 1];
+        for (uint32_t rs = b + threadIdx.x; rs < e; rs += blockDim.x) {
+          RivOps riv;
+          load_riv(m, (int32_t)rs, riv);
+          task_river<WF_CTA>(m, (int32_t)rs, v, riv, 0 WF_PNONE);
+        }
+        __syncthreads();
+      }
+    }
   }
 }
 

@@ -16,6 +16,7 @@ struct EndArgs {
   float *preOrg;     // n    OrgStorage (:2627-2629)
   float *ctR;        // n    catchmenttotal(RainFallPlusMelt)
   const float *ct1;  // n    catchmenttotal(1): upstream cell count incl. the cell itself (static)
+  const float *sws;  // nr   SurfaceWaterSupply of the step (abstractions enabled), else nullptr
   int32_t satwd_valid;  // the SatWaterDepth map holds the end of the previous step (else: derived from zi, like resume())
 };
 
@@ -126,7 +127,7 @@ __global__ void k_end_outputs(const DevModel m, const EndArgs e) {
   }
   if (m.f[F_ExfiltWaterCubic]) m.f[F_ExfiltWaterCubic][i] = m.f[F_ExfiltWater][i] * ToCubic;  // :3128-3129
   if (m.f[F_InfiltExcessCubic]) m.f[F_InfiltExcessCubic][i] = m.f[F_InfiltExcess][i] * ToCubic;
-  OUTF(SurfaceWaterSupply, 0.0f);  // no abstraction on this path (Inflow >= 0, :3138-3140)
+  OUTF(SurfaceWaterSupply, (e.sws && riv) ? e.sws[rs] : 0.0f);  // :3138-3140, 3217-3221
   // cumulative sums, :3487-3504 and :3058
 #define WF_CUM(dst, add)                                    \
   do {                                                      \

@@ -7,19 +7,27 @@
 
 namespace wf {
 
-// One block per id.  Cells of an id are the run perm[seg[b] .. seg[b+1]) of network-order
-// indices (sorted by id at wf_area_create).  Sums accumulate in float64 in a fixed order
-// (thread-strided partials, shuffle tree, then warp partials in order): deterministic.
+// Two passes, both deterministic.  The cells of an id are the run perm[seg[b] .. seg[b+1]) of storage positions (sorted by
+// id at wf_area_create); the runs are cut into chunks of WF_AREA_CHUNK cells, listed in chunk_id / chunk_beg / chunk_end.
+//   k_area_partial  one block per chunk: float64 sum, maximum and minimum of the chunk (thread-strided partials, shuffle
+//                   tree, warp partials in order) -> partial[chunk]
+//   k_area_combine  one thread per id: the chunks of the id in order -> areaaverage / areatotal / areamaximum / areaminimum
+// so a subcatchment of millions of cells is reduced by thousands of blocks instead of one (r1: one block per id).
 // slot != nullptr: `field` is a river-order array; cells without a river slot contribute 0.
-__global__ void __launch_bounds__(256) k_area_reduce(const float *__restrict__ field, const int32_t *__restrict__ slot,
-                                                     const int32_t *__restrict__ perm, const int32_t *__restrict__ seg,
-                                                     int op, float *__restrict__ out) {
+#define WF_AREA_CHUNK 16384
+struct AreaPartial {
+  double sum;
+  float mx, mn;
+};
+__global__ void __launch_bounds__(256) k_area_partial(const float *__restrict__ field, const int32_t *__restrict__ slot,
+                                                      const int32_t *__restrict__ perm, const int32_t *__restrict__ chunk_beg,
+                                                      const int32_t *__restrict__ chunk_end, AreaPartial *__restrict__ partial) {
   const int b = blockIdx.x;
-  const int beg = seg[b], end = seg[b + 1];
+  const int beg = chunk_beg[b], end = chunk_end[b];
   double s = 0.0;
   float mx = -3.402823466e38f, mn = 3.402823466e38f;
   for (int p = beg + threadIdx.x; p < end; p += blockDim.x) {
-    int k = perm[p];
+    const int k = perm[p];
     float v;
     if (slot) {
       const int r = slot[k];
@@ -46,13 +54,28 @@ __global__ void __launch_bounds__(256) k_area_reduce(const float *__restrict__ f
     double t = 0.0;
     float a = smx[0], c = smn[0];
     for (int i = 0; i < 8; i++) { t += ss[i]; a = fmaxf(a, smx[i]); c = fminf(c, smn[i]); }
-    float r;
-    if (op == 0) r = (float)(t / (double)(end - beg));   // areaaverage
-    else if (op == 1) r = (float)t;                      // areatotal
-    else if (op == 2) r = a;                             // areamaximum
-    else r = c;                                          // areaminimum
-    out[b] = r;
+    partial[b].sum = t;
+    partial[b].mx = a;
+    partial[b].mn = c;
   }
+}
+__global__ void k_area_combine(const AreaPartial *__restrict__ partial, const int32_t *__restrict__ id_chunk0,
+                               const int32_t *__restrict__ seg, int nids, int op, float *__restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nids) return;
+  double t = 0.0;
+  float a = -3.402823466e38f, c = 3.402823466e38f;
+  for (int k = id_chunk0[b]; k < id_chunk0[b + 1]; k++) {
+    t += partial[k].sum;
+    a = fmaxf(a, partial[k].mx);
+    c = fminf(c, partial[k].mn);
+  }
+  float r;
+  if (op == 0) r = (float)(t / (double)(seg[b + 1] - seg[b]));  // areaaverage
+  else if (op == 1) r = (float)t;                               // areatotal
+  else if (op == 2) r = a;                                      // areamaximum
+  else r = c;                                                   // areaminimum
+  out[b] = r;
 }
 
 __global__ void k_sample(const float *__restrict__ field, const int32_t *__restrict__ pos, float *__restrict__ out,
