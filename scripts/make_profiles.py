@@ -1,9 +1,11 @@
 """Development aid: turn the ncu reports a gpurun call brought back (gpurun_out/) into the tracked summaries under profiles/.
-usage: python scripts/make_profiles.py"""
+usage: python scripts/make_profiles.py [tag]     (tag of scripts/r2_gpu_run.sh, default r2)"""
 import csv
 import io
+import json
 import os
 import subprocess
+import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles")
@@ -64,30 +66,34 @@ def launches(src, dest, header):
     print("wrote", dest)
 
 
+def traffic(rep, ncell, dest, source):
+    """DRAM bytes per cell and launch of the two hot kernels -> profiles/<dest> (read by bench.py's roofline.traffic)."""
+    raw = list(csv.reader(io.StringIO(ncu("-i", rep, "--page", "raw", "--csv"))))
+    h, units = raw[0], raw[1]
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    out = {}
+    for v in raw[2:]:
+        d = dict(zip(h, v))
+        for key in ("k_vertical", "k_lateral_wave"):
+            if key in d.get("Kernel Name", "") and key not in out:
+                b = sum(float(d[c]) * scale[units[h.index(c)]] for c in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                out[key] = {"bytes_per_cell": b / ncell, "dram_bytes": b, "ms": float(d["gpu__time_duration.sum"]),
+                            "inst_executed": float(d["smsp__inst_executed.sum"]), "kernel": d["Kernel Name"], "source": source}
+    json.dump(out, open(os.path.join(OUT, dest), "w"), indent=1)
+    print("wrote", dest, {k: round(v["bytes_per_cell"], 1) for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    rep = os.path.join(G, "prof_r1_final.ncu-rep")
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
+    rep = os.path.join(G, "prof_%s.ncu-rep" % tag)
     cmd = "python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-single-basin"
-    details(rep, "k_vertical", "r1_vertical_ncu_details.txt",
-            "# ncu --set full --clock-control none --import-source on, one launch of k_vertical (round 1, default bench workload: "
-            "32 basins of 1024^2 = 33.5 M cells)\n# command: %s ; report read with: ncu -i prof_r1_final.ncu-rep --page details" % cmd)
-    details(rep, "k_lateral_wave", "r1_lateral_ncu_details.txt",
-            "# ncu --set full --clock-control none --import-source on, one launch of k_lateral_wave (round 1, default bench workload: "
-            "32 basins of 1024^2 = 33.5 M cells)\n# command: %s ; report read with: ncu -i prof_r1_final.ncu-rep --page details" % cmd)
-    pipe = os.path.join(G, "prof_pipe_full2.ncu-rep")
-    if os.path.isfile(pipe):
-        details(pipe, "k_pipeline", "r1_pipeline_ncu_details.txt",
-                "# ncu --set full --clock-control none --import-source on, one launch of k_pipeline (round 1): 20 timesteps in one launch, "
-                "the default bench shard (32 basins of 1024^2 = 33.5 M cells) swept as one group by the cooperative grid kernel,\n"
-                "# chunks dealt on demand inside a block; development build with 1024 threads per block (64 registers; the default is 768 / 80)\n"
-                "# command: python scripts/pipe_bench.py --basins 32 --modes grid+lib:libwflowsbm_pfh.so --ks 20")
-    old = os.path.join(G, "prof_pipe_grid.ncu-rep")
-    if os.path.isfile(old):
-        details(old, "k_pipeline", "r1_pipeline_static_ncu_details.txt",
-                "# ncu --set full, one launch of k_pipeline BEFORE chunks were dealt on demand (fixed item -> thread map, 3 blocks of 256 threads "
-                "per SM): 8 timesteps, 8 basins of 1024^2; 57 % of the stall cycles at the block barrier ahead of the grid barrier\n"
-                "# command: python scripts/pipe_bench.py --basins 8 --modes grid --ks 8")
-    launches(os.path.join(G, "launches_r1.csv"), "r1_launches_ncu.csv",
-             "# ncu launch list (round 1): %s  (32 basins of 1024^2, default workload)\n"
+    note = ("# ncu --set full --clock-control none --import-source on, one launch of %s (round 2, default bench workload: "
+            "32 basins of 1024^2 = 33.5 M cells)\n# command: " + cmd + " ; report read with: ncu -i prof_" + tag + ".ncu-rep --page details")
+    details(rep, "k_vertical", "r2_vertical_ncu_details.txt", note % "k_vertical")
+    details(rep, "k_lateral_wave", "r2_lateral_ncu_details.txt", note % "k_lateral_wave")
+    traffic(rep, 33554431, "r2_traffic.json",
+            "profiles/r2_*_ncu_details.txt (ncu --set full capture of the default workload, dram__bytes_read.sum + dram__bytes_write.sum per launch; static)")
+    launches(os.path.join(G, "launches_%s.csv" % tag), "r2_launches_ncu.csv",
+             "# ncu launch list (round 2): %s  (32 basins of 1024^2, default workload)\n"
              "# ncu --metrics gpu__time_duration.sum --clock-control none -c 400; per-launch times are cold-cache and serialised: compare SHARES\n"
-             "# (k_gather = uploads of the model's rasters and of the forcing; k_vertical<4;0> + k_lateral_wave<4;3;0> = one timestep:\n"
-             "#  column 4.64-4.73 ms + sweep 7.90-8.05 ms here, 5.02 + 7.88 ms by CUDA events inside bench.py -- share of the step 37 %% / 63 %% vs 39 %% / 61 %%)" % cmd)
+             "# (k_gather = uploads of the model's rasters and of the forcing; k_vertical + k_lateral_wave = one timestep)" % cmd)

@@ -82,3 +82,29 @@ def test_cuda_matches_reference_dynamic(name):
         print("%s: %d outputs x %d steps, worst error/tolerance %.3g (%s)" % (name, len(outs), kw["steps"], worst[0], worst[1]))
     finally:
         mod.close()
+
+
+END_OUTPUTS = ("MassBalKinWaveR", "MassBalKinWaveL", "KinWaveVolumeR", "KinWaveVolumeL", "RiverRunoffMM", "LandRunoffMM",
+               "QCatchmentMM", "RunoffCoeff", "CellStorage", "DeltaStorage", "SatWaterFlux", "SnowCover", "RootStore", "vwcRoot",
+               "CumPrec", "CumEvap", "CumLeakage", "CumSurfaceWater", "vwc_perc_0", "SurfaceWatbal", "watbal")
+
+
+@pytest.mark.parametrize("field", END_OUTPUTS)
+def test_an_output_requested_alone(field):
+    """An ini usually lists ONE of these outputs: every one must pull in what it is formed from by itself (found by the
+    reference's dynamic-vegetation case, whose [summary] asks for QCatchmentMM and nothing else of the end of dynamic())."""
+    g, kw, _, mod = common.load_dyn_case("gash_snow_daily", oracle=False, gpu=True)
+    try:
+        nodes = mod.network()[0]
+        mask = np.zeros(mod.shape, bool)
+        mask.flat[nodes] = True
+        if field in CATCHMENT:
+            mask &= ~_downstream_of_dropped(np.asarray(g["ldd"]), mask)
+        mod.request(field)
+        for f in ("P", "PET", "TEMP"):
+            mod.set(f, g["forcing/0/%s" % f])
+        mod.step()
+        e = common.compare(mod.get(field), g["out/0/%s" % field], mask, 1e-5, ATOL.get(field, 2e-5))
+        assert e <= 1.0, (field, e)
+    finally:
+        mod.close()

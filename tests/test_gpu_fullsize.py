@@ -193,3 +193,69 @@ def test_per_gpu_shard_of_the_16k_grid():
         w = common.compare(big.get(k), last[k], inside, 1e-6, 1e2 if k == "SubsurfaceFlow" else 2e-6)
         assert w <= 1.0, "%s: pipelined launch deviates from the per-step path (error/tolerance %.3g)" % (k, w)
     big.close()
+
+
+def test_outlet_hydrograph_of_a_free_running_basin():
+    """The number a hydrologist asks for: one whole 1024 x 1024 basin of the bench workload run FREE for 240 hourly steps
+    (no re-synchronisation of states with the oracle), discharge at the outlet and at three interior river cells compared
+    with the oracle's step by step, and the volume that left the basin over the run.  Individual cells sit on the
+    reference's float32-ulp discontinuities (tests/test_reference_sensitivity.py), a gauge integrates a million of them."""
+    import bench
+    from oracle import oracle as O
+    from wflow_b200 import core, synth
+    args = _args()
+    n = args.tile
+    nsteps = int(os.environ.get("WF_HYDROGRAPH_STEPS", "240"))
+    ldd, river, sched, static, state, lt = bench.make_model_inputs(args, 0, n, n, core.Schedule)
+    it_l, it_r = bench.it_substeps(args)
+    orc = O.Oracle(ldd, river, timestepsecs=args.timestepsecs, layer_thickness=lt, modelSnow=1, it_kinL=it_l, it_kinR=it_r)
+    for k, v in {**static, **state}.items():
+        orc.set(k, v)
+    O.set_threads(os.cpu_count() or 1)
+    upstream = sched.catchment_total(None)  # (the model takes the schedule over)
+    mod = core.SbmModel(ldd, river, schedule=sched, timestepsecs=args.timestepsecs, layer_thickness=lt, model_snow=1,
+                        it_kin_l=it_l, it_kin_r=it_r)
+    _load(mod, static, state)
+    pit = int(np.flatnonzero(ldd.ravel() == 5)[0])
+    pr = pit // n
+    cells = [pit]
+    for frac in (0.25, 0.5, 0.75):  # the widest river cell of three rows on the way up
+        rr = int(pr * frac)
+        cols = np.flatnonzero(river[rr])
+        up = upstream[rr]
+        cells.append(rr * n + int(cols[np.argmax(up[cols])]))
+    cells = np.array(cells, np.int64)
+    forc = synth.Forcing(n, n, seed=5, timestepsecs=args.timestepsecs, rain_mean=20.0)
+    q_gpu = np.zeros((nsteps, cells.size))
+    q_orc = np.zeros((nsteps, cells.size))
+    for t in range(nsteps):
+        P, PET, T = forc.step(t)
+        for m in (orc, mod):
+            m.set("P", P); m.set("PET", PET); m.set("TEMP", T)
+        orc.step()
+        mod.step()
+        q_gpu[t] = mod.sample("RiverRunoff", cells)
+        q_orc[t] = orc["RiverRunoff"].ravel()[cells]
+    rel = np.abs(q_gpu - q_orc) / np.maximum(np.abs(q_orc), 1e-3)
+    vol_g, vol_o = q_gpu.sum(axis=0) * args.timestepsecs, q_orc.sum(axis=0) * args.timestepsecs
+    vol_rel = np.abs(vol_g - vol_o) / vol_o
+    for j, name in enumerate(("outlet", "1/4", "1/2", "3/4")):
+        print("hydrograph %-6s: Q %.3g..%.3g m3/s over %d free-running steps; rel error median %.2e, p99 %.2e, max %.2e; "
+              "volume %.6e vs %.6e m3 (rel %.2e)" % (name, q_orc[:, j].min(), q_orc[:, j].max(), nsteps, np.median(rel[:, j]),
+                                                     np.quantile(rel[:, j], 0.99), rel[:, j].max(), vol_g[j], vol_o[j], vol_rel[j]))
+    # the state the run ends in, cell by cell: fraction of values outside rel 1e-5 after the free run
+    mask = common.network_mask(orc)
+    out = tot = 0
+    for k in common.state_names(4):
+        atol = 1e3 if k == "SubsurfaceFlow" else 2e-5
+        a, b = mod.get(k)[mask].astype(np.float64), orc[k][mask].astype(np.float64)
+        out += int((np.abs(a - b) > atol + 1e-5 * np.abs(b)).sum())
+        tot += a.size
+    print("end state of the free run: %d of %d values outside rel 1e-5 (%.4f %%)" % (out, tot, 100.0 * out / tot))
+    assert q_orc[:, 0].max() > 1.0
+    # Measured on B200 (round 2, 240 steps): rel error of the discharge median 7e-8, p99 3e-7, max 3.2e-7 at all four cells;
+    # volume over the run rel 1e-8; 0.004 % of the end state's values outside rel 1e-5.  Asserted with a margin of ~10.
+    assert np.median(rel) <= 1e-6 and rel.max() <= 5e-6, (float(np.median(rel)), float(rel.max()))
+    assert vol_rel.max() <= 2e-7, vol_rel
+    assert out / tot < 5e-4
+    mod.close()

@@ -250,6 +250,8 @@ LateralPlan plan_lateral(int64_t n, int64_t D, int64_t nbasins, int sms) {
 template <int ML>
 int launch_lateral(wf_model *m) {
   if (const char *iv = std::getenv("WF_LAT_INTERLEAVE")) m->dm.lat_interleave = std::atoi(iv);  // development aid
+  if (const char *tm = std::getenv("WF_LATERAL_TASKS"))  // development aid: bit0 subsurface, bit1 overland, bit2 river
+    m->dm.task_mask = (m->dm.task_mask & 8) | (std::atoi(tm) & 7);
   if (const char *iv = std::getenv("WF_LAT_PREFETCH"))  // development aid: 0 = no L2 warm-up of the coming ticks' operands
     m->dm.task_mask = std::atoi(iv) ? (m->dm.task_mask & ~8) : (m->dm.task_mask | 8);
   void *args[] = {(void *)&m->dm};
@@ -530,7 +532,7 @@ int launch_step(wf_model *m) {
     }
   }
   if (end_out) {
-    if (m->dm.f[F_QCatchmentMM] || m->dm.f[F_RunoffCoeff]) {
+    if (m->dm.f[F_RunoffCoeff]) {  // (QCatchmentMM alone needs the static upstream cell count only)
       k_catchment_total<<<(unsigned)std::max(1, std::min(m->dm.ngroups, 1024)), 1024, 0, m->stream>>>(m->dm, m->dm.f[F_RainFallPlusMelt], m->end.ctR);
       m->launches++;
     }
@@ -544,14 +546,18 @@ int launch_step(wf_model *m) {
 
 int dispatch_step(wf_model *m) {
   switch (m->ML) {
+#ifndef WF_DEV_ML4
     case 1: return launch_step<1>(m);
     case 2: return launch_step<2>(m);
     case 3: return launch_step<3>(m);
+#endif
     case 4: return launch_step<4>(m);
+#ifndef WF_DEV_ML4
     case 5: return launch_step<5>(m);
     case 6: return launch_step<6>(m);
     case 7: return launch_step<7>(m);
     case 8: return launch_step<8>(m);
+#endif
   }
   return fail(WF_EINVAL, "unsupported number of soil layers");
 }
@@ -648,14 +654,20 @@ int setup_substep_buffers(wf_model *m) {
 
 LateralPlan dispatch_plan(int ML, int64_t n, int64_t D, int64_t nbasins, int sms) {
   switch (ML) {
+#ifndef WF_DEV_ML4
     case 1: return plan_lateral<1>(n, D, nbasins, sms);
     case 2: return plan_lateral<2>(n, D, nbasins, sms);
     case 3: return plan_lateral<3>(n, D, nbasins, sms);
+#endif
     case 4: return plan_lateral<4>(n, D, nbasins, sms);
+#ifndef WF_DEV_ML4
     case 5: return plan_lateral<5>(n, D, nbasins, sms);
     case 6: return plan_lateral<6>(n, D, nbasins, sms);
     case 7: return plan_lateral<7>(n, D, nbasins, sms);
     default: return plan_lateral<8>(n, D, nbasins, sms);
+#else
+    default: return plan_lateral<4>(n, D, nbasins, sms);  // (development build: four layers only)
+#endif
   }
 }
 
@@ -820,14 +832,18 @@ int run_pipeline(wf_model *m, int nsteps) {
 
 int dispatch_pipeline(wf_model *m, int nsteps) {
   switch (m->ML) {
+#ifndef WF_DEV_ML4
     case 1: return run_pipeline<1>(m, nsteps);
     case 2: return run_pipeline<2>(m, nsteps);
     case 3: return run_pipeline<3>(m, nsteps);
+#endif
     case 4: return run_pipeline<4>(m, nsteps);
+#ifndef WF_DEV_ML4
     case 5: return run_pipeline<5>(m, nsteps);
     case 6: return run_pipeline<6>(m, nsteps);
     case 7: return run_pipeline<7>(m, nsteps);
     case 8: return run_pipeline<8>(m, nsteps);
+#endif
   }
   return fail(WF_EINVAL, "unsupported number of soil layers");
 }

@@ -17,6 +17,14 @@
 #pragma once
 #include "kernels.cuh"
 
+// build switches of this file (measured variants)
+#ifndef WF_OVL_TAIL_PREFETCH
+#define WF_OVL_TAIL_PREFETCH 0
+#endif
+#ifndef WF_SSF_INLINE
+#define WF_SSF_INLINE 0
+#endif
+
 namespace wf {
 
 // x^b for x >= 0 as exp(b*log(x)): the two CUDA double routines are each accurate to ~1 ulp, the
@@ -156,7 +164,12 @@ __device__ __noinline__ double kinematic_wave(double Qin, double Qold, double Qo
 // found by a few Halley steps from the previous water table u = -f*zi_old.  The reference loop then
 // needs one or two iterations; exit tests, NaN guard, 1e-30 floor and the returned (stale) zi are the
 // reference's.  exp(-f*zi) inside the loop is the log's own argument x (saves an exp; ~1e-14 rel).
-__device__ __noinline__ void kinematic_wave_ssf(double ssf_in, double ssf_old, double zi_old, double r,
+#if WF_SSF_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+void kinematic_wave_ssf(double ssf_in, double ssf_old, double zi_old, double r,
                                                 double Ks_hor, double Ks, double slope, double neff, double f,
                                                 double D, double efD, double dt, double dx, double w, double ssf_max,
                                                 double &ssf_out, double &zi_out, double &exfilt_out) {
@@ -600,6 +613,15 @@ __device__ __forceinline__ void task_overland(const DevModel &m, const int64_t i
   const int itL = m.itL;
   const double SW = o.SW, AlphaL = o.AlphaL, Beta = m.beta, DLd = o.DL;
   const double dts = qdiv(m.dt, (double)itL);
+#if WF_OVL_TAIL_PREFETCH
+  // What the channel's lateral inflow (behind the solve) reads of a river cell is DRAM-cold: requested now, it arrives
+  // while the wave is solved (nine in ten warps of a level hold a river cell and would wait for it in the tail).
+  if (riverMap) {
+    prefetch_l1(m.f[F_xl] + i); prefetch_l1(m.f[F_yl] + i); prefetch_l1(m.h_inwaterMM + rs);
+    if (m.obj_inflow) prefetch_l1(m.obj_inflow + rs);
+    else if (m.f[F_Inflow]) prefetch_l1(m.f[F_Inflow] + rs);
+  }
+#endif
   const double q = qdiv(ldx<MODE>(m.h_inwO + i), DLd);
   double Qold = o.Qold;
   double QoldBeta = carried_pow(Qold, o.q64, o.qb64, Beta);
