@@ -614,7 +614,10 @@ int setup_sweep(wf_model *m) {
   // a group's level offsets and tick sizes live in shared memory during its sweep when they fit
   dm.lev_cache = 0;
   m->lat_smem = 0;
-  if (most * 4 <= ((m->lat_mode == WF_GRID) ? 40 : 96) * 1024) {
+  // (beside the operand staging columns of the block's threads, lateral.cuh: 227 KB of shared memory per block in all)
+  const size_t lev_room = (m->lat_mode == WF_GRID) ? (size_t)40 * 1024
+                                                   : std::min<size_t>((size_t)96 * 1024, (size_t)226 * 1024 - wf_stage_bytes(m->ML, wf_block_threads(m->lat_mode)));
+  if ((size_t)most * 4 <= lev_room) {
     dm.lev_cache = (int32_t)most;
     m->lat_smem = (size_t)most * 4;
   }
@@ -1080,7 +1083,7 @@ static int create_impl(wf_model *m, const wf_config *cfg, wf_schedule *sched, co
   }
 #endif
   auto upload = [&](const void *src, size_t bytes, void **dst) -> int {
-    CUDA_OK(cudaMalloc(dst, std::max<size_t>(bytes, 16)));
+    CUDA_OK(cudaMalloc(dst, (std::max<size_t>(bytes, 16) + 15) & ~(size_t)15));  // (whole 16-byte rows: the byte arrays are also read by aligned words)
     if (bytes) CUDA_OK(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
     return WF_OK;
   };

@@ -24,6 +24,10 @@
 #ifndef WF_SSF_INLINE
 #define WF_SSF_INLINE 0
 #endif
+#ifndef WF_STAGE_AHEAD
+#define WF_STAGE_AHEAD 1  // 1: the staged sweeps fetch the operands of a thread's NEXT item while it works on the current one
+                          //    (sweep_group_ahead); 0: after the arrival at the tick barrier (sweep_group)
+#endif
 
 namespace wf {
 
@@ -369,10 +373,20 @@ __device__ __forceinline__ void load_riv(const DevModel &m, const int32_t rs, Ri
 // barrier; after the barrier they are a shared-memory read away and the tick's critical path starts with the
 // gather of the neighbours' fresh outflows instead of a DRAM round trip (r1 tick profile: 1.2 us of 7.9).
 // Layout: word w of thread x at sw[w * T + x] (conflict-free), doubles likewise behind the words.
+// Per-thread bytes of one staging column: 16 + 2 ML operand words, the word of the topology byte array that holds the
+// item's upstream count, two words for the item itself (sweep_group_ahead), three float64 operands.
+__host__ __device__ constexpr int wf_stage_words(int ML) { return 16 + 2 * ML + 3; }
+// columns per thread: two where they fit beside the level cache (the next item's operands land while the current
+// item's are still being read); with one, an item's operands move to registers before the next item's are requested
+__host__ __device__ constexpr int wf_stage_nbuf(int ML) { return (WF_STAGE_AHEAD && ML <= 5) ? 2 : 1; }
+__host__ __device__ constexpr size_t wf_stage_bytes(int ML, int threads) {
+  return (size_t)threads * (size_t)wf_stage_nbuf(ML) * (size_t)(wf_stage_words(ML) * 4 + 3 * 8);
+}
 template <int ML>
 struct StageLayout {
-  static constexpr int NW = 16 + 2 * ML, ND = 3;  // 4-byte words, 8-byte words per thread
-  __host__ __device__ static constexpr size_t bytes(int threads) { return (size_t)threads * (NW * 4 + ND * 8); }
+  static constexpr int NW = wf_stage_words(ML), ND = 3, NBUF = wf_stage_nbuf(ML);  // 4-byte words, 8-byte words per thread and column
+  static constexpr int W_TOPO = NW - 3, W_IDX = NW - 2, W_TYPE = NW - 1;
+  __host__ __device__ static constexpr size_t bytes(int threads) { return wf_stage_bytes(ML, threads); }
 };
 __device__ __forceinline__ void cp_async4(void *sdst, const void *gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
@@ -1068,6 +1082,169 @@ __device__ __forceinline__ void sweep_group(const DevModel &m, const GroupDesc g
   }
 }
 
+// The staged sweeps (cluster / single block), software-pipelined over a thread's items.
+//
+// r2 tick profile of sweep_group on the bench shard: a thread's first instructions of a tick waited ~1.1 us for its
+// staged operands.  They were requested behind the thread's arrival at the barrier, and the thread that arrives LAST --
+// the one the tick waits for -- finds the barrier open: its copies had no time to land.  And the items beyond a
+// thread's first of a tick (levels wider than the sweep has threads: every tick of a single-block sweep of several
+// basins) loaded their operands where they were used.  Here every item's operands are requested one whole item
+// earlier: while item k is solved, cp.async brings item k+1's operands (the thread's next item of this tick or its first
+// of the next tick) into the thread's other staging column.  Nothing that is staged is written by another thread
+// during the sweep (statics, the column kernel's hand-offs, the cell's own states), so the early copy reads the same
+// values; what the neighbours produce is read behind the barrier as before.  The item itself (position, type,
+// sub-step) waits in the column too, so it takes no registers while the current item is solved.
+template <int ML, int MODE, bool DIAG>
+__device__ __forceinline__ void sweep_group_ahead(const DevModel &m, const GroupDesc gd, const uint32_t *lo, const uint32_t *ro,
+                                                  const uint32_t *tt, const int tid, const int nthreads, WaveSync &ws, float *stage) {
+  constexpr bool EARLY = wf_is_cluster(MODE);
+  using SL = StageLayout<ML>;
+  constexpr int NW = SL::NW, ND = SL::ND, NBUF = SL::NBUF;
+  const int D = m.nlev, itR = m.itR;
+  const int nl = D - gd.lev0;
+  const bool rivers = gd.rlev0 < m.nrlev && (m.task_mask & 4);
+  const int nrl = rivers ? m.nrlev - gd.rlev0 : 0;
+  const int nticks = gd.nticks;
+  const int q0 = wf_sweep_q0(gd.lev0, m.rlev_shift, gd.rlev0);
+  const int T = (int)blockDim.x, x = (int)threadIdx.x;
+  double *const sdbase = reinterpret_cast<double *>(stage + (size_t)NBUF * NW * T);
+  auto decode_item = [&](int j, int t) -> WaveItem {  // the item space of sweep_group
+    WaveItem it;
+    it.type = -1; it.idx = 0; it.v = 0; it.nup = 0;
+    int cnt0 = 0, cnt1 = 0;
+    const int t1 = t - WF_OVL_LAG;
+    if (t < nl && (m.task_mask & 1)) cnt0 = (int)(lo[t + 1] - lo[t]);
+    if (t1 >= 0 && t1 < nl && (m.task_mask & 2)) cnt1 = (int)(lo[t1 + 1] - lo[t1]);
+    const int c0p = (cnt0 + 31) & ~31, c1p = (cnt1 + 31) & ~31;
+    if (j < c0p) {
+      if (j < cnt0) { it.type = 0; it.idx = lo[t] + (uint32_t)j; }
+    } else if (j < c0p + c1p) {
+      if (j - c0p < cnt1) { it.type = 1; it.idx = lo[t1] + (uint32_t)(j - c0p); }
+    } else if (rivers) {
+      int jj = j - c0p - c1p;
+#pragma unroll 1
+      for (int v = 0; v < itR; v++) {
+        const int q = q0 + t - v;
+        if (q < 0 || q >= nrl) continue;
+        const uint32_t rb = ro[q];
+        const int rc = (int)(ro[q + 1] - rb);
+        if (jj < rc) { it.type = 2; it.v = v; it.idx = rb + (uint32_t)jj; break; }
+        jj -= rc;
+      }
+    }
+    return it;
+  };
+  // request an item's operands into column b (and park the item there)
+  auto stage_item = [&](const WaveItem &it, const int b) {
+    float *const sw = stage + (size_t)b * NW * T;
+    double *const sd = sdbase + (size_t)b * ND * T;
+    reinterpret_cast<uint32_t *>(sw)[SL::W_IDX * T + x] = it.idx;
+    reinterpret_cast<uint32_t *>(sw)[SL::W_TYPE * T + x] = (uint32_t)(it.type & 0xff) | ((uint32_t)it.v << 8);
+    if (it.type == 0) {
+      stage_sub<ML>(m, (int64_t)it.idx, sw, sd, T);
+      cp_async4(sw + SL::W_TOPO * T + x, m.topo + (it.idx & ~3u));
+    } else if (it.type == 1) {
+      stage_ovl(m, (int64_t)it.idx, sw, sd, T);
+      cp_async4(sw + SL::W_TOPO * T + x, m.topo + (it.idx & ~3u));
+    } else if (it.type == 2) {
+      stage_riv(m, (int32_t)it.idx, sw, T);
+      cp_async4(sw + SL::W_TOPO * T + x, m.r_nup + (it.idx & ~3u));
+    }
+  };
+  auto staged_item = [&](const int b) -> WaveItem {
+    const uint32_t *const sw = reinterpret_cast<const uint32_t *>(stage + (size_t)b * NW * T);
+    WaveItem it;
+    it.idx = sw[SL::W_IDX * T + x];
+    const uint32_t tv = sw[SL::W_TYPE * T + x];
+    it.type = (int)(int8_t)(tv & 0xff);
+    it.v = (int)(tv >> 8);
+    it.nup = 0;
+    return it;
+  };
+  // the byte of the item's entry in the staged word of the topology array
+  auto staged_byte = [&](const int b, const uint32_t idx) -> int {
+    const uint32_t w = reinterpret_cast<const uint32_t *>(stage + (size_t)b * NW * T)[SL::W_TOPO * T + x];
+    return (int)((w >> (8 * (idx & 3u))) & 0xffu);
+  };
+  SubOps<ML> sub;
+  OvlOps ovl;
+  RivOps riv;
+  int p = 0;  // column of the current item
+  WaveItem cur;
+  cur.type = -1; cur.idx = 0; cur.v = 0; cur.nup = 0;
+  if (tid < (int)tt[0]) cur = decode_item(tid, 0);
+  stage_item(cur, 0);
+  for (int t = 0; t < nticks; t++) {
+#ifdef WF_PROFILE
+    unsigned long long *pbase = (m.prof && gd.lev_idx == 0) ? m.prof + 16 * (size_t)t : nullptr;
+    const unsigned long long c0 = gtimer();
+    if (pbase && tid == 0) pbase[14] = c0;
+#endif
+    const int total = (int)tt[t];
+    const bool more = t + 1 < nticks;
+    bool arrived = false;
+    if (tid >= total) {
+      // nothing to do this tick: the thread's first item of the next tick and its operands
+      cur.type = -1;
+      if (more && tid < (int)tt[t + 1]) cur = decode_item(tid, t + 1);
+      stage_item(cur, p);
+    }
+    for (int j = tid; j < total; j += nthreads) {
+      // cur = item j of this tick, its operands in (or on their way into) column p
+      WaveItem nx;
+      nx.type = -1; nx.idx = 0; nx.v = 0; nx.nup = 0;
+      if (j + nthreads < total) nx = decode_item(j + nthreads, t);
+      else if (more && tid < (int)tt[t + 1]) nx = decode_item(tid, t + 1);
+      cp_async_wait_all();  // (requested one item ago)
+      const int q = (NBUF == 2) ? (p ^ 1) : p;
+      const float *const sw = stage + (size_t)p * NW * T;
+      const double *const sd = sdbase + (size_t)p * ND * T;
+      if (NBUF == 2) stage_item(nx, q);  // two columns: the next item's copies start now, this item's operands are read where they are used
+      const bool signal = EARLY && more && (j + nthreads >= total);  // the thread's last item of the tick
+      const int type = cur.type;
+      const uint32_t idx = cur.idx;
+      if (type == 0) {
+        unstage_sub<ML>(m, (int64_t)idx, sw, sd, T, sub);
+        sub.nup = staged_byte(p, idx) >> 4;
+        if (NBUF == 1) stage_item(nx, q);  // one column: its operands are in registers now
+        task_subsurface<ML, MODE, DIAG, EARLY>(m, (int64_t)idx, sub, signal WF_PPASS(0));
+        arrived = signal;
+      } else if (type == 1) {
+        unstage_ovl(m, (int64_t)idx, sw, sd, T, ovl);
+        ovl.nup = staged_byte(p, idx) >> 4;
+        if (NBUF == 1) stage_item(nx, q);
+        task_overland<MODE, DIAG, EARLY>(m, (int64_t)idx, ovl, signal WF_PPASS(1));
+        arrived = signal;
+      } else {
+        const int v = cur.v;
+        if (type == 2) {
+          unstage_riv(m, (int32_t)idx, sw, T, riv);
+          riv.nup = staged_byte(p, idx);
+        }
+        if (NBUF == 1) stage_item(nx, q);
+        if (type == 2) task_river<MODE>(m, (int32_t)idx, v, riv, 0 WF_PPASS(2));
+      }
+      cur = staged_item(q);
+      p = q;
+    }
+    if (more) {
+#ifdef WF_PROFILE
+      if (pbase) prof_stamp(pbase + 12, c0, 0);
+#endif
+      if (EARLY) {
+        if (!arrived) wave_arrive_early();
+      } else {
+        wave_arrive<MODE>(ws);
+      }
+      wave_wait<MODE>(ws);
+#ifdef WF_PROFILE
+      if (pbase) prof_stamp(pbase + 13, c0, 0);
+#endif
+    }
+  }
+  cp_async_wait_all();  // (nothing is pending after the last item; the columns are re-used by the cluster's next group)
+}
+
 template <int ML, int MODE, bool DIAG = true>
 __global__ void __launch_bounds__(wf_block_threads(MODE), 1) k_lateral_wave(const DevModel m) {
   extern __shared__ __align__(16) uint32_t s_lev[];
@@ -1108,6 +1285,10 @@ __global__ void __launch_bounds__(wf_block_threads(MODE), 1) k_lateral_wave(cons
       ro = s_lev + nlo;
       tt = s_lev + nlo + nro;
     }
+#if WF_STAGE_AHEAD
+    if (MODE != WF_GRID) sweep_group_ahead<ML, MODE, DIAG>(m, gd, lo, ro, tt, tid, nthreads, ws, stage);
+    else
+#endif
     sweep_group<ML, MODE, DIAG>(m, gd, lo, ro, tt, tid, nthreads, ws, stage);
     // The next group of this cluster touches other cells only, but a thread's early arrival may still be pending:
     // the cluster sweeps close a group with one full barrier so that the next group starts on a fresh phase.
