@@ -12,6 +12,7 @@ from tests import common
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-5
+FREE_RUN_OUTSIDE = 0.05  # free-running trajectories: bound on the fraction of values outside rel 1e-5 (see the test)
 RAIN_MEAN = 8.0
 # absolute floors per quantity [unit of the field]
 ATOL = {"SubsurfaceFlow": 1e3, "CellInFlow": 1e3, "default": 2e-5, "SurfaceWatbal": 5e-4, "InterceptionWatBal": 1e-5}
@@ -86,7 +87,8 @@ def test_free_running_trajectory_stays_with_oracle(kw):
     stats = run_case(32, 32, 30, kw, resync=False)
     tot = sum(v[2] for v in stats.values())
     out = sum(v[1] for v in stats.values())
-    assert out / tot < 0.05, "fraction outside rel 1e-5: %.4f %s" % (out / tot, {k: v for k, v in stats.items() if v[1]})
+    print("free run: %d of %d values outside rel 1e-5 (fraction %.2e)" % (out, tot, out / tot))
+    assert out / tot < FREE_RUN_OUTSIDE, "fraction outside rel 1e-5: %.4f %s" % (out / tot, {k: v for k, v in stats.items() if v[1]})
 
 
 def test_network_matches_oracle_set_dd():
