@@ -80,3 +80,26 @@ def test_area_majority_takes_the_highest_of_tied_values():
     a = np.array([[1, 1, 2, 2], [3, 3, 3, 5], [7, 8, 8, 7]], np.float32)
     ids = np.array([[1, 1, 1, 1], [2, 2, 2, 2], [4, 4, 4, 4]])
     assert list(area_majority(a, ids, [1, 2, 4])) == [2.0, 3.0, 8.0]
+
+
+def test_run_length_steps_and_intervals():
+    """[run] runlengthdetermination (wf_DynamicFramework.py:74-96): 'steps' puts the state time one step before
+    starttime (the Rhine example: 29 steps), 'intervals' at starttime itself (one step fewer, first forcing a step later)."""
+    import configparser
+    import datetime as dt
+    from wflow_b200.framework import WflowSbm
+
+    class Holder:
+        pass
+
+    for mode, steps, first in (("steps", 29, dt.datetime(1995, 1, 31)), ("intervals", 28, dt.datetime(1995, 2, 1))):
+        h = Holder()
+        h.config = configparser.ConfigParser()
+        h.config.optionxform = str
+        h.config.read_string("[run]\nstarttime=1995-01-31 00:00:00\nendtime=1995-02-28 00:00:00\ntimestepsecs=86400\n"
+                             "runlengthdetermination=%s\n[model]\n" % mode)
+        WflowSbm._read_time(h)
+        assert (h.nrTimeSteps, h.datetime_start) == (steps, first)
+    h.config.set("run", "runlengthdetermination", "weeks")
+    with pytest.raises(ValueError):
+        WflowSbm._read_time(h)

@@ -160,7 +160,15 @@ class WflowSbm:
         if st != "None" and et != "None":
             self.datetime_start = _dt.datetime.strptime(st, fmt)
             self.datetime_end = _dt.datetime.strptime(et, fmt)
-            # 'steps' mode: the state time is one step before the first forcing (wf_DynamicFramework.py:1282-1390)
+            # [run] runlengthdetermination (wf_DynamicFramework.py:74-96, 1257): 'steps' (default) -- the state time is one
+            # step before starttime; 'intervals' -- the state time IS starttime, every timestep is the interval that ends
+            # at its forcing, so the run has one step fewer.  datetime_start is the time of the first forcing either way.
+            mode = run("runlengthdetermination", "steps").strip()
+            if mode not in ("steps", "intervals"):
+                raise ValueError("[run] runlengthdetermination = %s (steps or intervals)" % mode)
+            self.runlengthdetermination = mode
+            if mode == "intervals":
+                self.datetime_start += _dt.timedelta(seconds=self.timestepsecs)
             self.nrTimeSteps = int((self.datetime_end - self.datetime_start).total_seconds() // self.timestepsecs) + 1
         else:
             self.datetime_start = _dt.datetime(1990, 1, 1)
@@ -333,8 +341,13 @@ class WflowSbm:
                              layer_thickness=self.layer_thickness, model_snow=self.modelSnow,
                              soil_inf_redu=self.soilInfReduction, transfer_method=self.TransferMethod, ust=self.UST,
                              it_kin_l=it_l, it_kin_r=it_r, device=self.device)
+        active_cells = np.asarray(active, bool) & np.isin(ldd, (1, 2, 3, 4, 5, 6, 7, 8, 9))
         for k, v in self.static.items():
             if k not in ("River", "Beta"):
+                if np.ndim(v) == 2 and np.isnan(v[active_cells]).any():
+                    # the reference's lookups log "Not all catchment cells have a value" (wflow_lib / pcrut readtbl checks)
+                    self.logger.error("Not all catchment cells have a value for %s: %d undefined cells are set to 0"
+                                      % (k, int(np.isnan(v[active_cells]).sum())))
                 self._mod.set(k, np.where(np.isnan(v), F32(0.0), v))
         self._update_parameters(0, initial=True)
         # initial() ends with wf_updateparameters(): the forcing of the first timestep is in place (and can be read
@@ -587,7 +600,14 @@ class WflowSbm:
             if self._estimate_l or self._estimate_r:  # wflow_sbm.py:2911-2923, 3159-3171
                 it_l = self._mod.estimate_iterations("land") if self._estimate_l else self._it_fixed[0]
                 it_r = self._mod.estimate_iterations("river") if self._estimate_r else self._it_fixed[1]
-                self._mod.set_substeps(it_l, it_r)
+                # the library holds sub-step buffers for at most 1024 sub-steps: a Courant estimate beyond that (a fine grid
+                # under a long timestep) is clamped with a warning where the reference would run ever more sub-steps
+                if max(it_l, it_r) > 1024:
+                    self.logger.warning("kinematic-wave sub-steps clamped to 1024 (Courant estimate: land %d, river %d)" % (it_l, it_r))
+                    it_l, it_r = min(it_l, 1024), min(it_r, 1024)
+                if (it_l, it_r) != getattr(self, "_it_now", None):  # (a change re-sizes the sweep: only when it is one)
+                    self._mod.set_substeps(it_l, it_r)
+                    self._it_now = (it_l, it_r)
             self._mod.step()
             self._write_outputs(step)
 
