@@ -235,6 +235,15 @@ int wf_lakes_create(wf_model *m, const int32_t *locs, const int32_t *linked, con
  *                     3203-3308; reproduced with its re-routing quirk).  Off: Inflow is added as it is.
  *   "maxitsupply"  iterations of that loop at most (default 5, :1241);  "breakoff" its stopping change (default 1e-4, :3206) */
 int wf_set_option(wf_model *m, const char *name, double value);
+/* Irrigation areas fed from river intakes (self.nrirri > 0; irrigationdemand wflow/wflow_sbm.py:927-945, :3014-3031, 3314-3328;
+ * idtoid wflow/wflow_lib.py:81-101).  areas / intakes: the IrrigationAreas and IrrigationSurfaceIntakes id maps
+ * (nrow*ncol, <= 0 = none; intakes on river cells).  Every step the demand of an area -- areaaverage(PotTrans -
+ * Transpiration) over it, in m3/s -- becomes the negative Inflow of the intakes with its id (the "Abstractions" option is
+ * switched on), and what the supply iteration gave them, times (1 - DemandReturnFlowFraction), comes back to the area as
+ * IRSupplymm [mm], added to the water available for infiltration in the NEXT step (IRSupplymm is a state: get / set).
+ * Not restated: irrigation return points (IrrigationSurfaceReturn), paddy areas, IrriDemandExternal.
+ * Returns the number of areas, or a negative wf_status. */
+int wf_irrigation_create(wf_model *m, const int32_t *areas, const int32_t *intakes);
 int wf_supply_iterations(const wf_model *m);   /* self.nrit of the last step */
 /* Day of the year (1..366) of the coming steps: column of the lakes' rating tables (wf_supplyJulianDOY). */
 int wf_set_day_of_year(wf_model *m, int jdoy);

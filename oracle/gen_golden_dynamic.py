@@ -58,6 +58,11 @@ CASES = {
     "masswasting_daily": dict(n=24, kind="tiles", tile=12, layer_thickness=(100, 300, 800), steps=5, masswasting=1),
     # abstractions: a negative Inflow at some river cells, met from the river through the supply iteration (:3131-3146, 3203-3308)
     "abstraction_daily": dict(n=24, kind="tiles", tile=12, layer_thickness=(100, 300, 800), steps=5, inflow=-1),
+    # irrigation areas fed from river intakes (wflow_sbm.py:927-945, 3014-3031, 3314-3328): the demand of an area (potential
+    # minus actual transpiration) becomes a negative Inflow at its intakes, the supply iteration meets it from the river, and
+    # what was taken is spread over the area as extra water of the NEXT step (IRSupplymm); an area with two intakes, one
+    # without any and an intake without an area (idtoid's left-over values, wflow_lib.py:81-101)
+    "irrigation_daily": dict(n=24, kind="tiles", tile=12, layer_thickness=(100, 300, 800), steps=6, irrigation=1),
     "abstraction_hourly_substeps": dict(n=24, kind="tiles", tile=12, layer_thickness=(100, 300), dt=3600, kinwaveIters=1,
                                         landTstep=3600, riverTstep=900, steps=5, inflow=-1),
 }
@@ -83,6 +88,7 @@ OUTPUTS = [
     "SatWaterFlux", "sumUstore", "SnowCover", "RootStore", "RootStore_sat", "vwcRoot", "vwc_percRoot", "SurfaceWaterSupply",
     "ExfiltWaterCubic", "InfiltExcessCubic", "SumEvapSat", "SumEvapUstore", "CumOutFlow", "CumActInfilt", "CumCellInFlow",
     "CumPrec", "CumEvap", "CumPotenEvap", "CumInt", "CumLeakage", "CumExfiltWater", "CumSurfaceWater",
+    "IRSupplymm", "IrriDemand", "IrriDemandm3",
     # reservoirs / lakes
     "OutflowSR", "ResPercFull", "ResPrecipSR", "ResEvapSR", "DemandRelease", "LakeOutflow", "LakeVolume", "LakePrecip",
     "LakeEvap", "Inflow",
@@ -197,6 +203,21 @@ def object_inputs(kw, ldd, river, static):
     return cut, res, lak
 
 
+def irrigation_inputs(kw, ldd, river):
+    """(areas, intakes, DemandReturnFlowFraction) of an irrigation case: int32 id rasters (0 = none) and a float32 raster."""
+    n = ldd.shape[0]
+    active = ldd > 0
+    areas, intakes = np.zeros((n, n), np.int32), np.zeros((n, n), np.int32)
+    for k, (r0, c0) in enumerate([(1, 1), (9, 17), (14, 3), (16, 11)]):  # four 5 x 4 blocks
+        areas[r0:r0 + 5, c0:c0 + 4] = k + 1
+    areas[~active] = 0
+    spots = _river_spots(ldd, river, 5, 21)
+    for k, (r, c) in zip([1, 2, 2, 3, 7], spots):  # area 2: two intakes; area 4: none; intake 7: no area
+        intakes[r, c] = k
+    drff = np.full((n, n), 0.25, F32)
+    return areas, intakes, drff
+
+
 def gen_case(name, kw):
     funcs, _ = refload.load()
     n, dt = kw["n"], kw.get("dt", 86400)
@@ -214,6 +235,15 @@ def gen_case(name, kw):
         kinwaveRiverTstep=kw.get("riverTstep", 0), massWasting=kw.get("masswasting", 0))
     forc = synth.Forcing(n, n, seed=5, timestepsecs=dt, rain_mean=kw.get("rain_mean", 20.0))
     data = {"ldd": ldd, "river": river}
+    if kw.get("irrigation"):
+        from . import pcrshim as pcr
+        areas, intakes, drff = irrigation_inputs(kw, ldd, river)
+        m = ref.m
+        idm = lambda a: pcr.numpy2pcr(pcr.Nominal, np.where(a > 0, a, -999).astype(np.float64), -999.0)  # noqa: E731
+        m.IrrigationAreas, m.IrrigationSurfaceIntakes = idm(areas), idm(intakes)
+        m.nrirri = int(areas.max())  # :1637-1638
+        m.DemandReturnFlowFraction = m._map(drff)
+        data["irri/areas"], data["irri/intakes"], data["static/DemandReturnFlowFraction"] = areas, intakes, drff
     if res or lak:
         data["ldd_org"] = ldd_org
         data["static/filter_P_PET"] = ref.get("filter_P_PET")
@@ -257,7 +287,7 @@ def gen_case(name, kw):
             itr = funcs.estimate_iterations_kin_wave(m.RiverRunoffsub, m.Beta, m.AlphaR, m.timestepsecs, m.DCL, m.mv)
             data["it/%d" % t] = np.array([itl, itr], np.int64)
         ref.step(P, PET, T, Inflow=inflow, LAI=lai)
-        if kw.get("inflow", 0) < 0:
+        if kw.get("inflow", 0) < 0 or kw.get("irrigation"):
             data["nrit/%d" % t] = np.array(ref.m.nrit, np.int64)
         for k in outs:
             if ref.has(k):

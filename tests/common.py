@@ -121,10 +121,10 @@ def load_golden_case(name, oracle=True, gpu=False):
 
 # ---- goldens of the reference's whole dynamic() (tests/golden/dyn_*.npz, oracle/gen_golden_dynamic.py) ----
 def golden_dyn_cases(objects=True):
-    """objects=False: without the reservoir / lake / mass-wasting / abstraction cases (the C oracle does not restate those
+    """objects=False: without the reservoir / lake / mass-wasting / abstraction / irrigation cases (the C oracle does not restate those
     optional modules; the CUDA path is checked against the reference's own goldens for them)."""
     names = sorted(os.path.basename(p)[4:-4] for p in glob.glob(os.path.join(GOLD, "dyn_*.npz")))
-    return [n for n in names if objects or not n.startswith(("reservoirs", "lakes", "masswasting", "abstraction"))]
+    return [n for n in names if objects or not n.startswith(("reservoirs", "lakes", "masswasting", "abstraction", "irrigation"))]
 
 
 def dyn_substeps(kw):
@@ -168,6 +168,8 @@ def load_dyn_case(name, oracle=True, gpu=False):
             mod.set_option("MassWasting", 1)
         if kw.get("inflow", 0) < 0:
             mod.set_option("Abstractions", 1)
+        if "irri/areas" in g.files:  # irrigation areas and intakes (:1096-1115, 3014-3031, 3314-3328)
+            assert mod.irrigation_create(g["irri/areas"], g["irri/intakes"]) == len(np.unique(g["irri/areas"][g["irri/areas"] > 0]))
         if "res/locs" in g.files:  # simple reservoirs (wflow_sbm.py:1804-1826, 2822-2852)
             assert mod.reservoirs_create(g["res/locs"], g["res/areas"], g["ldd_org"]) == int((g["res/locs"] > 0).sum())
             mod.set("ReservoirVolume", state["ReservoirVolume"])

@@ -63,6 +63,14 @@ class OracleSbmModel:
     def synchronize(self):
         pass
 
+    def set_option(self, name, value):
+        """[model] options of the optional modules: the oracle restates none of them (a value that switches one on is refused)."""
+        if name in ("MassWasting", "Abstractions") and value:
+            raise NotImplementedError("the CPU oracle does not restate %s" % name)
+
+    def irrigation_create(self, areas, intakes):
+        raise NotImplementedError("the CPU oracle does not restate the irrigation module")
+
     def quick_suspend(self):
         self._saved = {k: v.copy() for k, v in self._o.fields.items()}
 

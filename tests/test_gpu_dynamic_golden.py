@@ -18,7 +18,7 @@ ATOL = {"SubsurfaceFlow": 1e3, "SoilWatbal": 1e-3, "watbal": 1e-3, "SurfaceWatba
 # pcr.catchmenttotal runs over the LDD map, the device over the network set_dd built: they differ downstream of a cell that
 # set_dd's flat-index-0 quirk drops (wflow_funcs.py:88) -- such a cell is not on the device at all
 CATCHMENT = ("QCatchmentMM", "RunoffCoeff")
-OBJECT_FIELDS = ("ReservoirVolume", "OutflowSR", "ResPercFull", "ResPrecipSR", "ResEvapSR", "DemandRelease", "LakeWaterLevel",
+OBJECT_FIELDS = ("IrriDemand", "IrriDemandm3", "ReservoirVolume", "OutflowSR", "ResPercFull", "ResPrecipSR", "ResEvapSR", "DemandRelease", "LakeWaterLevel",
                  "LakeOutflow", "LakeVolume", "LakePrecip", "LakeEvap")
 
 
@@ -53,6 +53,7 @@ def test_cuda_matches_reference_dynamic(name):
                 "Inflow"}                                # likewise: the reference adds the objects' outflow to the map
         outs = [f for f in common.dyn_outputs(g) if f in known and f not in skip]
         states = [f for f in outs if "state0/" + f in g.files and f != "SatWaterDepth"] + ["SatWaterDepth"]  # the map itself, last
+        irrigation = "irri/areas" in g.files  # IRSupplymm is carried from step to step like a state (0 before the first)
         mod.request(*outs)
         cmask = mask & ~_downstream_of_dropped(np.asarray(g["ldd"]), mask)
         worst = (0.0, "")
@@ -63,6 +64,8 @@ def test_cuda_matches_reference_dynamic(name):
                     mod.set(f, g[key])
             for f in states:  # the reference's states of the step before, bit for bit
                 mod.set(f, g["state0/" + f] if t == 0 else g["out/%d/%s" % (t - 1, f)])
+            if irrigation and t > 0:
+                mod.set("IRSupplymm", g["out/%d/IRSupplymm" % (t - 1)])
             if kw.get("courant"):
                 itl, itr = mod.estimate_iterations("land"), mod.estimate_iterations("river")
                 assert (itl, itr) == tuple(int(v) for v in g["it/%d" % t]), (name, t)

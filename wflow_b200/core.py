@@ -242,6 +242,13 @@ class SbmModel:
         l = np.ascontiguousarray(ldd_org, dtype=np.uint8)
         return _lib.check(self._l.wf_reservoirs_create(self._h, a[0].ctypes.data, a[1].ctypes.data, l.ctypes.data))
 
+    def irrigation_create(self, areas, intakes):
+        """Irrigation areas and their river intakes (id rasters IrrigationAreas / IrrigationSurfaceIntakes,
+        wflow_sbm.py:1096-1115, 3014-3031, 3314-3328): the demand of an area becomes the negative Inflow of the intakes
+        with its id, the supply comes back as IRSupplymm in the next step.  Returns the number of areas."""
+        a = [np.ascontiguousarray(x, dtype=np.int32) for x in (areas, intakes)]
+        return _lib.check(self._l.wf_irrigation_create(self._h, a[0].ctypes.data, a[1].ctypes.data))
+
     def lakes_create(self, locs, linked, areas, ldd_org, sh=None, hq=None):
         """Natural lakes: id rasters LakeLocs / LinkedLakeLocs / LakeAreasMap, the original LDD and the curve tables
         sh = {lake id: array[rows, 2] (H, S)}, hq = {lake id: array[rows, 367] (H, Q per day of the year)}."""

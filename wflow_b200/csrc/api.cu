@@ -145,6 +145,8 @@ struct wf_model {
     bool lakes = false;
   };
   Objects reservoirs, lakes;
+  IrrigationSet irri = {};            // irrigation areas and their intakes (wf_irrigation_create)
+  std::vector<void *> irri_owned;
   float *d_obj_inflow = nullptr;      // nr: Inflow map + outflow of the objects above each river cell
   int jdoy = 1;                       // day of the year for the lakes' rating tables (wf_set_day_of_year)
   // options of wf_set_option
@@ -504,6 +506,10 @@ int launch_step(wf_model *m) {
     k_mass_wasting<<<(unsigned)std::max(1, std::min(m->dm.ngroups, 1024)), 1024, 0, m->stream>>>(m->dm, m->d_mw_flux);
     m->launches++;
   }
+  if (m->irri.n > 0) {  // the areas' demand of this step -> Inflow of their intakes (wflow_sbm.py:3014-3031)
+    k_irrigation_demand<<<(unsigned)m->irri.n, 256, 0, m->stream>>>(m->dm, m->irri, m->dm.obj_inflow ? m->d_obj_inflow : nullptr);
+    m->launches++;
+  }
   if (m->timed) cudaEventRecord(e1, m->stream);
   if (int rc = launch_lateral<ML>(m)) return rc;
   m->launches++;
@@ -530,6 +536,10 @@ int launch_step(wf_model *m) {
         if ((double)delta < m->breakoff || k >= m->maxitsupply) break;
       }
     }
+  }
+  if (m->irri.n > 0) {  // what the intakes were given -> extra water of the areas in the next step (:3314-3328)
+    k_irrigation_supply<<<(unsigned)m->irri.n, 256, 0, m->stream>>>(m->dm, m->irri, m->sup.sws);
+    m->launches++;
   }
   if (end_out) {
     if (m->dm.f[F_RunoffCoeff]) {  // (QCatchmentMM alone needs the static upstream cell count only)
@@ -1195,6 +1205,7 @@ void wf_destroy(wf_model *m) {
   for (auto &a : m->areas) { cudaFree(a.d_perm); cudaFree(a.d_seg); cudaFree(a.d_chunk_beg); cudaFree(a.d_chunk_end); cudaFree(a.d_id_chunk0); cudaFree(a.d_partial); cudaFree(a.d_out); }
   for (void *p : m->reservoirs.owned) cudaFree(p);
   for (void *p : m->lakes.owned) cudaFree(p);
+  for (void *p : m->irri_owned) cudaFree(p);
   cudaFree(m->d_obj_inflow); cudaFree(m->d_mw_flux);
   cudaFree(m->sup.sws); cudaFree(m->sup.old_inwater); cudaFree(m->sup.delta); cudaFree(m->sup.any_neg);
   cudaFree(m->end.preWLRsub); cudaFree(m->end.preWLR); cudaFree(m->end.preWLLsub); cudaFree(m->end.preOrg); cudaFree(m->end.ctR); cudaFree(m->d_ct1);
@@ -1669,8 +1680,8 @@ int wf_step_pipelined(wf_model *m, int nsteps, float *gauge_out, float mv, int a
   if (m->cfg.model_snow && !m->pipe_has[2]) return fail(WF_EINVAL, "pipelined forcing not set: TEMP");
   if (m->dm.task_mask != 7) return fail(WF_EUNSUPPORTED, "WF_LATERAL_TASKS is a development aid of the per-step sweep");
   if (gauge_out && m->pipe_gauges < 0) return fail(WF_EINVAL, "no gauge set registered (wf_pipeline_capture)");
-  if (m->reservoirs.dev.n + m->lakes.dev.n > 0 || m->mass_wasting || m->abstractions)
-    return fail(WF_EUNSUPPORTED, "reservoirs, lakes, mass wasting and abstractions need the per-step path (wf_step)");
+  if (m->reservoirs.dev.n + m->lakes.dev.n > 0 || m->mass_wasting || m->abstractions || m->irri.n > 0)
+    return fail(WF_EUNSUPPORTED, "reservoirs, lakes, mass wasting, abstractions and irrigation need the per-step path (wf_step)");
   if (end_outputs_requested(m))
     return fail(WF_EUNSUPPORTED, "the end-of-dynamic() outputs (mass balances, cumulative sums ...) need the per-step path (wf_step)");
   CUDA_OK(cudaSetDevice(m->cfg.device));
@@ -2016,6 +2027,78 @@ int wf_lakes_create(wf_model *m, const int32_t *locs, const int32_t *linked, con
   if ((rc = up(hq_off.data(), sizeof(int32_t) * hq_off.size(), (const void **)&ob.dev.hq_off))) return rc;
   ob.lakes = true;
   if (int rc2 = ensure_field(m, F_LakeWaterLevel)) return rc2;
+  return n;
+}
+
+int wf_irrigation_create(wf_model *m, const int32_t *areas, const int32_t *intakes) {
+  if (!m || !areas || !intakes) return fail(WF_EINVAL, "null argument");
+  CUDA_OK(cudaSetDevice(m->cfg.device));
+  CUDA_OK(cudaStreamSynchronize(m->stream));
+  for (void *p : m->irri_owned) cudaFree(p);
+  m->irri_owned.clear();
+  m->irri = IrrigationSet();
+  const int64_t N = (int64_t)m->cfg.nrow * m->cfg.ncol;
+  // areas: the ids present on network cells, ascending (np.unique of idtoid); cells of an area in raster order
+  std::vector<int32_t> ids;
+  for (int64_t fl = 0; fl < N; fl++)
+    if (areas[fl] > 0 && m->pos_of_flat[(size_t)fl] >= 0) ids.push_back(areas[fl]);
+  std::sort(ids.begin(), ids.end());
+  ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+  const int n = (int)ids.size();
+  if (n == 0) return 0;
+  if (m->nr <= 0) return fail(WF_EINVAL, "irrigation areas need a river to take their water from");
+  auto area_of = [&](int32_t id) -> int {
+    const auto it = std::lower_bound(ids.begin(), ids.end(), id);
+    return (it != ids.end() && *it == id) ? (int)(it - ids.begin()) : -1;
+  };
+  std::vector<std::vector<int32_t>> cells((size_t)n), in_rs((size_t)n), in_pos((size_t)n);
+  std::vector<int32_t> orphan_rs, orphan_id;
+  for (int64_t fl = 0; fl < N; fl++) {
+    const int32_t p = m->pos_of_flat[(size_t)fl];
+    if (p < 0) continue;
+    if (areas[fl] > 0) cells[(size_t)area_of(areas[fl])].push_back(p);
+    if (intakes[fl] > 0) {
+      const int32_t rs = m->river_slot[(size_t)p];
+      if (rs < 0) return fail(WF_EINVAL, "an irrigation intake lies outside the river");
+      const int a = area_of(intakes[fl]);
+      if (a >= 0) { in_rs[(size_t)a].push_back(rs); in_pos[(size_t)a].push_back(p); }
+      else { orphan_rs.push_back(rs); orphan_id.push_back(intakes[fl]); }
+    }
+  }
+  std::vector<int32_t> seg(1, 0), perm, iseg(1, 0), irs, ipos;
+  for (int a = 0; a < n; a++) {
+    perm.insert(perm.end(), cells[(size_t)a].begin(), cells[(size_t)a].end());
+    seg.push_back((int32_t)perm.size());
+    irs.insert(irs.end(), in_rs[(size_t)a].begin(), in_rs[(size_t)a].end());
+    ipos.insert(ipos.end(), in_pos[(size_t)a].begin(), in_pos[(size_t)a].end());
+    iseg.push_back((int32_t)irs.size());
+  }
+  auto up = [&](const void *src, size_t bytes, const void **dst) -> int {
+    void *d = nullptr;
+    CUDA_OK(cudaMalloc(&d, std::max<size_t>(bytes, 16)));
+    if (bytes) CUDA_OK(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+    m->irri_owned.push_back(d);
+    *dst = d;
+    return WF_OK;
+  };
+  int rc;
+  IrrigationSet &s = m->irri;
+  if ((rc = up(ids.data(), sizeof(int32_t) * ids.size(), (const void **)&s.id))) return rc;
+  if ((rc = up(seg.data(), sizeof(int32_t) * seg.size(), (const void **)&s.seg))) return rc;
+  if ((rc = up(perm.data(), sizeof(int32_t) * perm.size(), (const void **)&s.perm))) return rc;
+  if ((rc = up(iseg.data(), sizeof(int32_t) * iseg.size(), (const void **)&s.in_seg))) return rc;
+  if ((rc = up(irs.data(), sizeof(int32_t) * irs.size(), (const void **)&s.in_rs))) return rc;
+  if ((rc = up(ipos.data(), sizeof(int32_t) * ipos.size(), (const void **)&s.in_pos))) return rc;
+  if ((rc = up(orphan_rs.data(), sizeof(int32_t) * orphan_rs.size(), (const void **)&s.orphan_rs))) return rc;
+  if ((rc = up(orphan_id.data(), sizeof(int32_t) * orphan_id.size(), (const void **)&s.orphan_id))) return rc;
+  std::vector<float> z((size_t)n, 0.0f);
+  if ((rc = up(z.data(), sizeof(float) * z.size(), (const void **)&s.sqm))) return rc;
+  s.n_orphan = (int32_t)orphan_rs.size();
+  // the demand is an abstraction; its inputs are outputs of the column
+  for (int id : {F_Inflow, F_IRSupplymm, F_PotTrans, F_Transpiration})
+    if ((rc = ensure_field(m, id))) return rc;
+  if ((rc = wf_set_option(m, "Abstractions", 1.0))) return rc;
+  s.n = n;  // (last: the step launches the irrigation kernels from here on)
   return n;
 }
 

@@ -36,7 +36,7 @@ enum FieldKind : int { K_FORCING = 0, K_STATIC = 1, K_STATE = 2, K_DIAG = 3, K_R
   X(filter_P_PET, K_STATIC) X(ResSimpleArea, K_STATIC) X(ResMaxVolume, K_STATIC) X(ResTargetFullFrac, K_STATIC)     \
   X(ResMaxRelease, K_STATIC) X(ResDemand, K_STATIC) X(ResTargetMinFrac, K_STATIC)                  \
   X(LakeArea, K_STATIC) X(LakeThreshold, K_STATIC) X(LakeStorFunc, K_STATIC) X(LakeOutflowFunc, K_STATIC)          \
-  X(Lake_b, K_STATIC) X(Lake_e, K_STATIC)                                                          \
+  X(Lake_b, K_STATIC) X(Lake_e, K_STATIC) X(DemandReturnFlowFraction, K_STATIC)                    \
   /* dynamic vegetation (wflow_sbm.py:2587-2603): present when LAI is */                           \
   X(LAI, K_STATIC) X(Sl, K_STATIC) X(Swood, K_STATIC) X(Kext, K_STATIC)                            \
   /* states (stateVariables(), wflow_sbm.py:955-1010; zi is the live saturated-zone state) */      \
@@ -50,6 +50,8 @@ enum FieldKind : int { K_FORCING = 0, K_STATIC = 1, K_STATE = 2, K_DIAG = 3, K_R
   X(RiverRunoff, K_STATE | K_RIVER) X(RiverRunoffsub, K_STATE | K_RIVER)                           \
   X(WaterLevelR, K_STATE | K_RIVER) X(WaterLevelRsub, K_STATE | K_RIVER)                           \
   X(GlacierStore, K_STATE) X(ReservoirVolume, K_STATE) X(LakeWaterLevel, K_STATE)                  \
+  /* irrigation (wflow_sbm.py:2034, 2755, 3314-3328): the supply of a step is extra water of the next one */ \
+  X(IRSupplymm, K_STATE)                                                                           \
   /* diagnostics, materialised only on request */                                                  \
   X(SatWaterDepth, K_DIAG) X(Precipitation, K_DIAG) X(PotenEvap, K_DIAG) X(Temperature, K_DIAG)    \
   X(ThroughFall, K_DIAG) X(StemFlow, K_DIAG) X(Interception, K_DIAG) X(PotTransSoil, K_DIAG)       \
@@ -86,7 +88,7 @@ enum FieldKind : int { K_FORCING = 0, K_STATIC = 1, K_STATE = 2, K_DIAG = 3, K_R
   X(CumExfiltWater, K_DIAG) X(CumSurfaceWater, K_DIAG)                                             \
   X(OutflowSR, K_DIAG) X(ResPercFull, K_DIAG) X(ResPrecipSR, K_DIAG) X(ResEvapSR, K_DIAG)          \
   X(DemandRelease, K_DIAG) X(LakeOutflow, K_DIAG) X(LakeVolume, K_DIAG) X(LakePrecip, K_DIAG)      \
-  X(LakeEvap, K_DIAG)
+  X(LakeEvap, K_DIAG) X(IrriDemand, K_DIAG) X(IrriDemandm3, K_DIAG)
 
 enum FieldId : int {
 #define X(n, k) F_##n,

@@ -278,6 +278,128 @@ __global__ void k_mass_wasting(const DevModel m, float *__restrict__ flux) {
   }
 }
 
+// ---- irrigation areas (irrigationdemand, wflow_sbm.py:927-945; :3014-3031, 3314-3328; idtoid, wflow_lib.py:81-101) ---------
+// An irrigation area asks for what its crops lacked this step: IrriDemand = areaaverage(PotTrans - Transpiration) [mm],
+// IrriDemandm3 = IrriDemand * areatotal(xl * yl) / 1000 / timestepsecs [m3/s].  idtoid hands that figure to the river cells of the
+// intake map that carry the area's id, as a NEGATIVE Inflow -- from there on it is an abstraction like any other (the
+// overland task's first estimate, the supply iteration above).  What the intakes of an area were given,
+// SurfaceWaterSupply * (1 - DemandReturnFlowFraction), averaged over them (np.mean of float32 values, in raster order),
+// is spread over the area as IRSupplymm = supply / (area / 1000 / timestepsecs) [mm], which the NEXT step's column adds
+// to the water available for infiltration.  idtoid's left-over values are the reference's and kept: an intake whose
+// id is no area's asks for its own id in m3/s, an area without an intake is "supplied" its own id.
+// All REAL4 map algebra: float32, operation by operation; the area sums in float64 like the area statistics.
+struct IrrigationSet {
+  int32_t n;                 // areas, ascending id
+  const int32_t *id;         // n    id of the area
+  const int32_t *seg;        // n+1  offsets into perm
+  const int32_t *perm;       //      storage positions of the cells of each area
+  const int32_t *in_seg;     // n+1  offsets into in_rs / in_pos: the intakes of each area, raster order
+  const int32_t *in_rs;      //      river slot of the intake cell
+  const int32_t *in_pos;     //      storage position of the intake cell
+  int32_t n_orphan;          // intakes whose id is no area's
+  const int32_t *orphan_rs;
+  const int32_t *orphan_id;
+  float *sqm;                // n    areatotal(xl * yl) of the step
+};
+
+// block-wide sum of float64 partials in a fixed order (thread-strided partials, then a tree over the threads)
+__device__ __forceinline__ double irri_block_sum(double v, double *sh) {
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  const double r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+// after the column, ahead of the sweep: the demand of every area becomes the (negative) Inflow of its intakes
+__global__ void __launch_bounds__(256) k_irrigation_demand(const DevModel m, const IrrigationSet s, float *obj_inflow) {
+  __shared__ double sh[256];
+  const int a = blockIdx.x;
+  const int beg = s.seg[a], end = s.seg[a + 1];
+  double se = 0.0, sa = 0.0;
+  for (int p = beg + threadIdx.x; p < end; p += blockDim.x) {
+    const int i = s.perm[p];
+    se += (double)(m.f[F_PotTrans][i] - m.f[F_Transpiration][i]);
+    sa += (double)(m.f[F_xl][i] * m.f[F_yl][i]);
+  }
+  se = irri_block_sum(se, sh);
+  sa = irri_block_sum(sa, sh);
+  const int cnt = end - beg;
+  const float et = (cnt > 0) ? (float)(se / (double)cnt) : 0.0f;   // pcr.areaaverage
+  const float sqm = (float)sa;                                     // pcr.areatotal
+  const float m3 = ((et * sqm) / 1000.0f) / (float)m.dt;           // :942
+  for (int p = beg + threadIdx.x; p < end; p += blockDim.x) {
+    const int i = s.perm[p];
+    if (m.f[F_IrriDemand]) m.f[F_IrriDemand][i] = et;
+    if (m.f[F_IrriDemandm3]) m.f[F_IrriDemandm3][i] = m3;
+  }
+  if (threadIdx.x == 0) {
+    s.sqm[a] = sqm;
+    // idtoid(IrrigationAreas, IrrigationSurfaceIntakes, IrriDemandm3) * -1: the mean over the area of a uniform value
+    // (np.mean in float32 may differ from the value in its last bit; not reproduced)
+    const float v = m3 * -1.0f;
+    for (int k = s.in_seg[a]; k < s.in_seg[a + 1]; k++) {
+      const int rs = s.in_rs[k];
+      m.f[F_Inflow][rs] = v;
+      if (obj_inflow) obj_inflow[rs] = v;
+    }
+    if (a == 0)
+      for (int k = 0; k < s.n_orphan; k++) {  // an intake without an area keeps idtoid's initial value: its own id
+        const float v0 = (float)s.orphan_id[k] * -1.0f;
+        m.f[F_Inflow][s.orphan_rs[k]] = v0;
+        if (obj_inflow) obj_inflow[s.orphan_rs[k]] = v0;
+      }
+  }
+}
+
+// np.mean of k float32 values (numpy's pairwise sum: sequential below 8 values, eight partial sums up to 128)
+__device__ __forceinline__ float irri_np_mean(const float *v, int k) {
+  float res;
+  if (k < 8) {
+    res = -0.0f;
+    for (int i = 0; i < k; i++) res = res + v[i];
+  } else {
+    float r[8];
+    for (int j = 0; j < 8; j++) r[j] = v[j];
+    int i = 8;
+    for (; i < k - (k % 8); i += 8)
+      for (int j = 0; j < 8; j++) r[j] = r[j] + v[i + j];
+    res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < k; i++) res = res + v[i];
+  }
+  return res / (float)k;
+}
+
+// after the supply iteration: what the intakes were given, spread over their areas for the next step
+__global__ void __launch_bounds__(256) k_irrigation_supply(const DevModel m, const IrrigationSet s, const float *sws) {
+  __shared__ float sv;
+  const int a = blockIdx.x;
+  if (threadIdx.x == 0) {
+    const int kb = s.in_seg[a], k = s.in_seg[a + 1] - kb;
+    float val;
+    if (k == 0) {
+      val = (float)s.id[a];  // idtoid: no source point with this id, the area keeps its id as the value
+    } else {
+      float tmp[128];
+      const int kk = k < 128 ? k : 128;  // (more than 128 intakes of one area: the first 128)
+      for (int j = 0; j < kk; j++) {
+        const float drf = m.f[F_DemandReturnFlowFraction] ? m.f[F_DemandReturnFlowFraction][s.in_pos[kb + j]] : 0.0f;
+        tmp[j] = sws[s.in_rs[kb + j]] * (1.0f - drf);  // :3320
+      }
+      val = irri_np_mean(tmp, kk);
+    }
+    // numpy2pcr(Scalar, ., 0.0): a value of exactly 0 is missing, covered with 0 (:3326-3328)
+    sv = (val == 0.0f) ? 0.0f : val / ((s.sqm[a] / 1000.0f) / (float)m.dt);
+  }
+  __syncthreads();
+  const float out = sv;
+  for (int p = s.seg[a] + threadIdx.x; p < s.seg[a + 1]; p += blockDim.x) m.f[F_IRSupplymm][s.perm[p]] = out;
+}
+
 // ---- abstractions: Inflow < 0 (wflow_sbm.py:3131-3146, 3203-3308) ---------------------------------------
 // The demand of a river cell is met from what reaches it: SurfaceWaterSupply = min(upstream(RiverRunoff) + Inwater, -Inflow).
 // The first estimate is made inside the sweep (task_overland); the reference then repeats { new estimate from the routed

@@ -349,6 +349,7 @@ class WflowSbm:
                     self.logger.error("Not all catchment cells have a value for %s: %d undefined cells are set to 0"
                                       % (k, int(np.isnan(v[active_cells]).sum())))
                 self._mod.set(k, np.where(np.isnan(v), F32(0.0), v))
+        self._setup_optional_modules(cfg)
         self._update_parameters(0, initial=True)
         # initial() ends with wf_updateparameters(): the forcing of the first timestep is in place (and can be read
         # back through the API) before the first step
@@ -359,6 +360,26 @@ class WflowSbm:
             self._mod.set("TEMP", self._forcing("TEMP", "Temperature", "/inmaps/TEMP", 1, 10.0))
         self._api_values = saved
         self._setup_outputs()
+
+    def _setup_optional_modules(self, cfg):
+        """Modules of dynamic() that the ini or the case's maps switch on (wflow_sbm.py:1241, 1290, 1096-1135, 1636-1641)."""
+        self._mod.set_option("maxitsupply", int(cfg("maxitsupply", "5")))
+        if int(cfg("MassWasting", "0")):
+            self._mod.set_option("MassWasting", 1)
+        ids = lambda name: None if self._staticmap(name) is None else np.nan_to_num(self._staticmap(name), nan=0.0).astype(np.int32)  # noqa: E731
+        paddy = ids("staticmaps/wflow_irrigationpaddyareas.map")
+        if paddy is not None and (paddy > 0).any():
+            raise ValueError("staticmaps/wflow_irrigationpaddyareas.map: paddy irrigation (nrpaddyirri > 0) is not part of this implementation")
+        areas, intakes = ids("staticmaps/wflow_irrigationareas.map"), ids("staticmaps/wflow_irrisurfaceintake.map")
+        if areas is not None and (areas > 0).any():
+            returns = ids("staticmaps/wflow_irrisurfacereturns.map")
+            if returns is not None and (returns > 0).any():
+                raise ValueError("staticmaps/wflow_irrisurfacereturns.map: irrigation return points are not part of this implementation")
+            if intakes is None:
+                intakes = np.zeros(self.shape, np.int32)
+            n = self._mod.irrigation_create(areas, intakes)
+            self._abstractions = True
+            self.logger.info("%d irrigation areas" % n)
 
     # ---- resume / suspend ------------------------------------------------------------------------
     def _state_names(self):
@@ -461,7 +482,8 @@ class WflowSbm:
     _DYNAMIC_TYPES = ("timeseries", "monthlyclim", "dailyclim", "tblmonthlyclim")
     # parameters that are library fields as they stand (no derived static depends on them)
     _DIRECT = ("LAI", "Sl", "Swood", "Kext", "RootingDepth", "Cmax", "CanopyGapFraction", "EoverR", "et_RefToPot",
-               "PathFrac", "rootdistpar", "CapScale", "AirEntryPressure", "MaxLeakage", "WaterFrac", "TempCor")
+               "PathFrac", "rootdistpar", "CapScale", "AirEntryPressure", "MaxLeakage", "WaterFrac", "TempCor",
+               "Inflow", "DemandReturnFlowFraction")
 
     def _read_modelparameters(self):
         """name = stack,type,default,verbose[,lookupmap_1,...]"""
@@ -546,7 +568,12 @@ class WflowSbm:
             if self._par_loaded.get(name) == src:
                 continue
             self._par_loaded[name] = src
-            self._mod.set(name, self._parameter_raster(par, step))
+            a = self._parameter_raster(par, step)
+            if name == "Inflow" and not getattr(self, "_abstractions", False) and float(np.nanmin(a)) < 0.0:
+                # a negative Inflow is an abstraction: met from the river through the supply iteration (wflow_sbm.py:3203-3308)
+                self._mod.set_option("Abstractions", 1)
+                self._abstractions = True
+            self._mod.set(name, a)
 
     def _read_variable_changes(self):
         """[variable_change_once] / [variable_change_timestep]: 'self.X = self.X * c' (wf_DynamicFramework.py:1691-1707)."""
