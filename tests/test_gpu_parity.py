@@ -12,7 +12,8 @@ from tests import common
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-5
-FREE_RUN_OUTSIDE = 0.05  # free-running trajectories: bound on the fraction of values outside rel 1e-5 (see the test)
+FREE_RUN_OUTSIDE = 1e-3  # free-running trajectories: bound on the fraction of values outside rel 1e-5 (measured on B200, round 2:
+                         # 1.5e-5, 5.4e-6 and 0 for the three cases; the bound leaves two orders of magnitude)
 RAIN_MEAN = 8.0
 # absolute floors per quantity [unit of the field]
 ATOL = {"SubsurfaceFlow": 1e3, "CellInFlow": 1e3, "default": 2e-5, "SurfaceWatbal": 5e-4, "InterceptionWatBal": 1e-5}

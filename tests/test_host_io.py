@@ -103,3 +103,11 @@ def test_run_length_steps_and_intervals():
     h.config.set("run", "runlengthdetermination", "weeks")
     with pytest.raises(ValueError):
         WflowSbm._read_time(h)
+
+
+def test_tss_round_trip(tmp_path):
+    from wflow_b200 import fit
+    a = np.array([[1.5, 2.5], [3.0, 1e31], [0.0, 7.25]])
+    fit.write_tss(str(tmp_path / "x.tss"), a)
+    b = fit.read_tss(str(tmp_path / "x.tss"))
+    assert b.shape == (3, 3) and np.array_equal(b[:, 0], [1, 2, 3]) and np.isnan(b[1, 2]) and b[2, 2] == 7.25

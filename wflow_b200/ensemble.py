@@ -110,9 +110,10 @@ class CaseEnsemble:
     ``name`` (a table parameter of initial(): M, KsatVer, N, N_River, SoilThickness ...) of member m before the
     derivations of initial(); forcing and every map the trials share cross PCIe once per step (wf_set_field_tiled).
     ``members`` selects the trials this process holds (parallel.shard_members); results are member-major.
+    ``area`` = (id map under the case, code) limits the factors to the cells that hold the code (wflow_fit's areamap / areacode).
     """
 
-    def __init__(self, case_dir, factors, members=None, inifile="wflow_sbm.ini", run_dir="ensemble", device=0):
+    def __init__(self, case_dir, factors, members=None, inifile="wflow_sbm.ini", run_dir="ensemble", device=0, area=None):
         from . import params
         from .framework import WflowSbm
         F32 = np.float32
@@ -131,12 +132,19 @@ class CaseEnsemble:
         self.ens = SbmEnsemble(ldd, river, M, timestepsecs=fw.timestepsecs, layer_thickness=fw.layer_thickness,
                                model_snow=fw.modelSnow, soil_inf_redu=fw.soilInfReduction, transfer_method=fw.TransferMethod,
                                ust=fw.UST, it_kin_l=it_l, it_kin_r=it_r, device=device)
+        area_mask = None
+        if area is not None:
+            amap = fw._staticmap(area[0], fail=True)
+            area_mask = np.nan_to_num(amap, nan=-1.0).astype(np.int64) == int(area[1])
         # statics: derive per trial, upload what the trials share once
         stat = []
         for m in self.member_ids:
             b = dict(fw._base)
             for n in names:
-                b[n] = (np.asarray(b[n], F32) * F32(np.asarray(factors[n]).reshape(-1)[m])).astype(F32)
+                scaled = (np.asarray(b[n], F32) * F32(np.asarray(factors[n]).reshape(-1)[m])).astype(F32)
+                # area: (file name of an id map under the case, code) -- the factor applies where the map holds the code,
+                # like wflow_fit's multVarWithPar (wflow/wflow_fit.py:186-214)
+                b[n] = scaled if area_mask is None else np.where(area_mask, scaled, np.broadcast_to(np.asarray(b[n], F32), self.shape)).astype(F32)
             stat.append(params.derive_static(b, ldd, river != 0, fw.timestepsecs, cellsize=fw._cellsize, n_layers=fw.maxLayers))
         self.statics = stat
         self.varied = []
