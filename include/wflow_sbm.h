@@ -175,6 +175,9 @@ int wf_pipeline_set_forcing(wf_model *m, const char *name, int step, const float
 int wf_pipeline_forcing_ptr(wf_model *m, const char *name, void **dptr, int64_t *stride);
 int wf_pipeline_capture(wf_model *m, int gauges);
 int wf_step_pipelined(wf_model *m, int nsteps, float *gauge_out, float mv, int async);
+/* How the last wf_step_pipelined ran: 1 = the time-skewed kernel (k_pipeline), 2 = the per-step kernels with the next
+ * timestep's column on the SMs a cluster sweep of several groups leaves idle (same results either way); 0 = none yet. */
+int wf_pipeline_mode(const wf_model *m);
 /* Device time of the kernels of the last wf_step call, milliseconds (CUDA events on the
  * model's stream): [0] vertical column, [1] lateral sweep, [2] whole step. */
 int wf_last_step_ms(wf_model *m, float ms[3]);

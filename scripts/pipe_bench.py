@@ -31,7 +31,7 @@ def main():
     trips = [forc.step(f) for f in range(4)]
     ks = [int(k) for k in args.ks.split(",")]
     for mode in args.modes.split(","):
-        for k in ("WF_LATERAL_MODE", "WF_CLUSTER_SIZE", "WF_CLUSTER_WIDE", "WF_GROUPS"):
+        for k in ("WF_LATERAL_MODE", "WF_CLUSTER_SIZE", "WF_CLUSTER_WIDE", "WF_GROUPS", "WF_PIPE_OVERLAP", "WF_AHEAD_CLUSTERS"):
             os.environ.pop(k, None)
         for kv in mode.split("+"):
             if kv == "default":
@@ -84,7 +84,7 @@ def main():
             e1.record(stream)
             mod.synchronize()
             ms = e0.elapsed_time(e1) / K
-            print("  pipelined K=%d: %.3f ms/step  %.3f G cell-steps/s" % (K, ms, ncell / ms / 1e6), flush=True)
+            print("  multi-step launch (%s) K=%d: %.3f ms/step  %.3f G cell-steps/s" % (mod.pipeline_mode, K, ms, ncell / ms / 1e6), flush=True)
         mod.close()
 
 

@@ -9,12 +9,16 @@ from tests import common
 
 pytestmark = pytest.mark.gpu
 
-ENV_KEYS = ("WF_LATERAL_MODE", "WF_CLUSTER_SIZE", "WF_CLUSTER_WIDE", "WF_GROUPS")
+ENV_KEYS = ("WF_LATERAL_MODE", "WF_CLUSTER_SIZE", "WF_CLUSTER_WIDE", "WF_GROUPS", "WF_PIPE_OVERLAP")
 MODES = {
     "grid": {"WF_LATERAL_MODE": "grid"},
     "cta": {"WF_LATERAL_MODE": "cta"},
     "cluster": {"WF_LATERAL_MODE": "cluster", "WF_CLUSTER_SIZE": "2", "WF_CLUSTER_WIDE": "0"},
     "cluster-wide": {"WF_LATERAL_MODE": "cluster", "WF_CLUSTER_SIZE": "4", "WF_CLUSTER_WIDE": "1"},
+    # cluster sweeps of several groups default to the per-step kernels with the next column on the idle SMs
+    # (lateral.cuh column_ahead); "-skewed": the time-skewed kernel (k_pipeline) under the same plan
+    "cluster-skewed": {"WF_LATERAL_MODE": "cluster", "WF_CLUSTER_SIZE": "2", "WF_CLUSTER_WIDE": "0", "WF_PIPE_OVERLAP": "0"},
+    "cluster-wide-skewed": {"WF_LATERAL_MODE": "cluster", "WF_CLUSTER_SIZE": "4", "WF_CLUSTER_WIDE": "1", "WF_PIPE_OVERLAP": "0"},
 }
 CASES = [
     # (mode, grid, steps, make_pair keywords)
@@ -22,6 +26,9 @@ CASES = [
     ("cta", (48, 64), 7, dict(kind="tiles", tile=16, layer_thickness=(100, 300, 800), dt=3600, itL=2, itR=3)),
     ("cluster", (48, 64), 7, dict(kind="tiles", tile=16, layer_thickness=(100, 300, 800), dt=3600, itL=2, itR=3)),
     ("cluster-wide", (48, 64), 7, dict(kind="tiles", tile=16, layer_thickness=(100, 300, 800), dt=3600, itL=1, itR=4)),
+    ("cluster-skewed", (48, 64), 7, dict(kind="tiles", tile=16, layer_thickness=(100, 300, 800), dt=3600, itL=2, itR=3)),
+    ("cluster-wide-skewed", (48, 64), 7, dict(kind="tiles", tile=16, layer_thickness=(100, 300, 800), dt=3600, itL=1, itR=4)),
+    ("cluster-wide", (96, 128), 6, dict(kind="tiles", tile=32, layer_thickness=(100, 300, 800), dt=3600, itL=1, itR=4, mask_frac=0.1)),
     ("grid", (40, 40), 12, dict(kind="forest", layer_thickness=(), tm=1)),                    # one layer, daily (Gash), Topog transfer
     ("cta", (40, 40), 12, dict(kind="forest", layer_thickness=(100, 300), snow=0, itL=2, itR=2, dt=21600)),
     ("cluster", (64, 64), 5, dict(kind="tiles", tile=32, layer_thickness=(100, 300, 800), glacier=1, mask_frac=0.1)),
@@ -63,7 +70,7 @@ def test_pipelined_steps_are_bit_identical_to_single_steps(monkeypatch, mode, sh
     nrow, ncol = shape
     _, a, ldd, river = common.make_pair(nrow, ncol, oracle=False, **kw)
     _, b, _, _ = common.make_pair(nrow, ncol, oracle=False, **kw)
-    assert a.lateral_plan["mode"] == mode
+    assert a.lateral_plan["mode"] == mode.replace("-skewed", "")
     forc = synth.Forcing(nrow, ncol, seed=5, timestepsecs=kw.get("dt", 86400), rain_mean=12.0)
     states = common.state_names(a.max_layers, kw.get("snow", 1)) + (["GlacierStore"] if kw.get("glacier") else [])
     cells = _gauge_cells(a, river, shape)
@@ -92,6 +99,10 @@ def test_pipelined_steps_are_bit_identical_to_single_steps(monkeypatch, mode, sh
     for k in states:
         np.testing.assert_array_equal(b.get(k), a.get(k), err_msg="%s differs between pipelined and per-step runs" % k)
     np.testing.assert_array_equal(got, want)
+    if mode in ("cluster", "cluster-wide") and a.lateral_plan["groups"] > 1:
+        assert b.pipeline_mode == "ahead"   # several groups under a cluster sweep: per-step kernels + the next column on idle SMs
+    else:
+        assert b.pipeline_mode == "skewed"
     assert np.isfinite(a.get("RiverRunoff")[np.asarray(river) != 0]).all()
     assert float(np.abs(want).max()) > 0.0  # the gauges saw water
     a.close()

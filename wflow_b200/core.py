@@ -273,6 +273,11 @@ class SbmModel:
         _lib.check(self._l.wf_set_option(self._h, name.encode(), float(value)))
 
     @property
+    def pipeline_mode(self):
+        """How the last step_pipelined ran: "skewed" (k_pipeline), "ahead" (per-step kernels, next column on idle SMs) or None."""
+        return {1: "skewed", 2: "ahead"}.get(int(self._l.wf_pipeline_mode(self._h)))
+
+    @property
     def supply_iterations(self):
         return int(self._l.wf_supply_iterations(self._h))
 

@@ -75,6 +75,11 @@ struct wf_model {
   GroupLayout lay, rlay;
   int lat_mode = 0, cluster_size = 1, lat_blocks = 0;  // how the lateral sweep is launched (plan_lateral)
   size_t lat_smem = 0;
+  // the next step's column on the SMs a cluster sweep leaves idle (lateral.cuh column_ahead; built by setup_ahead)
+  int32_t *d_ah_progress = nullptr, *d_ah_queue = nullptr, *d_ah_order = nullptr, *d_ah_need = nullptr, *d_ah_rank = nullptr;
+  int ah_ntiles = 0, ah_tile = 0, ah_extra = 0, ah_nsweep = 0;
+  bool ah_valid = false;
+  int last_multistep = 0;             // how the last wf_step_pipelined ran: 1 time-skewed kernel, 2 per-step sweeps + column ahead
   GroupDesc *d_groups = nullptr;
   uint32_t *d_lev_off = nullptr, *d_rlev_off = nullptr, *d_tick_total = nullptr;
   std::vector<int32_t> river_slot;   // network order -> river order (or -1)
@@ -633,6 +638,7 @@ int setup_sweep(wf_model *m) {
   }
   m->lat_blocks = 0;  // re-derived at the next launch
   m->pipe_blocks = 0;
+  m->ah_valid = false;
   // busiest tick of the whole network (grid sweep: no more blocks than it can use)
   const int D = dm.nlev;
   int64_t best = 1;
@@ -843,19 +849,186 @@ int run_pipeline(wf_model *m, int nsteps) {
   return WF_OK;
 }
 
+// ---- multi-step launch of the per-step kernels with the next step's column on the idle SMs (lateral.cuh, column_ahead) ----
+// Tiles of the column (as many cells as a sweep block has threads) in the order the sweep frees them: a tile whose last
+// cell is on level L of group g is free once the barrier of tick L + 3 + it_kinR of g's sweep has completed
+// (progress >= L + 4 + it_kinR; the last levels of a group when the group is swept).
+template <int ML>
+int setup_ahead(wf_model *m) {
+  if (m->ah_valid) return WF_OK;
+  m->ah_extra = 0;
+  m->ah_valid = true;
+  if (!wf_is_cluster(m->lat_mode) || m->n == 0) return WF_OK;
+  const int threads = wf_block_threads(m->lat_mode);
+  const size_t smem = ((m->lat_smem + 15) & ~(size_t)15) + StageLayout<ML>::bytes(threads);
+  const int res = resident_clusters<ML>(m->lat_mode, m->cluster_size, smem);
+  const int nsweep = std::min(res, m->dm.ngroups);
+  int extra = res - nsweep;
+  if (const char *e = std::getenv("WF_AHEAD_CLUSTERS")) extra = std::min(extra, std::max(0, std::atoi(e)));  // development aid
+  extra = std::min(extra, 8);  // (a handful of clusters is what a sweep of many groups leaves; more would only poll)
+  if (nsweep < m->dm.ngroups || extra < 1) return WF_OK;  // every group needs its own resident cluster beside the workers
+  const int G = m->dm.ngroups, itR = m->dm.itR;
+  const int Dn = (int)m->net.nlevels(), Dr = (int)m->rnet.nlevels();
+  const int64_t n = m->n;
+  const int ntiles = (int)((n + threads - 1) / threads);
+  // group and group-local level of every storage position: groups are consecutive, levels consecutive inside a group
+  std::vector<int32_t> need((size_t)ntiles * 4), order((size_t)ntiles), rank((size_t)ntiles);
+  auto locate = [&](int64_t pos, int &g, int &need_ticks) {
+    g = 0;
+    while (g + 1 < G && (int64_t)m->lay.lev_off[(size_t)m->lay.lev_idx[(size_t)g + 1]] <= pos) g++;
+    const uint32_t *lo = m->lay.lev_off.data() + m->lay.lev_idx[(size_t)g];
+    const int nl = Dn - m->lay.lev0[(size_t)g];
+    int L = (int)(std::upper_bound(lo, lo + nl + 1, (uint32_t)pos) - lo) - 1;
+    L = std::max(0, std::min(L, nl - 1));
+    const bool rivers = m->rlay.lev0[(size_t)g] < Dr;
+    const int nticks = wf_sweep_ticks(nl, rivers, itR);
+    need_ticks = L + 4 + (rivers ? itR : 0);
+    if (need_ticks >= nticks) need_ticks = 0x7fffffff;  // no barrier follows the last tick: free when the group is swept
+  };
+  std::vector<int64_t> key((size_t)ntiles);
+  for (int t = 0; t < ntiles; t++) {
+    const int64_t a = (int64_t)t * threads, b = std::min<int64_t>(n, a + threads) - 1;
+    int g1, n1, g2, n2;
+    locate(b, g2, n2);
+    locate(a, g1, n1);
+    if (g1 == g2) n1 = n2;
+    else n1 = 0x7fffffff;  // the tile holds the last levels of group g1: free when g1 is swept (tiles across more than two
+                           // groups are left to k_vertical_rest, below)
+    need[(size_t)4 * t + 0] = g1; need[(size_t)4 * t + 1] = n1;
+    need[(size_t)4 * t + 2] = g2; need[(size_t)4 * t + 3] = n2;
+    key[(size_t)t] = std::max<int64_t>(n1, n2);
+    order[(size_t)t] = t;
+  }
+  // tiles that span more than two groups are never handed to the workers: they sort beyond the queue
+  int usable = ntiles;
+  for (int t = 0; t < ntiles; t++) {
+    const int64_t a = (int64_t)t * threads, b = std::min<int64_t>(n, a + threads) - 1;
+    int ga, gb, dummy;
+    locate(a, ga, dummy);
+    locate(b, gb, dummy);
+    if (gb - ga > 1) key[(size_t)t] = (int64_t)1 << 40;
+  }
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return key[(size_t)x] < key[(size_t)y]; });
+  while (usable > 0 && key[(size_t)order[(size_t)usable - 1]] >= ((int64_t)1 << 40)) usable--;
+  for (int r = 0; r < ntiles; r++) rank[(size_t)order[(size_t)r]] = r;
+  cudaFree(m->d_ah_progress); cudaFree(m->d_ah_queue); cudaFree(m->d_ah_order); cudaFree(m->d_ah_need); cudaFree(m->d_ah_rank);
+  m->d_ah_progress = m->d_ah_queue = m->d_ah_order = m->d_ah_need = m->d_ah_rank = nullptr;
+  CUDA_OK(cudaMalloc(&m->d_ah_progress, sizeof(int32_t) * (size_t)std::max(G, 1)));
+  CUDA_OK(cudaMalloc(&m->d_ah_queue, sizeof(int32_t) * 4));
+  CUDA_OK(cudaMalloc(&m->d_ah_order, sizeof(int32_t) * (size_t)ntiles));
+  CUDA_OK(cudaMalloc(&m->d_ah_need, sizeof(int32_t) * (size_t)ntiles * 4));
+  CUDA_OK(cudaMalloc(&m->d_ah_rank, sizeof(int32_t) * (size_t)ntiles));
+  CUDA_OK(cudaMemcpy(m->d_ah_order, order.data(), sizeof(int32_t) * (size_t)ntiles, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(m->d_ah_need, need.data(), sizeof(int32_t) * (size_t)ntiles * 4, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(m->d_ah_rank, rank.data(), sizeof(int32_t) * (size_t)ntiles, cudaMemcpyHostToDevice));
+  m->ah_ntiles = usable;
+  m->ah_tile = threads;
+  m->ah_extra = extra;
+  m->ah_nsweep = nsweep;
+  return WF_OK;
+}
+
+template <int ML>
+int run_overlap(wf_model *m, int nsteps) {
+  if (m->n == 0) return WF_OK;
+  cudaEvent_t e0 = m->ev[0], e1 = m->ev[1], e2 = m->ev[2];
+  if (m->tev_used + 3 <= m->tev.size()) {
+    e0 = m->tev[m->tev_used]; e1 = m->tev[m->tev_used + 1]; e2 = m->tev[m->tev_used + 2];
+    m->tev_used += 3;
+    m->tev_extra_steps += nsteps - 1;
+  }
+  float *saved[3] = {m->dm.f[F_P], m->dm.f[F_PET], m->dm.f[F_TEMP]};
+  m->dm.f[F_P] = m->pipe_forc[0];
+  m->dm.f[F_PET] = m->pipe_forc[1];
+  if (m->pipe_has[2]) m->dm.f[F_TEMP] = m->pipe_forc[2];
+  int rc = check_ready(m);
+  if (rc == WF_OK) {
+    if (m->timed) { cudaEventRecord(e0, m->stream); cudaEventRecord(e1, m->stream); }
+    prepare_step<ML>(m);
+    DevModel dmp = m->dm;
+    if (m->pipe_gauges >= 0 && m->cap_n > 0) {
+      dmp.cap_slot = m->d_cap_slot;
+      dmp.cap_out = m->d_cap_out;
+      dmp.cap_n = m->cap_n;
+    }
+    const int threads = wf_block_threads(m->lat_mode);
+    const size_t smem = ((m->lat_smem + 15) & ~(size_t)15) + StageLayout<ML>::bytes(threads);
+    void *fn = (m->lat_mode == WF_CLUSTER_WIDE) ? (void *)k_lateral_wave<ML, WF_CLUSTER_WIDE, false> : (void *)k_lateral_wave<ML, WF_CLUSTER, false>;
+    if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned vblocks = (unsigned)((m->n + WF_VERT_THREADS - 1) / WF_VERT_THREADS);
+    for (int s = 0; s < nsteps && rc == WF_OK; s++) {
+      const int64_t fo = (int64_t)s * m->dm.npad;
+      // the column of step s: what the workers of the sweep before did not take (everything for the first step)
+      k_vertical_rest<ML, false><<<vblocks, WF_VERT_THREADS, 0, m->stream>>>(dmp, fo, m->d_ah_rank, s > 0 ? m->d_ah_queue : nullptr, m->ah_tile, m->ah_ntiles);
+      CUDA_OK(cudaMemsetAsync(m->d_ah_queue, 0, sizeof(int32_t) * 4, m->stream));
+      CUDA_OK(cudaMemsetAsync(m->d_ah_progress, 0, sizeof(int32_t) * (size_t)std::max(m->dm.ngroups, 1), m->stream));
+      DevModel dms = dmp;
+      dms.cap_step = s;
+      dms.any_diag = 0;
+      const bool last = s + 1 == nsteps;
+      dms.ahead.progress = m->d_ah_progress;
+      dms.ahead.queue = m->d_ah_queue;
+      dms.ahead.order = m->d_ah_order;
+      dms.ahead.need = m->d_ah_need;
+      dms.ahead.ntiles = last ? 0 : m->ah_ntiles;  // (the last step's sweep has no next column: its workers leave at once)
+      dms.ahead.tile = m->ah_tile;
+      dms.ahead.nsweep = m->ah_nsweep;
+      dms.ahead.fo = fo + m->dm.npad;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)((m->ah_nsweep + m->ah_extra) * m->cluster_size));
+      cfg.blockDim = dim3((unsigned)threads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = m->stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = (unsigned)m->cluster_size;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      void *args[] = {(void *)&dms};
+      CUDA_OK(cudaLaunchKernelExC(&cfg, fn, args));
+      m->launches += 2;
+    }
+    if (rc == WF_OK) {
+      if (m->timed) cudaEventRecord(e2, m->stream);
+      m->ev_last[0] = e0; m->ev_last[1] = e1; m->ev_last[2] = e2;
+    }
+  }
+  m->dm.f[F_P] = saved[0]; m->dm.f[F_PET] = saved[1]; m->dm.f[F_TEMP] = saved[2];
+  if (rc != WF_OK) return rc;
+  CUDA_OK(cudaGetLastError());
+  return WF_OK;
+}
+
+// Which multi-step launch: the per-step kernels with the next column on the idle SMs where a cluster sweep of several
+// groups leaves SMs idle (there the time-skewed kernel is slower than the per-step path), else k_pipeline.
+// WF_PIPE_OVERLAP = 0 / 1 forces the choice where both are possible (development aid).
+template <int ML>
+int run_multistep(wf_model *m, int nsteps) {
+  if (int rc = setup_ahead<ML>(m)) return rc;
+  bool any_diag = m->dm.h_wb != nullptr;
+  for (int id = 0; id < F_COUNT; id++)
+    if ((g_fields[id].kind & 0xff) == K_DIAG && m->dm.f[id]) any_diag = true;
+  bool overlap = m->ah_extra > 0 && m->dm.ngroups > 1 && !m->dm.f[F_LAI] && !any_diag;
+  if (const char *e = std::getenv("WF_PIPE_OVERLAP")) overlap = overlap && std::atoi(e) != 0;
+  m->last_multistep = overlap ? 2 : 1;
+  return overlap ? run_overlap<ML>(m, nsteps) : run_pipeline<ML>(m, nsteps);
+}
+
 int dispatch_pipeline(wf_model *m, int nsteps) {
   switch (m->ML) {
 #ifndef WF_DEV_ML4
-    case 1: return run_pipeline<1>(m, nsteps);
-    case 2: return run_pipeline<2>(m, nsteps);
-    case 3: return run_pipeline<3>(m, nsteps);
+    case 1: return run_multistep<1>(m, nsteps);
+    case 2: return run_multistep<2>(m, nsteps);
+    case 3: return run_multistep<3>(m, nsteps);
 #endif
-    case 4: return run_pipeline<4>(m, nsteps);
+    case 4: return run_multistep<4>(m, nsteps);
 #ifndef WF_DEV_ML4
-    case 5: return run_pipeline<5>(m, nsteps);
-    case 6: return run_pipeline<6>(m, nsteps);
-    case 7: return run_pipeline<7>(m, nsteps);
-    case 8: return run_pipeline<8>(m, nsteps);
+    case 5: return run_multistep<5>(m, nsteps);
+    case 6: return run_multistep<6>(m, nsteps);
+    case 7: return run_multistep<7>(m, nsteps);
+    case 8: return run_multistep<8>(m, nsteps);
 #endif
   }
   return fail(WF_EINVAL, "unsupported number of soil layers");
@@ -1206,6 +1379,7 @@ void wf_destroy(wf_model *m) {
   for (void *p : m->reservoirs.owned) cudaFree(p);
   for (void *p : m->lakes.owned) cudaFree(p);
   for (void *p : m->irri_owned) cudaFree(p);
+  cudaFree(m->d_ah_progress); cudaFree(m->d_ah_queue); cudaFree(m->d_ah_order); cudaFree(m->d_ah_need); cudaFree(m->d_ah_rank);
   cudaFree(m->d_obj_inflow); cudaFree(m->d_mw_flux);
   cudaFree(m->sup.sws); cudaFree(m->sup.old_inwater); cudaFree(m->sup.delta); cudaFree(m->sup.any_neg);
   cudaFree(m->end.preWLRsub); cudaFree(m->end.preWLR); cudaFree(m->end.preWLLsub); cudaFree(m->end.preOrg); cudaFree(m->end.ctR); cudaFree(m->d_ct1);
@@ -1702,6 +1876,8 @@ int wf_step_pipelined(wf_model *m, int nsteps, float *gauge_out, float mv, int a
   CUDA_OK(cudaGetLastError());
   return WF_OK;
 }
+
+int wf_pipeline_mode(const wf_model *m) { return m ? m->last_multistep : 0; }
 
 int wf_synchronize(wf_model *m) {
   if (!m) return fail(WF_EINVAL, "null model");

@@ -817,7 +817,7 @@ __device__ __forceinline__ void task_river(const DevModel &m, const int32_t rs, 
     m.f[F_RiverRunoff][rs] = rr;
     if (m.cap_slot) {  // pipelined sweep: the step's discharge at a gauge, before the next step overwrites it
       const int32_t g = __ldg(m.cap_slot + rs);
-      if (g >= 0) m.cap_out[(int64_t)step * m.cap_n + g] = rr;
+      if (g >= 0) m.cap_out[(int64_t)(step + m.cap_step) * m.cap_n + g] = rr;
     }
     m.f[F_WaterLevelR][rs] = (float)qdiv(rh, (double)itR);
     m.f[F_WaterLevelRsub][rs] = (float)wl;
@@ -1096,7 +1096,7 @@ __device__ __forceinline__ void sweep_group(const DevModel &m, const GroupDesc g
 // sub-step) waits in the column too, so it takes no registers while the current item is solved.
 template <int ML, int MODE, bool DIAG>
 __device__ __forceinline__ void sweep_group_ahead(const DevModel &m, const GroupDesc gd, const uint32_t *lo, const uint32_t *ro,
-                                                  const uint32_t *tt, const int tid, const int nthreads, WaveSync &ws, float *stage) {
+                                                  const uint32_t *tt, const int tid, const int nthreads, WaveSync &ws, float *stage, int32_t *progress) {
   constexpr bool EARLY = wf_is_cluster(MODE);
   using SL = StageLayout<ML>;
   constexpr int NW = SL::NW, ND = SL::ND, NBUF = SL::NBUF;
@@ -1237,6 +1237,11 @@ __device__ __forceinline__ void sweep_group_ahead(const DevModel &m, const Group
         wave_arrive<MODE>(ws);
       }
       wave_wait<MODE>(ws);
+      // the barrier of tick t has completed: what the tick's tasks stored ahead of their arrival, and the tick before's
+      // behind it, is visible to whoever reads the group's progress with an acquire (column_ahead)
+      // (a relaxed store: the data it announces was fenced by its writers' arrivals, MEMBAR.ALL.GPU ahead of UCGABAR_ARV,
+      //  and this thread has passed the acquiring wait; a release here would put another fence on the tick's critical path)
+      if (progress && tid == 0) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(progress), "r"(t + 1) : "memory");
 #ifdef WF_PROFILE
       if (pbase) prof_stamp(pbase + 13, c0, 0);
 #endif
@@ -1245,8 +1250,52 @@ __device__ __forceinline__ void sweep_group_ahead(const DevModel &m, const Group
   cp_async_wait_all();  // (nothing is pending after the last item; the columns are re-used by the cluster's next group)
 }
 
+// ---- the column of the next timestep on the SMs the sweep leaves idle ---------------------------------------------
+// A cluster sweep holds one cluster per group: 32 groups of 4 blocks are 128 of the 148 SMs, and the column kernel of the
+// next timestep starts when the last group has reached its outlet.  But the column of a cell only needs the cell's OWN
+// lateral tasks of this step to be done -- the wavefront has passed level L once the barrier of tick L + 3 + it_kinR has
+// completed -- so the clusters beyond the groups (as many as fit the GPU beside them) run column tiles of the next
+// timestep meanwhile, in the order the tiles become ready, behind the groups' progress counters.  They take a new tile
+// only while some group is still sweeping; k_vertical_rest does what is left.  Multi-step launches only (between two
+// launches the states would be mid-step): wf_step_pipelined with the per-step sweeps, bit-identical to wf_step.
+template <int ML>
+__device__ __noinline__ void column_ahead(const DevModel &m) {  // (its own function: the sweep's registers are not its business)
+  __shared__ int s_tile;
+  const DevModel::WorkAhead &w = m.ahead;
+  for (;;) {
+    if (threadIdx.x == 0) {
+      int t = -1, done;
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(w.queue + 1) : "memory");
+      if (done < w.nsweep) t = atomicAdd(w.queue, 1);
+      if (t >= w.ntiles) t = -1;
+      if (t >= 0) {
+        const int tile = w.order[t];
+        for (int k = 0; k < 2; k++) {  // the tile's group(s) must have swept past its last level
+          const int32_t *p = w.progress + w.need[4 * tile + 2 * k];
+          const int need = w.need[4 * tile + 2 * k + 1];
+          int have, spins = 0;
+          for (;;) {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(have) : "l"(p) : "memory");
+            if (have >= need) break;
+            __nanosleep(400);
+            if (++spins > (1 << 23)) __trap();  // (seconds: the sweep is not advancing)
+          }
+        }
+        t = tile;
+      }
+      s_tile = t;
+    }
+    __syncthreads();
+    const int tile = s_tile;
+    __syncthreads();
+    if (tile < 0) break;
+    const int64_t i = (int64_t)tile * w.tile + threadIdx.x;
+    if (i < m.n) column_cell<ML, 1, false, false, false>(m, i, nullptr, nullptr, (int)threadIdx.x, w.fo, nullptr);
+  }
+}
+
 template <int ML, int MODE, bool DIAG = true>
-__global__ void __launch_bounds__(wf_block_threads(MODE), 1) k_lateral_wave(const DevModel m) {
+__global__ void __launch_bounds__(wf_block_threads(MODE), 1) k_lateral_wave(const __grid_constant__ DevModel m) {
   extern __shared__ __align__(16) uint32_t s_lev[];
   int crank = 0, csize = 1;
   if (wf_is_cluster(MODE)) {
@@ -1255,8 +1304,16 @@ __global__ void __launch_bounds__(wf_block_threads(MODE), 1) k_lateral_wave(cons
     csize = (int)cl.num_blocks();
   }
   // grid: every block sweeps the one group; otherwise cluster (or block) c takes groups c, c + nclusters, ...
-  const int nclusters = (MODE == WF_GRID) ? 1 : (int)gridDim.x / csize;
+  int nclusters = (MODE == WF_GRID) ? 1 : (int)gridDim.x / csize;
   const int cid = (MODE == WF_GRID) ? 0 : (int)blockIdx.x / csize;
+  const bool ahead = wf_is_cluster(MODE) && !DIAG && m.ahead.queue != nullptr;
+  if (ahead) {
+    if (cid >= m.ahead.nsweep) {  // a cluster beyond the groups: next timestep's column tiles
+      column_ahead<ML>(m);
+      return;
+    }
+    nclusters = m.ahead.nsweep;
+  }
   // Position in the flat item space of a tick.  The item space is type-major ([subsurface | overland | river], the
   // subsurface items the longest), so with block-major positions the first block of a cluster ran nothing but
   // subsurface solves and the last one a few river cells: consecutive item warps are dealt round robin to the blocks
@@ -1286,17 +1343,23 @@ __global__ void __launch_bounds__(wf_block_threads(MODE), 1) k_lateral_wave(cons
       tt = s_lev + nlo + nro;
     }
 #if WF_STAGE_AHEAD
-    if (MODE != WF_GRID) sweep_group_ahead<ML, MODE, DIAG>(m, gd, lo, ro, tt, tid, nthreads, ws, stage);
+    if (MODE != WF_GRID) sweep_group_ahead<ML, MODE, DIAG>(m, gd, lo, ro, tt, tid, nthreads, ws, stage, ahead ? m.ahead.progress + g : nullptr);
     else
 #endif
     sweep_group<ML, MODE, DIAG>(m, gd, lo, ro, tt, tid, nthreads, ws, stage);
     // The next group of this cluster touches other cells only, but a thread's early arrival may still be pending:
     // the cluster sweeps close a group with one full barrier so that the next group starts on a fresh phase.
-    if (wf_is_cluster(MODE) && g + nclusters < m.ngroups) {
+    if (wf_is_cluster(MODE) && (g + nclusters < m.ngroups || ahead)) {
       asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
       asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     }
+    if (ahead && tid == 0)  // everything of the group is stored and released: its column tiles of the next step are free
+      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(m.ahead.progress + g), "r"(0x7fffffff) : "memory");
     if (MODE == WF_GRID) break;
+  }
+  if (ahead && tid == 0) {
+    __threadfence();
+    atomicAdd(m.ahead.queue + 1, 1);  // this cluster has swept its groups
   }
 }
 
