@@ -109,6 +109,22 @@ def kinematic_wave(Qin, Qold, q, alpha, beta, dT, dX):
     return lib().wfo_kinematic_wave(Qin, Qold, q, alpha, beta, dT, dX)
 
 
+def kin_wave(net, Qold, q, Alpha, Beta, DCL, Bw, deltaT, it):
+    """kin_wave (wflow_funcs.py:155-207) over a Network; Qold / q float32 flat arrays (Qold is updated in place like the
+    reference's), Alpha / Beta / DCL / Bw float64.  Returns (acc_flow, Qnew, waterlevel_av, waterlevel), float64 flat."""
+    n = Qold.size
+    assert Qold.dtype == np.float32 and Qold.flags.c_contiguous
+    q = np.ascontiguousarray(q, np.float32)
+    st = [np.ascontiguousarray(a, np.float64) for a in (Alpha, Beta, DCL, Bw)]
+    out = [np.zeros(n, np.float64) for _ in range(4)]
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    rc = lib().wfo_kin_wave(C.byref(net._net), C.c_int64(n), p(Qold), p(q), *[p(a) for a in st], C.c_double(deltaT), C.c_int(int(it)),
+                            *[p(a) for a in out])
+    if rc != 0:
+        raise MemoryError("wfo_kin_wave failed (%d)" % rc)
+    return tuple(out)
+
+
 def kinematic_wave_ssf(*a):
     o = [C.c_double() for _ in range(3)]
     lib().wfo_kinematic_wave_ssf(*[C.c_double(float(x)) for x in a], *[C.byref(x) for x in o])

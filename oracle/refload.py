@@ -78,3 +78,19 @@ def load():
     sbm = _load("wflow.wflow_sbm", os.path.join(REFERENCE_ROOT, "wflow", "wflow_sbm.py"))
     _cache["mods"] = (funcs, sbm)
     return funcs, sbm
+
+
+def load_hbv():
+    """The reference's wflow_hbv module (wflow/wflow_hbv.py), executed where it lies like wflow_sbm above."""
+    if "hbv" in _cache:
+        return _cache["hbv"]
+    load()
+    path = os.path.join(REFERENCE_ROOT, "wflow", "wflow_hbv.py")
+    if not os.path.isfile(path):
+        raise RuntimeError("wflow_hbv.py not present under %s" % REFERENCE_ROOT)
+    spec = importlib.util.spec_from_file_location("wflow.wflow_hbv", path)
+    m = importlib.util.module_from_spec(spec)
+    sys.modules["wflow.wflow_hbv"] = m
+    spec.loader.exec_module(m)
+    _cache["hbv"] = m
+    return m

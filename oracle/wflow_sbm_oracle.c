@@ -1107,3 +1107,43 @@ int wfo_step(const wfo_params *p, const wfo_network *net, const wfo_network *rne
   free(W); free(Ul); free(pre);
   return 0;
 }
+
+/* kin_wave, wflow/wflow_funcs.py:155-207, as a function of its own (wflow_hbv.py:1633-1647 calls it on the full network with
+ * every cell a channel).  Qold: the REAL4 array the caller hands over (pcr2numpy of the SurfaceRunoffsub map), which
+ * kin_wave stores into between sub-steps (:199): the outflow is rounded to float32 there.  q REAL4; Alpha, Beta, DCL, Bw
+ * float64 (the `static` mirror).  Outputs (float64, N values each, untouched outside the network): acc_flow [m3],
+ * Qnew [m3/s], waterlevel_av, waterlevel [m]. */
+int wfo_kin_wave(const wfo_network *net, int64_t N, float *Qold, const float *q, const double *Alpha, const double *Beta,
+                 const double *DCL, const double *Bw, double deltaT, int it, double *acc_flow, double *Qnew_out,
+                 double *wl_av, double *wl) {
+  double *Qnew = (double *)calloc((size_t)N + 1, sizeof(double));
+  double *acc_h = (double *)calloc((size_t)N, sizeof(double));
+  if (!Qnew || !acc_h) { free(Qnew); free(acc_h); return -4; }
+  memset(acc_flow, 0, sizeof(double) * (size_t)N);
+  memset(wl, 0, sizeof(double) * (size_t)N);
+  for (int v = 0; v < it; v++) {
+    memset(Qnew, 0, sizeof(double) * ((size_t)N + 1));
+    for (int64_t lev = 0; lev < net->nlev; lev++) {
+#pragma omp parallel for schedule(dynamic, 16) num_threads(g_threads)
+      for (int64_t kk = net->lev_off[lev]; kk < net->lev_off[lev + 1]; kk++) {
+        const int64_t idx = net->nodes[kk];
+        const int64_t *nbs = net->nodes_up + 8 * kk;
+        double Qin = 0.0;
+        for (int j = 0; j < 8; j++) Qin = Qin + ((nbs[j] < 0) ? 0.0 : Qnew[nbs[j]]);
+        const double qn = wfo_kinematic_wave(Qin, (double)Qold[idx], (double)q[idx], Alpha[idx], Beta[idx], deltaT / it, DCL[idx]);
+        Qnew[idx] = qn;
+        acc_flow[idx] = acc_flow[idx] + qn * (deltaT / it);
+        wl[idx] = (Alpha[idx] * pow(qn, Beta[idx])) / Bw[idx];
+        acc_h[idx] = acc_h[idx] + wl[idx];
+        Qold[idx] = (float)qn;
+      }
+    }
+  }
+  for (int64_t i = 0; i < N; i++) {
+    Qnew_out[i] = Qnew[i];
+    wl_av[i] = acc_h[i] / it;
+  }
+  free(Qnew);
+  free(acc_h);
+  return 0;
+}

@@ -406,3 +406,71 @@ self.RiverRunoff = run.tss
 """ % (start.strftime("%Y-%m-%d %H:%M:%S"), end.strftime("%Y-%m-%d %H:%M:%S"), timestepsecs, model_snow,
        ",".join(str(int(t)) for t in layer_thickness) if layer_thickness else "0"))
     return ldd, river
+
+
+def hbv_case(nrow, ncol, *, kind="tiles", tile=12, seed=3, timestepsecs=86400, mask_frac=0.0, block=4, glacier=0, edge=0):
+    """(ldd, static, state) of a synthetic wflow_hbv case: parameter maps in the ranges of the reference's defaults and
+    the Rhine tables (wflow/wflow_hbv.py:560-900), a spun-up random state (stateVariables, :131-163).  Rate parameters
+    are per timestep like the reference's tables scaled by timestepsecs / basetimestep."""
+    if kind == "pits":
+        ldd = ldd_all_pits(nrow, ncol)
+    elif kind == "tiles":
+        ldd = ldd_basin_tiles(nrow, ncol, tile=tile, seed=7, mask_frac=mask_frac)
+    else:
+        ldd = ldd_random_forest(nrow, ncol, seed=seed)
+    rng = np.random.default_rng(seed)
+    shape = (nrow, ncol)
+    br, bc = (nrow + block - 1) // block, (ncol + block - 1) // block
+    lu = np.kron(rng.integers(0, 6, (br, bc)), np.ones((block, block), np.int64))[:nrow, :ncol]
+    sc = F32(timestepsecs / 86400.0)
+
+    def by_lu(lo, hi, log=False):
+        v = np.exp(rng.uniform(np.log(lo), np.log(hi), 6)) if log else rng.uniform(lo, hi, 6)
+        return v.astype(F32)[lu]
+
+    full = lambda v: np.full(shape, v, F32)  # noqa: E731
+    fc = by_lu(120.0, 400.0)
+    st = {
+        "Pcorr": full(1.0), "RFCF": by_lu(0.9, 1.1), "SFCF": by_lu(0.8, 1.2), "TTI": by_lu(0.5, 2.0), "TT": by_lu(-1.5, 0.5),
+        "Cfmax": (by_lu(2.5, 4.5) * sc).astype(F32), "CFR": full(0.05), "WHC": full(0.1), "ICF": by_lu(0.0, 3.0),
+        "EPF": by_lu(0.0, 0.05), "ECORR": full(1.0), "CEVPF": by_lu(0.8, 1.2), "FieldCapacity": fc,
+        "Treshold": (by_lu(0.4, 0.9) * fc).astype(F32), "BetaSeepage": by_lu(1.0, 4.0), "PERC": (by_lu(0.2, 1.5) * sc).astype(F32),
+        "Cflux": (by_lu(0.0, 2.5) * sc).astype(F32), "KQuickFlow": (by_lu(0.02, 0.15) * sc).astype(F32),
+        "AlphaNL": by_lu(0.3, 1.3), "K4": (by_lu(0.005, 0.05) * sc).astype(F32), "K0": (by_lu(0.1, 0.4) * sc).astype(F32),
+        "SUZ": by_lu(20.0, 120.0), "xl": full(1000.0), "yl": full(1000.0),
+    }
+    elev = (_smooth_noise(rng, nrow, ncol, 128) * F32(2000.0)).astype(F32)
+    st["TempCor"] = (F32(-0.0065) * elev).astype(F32)
+    slope = np.exp(np.log(1e-3) + _smooth_noise(rng, nrow, ncol) * (np.log(0.3) - np.log(1e-3))).astype(F32)
+    st["Slope"] = slope
+    up = upstream_count(ldd).astype(F32)
+    # every cell carries a channel in wflow_hbv (:1040-1068): width from the upstream area, Manning's alpha
+    st["Bw"] = (F32(2.0) * np.power(np.maximum(up, 1), F32(0.35))).astype(F32)
+    st["DCL"] = np.where((ldd % 2 == 1) & (ldd != 5), F32(1000.0 * np.sqrt(2.0)), F32(1000.0)).astype(F32)
+    N = by_lu(0.03, 0.3, True)
+    beta = F32(0.6)
+    alp_term = np.power((N / np.sqrt(slope)).astype(np.float64), float(beta)).astype(F32)
+    alp_pow = F32(F32(2.0 / 3.0) * beta)
+    st["Alpha"] = (alp_term * np.power((st["Bw"] + F32(1.0)).astype(np.float64), float(alp_pow)).astype(F32)).astype(F32)
+    if edge:  # edge branches: threshold without interval, no interception store, a soil that cannot hold water
+        u = rng.random(shape)
+        st["TTI"][u < 0.15] = 0.0
+        st["ICF"][(u > 0.15) & (u < 0.3)] = 0.0
+        st["Cflux"][(u > 0.3) & (u < 0.4)] = 0.0
+    snowy = rng.random(shape) < 0.4
+    wet = rng.random(shape) < 0.5
+    state = {
+        "DrySnow": np.where(snowy, rng.uniform(0, 120, shape), 0).astype(F32),
+        "SoilMoisture": (fc * rng.uniform(0.1, 1.0, shape)).astype(F32),
+        "UpperZoneStorage": np.where(wet, rng.uniform(0, 60, shape), rng.uniform(0, 0.5, shape)).astype(F32),
+        "LowerZoneStorage": rng.uniform(1.0, 80.0, shape).astype(F32),
+        "InterceptionStorage": (st["ICF"] * rng.uniform(0, 1.0, shape)).astype(F32),
+        "SurfaceRunoff": (np.exp(rng.uniform(np.log(1e-3), np.log(2.0), shape)) * np.maximum(up, 1) ** 0.8).astype(F32),
+        "WaterLevel": rng.uniform(0.01, 2.0, shape).astype(F32),
+    }
+    state["FreeWater"] = (state["DrySnow"] * rng.uniform(0, 0.1, shape)).astype(F32)
+    if glacier:
+        gf = np.where(rng.random(shape) < 0.35, rng.uniform(0.05, 1.0, shape), 0.0).astype(F32)
+        st.update(GlacierFrac=gf, G_TT=full(1.3), G_Cfmax=full(5.3 * float(sc)), G_SIfrac=full(0.002 * float(sc)))
+        state["GlacierStore"] = np.where(gf > 0, rng.uniform(0.0, 5500.0, shape), 0.0).astype(F32)
+    return ldd, st, state
