@@ -95,6 +95,22 @@ int wf_create_from_schedule(const wf_config *cfg, wf_schedule *s, const uint8_t 
 int wf_schedule_partition(const wf_schedule *s, int ngroups, int64_t *storage_order, int64_t *group_off,
                           int64_t *up_start, uint8_t *nup);
 
+/* --- wflow_hbv ------------------------------------------------------------------------
+ * A model whose timestep is wflow_hbv's: replaces one pass of WflowModel.dynamic() of wflow/wflow_hbv.py:1222-1767 -- the
+ * HBV-96 column (rain / snow split, interception, snow pack, glacierHBV, soil moisture, upper and lower zone; REAL4 map
+ * algebra in the reference, one thread per cell here) and kin_wave (wflow/wflow_funcs.py:155-207) on the FULL network with
+ * every cell a channel (wflow_hbv.py:1633-1647), which is the river task of the same level sweep wflow_sbm's river uses.
+ * Of cfg: nrow, ncol, timestepsecs, it_kin_r (sub-steps of the wave; wf_set_substeps / wf_estimate_iterations(which = 1)
+ * for [model] kinwaveIters), glacier, beta, device.  Fields by the reference's attribute names (wf_set_field / wf_get_field,
+ * wf_request_output for the outputs): forcing P PET TEMP Inflow Seepage; parameters Pcorr TempCor TTI TT SFCF RFCF ICF EPF
+ * ECORR CEVPF Cfmax CFR WHC FieldCapacity Treshold BetaSeepage PERC Cflux KQuickFlow AlphaNL K4 K0 SUZ xl yl DCL Bw Alpha
+ * (+ GlacierFrac G_TT G_Cfmax G_SIfrac); states FreeWater DrySnow SoilMoisture UpperZoneStorage LowerZoneStorage
+ * InterceptionStorage SurfaceRunoff SurfaceRunoffsub WaterLevel WaterLevelsub (+ GlacierStore).  wf_set_option:
+ * "SetKquickFlow", "ExternalQbase".  Not restated, refused: reservoirs / lakes, MassWasting, updating from observed
+ * discharge, multi-step launches.  wf_step, wf_gauges_*, wf_area_*, wf_sample, wf_quick_suspend / resume work as for
+ * wflow_sbm models. */
+int wf_hbv_create(const wf_config *cfg, const uint8_t *ldd, wf_model **out);
+
 int64_t wf_num_cells(const wf_model *m);        /* cells in the drainage network */
 int64_t wf_num_levels(const wf_model *m);
 int64_t wf_num_river_cells(const wf_model *m);  /* cells of the river network (rnodes) */

@@ -18,6 +18,7 @@
 #include "network.h"
 #include "reduce.cuh"
 #include "outputs.cuh"
+#include "hbv.cuh"
 #include "objects.cuh"
 
 namespace wf {
@@ -32,6 +33,14 @@ int field_index(const char *name) {
   static std::map<std::string, int> idx;
   if (idx.empty())
     for (int i = 0; i < F_COUNT; i++) idx[g_fields[i].name] = i;
+  if (idx.size() == (size_t)F_COUNT) {
+    // wflow_hbv's names of the channel rasters it shares with wflow_sbm's river (wflow_hbv.py:131-163, 1064-1068)
+    idx["SurfaceRunoff"] = F_RiverRunoff;
+    idx["SurfaceRunoffsub"] = F_RiverRunoffsub;
+    idx["WaterLevel"] = F_WaterLevelR;
+    idx["WaterLevelsub"] = F_WaterLevelRsub;
+    idx["Alpha"] = F_AlphaR;
+  }
   auto it = idx.find(name ? name : "");
   return it == idx.end() ? -1 : it->second;
 }
@@ -165,6 +174,9 @@ struct wf_model {
   // end-of-dynamic() outputs (outputs.cuh): work arrays, allocated with the first request
   EndArgs end = {};
   float *d_ct1 = nullptr;
+  // wflow_hbv (hbv.cuh): a model made by wf_hbv_create runs the HBV column and the river task of the sweep on the whole network
+  bool hbv = false;
+  HbvOptions hbv_opt = {};
   bool satwd_valid = false;           // the SatWaterDepth map holds the end of the previous step          // dynamic shared memory limit already raised for the pipelined kernel
 };
 
@@ -258,7 +270,7 @@ template <int ML>
 int launch_lateral(wf_model *m) {
   if (const char *iv = std::getenv("WF_LAT_INTERLEAVE")) m->dm.lat_interleave = std::atoi(iv);  // development aid
   if (const char *tm = std::getenv("WF_LATERAL_TASKS"))  // development aid: bit0 subsurface, bit1 overland, bit2 river
-    m->dm.task_mask = (m->dm.task_mask & 8) | (std::atoi(tm) & 7);
+    if (!m->hbv) m->dm.task_mask = (m->dm.task_mask & 8) | (std::atoi(tm) & 7);
   if (const char *iv = std::getenv("WF_LAT_PREFETCH"))  // development aid: 0 = no L2 warm-up of the coming ticks' operands
     m->dm.task_mask = std::atoi(iv) ? (m->dm.task_mask & ~8) : (m->dm.task_mask | 8);
   void *args[] = {(void *)&m->dm};
@@ -559,7 +571,30 @@ int launch_step(wf_model *m) {
   return WF_OK;
 }
 
+// One timestep of a wflow_hbv model: the HBV column (hbv.cuh), then kin_wave on the whole network = the river task of the sweep.
+int launch_step_hbv(wf_model *m) {
+  const int64_t n = m->n;
+  if (n == 0) return WF_OK;
+  cudaEvent_t e0 = m->ev[0], e1 = m->ev[1], e2 = m->ev[2];
+  if (m->tev_used + 3 <= m->tev.size()) {
+    e0 = m->tev[m->tev_used]; e1 = m->tev[m->tev_used + 1]; e2 = m->tev[m->tev_used + 2];
+    m->tev_used += 3;
+  }
+  if (m->timed) cudaEventRecord(e0, m->stream);
+  m->dm.any_diag = 0;  // (the sweep's river task has no diagnostic build)
+  k_hbv_column<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->dm, m->hbv_opt);
+  m->launches++;
+  if (m->timed) cudaEventRecord(e1, m->stream);
+  if (int rc = launch_lateral<1>(m)) return rc;
+  m->launches++;
+  if (m->timed) cudaEventRecord(e2, m->stream);
+  m->ev_last[0] = e0; m->ev_last[1] = e1; m->ev_last[2] = e2;
+  CUDA_OK(cudaGetLastError());
+  return WF_OK;
+}
+
 int dispatch_step(wf_model *m) {
+  if (m->hbv) return launch_step_hbv(m);
   switch (m->ML) {
 #ifndef WF_DEV_ML4
     case 1: return launch_step<1>(m);
@@ -704,6 +739,22 @@ int check_ready(wf_model *m) {
     if (!m->dm.f[id]) return fail(WF_EINVAL, std::string("field not set: ") + g_fields[id].name);
     return WF_OK;
   };
+  if (m->hbv) {  // parameter maps of wflow_hbv's timestep (wflow_hbv.py:560-900)
+    for (int id : {F_P, F_PET, F_Pcorr, F_TempCor, F_TTI, F_TT, F_SFCF, F_RFCF, F_ICF, F_EPF, F_ECORR, F_CEVPF, F_Cfmax, F_CFR,
+                   F_WHC, F_FieldCapacity, F_Treshold, F_BetaSeepage, F_PERC, F_Cflux, F_KQuickFlow, F_K4, F_xl, F_yl, F_AlphaR,
+                   F_DCL, F_Bw})
+      if (int rc = need(id)) return rc;
+    if (m->hbv_opt.set_kquick) {
+      if (int rc = need(F_K0)) return rc;
+      if (int rc = need(F_SUZ)) return rc;
+    } else if (int rc = need(F_AlphaNL)) {
+      return rc;
+    }
+    if (m->cfg.glacier)
+      for (int id : kRequiredGlacier)
+        if (int rc = need(id)) return rc;
+    return WF_OK;
+  }
   for (int id : kRequired)
     if (int rc = need(id)) return rc;
   for (int k = 0; k < m->ML; k++) {
@@ -1070,8 +1121,25 @@ int wf_schedule_catchment_total(const wf_schedule *s, const float *values, doubl
   return WF_OK;
 }
 
+static int create_common(const wf_config *cfg, wf_schedule *sched, const uint8_t *ldd, const uint8_t *river, bool hbv, wf_model **out);
+
 int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint8_t *ldd, const uint8_t *river,
                             wf_model **out) {
+  return create_common(cfg, sched, ldd, river, false, out);
+}
+
+int wf_hbv_create(const wf_config *cfg, const uint8_t *ldd, wf_model **out) {
+  if (!cfg || !ldd || !out) return fail(WF_EINVAL, "null argument");
+  if (cfg->nrow <= 0 || cfg->ncol <= 0) return fail(WF_EINVAL, "bad grid size");
+  wf_config c = *cfg;
+  c.n_layer_thickness = 0;  // no soil layers in HBV; the overland wave does not exist
+  c.it_kin_l = 1;
+  // every cell with an ldd code carries a channel (self.static["River"] is never consulted by kin_wave, wflow_funcs.py:155-207)
+  std::vector<uint8_t> river((size_t)c.nrow * (size_t)c.ncol, 1);
+  return create_common(&c, nullptr, ldd, river.data(), true, out);
+}
+
+static int create_common(const wf_config *cfg, wf_schedule *sched, const uint8_t *ldd, const uint8_t *river, bool hbv, wf_model **out) {
   if (!cfg || !ldd || !out) return fail(WF_EINVAL, "null argument");
   if (cfg->nrow <= 0 || cfg->ncol <= 0) return fail(WF_EINVAL, "bad grid size");
   if (cfg->n_layer_thickness < 0 || cfg->n_layer_thickness + 1 > WF_MAX_LAYERS)
@@ -1089,6 +1157,7 @@ int wf_create_from_schedule(const wf_config *cfg, wf_schedule *sched, const uint
   CUDA_OK(cudaSetDevice(cfg->device));
 
   wf_model *m = new wf_model();
+  m->hbv = hbv;
   const int rc = create_impl(m, cfg, sched, ldd, river);
   if (rc != WF_OK) {  // release whatever the failed construction had allocated; keep its message
     const std::string msg = g_err;
@@ -1257,6 +1326,7 @@ static int create_impl(wf_model *m, const wf_config *cfg, wf_schedule *sched, co
   dm.beta = m->cfg.beta;
   dm.task_mask = 7;
   if (const char *tm = std::getenv("WF_LATERAL_TASKS")) dm.task_mask = std::atoi(tm);
+  if (m->hbv) dm.task_mask = 4;  // the channel of every cell is all the sweep routes (wflow_hbv.py:1633-1647)
   dm.lat_interleave = 1;
 #ifdef WF_PROFILE
   if (std::getenv("WF_TICK_PROFILE")) {
@@ -1323,6 +1393,8 @@ static int create_impl(wf_model *m, const wf_config *cfg, wf_schedule *sched, co
   // states exist from the start (zero = the reference's cold ZeroMap)
   for (int id = 0; id < F_COUNT; id++) {
     if ((g_fields[id].kind & 0xff) != K_STATE) continue;
+    const bool channel = id == F_RiverRunoff || id == F_RiverRunoffsub || id == F_WaterLevelR || id == F_WaterLevelRsub;
+    if (m->hbv != ((g_fields[id].kind & K_HBV) != 0) && !(m->hbv && (channel || id == F_GlacierStore))) continue;
     if (id >= F_UStoreLayerDepth_0 && id <= F_UStoreLayerDepth_7 && id - F_UStoreLayerDepth_0 >= m->ML) continue;
     if (id == F_GlacierStore && !cfg->glacier) continue;
     if (id == F_ReservoirVolume || id == F_LakeWaterLevel) continue;  // created with the objects
@@ -1850,6 +1922,7 @@ int wf_step_pipelined(wf_model *m, int nsteps, float *gauge_out, float mv, int a
   if (nsteps < 1) return fail(WF_EINVAL, "nsteps must be >= 1");
   if (nsteps > m->pipe_cap) return fail(WF_EINVAL, "more steps than reserved (wf_pipeline_reserve)");
   if (nsteps > WF_PIPE_MAX_INFLIGHT) return fail(WF_EUNSUPPORTED, "at most 64 timesteps per pipelined launch");
+  if (m->hbv) return fail(WF_EUNSUPPORTED, "wflow_hbv models run the per-step path (wf_step)");
   if (!m->pipe_has[0] || !m->pipe_has[1]) return fail(WF_EINVAL, "pipelined forcing not set: P and PET (wf_pipeline_set_forcing)");
   if (m->cfg.model_snow && !m->pipe_has[2]) return fail(WF_EINVAL, "pipelined forcing not set: TEMP");
   if (m->dm.task_mask != 7) return fail(WF_EUNSUPPORTED, "WF_LATERAL_TASKS is a development aid of the per-step sweep");
@@ -2136,6 +2209,7 @@ int wf_gauges_sample_device(wf_model *m, int gauges, const char *field, float *d
 // ---- reservoirs / lakes ------------------------------------------------------------------------------
 int wf_reservoirs_create(wf_model *m, const int32_t *locs, const int32_t *areas, const uint8_t *ldd_org) {
   if (!m || !locs) return fail(WF_EINVAL, "null argument");
+  if (m->hbv) return fail(WF_EUNSUPPORTED, "reservoirs and lakes are not available for wflow_hbv models");
   CUDA_OK(cudaSetDevice(m->cfg.device));
   CUDA_OK(cudaStreamSynchronize(m->stream));
   for (void *p : m->reservoirs.owned) cudaFree(p);
@@ -2151,6 +2225,7 @@ int wf_lakes_create(wf_model *m, const int32_t *locs, const int32_t *linked, con
                     int n_sh, const int32_t *sh_ids, const int32_t *sh_rows, const float *sh_data, int n_hq,
                     const int32_t *hq_ids, const int32_t *hq_rows, const float *hq_data) {
   if (!m || !locs) return fail(WF_EINVAL, "null argument");
+  if (m->hbv) return fail(WF_EUNSUPPORTED, "reservoirs and lakes are not available for wflow_hbv models");
   CUDA_OK(cudaSetDevice(m->cfg.device));
   CUDA_OK(cudaStreamSynchronize(m->stream));
   for (void *p : m->lakes.owned) cudaFree(p);
@@ -2208,6 +2283,7 @@ int wf_lakes_create(wf_model *m, const int32_t *locs, const int32_t *linked, con
 
 int wf_irrigation_create(wf_model *m, const int32_t *areas, const int32_t *intakes) {
   if (!m || !areas || !intakes) return fail(WF_EINVAL, "null argument");
+  if (m->hbv) return fail(WF_EUNSUPPORTED, "irrigation areas are not available for wflow_hbv models");
   CUDA_OK(cudaSetDevice(m->cfg.device));
   CUDA_OK(cudaStreamSynchronize(m->stream));
   for (void *p : m->irri_owned) cudaFree(p);
@@ -2282,6 +2358,12 @@ int wf_set_option(wf_model *m, const char *name, double value) {
   if (!m || !name) return fail(WF_EINVAL, "null argument");
   CUDA_OK(cudaSetDevice(m->cfg.device));
   const std::string k(name);
+  if (m->hbv) {  // [model] options of wflow_hbv (wflow_hbv.py:383-470)
+    if (k == "SetKquickFlow") m->hbv_opt.set_kquick = value != 0.0;
+    else if (k == "ExternalQbase") m->hbv_opt.external_qbase = value != 0.0;
+    else if (value != 0.0) return fail(WF_EUNSUPPORTED, "option not available for wflow_hbv models: " + k);
+    return WF_OK;
+  }
   if (k == "MassWasting") {
     if (value != 0.0 && m->cfg.glacier)
       return fail(WF_EUNSUPPORTED, "MassWasting together with the glacier module is not supported (the glacier reads the wasted pack)");

@@ -5,9 +5,10 @@
 
 namespace wf {
 
-enum FieldKind : int { K_FORCING = 0, K_STATIC = 1, K_STATE = 2, K_DIAG = 3, K_RIVER = 0x100 };
+enum FieldKind : int { K_FORCING = 0, K_STATIC = 1, K_STATE = 2, K_DIAG = 3, K_RIVER = 0x100, K_HBV = 0x200 };
 
-// X(name, kind)   -- K_RIVER marks arrays that exist only for river cells (river order)
+// X(name, kind)   -- K_RIVER marks arrays that exist only for river cells (river order),
+//                    K_HBV the rasters of the wflow_hbv column (hbv.cuh; states created for wf_hbv_create models only)
 #define WF_FIELDS(X)                                                                               \
   /* forcing (wf_updateparameters, wflow_sbm.py:2583) */                                           \
   X(P, K_FORCING) X(PET, K_FORCING) X(TEMP, K_FORCING) X(Inflow, K_FORCING | K_RIVER)              \
@@ -88,7 +89,23 @@ enum FieldKind : int { K_FORCING = 0, K_STATIC = 1, K_STATE = 2, K_DIAG = 3, K_R
   X(CumExfiltWater, K_DIAG) X(CumSurfaceWater, K_DIAG)                                             \
   X(OutflowSR, K_DIAG) X(ResPercFull, K_DIAG) X(ResPrecipSR, K_DIAG) X(ResEvapSR, K_DIAG)          \
   X(DemandRelease, K_DIAG) X(LakeOutflow, K_DIAG) X(LakeVolume, K_DIAG) X(LakePrecip, K_DIAG)      \
-  X(LakeEvap, K_DIAG) X(IrriDemand, K_DIAG) X(IrriDemandm3, K_DIAG)
+  X(LakeEvap, K_DIAG) X(IrriDemand, K_DIAG) X(IrriDemandm3, K_DIAG)                                  \
+  /* wflow_hbv (wflow/wflow_hbv.py:560-900 parameters, :131-163 states, :1222-1767 dynamic(); hbv.cuh).  Shared with the   \
+   * rows above: P PET TEMP Inflow, TempCor TTI TT Cfmax WHC xl yl, the glacier rows, DCL Bw and AlphaR (= Alpha), the       \
+   * channel states RiverRunoff(sub) / WaterLevelR(sub) (= SurfaceRunoff(sub) / WaterLevel(sub)) and some outputs */        \
+  X(Seepage, K_FORCING | K_HBV)                                                                    \
+  X(Pcorr, K_STATIC | K_HBV) X(SFCF, K_STATIC | K_HBV) X(RFCF, K_STATIC | K_HBV) X(ICF, K_STATIC | K_HBV)                  \
+  X(EPF, K_STATIC | K_HBV) X(ECORR, K_STATIC | K_HBV) X(CEVPF, K_STATIC | K_HBV) X(CFR, K_STATIC | K_HBV)                  \
+  X(FieldCapacity, K_STATIC | K_HBV) X(Treshold, K_STATIC | K_HBV) X(BetaSeepage, K_STATIC | K_HBV)                        \
+  X(PERC, K_STATIC | K_HBV) X(Cflux, K_STATIC | K_HBV) X(KQuickFlow, K_STATIC | K_HBV) X(AlphaNL, K_STATIC | K_HBV)        \
+  X(K4, K_STATIC | K_HBV) X(K0, K_STATIC | K_HBV) X(SUZ, K_STATIC | K_HBV)                                                 \
+  X(FreeWater, K_STATE | K_HBV) X(DrySnow, K_STATE | K_HBV) X(SoilMoisture, K_STATE | K_HBV)                               \
+  X(UpperZoneStorage, K_STATE | K_HBV) X(LowerZoneStorage, K_STATE | K_HBV) X(InterceptionStorage, K_STATE | K_HBV)        \
+  X(PotEvaporation, K_DIAG | K_HBV) X(IntEvap, K_DIAG | K_HBV) X(SoilEvap, K_DIAG | K_HBV) X(HBVSeepage, K_DIAG | K_HBV)   \
+  X(DirectRunoff, K_DIAG | K_HBV) X(InUpperZone, K_DIAG | K_HBV) X(Percolation, K_DIAG | K_HBV)                            \
+  X(QuickFlow, K_DIAG | K_HBV) X(RealQuickFlow, K_DIAG | K_HBV) X(BaseFlow, K_DIAG | K_HBV) X(InSoil, K_DIAG | K_HBV)      \
+  X(NetInSoil, K_DIAG | K_HBV) X(RainAndSnowmelt, K_DIAG | K_HBV) X(QuickFlowCubic, K_DIAG | K_HBV)                        \
+  X(BaseFlowCubic, K_DIAG | K_HBV)
 
 enum FieldId : int {
 #define X(n, k) F_##n,

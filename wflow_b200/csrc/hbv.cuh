@@ -1,0 +1,175 @@
+// wflow_hbv on the device: the HBV-96 column of one timestep, ahead of the kinematic wave.
+//
+// Reference: WflowModel.dynamic(), wflow/wflow_hbv.py:1222-1767.  Everything up to the lateral inflow of the channel
+// (:1264-1612) is cell-local REAL4 map algebra: rain / snow split, interception, snow pack with refreezing and liquid
+// water, glacierHBV (wflow/wflow_funcs.py:549-603), soil moisture with direct runoff and seepage, upper zone (percolation,
+// capillary flux, quick flow), lower zone (base flow).  It runs here as one thread per cell in float32, operation by
+// operation in the reference's order (the library is compiled without FMA contraction); pcr.exp and ** are evaluated in
+// float64 and rounded to REAL4 once, like the PCRaster stand-in the goldens were made with (oracle/pcrshim.py).
+// The kinematic wave that follows (kin_wave, wflow/wflow_funcs.py:155-207, called on the FULL network with every cell a
+// channel, wflow_hbv.py:1633-1647) is the river task of the sweep in lateral.cuh: a wf_hbv_create model is a model whose
+// river network is its whole network and whose sweep runs the river task only; this kernel hands it the lateral inflow
+// (h_inwater, river order) where the SBM model's overland task does.
+//
+// Not restated (wf_set_option refuses them for these models): reservoirs / lakes (:1533-1594), snow mass wasting
+// (:1351-1364), state updating from observed discharge (:1684-1726).
+#pragma once
+#include "kernels.cuh"
+
+namespace wf {
+
+struct HbvOptions {
+  int32_t set_kquick;      // [model] SetKquickFlow: K0 / SUZ quick flow instead of the non-linear upper zone (:1466-1500)
+  int32_t external_qbase;  // [model] ExternalQbase: seepage of an external model instead of the lower zone's base flow (:1271, :1512)
+};
+
+#define HF(name) (__ldg(m.f[F_##name] + i))
+#define HOUT(name, v)                            \
+  do {                                           \
+    if (m.f[F_##name]) m.f[F_##name][i] = (v);   \
+  } while (0)
+
+__device__ __forceinline__ float hbv_pow(float x, float y) { return (float)pow((double)x, (double)y); }
+
+__global__ void __launch_bounds__(256) k_hbv_column(const DevModel m, const HbvOptions opt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m.n) return;
+  const int32_t rs = __ldg(m.river_slot + i);
+  const float dtf = (float)m.dt;
+  // ---- forcing, rain / snow split (:1264-1300) ----
+  float Precipitation = fmaxf(0.0f, HF(P)) * HF(Pcorr);
+  float PotEvaporation = HF(PET);
+  const float Temperature = (m.f[F_TEMP] ? HF(TEMP) : 10.0f) + HF(TempCor);
+  const float TT = HF(TT), TTI = HF(TTI);
+  float RainFrac;
+  if (1.0f * TTI == 0.0f) RainFrac = (Temperature <= TT) ? 0.0f : 1.0f;
+  else RainFrac = fminf((Temperature - (TT - TTI / 2.0f)) / TTI, 1.0f);
+  RainFrac = fmaxf(RainFrac, 0.0f);
+  const float SnowFrac = 1.0f - RainFrac;
+  Precipitation = HF(SFCF) * SnowFrac * Precipitation + HF(RFCF) * RainFrac * Precipitation;
+  // ---- interception (:1302-1322) ----
+  float IS = m.f[F_InterceptionStorage][i];
+  const float Interception = fminf(Precipitation, HF(ICF) - IS);
+  IS = IS + Interception;
+  Precipitation = Precipitation - Interception;
+  PotEvaporation = (float)exp((double)(-HF(EPF) * Precipitation)) * HF(ECORR) * PotEvaporation;
+  PotEvaporation = HF(CEVPF) * PotEvaporation;
+  const float IntEvap = fminf(IS, PotEvaporation);
+  IS = IS - IntEvap;
+  const float RestEvap = fmaxf(0.0f, PotEvaporation - IntEvap);
+  // ---- snow pack (:1332-1362) ----
+  const float SnowFall = SnowFrac * Precipitation;
+  const float RainFall = RainFrac * Precipitation;
+  const float Cfmax = HF(Cfmax);
+  const float PotSnowMelt = (Temperature > TT) ? Cfmax * (Temperature - TT) : 0.0f;
+  const float PotRefreezing = (Temperature < TT) ? Cfmax * HF(CFR) * (TT - Temperature) : 0.0f;
+  float FreeWater = m.f[F_FreeWater][i];
+  float DrySnow = m.f[F_DrySnow][i];
+  const float Refreezing = (Temperature < TT) ? fminf(PotRefreezing, FreeWater) : 0.0f;
+  const float SnowMelt = fminf(PotSnowMelt, DrySnow);
+  DrySnow = DrySnow + SnowFall + Refreezing - SnowMelt;
+  FreeWater = FreeWater - Refreezing;
+  const float MaxFreeWater = DrySnow * HF(WHC);
+  FreeWater = FreeWater + SnowMelt + RainFall;
+  const float InSoil = fmaxf(FreeWater - MaxFreeWater, 0.0f);
+  FreeWater = FreeWater - InSoil;
+  const float RainAndSnowmelt = RainFall + SnowMelt;
+  const float SnowCover = (DrySnow > 0.0f) ? 1.0f : 0.0f;
+  // ---- soil moisture: direct runoff (:1370-1378) ----
+  float NetInSoil = InSoil;
+  const float FC = HF(FieldCapacity);
+  float SM = m.f[F_SoilMoisture][i] + NetInSoil;
+  float DirectRunoff = fmaxf(SM - FC, 0.0f);
+  SM = SM - DirectRunoff;
+  NetInSoil = NetInSoil - DirectRunoff;
+  // ---- glacier (:1378-1404; glacierHBV, wflow_funcs.py:549-603) ----
+  if (m.glacier) {
+    const float ts = (float)(m.dt / m.basetimestep);
+    const float gf = HF(GlacierFrac), gtt = HF(G_TT);
+    float S2G = HF(G_SIfrac) * ts * DrySnow;
+    S2G = (gf > 0.0f) ? S2G : 0.0f;
+    S2G = fminf(S2G, (float)(8.0 * (m.dt / m.basetimestep)));
+    DrySnow = DrySnow - (S2G * gf);
+    float GS = m.f[F_GlacierStore][i] + S2G;
+    const float PotMelt = (Temperature > gtt) ? HF(G_Cfmax) * ts * (Temperature - gtt) : 0.0f;
+    float GM = (DrySnow < 10.0f) ? fminf(PotMelt, GS) : 0.0f;
+    GS = GS - GM;
+    GM = GM * gf;  // :1402
+    FreeWater = FreeWater + GM;
+    m.f[F_GlacierStore][i] = GS;
+    HOUT(Snow2Glacier, S2G);
+    HOUT(GlacierMelt, GM);
+  }
+  // ---- soil evaporation, seepage (:1412-1442) ----
+  const float Tr = HF(Treshold);
+  const float SoilEvap = (SM > Tr) ? fminf(SM, RestEvap) : fminf(SM, fminf(RestEvap, PotEvaporation * (SM / Tr)));
+  SM = SM - SoilEvap;
+  const float ActEvap = IntEvap + SoilEvap;
+  const float HBVSeepage = hbv_pow(fminf(SM / FC, 1.0f), HF(BetaSeepage)) * NetInSoil;
+  SM = SM - HBVSeepage;
+  const float Backtosoil = fminf(FC - SM, DirectRunoff);
+  DirectRunoff = DirectRunoff - Backtosoil;
+  SM = SM + Backtosoil;
+  const float InUpperZone = DirectRunoff + HBVSeepage;
+  // ---- upper zone (:1448-1506) ----
+  const float PERC = HF(PERC);
+  float UZ = m.f[F_UpperZoneStorage][i] + InUpperZone;
+  const float Percolation = fminf(PERC, UZ - InUpperZone / 2.0f);
+  UZ = UZ - Percolation;
+  float CapFlux = HF(Cflux) * ((FC - SM) / FC);
+  CapFlux = fminf(UZ, CapFlux);
+  CapFlux = fminf(FC - SM, CapFlux);
+  UZ = UZ - CapFlux;
+  SM = SM + CapFlux;
+  float QuickFlow, RealQuickFlow;
+  if (!opt.set_kquick) {
+    const bool low = Percolation < PERC;
+    const float qf = low ? 0.0f : HF(KQuickFlow) * hbv_pow(UZ - fminf(InUpperZone / 2.0f, UZ), 1.0f + HF(AlphaNL));
+    QuickFlow = fminf(qf, UZ);
+    UZ = fmaxf(low ? UZ : UZ - QuickFlow, 0.0f);
+    RealQuickFlow = 0.0f;
+  } else {
+    QuickFlow = HF(KQuickFlow) * UZ;
+    RealQuickFlow = fmaxf(0.0f, HF(K0) * (UZ - HF(SUZ)));
+    UZ = UZ - QuickFlow - RealQuickFlow;
+  }
+  // ---- lower zone, runoff generation (:1508-1528) ----
+  float LZ = m.f[F_LowerZoneStorage][i] + Percolation;
+  const float BaseFlow = fminf(LZ, HF(K4) * LZ);
+  LZ = LZ - BaseFlow;
+  float DirectRunoffStorage;
+  if (opt.external_qbase) DirectRunoffStorage = QuickFlow + (m.f[F_Seepage] ? HF(Seepage) : 0.0f) + RealQuickFlow;
+  else DirectRunoffStorage = QuickFlow + BaseFlow + RealQuickFlow;
+  const float InwaterMM = fmaxf(0.0f, DirectRunoffStorage);
+  const float ToCubic = ((HF(xl) * HF(yl)) * 0.001f) / dtf;  // :1014
+  float Inwater = InwaterMM * ToCubic;
+  // ---- sources and demands (:1599-1606), lateral inflow of the channel (:1612) ----
+  const float Inflow = (m.f[F_Inflow] && rs >= 0) ? __ldg(m.f[F_Inflow] + rs) : 0.0f;
+  const float SurfaceRunoff = (rs >= 0) ? m.f[F_RiverRunoff][rs] : 0.0f;
+  const float SWS = (Inflow < 0.0f) ? fmaxf(-1.0f * Inwater, SurfaceRunoff) : 0.0f;
+  Inwater = Inwater + ((SWS > 0.0f) ? -1.0f * SWS : Inflow);
+  if (rs >= 0) {
+    m.h_inwater[rs] = Inwater;
+    if (m.f[F_Inwater]) m.f[F_Inwater][rs] = Inwater;
+  }
+  // ---- states ----
+  m.f[F_InterceptionStorage][i] = IS;
+  m.f[F_DrySnow][i] = DrySnow;
+  m.f[F_FreeWater][i] = FreeWater;
+  m.f[F_SoilMoisture][i] = SM;
+  m.f[F_UpperZoneStorage][i] = UZ;
+  m.f[F_LowerZoneStorage][i] = LZ;
+  // ---- outputs on request ----
+  HOUT(Precipitation, Precipitation); HOUT(PotEvaporation, PotEvaporation); HOUT(Temperature, Temperature);
+  HOUT(IntEvap, IntEvap); HOUT(SnowMelt, SnowMelt); HOUT(SnowCover, SnowCover); HOUT(SoilEvap, SoilEvap);
+  HOUT(ActEvap, ActEvap); HOUT(HBVSeepage, HBVSeepage); HOUT(DirectRunoff, DirectRunoff); HOUT(InUpperZone, InUpperZone);
+  HOUT(Percolation, Percolation); HOUT(CapFlux, CapFlux); HOUT(QuickFlow, QuickFlow); HOUT(RealQuickFlow, RealQuickFlow);
+  HOUT(BaseFlow, BaseFlow); HOUT(InSoil, InSoil); HOUT(RainAndSnowmelt, RainAndSnowmelt); HOUT(NetInSoil, NetInSoil);
+  HOUT(InwaterMM, InwaterMM); HOUT(QuickFlowCubic, (QuickFlow + RealQuickFlow) * ToCubic); HOUT(BaseFlowCubic, BaseFlow * ToCubic);
+  HOUT(SurfaceWaterSupply, SWS);
+}
+
+#undef HF
+#undef HOUT
+
+}  // namespace wf
