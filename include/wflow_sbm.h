@@ -260,9 +260,19 @@ int wf_set_option(wf_model *m, const char *name, double value);
  * Transpiration) over it, in m3/s -- becomes the negative Inflow of the intakes with its id (the "Abstractions" option is
  * switched on), and what the supply iteration gave them, times (1 - DemandReturnFlowFraction), comes back to the area as
  * IRSupplymm [mm], added to the water available for infiltration in the NEXT step (IRSupplymm is a state: get / set).
- * Not restated: irrigation return points (IrrigationSurfaceReturn), paddy areas, IrriDemandExternal.
+ * Not restated: irrigation return points (IrrigationSurfaceReturn), IrriDemandExternal.
  * Returns the number of areas, or a negative wf_status. */
 int wf_irrigation_create(wf_model *m, const int32_t *areas, const int32_t *intakes);
+/* Paddy areas fed from river intakes (self.nrpaddyirri > 0; wflow/wflow_sbm.py:762-785 ponding inside sbm_cell, :2811-2815
+ * pond evaporation, :3033-3050 demand, :3330-3346 supply; idtoid wflow/wflow_lib.py:81-101).  areas / intakes: the
+ * IrrigationPaddyAreas and IrrigationSurfaceIntakes id maps (0 or negative = none).  Fields: h_p (bund height; 0 = the cell
+ * ponds nothing), h_min / h_max (the pond depth that triggers irrigation / that it fills to), CRPST (crop-stage multiplier,
+ * a per-step raster the user's [modelparameters] supplies; 1 when not set), state PondingDepth, outputs ActEvapPond,
+ * irr_depth, IrriDemandm3, IRSupplymm.  The step then sweeps twice (subsurface flow and the column tail that ponds; the
+ * areas' demand; overland and river flow), with the supply iteration of the abstractions behind it.  Intake cells carry no
+ * other Inflow.  Not together with wf_irrigation_create (the reference lets the paddy supply overwrite the other).
+ * Returns the number of areas. */
+int wf_paddy_create(wf_model *m, const int32_t *areas, const int32_t *intakes);
 int wf_supply_iterations(const wf_model *m);   /* self.nrit of the last step */
 /* Day of the year (1..366) of the coming steps: column of the lakes' rating tables (wf_supplyJulianDOY). */
 int wf_set_day_of_year(wf_model *m, int jdoy);

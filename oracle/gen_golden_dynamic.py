@@ -63,6 +63,10 @@ CASES = {
     # what was taken is spread over the area as extra water of the NEXT step (IRSupplymm); an area with two intakes, one
     # without any and an intake without an area (idtoid's left-over values, wflow_lib.py:81-101)
     "irrigation_daily": dict(n=24, kind="tiles", tile=12, layer_thickness=(100, 300, 800), steps=6, irrigation=1),
+    # paddy areas (wflow_sbm.py:2812-2815 pond evaporation, :762-785 ponding of what would run off, :3033-3050 demand when the
+    # pond falls below h_min, :3330-3346 supply of the intakes spread over the cells that asked); CRPST (the crop-stage
+    # multiplier of the demand, a [modelparameters] map of the user) changes from step to step
+    "irrigation_paddy_daily": dict(n=24, kind="tiles", tile=12, layer_thickness=(100, 300, 800), steps=7, paddy=1),
     "abstraction_hourly_substeps": dict(n=24, kind="tiles", tile=12, layer_thickness=(100, 300), dt=3600, kinwaveIters=1,
                                         landTstep=3600, riverTstep=900, steps=5, inflow=-1),
 }
@@ -88,7 +92,7 @@ OUTPUTS = [
     "SatWaterFlux", "sumUstore", "SnowCover", "RootStore", "RootStore_sat", "vwcRoot", "vwc_percRoot", "SurfaceWaterSupply",
     "ExfiltWaterCubic", "InfiltExcessCubic", "SumEvapSat", "SumEvapUstore", "CumOutFlow", "CumActInfilt", "CumCellInFlow",
     "CumPrec", "CumEvap", "CumPotenEvap", "CumInt", "CumLeakage", "CumExfiltWater", "CumSurfaceWater",
-    "IRSupplymm", "IrriDemand", "IrriDemandm3",
+    "IRSupplymm", "IrriDemand", "IrriDemandm3", "PondingDepth", "ActEvapPond", "irr_depth",
     # reservoirs / lakes
     "OutflowSR", "ResPercFull", "ResPrecipSR", "ResEvapSR", "DemandRelease", "LakeOutflow", "LakeVolume", "LakePrecip",
     "LakeEvap", "Inflow",
@@ -244,6 +248,24 @@ def gen_case(name, kw):
         m.nrirri = int(areas.max())  # :1637-1638
         m.DemandReturnFlowFraction = m._map(drff)
         data["irri/areas"], data["irri/intakes"], data["static/DemandReturnFlowFraction"] = areas, intakes, drff
+    if kw.get("paddy"):
+        from . import pcrshim as pcr
+        areas, intakes, _drff = irrigation_inputs(kw, ldd, river)
+        m = ref.m
+        idm = lambda a: pcr.numpy2pcr(pcr.Nominal, np.where(a > 0, a, -999).astype(np.float64), -999.0)  # noqa: E731
+        m.IrrigationPaddyAreas, m.IrrigationSurfaceIntakes = idm(areas), idm(intakes)
+        m.nrpaddyirri = int(areas.max())  # :1639-1641
+        prng = np.random.default_rng(31)
+        inside = areas > 0
+        hp = np.where(inside, prng.uniform(40.0, 120.0, (n, n)), 0.0).astype(F32)
+        hp[areas == 3] = 0.0  # an area whose bunds hold nothing: asks for water, ponds none
+        hmax = np.where(inside, prng.uniform(30.0, 60.0, (n, n)), 0.0).astype(F32)
+        hmin = np.where(inside, prng.uniform(5.0, 25.0, (n, n)), 0.0).astype(F32)
+        pond0 = np.where(inside, prng.uniform(0.0, 45.0, (n, n)), 0.0).astype(F32)
+        m.h_p, m.h_max, m.h_min, m.PondingDepth = m._map(hp), m._map(hmax), m._map(hmin), m._map(pond0)
+        m.static["h_p"] = pcr.pcr2numpy(m.h_p, -999.0).ravel()  # :2284
+        data["paddy/areas"], data["paddy/intakes"] = areas, intakes
+        data["static/h_p"], data["static/h_max"], data["static/h_min"], data["state0/PondingDepth"] = hp, hmax, hmin, pond0
     if res or lak:
         data["ldd_org"] = ldd_org
         data["static/filter_P_PET"] = ref.get("filter_P_PET")
@@ -280,6 +302,10 @@ def gen_case(name, kw):
         data["forcing/%d/P" % t], data["forcing/%d/PET" % t], data["forcing/%d/TEMP" % t] = P, PET, T
         if inflow is not None:
             data["forcing/%d/Inflow" % t] = inflow
+        if kw.get("paddy"):  # the crop stage of the step (a timeseries parameter of the user's ini)
+            crpst = np.full((n, n), [1.0, 0.6, 0.0, 1.0, 0.8, 1.0, 0.3][t % 7], F32)
+            ref.m.CRPST = ref.m._map(crpst)
+            data["forcing/%d/CRPST" % t] = crpst
         if courant:  # what the reference will derive inside dynamic() (:2911-2921, 3159-3169); the river estimate
             # uses the state BEFORE the step as well (RiverRunoffsub is not touched before kin_wave)
             m = ref.m
@@ -287,7 +313,7 @@ def gen_case(name, kw):
             itr = funcs.estimate_iterations_kin_wave(m.RiverRunoffsub, m.Beta, m.AlphaR, m.timestepsecs, m.DCL, m.mv)
             data["it/%d" % t] = np.array([itl, itr], np.int64)
         ref.step(P, PET, T, Inflow=inflow, LAI=lai)
-        if kw.get("inflow", 0) < 0 or kw.get("irrigation"):
+        if kw.get("inflow", 0) < 0 or kw.get("irrigation") or kw.get("paddy"):
             data["nrit/%d" % t] = np.array(ref.m.nrit, np.int64)
         for k in outs:
             if ref.has(k):

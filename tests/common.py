@@ -162,7 +162,7 @@ def load_dyn_case(name, oracle=True, gpu=False):
                        it_kin_l=itl, it_kin_r=itr, transfer_method=kw.get("tm", 0), ust=kw.get("ust", 0),
                        soil_inf_redu=kw.get("sir", 0), glacier=glacier)
         for k, v in {**static, **state}.items():
-            if k not in ("River", "Beta", "SatWaterDepth", "ReservoirVolume", "LakeWaterLevel"):
+            if k not in ("River", "Beta", "SatWaterDepth", "ReservoirVolume", "LakeWaterLevel", "PondingDepth"):
                 mod.set(k, v)
         if kw.get("masswasting"):
             mod.set_option("MassWasting", 1)
@@ -170,6 +170,9 @@ def load_dyn_case(name, oracle=True, gpu=False):
             mod.set_option("Abstractions", 1)
         if "irri/areas" in g.files:  # irrigation areas and intakes (:1096-1115, 3014-3031, 3314-3328)
             assert mod.irrigation_create(g["irri/areas"], g["irri/intakes"]) == len(np.unique(g["irri/areas"][g["irri/areas"] > 0]))
+        if "paddy/areas" in g.files:  # paddy areas (:762-785, 2811-2815, 3033-3050, 3330-3346)
+            assert mod.paddy_create(g["paddy/areas"], g["paddy/intakes"]) == len(np.unique(g["paddy/areas"][g["paddy/areas"] > 0]))
+            mod.set("PondingDepth", state["PondingDepth"])
         if "res/locs" in g.files:  # simple reservoirs (wflow_sbm.py:1804-1826, 2822-2852)
             assert mod.reservoirs_create(g["res/locs"], g["res/areas"], g["ldd_org"]) == int((g["res/locs"] > 0).sum())
             mod.set("ReservoirVolume", state["ReservoirVolume"])

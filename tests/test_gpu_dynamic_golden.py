@@ -53,12 +53,12 @@ def test_cuda_matches_reference_dynamic(name):
                 "Inflow"}                                # likewise: the reference adds the objects' outflow to the map
         outs = [f for f in common.dyn_outputs(g) if f in known and f not in skip]
         states = [f for f in outs if "state0/" + f in g.files and f != "SatWaterDepth"] + ["SatWaterDepth"]  # the map itself, last
-        irrigation = "irri/areas" in g.files  # IRSupplymm is carried from step to step like a state (0 before the first)
+        irrigation = "irri/areas" in g.files or "paddy/areas" in g.files  # IRSupplymm is carried from step to step like a state (0 before the first)
         mod.request(*outs)
         cmask = mask & ~_downstream_of_dropped(np.asarray(g["ldd"]), mask)
         worst = (0.0, "")
         for t in range(kw["steps"]):
-            for f in ("P", "PET", "TEMP", "Inflow"):
+            for f in ("P", "PET", "TEMP", "Inflow", "CRPST"):
                 key = "forcing/%d/%s" % (t, f)
                 if key in g.files:
                     mod.set(f, g[key])

@@ -44,7 +44,7 @@ SYMBOLS = [
     "wf_schedule_partition", "wf_lateral_plan", "wf_gauges_create", "wf_gauges_sample",
     "wf_estimate_iterations", "wf_set_substeps", "wf_pipeline_reserve", "wf_pipeline_set_forcing",
     "wf_pipeline_forcing_ptr", "wf_pipeline_capture", "wf_step_pipelined", "wf_gauges_sample_device", "wf_set_field_tiled", "wf_reservoirs_create", "wf_lakes_create",
-    "wf_set_day_of_year", "wf_set_option", "wf_supply_iterations", "wf_irrigation_create", "wf_pipeline_mode", "wf_hbv_create",
+    "wf_set_day_of_year", "wf_set_option", "wf_supply_iterations", "wf_irrigation_create", "wf_pipeline_mode", "wf_hbv_create", "wf_paddy_create",
 ]
 
 
@@ -82,6 +82,7 @@ def lib():
     l.wf_reservoirs_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.wf_lakes_create.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] * 2
     l.wf_irrigation_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    l.wf_paddy_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     l.wf_pipeline_mode.argtypes = [C.c_void_p]
     l.wf_hbv_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     l.wf_set_day_of_year.argtypes = [C.c_void_p, C.c_int]

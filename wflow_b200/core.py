@@ -249,6 +249,13 @@ class SbmModel:
         a = [np.ascontiguousarray(x, dtype=np.int32) for x in (areas, intakes)]
         return _lib.check(self._l.wf_irrigation_create(self._h, a[0].ctypes.data, a[1].ctypes.data))
 
+    def paddy_create(self, areas, intakes):
+        """Paddy areas and their river intakes (id rasters IrrigationPaddyAreas / IrrigationSurfaceIntakes, 0 = none;
+        wflow_sbm.py:762-785, 2811-2815, 3033-3050, 3330-3346): fields h_p / h_min / h_max / CRPST, state PondingDepth.
+        Returns the number of areas."""
+        a = [np.ascontiguousarray(x, dtype=np.int32) for x in (areas, intakes)]
+        return _lib.check(self._l.wf_paddy_create(self._h, a[0].ctypes.data, a[1].ctypes.data))
+
     def lakes_create(self, locs, linked, areas, ldd_org, sh=None, hq=None):
         """Natural lakes: id rasters LakeLocs / LinkedLakeLocs / LakeAreasMap, the original LDD and the curve tables
         sh = {lake id: array[rows, 2] (H, S)}, hq = {lake id: array[rows, 367] (H, Q per day of the year)}."""

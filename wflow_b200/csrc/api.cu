@@ -161,6 +161,9 @@ struct wf_model {
   Objects reservoirs, lakes;
   IrrigationSet irri = {};            // irrigation areas and their intakes (wf_irrigation_create)
   std::vector<void *> irri_owned;
+  IrrigationSet paddy = {};           // paddy areas and their intakes (wf_paddy_create)
+  std::vector<void *> paddy_owned;
+  std::map<int, uint32_t *> tick_total_of_mask;  // the sweep's tick sizes for a subset of its tasks (paddy: subsurface, then the rest)
   float *d_obj_inflow = nullptr;      // nr: Inflow map + outflow of the objects above each river cell
   int jdoy = 1;                       // day of the year for the lakes' rating tables (wf_set_day_of_year)
   // options of wf_set_option
@@ -337,7 +340,7 @@ void prepare_step(wf_model *m) {
   m->dm.any_diag = 0;
   for (int id = 0; id < F_COUNT; id++)
     if ((g_fields[id].kind & 0xff) == K_DIAG && m->dm.f[id]) m->dm.any_diag = 1;
-  if (m->dm.h_wb) m->dm.any_diag = 1;
+  if (m->dm.h_wb || m->paddy.n > 0) m->dm.any_diag = 1;  // (the ponds live in the builds with the outputs)
   {  // sources of the staged inputs (VLayout); pointers may have been re-bound since the last step
     using VL = VLayout<ML>;
     static_assert(VL::nslots(true) <= WF_MAX_VSLOTS, "WF_MAX_VSLOTS too small");
@@ -485,6 +488,8 @@ int end_prepare(wf_model *m) {
   return WF_OK;
 }
 
+int sweep_mask_totals(wf_model *m, int mask, const uint32_t **out);
+
 template <int ML>
 int launch_step(wf_model *m) {
   const int64_t n = m->n;
@@ -528,7 +533,25 @@ int launch_step(wf_model *m) {
     m->launches++;
   }
   if (m->timed) cudaEventRecord(e1, m->stream);
-  if (int rc = launch_lateral<ML>(m)) return rc;
+  if (m->paddy.n > 0 && m->dm.task_mask == 7) {
+    // Paddy areas: what a field asks of its intakes depends on its pond AFTER the column tail of this step (ponding,
+    // wflow_sbm.py:762-772 inside sbm_cell), and the intakes' demand is met by the overland / river tasks of the same
+    // step.  So the sweep runs twice over the same schedule: subsurface flow + column tail, the areas' demand, then the
+    // overland and river waves (every task reads its own cell's hand-offs and the level above: same results as one sweep).
+    const uint32_t *all = m->dm.tick_total, *tt = nullptr;
+    if (int rc = sweep_mask_totals(m, 1, &tt)) return rc;
+    m->dm.task_mask = 1; m->dm.tick_total = tt;
+    if (int rc = launch_lateral<ML>(m)) return rc;
+    k_paddy_demand<<<(unsigned)m->paddy.n, 256, 0, m->stream>>>(m->dm, m->paddy, m->dm.obj_inflow ? m->d_obj_inflow : nullptr);
+    if (int rc = sweep_mask_totals(m, 6, &tt)) return rc;
+    m->dm.task_mask = 6; m->dm.tick_total = tt;
+    const int rc2 = launch_lateral<ML>(m);
+    m->dm.task_mask = 7; m->dm.tick_total = all;
+    if (rc2) return rc2;
+    m->launches += 2;
+  } else if (int rc = launch_lateral<ML>(m)) {
+    return rc;
+  }
   m->launches++;
   if (m->timed) cudaEventRecord(e2, m->stream);
   m->ev_last[0] = e0; m->ev_last[1] = e1; m->ev_last[2] = e2;
@@ -556,6 +579,11 @@ int launch_step(wf_model *m) {
   }
   if (m->irri.n > 0) {  // what the intakes were given -> extra water of the areas in the next step (:3314-3328)
     k_irrigation_supply<<<(unsigned)m->irri.n, 256, 0, m->stream>>>(m->dm, m->irri, m->sup.sws);
+    m->launches++;
+  }
+  if (m->paddy.n > 0) {  // :3330-3346 (cover(.., 0): no supply outside the cells that asked)
+    CUDA_OK(cudaMemsetAsync(m->dm.f[F_IRSupplymm], 0, sizeof(float) * (size_t)n, m->stream));
+    k_paddy_supply<<<(unsigned)m->paddy.n, 256, 0, m->stream>>>(m->dm, m->paddy, m->sup.sws);
     m->launches++;
   }
   if (end_out) {
@@ -614,32 +642,36 @@ int dispatch_step(wf_model *m) {
 
 // Everything of the sweep that depends on the sub-step counts: ticks per group, items per tick, the
 // busiest tick, shared-memory need.  Called at creation and by wf_set_substeps.
-int setup_sweep(wf_model *m) {
-  DevModel &dm = m->dm;
+// Items of every tick of every group for the task subset `mask` (mirrors sweep_group's item space, lateral.cuh).
+void sweep_tick_totals(const wf_model *m, int mask, std::vector<GroupDesc> *gd_out, std::vector<uint32_t> &tick_total, int64_t *most_out) {
+  const DevModel &dm = m->dm;
   const int itR = dm.itR;
   const int G = m->lay.ngroups;
-  std::vector<GroupDesc> gd((size_t)G);
-  std::vector<uint32_t> tick_total;  // items of every tick of every group (lateral.cuh: tick item space)
   int64_t most = 0;
   const int Dn = (int)m->net.nlevels(), Dr = (int)m->rnet.nlevels(), shift = Dn - Dr;
+  tick_total.clear();
+  if (gd_out) gd_out->assign((size_t)G, GroupDesc());
   for (int g = 0; g < G; g++) {
-    gd[(size_t)g].lev_idx = (uint32_t)m->lay.lev_idx[(size_t)g];
-    gd[(size_t)g].rlev_idx = (uint32_t)m->rlay.lev_idx[(size_t)g];
-    gd[(size_t)g].lev0 = m->lay.lev0[(size_t)g];
-    gd[(size_t)g].rlev0 = m->rlay.lev0[(size_t)g];
     const uint32_t *lo = m->lay.lev_off.data() + m->lay.lev_idx[(size_t)g];
     const uint32_t *ro = m->rlay.lev_off.data() + m->rlay.lev_idx[(size_t)g];
     const int l0 = m->lay.lev0[(size_t)g], r0 = m->rlay.lev0[(size_t)g];
     const int nl = Dn - l0, nrl = Dr - r0;
-    const bool rivers = r0 < Dr && (dm.task_mask & 4);
+    const bool rivers = r0 < Dr && (mask & 4);
     const int nticks = wf_sweep_ticks(nl, r0 < Dr, itR);
-    gd[(size_t)g].tick_idx = (uint32_t)tick_total.size();
-    gd[(size_t)g].nticks = nticks;
-    for (int t = 0; t < nticks; t++) {  // mirrors sweep_group's item space (lateral.cuh)
+    if (gd_out) {
+      GroupDesc &d = (*gd_out)[(size_t)g];
+      d.lev_idx = (uint32_t)m->lay.lev_idx[(size_t)g];
+      d.rlev_idx = (uint32_t)m->rlay.lev_idx[(size_t)g];
+      d.lev0 = l0;
+      d.rlev0 = r0;
+      d.tick_idx = (uint32_t)tick_total.size();
+      d.nticks = nticks;
+    }
+    for (int t = 0; t < nticks; t++) {
       uint32_t items = 0;
       const int t1 = t - WF_OVL_LAG;
-      if (t < nl && (dm.task_mask & 1)) items += ((lo[t + 1] - lo[t]) + 31u) & ~31u;
-      if (t1 >= 0 && t1 < nl && (dm.task_mask & 2)) items += ((lo[t1 + 1] - lo[t1]) + 31u) & ~31u;
+      if (t < nl && (mask & 1)) items += ((lo[t + 1] - lo[t]) + 31u) & ~31u;
+      if (t1 >= 0 && t1 < nl && (mask & 2)) items += ((lo[t1 + 1] - lo[t1]) + 31u) & ~31u;
       if (rivers)
         for (int v = 0; v < itR; v++) {
           const int q = wf_sweep_q0(l0, shift, r0) + t - v;
@@ -650,6 +682,36 @@ int setup_sweep(wf_model *m) {
     most = std::max(most, (m->lay.lev_idx[(size_t)g + 1] - m->lay.lev_idx[(size_t)g]) +
                               (m->rlay.lev_idx[(size_t)g + 1] - m->rlay.lev_idx[(size_t)g]) + (int64_t)nticks);
   }
+  if (most_out) *most_out = most;
+}
+
+// The sweep restricted to a subset of its tasks (bit0 subsurface, bit1 overland, bit2 river): same groups and ticks, other
+// tick sizes.  Returns the device array of the subset's tick sizes (cached until setup_sweep runs again).
+int sweep_mask_totals(wf_model *m, int mask, const uint32_t **out) {
+  auto it = m->tick_total_of_mask.find(mask);
+  if (it == m->tick_total_of_mask.end()) {
+    std::vector<uint32_t> tt;
+    sweep_tick_totals(m, mask, nullptr, tt, nullptr);
+    uint32_t *d = nullptr;
+    CUDA_OK(cudaMalloc(&d, std::max<size_t>(sizeof(uint32_t) * tt.size(), 16)));
+    CUDA_OK(cudaMemcpyAsync(d, tt.data(), sizeof(uint32_t) * tt.size(), cudaMemcpyHostToDevice, m->stream));
+    CUDA_OK(cudaStreamSynchronize(m->stream));
+    it = m->tick_total_of_mask.emplace(mask, d).first;
+  }
+  *out = it->second;
+  return WF_OK;
+}
+
+int setup_sweep(wf_model *m) {
+  DevModel &dm = m->dm;
+  const int itR = dm.itR;
+  const int G = m->lay.ngroups;
+  std::vector<GroupDesc> gd;
+  std::vector<uint32_t> tick_total;  // items of every tick of every group (lateral.cuh: tick item space)
+  int64_t most = 0;
+  sweep_tick_totals(m, dm.task_mask, &gd, tick_total, &most);
+  for (auto &kv : m->tick_total_of_mask) cudaFree(kv.second);
+  m->tick_total_of_mask.clear();
   cudaFree(m->d_tick_total);
   cudaFree(m->d_groups);
   m->d_tick_total = nullptr;
@@ -774,6 +836,9 @@ int check_ready(wf_model *m) {
       if (int rc = need(id)) return rc;
   if (m->dm.f[F_LAI])
     for (int id : kRequiredLAI)
+      if (int rc = need(id)) return rc;
+  if (m->paddy.n > 0)
+    for (int id : {F_h_p, F_h_max, F_h_min})
       if (int rc = need(id)) return rc;
   return WF_OK;
 }
@@ -1397,7 +1462,7 @@ static int create_impl(wf_model *m, const wf_config *cfg, wf_schedule *sched, co
     if (m->hbv != ((g_fields[id].kind & K_HBV) != 0) && !(m->hbv && (channel || id == F_GlacierStore))) continue;
     if (id >= F_UStoreLayerDepth_0 && id <= F_UStoreLayerDepth_7 && id - F_UStoreLayerDepth_0 >= m->ML) continue;
     if (id == F_GlacierStore && !cfg->glacier) continue;
-    if (id == F_ReservoirVolume || id == F_LakeWaterLevel) continue;  // created with the objects
+    if (id == F_ReservoirVolume || id == F_LakeWaterLevel || id == F_PondingDepth) continue;  // created with the objects
     if ((rc = ensure_field(m, id))) return rc;
   }
   CUDA_OK(cudaStreamSynchronize(m->stream));
@@ -1451,6 +1516,9 @@ void wf_destroy(wf_model *m) {
   for (void *p : m->reservoirs.owned) cudaFree(p);
   for (void *p : m->lakes.owned) cudaFree(p);
   for (void *p : m->irri_owned) cudaFree(p);
+  for (void *p : m->paddy_owned) cudaFree(p);
+  for (auto &kv : m->tick_total_of_mask) cudaFree(kv.second);
+  cudaFree(m->dm.h_pondsrc);
   cudaFree(m->d_ah_progress); cudaFree(m->d_ah_queue); cudaFree(m->d_ah_order); cudaFree(m->d_ah_need); cudaFree(m->d_ah_rank);
   cudaFree(m->d_obj_inflow); cudaFree(m->d_mw_flux);
   cudaFree(m->sup.sws); cudaFree(m->sup.old_inwater); cudaFree(m->sup.delta); cudaFree(m->sup.any_neg);
@@ -1927,7 +1995,7 @@ int wf_step_pipelined(wf_model *m, int nsteps, float *gauge_out, float mv, int a
   if (m->cfg.model_snow && !m->pipe_has[2]) return fail(WF_EINVAL, "pipelined forcing not set: TEMP");
   if (m->dm.task_mask != 7) return fail(WF_EUNSUPPORTED, "WF_LATERAL_TASKS is a development aid of the per-step sweep");
   if (gauge_out && m->pipe_gauges < 0) return fail(WF_EINVAL, "no gauge set registered (wf_pipeline_capture)");
-  if (m->reservoirs.dev.n + m->lakes.dev.n > 0 || m->mass_wasting || m->abstractions || m->irri.n > 0)
+  if (m->reservoirs.dev.n + m->lakes.dev.n > 0 || m->mass_wasting || m->abstractions || m->irri.n > 0 || m->paddy.n > 0)
     return fail(WF_EUNSUPPORTED, "reservoirs, lakes, mass wasting, abstractions and irrigation need the per-step path (wf_step)");
   if (end_outputs_requested(m))
     return fail(WF_EUNSUPPORTED, "the end-of-dynamic() outputs (mass balances, cumulative sums ...) need the per-step path (wf_step)");
@@ -2281,14 +2349,15 @@ int wf_lakes_create(wf_model *m, const int32_t *locs, const int32_t *linked, con
   return n;
 }
 
-int wf_irrigation_create(wf_model *m, const int32_t *areas, const int32_t *intakes) {
+// id rasters of areas and of the river intakes that carry their ids -> the device form both kinds of irrigation use
+static int build_area_intakes(wf_model *m, const int32_t *areas, const int32_t *intakes, IrrigationSet &s, std::vector<void *> &owned) {
   if (!m || !areas || !intakes) return fail(WF_EINVAL, "null argument");
   if (m->hbv) return fail(WF_EUNSUPPORTED, "irrigation areas are not available for wflow_hbv models");
   CUDA_OK(cudaSetDevice(m->cfg.device));
   CUDA_OK(cudaStreamSynchronize(m->stream));
-  for (void *p : m->irri_owned) cudaFree(p);
-  m->irri_owned.clear();
-  m->irri = IrrigationSet();
+  for (void *p : owned) cudaFree(p);
+  owned.clear();
+  s = IrrigationSet();
   const int64_t N = (int64_t)m->cfg.nrow * m->cfg.ncol;
   // areas: the ids present on network cells, ascending (np.unique of idtoid); cells of an area in raster order
   std::vector<int32_t> ids;
@@ -2329,12 +2398,11 @@ int wf_irrigation_create(wf_model *m, const int32_t *areas, const int32_t *intak
     void *d = nullptr;
     CUDA_OK(cudaMalloc(&d, std::max<size_t>(bytes, 16)));
     if (bytes) CUDA_OK(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
-    m->irri_owned.push_back(d);
+    owned.push_back(d);
     *dst = d;
     return WF_OK;
   };
   int rc;
-  IrrigationSet &s = m->irri;
   if ((rc = up(ids.data(), sizeof(int32_t) * ids.size(), (const void **)&s.id))) return rc;
   if ((rc = up(seg.data(), sizeof(int32_t) * seg.size(), (const void **)&s.seg))) return rc;
   if ((rc = up(perm.data(), sizeof(int32_t) * perm.size(), (const void **)&s.perm))) return rc;
@@ -2346,11 +2414,38 @@ int wf_irrigation_create(wf_model *m, const int32_t *areas, const int32_t *intak
   std::vector<float> z((size_t)n, 0.0f);
   if ((rc = up(z.data(), sizeof(float) * z.size(), (const void **)&s.sqm))) return rc;
   s.n_orphan = (int32_t)orphan_rs.size();
+  return n;
+}
+
+int wf_irrigation_create(wf_model *m, const int32_t *areas, const int32_t *intakes) {
+  if (!m || !areas || !intakes) return fail(WF_EINVAL, "null argument");
+  if (m->paddy.n > 0) return fail(WF_EUNSUPPORTED, "irrigation areas together with paddy areas are not supported (the reference lets the paddy supply overwrite the other)");
+  const int n = build_area_intakes(m, areas, intakes, m->irri, m->irri_owned);
+  if (n <= 0) return n;
+  int rc;
   // the demand is an abstraction; its inputs are outputs of the column
   for (int id : {F_Inflow, F_IRSupplymm, F_PotTrans, F_Transpiration})
     if ((rc = ensure_field(m, id))) return rc;
   if ((rc = wf_set_option(m, "Abstractions", 1.0))) return rc;
-  s.n = n;  // (last: the step launches the irrigation kernels from here on)
+  m->irri.n = n;  // (last: the step launches the irrigation kernels from here on)
+  return n;
+}
+
+int wf_paddy_create(wf_model *m, const int32_t *areas, const int32_t *intakes) {
+  if (!m || !areas || !intakes) return fail(WF_EINVAL, "null argument");
+  if (m->irri.n > 0) return fail(WF_EUNSUPPORTED, "paddy areas together with irrigation areas are not supported (the reference lets the paddy supply overwrite the other)");
+  const int n = build_area_intakes(m, areas, intakes, m->paddy, m->paddy_owned);
+  if (n <= 0) return n;
+  int rc;
+  for (int id : {F_Inflow, F_IRSupplymm, F_PondingDepth, F_IrriDemandm3})
+    if ((rc = ensure_field(m, id))) return rc;
+  if (!m->dm.h_pondsrc) {
+    CUDA_OK(cudaMalloc(&m->dm.h_pondsrc, sizeof(float) * (size_t)std::max<int64_t>(m->n, 1)));
+    CUDA_OK(cudaMemset(m->dm.h_pondsrc, 0, sizeof(float) * (size_t)std::max<int64_t>(m->n, 1)));
+  }
+  if ((rc = wf_set_option(m, "Abstractions", 1.0))) return rc;
+  m->dm.paddy = 1;
+  m->paddy.n = n;  // (last: the step launches the paddy kernels from here on)
   return n;
 }
 

@@ -53,6 +53,9 @@ enum FieldKind : int { K_FORCING = 0, K_STATIC = 1, K_STATE = 2, K_DIAG = 3, K_R
   X(GlacierStore, K_STATE) X(ReservoirVolume, K_STATE) X(LakeWaterLevel, K_STATE)                  \
   /* irrigation (wflow_sbm.py:2034, 2755, 3314-3328): the supply of a step is extra water of the next one */ \
   X(IRSupplymm, K_STATE)                                                                           \
+  /* paddy areas (wflow_sbm.py:762-785, 2812-2815, 3033-3050, 3330-3346; wf_paddy_create): the pond on the field, its bund   \
+   * height and the depths that trigger and size the irrigation; CRPST is the crop-stage multiplier of the user's ini */  \
+  X(PondingDepth, K_STATE) X(h_p, K_STATIC) X(h_max, K_STATIC) X(h_min, K_STATIC) X(CRPST, K_FORCING)                     \
   /* diagnostics, materialised only on request */                                                  \
   X(SatWaterDepth, K_DIAG) X(Precipitation, K_DIAG) X(PotenEvap, K_DIAG) X(Temperature, K_DIAG)    \
   X(ThroughFall, K_DIAG) X(StemFlow, K_DIAG) X(Interception, K_DIAG) X(PotTransSoil, K_DIAG)       \
@@ -89,7 +92,7 @@ enum FieldKind : int { K_FORCING = 0, K_STATIC = 1, K_STATE = 2, K_DIAG = 3, K_R
   X(CumExfiltWater, K_DIAG) X(CumSurfaceWater, K_DIAG)                                             \
   X(OutflowSR, K_DIAG) X(ResPercFull, K_DIAG) X(ResPrecipSR, K_DIAG) X(ResEvapSR, K_DIAG)          \
   X(DemandRelease, K_DIAG) X(LakeOutflow, K_DIAG) X(LakeVolume, K_DIAG) X(LakePrecip, K_DIAG)      \
-  X(LakeEvap, K_DIAG) X(IrriDemand, K_DIAG) X(IrriDemandm3, K_DIAG)                                  \
+  X(LakeEvap, K_DIAG) X(IrriDemand, K_DIAG) X(IrriDemandm3, K_DIAG) X(ActEvapPond, K_DIAG) X(irr_depth, K_DIAG)      \
   /* wflow_hbv (wflow/wflow_hbv.py:560-900 parameters, :131-163 states, :1222-1767 dynamic(); hbv.cuh).  Shared with the   \
    * rows above: P PET TEMP Inflow, TempCor TTI TT Cfmax WHC xl yl, the glacier rows, DCL Bw and AlphaR (= Alpha), the       \
    * channel states RiverRunoff(sub) / WaterLevelR(sub) (= SurfaceRunoff(sub) / WaterLevel(sub)) and some outputs */        \

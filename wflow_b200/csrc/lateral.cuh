@@ -574,8 +574,18 @@ __device__ __forceinline__ void task_subsurface(const DevModel &m, const int64_t
     for (int k = 0; k < ML; k++) m.f[F_UStoreLayerDepth_0 + k][i] = (float)U[k];
   }
   const double ExfiltWater = ExfiltSatWater + ExfiltFromUstore;
-  // InwaterO :774 -- ExfiltWater + [ExcessWater + InfiltExcess + RunoffLandCells - ActEvapOpenWaterLand]
-  const double InwaterO = qdiv(pymax(ExfiltWater + surplus, 0.0) * xlyl * 0.001, m.dt);
+  // a paddy field keeps what would run off, up to its bund (:762-772): the pond takes it before the overland wave sees it
+  double ponding_add = 0.0;
+  if (DIAG && m.paddy) {
+    const double hp = (double)__ldg(m.f[F_h_p] + i);
+    if (hp > 0) {
+      const double pond = (double)m.f[F_PondingDepth][i];
+      ponding_add = pymin(ExfiltWater + (double)m.h_pondsrc[i], hp - pond);
+      m.f[F_PondingDepth][i] = (float)(pond + ponding_add);
+    }
+  }
+  // InwaterO :774 -- ExfiltWater + [ExcessWater + InfiltExcess + RunoffLandCells - ActEvapOpenWaterLand] - ponding_add
+  const double InwaterO = qdiv(pymax(ExfiltWater + surplus - ponding_add, 0.0) * xlyl * 0.001, m.dt);
   m.h_inwO[i] = InwaterO;
 
   double sumU = 0.0;

@@ -400,6 +400,95 @@ __global__ void __launch_bounds__(256) k_irrigation_supply(const DevModel m, con
   for (int p = s.seg[a] + threadIdx.x; p < s.seg[a + 1]; p += blockDim.x) m.f[F_IRSupplymm][s.perm[p]] = out;
 }
 
+// ---- paddy areas (wflow_sbm.py:3033-3050, 3330-3346; idtoid, wflow_lib.py:81-101) -----------------------------------------
+// A paddy cell whose pond has fallen below h_min asks for the water that fills it to h_max, times the crop stage:
+// irr_depth = ifthenelse(PondingDepth < h_min, h_max - PondingDepth, 0) * CRPST [mm], and the reference turns that into
+// IrriDemandm3 = irr_depth / 1000 * areatotal(xl * yl, area) PER CELL (the area's whole surface, not the cell's -- kept).
+// idtoid hands the intakes of the area np.mean of that map over the area's cells, times -1 / timestepsecs, as their Inflow;
+// a mean of exactly 0 is a missing value there and leaves the intake alone.  After the supply iteration the cells that asked
+// (IrriDemandm3 > 0) share what their intakes were given: IRSupplymm = mean(SurfaceWaterSupply of the intakes) * timestepsecs
+// * 1000 / areatotal(xl * yl, the cells that asked), 0 everywhere else.  idtoid's left-overs as for the irrigation areas.
+// Runs between the subsurface sweep (which ponds) and the overland / river sweep (which meets the demand).
+__global__ void __launch_bounds__(256) k_paddy_demand(const DevModel m, const IrrigationSet s, float *obj_inflow) {
+  __shared__ double sh[256];
+  __shared__ float s_sqm;
+  const int a = blockIdx.x;
+  const int beg = s.seg[a], end = s.seg[a + 1];
+  double sa = 0.0;
+  for (int p = beg + threadIdx.x; p < end; p += blockDim.x) {
+    const int i = s.perm[p];
+    sa += (double)(m.f[F_xl][i] * m.f[F_yl][i]);
+  }
+  sa = irri_block_sum(sa, sh);
+  if (threadIdx.x == 0) s_sqm = (float)sa;  // pcr.areatotal
+  __syncthreads();
+  const float sqm = s_sqm;
+  double sm = 0.0, sq = 0.0;
+  for (int p = beg + threadIdx.x; p < end; p += blockDim.x) {
+    const int i = s.perm[p];
+    const float pond = m.f[F_PondingDepth][i];
+    const float crpst = m.f[F_CRPST] ? m.f[F_CRPST][i] : 1.0f;
+    const float irr = ((pond < m.f[F_h_min][i]) ? (m.f[F_h_max][i] - pond) : 0.0f) * crpst;  // :3034-3039
+    const float m3 = (irr / 1000.0f) * sqm;                                                  // :3041
+    if (m.f[F_irr_depth]) m.f[F_irr_depth][i] = irr;
+    m.f[F_IrriDemandm3][i] = m3;
+    sm += (double)m3;
+    if (m3 > 0.0f) sq += (double)(m.f[F_xl][i] * m.f[F_yl][i]);
+  }
+  sm = irri_block_sum(sm, sh);
+  sq = irri_block_sum(sq, sh);
+  if (threadIdx.x == 0) {
+    s.sqm[a] = (float)sq;  // areatotal over the cells that asked (:3337-3342), for k_paddy_supply
+    const int cnt = end - beg;
+    float mean;
+    if (cnt <= 128) {  // np.mean of float32 values in raster order (numpy's pairwise sum up to 128 values)
+      float tmp[128];
+      for (int j = 0; j < cnt; j++) tmp[j] = m.f[F_IrriDemandm3][s.perm[beg + j]];
+      mean = irri_np_mean(tmp, cnt);
+    } else {
+      mean = (float)(sm / (double)cnt);  // (numpy adds blocks of 128 pairwise in float32; within its rounding of this)
+    }
+    const float scale = (float)(-1.0 / m.dt);
+    const float v = (mean == 0.0f) ? 0.0f : mean * scale;  // exactly 0: missing in idtoid's result, the intake keeps its Inflow (none)
+    for (int k = s.in_seg[a]; k < s.in_seg[a + 1]; k++) {
+      const int rs = s.in_rs[k];
+      m.f[F_Inflow][rs] = v;
+      if (obj_inflow) obj_inflow[rs] = v;
+    }
+    if (a == 0)
+      for (int k = 0; k < s.n_orphan; k++) {  // an intake without an area keeps idtoid's initial value: its own id
+        const float v0 = (float)s.orphan_id[k] * scale;
+        m.f[F_Inflow][s.orphan_rs[k]] = v0;
+        if (obj_inflow) obj_inflow[s.orphan_rs[k]] = v0;
+      }
+  }
+}
+
+// after the supply iteration (IRSupplymm zeroed before the launch)
+__global__ void __launch_bounds__(256) k_paddy_supply(const DevModel m, const IrrigationSet s, const float *sws) {
+  __shared__ float sv;
+  const int a = blockIdx.x;
+  if (threadIdx.x == 0) {
+    const int kb = s.in_seg[a], k = s.in_seg[a + 1] - kb;
+    float val;
+    if (k == 0) {
+      val = (float)s.id[a];  // idtoid: no source point with this id, the area keeps its id as the value
+    } else {
+      float tmp[128];
+      const int kk = k < 128 ? k : 128;
+      for (int j = 0; j < kk; j++) tmp[j] = sws[s.in_rs[kb + j]];
+      val = irri_np_mean(tmp, kk);
+    }
+    sv = (val == 0.0f) ? 0.0f : ((val * (float)m.dt) * 1000.0f) / s.sqm[a];  // :3344-3346
+  }
+  __syncthreads();
+  const float out = sv;
+  for (int p = s.seg[a] + threadIdx.x; p < s.seg[a + 1]; p += blockDim.x) {
+    const int i = s.perm[p];
+    if (m.f[F_IrriDemandm3][i] > 0.0f) m.f[F_IRSupplymm][i] = out;
+  }
+}
+
 // ---- abstractions: Inflow < 0 (wflow_sbm.py:3131-3146, 3203-3308) ---------------------------------------
 // The demand of a river cell is met from what reaches it: SurfaceWaterSupply = min(upstream(RiverRunoff) + Inwater, -Inflow).
 // The first estimate is made inside the sweep (task_overland); the reference then repeats { new estimate from the routed

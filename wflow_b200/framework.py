@@ -11,7 +11,7 @@ outmaps, outsum), [run] [model] [layout] [inputmapstacks] [modelparameters] [var
 [variable_change_timestep] [outputmaps] [outputcsv_N] [outputtss_N] [summary] [summary_sum|avg|min|max] [API],
 cold start (reinit = 1) and warm start, wf_suspend / wf_resume, wf_setValues*, wf_supplyMapAsNumpy,
 wf_supplyVariableNamesAndRoles, wf_QuickSuspend/Resume, LAI-driven canopy parameters, the command line.
-Not covered (out of scope): netCDF I/O (refused loudly), reservoirs / lakes, irrigation, state
+Not covered (out of scope): netCDF I/O (refused loudly), state
 updating, [rollingmean].
 
 The derivations of `initial()` that need PCRaster neighbourhood operators (slope from the DEM, window
@@ -368,9 +368,20 @@ class WflowSbm:
             self._mod.set_option("MassWasting", 1)
         ids = lambda name: None if self._staticmap(name) is None else np.nan_to_num(self._staticmap(name), nan=0.0).astype(np.int32)  # noqa: E731
         paddy = ids("staticmaps/wflow_irrigationpaddyareas.map")
-        if paddy is not None and (paddy > 0).any():
-            raise ValueError("staticmaps/wflow_irrigationpaddyareas.map: paddy irrigation (nrpaddyirri > 0) is not part of this implementation")
         areas, intakes = ids("staticmaps/wflow_irrigationareas.map"), ids("staticmaps/wflow_irrisurfaceintake.map")
+        self._paddy = False
+        if paddy is not None and (paddy > 0).any():  # :1116-1165, 1639-1641 (nrpaddyirri > 0)
+            if areas is not None and (areas > 0).any():
+                raise ValueError("paddy areas together with irrigation areas are not part of this implementation "
+                                 "(the reference lets the paddy supply overwrite the other, wflow_sbm.py:3330-3346)")
+            for fld, fname in (("h_max", "wflow_hmax.map"), ("h_min", "wflow_hmin.map"), ("h_p", "wflow_hp.map")):
+                v = self._staticmap("staticmaps/" + fname)
+                self._mod.set(fld, np.zeros(self.shape, F32) if v is None else np.nan_to_num(v, nan=0.0).astype(F32))
+            n = self._mod.paddy_create(paddy, np.zeros(self.shape, np.int32) if intakes is None else intakes)
+            self._abstractions = True
+            self._paddy = True
+            self.logger.info("%d paddy areas (CRPST: the crop-stage parameter of [modelparameters], 1 when absent)" % n)
+            return
         if areas is not None and (areas > 0).any():
             returns = ids("staticmaps/wflow_irrisurfacereturns.map")
             if returns is not None and (returns > 0).any():
@@ -391,6 +402,8 @@ class WflowSbm:
                 continue
             else:
                 out.append(s)
+        if getattr(self, "_paddy", False):  # stateVariables(), wflow_sbm.py:1007-1009
+            out.append("PondingDepth")
         return out
 
     def _runResume(self):
@@ -483,7 +496,7 @@ class WflowSbm:
     # parameters that are library fields as they stand (no derived static depends on them)
     _DIRECT = ("LAI", "Sl", "Swood", "Kext", "RootingDepth", "Cmax", "CanopyGapFraction", "EoverR", "et_RefToPot",
                "PathFrac", "rootdistpar", "CapScale", "AirEntryPressure", "MaxLeakage", "WaterFrac", "TempCor",
-               "Inflow", "DemandReturnFlowFraction")
+               "Inflow", "DemandReturnFlowFraction", "CRPST", "h_p", "h_max", "h_min")
 
     def _read_modelparameters(self):
         """name = stack,type,default,verbose[,lookupmap_1,...]"""
