@@ -122,7 +122,8 @@ class RefHbv:
         m.WaterLevelsub = m.WaterLevel
         m.KinWaveVolume = m.WaterLevel * m.Bw * m.DCL
         m.OldKinWaveVolume = m.KinWaveVolume
-        m.initstorage = m.FreeWater + m.DrySnow + m.SoilMoisture + m.UpperZoneStorage + m.LowerZoneStorage  # :1208-1215
+        m.initstorage = (m.FreeWater + m.DrySnow + m.SoilMoisture + m.UpperZoneStorage + m.LowerZoneStorage
+                         + m.InterceptionStorage)  # :1208-1215
         # ---- numpy mirror and network, :1100-1132 ----
         n = self.shape[0] * self.shape[1]
         g = lambda x: pcr.pcr2numpy(x, MV).ravel()  # noqa: E731

@@ -9,6 +9,8 @@ of reference files) but travels to the GPU box with gpurun.  Run in the build co
   API, so only 8 static maps + the lookup tables + the ini are needed, ~1 MB; plus what its dynamic-vegetation
   variant, tests/test_wflow_sbm_dynveg.py, reads: 3 tables, the land-cover map, 2 months of LAI)
       -> baseline/_ref/ref_cases/wflow_sbm/
+* tests/wflow_hbv (the case of the reference's tests/test_wflow_hbv.py; static maps + tables + ini)
+      -> baseline/_ref/ref_cases/wflow_hbv/
 * examples/wflow_rhine_sbm (the case of tests/test_wflow_sbm_example.py; 132 MB with its forcing)
       -> baseline/_ref/wflow_rhine_sbm/
 """
@@ -38,6 +40,15 @@ def main():
     for f in ("LC.map", "LCtoBranchTrunkStorage.tbl", "LCtoExtinctionCoefficient.tbl", "LCtoSpecificLeafStorage.tbl",
               "LAI00000.001", "LAI00000.002"):
         shutil.copyfile(os.path.join(src, "inmaps", "clim", f), os.path.join(dst, "inmaps", "clim", f))
+    # tests/wflow_hbv (the case of the reference's tests/test_wflow_hbv.py: cold start, forcing through the API)
+    hsrc = os.path.join(REF, "tests", "wflow_hbv")
+    hdst = os.path.join(ROOT, "baseline", "_ref", "ref_cases", "wflow_hbv")
+    os.makedirs(os.path.join(hdst, "staticmaps"), exist_ok=True)
+    for m in MAPS:
+        shutil.copyfile(os.path.join(hsrc, "staticmaps", m + ".map"), os.path.join(hdst, "staticmaps", m + ".map"))
+    shutil.copytree(os.path.join(hsrc, "intbl"), os.path.join(hdst, "intbl"), dirs_exist_ok=True)
+    shutil.copyfile(os.path.join(hsrc, "wflow_hbv.ini"), os.path.join(hdst, "wflow_hbv.ini"))
+    os.system("chmod -R u+w '%s'" % hdst)
     rh = os.path.join(ROOT, "baseline", "_ref", "wflow_rhine_sbm")
     if not os.path.isdir(rh):
         shutil.copytree(os.path.join(REF, "examples", "wflow_rhine_sbm"), rh)

@@ -617,6 +617,10 @@ int launch_step_hbv(wf_model *m) {
   m->launches++;
   if (m->timed) cudaEventRecord(e2, m->stream);
   m->ev_last[0] = e0; m->ev_last[1] = e1; m->ev_last[2] = e2;
+  if (m->dm.f[F_sumlevel] || m->dm.f[F_SurfaceRunoffMM]) {
+    k_hbv_post<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->dm);
+    m->launches++;
+  }
   CUDA_OK(cudaGetLastError());
   return WF_OK;
 }
@@ -1069,7 +1073,7 @@ int run_overlap(wf_model *m, int nsteps) {
     }
     const int threads = wf_block_threads(m->lat_mode);
     const size_t smem = ((m->lat_smem + 15) & ~(size_t)15) + StageLayout<ML>::bytes(threads);
-    void *fn = (m->lat_mode == WF_CLUSTER_WIDE) ? (void *)k_lateral_wave<ML, WF_CLUSTER_WIDE, false> : (void *)k_lateral_wave<ML, WF_CLUSTER, false>;
+    void *fn = (m->lat_mode == WF_CLUSTER_WIDE) ? (void *)k_lateral_wave<ML, WF_CLUSTER_WIDE, false, true> : (void *)k_lateral_wave<ML, WF_CLUSTER, false, true>;
     if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned vblocks = (unsigned)((m->n + WF_VERT_THREADS - 1) / WF_VERT_THREADS);
     for (int s = 0; s < nsteps && rc == WF_OK; s++) {
@@ -1842,6 +1846,12 @@ int wf_request_output(wf_model *m, const char *name, int enable) {
           if (int rc = ensure_field(m, d)) return rc;
       if (id >= F_vwc_perc_0 && id <= F_vwc_perc_7)
         if (int rc = ensure_field(m, F_vwc_0 + (id - F_vwc_perc_0))) return rc;
+    }
+    if (m->hbv) {  // wflow_hbv's water balance is formed from its sums (hbv.cuh)
+      if (id == F_watbal)
+        for (int d : {F_initstorage, F_sumprecip, F_sumsoilevap, F_sumrunoff})
+          if (int rc = ensure_field(m, d)) return rc;
+      return WF_OK;
     }
     if (id == F_SoilWatbal || id == F_watbal) {
       if (!m->dm.h_wb) CUDA_OK(cudaMalloc(&m->dm.h_wb, sizeof(double) * std::max<int64_t>(m->n, 1)));

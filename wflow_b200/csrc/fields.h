@@ -108,7 +108,11 @@ enum FieldKind : int { K_FORCING = 0, K_STATIC = 1, K_STATE = 2, K_DIAG = 3, K_R
   X(DirectRunoff, K_DIAG | K_HBV) X(InUpperZone, K_DIAG | K_HBV) X(Percolation, K_DIAG | K_HBV)                            \
   X(QuickFlow, K_DIAG | K_HBV) X(RealQuickFlow, K_DIAG | K_HBV) X(BaseFlow, K_DIAG | K_HBV) X(InSoil, K_DIAG | K_HBV)      \
   X(NetInSoil, K_DIAG | K_HBV) X(RainAndSnowmelt, K_DIAG | K_HBV) X(QuickFlowCubic, K_DIAG | K_HBV)                        \
-  X(BaseFlowCubic, K_DIAG | K_HBV)
+  X(BaseFlowCubic, K_DIAG | K_HBV)                                                                                        \
+  /* water balance of wflow_hbv (:1208-1215, 1731-1766): the sums accumulate from the start of the run */                  \
+  X(initstorage, K_STATIC | K_HBV) X(storage, K_DIAG | K_HBV) X(sumprecip, K_DIAG | K_HBV) X(sumevap, K_DIAG | K_HBV)     \
+  X(sumrunoff, K_DIAG | K_HBV) X(sumlevel, K_DIAG | K_HBV) X(sumpotevap, K_DIAG | K_HBV) X(sumsoilevap, K_DIAG | K_HBV)   \
+  X(sumtemp, K_DIAG | K_HBV) X(suminflow, K_DIAG | K_HBV) X(SurfaceRunoffMM, K_DIAG | K_HBV)
 
 enum FieldId : int {
 #define X(n, k) F_##n,

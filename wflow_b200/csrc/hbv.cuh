@@ -167,6 +167,31 @@ __global__ void __launch_bounds__(256) k_hbv_column(const DevModel m, const HbvO
   HOUT(BaseFlow, BaseFlow); HOUT(InSoil, InSoil); HOUT(RainAndSnowmelt, RainAndSnowmelt); HOUT(NetInSoil, NetInSoil);
   HOUT(InwaterMM, InwaterMM); HOUT(QuickFlowCubic, (QuickFlow + RealQuickFlow) * ToCubic); HOUT(BaseFlowCubic, BaseFlow * ToCubic);
   HOUT(SurfaceWaterSupply, SWS);
+  // ---- water balance (:1731-1766): storage of the cell, sums since the start of the run ----
+  const float storage = (((FreeWater + DrySnow) + SM) + UZ) + LZ;
+  HOUT(storage, storage);
+#define HSUM(name, v)                                          \
+  do {                                                         \
+    if (m.f[F_##name]) m.f[F_##name][i] = m.f[F_##name][i] + (v); \
+  } while (0)
+  HSUM(sumprecip, Precipitation); HSUM(sumevap, ActEvap); HSUM(sumsoilevap, SoilEvap); HSUM(sumpotevap, PotEvaporation);
+  HSUM(sumtemp, Temperature); HSUM(sumrunoff, InwaterMM); HSUM(suminflow, Inflow);
+#undef HSUM
+  if (m.f[F_watbal])  // wf_request_output made the four maps it is formed from
+    m.f[F_watbal][i] = (((m.f[F_initstorage][i] - storage) + m.f[F_sumprecip][i]) - m.f[F_sumsoilevap][i]) - m.f[F_sumrunoff][i];
+}
+
+// behind the sweep: what the water balance and the outputs read of the routed channel (:1650-1668, 1745)
+__global__ void __launch_bounds__(256) k_hbv_post(const DevModel m) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m.n) return;
+  const int32_t rs = __ldg(m.river_slot + i);
+  if (rs < 0) return;
+  if (m.f[F_sumlevel]) m.f[F_sumlevel][i] = m.f[F_sumlevel][i] + m.f[F_WaterLevelR][rs];
+  if (m.f[F_SurfaceRunoffMM]) {
+    const float QMMConv = (float)m.dt / ((m.f[F_xl][i] * m.f[F_yl][i]) * 0.001f);  // :1013
+    m.f[F_SurfaceRunoffMM][i] = m.f[F_RiverRunoff][rs] * QMMConv;
+  }
 }
 
 #undef HF

@@ -1104,7 +1104,7 @@ __device__ __forceinline__ void sweep_group(const DevModel &m, const GroupDesc g
 // during the sweep (statics, the column kernel's hand-offs, the cell's own states), so the early copy reads the same
 // values; what the neighbours produce is read behind the barrier as before.  The item itself (position, type,
 // sub-step) waits in the column too, so it takes no registers while the current item is solved.
-template <int ML, int MODE, bool DIAG>
+template <int ML, int MODE, bool DIAG, bool AHEAD = false>
 __device__ __forceinline__ void sweep_group_ahead(const DevModel &m, const GroupDesc gd, const uint32_t *lo, const uint32_t *ro,
                                                   const uint32_t *tt, const int tid, const int nthreads, WaveSync &ws, float *stage, int32_t *progress) {
   constexpr bool EARLY = wf_is_cluster(MODE);
@@ -1251,7 +1251,7 @@ __device__ __forceinline__ void sweep_group_ahead(const DevModel &m, const Group
       // behind it, is visible to whoever reads the group's progress with an acquire (column_ahead)
       // (a relaxed store: the data it announces was fenced by its writers' arrivals, MEMBAR.ALL.GPU ahead of UCGABAR_ARV,
       //  and this thread has passed the acquiring wait; a release here would put another fence on the tick's critical path)
-      if (progress && tid == 0) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(progress), "r"(t + 1) : "memory");
+      if (AHEAD && progress && tid == 0) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(progress), "r"(t + 1) : "memory");
 #ifdef WF_PROFILE
       if (pbase) prof_stamp(pbase + 13, c0, 0);
 #endif
@@ -1304,7 +1304,9 @@ __device__ __noinline__ void column_ahead(const DevModel &m) {  // (its own func
   }
 }
 
-template <int ML, int MODE, bool DIAG = true>
+// AHEAD: the build of the multi-step launch whose spare clusters run the next timestep's column (column_ahead); the
+// per-step sweep is compiled without it (the progress stores and the worker branch cost the per-step sweep 4 %).
+template <int ML, int MODE, bool DIAG = true, bool AHEAD = false>
 __global__ void __launch_bounds__(wf_block_threads(MODE), 1) k_lateral_wave(const __grid_constant__ DevModel m) {
   extern __shared__ __align__(16) uint32_t s_lev[];
   int crank = 0, csize = 1;
@@ -1316,7 +1318,7 @@ __global__ void __launch_bounds__(wf_block_threads(MODE), 1) k_lateral_wave(cons
   // grid: every block sweeps the one group; otherwise cluster (or block) c takes groups c, c + nclusters, ...
   int nclusters = (MODE == WF_GRID) ? 1 : (int)gridDim.x / csize;
   const int cid = (MODE == WF_GRID) ? 0 : (int)blockIdx.x / csize;
-  const bool ahead = wf_is_cluster(MODE) && !DIAG && m.ahead.queue != nullptr;
+  const bool ahead = AHEAD && wf_is_cluster(MODE) && !DIAG && m.ahead.queue != nullptr;
   if (ahead) {
     if (cid >= m.ahead.nsweep) {  // a cluster beyond the groups: next timestep's column tiles
       column_ahead<ML>(m);
@@ -1353,7 +1355,7 @@ __global__ void __launch_bounds__(wf_block_threads(MODE), 1) k_lateral_wave(cons
       tt = s_lev + nlo + nro;
     }
 #if WF_STAGE_AHEAD
-    if (MODE != WF_GRID) sweep_group_ahead<ML, MODE, DIAG>(m, gd, lo, ro, tt, tid, nthreads, ws, stage, ahead ? m.ahead.progress + g : nullptr);
+    if (MODE != WF_GRID) sweep_group_ahead<ML, MODE, DIAG, AHEAD>(m, gd, lo, ro, tt, tid, nthreads, ws, stage, ahead ? m.ahead.progress + g : nullptr);
     else
 #endif
     sweep_group<ML, MODE, DIAG>(m, gd, lo, ro, tt, tid, nthreads, ws, stage);

@@ -855,7 +855,7 @@ def _repair_ldd(ldd):
     return out
 
 
-def main(argv=None):
+def main(argv=None, model_class=None, configfile="wflow_sbm.ini"):
     """python -m wflow_b200.framework -C case [-R runId] [-c ini] ... -- the reference's command line for the path
     (wflow/wflow_sbm.py:3531-3645): -C case, -R run id, -c ini file, -S / -T start / end time ("YYYY-MM-DD HH:MM:SS"),
     -s timestepsecs, -I cold start (reinit), -i intbl directory, -X overwrite instate with the end state,
@@ -869,7 +869,7 @@ def main(argv=None):
         return 0
     opts, _ = getopt.getopt(args, "XL:hC:Ii:v:S:T:WR:u:s:EP:p:x:U:fOc:l:M")
     o = dict(opts)
-    m = WflowSbm(Dir=o.get("-C", "."), RunDir=o.get("-R", "run_default"), configfile=o.get("-c", "wflow_sbm.ini"))
+    m = (model_class or WflowSbm)(Dir=o.get("-C", "."), RunDir=o.get("-R", "run_default"), configfile=o.get("-c", configfile))
 
     def configset(section, var, value):
         if not m.config.has_section(section):
