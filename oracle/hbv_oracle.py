@@ -56,6 +56,11 @@ class HbvOracle:
         f["QMMConv"] = dt / ((f["xl"] * f["yl"]) * F32(0.001))      # :1013
         f["ToCubic"] = ((f["xl"] * f["yl"]) * F32(0.001)) / dt      # :1014
         f["KinWaveVolume"] = (f["WaterLevel"] * f["Bw"]) * f["DCL"]
+        # resume(), :1208-1215, and the sums of the water balance (:1015-1031)
+        f.setdefault("initstorage", (((((f["FreeWater"] + f["DrySnow"]) + f["SoilMoisture"]) + f["UpperZoneStorage"])
+                                      + f["LowerZoneStorage"]) + f["InterceptionStorage"]).astype(F32))
+        for k in ("sumprecip", "sumevap", "sumrunoff", "sumlevel", "sumpotevap", "sumsoilevap", "sumtemp", "suminflow"):
+            f[k] = zero.copy()
         self.it_kin = None
         self.out = {}
 
@@ -219,5 +224,16 @@ class HbvOracle:
                  QuickFlowCubic=(QuickFlow + RealQuickFlow) * f["ToCubic"], BaseFlowCubic=BaseFlow * f["ToCubic"],
                  SurfaceWaterSupply=SWS, SurfaceRunoffMM=f["SurfaceRunoff"] * f["QMMConv"],
                  SurfaceRunoffsubMM=f["SurfaceRunoffsub"] * f["QMMConv"], OldKinWaveVolume=old_kw, MassBalKinWave=massbal)
+        # ---- water balance, :1731-1766 ----
+        f["sumprecip"] = f["sumprecip"] + Precipitation
+        f["sumevap"] = f["sumevap"] + ActEvap
+        f["sumsoilevap"] = f["sumsoilevap"] + SoilEvap
+        f["sumpotevap"] = f["sumpotevap"] + PotEvaporation
+        f["sumtemp"] = f["sumtemp"] + Temperature
+        f["sumrunoff"] = f["sumrunoff"] + InwaterMM
+        f["sumlevel"] = f["sumlevel"] + f["WaterLevel"]
+        f["suminflow"] = f["suminflow"] + Infl
+        o["storage"] = (((f["FreeWater"] + f["DrySnow"]) + f["SoilMoisture"]) + f["UpperZoneStorage"]) + f["LowerZoneStorage"]
+        o["watbal"] = (((f["initstorage"] - o["storage"]) + f["sumprecip"]) - f["sumsoilevap"]) - f["sumrunoff"]
         for k, v in list(o.items()):
             o[k] = np.asarray(v, F32)

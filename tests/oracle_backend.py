@@ -93,3 +93,74 @@ class OracleSbmModel:
 
     def sample(self, field, flat_index, mv=-999.0):
         return self.get(field, mv).reshape(-1)[np.asarray(flat_index, np.int64)]
+
+
+class OracleHbvModel:
+    """The float32-numpy restatement of wflow_hbv's timestep (oracle/hbv_oracle.py) behind the interface of
+    wflow_b200.hbv.HbvModel: the host side of framework_hbv runs without a GPU, and the restatement is pinned against the
+    reference's own acceptance numbers (tests/test_wflow_hbv.py of the reference)."""
+
+    def __init__(self, ldd, *, timestepsecs=86400, kinwaveIters=0, kinwaveTstep=0, set_kquick_flow=0, external_qbase=0,
+                 glacier=0, device=0, beta=0.0):
+        self.shape = ldd.shape
+        self._ldd = np.asarray(ldd)
+        self._kw = dict(timestepsecs=timestepsecs, kinwaveIters=kinwaveIters, kinwaveTstep=kinwaveTstep,
+                        setKquickFlow=set_kquick_flow, externalQbase=external_qbase)
+        self._fields, self._o, self._areas = {}, None, []
+        net = O.Network(self._ldd)
+        self._mask = np.zeros(self.shape, bool)
+        self._mask.flat[net.flat_nodes] = True
+        self.it_kin = 1
+        O.set_threads(8)
+
+    def close(self):
+        pass
+
+    def set(self, name, value):
+        v = np.array(np.broadcast_to(np.asarray(value, F32), self.shape))
+        if self._o is not None:
+            self._o.set(name, v)
+        else:
+            self._fields[name] = v
+
+    def set_many(self, fields):
+        for k, v in fields.items():
+            self.set(k, v)
+
+    def _model(self):
+        if self._o is None:
+            from oracle import hbv_oracle
+            self._o = hbv_oracle.HbvOracle(self._ldd, self._fields, **self._kw)
+        return self._o
+
+    def get(self, name, mv=-999.0):
+        return np.where(self._mask, self._model().get(name), F32(mv)).astype(F32)
+
+    def request(self, *names, enable=True):
+        pass
+
+    def device_ptr(self, name):
+        return 0, 0
+
+    def dynamic(self, P, PET, TEMP=None, Inflow=None, Seepage=None):
+        o = self._model()
+        o.step(P, PET, TEMP, Inflow=Inflow, Seepage=Seepage)
+        self.it_kin = o.last_it
+
+    def quick_suspend(self):
+        pass
+
+    def quick_resume(self):
+        raise NotImplementedError
+
+    def area_create(self, idmap):
+        ids = np.where(self._mask, np.asarray(idmap, np.int32), 0)
+        uniq = np.unique(ids[ids > 0]).astype(np.int32)
+        self._areas.append((ids, uniq))
+        return len(self._areas) - 1, uniq
+
+    def area_reduce(self, area, field, op="average"):
+        ids, uniq = self._areas[area]
+        a = self._model().get(field).astype(np.float64)
+        fn = {"average": np.mean, "total": np.sum, "maximum": np.max, "minimum": np.min}[op]
+        return np.array([fn(a[ids == i]) for i in uniq], F32)

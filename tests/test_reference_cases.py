@@ -170,9 +170,7 @@ needs_hbv = pytest.mark.skipif(not os.path.isfile(os.path.join(CASE_HBV, "wflow_
                                reason="the reference's tests/wflow_hbv inputs are not in baseline/_ref (tests/golden/make_ref_cases.py)")
 
 
-@needs_hbv
-@pytest.mark.gpu
-def test_cuda_reproduces_reference_test_wflow_hbv(tmp_path):
+def run_test_wflow_hbv(tmp_path):
     """tests/test_wflow_hbv.py:19-71 of the reference, call for call: cold start, 30 daily steps, forcing through
     wf_setValues (10 mm of rain on days 10-15, PET 2, 10 degrees).  The reference asserts, to 4 places,
     sum(watbal.csv[:, 2]) = 0.0011471913849163684 and mean(run.csv[:, 2]) = 1045.9255285898844 (m3/s at the second gauge).
@@ -202,3 +200,19 @@ def test_cuda_reproduces_reference_test_wflow_hbv(tmp_path):
     assert got_wb == pytest.approx(0.0011471913849163684, abs=5e-4)
     assert got_q == pytest.approx(1045.9255285898844, rel=2e-3)
     assert os.path.isfile(os.path.join(case, "unittest", "outstate", "SoilMoisture.map"))
+
+
+@needs_hbv
+def test_oracle_reproduces_reference_test_wflow_hbv(monkeypatch, tmp_path):
+    """The CPU restatement behind the same host code: pins oracle/hbv_oracle.py (and framework_hbv's initial()) to the
+    reference's acceptance numbers."""
+    import wflow_b200.hbv as hbv_mod
+    from tests.oracle_backend import OracleHbvModel
+    monkeypatch.setattr(hbv_mod, "HbvModel", OracleHbvModel)
+    run_test_wflow_hbv(tmp_path)
+
+
+@needs_hbv
+@pytest.mark.gpu
+def test_cuda_reproduces_reference_test_wflow_hbv(tmp_path):
+    run_test_wflow_hbv(tmp_path)

@@ -86,6 +86,7 @@ class WflowHbv(WflowSbm):
         soil = np.where(soil <= -999, active.astype(np.int32), soil)
         self.OutputLoc = np.where(gauges > 0, gauges, 0).astype(np.int32)
         self.LandUse, self.Soil = landuse, soil
+        ldd_map = _repair_ldd(np.where((ldd >= 1) & (ldd <= 9), ldd, 0).astype(np.uint8))  # TopoLdd as read: the whole map
         ldd = np.where(active & (ldd >= 1) & (ldd <= 9), ldd, 0).astype(np.uint8)  # lddmask(TopoLdd, TopoId), :995
         ldd = _repair_ldd(ldd)
         self.ldd = ldd
@@ -117,12 +118,13 @@ class WflowHbv(WflowSbm):
                 self.logger.error("Variable change (apply_once) could not be applied to " + var)
         N = np.where(river_b, p["N_River"], p["N"]).astype(F32)  # :928
         # river width from the upstream area and the yearly discharge, :936-949 (window average restated, unpinned)
-        sched = Schedule(ldd)
-        upcells = sched.catchment_total(None).astype(F32)
+        # (upstr is taken from TopoLdd BEFORE initial() masks it with the catchment, :936-941 against :995: cells that
+        # receive water from outside the mask count that area, and mapmaximum runs over the whole map)
+        upcells = Schedule(ldd_map).catchment_total(None).astype(F32)
         rw = self._staticmap(mapname("wflow_riverwidth"))
         rw = np.zeros(self.shape, F32) if rw is None else np.nan_to_num(rw, nan=0.0).astype(F32)
         alf, Qmax = float(cfg("Alpha", "60")), float(cfg("AnnualDischarge", "300"))
-        Qscale = (upcells / F32(max(float(upcells[active].max()), 1.0)) * F32(Qmax)).astype(F32)
+        Qscale = (upcells / F32(max(float(upcells.max()), 1.0)) * F32(Qmax)).astype(F32)
         wavg = np.nan_to_num(window_average(np.where(active, slope, np.nan), 4.0), nan=0.0001).astype(F32)
         c0 = F32((alf * (alf + 2.0) ** 0.6666666667) ** 0.375)  # (Python floats in the reference, REAL4 where it meets the map)
         W = (c0 * _pow(Qscale, F32(0.375)) * _pow(np.maximum(F32(0.0001), wavg), F32(-0.1875))
