@@ -11,8 +11,9 @@ outmaps, outsum), [run] [model] [layout] [inputmapstacks] [modelparameters] [var
 [variable_change_timestep] [outputmaps] [outputcsv_N] [outputtss_N] [summary] [summary_sum|avg|min|max] [API],
 cold start (reinit = 1) and warm start, wf_suspend / wf_resume, wf_setValues*, wf_supplyMapAsNumpy,
 wf_supplyVariableNamesAndRoles, wf_QuickSuspend/Resume, LAI-driven canopy parameters, the command line.
-Not covered (out of scope): netCDF I/O (refused loudly), state
-updating, [rollingmean].
+netCDF: forcing input and [outputmaps] output on the classic netCDF-3 formats (ncio.py); netCDF-4 files and static /
+state maps through netCDF are refused loudly (the netCDF4 / HDF5 libraries are not in the image).
+Not covered (out of scope): state updating, [rollingmean].
 
 The derivations of `initial()` that need PCRaster neighbourhood operators (slope from the DEM, window
 average for the river width) are restated in numpy and are NOT pinned against PCRaster (it cannot be
@@ -195,12 +196,41 @@ class WflowSbm:
             raise ValueError("Could not find required map: " + path)  # wf_DynamicFramework.py:3372
         return None if default is None else np.full(self.shape, default, F32)
 
+    # ---- netCDF (wf_DynamicFramework.py:1405-1580; wflow_b200/ncio.py) ---------------------------------------
+    def _check_netcdf_options(self):
+        """[framework] netcdfinput / netcdfoutput are served on the classic netCDF-3 formats (ncio.py); static and state
+        maps through netCDF are not part of this implementation."""
+        for opt in ("netcdfstaticinput", "netcdfstatesinput", "netcdfstaticoutput", "netcdfstatesoutput"):
+            if configget(self.config, "framework", opt, "None") != "None":
+                raise ValueError("[framework] %s: static / state maps through netCDF are not part of this implementation "
+                                 "(forcing input and [outputmaps] output are: netcdfinput, netcdfoutput)" % opt)
+        self._ncin = self._ncout = None
+
+    def _setup_netcdf(self):
+        """Called at the end of initial(), when the grid is known."""
+        from . import ncio
+        info = self._info
+        x = info.x_ul + (np.arange(info.ncol) + 0.5) * info.cellsize
+        y = info.ycoordinate()
+        ncfile = configget(self.config, "framework", "netcdfinput", "None")
+        if ncfile != "None":
+            names = [os.path.basename(v) for _, v in self.config.items("inputmapstacks")] if self.config.has_section("inputmapstacks") else []
+            names += [os.path.basename(p["stack"]) for p in getattr(self, "_modelparameters", []) if p["type"] == "timeseries"]
+            for dflt in ("P", "PET", "TEMP", "IF", "SE"):
+                if dflt not in names:
+                    names.append(dflt)
+            self._ncin = ncio.NetcdfInput(os.path.join(self.Dir, ncfile), self.logger, names, x, y)
+        ncout = configget(self.config, "framework", "netcdfoutput", "None")
+        if ncout != "None":
+            self._ncout = ncio.NetcdfOutput(
+                os.path.join(self.SaveDir, ncout), self.logger, self.datetime_start, self.nrTimeSteps, self.timestepsecs, x, y,
+                maxbuf=int(configget(self.config, "framework", "netcdfwritebuffer", "50")),
+                metadata={"caseName": self.caseName, "runId": self.runId, "wflow_ini": self.configfile},
+                fmt=configget(self.config, "framework", "netcdf_format", "NETCDF4"))
+
     def _runInitial(self):
         cfg = lambda k, d: configget(self.config, "model", k, d)
-        for opt in ("netcdfinput", "netcdfstaticinput", "netcdfstatesinput", "netcdfoutput", "netcdfstaticoutput",
-                    "netcdfstatesoutput"):
-            if configget(self.config, "framework", opt, "None") != "None":
-                raise ValueError("[framework] %s: netCDF I/O is not part of this implementation (PCRaster map stacks only)" % opt)
+        self._check_netcdf_options()
         mapname = lambda k: cfg(k, "staticmaps/%s.map" % k)
         self.modelSnow = int(cfg("ModelSnow", "1"))
         self.soilInfReduction = int(cfg("soilInfRedu", "0"))
@@ -538,6 +568,10 @@ class WflowSbm:
     def _parameter_raster(self, par, step):
         kind, path = self._parameter_source(par, step)
         default = np.float32(par["default"])
+        if par["type"] == "timeseries" and getattr(self, "_ncin", None) is not None:  # wf_readmap: from the netCDF input file
+            when = self.datetime_start + _dt.timedelta(seconds=self.timestepsecs * (max(step, 1) - 1))
+            a, ok = self._ncin.gettimestep(max(step, 1), tsdatetime=when, var=os.path.basename(par["stack"]))
+            return np.nan_to_num(a, nan=float(default)).astype(F32) if ok else np.full(self.shape, default, F32)
         if kind == "map":
             if os.path.isfile(path):
                 a, _ = csf.read_map(path)
@@ -619,6 +653,10 @@ class WflowSbm:
         if var in self._api_values:  # set through the API: skip the disk for this step (:3300-3306)
             return self._api_values.pop(var)
         prefix = configget(self.config, "inputmapstacks", stack_key, default_stack).lstrip("/")
+        if getattr(self, "_ncin", None) is not None:  # wf_readmap with a netCDF input file (wf_DynamicFramework.py:3340-3353)
+            when = self.datetime_start + _dt.timedelta(seconds=self.timestepsecs * (max(step, 1) - 1))  # DT.nextDateTime
+            a, ok = self._ncin.gettimestep(max(step, 1), tsdatetime=when, var=os.path.basename(prefix))
+            return np.nan_to_num(a, nan=default).astype(F32) if ok else np.full(self.shape, default, F32)
         path = generate_name_t(os.path.join(self.Dir, prefix), step)
         if os.path.isfile(path):
             a, _ = csf.read_map(path)
@@ -735,6 +773,7 @@ class WflowSbm:
     # ---- outputs ----------------------------------------------------------------------------------
     def _setup_outputs(self):
         """[outputcsv_N] / [outputtss_N]: samplemap, function, self.Var = file (wf_DynamicFramework.py:1709-1778)."""
+        self._setup_netcdf()
         for kind in ("csv", "tss"):
             n = 0
             while self.config.has_section("output%s_%d" % (kind, n)):
@@ -827,13 +866,22 @@ class WflowSbm:
                 st["data"] = np.where(np.isnan(st["data"]) | np.isnan(a), F32(np.nan), np.minimum(st["data"], a))
             st["count"] += 1
         for name, prefix in self._outmaps:
+            a = self._get(self._ALIAS.get(name, name))
+            if getattr(self, "_ncout", None) is not None:  # _reportNew with a netCDF output file (:3179-3189)
+                self._ncout.savetimestep(step, np.where(a == F32(MV), F32(np.nan), a), var=os.path.basename(prefix), name="self." + name)
+                continue
             path = generate_name_t(os.path.join(self.SaveDir, "outmaps", prefix), step)
-            csf.write_map(path, self._get(self._ALIAS.get(name, name)), self._info, mv=MV)
+            csf.write_map(path, a, self._info, mv=MV)
 
     def _wf_shutdown(self):
         for fh in self._files.values():
             fh.close()
         self._files = {}
+        if getattr(self, "_ncout", None) is not None:
+            self._ncout.finish()
+        if getattr(self, "_ncin", None) is not None:
+            self._ncin.close()
+            self._ncin = None
         with open(os.path.join(self.SaveDir, "runinfo", "configofrun.ini"), "w") as fh:
             self.config.write(fh)
         if self._mod is not None:

@@ -45,10 +45,7 @@ class WflowHbv(WflowSbm):
     # ---- initial(), wflow_hbv.py:324-1140 ---------------------------------------------------------------
     def _runInitial(self):
         cfg = lambda k, d: configget(self.config, "model", k, d)  # noqa: E731
-        for opt in ("netcdfinput", "netcdfstaticinput", "netcdfstatesinput", "netcdfoutput", "netcdfstaticoutput",
-                    "netcdfstatesoutput"):
-            if configget(self.config, "framework", opt, "None") != "None":
-                raise ValueError("[framework] %s: netCDF I/O is not part of this implementation (PCRaster map stacks only)" % opt)
+        self._check_netcdf_options()
         for opt, what in (("ScalarInput", "scalar (tss) input"), ("updating", "updating from observed discharge"),
                           ("MassWasting", "snow mass wasting"), ("SubCatchFlowOnly", "a subcatchment-only drainage network")):
             if int(cfg(opt, "0")):
@@ -224,6 +221,8 @@ class WflowHbv(WflowSbm):
         if key in self._api_values:
             return True
         prefix = configget(self.config, "inputmapstacks", key, default_stack).lstrip("/")
+        if getattr(self, "_ncin", None) is not None:
+            return os.path.basename(prefix) in self._ncin.alldat
         return os.path.isfile(generate_name_t(os.path.join(self.Dir, prefix), step))
 
     def run_pipelined(self, *a, **kw):
