@@ -216,3 +216,35 @@ def test_oracle_reproduces_reference_test_wflow_hbv(monkeypatch, tmp_path):
 @pytest.mark.gpu
 def test_cuda_reproduces_reference_test_wflow_hbv(tmp_path):
     run_test_wflow_hbv(tmp_path)
+
+
+@needs_hbv
+def test_bmi_runs_the_hbv_case_by_modeltype(monkeypatch, tmp_path):
+    """wflow_bmi picks the model by [model] modeltype (wflow_bmi.py:606-640): the reference's wflow_hbv case through the BMI
+    mirror, the CPU restatement behind it -- initialize, three updates with forcing set through set_value, values back."""
+    import wflow_b200.hbv as hbv_mod
+    from tests.oracle_backend import OracleHbvModel
+    from wflow_b200.bmi import wflowbmi_csdms
+    monkeypatch.setattr(hbv_mod, "HbvModel", OracleHbvModel)
+    case = str(tmp_path / "wflow_hbv")
+    shutil.copytree(CASE_HBV, case)
+    ini = os.path.join(case, "wflow_hbv.ini")
+    text = open(ini).read()  # the case's [API] section names the forcing only: two states for the exchange
+    assert "TEMP=0,3" in text
+    open(ini, "w").write(text.replace("TEMP=0,3", "TEMP=0,3\nSurfaceRunoff=2,m3/s\nSoilMoisture=2,mm", 1))
+    b = wflowbmi_csdms()
+    b.initialize(ini)
+    assert b.get_component_name() == "wflow_hbv"
+    ts = b.get_time_step()
+    t0 = b.get_current_time()
+    shape = b.dynModel.shape
+    for k in range(3):
+        b.set_value("P", np.full(shape, 10.0, np.float32))
+        b.set_value("PET", np.full(shape, 2.0, np.float32))
+        b.set_value("TEMP", np.full(shape, 10.0, np.float32))
+        b.update()
+    assert b.get_current_time() == t0 + 3 * ts
+    q = b.get_value("SurfaceRunoff")
+    sm = b.get_value("SoilMoisture")
+    assert q.shape == shape and float(q[q > -999].max()) > 10.0 and float(sm[sm > -999].min()) > 0.0
+    b.finalize()

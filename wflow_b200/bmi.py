@@ -36,10 +36,16 @@ class wflowbmi_csdms:
         self.datadir = os.path.dirname(os.path.abspath(filename))
         inifile = os.path.basename(filename)
         self.dynModel = WflowSbm(Dir=self.datadir, RunDir="run_default", configfile=inifile)
-        modeltype = configget(self.dynModel.config, "model", "modeltype", "sbm")
-        if modeltype != "sbm":
-            raise ValueError("only the wflow_sbm hot path is implemented (modeltype = sbm), got " + modeltype)
-        self.name = "wflow_sbm"
+        # wflow_bmi.py:606-640 picks the model module by [model] modeltype
+        modeltype = configget(self.dynModel.config, "model", "modeltype", "sbm").strip()
+        if modeltype in ("hbv", "wflow_hbv"):
+            from .framework_hbv import WflowHbv
+            self.dynModel = WflowHbv(Dir=self.datadir, RunDir="run_default", configfile=inifile)
+            self.name = "wflow_hbv"
+        elif modeltype in ("sbm", "wflow_sbm"):
+            self.name = "wflow_sbm"
+        else:
+            raise ValueError("modeltype = %s: only wflow_sbm and wflow_hbv are implemented" % modeltype)
         self.dynModel.createRunId()
         roles = self.dynModel.wf_supplyVariableNamesAndRoles()
         self.inputoutputvars = [r[0] for r in roles if r[1] in (0, 2, 3)]
