@@ -101,14 +101,14 @@ def main():
         "e2e": {"value": ncell / e2e_ms * 1e3, "unit": "cell-steps/s", "h2d_bytes_per_step": int(3 * 4 * nrow * ncol),
                 "d2h_bytes_per_step": int(4 * len(pits))},
         "gpu_launches": 2 * args.steps,
-        "kernels_ms_per_step": {"k_hbv_column": col_ms, "k_lateral_wave(river task)": sweep_ms},
-        "roofline": {"bound": "hbm", "kernel": "k_lateral_wave<1> (channel sweep)" if sweep_ms > col_ms else "k_hbv_column",
+        "kernels_ms_per_step": {"k_hbv_column": col_ms, "k_channel_wave": sweep_ms},
+        "roofline": {"bound": "hbm", "kernel": "k_channel_wave (kin_wave on the whole network)" if sweep_ms > col_ms else "k_hbv_column",
                      "achieved": (channel_bytes(it) if sweep_ms > col_ms else COLUMN_BYTES) * ncell / (max(sweep_ms, col_ms) * 1e-3) / 1e9,
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None,
                      "kernels": [
                          {"kernel": "k_hbv_column", "ms": col_ms, "algorithmic_bytes_per_cell": COLUMN_BYTES,
                           "achieved": COLUMN_BYTES * ncell / (col_ms * 1e-3) / 1e9, "frac": COLUMN_BYTES * ncell / (col_ms * 1e-3) / 1e9 / peak},
-                         {"kernel": "k_lateral_wave<1> (channel sweep)", "ms": sweep_ms, "algorithmic_bytes_per_cell": channel_bytes(it),
+                         {"kernel": "k_channel_wave (kin_wave on the whole network)", "ms": sweep_ms, "algorithmic_bytes_per_cell": channel_bytes(it),
                           "achieved": channel_bytes(it) * ncell / (sweep_ms * 1e-3) / 1e9,
                           "frac": channel_bytes(it) * ncell / (sweep_ms * 1e-3) / 1e9 / peak}]},
         "clocks": clk.summary(), "gen_s": gen_s,

@@ -134,3 +134,32 @@ def test_refused_options_fail_loudly():
             mod.step()  # parameters not set
     finally:
         mod.close()
+
+
+@pytest.mark.parametrize("cluster_size", ["2", "4"])
+def test_channel_kernel_is_bit_identical_to_the_shared_sweep(monkeypatch, cluster_size):
+    """Under a cluster plan the channel wave runs as k_channel_wave (1024 threads per block); the river task of the shared
+    sweep (WF_HBV_SHARED_SWEEP=1) must give the same bits: same device function, same schedule of dependencies.  Both
+    against the reference's golden as well.  Hourly steps with four sub-steps, missing cells inside the basins."""
+    g = np.load(os.path.join(GOLD, "hbv_tiles_hourly_sub.npz"))
+    kw = ast.literal_eval(str(g["meta"]))
+    monkeypatch.setenv("WF_LATERAL_MODE", "cluster")
+    monkeypatch.setenv("WF_CLUSTER_SIZE", cluster_size)
+    got = {}
+    for shared in ("0", "1"):
+        monkeypatch.setenv("WF_HBV_SHARED_SWEEP", shared)
+        _, _, mod = _load("tiles_hourly_sub")
+        try:
+            assert mod.lateral_plan["mode"] in ("cluster", "cluster-wide"), mod.lateral_plan
+            for t in range(kw["steps"]):
+                P, PET, T, Inflow, Seep = _forcing(g, t)
+                mod.dynamic(P, PET, T, Inflow=Inflow, Seepage=Seep)
+            got[shared] = {f: mod.get(f) for f in hbv.STATES}
+            mask = np.zeros(mod.shape, bool)
+            mask.flat[mod.network()[0]] = True
+        finally:
+            mod.close()
+    last = kw["steps"] - 1
+    for f in hbv.STATES:
+        np.testing.assert_array_equal(got["0"][f], got["1"][f], err_msg=f)
+        assert common.compare(got["0"][f], g["out/%d/%s" % (last, f)], mask, 1e-4, 1e-4) <= 1.0, f

@@ -180,6 +180,7 @@ struct wf_model {
   // wflow_hbv (hbv.cuh): a model made by wf_hbv_create runs the HBV column and the river task of the sweep on the whole network
   bool hbv = false;
   HbvOptions hbv_opt = {};
+  int hbv_blocks = 0;                 // grid of k_channel_wave (0: not derived yet; setup_sweep resets it)
   bool satwd_valid = false;           // the SatWaterDepth map holds the end of the previous step          // dynamic shared memory limit already raised for the pipelined kernel
 };
 
@@ -613,7 +614,39 @@ int launch_step_hbv(wf_model *m) {
   k_hbv_column<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->dm, m->hbv_opt);
   m->launches++;
   if (m->timed) cudaEventRecord(e1, m->stream);
-  if (int rc = launch_lateral<1>(m)) return rc;
+  // the channel wave: a sweep of its own where the plan is one cluster per group (hbv.cuh, k_channel_wave: 1024 threads per
+  // block instead of the shared sweep's 640), the river task of the shared sweep otherwise.  WF_HBV_SHARED_SWEEP=1 forces
+  // the shared sweep (development aid; same results).
+  const char *shared_sweep = std::getenv("WF_HBV_SHARED_SWEEP");
+  if (wf_is_cluster(m->lat_mode) && !(shared_sweep && std::atoi(shared_sweep))) {
+    const size_t smem = (m->lat_smem + 15) & ~(size_t)15;
+    if (smem > 48 * 1024) CUDA_OK(cudaFuncSetAttribute((void *)k_channel_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)m->cluster_size;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cfg.blockDim = dim3(WF_CHANNEL_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = m->stream;
+    if (m->hbv_blocks == 0) {
+      cfg.gridDim = dim3((unsigned)m->cluster_size * 64);
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, (void *)k_channel_wave, &cfg) != cudaSuccess || nc < 1) {
+        cudaGetLastError();
+        return fail(WF_ENODEVICE, "k_channel_wave does not fit on the device");
+      }
+      m->hbv_blocks = std::min(nc, m->dm.ngroups) * m->cluster_size;
+    }
+    cfg.gridDim = dim3((unsigned)m->hbv_blocks);
+    void *args[] = {(void *)&m->dm};
+    CUDA_OK(cudaLaunchKernelExC(&cfg, (void *)k_channel_wave, args));
+  } else if (int rc = launch_lateral<1>(m)) {
+    return rc;
+  }
   m->launches++;
   if (m->timed) cudaEventRecord(e2, m->stream);
   m->ev_last[0] = e0; m->ev_last[1] = e1; m->ev_last[2] = e2;
@@ -738,6 +771,7 @@ int setup_sweep(wf_model *m) {
     m->lat_smem = (size_t)most * 4;
   }
   m->lat_blocks = 0;  // re-derived at the next launch
+  m->hbv_blocks = 0;
   m->pipe_blocks = 0;
   m->ah_valid = false;
   // busiest tick of the whole network (grid sweep: no more blocks than it can use)

@@ -15,6 +15,7 @@
 // (:1351-1364), state updating from observed discharge (:1684-1726).
 #pragma once
 #include "kernels.cuh"
+#include "lateral.cuh"
 
 namespace wf {
 
@@ -196,5 +197,71 @@ __global__ void __launch_bounds__(256) k_hbv_post(const DevModel m) {
 
 #undef HF
 #undef HOUT
+
+// ---- the channel wave of every cell as a sweep of its own ------------------------------------------------------------
+// kin_wave on the full network (wflow_hbv.py:1633-1647; wflow/wflow_funcs.py:155-207).  The shared sweep of lateral.cuh
+// can run it (river task only), but its blocks are sized for the subsurface task: 640 threads at 96 registers, 2560
+// threads per cluster of four for the ~4 x 1024 channel items a tick of the bench shard holds -- two rounds per tick.  The
+// channel task alone needs far fewer registers, so this kernel runs one cluster per group with 1024 threads per block
+// (64 registers): a tick's items fit one round.  Same schedule as the river task of the shared sweep, re-based: at tick t
+// sub-step v solves level t - v of the group, so a cell's sub-step v follows its own sub-step v - 1 and its upstream
+// neighbours' sub-step v by exactly one tick, one cluster barrier per tick, levels + it - 1 ticks.  task_river is the
+// shared device function: same arithmetic, same hand-off arrays, bit-identical results (tests/test_gpu_hbv.py).
+#define WF_CHANNEL_THREADS 1024
+__global__ void __launch_bounds__(WF_CHANNEL_THREADS, 1) k_channel_wave(const __grid_constant__ DevModel m) {
+  extern __shared__ __align__(16) uint32_t s_ro[];
+#ifdef WF_PROFILE
+  unsigned long long *pbase = nullptr;
+  const unsigned long long c0 = 0;
+#endif
+  cg::cluster_group cl = cg::this_cluster();
+  const int crank = (int)cl.block_rank(), csize = (int)cl.num_blocks();
+  const int nclusters = (int)gridDim.x / csize, cid = (int)blockIdx.x / csize;
+  // item warps dealt round robin to the blocks of the cluster (every SM gets the same mix of sub-steps)
+  const int tid = (((int)threadIdx.x >> 5) * csize + crank) * 32 + ((int)threadIdx.x & 31);
+  const int nthreads = csize * (int)blockDim.x;
+  const int itR = m.itR;
+  for (int g = cid; g < m.ngroups; g += nclusters) {
+    const GroupDesc gd = m.groups[g];
+    const int nrl = (gd.rlev0 < m.nrlev) ? m.nrlev - gd.rlev0 : 0;
+    const uint32_t *ro = m.rlev_off + gd.rlev_idx;
+    if (nrl + 1 <= m.lev_cache) {  // the group's level offsets into shared memory
+      __syncthreads();
+      for (int k = threadIdx.x; k <= nrl; k += blockDim.x) s_ro[k] = ro[k];
+      __syncthreads();
+      ro = s_ro;
+    }
+    const int nticks = (nrl > 0) ? nrl + itR - 1 : 0;
+    for (int t = 0; t < nticks; t++) {
+      // items of the tick: [sub-step 0: level t | sub-step 1: level t - 1 | ...]
+      const int v0 = max(0, t - (nrl - 1)), v1 = min(itR - 1, t);
+      int j = tid;
+      for (int v = v0; v <= v1; v++) {
+        const int q = t - v;
+        const uint32_t rb = ro[q];
+        const int rc = (int)(ro[q + 1] - rb);
+        while (j < rc) {
+          const int32_t rs = (int32_t)(rb + (uint32_t)j);
+          RivOps o;
+          load_riv(m, rs, o);
+          task_river<WF_CLUSTER>(m, rs, v, o, 0 WF_PPASS(2));
+          j += nthreads;
+        }
+        j -= rc;
+      }
+      // (warming L2 with the level that enters the wave next tick measured slower, 7.04 against 6.70 ms: with a tick's items
+      //  filling every thread the kernel is bound by the solves' instructions, not by the cold operands of a quarter of them)
+      __syncwarp();
+      if (t + 1 < nticks) {
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+      }
+    }
+    if (g + nclusters < m.ngroups) {  // the next group re-uses the shared-memory offsets
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
+  }
+}
 
 }  // namespace wf
