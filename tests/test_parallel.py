@@ -66,3 +66,55 @@ def test_gather_over_gloo_world_size_2(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=240)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "GATHER_OK 2" in res.stdout
+
+
+HBV_WORKER = r'''
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, %r)
+from wflow_b200 import parallel, synth
+from oracle import hbv_oracle
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+n = 48
+ldd, static, state = synth.hbv_case(n, n, kind="tiles", tile=16, seed=5)      # 9 basins, the same case on every rank
+state["SurfaceRunoff"][0, 0] = 0.0
+labels, sizes = parallel.basin_labels(ldd)
+mine = parallel.partition(sizes, world)[rank]
+shard = parallel.shard_ldd(ldd, labels, mine)
+fields = dict(static); fields.update(state)
+forc = synth.Forcing(n, n, seed=5, rain_mean=14.0, t_mean=3.0)
+m = hbv_oracle.HbvOracle(shard, fields)                                         # this rank's basins only
+whole = hbv_oracle.HbvOracle(ldd, fields) if rank == 0 else None
+for t in range(3):
+    P, PET, T = forc.step(t)
+    m.step(P, PET, T)
+    if whole is not None:
+        whole.step(P, PET, T)
+pits = np.argwhere(ldd == 5)
+own = [tuple(pits[b]) for b in mine]
+series = np.array([m.get("SurfaceRunoff")[r, c] for r, c in own], np.float32)   # outlet discharge of the own basins
+parts = parallel.gather_series(series)
+if rank == 0:
+    parts_of = parallel.partition(sizes, world)
+    for r in range(world):
+        want = np.array([whole.get("SurfaceRunoff")[tuple(pits[b])] for b in parts_of[r]], np.float32)
+        assert np.array_equal(parts[r], want), (r, parts[r], want)       # a basin computed alone = the basin inside the whole grid
+    assert float(np.concatenate(parts).max()) > 0.0
+    print("HBV_SHARDS_OK", world, sum(len(p) for p in parts))
+dist.destroy_process_group()
+'''
+
+
+def test_hbv_shards_by_basin_over_gloo_world_size_2(tmp_path):
+    """wflow_hbv shards like wflow_sbm (independent basins per rank, gather of the outlets): every rank steps its basins with
+    the CPU restatement, the gathered outlet discharges are bit-identical to the whole grid's."""
+    script = tmp_path / "hbv_worker.py"
+    script.write_text(HBV_WORKER % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29519", str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "HBV_SHARDS_OK 2 9" in res.stdout
