@@ -115,6 +115,9 @@ def main():
     }
     line["roofline"]["frac"] = line["roofline"]["achieved"] / peak
     mod.close()
+    if args.cpu_steps <= 0:  # (profiling runs: the device part only)
+        print(json.dumps(line))
+        return
     # ---- CPU beside it: one basin tile, one core ----
     n = args.cpu_tile
     ldd_c, st_c, state_c = synth.hbv_case(n, n, kind="tiles", tile=n, seed=11, timestepsecs=dt, block=64)

@@ -48,6 +48,7 @@ def main():
         shutil.copyfile(os.path.join(hsrc, "staticmaps", m + ".map"), os.path.join(hdst, "staticmaps", m + ".map"))
     shutil.copytree(os.path.join(hsrc, "intbl"), os.path.join(hdst, "intbl"), dirs_exist_ok=True)
     shutil.copyfile(os.path.join(hsrc, "wflow_hbv.ini"), os.path.join(hdst, "wflow_hbv.ini"))
+    shutil.copyfile(os.path.join(hsrc, "wflow_hbv_hr.ini"), os.path.join(hdst, "wflow_hbv_hr.ini"))  # tests/test_wflow_hbv2.py
     os.system("chmod -R u+w '%s'" % hdst)
     rh = os.path.join(ROOT, "baseline", "_ref", "wflow_rhine_sbm")
     if not os.path.isdir(rh):

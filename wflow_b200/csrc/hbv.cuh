@@ -32,7 +32,10 @@ struct HbvOptions {
 
 __device__ __forceinline__ float hbv_pow(float x, float y) { return (float)pow((double)x, (double)y); }
 
-__global__ void __launch_bounds__(256) k_hbv_column(const DevModel m, const HbvOptions opt) {
+#ifndef WF_HBV_MINBLOCKS
+#define WF_HBV_MINBLOCKS 8  // resident blocks of 256 threads per SM (32 registers: the loads of 37 rasters wait on DRAM, occupancy pays for the spills: 1.78 ms at 4 blocks, 1.48 at 6, 1.38 at 8)
+#endif
+__global__ void __launch_bounds__(256, WF_HBV_MINBLOCKS) k_hbv_column(const DevModel m, const HbvOptions opt) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m.n) return;
   const int32_t rs = __ldg(m.river_slot + i);
