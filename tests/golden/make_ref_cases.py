@@ -50,6 +50,22 @@ def main():
     shutil.copyfile(os.path.join(hsrc, "wflow_hbv.ini"), os.path.join(hdst, "wflow_hbv.ini"))
     shutil.copyfile(os.path.join(hsrc, "wflow_hbv_hr.ini"), os.path.join(hdst, "wflow_hbv_hr.ini"))  # tests/test_wflow_hbv2.py
     os.system("chmod -R u+w '%s'" % hdst)
+    # examples/wflow_rhine_hbv as shipped (warm start from instate, stream-order roughness, Courant sub-steps): static maps,
+    # tables, states and the forcing of the first ten days (the shipped run is five days long)
+    esrc = os.path.join(REF, "examples", "wflow_rhine_hbv")
+    edst = os.path.join(ROOT, "baseline", "_ref", "wflow_rhine_hbv")
+    for sub in ("intbl", "instate"):
+        shutil.copytree(os.path.join(esrc, sub), os.path.join(edst, sub), dirs_exist_ok=True)
+    os.makedirs(os.path.join(edst, "staticmaps"), exist_ok=True)
+    for m in MAPS + ["wflow_streamorder"]:
+        shutil.copyfile(os.path.join(esrc, "staticmaps", m + ".map"), os.path.join(edst, "staticmaps", m + ".map"))
+    os.makedirs(os.path.join(edst, "inmaps"), exist_ok=True)
+    for stem in ("P0000000", "PET00000", "TEMP0000"):
+        for t in range(1, 11):
+            f = "%s.%03d" % (stem, t)
+            shutil.copyfile(os.path.join(esrc, "inmaps", f), os.path.join(edst, "inmaps", f))
+    shutil.copyfile(os.path.join(esrc, "wflow_hbv.ini"), os.path.join(edst, "wflow_hbv.ini"))
+    os.system("chmod -R u+w '%s'" % edst)
     rh = os.path.join(ROOT, "baseline", "_ref", "wflow_rhine_sbm")
     if not os.path.isdir(rh):
         shutil.copytree(os.path.join(REF, "examples", "wflow_rhine_sbm"), rh)

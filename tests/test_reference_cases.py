@@ -259,3 +259,57 @@ def test_bmi_runs_the_hbv_case_by_modeltype(monkeypatch, tmp_path):
     sm = b.get_value("SoilMoisture")
     assert q.shape == shape and float(q[q > -999].max()) > 10.0 and float(sm[sm > -999].min()) > 0.0
     b.finalize()
+
+
+# ---- examples/wflow_rhine_hbv as shipped ---------------------------------------------------------------------------------
+CASE_RHINE_HBV = os.path.join(os.path.dirname(HERE), "baseline", "_ref", "wflow_rhine_hbv")
+needs_rhine_hbv = pytest.mark.skipif(not os.path.isfile(os.path.join(CASE_RHINE_HBV, "wflow_hbv.ini")),
+                                     reason="examples/wflow_rhine_hbv is not in baseline/_ref (tests/golden/make_ref_cases.py)")
+
+
+def run_rhine_hbv_example(tmp_path, tag):
+    """python -m wflow.wflow_hbv -C wflow_rhine_hbv as shipped: 2000-01-01 .. 01-05, warm start from instate/, forcing from the
+    map stacks, roughness of the river by stream order (nrivermethod = 2), sub-steps of the kinematic wave from the Courant
+    number every step (kinwaveIters = 1).  Returns (run.csv rows, sub-steps per step)."""
+    from wflow_b200.framework_hbv import WflowHbv
+    case = str(tmp_path / ("rhine_hbv_" + tag))
+    shutil.copytree(CASE_RHINE_HBV, case)
+    m = WflowHbv(Dir=case, RunDir="run_default", configfile="wflow_hbv.ini")
+    m.createRunId()
+    m._runInitial()
+    m._runResume()
+    assert m.nrTimeSteps == 5 and m.reinit == 0
+    its = []
+    for ts in range(1, m.nrTimeSteps + 1):
+        m._runDynamic(ts, ts)
+        its.append(m._mod.it_kin)
+    m._runSuspend()
+    m._wf_shutdown()
+    run = np.genfromtxt(os.path.join(case, "run_default", "run.csv"), delimiter=",")
+    assert run.shape == (5, 16)
+    assert os.path.isfile(os.path.join(case, "run_default", "outmaps", "run00000.005"))
+    assert os.path.isfile(os.path.join(case, "run_default", "outstate", "UpperZoneStorage.map"))
+    return run, its
+
+
+@needs_rhine_hbv
+def test_oracle_runs_the_shipped_rhine_hbv_example(monkeypatch, tmp_path):
+    import wflow_b200.hbv as hbv_mod
+    from tests.oracle_backend import OracleHbvModel
+    monkeypatch.setattr(hbv_mod, "HbvModel", OracleHbvModel)
+    run, its = run_rhine_hbv_example(tmp_path, "cpu")
+    assert its == [11, 11, 11, 11, 10]                       # estimate_iterations_kin_wave of every step
+    assert 1500.0 < run[:, 2:].max() < 5000.0                # the Rhine in January, m3/s at the gauges
+    assert (np.diff(run[:, 7]) > 0).all()                    # a rising limb at the outlet gauge over the five days
+
+
+@needs_rhine_hbv
+@pytest.mark.gpu
+def test_cuda_runs_the_shipped_rhine_hbv_example_like_the_cpu_restatement(monkeypatch, tmp_path):
+    got, its = run_rhine_hbv_example(tmp_path, "gpu")
+    import wflow_b200.hbv as hbv_mod
+    from tests.oracle_backend import OracleHbvModel
+    monkeypatch.setattr(hbv_mod, "HbvModel", OracleHbvModel)
+    want, its_cpu = run_rhine_hbv_example(tmp_path, "cpu")
+    assert its == its_cpu
+    np.testing.assert_allclose(got[:, 1:], want[:, 1:], rtol=2e-5, atol=1e-4)

@@ -7,8 +7,8 @@ Everything the framework does around a model -- ini handling, time loop, map sta
 model's own: ``initial()`` (wflow_hbv.py:324-1140: tables with HBV's defaults, rates scaled by timestepsecs / basetimestep,
 river width and length, the channel's Alpha), ``resume()`` (:1146-1220: cold state, initstorage, KQuickFlow from KHQ / HQ /
 AlphaNL), ``stateVariables()`` and the per-timestep call (``dynamic()``, :1222-1767 = wf_hbv_create's step).
-Not covered: reservoirs / lakes, MassWasting, updating from observed discharge, scalar (tss) input, SubCatchFlowOnly,
-nrivermethod = 2 -- refused loudly.  The slope and window-average restatements are framework.py's (not pinned against
+Not covered: reservoirs / lakes, MassWasting, updating from observed discharge, scalar (tss) input, SubCatchFlowOnly
+-- refused loudly.  The slope and window-average restatements are framework.py's (not pinned against
 PCRaster; supply Slope.map / wflow_riverwidth.map to bypass them).
 """
 import os
@@ -50,8 +50,9 @@ class WflowHbv(WflowSbm):
                           ("MassWasting", "snow mass wasting"), ("SubCatchFlowOnly", "a subcatchment-only drainage network")):
             if int(cfg(opt, "0")):
                 raise ValueError("[model] %s: %s is not part of this implementation of wflow_hbv" % (opt, what))
-        if int(cfg("nrivermethod", "1")) != 1:
-            raise ValueError("[model] nrivermethod = 2 (N_River by stream order) is not part of this implementation")
+        nrivermethod = int(cfg("nrivermethod", "1"))
+        if nrivermethod not in (1, 2):
+            raise ValueError("[model] nrivermethod = %d (1: N_River by land use / subcatchment / soil, 2: by stream order)" % nrivermethod)
         mapname = lambda k: cfg(k, "staticmaps/%s.map" % k)  # noqa: E731
         self.modelSnow = 1  # (the temperature stack is always read, wflow_hbv.py:1275)
         self.kinwaveIters = int(cfg("kinwaveIters", "0"))
@@ -91,8 +92,17 @@ class WflowHbv(WflowSbm):
 
         p = {}
         for name, (default, scaled) in TABLES.items():
+            if name == "N_River" and nrivermethod == 2:
+                continue  # (looked up by stream order below: its table has one key column)
             v = tbl.read_tbl_default(self.Dir, self.intbl, name, landuse, sub, soil, default)
             p[name] = ((v * dt) / base_dt).astype(F32) if scaled else v.astype(F32)
+        if nrivermethod == 2:  # readtblFlexDefault(N_River.tbl, 0.036, wflow_streamorder), :572-577
+            so = self._staticmap(mapname("wflow_streamorder"))
+            path = os.path.join(self.Dir, self.intbl, "N_River.tbl")
+            if so is None or not os.path.isfile(path):
+                p["N_River"] = np.full(self.shape, 0.036, F32)
+            else:
+                p["N_River"] = np.nan_to_num(tbl.lookupscalar(path, so), nan=0.036).astype(F32)
         tc = self._staticmap(cfg("TemperatureCorrectionMap", "staticmap/swflow_tempcor.map"))  # (the reference's default path)
         p["TempCor"] = np.zeros(self.shape, F32) if tc is None else np.nan_to_num(tc, nan=0.0).astype(F32)
         # cell sizes, wflow/pcrut.py:53-73
