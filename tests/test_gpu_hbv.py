@@ -136,19 +136,19 @@ def test_refused_options_fail_loudly():
         mod.close()
 
 
-@pytest.mark.parametrize("cluster_size", ["2", "4"])
-def test_channel_kernel_is_bit_identical_to_the_shared_sweep(monkeypatch, cluster_size):
+@pytest.mark.parametrize("cluster_size,case", [("2", "tiles_hourly_sub"), ("4", "tiles_hourly_sub"), ("2", "tiles_courant")])
+def test_channel_kernel_is_bit_identical_to_the_shared_sweep(monkeypatch, cluster_size, case):
     """Under a cluster plan the channel wave runs as k_channel_wave (1024 threads per block); the river task of the shared
     sweep (WF_HBV_SHARED_SWEEP=1) must give the same bits: same device function, same schedule of dependencies.  Both
     against the reference's golden as well.  Hourly steps with four sub-steps, missing cells inside the basins."""
-    g = np.load(os.path.join(GOLD, "hbv_tiles_hourly_sub.npz"))
+    g = np.load(os.path.join(GOLD, "hbv_%s.npz" % case))  # (the Courant case: sub-steps re-sized every step, 80 ... 304 of them)
     kw = ast.literal_eval(str(g["meta"]))
     monkeypatch.setenv("WF_LATERAL_MODE", "cluster")
     monkeypatch.setenv("WF_CLUSTER_SIZE", cluster_size)
     got = {}
     for shared in ("0", "1"):
         monkeypatch.setenv("WF_HBV_SHARED_SWEEP", shared)
-        _, _, mod = _load("tiles_hourly_sub")
+        _, _, mod = _load(case)
         try:
             assert mod.lateral_plan["mode"] in ("cluster", "cluster-wide"), mod.lateral_plan
             for t in range(kw["steps"]):
