@@ -69,7 +69,6 @@ def main():
     (col_ms, sweep_ms, _), nst = mod.timing_get()
     col_ms, sweep_ms = col_ms / max(nst, 1), sweep_ms / max(nst, 1)
     # ---- end to end: pinned host rasters -> device -> step -> outlet discharge back, every step ----
-    up = np.zeros(ldd.shape, np.int64)
     pits = np.flatnonzero(ldd.ravel() == 5)
     g = mod.gauges_create(pits)
     out = torch.zeros(len(pits), dtype=torch.float32).pin_memory()
@@ -88,7 +87,6 @@ def main():
     e1.record(stream)
     mod.synchronize()
     e2e_ms = e0.elapsed_time(e1) / args.steps
-    del up
     peak, peak_src = bench.peaks()
     it = mod.it_kin
     line = {
