@@ -111,3 +111,42 @@ def test_an_output_requested_alone(field):
         assert e <= 1.0, (field, e)
     finally:
         mod.close()
+
+
+def test_two_sweeps_around_the_paddy_demand_equal_one_sweep():
+    """With paddy areas the step sweeps twice over the same schedule (subsurface task | the areas' demand | overland and river
+    tasks).  Areas that neither pond nor ask (h_p = h_min = 0) must therefore leave every state bit-identical to the model
+    without them, over several free-running hourly steps with river sub-steps -- the tasks read their own cell's hand-offs
+    and the level above, whichever sweep wrote them."""
+    from wflow_b200 import synth
+    n, dt = 64, 3600
+    kw = dict(kind="tiles", tile=32, layer_thickness=(100, 300, 800), dt=dt, itL=1, itR=4, river_area=20, oracle=False)
+    _, a, ldd, river = common.make_pair(n, n, **kw)
+    _, b, _, _ = common.make_pair(n, n, **kw)
+    try:
+        areas = np.zeros((n, n), np.int32)
+        areas[4:20, 6:30] = 1
+        areas[40:60, 34:50] = 2
+        areas[ldd == 0] = 0
+        intakes = np.zeros((n, n), np.int32)
+        cand = np.argwhere((river != 0) & (ldd != 5))
+        intakes[tuple(cand[len(cand) // 3])] = 1
+        intakes[tuple(cand[2 * len(cand) // 3])] = 2
+        zero = np.zeros((n, n), np.float32)
+        for f in ("h_p", "h_max", "h_min"):
+            b.set(f, zero)
+        assert b.paddy_create(areas, intakes) == 2
+        forc = synth.Forcing(n, n, seed=5, timestepsecs=dt, rain_mean=20.0)
+        states = common.state_names(a.max_layers)
+        for t in range(6):
+            P, PET, T = forc.step(t)
+            for m in (a, b):
+                m.set("P", P); m.set("PET", PET); m.set("TEMP", T)
+                m.step()
+        for k in states:
+            np.testing.assert_array_equal(b.get(k), a.get(k), err_msg=k)
+        assert float(np.nanmax(b.get("PondingDepth"))) == 0.0 and float(np.nanmax(b.get("IRSupplymm"))) == 0.0
+        assert float(a.get("RiverRunoff")[river != 0].max()) > 0.0
+    finally:
+        a.close()
+        b.close()
