@@ -106,7 +106,8 @@ int wf_schedule_partition(const wf_schedule *s, int ngroups, int64_t *storage_or
  * ECORR CEVPF Cfmax CFR WHC FieldCapacity Treshold BetaSeepage PERC Cflux KQuickFlow AlphaNL K4 K0 SUZ xl yl DCL Bw Alpha
  * (+ GlacierFrac G_TT G_Cfmax G_SIfrac); states FreeWater DrySnow SoilMoisture UpperZoneStorage LowerZoneStorage
  * InterceptionStorage SurfaceRunoff SurfaceRunoffsub WaterLevel WaterLevelsub (+ GlacierStore).  wf_set_option:
- * "SetKquickFlow", "ExternalQbase".  Not restated, refused: reservoirs / lakes, MassWasting, updating from observed
+ * "SetKquickFlow", "ExternalQbase", "MassWasting" (with the Slope raster; one more level sweep between the column and
+ * the channel wave, :1351-1364).  Not restated, refused: reservoirs / lakes, updating from observed
  * discharge, multi-step launches.  wf_step, wf_gauges_*, wf_area_*, wf_sample, wf_quick_suspend / resume work as for
  * wflow_sbm models. */
 int wf_hbv_create(const wf_config *cfg, const uint8_t *ldd, wf_model **out);

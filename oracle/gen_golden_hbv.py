@@ -28,6 +28,8 @@ CASES = {
     "forest_kquick": dict(n=20, kind="forest", steps=6, setKquickFlow=1, inflow=1),
     # seepage from an external model instead of the lower zone (ExternalQbase = 1), glacier module
     "tiles_qbase_glacier": dict(n=24, kind="tiles", tile=12, steps=6, externalQbase=1, glacier=1, cold=1),
+    # snow mass wasting (MassWasting = 1: pcr.accucapacitystate of the dry pack and its liquid water): deep packs on steep cells
+    "tiles_masswasting": dict(n=24, kind="tiles", tile=12, steps=5, massWasting=1, cold=1),
     # the Courant estimate of the sub-steps (kinwaveIters = 1, kinwaveTstep = 0)
     "tiles_courant": dict(n=24, kind="tiles", tile=12, steps=5, kinwaveIters=1, kinwaveTstep=0, boost=3.0),
 }
@@ -54,10 +56,17 @@ def gen_case(name, kw):
     # (Courant estimate, upstream()) still sees its initial discharge.  A real catchment never has its top-left corner inside
     # the mask; here the cell starts without discharge so that no case hinges on that quirk.
     state["SurfaceRunoff"][0, 0] = F32(0.0)
+    if kw.get("massWasting"):
+        mrng = np.random.default_rng(41)
+        state["DrySnow"] = np.where(mrng.random((n, n)) < 0.7, mrng.uniform(0, 6000, (n, n)), 0.0).astype(F32)
+        state["FreeWater"] = (state["DrySnow"] * mrng.uniform(0, 0.1, (n, n))).astype(F32)
+        static["Slope"] = np.where(mrng.random((n, n)) < 0.5, mrng.uniform(0.5, 4.0, (n, n)), static["Slope"]).astype(F32)
+        static["Slope"][0, 0] = F32(0.0)  # (the cell set_dd may leave out of the network keeps its snow: see above)
     fields = dict(static)
     fields.update(state)
     ref = ref_hbv.RefHbv(ldd, fields, timestepsecs=dt, kinwaveIters=kw.get("kinwaveIters", 0), kinwaveTstep=kw.get("kinwaveTstep", 0),
-                         setKquickFlow=kw.get("setKquickFlow", 0), externalQbase=kw.get("externalQbase", 0))
+                         setKquickFlow=kw.get("setKquickFlow", 0), externalQbase=kw.get("externalQbase", 0),
+                         massWasting=kw.get("massWasting", 0))
     forc = synth.Forcing(n, n, seed=5, timestepsecs=dt, rain_mean=kw.get("rain_mean", 14.0), t_mean=-2.0 if kw.get("cold") else 4.0)
     data = {"ldd": ldd}
     for k, v in static.items():

@@ -11,7 +11,7 @@ PINNED: tests/test_hbv_oracle.py compares every state and output of every timest
 own, unmodified ``dynamic()`` (tests/golden/hbv_*.npz, written by oracle/gen_golden_hbv.py) bit for bit.
 
 Not restated (the reference's optional parts that the CUDA path refuses as well): reservoirs / lakes (:1533-1594),
-snow mass wasting (:1351-1364), state updating from observed discharge (:1684-1726).
+state updating from observed discharge (:1684-1726).
 """
 import numpy as np
 
@@ -34,7 +34,8 @@ class HbvOracle:
     STATES = ["FreeWater", "SoilMoisture", "UpperZoneStorage", "LowerZoneStorage", "InterceptionStorage", "SurfaceRunoff",
               "WaterLevel", "DrySnow", "SurfaceRunoffsub", "WaterLevelsub"]
 
-    def __init__(self, ldd, fields, *, timestepsecs=86400, kinwaveIters=0, kinwaveTstep=0, setKquickFlow=0, externalQbase=0):
+    def __init__(self, ldd, fields, *, timestepsecs=86400, kinwaveIters=0, kinwaveTstep=0, setKquickFlow=0, externalQbase=0,
+                 massWasting=0):
         ldd = np.asarray(ldd)
         self.shape = ldd.shape
         self.net = _orc.Network(ldd)
@@ -44,6 +45,7 @@ class HbvOracle:
         self.dt = int(timestepsecs) if float(timestepsecs).is_integer() else float(timestepsecs)
         self.kinwaveIters, self.kinwaveTstep = int(kinwaveIters), kinwaveTstep
         self.setKquickFlow, self.externalQbase = int(setKquickFlow), int(externalQbase)
+        self.massWasting = int(massWasting)
         self.f = {k: np.array(np.broadcast_to(np.asarray(v, F32), self.shape)) for k, v in fields.items()}
         f = self.f
         zero = np.zeros(self.shape, F32)
@@ -69,6 +71,22 @@ class HbvOracle:
 
     def get(self, name):
         return self.out[name] if name in self.out else self.f[name]
+
+    def _accucapacitystate(self, material, capacity):
+        """pcr.accucapacitystate(ldd, material, capacity): what a cell holds plus what arrives from upstream leaves it up to
+        `capacity`; the state is what stays (REAL4, neighbours summed in the network's order)."""
+        flux = np.zeros(material.size, F32)
+        state = material.ravel().copy()
+        cap = capacity.ravel()
+        for kk, idx in enumerate(self.net.flat_nodes):  # level-major: upstream cells come first
+            tot = state[idx]
+            for nb in self.net.flat_up[kk]:
+                if nb >= 0:
+                    tot = F32(tot + flux[nb])
+            out = min(tot, cap[idx])
+            flux[idx] = out
+            state[idx] = F32(tot - out)
+        return state.reshape(self.shape)
 
     def estimate_iterations(self):
         """estimate_iterations_kin_wave(SurfaceRunoffsub, Beta, Alpha, timestepsecs, DCL), wflow_funcs.py:103-116."""
@@ -131,6 +149,10 @@ class HbvOracle:
             DirectRunoff = mx(SM - FC, F32(0.0))
             SM = SM - DirectRunoff
             NetInSoil = NetInSoil - DirectRunoff
+            if self.massWasting:  # :1351-1364, pcr.accucapacitystate along the network (level by level, upstream first)
+                frac = (mn(F32(0.5), f["Slope"] / F32(5.67)) * mn(F32(1.0), DrySnow / F32(10000.0))).astype(F32)
+                DrySnow = self._accucapacitystate(DrySnow.astype(F32), (frac * DrySnow).astype(F32))
+                FreeWater = self._accucapacitystate(FreeWater.astype(F32), (frac * FreeWater).astype(F32))
             if self.glacier:  # glacierHBV, wflow_funcs.py:549-603 (timestepsecs / basetimestep is a Python float)
                 ts = F32(self.dt / 86400)
                 gf = f["GlacierFrac"]

@@ -101,11 +101,11 @@ class OracleHbvModel:
     reference's own acceptance numbers (tests/test_wflow_hbv.py of the reference)."""
 
     def __init__(self, ldd, *, timestepsecs=86400, kinwaveIters=0, kinwaveTstep=0, set_kquick_flow=0, external_qbase=0,
-                 glacier=0, device=0, beta=0.0):
+                 mass_wasting=0, glacier=0, device=0, beta=0.0):
         self.shape = ldd.shape
         self._ldd = np.asarray(ldd)
         self._kw = dict(timestepsecs=timestepsecs, kinwaveIters=kinwaveIters, kinwaveTstep=kinwaveTstep,
-                        setKquickFlow=set_kquick_flow, externalQbase=external_qbase)
+                        setKquickFlow=set_kquick_flow, externalQbase=external_qbase, massWasting=mass_wasting)
         self._fields, self._o, self._areas = {}, None, []
         net = O.Network(self._ldd)
         self._mask = np.zeros(self.shape, bool)

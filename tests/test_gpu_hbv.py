@@ -28,7 +28,7 @@ def _load(name):
     kw = ast.literal_eval(str(g["meta"]))
     mod = hbv.HbvModel(g["ldd"], timestepsecs=kw.get("dt", 86400), kinwaveIters=kw.get("kinwaveIters", 0),
                        kinwaveTstep=kw.get("kinwaveTstep", 0), set_kquick_flow=kw.get("setKquickFlow", 0),
-                       external_qbase=kw.get("externalQbase", 0), glacier=kw.get("glacier", 0))
+                       external_qbase=kw.get("externalQbase", 0), glacier=kw.get("glacier", 0), mass_wasting=kw.get("massWasting", 0))
     known = set(hbv.PARAMETERS)
     mod.set_many({k.split("/", 1)[1]: g[k] for k in g.files if k.startswith("static/") and k.split("/", 1)[1] in known})
     mod.set_many({k.split("/", 1)[1]: g[k] for k in g.files if k.startswith("state0/")})
@@ -41,7 +41,7 @@ def _forcing(g, t):
 
 
 def test_goldens_present():
-    assert len(CASES) >= 5
+    assert len(CASES) >= 6
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -126,10 +126,12 @@ def test_larger_grid_against_the_cpu_restatement():
 
 def test_refused_options_fail_loudly():
     ldd, static, state = synth.hbv_case(24, 24, kind="tiles", tile=12)
-    mod = hbv.HbvModel(ldd)
+    mod = hbv.HbvModel(ldd, glacier=1)
     try:
         with pytest.raises(Exception):
-            mod.set_option("MassWasting", 1)
+            mod.set_option("MassWasting", 1)  # (not together with the glacier module)
+        with pytest.raises(Exception):
+            mod.set_option("Abstractions", 1)
         with pytest.raises(Exception):
             mod.step()  # parameters not set
     finally:

@@ -20,7 +20,7 @@ def load_case(name):
 
 
 def test_goldens_present():
-    assert len(CASES) >= 5
+    assert len(CASES) >= 6
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -28,7 +28,7 @@ def test_hbv_oracle_reproduces_the_reference(name):
     g, kw, fields = load_case(name)
     o = hbv_oracle.HbvOracle(g["ldd"], fields, timestepsecs=kw.get("dt", 86400), kinwaveIters=kw.get("kinwaveIters", 0),
                              kinwaveTstep=kw.get("kinwaveTstep", 0), setKquickFlow=kw.get("setKquickFlow", 0),
-                             externalQbase=kw.get("externalQbase", 0))
+                             externalQbase=kw.get("externalQbase", 0), massWasting=kw.get("massWasting", 0))
     act = o.active
     checked = 0
     for t in range(kw["steps"]):
@@ -44,6 +44,12 @@ def test_hbv_oracle_reproduces_the_reference(name):
                 continue  # (pcr.catchmenttotal over the LDD map: not part of the timestep's restatement)
             want = g[key]
             got = o.get(k)
-            np.testing.assert_array_equal(got[act], want[act], err_msg="%s, step %d" % (k, t))
+            if kw.get("massWasting") and k in ("DrySnow", "FreeWater", "storage", "watbal"):
+                # accucapacitystate adds what arrives from several upstream cells in an order of its own (the stand-in's
+                # topological order here, PCRaster's in the reference, the network's neighbour order in the restatement
+                # and on the device): float32 sums of the same terms, equal to an ulp of the pack per step (the run is free: a few ulp after five steps)
+                np.testing.assert_allclose(got[act], want[act], rtol=2e-6, atol=2e-3 if k == "watbal" else 0, err_msg="%s, step %d" % (k, t))
+            else:
+                np.testing.assert_array_equal(got[act], want[act], err_msg="%s, step %d" % (k, t))
             checked += 1
     assert checked > 30 * kw["steps"]

@@ -613,6 +613,11 @@ int launch_step_hbv(wf_model *m) {
   m->dm.any_diag = 0;  // (the sweep's river task has no diagnostic build)
   k_hbv_column<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->dm, m->hbv_opt);
   m->launches++;
+  if (m->hbv_opt.mass_wasting) {  // between the snow routine and the channel wave (wflow_hbv.py:1351-1364)
+    if (!m->d_mw_flux) CUDA_OK(cudaMalloc(&m->d_mw_flux, sizeof(float) * 2 * (size_t)std::max<int64_t>(n, 1)));
+    k_hbv_mass_wasting<<<(unsigned)std::max(1, std::min(m->dm.ngroups, 1024)), 1024, 0, m->stream>>>(m->dm, m->d_mw_flux, m->d_mw_flux + n);
+    m->launches++;
+  }
   if (m->timed) cudaEventRecord(e1, m->stream);
   // the channel wave: a sweep of its own where the plan is one cluster per group (hbv.cuh, k_channel_wave: 1024 threads per
   // block instead of the shared sweep's 640), the river task of the shared sweep otherwise.  WF_HBV_SHARED_SWEEP=1 forces
@@ -650,8 +655,8 @@ int launch_step_hbv(wf_model *m) {
   m->launches++;
   if (m->timed) cudaEventRecord(e2, m->stream);
   m->ev_last[0] = e0; m->ev_last[1] = e1; m->ev_last[2] = e2;
-  if (m->dm.f[F_sumlevel] || m->dm.f[F_SurfaceRunoffMM]) {
-    k_hbv_post<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->dm);
+  if (m->dm.f[F_sumlevel] || m->dm.f[F_SurfaceRunoffMM] || (m->hbv_opt.mass_wasting && (m->dm.f[F_storage] || m->dm.f[F_watbal]))) {
+    k_hbv_post<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(m->dm, m->hbv_opt);
     m->launches++;
   }
   CUDA_OK(cudaGetLastError());
@@ -853,6 +858,8 @@ int check_ready(wf_model *m) {
     if (m->cfg.glacier)
       for (int id : kRequiredGlacier)
         if (int rc = need(id)) return rc;
+    if (m->hbv_opt.mass_wasting)
+      if (int rc = need(F_Slope)) return rc;
     return WF_OK;
   }
   for (int id : kRequired)
@@ -2498,7 +2505,11 @@ int wf_set_option(wf_model *m, const char *name, double value) {
   CUDA_OK(cudaSetDevice(m->cfg.device));
   const std::string k(name);
   if (m->hbv) {  // [model] options of wflow_hbv (wflow_hbv.py:383-470)
-    if (k == "SetKquickFlow") m->hbv_opt.set_kquick = value != 0.0;
+    if (k == "MassWasting") {
+      if (value != 0.0 && m->cfg.glacier)
+        return fail(WF_EUNSUPPORTED, "MassWasting together with the glacier module is not supported (the glacier reads the wasted pack)");
+      m->hbv_opt.mass_wasting = value != 0.0;
+    } else if (k == "SetKquickFlow") m->hbv_opt.set_kquick = value != 0.0;
     else if (k == "ExternalQbase") m->hbv_opt.external_qbase = value != 0.0;
     else if (value != 0.0) return fail(WF_EUNSUPPORTED, "option not available for wflow_hbv models: " + k);
     return WF_OK;

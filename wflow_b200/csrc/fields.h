@@ -101,7 +101,7 @@ enum FieldKind : int { K_FORCING = 0, K_STATIC = 1, K_STATE = 2, K_DIAG = 3, K_R
   X(EPF, K_STATIC | K_HBV) X(ECORR, K_STATIC | K_HBV) X(CEVPF, K_STATIC | K_HBV) X(CFR, K_STATIC | K_HBV)                  \
   X(FieldCapacity, K_STATIC | K_HBV) X(Treshold, K_STATIC | K_HBV) X(BetaSeepage, K_STATIC | K_HBV)                        \
   X(PERC, K_STATIC | K_HBV) X(Cflux, K_STATIC | K_HBV) X(KQuickFlow, K_STATIC | K_HBV) X(AlphaNL, K_STATIC | K_HBV)        \
-  X(K4, K_STATIC | K_HBV) X(K0, K_STATIC | K_HBV) X(SUZ, K_STATIC | K_HBV)                                                 \
+  X(K4, K_STATIC | K_HBV) X(K0, K_STATIC | K_HBV) X(SUZ, K_STATIC | K_HBV) X(Slope, K_STATIC | K_HBV)                                                 \
   X(FreeWater, K_STATE | K_HBV) X(DrySnow, K_STATE | K_HBV) X(SoilMoisture, K_STATE | K_HBV)                               \
   X(UpperZoneStorage, K_STATE | K_HBV) X(LowerZoneStorage, K_STATE | K_HBV) X(InterceptionStorage, K_STATE | K_HBV)        \
   X(PotEvaporation, K_DIAG | K_HBV) X(IntEvap, K_DIAG | K_HBV) X(SoilEvap, K_DIAG | K_HBV) X(HBVSeepage, K_DIAG | K_HBV)   \

@@ -11,8 +11,8 @@
 // river network is its whole network and whose sweep runs the river task only; this kernel hands it the lateral inflow
 // (h_inwater, river order) where the SBM model's overland task does.
 //
-// Not restated (wf_set_option refuses them for these models): reservoirs / lakes (:1533-1594), snow mass wasting
-// (:1351-1364), state updating from observed discharge (:1684-1726).
+// Snow mass wasting (:1351-1364) is one more level sweep between the column and the channel wave (k_hbv_mass_wasting).
+// Not restated (refused for these models): reservoirs / lakes (:1533-1594), state updating from observed discharge (:1684-1726).
 #pragma once
 #include "kernels.cuh"
 #include "lateral.cuh"
@@ -20,6 +20,7 @@
 namespace wf {
 
 struct HbvOptions {
+  int32_t mass_wasting;    // [model] MassWasting: the snow pack slides downslope between the column and the channel wave (:1351-1364)
   int32_t set_kquick;      // [model] SetKquickFlow: K0 / SUZ quick flow instead of the non-linear upper zone (:1466-1500)
   int32_t external_qbase;  // [model] ExternalQbase: seepage of an external model instead of the lower zone's base flow (:1271, :1512)
 };
@@ -185,10 +186,49 @@ __global__ void __launch_bounds__(256, WF_HBV_MINBLOCKS) k_hbv_column(const DevM
     m.f[F_watbal][i] = (((m.f[F_initstorage][i] - storage) + m.f[F_sumprecip][i]) - m.f[F_sumsoilevap][i]) - m.f[F_sumrunoff][i];
 }
 
+// Snow mass wasting (wflow_hbv.py:1351-1364): DrySnow = accucapacitystate(TopoLdd, DrySnow, SnowFluxFrac * DrySnow) and the
+// same for the liquid water in the pack, SnowFluxFrac = min(0.5, Slope / 5.67) * min(1, DrySnow / 10000) formed from the pack
+// BEFORE it slides.  One more sweep over the levels, both stores at once: one block per group, a block barrier per level,
+// float32 like the map algebra (the SBM model's k_mass_wasting, objects.cuh, on wflow_hbv's rasters).  Nothing of the column
+// reads the pack after this point except the glacier module (refused together) and the water balance (k_hbv_post).
+__global__ void k_hbv_mass_wasting(const DevModel m, float *__restrict__ flux, float *__restrict__ flux_w) {
+  for (int g = blockIdx.x; g < m.ngroups; g += gridDim.x) {
+    const GroupDesc gd = m.groups[g];
+    const uint32_t *lo = m.lev_off + gd.lev_idx;
+    const int nl = m.nlev - gd.lev0;
+    for (int l = 0; l < nl; l++) {
+      const uint32_t b = lo[l], e = lo[l + 1];
+      for (uint32_t i = b + threadIdx.x; i < e; i += blockDim.x) {
+        const float snow = m.f[F_DrySnow][i], fw = m.f[F_FreeWater][i];
+        const float frac = fminf(0.5f, m.f[F_Slope][i] / 5.67f) * fminf(1.0f, snow / 10000.0f);  // 5.67 = tan 80 degrees
+        float tot = snow, totw = fw;
+        const int nup = m.topo[i] >> 4;
+        const uint32_t us = m.up_start[i];
+        for (int j = 0; j < nup; j++) {
+          tot = tot + flux[us + j];
+          totw = totw + flux_w[us + j];
+        }
+        const float out = fminf(tot, frac * snow), outw = fminf(totw, frac * fw);
+        flux[i] = out;
+        flux_w[i] = outw;
+        m.f[F_DrySnow][i] = tot - out;
+        m.f[F_FreeWater][i] = totw - outw;
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // behind the sweep: what the water balance and the outputs read of the routed channel (:1650-1668, 1745)
-__global__ void __launch_bounds__(256) k_hbv_post(const DevModel m) {
+__global__ void __launch_bounds__(256) k_hbv_post(const DevModel m, const HbvOptions opt) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m.n) return;
+  if (opt.mass_wasting && (m.f[F_storage] || m.f[F_watbal])) {  // the pack has moved since the column formed these
+    const float storage = (((m.f[F_FreeWater][i] + m.f[F_DrySnow][i]) + m.f[F_SoilMoisture][i]) + m.f[F_UpperZoneStorage][i]) + m.f[F_LowerZoneStorage][i];
+    if (m.f[F_storage]) m.f[F_storage][i] = storage;
+    if (m.f[F_watbal])
+      m.f[F_watbal][i] = (((m.f[F_initstorage][i] - storage) + m.f[F_sumprecip][i]) - m.f[F_sumsoilevap][i]) - m.f[F_sumrunoff][i];
+  }
   const int32_t rs = __ldg(m.river_slot + i);
   if (rs < 0) return;
   if (m.f[F_sumlevel]) m.f[F_sumlevel][i] = m.f[F_sumlevel][i] + m.f[F_WaterLevelR][rs];

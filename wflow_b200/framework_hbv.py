@@ -7,7 +7,7 @@ Everything the framework does around a model -- ini handling, time loop, map sta
 model's own: ``initial()`` (wflow_hbv.py:324-1140: tables with HBV's defaults, rates scaled by timestepsecs / basetimestep,
 river width and length, the channel's Alpha), ``resume()`` (:1146-1220: cold state, initstorage, KQuickFlow from KHQ / HQ /
 AlphaNL), ``stateVariables()`` and the per-timestep call (``dynamic()``, :1222-1767 = wf_hbv_create's step).
-Not covered: reservoirs / lakes, MassWasting, updating from observed discharge, scalar (tss) input, SubCatchFlowOnly
+Not covered: reservoirs / lakes, updating from observed discharge, scalar (tss) input, SubCatchFlowOnly
 -- refused loudly.  The slope and window-average restatements are framework.py's (not pinned against
 PCRaster; supply Slope.map / wflow_riverwidth.map to bypass them).
 """
@@ -47,7 +47,7 @@ class WflowHbv(WflowSbm):
         cfg = lambda k, d: configget(self.config, "model", k, d)  # noqa: E731
         self._check_netcdf_options()
         for opt, what in (("ScalarInput", "scalar (tss) input"), ("updating", "updating from observed discharge"),
-                          ("MassWasting", "snow mass wasting"), ("SubCatchFlowOnly", "a subcatchment-only drainage network")):
+                          ("SubCatchFlowOnly", "a subcatchment-only drainage network")):
             if int(cfg(opt, "0")):
                 raise ValueError("[model] %s: %s is not part of this implementation of wflow_hbv" % (opt, what))
         nrivermethod = int(cfg("nrivermethod", "1"))
@@ -59,6 +59,7 @@ class WflowHbv(WflowSbm):
         self.kinwaveTstep = int(cfg("kinwaveTstep", "0"))
         self.SetKquickFlow = int(cfg("SetKquickFlow", "0"))
         self.ExternalQbase = int(cfg("ExternalQbase", "0"))
+        self.MassWasting = int(cfg("MassWasting", "0"))
         self.intbl = cfg("intbl", "intbl")
         sizeinmetres = int(configget(self.config, "layout", "sizeinmetres", "0"))
         self.maxLayers = 1
@@ -160,7 +161,7 @@ class WflowHbv(WflowSbm):
             st["KQuickFlow"] = p["KQuickFlow"]
         else:  # resume(), :1217-1220
             st["KQuickFlow"] = (_pow(p["KHQ"], F32(1.0) + p["AlphaNL"]) * _pow(p["HQ"], -p["AlphaNL"])).astype(F32)
-        st.update(xl=xl, yl=yl, DCL=dcl, Bw=bw, Alpha=alpha)
+        st.update(xl=xl, yl=yl, DCL=dcl, Bw=bw, Alpha=alpha, Slope=slope)
         self.static = st
         self._slope, self._N, self._riverwidth = slope, N, rw
         self.River = river_b
@@ -172,7 +173,8 @@ class WflowHbv(WflowSbm):
         self._it_fixed = (1, it)
         self._requested = set()
         self._mod = hbv.HbvModel(ldd, timestepsecs=self.timestepsecs, kinwaveIters=self.kinwaveIters, kinwaveTstep=self.kinwaveTstep,
-                                 set_kquick_flow=self.SetKquickFlow, external_qbase=self.ExternalQbase, device=self.device)
+                                 set_kquick_flow=self.SetKquickFlow, external_qbase=self.ExternalQbase, mass_wasting=self.MassWasting,
+                                 device=self.device)
         for k, v in st.items():
             self._mod.set(k, np.nan_to_num(v, nan=0.0).astype(F32))
         self._update_parameters(0, initial=True)

@@ -21,7 +21,7 @@ STATES = ["FreeWater", "SoilMoisture", "UpperZoneStorage", "LowerZoneStorage", "
 #: parameter maps of the timestep (readtblDefault / wf_readmap in initial(), wflow_hbv.py:560-900)
 PARAMETERS = ["Pcorr", "TempCor", "TTI", "TT", "SFCF", "RFCF", "ICF", "EPF", "ECORR", "CEVPF", "Cfmax", "CFR", "WHC",
               "FieldCapacity", "Treshold", "BetaSeepage", "PERC", "Cflux", "KQuickFlow", "AlphaNL", "K4", "K0", "SUZ",
-              "xl", "yl", "DCL", "Bw", "Alpha", "GlacierFrac", "G_TT", "G_Cfmax", "G_SIfrac"]
+              "xl", "yl", "DCL", "Bw", "Alpha", "Slope", "GlacierFrac", "G_TT", "G_Cfmax", "G_SIfrac"]
 #: outputs of the column that wf_request_output materialises
 OUTPUTS = ["Precipitation", "PotEvaporation", "Temperature", "IntEvap", "SnowMelt", "SnowCover", "SoilEvap", "ActEvap",
            "HBVSeepage", "DirectRunoff", "InUpperZone", "Percolation", "CapFlux", "QuickFlow", "RealQuickFlow", "BaseFlow",
@@ -31,7 +31,7 @@ OUTPUTS = ["Precipitation", "PotEvaporation", "Temperature", "IntEvap", "SnowMel
 
 class HbvModel(SbmModel):
     def __init__(self, ldd, *, timestepsecs=86400, kinwaveIters=0, kinwaveTstep=0, set_kquick_flow=0, external_qbase=0,
-                 glacier=0, device=0, beta=0.0):
+                 mass_wasting=0, glacier=0, device=0, beta=0.0):
         self._l = _lib.lib()
         ldd = np.ascontiguousarray(ldd, dtype=np.uint8)
         if ldd.ndim != 2:
@@ -57,6 +57,8 @@ class HbvModel(SbmModel):
             self.set_option("SetKquickFlow", 1)
         if external_qbase:
             self.set_option("ExternalQbase", 1)
+        if mass_wasting:  # (needs the Slope raster)
+            self.set_option("MassWasting", 1)
         self.it_kin = it
 
     def set_many(self, fields):
