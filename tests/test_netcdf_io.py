@@ -154,3 +154,52 @@ def test_static_and_state_maps_through_netcdf_are_refused(tmp_path, monkeypatch)
     m.createRunId()
     with pytest.raises(ValueError, match="netcdfstatesinput"):
         m._runInitial()
+
+
+CASE_RHINE_HBV = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "wflow_rhine_hbv")
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(CASE_RHINE_HBV, "wflow_hbv.ini")),
+                    reason="examples/wflow_rhine_hbv is not in baseline/_ref (tests/golden/make_ref_cases.py)")
+def test_hbv_example_from_a_netcdf_forcing_file(tmp_path, monkeypatch):
+    """The shipped wflow_rhine_hbv example (lat / lon grid, warm start, Courant sub-steps) with its map stacks turned into one
+    netCDF-3 file: same discharge at every gauge and step as from the map stacks (the CPU restatement behind the host code)."""
+    import shutil
+
+    import wflow_b200.framework as fw
+    import wflow_b200.hbv as hbv_mod
+    from tests.oracle_backend import OracleHbvModel
+    from wflow_b200.framework_hbv import WflowHbv
+    monkeypatch.setattr(hbv_mod, "HbvModel", OracleHbvModel)
+
+    def run(case, extra=""):
+        ini = os.path.join(case, "wflow_hbv.ini")
+        if extra:  # the example's ini names netcdfinput = None: set it
+            text = open(ini).read()
+            assert "netcdfinput = None" in text
+            open(ini, "w").write(text.replace("netcdfinput = None", extra, 1))
+        m = WflowHbv(Dir=case, RunDir="run_default", configfile="wflow_hbv.ini")
+        m.createRunId()
+        m._runInitial()
+        m._runResume()
+        m._runDynamic(1, m.nrTimeSteps)
+        m._wf_shutdown()
+        return np.genfromtxt(os.path.join(case, "run_default", "run.csv"), delimiter=",")
+
+    a = str(tmp_path / "maps")
+    shutil.copytree(CASE_RHINE_HBV, a)
+    want = run(a)
+    b = str(tmp_path / "nc")
+    shutil.copytree(CASE_RHINE_HBV, b)
+    _, info = csf.read_map(os.path.join(b, "staticmaps", "wflow_dem.map"))
+    x = info.x_ul + (np.arange(info.ncol) + 0.5) * info.cellsize
+    y = info.ycoordinate()
+    stacks = {v: [csf.read_map(fw.generate_name_t(os.path.join(b, "inmaps", v), t + 1))[0] for t in range(5)] for v in ("P", "PET", "TEMP")}
+    _write_forcing_nc(os.path.join(b, "inmaps", "forcing.nc"), stacks, x, y, datetime.datetime(2000, 1, 1), 86400, south_first=False, fmt=2)
+    for v in ("P0000000", "PET00000", "TEMP0000"):
+        for t in range(1, 11):
+            os.remove(os.path.join(b, "inmaps", "%s.%03d" % (v, t)))
+    got = run(b, "netcdfinput = inmaps/forcing.nc")
+    assert want.shape == (5, 16)
+    np.testing.assert_array_equal(got, want)
+    assert float(want[:, 2:].max()) > 1500.0
