@@ -313,3 +313,20 @@ def test_cuda_runs_the_shipped_rhine_hbv_example_like_the_cpu_restatement(monkey
     want, its_cpu = run_rhine_hbv_example(tmp_path, "cpu")
     assert its == its_cpu
     np.testing.assert_allclose(got[:, 1:], want[:, 1:], rtol=2e-5, atol=1e-4)
+
+
+@needs_rhine_hbv
+def test_command_line_of_the_hbv_case_runner(monkeypatch, tmp_path):
+    """python -m wflow_b200.framework_hbv -C case -R run -T endtime: the reference's command line (wflow_hbv.py main(), -C / -R /
+    -T / -c), in process with the CPU restatement behind it: three days of the shipped Rhine example."""
+    import wflow_b200.hbv as hbv_mod
+    from tests.oracle_backend import OracleHbvModel
+    from wflow_b200 import framework_hbv
+    monkeypatch.setattr(hbv_mod, "HbvModel", OracleHbvModel)
+    case = str(tmp_path / "rhine_hbv_cli")
+    shutil.copytree(CASE_RHINE_HBV, case)
+    assert framework_hbv.main(["-C", case, "-R", "cli_run", "-T", "2000-01-03 00:00:00"]) == 0
+    run = np.genfromtxt(os.path.join(case, "cli_run", "run.csv"), delimiter=",")
+    assert run.shape == (3, 16) and run[:, 2:].max() > 1000.0
+    assert os.path.isfile(os.path.join(case, "cli_run", "outstate", "DrySnow.map"))
+    assert os.path.isfile(os.path.join(case, "cli_run", "runinfo", "configofrun.ini"))
