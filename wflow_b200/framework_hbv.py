@@ -163,7 +163,13 @@ class WflowHbv(WflowSbm):
             st["KQuickFlow"] = (_pow(p["KHQ"], F32(1.0) + p["AlphaNL"]) * _pow(p["HQ"], -p["AlphaNL"])).astype(F32)
         st.update(xl=xl, yl=yl, DCL=dcl, Bw=bw, Alpha=alpha, Slope=slope)
         self.static = st
-        self._slope, self._N, self._riverwidth = slope, N, rw
+        # maps of initial() that outputs, summaries and the API may name and that are not rasters of the library
+        # (wflow_hbv.py: self.Altitude, self.River, self.Slope, self.N, self.RiverWidth, self.reallength; DLC is the [API]
+        # section's name of DCL in the shipped examples)
+        inside = active & np.isin(ldd, (1, 2, 3, 4, 5, 6, 7, 8, 9))
+        self._host_maps = {k: np.where(inside, np.nan_to_num(v, nan=0.0).astype(F32), F32(MV)).astype(F32) for k, v in
+                           dict(Altitude=dem, River=river_b.astype(F32), Slope=slope, N=N, RiverWidth=rw, reallength=reallength,
+                                DLC=dcl).items()}
         self.River = river_b
         self._read_modelparameters()
         it = 1
@@ -211,7 +217,13 @@ class WflowHbv(WflowSbm):
         self._mod.set("initstorage", init)
 
     def _get(self, name):
+        if name in self._host_maps:
+            return self._host_maps[name]
         return self._mod.get(name, MV)
+
+    def _request(self, name):
+        if name not in self._host_maps:
+            super()._request(name)
 
     # ---- dynamic(), wflow_hbv.py:1222-1767 -----------------------------------------------------------------
     def _runDynamic(self, firststep, laststep):
