@@ -165,3 +165,45 @@ def test_channel_kernel_is_bit_identical_to_the_shared_sweep(monkeypatch, cluste
     for f in hbv.STATES:
         np.testing.assert_array_equal(got["0"][f], got["1"][f], err_msg=f)
         assert common.compare(got["0"][f], g["out/%d/%s" % (last, f)], mask, 1e-4, 1e-4) <= 1.0, f
+
+
+def test_ensemble_members_are_bit_identical_to_stand_alone_models():
+    """Calibration trials of a wflow_hbv case as ONE device model (ensemble.HbvEnsemble: members side by side, what they share
+    uploaded once): every member must equal the stand-alone model with its parameters, bit for bit."""
+    from wflow_b200.ensemble import HbvEnsemble
+    n, dt, M = 36, 3600, 4
+    ldd, static, state = synth.hbv_case(n, n, kind="tiles", tile=12, seed=9, timestepsecs=dt)
+    factors = {"FieldCapacity": [1.0, 0.7, 1.3, 1.1], "KQuickFlow": [1.0, 1.5, 0.6, 1.0], "Alpha": [1.0, 1.0, 1.2, 0.8]}
+    ens = HbvEnsemble(ldd, M, timestepsecs=dt, kinwaveIters=1, kinwaveTstep=900)
+    singles = []
+    try:
+        for k, v in static.items():
+            if k in hbv.PARAMETERS and k not in factors:
+                ens.set(k, v)
+        for k, f in factors.items():
+            ens.scale(k, static[k], f)
+        ens.set_states(state)
+        for m in range(M):
+            mod = hbv.HbvModel(ens.ldd, timestepsecs=dt, kinwaveIters=1, kinwaveTstep=900)
+            par = {k: v for k, v in static.items() if k in hbv.PARAMETERS}
+            for k, f in factors.items():
+                par[k] = (static[k] * np.float32(f[m])).astype(np.float32)
+            mod.set_many(par)
+            mod.set_many(state)
+            singles.append(mod)
+        forc = synth.Forcing(n, n, seed=5, timestepsecs=dt, rain_mean=14.0, t_mean=3.0)
+        for t in range(4):
+            P, PET, T = forc.step(t)
+            ens.dynamic(P, PET, T)
+            for mod in singles:
+                mod.dynamic(P, PET, T)
+        for f in hbv.STATES:
+            got = ens.get(f)
+            for m in range(M):
+                np.testing.assert_array_equal(got[m], singles[m].get(f), err_msg="%s, member %d" % (f, m))
+        q = ens.get("SurfaceRunoff")
+        assert not np.array_equal(q[0], q[1]) and float(q[q > -999].max()) > 0.0
+    finally:
+        ens.close()
+        for mod in singles:
+            mod.close()

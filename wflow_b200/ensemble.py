@@ -101,6 +101,36 @@ class SbmEnsemble:
         self.model.close()
 
 
+class HbvEnsemble(SbmEnsemble):
+    """`members` copies of a wflow_hbv grid in one HbvModel (hbv.py): wflow_fit's trials of a wflow_hbv case (`-M wflow_hbv`,
+    wflow/wflow_fit.py:105-123) as one device model.  Same raster interface as SbmEnsemble; `dynamic` is one timestep for all
+    members with the forcing they share."""
+
+    def __init__(self, ldd, members, **model_kw):
+        from . import hbv
+        self.members = int(members)
+        if self.members < 1:
+            raise ValueError("an ensemble needs at least one member")
+        self.grid_shape = tuple(np.asarray(ldd).shape)
+        self.ldd = _member_ldd(ldd)
+        self.model = hbv.HbvModel(np.tile(self.ldd, (1, self.members)), **model_kw)
+
+    def set_states(self, state):
+        """States shared by all members; the sub-step twins of SurfaceRunoff / WaterLevel start from them (resume(), :1202)."""
+        for k, v in state.items():
+            self.set(k, v)
+        if "SurfaceRunoff" in state and "SurfaceRunoffsub" not in state:
+            self.set("SurfaceRunoffsub", state["SurfaceRunoff"])
+        if "WaterLevel" in state and "WaterLevelsub" not in state:
+            self.set("WaterLevelsub", state["WaterLevel"])
+
+    def dynamic(self, P, PET, TEMP=None, Inflow=None, Seepage=None):
+        for name, a in (("P", P), ("PET", PET), ("TEMP", TEMP), ("Inflow", Inflow), ("Seepage", Seepage)):
+            if a is not None:
+                self.set(name, a)
+        self.model.advance()
+
+
 class CaseEnsemble:
     """M parameter trials of a wflow_sbm CASE (ini, staticmaps, intbl, forcing stacks) advanced together on one GPU.
 

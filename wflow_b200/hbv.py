@@ -80,6 +80,11 @@ class HbvModel(SbmModel):
             self.set("Inflow", Inflow)
         if Seepage is not None:
             self.set("Seepage", Seepage)
+        self.advance()
+
+    def advance(self):
+        """The timestep itself, forcing already in place: sub-steps of the kinematic wave the way the reference derives them,
+        then the device step."""
         if self.kinwaveIters == 1 and not self.kinwaveTstep:  # Courant estimate from the state before the step (:1617-1624)
             it = min(self.estimate_iterations("river"), 1024)
             if it != self.it_kin:
