@@ -141,7 +141,48 @@ def test_framework_run_from_a_netcdf_forcing_file(tmp_path, monkeypatch):
         np.testing.assert_array_equal(np.nan_to_num(got_t, nan=-999.0), np.nan_to_num(ref, nan=-999.0))
 
 
-def test_static_and_state_maps_through_netcdf_are_refused(tmp_path, monkeypatch):
+def test_states_through_netcdf_round_trip(tmp_path, monkeypatch):
+    """[framework] netcdfstatesoutput writes the end states as one netCDF-3 file; a second run that resumes from it through
+    netcdfstatesinput (reinit = 0, no instate/ maps) starts from exactly the states a run resumed from the map files has."""
+    import shutil
+
+    import wflow_b200.framework as fw
+    from tests.oracle_backend import OracleSbmModel
+    from wflow_b200 import synth
+    monkeypatch.setattr(fw, "SbmModel", OracleSbmModel)
+    case = str(tmp_path / "case")
+    synth.write_case_dir(case, nsteps=3)
+    _run(case, "run_a", "\n[framework]\nnetcdfstatesoutput = states.nc\n")
+    assert os.path.isfile(os.path.join(case, "run_a", "states.nc")) and not os.path.isfile(os.path.join(case, "run_a", "outstate", "SatWaterDepth.map"))
+    # the same run with map states, for the comparison
+    case_b = str(tmp_path / "case_b")
+    synth.write_case_dir(case_b, nsteps=3)
+    _run(case_b, "run_b")
+    shutil.copytree(os.path.join(case_b, "run_b", "outstate"), os.path.join(case_b, "instate"), dirs_exist_ok=True)
+    shutil.copyfile(os.path.join(case, "run_a", "states.nc"), os.path.join(case, "instates.nc"))
+
+    def resumed(c, extra):
+        text = open(os.path.join(c, "wflow_sbm.ini")).read().replace("reinit = 1", "reinit = 0")
+        if "[framework]" in text:
+            text = text[: text.index("[framework]")]
+        open(os.path.join(c, "wflow_sbm.ini"), "w").write(text + extra)
+        m = fw.WflowSbm(Dir=c, RunDir="run_r")
+        m.createRunId()
+        m._runInitial()
+        m._runResume()
+        out = {k: m._get(k) for k in m._state_names()}
+        m._wf_shutdown()
+        return out
+
+    from_nc = resumed(case, "\n[framework]\nnetcdfstatesinput = instates.nc\n")
+    from_maps = resumed(case_b, "")
+    assert set(from_nc) == set(from_maps) and len(from_nc) >= 14
+    for k in from_maps:
+        np.testing.assert_array_equal(from_nc[k], from_maps[k], err_msg=k)
+    assert float(np.abs(from_maps["SatWaterDepth"][from_maps["SatWaterDepth"] > -999]).max()) > 0
+
+
+def test_static_maps_through_netcdf_are_refused(tmp_path, monkeypatch):
     import wflow_b200.framework as fw
     from tests.oracle_backend import OracleSbmModel
     from wflow_b200 import synth
@@ -149,10 +190,10 @@ def test_static_and_state_maps_through_netcdf_are_refused(tmp_path, monkeypatch)
     case = str(tmp_path / "case")
     synth.write_case_dir(case, nsteps=2)
     with open(os.path.join(case, "wflow_sbm.ini"), "a") as fh:
-        fh.write("\n[framework]\nnetcdfstatesinput = instates.nc\n")
+        fh.write("\n[framework]\nnetcdfstaticinput = staticmaps.nc\n")
     m = fw.WflowSbm(Dir=case, RunDir="r")
     m.createRunId()
-    with pytest.raises(ValueError, match="netcdfstatesinput"):
+    with pytest.raises(ValueError, match="netcdfstaticinput"):
         m._runInitial()
 
 

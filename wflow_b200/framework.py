@@ -11,8 +11,8 @@ outmaps, outsum), [run] [model] [layout] [inputmapstacks] [modelparameters] [var
 [variable_change_timestep] [outputmaps] [outputcsv_N] [outputtss_N] [summary] [summary_sum|avg|min|max] [API],
 cold start (reinit = 1) and warm start, wf_suspend / wf_resume, wf_setValues*, wf_supplyMapAsNumpy,
 wf_supplyVariableNamesAndRoles, wf_QuickSuspend/Resume, LAI-driven canopy parameters, the command line.
-netCDF: forcing input and [outputmaps] output on the classic netCDF-3 formats (ncio.py); netCDF-4 files and static /
-state maps through netCDF are refused loudly (the netCDF4 / HDF5 libraries are not in the image).
+netCDF: forcing input, [outputmaps] output and states in / out on the classic netCDF-3 formats (ncio.py); netCDF-4 files
+and static maps through netCDF are refused loudly (the netCDF4 / HDF5 libraries are not in the image).
 Not covered (out of scope): state updating, [rollingmean].
 
 The derivations of `initial()` that need PCRaster neighbourhood operators (slope from the DEM, window
@@ -198,20 +198,23 @@ class WflowSbm:
 
     # ---- netCDF (wf_DynamicFramework.py:1405-1580; wflow_b200/ncio.py) ---------------------------------------
     def _check_netcdf_options(self):
-        """[framework] netcdfinput / netcdfoutput are served on the classic netCDF-3 formats (ncio.py); static and state
-        maps through netCDF are not part of this implementation."""
-        for opt in ("netcdfstaticinput", "netcdfstatesinput", "netcdfstaticoutput", "netcdfstatesoutput"):
+        """[framework] netcdfinput / netcdfoutput / netcdfstatesinput / netcdfstatesoutput are served on the classic netCDF-3
+        formats (ncio.py); static maps through netCDF are not part of this implementation."""
+        for opt in ("netcdfstaticinput", "netcdfstaticoutput"):
             if configget(self.config, "framework", opt, "None") != "None":
-                raise ValueError("[framework] %s: static / state maps through netCDF are not part of this implementation "
-                                 "(forcing input and [outputmaps] output are: netcdfinput, netcdfoutput)" % opt)
+                raise ValueError("[framework] %s: static maps through netCDF are not part of this implementation "
+                                 "(forcing input, [outputmaps] output and states are: netcdfinput, netcdfoutput, "
+                                 "netcdfstatesinput, netcdfstatesoutput)" % opt)
         self._ncin = self._ncout = None
+
+    def _grid_xy(self):
+        info = self._info
+        return info.x_ul + (np.arange(info.ncol) + 0.5) * info.cellsize, info.ycoordinate()
 
     def _setup_netcdf(self):
         """Called at the end of initial(), when the grid is known."""
         from . import ncio
-        info = self._info
-        x = info.x_ul + (np.arange(info.ncol) + 0.5) * info.cellsize
-        y = info.ycoordinate()
+        x, y = self._grid_xy()
         ncfile = configget(self.config, "framework", "netcdfinput", "None")
         if ncfile != "None":
             names = [os.path.basename(v) for _, v in self.config.items("inputmapstacks")] if self.config.has_section("inputmapstacks") else []
@@ -470,9 +473,22 @@ class WflowSbm:
         self._mod.request(name)
 
     def wf_resume(self, directory):
-        """Read the state maps (wf_DynamicFramework.py:2065-2129): list-valued states as Name_<k>.map."""
+        """Read the state maps (wf_DynamicFramework.py:2065-2129): list-valued states as Name_<k>.map.  With [framework]
+        netcdfstatesinput the first time slice of the variables of that file, the map files for what it does not hold
+        (wf_readmap in resume, :3419-3436; netcdfinputstates, wf_netcdfio.py:793-957)."""
         state = {}
+        ncst = None
+        ncfile = configget(self.config, "framework", "netcdfstatesinput", "None")
+        if ncfile != "None":
+            from . import ncio
+            x, y = self._grid_xy()
+            ncst = ncio.NetcdfInput(os.path.join(self.Dir, ncfile), self.logger, self._state_names(), x, y)
         for name in self._state_names():
+            if ncst is not None:
+                a, ok = ncst.gettimestep(1, var=name)
+                if ok:
+                    state[name] = np.nan_to_num(a, nan=0.0).astype(F32)
+                    continue
             path = os.path.join(directory, name + ".map")
             if not os.path.isfile(path):
                 # wf_readmap(path, 0.0) hands back the default map for a missing file (:2109)
@@ -508,7 +524,19 @@ class WflowSbm:
             csf.write_map(st["path"], np.where(np.isnan(d), F32(MV), d).astype(F32), self._info, mv=MV)
 
     def _runSuspend(self):
-        self.wf_suspend(os.path.join(self.SaveDir, "outstate"))
+        ncfile = configget(self.config, "framework", "netcdfstatesoutput", "None")
+        if ncfile != "None":  # reportState with a netCDF state file (wf_DynamicFramework.py:3099-3119): one time slice, the run's end
+            from . import ncio
+            x, y = self._grid_xy()
+            out = ncio.NetcdfOutput(os.path.join(self.SaveDir, ncfile), self.logger, self.datetime_end, 1, self.timestepsecs, x, y,
+                                    maxbuf=1, metadata={"caseName": self.caseName, "runId": self.runId},
+                                    fmt=configget(self.config, "framework", "netcdf_format", "NETCDF4"))
+            for name in self._state_names():
+                a = self._get(name)
+                out.savetimestep(1, np.where(a == F32(MV), F32(np.nan), a), var=name, name=name)
+            out.finish()
+        else:
+            self.wf_suspend(os.path.join(self.SaveDir, "outstate"))
         self.wf_savesummarymaps()
         if int(configget(self.config, "model", "OverWriteInit", "0")):
             self.wf_suspend(os.path.join(self.Dir, "instate"))
