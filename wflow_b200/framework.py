@@ -202,6 +202,8 @@ class WflowSbm:
         formats (ncio.py); static maps through netCDF are not part of this implementation."""
         for opt in ("netcdfstaticinput", "netcdfstaticoutput"):
             if configget(self.config, "framework", opt, "None") != "None":
+                # (the reference's own reader of static maps cannot serve a map: netcdfinputstatic.gettimestep reads
+                #  self.alldat, which that class never sets, wf_netcdfio.py:960-1013)
                 raise ValueError("[framework] %s: static maps through netCDF are not part of this implementation "
                                  "(forcing input, [outputmaps] output and states are: netcdfinput, netcdfoutput, "
                                  "netcdfstatesinput, netcdfstatesoutput)" % opt)
