@@ -152,7 +152,17 @@ def test_states_through_netcdf_round_trip(tmp_path, monkeypatch):
     monkeypatch.setattr(fw, "SbmModel", OracleSbmModel)
     case = str(tmp_path / "case")
     synth.write_case_dir(case, nsteps=3)
-    _run(case, "run_a", "\n[framework]\nnetcdfstatesoutput = states.nc\n")
+    with open(os.path.join(case, "wflow_sbm.ini"), "a") as fh:  # summary maps into a netCDF file as well
+        fh.write("\n[summary]\nself.RiverRunoff = endrun.map\n[summary_max]\nself.RiverRunoff = maxrun.map\n")
+    end = _run(case, "run_a", "\n[framework]\nnetcdfstatesoutput = states.nc\nnetcdfstaticoutput = summary.nc\n")
+    _, info = csf.read_map(os.path.join(case, "staticmaps", "wflow_dem.map"))
+    sx, sy = info.x_ul + (np.arange(info.ncol) + 0.5) * info.cellsize, info.ycoordinate()
+    summ = ncio.NetcdfInput(os.path.join(case, "run_a", "summary.nc"), LOG, ["endrun", "maxrun"], sx, sy)
+    er, ok1 = summ.gettimestep(1, var="endrun")
+    mr, ok2 = summ.gettimestep(1, var="maxrun")
+    assert ok1 and ok2 and not os.path.isfile(os.path.join(case, "run_a", "outsum", "endrun.map"))
+    np.testing.assert_array_equal(np.nan_to_num(er, nan=-999.0), end["RiverRunoff"])
+    assert (np.nan_to_num(mr, nan=0.0) >= np.nan_to_num(er, nan=0.0)).all()
     assert os.path.isfile(os.path.join(case, "run_a", "states.nc")) and not os.path.isfile(os.path.join(case, "run_a", "outstate", "SatWaterDepth.map"))
     # the same run with map states, for the comparison
     case_b = str(tmp_path / "case_b")

@@ -200,13 +200,13 @@ class WflowSbm:
     def _check_netcdf_options(self):
         """[framework] netcdfinput / netcdfoutput / netcdfstatesinput / netcdfstatesoutput are served on the classic netCDF-3
         formats (ncio.py); static maps through netCDF are not part of this implementation."""
-        for opt in ("netcdfstaticinput", "netcdfstaticoutput"):
+        for opt in ("netcdfstaticinput",):
             if configget(self.config, "framework", opt, "None") != "None":
                 # (the reference's own reader of static maps cannot serve a map: netcdfinputstatic.gettimestep reads
                 #  self.alldat, which that class never sets, wf_netcdfio.py:960-1013)
-                raise ValueError("[framework] %s: static maps through netCDF are not part of this implementation "
-                                 "(forcing input, [outputmaps] output and states are: netcdfinput, netcdfoutput, "
-                                 "netcdfstatesinput, netcdfstatesoutput)" % opt)
+                raise ValueError("[framework] %s: static maps read from netCDF are not part of this implementation "
+                                 "(forcing input, [outputmaps] / summary output and states are: netcdfinput, netcdfoutput, "
+                                 "netcdfstaticoutput, netcdfstatesinput, netcdfstatesoutput)" % opt)
         self._ncin = self._ncout = None
 
     def _grid_xy(self):
@@ -510,6 +510,21 @@ class WflowSbm:
     def wf_savesummarymaps(self):
         """[summary]: end values; [summary_*]: the statistics gathered over the run (wf_DynamicFramework.py:1886-1951)."""
         os.makedirs(os.path.join(self.SaveDir, "outsum"), exist_ok=True)
+        ncfile = configget(self.config, "framework", "netcdfstaticoutput", "None")
+        nc = None
+        if ncfile != "None":  # _reportStatic with a netCDF file (wf_DynamicFramework.py:3069-3090): one time slice, the run's end
+            from . import ncio
+            x, y = self._grid_xy()
+            nc = ncio.NetcdfOutput(os.path.join(self.SaveDir, ncfile), self.logger, self.datetime_end, 1, self.timestepsecs, x, y,
+                                   maxbuf=1, metadata={"caseName": self.caseName, "runId": self.runId},
+                                   fmt=configget(self.config, "framework", "netcdf_format", "NETCDF4"))
+
+        def save(path, a, longname):
+            if nc is not None:
+                nc.savetimestep(1, np.where(a == F32(MV), F32(np.nan), a), var=os.path.splitext(os.path.basename(path))[0], name=longname)
+            else:
+                csf.write_map(path, a, self._info, mv=MV)
+
         if self.config.has_section("summary"):
             for var, fname in self.config.items("summary"):
                 name = var.replace("self.", "")
@@ -518,12 +533,14 @@ class WflowSbm:
                 except Exception:
                     self.logger.warning("Could not find or save the configured summary map:" + var)
                     continue
-                csf.write_map(os.path.join(self.SaveDir, "outsum", fname), a, self._info, mv=MV)
+                save(os.path.join(self.SaveDir, "outsum", fname), a, var)
         for st in getattr(self, "_stats", []):
             if st["count"] == 0:
                 continue
             d = st["data"] / F32(st["count"]) if st["mode"] == "avg" else st["data"]
-            csf.write_map(st["path"], np.where(np.isnan(d), F32(MV), d).astype(F32), self._info, mv=MV)
+            save(st["path"], np.where(np.isnan(d), F32(MV), d).astype(F32), "self." + st["name"])
+        if nc is not None:
+            nc.finish()
 
     def _runSuspend(self):
         ncfile = configget(self.config, "framework", "netcdfstatesoutput", "None")
